@@ -1,0 +1,207 @@
+/*
+ * restir_b200.h -- C ABI of the B200-native ReSTIR direct-illumination pipeline.
+ *
+ * Drop-in boundary for the frame hot path of HummaWhite/ReSTIR.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference's src/).  The reference has no
+ * plugin registry: the path sits behind C++ free functions / methods over global state
+ * (State::scene, State::looper, Settings::reservoirReuse, file-static reservoir pointers); here that
+ * state is explicit in opaque handles and every call returns 0 on success or a negative code, with
+ * the message available from rstr_last_error().  Nothing in this library exit()s (the reference's
+ * checkCUDAError does, cudaUtil.h:13-31) and nothing falls back to the CPU: without a usable CUDA
+ * device every compute call fails with RSTR_ERR_CUDA.
+ *
+ * Host-facing layouts kept from the reference (all little-endian, fp32 / int32):
+ *   Camera 196 B (sceneStructs.h:22-126), Material 44 B (material.h:258-267),
+ *   reservoir 36 B AoS {Li, wi, dist, numSamples, weight} (restir.h:7-11,114-116),
+ *   G-buffer arrays albedo vec3 / normal vec3 / "primId" = material id / depth / motion (gbuffer.h:15-58),
+ *   boundingBoxes 24 B and MTBVHNode 12 B x 6 orderings (bvh.h:15-171), alias entries 8 B (sampler.h:63-67).
+ * Device-internal layouts are different; rstr_*_read converts.
+ */
+#ifndef RESTIR_B200_H
+#define RESTIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSTR_OK 0
+#define RSTR_ERR_ARG (-1)    /* bad argument / unsupported feature */
+#define RSTR_ERR_CUDA (-2)   /* CUDA runtime error (message in rstr_last_error) */
+#define RSTR_ERR_IO (-3)     /* scene file / OBJ could not be read or parsed */
+#define RSTR_ERR_LIMIT (-4)  /* BVH deeper than the traversal stack, etc. */
+
+/* Camera POD -- sceneStructs.h:22-126 (offsets: SURVEY.md App. E) */
+typedef struct RstrCamera {
+    int   resolution[2];      /*   0 */
+    float position[3];        /*   8 */
+    float rotation[3];        /*  20  yaw, pitch, roll (degrees) */
+    float view[3];            /*  32 */
+    float up[3];              /*  44 */
+    float right[3];           /*  56 */
+    float fov[2];             /*  68  degrees; y is the HALF vertical angle (sceneStructs.h:72) */
+    float pixelLength[2];     /*  76 */
+    float rotationMatInv[9];  /*  84  column-major */
+    float viewProjection[16]; /* 120  not used by the DI path */
+    float lensRadius;         /* 184 */
+    float focalDist;          /* 188 */
+    float tanFovY;            /* 192 */
+} RstrCamera;
+
+/* Material POD -- material.h:258-267 */
+typedef struct RstrMaterial {
+    int   type;               /* 0 Lambertian, 1 MetallicWorkflow, 2 Dielectric, 3 Disney, 4 Light (material.h:114-120) */
+    float baseColor[3];       /* for Light: emitted radiance */
+    float metallic, roughness, ior;
+    int   baseColorMapId, metallicMapId, roughnessMapId, normalMapId;  /* -1 none; textures are not supported yet */
+} RstrMaterial;
+
+/* Knobs that are literals in restir.cu; rstr_params_default() reproduces the reference. */
+typedef struct RstrParams {
+    int   numCandidates;   /* restir.cu:3    #define ReservoirSize 32 */
+    int   temporalCap;     /* restir.cu:183  preClampedMerge<20> */
+    int   numSpatial;      /* restir.cu:93   5 neighbours */
+    float spatialRadius;   /* restir.cu:49   5 px */
+    int   reuse;           /* Settings::reservoirReuse (common.h:36-43): bit0 temporal, bit1 spatial */
+} RstrParams;
+
+#define RSTR_REUSE_NONE 0
+#define RSTR_REUSE_TEMPORAL 1
+#define RSTR_REUSE_SPATIAL 2
+#define RSTR_REUSE_SPATIOTEMPORAL 3
+
+/* Flattened world-space scene, i.e. the arrays Scene::buildDevData() produces (scene.cpp:159-190). */
+typedef struct RstrSceneDesc {
+    int numTris;
+    const float* vertices;     /* 3T x 3 */
+    const float* normals;      /* 3T x 3 */
+    const float* texcoords;    /* 3T x 2, may be NULL */
+    const int*   materialIds;  /* T */
+    int numMaterials;
+    const RstrMaterial* materials;
+} RstrSceneDesc;
+
+typedef struct RstrSceneInfo {
+    int numTris, numLights, bvhSize, bvhDepth, numMaterials;
+    float sumLightPower;
+    double buildSeconds;       /* host BVH + tables */
+    size_t deviceBytes;
+} RstrSceneInfo;
+
+typedef struct RstrScene RstrScene;
+typedef struct RstrFrame RstrFrame;
+
+/* scene arrays readable through rstr_scene_read (reference host layouts) */
+enum {
+    RSTR_SCENE_BOXES = 0,          /* (2T-1) x 24 B           bvh.cpp:54   Scene::boundingBoxes */
+    RSTR_SCENE_MTBVH0 = 1,         /* +i: (2T-1) x 12 B, i=0..5  bvh.cpp:133-201 Scene::BVHNodes[i] */
+    RSTR_SCENE_LIGHT_PRIM_IDS = 7, /* L x i32                 scene.cpp:182 */
+    RSTR_SCENE_LIGHT_RADIANCE = 8, /* L x 12 B                scene.cpp:183 */
+    RSTR_SCENE_ALIAS = 9,          /* L x {f32 prob, i32 failId}  sampler.h:79-121 */
+    RSTR_SCENE_VERTICES = 10,      /* 3T x 12 B */
+    RSTR_SCENE_NORMALS = 11,
+    RSTR_SCENE_TEXCOORDS = 12,     /* 3T x 8 B */
+    RSTR_SCENE_MATERIAL_IDS = 13,  /* T x i32 */
+    RSTR_SCENE_MATERIALS = 14      /* numMaterials x 44 B */
+};
+
+/* frame buffers readable through rstr_frame_read (reference layouts, full image rows of this frame/strip) */
+enum {
+    RSTR_BUF_ALBEDO = 0,          /* P x 12 B  GBuffer::devAlbedo */
+    RSTR_BUF_NORMAL = 1,          /* P x 12 B  GBuffer::normal() */
+    RSTR_BUF_MATID = 2,           /* P x i32   GBuffer::primId()  (material id, -1 miss, -2 light; gbuffer.cu:29,42,65) */
+    RSTR_BUF_DEPTH = 3,           /* P x f32   GBuffer::depth() */
+    RSTR_BUF_MOTION = 4,          /* P x i32   GBuffer::devMotion */
+    RSTR_BUF_RADIANCE = 5,        /* P x 12 B  devDirectIllum */
+    RSTR_BUF_RESERVOIR = 6,       /* P x 36 B  history reservoirs written by the last rstr_restir_direct */
+    RSTR_BUF_RESERVOIR_TEMP = 7,  /* P x 36 B  devDirectTemp */
+    RSTR_BUF_LIGHT_INDEX = 8,     /* P x i32   light id held by each history reservoir (-1 = none) */
+    RSTR_BUF_LDR = 9              /* P x uchar4  output of rstr_tonemap */
+};
+
+const char* rstr_last_error(void);
+/* binds the calling thread to a device (the reference pins device 0, preview.cpp:112) */
+int rstr_init(int device);
+void rstr_params_default(RstrParams*);
+
+/* replaces Scene::buildDevData() + DevScene::create() (scene.cpp:159-215, 435-509): light list, alias
+ * table, BVH (bit-identical node/primitive order to BVHBuilder::build, bvh.cpp:10-201), upload. */
+int rstr_scene_create(const RstrSceneDesc*, RstrScene**);
+/* replaces Scene::Scene(filename) (scene.cpp:96-131) + buildDevData; fills the scene file's camera */
+int rstr_scene_load_file(const char* path, RstrScene**, RstrCamera* cameraOut);
+/* replaces Scene::clear() + DevScene::destroy() (scene.cpp:217-220, 511-532) */
+int rstr_scene_destroy(RstrScene*);
+int rstr_scene_info(const RstrScene*, RstrSceneInfo*);
+int rstr_scene_read(const RstrScene*, int which, void* host, size_t bytes);
+
+/* replaces Camera::update() (sceneStructs.h:88-102) */
+int rstr_camera_update(RstrCamera*);
+
+/* replaces GBuffer::create (denoiser.cu:373) + ReSTIRInit (restir.cu:478) + the devDirectIllum allocation
+ * (main.cpp:38).  The strip variant owns image rows [row0,row1) of a W x H image plus `halo` rows on each
+ * side (multi-GPU strips); pixel indices and RNG streams stay global. */
+int rstr_frame_create(RstrScene*, int width, int height, RstrFrame**);
+int rstr_frame_create_strip(RstrScene*, int width, int height, int row0, int row1, int halo, RstrFrame**);
+/* replaces GBuffer::destroy (denoiser.cu:391) + ReSTIRFree (restir.cu:506) */
+int rstr_frame_destroy(RstrFrame*);
+/* replaces ReSTIRReset (restir.cu:516) */
+int rstr_frame_reset(RstrFrame*);
+
+/* replaces GBuffer::render(devScene, cam) (gbuffer.cu:80-85) */
+int rstr_gbuffer_render(RstrFrame*, const RstrCamera*);
+/* replaces GBuffer::update(cam) (gbuffer.cu:75-78) */
+int rstr_gbuffer_update(RstrFrame*, const RstrCamera*);
+/* replaces ReSTIRDirect(devDirectIllum, iter, gBuffer) (restir.cu:418-446); looper = State::looper */
+int rstr_restir_direct(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter);
+/* replaces pathTraceDirect(devDirectIllum, iter) (pathtrace.cu:457-473) */
+int rstr_pathtrace_direct(RstrFrame*, const RstrCamera*, int looper, int iter);
+/* replaces copyImageToPBO(devPBO, devImage, w, h, toneMapping, scale) (pathtrace.cu:108-113);
+ * toneMapping: 0 none, 1 filmic, 2 ACES (common.h:18-22) */
+int rstr_tonemap(RstrFrame*, int toneMapping, float scale);
+
+/* One whole frame of runCuda (main.cpp:146-185) from HOST inputs to a HOST result:
+ * gbuffer_render + restir_direct (or pathtrace_direct when params == NULL) + tonemap + gbuffer_update,
+ * then the LDR image (P x uchar4) is copied to hostLdr (pinned or pageable).  Synchronous. */
+int rstr_render_frame_host(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter,
+                           int toneMapping, void* hostLdr, size_t bytes);
+
+int rstr_frame_sync(RstrFrame*);
+int rstr_frame_read(RstrFrame*, int which, void* host, size_t bytes);
+
+/* ---- instrumentation / plumbing ---- */
+/* device time (ms, CUDA events on the frame's stream) of the stages of the last frame */
+enum { RSTR_T_GBUFFER = 0, RSTR_T_RIS = 1, RSTR_T_SPATIAL = 2, RSTR_T_PTDIRECT = 3, RSTR_T_TONEMAP = 4, RSTR_T_COUNT = 5 };
+int rstr_frame_stage_ms(RstrFrame*, float* ms, int n);
+/* number of kernel launches issued by this library so far (all frames of this process) */
+uint64_t rstr_launch_count(void);
+/* the frame's CUDA stream (cudaStream_t) for callers that enqueue their own work */
+void* rstr_frame_stream(RstrFrame*);
+
+/* number of temporal / spatial neighbour reads that fell outside the rows resident in a strip frame (must stay 0
+ * for results identical to the single-GPU frame; widen `halo` otherwise) */
+int rstr_frame_halo_miss(RstrFrame*, unsigned int* count);
+/* page-locked host memory for rstr_render_frame_host / rstr_frame_read targets */
+void* rstr_host_alloc(size_t bytes);
+void rstr_host_free(void*);
+
+/* Halo planes of a strip frame, for the neighbour exchange.  `plane` selects one of
+ * the device-internal per-pixel arrays; the returned pointer addresses row `row` (global image row) and
+ * *rowBytes is the size of one image row of that plane. */
+enum {
+    RSTR_PLANE_GEOM_CUR = 0,   /* float4 {n.xyz, depth}, current frame */
+    RSTR_PLANE_MATID_CUR = 1,  /* int */
+    RSTR_PLANE_RESV_HISTORY = 2, /* 32 B reservoirs written by the last restir_direct */
+    RSTR_PLANE_RESV_TEMP = 3   /* 32 B post-temporal reservoirs (input of the spatial pass) */
+};
+int rstr_frame_plane_row(RstrFrame*, int plane, int row, void** devPtr, size_t* rowBytes);
+/* split form of rstr_restir_direct for strips: phase A (candidates + shadow + temporal), then the caller
+ * exchanges RESV_TEMP / GEOM_CUR / MATID_CUR halo rows, then phase B (spatial + shade). */
+int rstr_restir_phase_a(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter);
+int rstr_restir_phase_b(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

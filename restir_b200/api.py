@@ -1,0 +1,357 @@
+"""Host-side mirror of the reference's frame interface over the C ABI (include/restir_b200.h).
+
+Names follow the reference: ``Scene`` (scene.h:483), ``Camera`` (sceneStructs.h:22), ``GBuffer.render/update``
+(gbuffer.h:24-27) and ``ReSTIRDirect`` / ``pathTraceDirect`` (restir.h:132, pathtrace.h:15) are methods of
+:class:`Frame`; ``Settings`` toggles (common.h:47-60) are the fields of :class:`RstrParams`.
+
+The CUDA library is the only implementation: if librestir_b200.so is missing it is built with nvcc, and if
+that fails (or no CUDA device is usable) every compute call raises :class:`RestirError` -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class RestirError(RuntimeError):
+    pass
+
+
+class RstrCamera(C.Structure):
+    _fields_ = [
+        ("resolution", C.c_int * 2),
+        ("position", C.c_float * 3),
+        ("rotation", C.c_float * 3),
+        ("view", C.c_float * 3),
+        ("up", C.c_float * 3),
+        ("right", C.c_float * 3),
+        ("fov", C.c_float * 2),
+        ("pixelLength", C.c_float * 2),
+        ("rotationMatInv", C.c_float * 9),
+        ("viewProjection", C.c_float * 16),
+        ("lensRadius", C.c_float),
+        ("focalDist", C.c_float),
+        ("tanFovY", C.c_float),
+    ]
+
+
+assert C.sizeof(RstrCamera) == 196
+
+
+class RstrParams(C.Structure):
+    _fields_ = [
+        ("numCandidates", C.c_int),
+        ("temporalCap", C.c_int),
+        ("numSpatial", C.c_int),
+        ("spatialRadius", C.c_float),
+        ("reuse", C.c_int),
+    ]
+
+
+class RstrSceneDesc(C.Structure):
+    _fields_ = [
+        ("numTris", C.c_int),
+        ("vertices", C.c_void_p),
+        ("normals", C.c_void_p),
+        ("texcoords", C.c_void_p),
+        ("materialIds", C.c_void_p),
+        ("numMaterials", C.c_int),
+        ("materials", C.c_void_p),
+    ]
+
+
+class RstrSceneInfo(C.Structure):
+    _fields_ = [
+        ("numTris", C.c_int),
+        ("numLights", C.c_int),
+        ("bvhSize", C.c_int),
+        ("bvhDepth", C.c_int),
+        ("numMaterials", C.c_int),
+        ("sumLightPower", C.c_float),
+        ("buildSeconds", C.c_double),
+        ("deviceBytes", C.c_size_t),
+    ]
+
+
+REUSE_NONE, REUSE_TEMPORAL, REUSE_SPATIAL, REUSE_SPATIOTEMPORAL = 0, 1, 2, 3
+TONEMAP_NONE, TONEMAP_FILMIC, TONEMAP_ACES = 0, 1, 2
+
+RESERVOIR_DTYPE = np.dtype([("Li", "<f4", (3,)), ("wi", "<f4", (3,)), ("dist", "<f4"), ("M", "<i4"), ("w", "<f4")])
+ALIAS_DTYPE = np.dtype([("prob", "<f4"), ("failId", "<i4")])
+
+SCENE_ARRAYS = dict(boxes=0, mtbvh0=1, light_prim_ids=7, light_radiance=8, alias=9, vertices=10, normals=11,
+                    texcoords=12, material_ids=13, materials=14)
+FRAME_BUFFERS = dict(albedo=0, normal=1, matid=2, depth=3, motion=4, radiance=5, reservoir=6, reservoir_temp=7,
+                     light_index=8, ldr=9)
+STAGES = ("gbuffer", "ris", "spatial", "ptdirect", "tonemap")
+PLANES = dict(geom_cur=0, matid_cur=1, resv_history=2, resv_temp=3)
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (building if needed) librestir_b200.so.  Raises if the CUDA extension cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        path = _build.build()
+    except Exception as e:  # no silent fallback
+        raise RestirError("librestir_b200.so is missing and could not be built: %s" % e) from e
+    L = C.CDLL(path)
+    vp, ip, fp = C.c_void_p, C.c_int, C.c_float
+    L.rstr_last_error.restype = C.c_char_p
+    L.rstr_init.argtypes = [ip]
+    L.rstr_params_default.argtypes = [C.POINTER(RstrParams)]
+    L.rstr_scene_create.argtypes = [C.POINTER(RstrSceneDesc), C.POINTER(vp)]
+    L.rstr_scene_load_file.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(RstrCamera)]
+    L.rstr_scene_destroy.argtypes = [vp]
+    L.rstr_scene_info.argtypes = [vp, C.POINTER(RstrSceneInfo)]
+    L.rstr_scene_read.argtypes = [vp, ip, vp, C.c_size_t]
+    L.rstr_camera_update.argtypes = [C.POINTER(RstrCamera)]
+    L.rstr_frame_create.argtypes = [vp, ip, ip, C.POINTER(vp)]
+    L.rstr_frame_create_strip.argtypes = [vp, ip, ip, ip, ip, ip, C.POINTER(vp)]
+    L.rstr_frame_destroy.argtypes = [vp]
+    L.rstr_frame_reset.argtypes = [vp]
+    L.rstr_gbuffer_render.argtypes = [vp, C.POINTER(RstrCamera)]
+    L.rstr_gbuffer_update.argtypes = [vp, C.POINTER(RstrCamera)]
+    L.rstr_restir_direct.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
+    L.rstr_restir_phase_a.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
+    L.rstr_restir_phase_b.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
+    L.rstr_pathtrace_direct.argtypes = [vp, C.POINTER(RstrCamera), ip, ip]
+    L.rstr_tonemap.argtypes = [vp, ip, fp]
+    L.rstr_render_frame_host.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip, vp, C.c_size_t]
+    L.rstr_frame_sync.argtypes = [vp]
+    L.rstr_frame_read.argtypes = [vp, ip, vp, C.c_size_t]
+    L.rstr_frame_stage_ms.argtypes = [vp, C.POINTER(fp), ip]
+    L.rstr_launch_count.restype = C.c_uint64
+    L.rstr_frame_stream.restype = vp
+    L.rstr_frame_stream.argtypes = [vp]
+    L.rstr_frame_halo_miss.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.rstr_frame_plane_row.argtypes = [vp, ip, ip, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.rstr_host_alloc.restype = vp
+    L.rstr_host_alloc.argtypes = [C.c_size_t]
+    L.rstr_host_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RestirError("restir_b200 error %d: %s" % (rc, lib().rstr_last_error().decode(errors="replace")))
+
+
+def init(device: int = 0) -> None:
+    """Bind this thread to a CUDA device; raises RestirError when none is usable."""
+    _check(lib().rstr_init(device))
+
+
+def default_params(reuse: int = REUSE_TEMPORAL, radius: float = 5.0, k: int = 5, cap: int = 20, candidates: int = 32) -> RstrParams:
+    """restir.cu literals (32 candidates, cap 20, 5 neighbours, radius 5 px) unless overridden."""
+    return RstrParams(candidates, cap, k, radius, reuse)
+
+
+def launch_count() -> int:
+    return int(lib().rstr_launch_count())
+
+
+class Camera(RstrCamera):
+    """Camera POD (sceneStructs.h:22-126) + the scene-file camera block (scene.cpp:288-355)."""
+
+    @classmethod
+    def from_scene(cls, sd, resolution=None) -> "Camera":
+        cam = cls()
+        res = tuple(resolution or sd.resolution)
+        cam.resolution[0], cam.resolution[1] = int(res[0]), int(res[1])
+        for i in range(3):
+            cam.position[i] = sd.eye[i]
+            cam.rotation[i] = sd.rotation[i]
+        f32 = np.float32
+        pi = f32(3.1415926535897932384626422832795028841971)
+        fovy = f32(sd.fovy)
+        yscaled = f32(np.tan(f32(fovy * f32(pi / f32(180)))))
+        xscaled = f32(f32(yscaled * f32(res[0])) / f32(res[1]))
+        fovx = f32(f32(np.arctan(xscaled) * f32(180)) / pi)
+        cam.fov[0], cam.fov[1] = float(fovx), float(fovy)
+        cam.lensRadius = sd.lens_radius
+        cam.focalDist = sd.focal_dist
+        cam.tanFovY = float(np.tan(np.radians(f32(fovy * f32(0.5)))))
+        cam.update()
+        return cam
+
+    def copy(self) -> "Camera":
+        return Camera.from_buffer_copy(bytes(self))
+
+    def update(self) -> None:
+        """Camera::update() (sceneStructs.h:88-102)."""
+        _check(lib().rstr_camera_update(C.byref(self)))
+
+    def orbit(self, k: int, speed: float = 2.7, radius: float = 1.0, fps: float = 60.0) -> "Camera":
+        """runCuda's camera animation with the fixed clock t_k = k*speed/fps (main.cpp:149-162)."""
+        cam = self.copy()
+        t = np.float32(np.float32(k / fps) * np.float32(speed))
+        cam.position[0] = float(np.float32(self.position[0]) + np.float32(np.cos(t)) * np.float32(radius))
+        cam.position[1] = float(np.float32(self.position[1]) + np.float32(0.0) * np.float32(radius))
+        cam.position[2] = float(np.float32(self.position[2]) + np.float32(np.sin(t)) * np.float32(radius))
+        cam.update()
+        return cam
+
+
+class Scene:
+    """Scene + DevScene (scene.h:64-531): host build (light list, alias table, BVH) and device upload."""
+
+    def __init__(self, handle, camera=None):
+        self.h = handle
+        self.camera = camera
+        info = RstrSceneInfo()
+        _check(lib().rstr_scene_info(self.h, C.byref(info)))
+        self.info = info
+
+    @classmethod
+    def from_arrays(cls, sd) -> "Scene":
+        v = np.ascontiguousarray(sd.vertices, np.float32)
+        n = np.ascontiguousarray(sd.normals, np.float32)
+        t = np.ascontiguousarray(sd.texcoords, np.float32)
+        m = np.ascontiguousarray(sd.material_ids, np.int32)
+        mats = np.ascontiguousarray(sd.materials)
+        desc = RstrSceneDesc(int(m.shape[0]), v.ctypes.data, n.ctypes.data, t.ctypes.data, m.ctypes.data, len(mats), mats.ctypes.data)
+        h = C.c_void_p()
+        _check(lib().rstr_scene_create(C.byref(desc), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_file(cls, path: str) -> "Scene":
+        """Scene::Scene(filename) + buildDevData (scene.cpp:96, 159)."""
+        h = C.c_void_p()
+        cam = Camera()
+        _check(lib().rstr_scene_load_file(path.encode(), C.byref(h), C.byref(cam)))
+        return cls(h, cam)
+
+    def close(self) -> None:
+        if self.h:
+            lib().rstr_scene_destroy(self.h)
+            self.h = None
+
+    def read(self, name: str, ordering: int = 0) -> np.ndarray:
+        T, L, N = self.info.numTris, self.info.numLights, self.info.bvhSize
+        spec = {
+            "boxes": (np.float32, (N, 6)), "mtbvh": (np.int32, (N, 3)), "light_prim_ids": (np.int32, (L,)),
+            "light_radiance": (np.float32, (L, 3)), "alias": (ALIAS_DTYPE, (L,)), "vertices": (np.float32, (3 * T, 3)),
+            "normals": (np.float32, (3 * T, 3)), "texcoords": (np.float32, (3 * T, 2)), "material_ids": (np.int32, (T,)),
+            "materials": (np.dtype("V44"), (self.info.numMaterials,)),
+        }[name]
+        out = np.zeros(spec[1], spec[0])
+        which = SCENE_ARRAYS["mtbvh0"] + ordering if name == "mtbvh" else SCENE_ARRAYS[name]
+        _check(lib().rstr_scene_read(self.h, which, out.ctypes.data, out.nbytes))
+        return out
+
+    def frame(self, width: int, height: int, rows=None, halo: int = 0) -> "Frame":
+        return Frame(self, width, height, rows, halo)
+
+
+class Frame:
+    """G-buffer + reservoirs + radiance of one image (or one horizontal strip of it).
+
+    Mirrors GBuffer::create/destroy (denoiser.cu:373-403), ReSTIRInit/Free/Reset (restir.cu:478-517) and the
+    per-frame calls of runCuda (main.cpp:146-185).
+    """
+
+    def __init__(self, scene: Scene, width: int, height: int, rows=None, halo: int = 0):
+        self.scene, self.w, self.h = scene, width, height
+        self.rows = (0, height) if rows is None else (int(rows[0]), int(rows[1]))
+        self.halo = halo
+        self.f = C.c_void_p()
+        _check(lib().rstr_frame_create_strip(scene.h, width, height, self.rows[0], self.rows[1], halo, C.byref(self.f)))
+        self.npix = (self.rows[1] - self.rows[0]) * width
+
+    def close(self) -> None:
+        if self.f:
+            lib().rstr_frame_destroy(self.f)
+            self.f = None
+
+    # --- reference-named entry points -------------------------------------------------------------
+    def gbuffer_render(self, cam) -> None:       # GBuffer::render
+        _check(lib().rstr_gbuffer_render(self.f, C.byref(cam)))
+
+    def gbuffer_update(self, cam) -> None:       # GBuffer::update
+        _check(lib().rstr_gbuffer_update(self.f, C.byref(cam)))
+
+    def restir_direct(self, cam, params, looper: int, it: int = 0) -> None:   # ReSTIRDirect
+        _check(lib().rstr_restir_direct(self.f, C.byref(cam), C.byref(params), looper, it))
+
+    def restir_phase_a(self, cam, params, looper: int, it: int = 0) -> None:
+        _check(lib().rstr_restir_phase_a(self.f, C.byref(cam), C.byref(params), looper, it))
+
+    def restir_phase_b(self, cam, params, looper: int, it: int = 0) -> None:
+        _check(lib().rstr_restir_phase_b(self.f, C.byref(cam), C.byref(params), looper, it))
+
+    def pathtrace_direct(self, cam, looper: int, it: int = 0) -> None:        # pathTraceDirect
+        _check(lib().rstr_pathtrace_direct(self.f, C.byref(cam), looper, it))
+
+    def reset(self) -> None:                     # ReSTIRReset
+        _check(lib().rstr_frame_reset(self.f))
+
+    def tonemap(self, mode: int = TONEMAP_ACES, scale: float = 1.0) -> None:  # copyImageToPBO
+        _check(lib().rstr_tonemap(self.f, mode, scale))
+
+    def render_frame_host(self, cam, params, looper: int, it: int = 0, tonemap: int = TONEMAP_ACES, out=None) -> None:
+        """One runCuda() frame; ``out`` is a host uint8 buffer of npix*4 bytes receiving the LDR image."""
+        ptr, nbytes = (None, 0) if out is None else (out.ctypes.data, out.nbytes)
+        p = C.byref(params) if params is not None else None
+        _check(lib().rstr_render_frame_host(self.f, C.byref(cam), p, looper, it, tonemap, ptr, nbytes))
+
+    def sync(self) -> None:
+        _check(lib().rstr_frame_sync(self.f))
+
+    def stage_ms(self) -> dict:
+        ms = (C.c_float * len(STAGES))()
+        _check(lib().rstr_frame_stage_ms(self.f, ms, len(STAGES)))
+        return {s: float(ms[i]) for i, s in enumerate(STAGES)}
+
+    def halo_miss(self) -> int:
+        v = C.c_uint(0)
+        _check(lib().rstr_frame_halo_miss(self.f, C.byref(v)))
+        return int(v.value)
+
+    def stream(self) -> int:
+        return int(lib().rstr_frame_stream(self.f) or 0)
+
+    def plane_row(self, plane: str, row: int):
+        p, nb = C.c_void_p(), C.c_size_t()
+        _check(lib().rstr_frame_plane_row(self.f, PLANES[plane], row, C.byref(p), C.byref(nb)))
+        return int(p.value or 0), int(nb.value)
+
+    def read(self, name: str) -> np.ndarray:
+        P = self.npix
+        if name in ("albedo", "normal", "radiance"):
+            out = np.zeros((P, 3), np.float32)
+        elif name in ("matid", "motion", "light_index"):
+            out = np.zeros((P,), np.int32)
+        elif name == "depth":
+            out = np.zeros((P,), np.float32)
+        elif name == "ldr":
+            out = np.zeros((P, 4), np.uint8)
+        else:
+            out = np.zeros((P,), RESERVOIR_DTYPE)
+        _check(lib().rstr_frame_read(self.f, FRAME_BUFFERS[name], out.ctypes.data, out.nbytes))
+        return out
+
+
+def pinned_empty(nbytes: int) -> np.ndarray:
+    """Page-locked host buffer (cudaHostAlloc) as a uint8 array; freed with :func:`pinned_free`."""
+    p = lib().rstr_host_alloc(nbytes)
+    if not p:
+        raise RestirError("cudaHostAlloc failed")
+    arr = np.frombuffer((C.c_uint8 * nbytes).from_address(p), dtype=np.uint8)
+    arr.flags.writeable = True
+    return arr
+
+
+def pinned_free(arr: np.ndarray) -> None:
+    lib().rstr_host_free(arr.ctypes.data)

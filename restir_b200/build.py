@@ -1,0 +1,64 @@
+"""In-tree build of librestir_b200.so (sm_100a only) with nvcc.
+
+    python -m restir_b200.build [--force] [--verbose]
+
+The library is compiled with -fmad=false (device) and -ffp-contract=off (host) because bit-level parity with
+the reference's arithmetic order is part of the contract; -lineinfo keeps ncu's source
+page usable.  The .so lands next to this file so that it travels to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "librestir_b200.so")
+SOURCES = ["capi.cu", "kernels.cu", "scene_host.cpp", "scene_file.cpp"]
+HEADERS = ["kernels.h", "device_types.h", "scene_host.h", "vecmath.h", os.path.join("..", "..", "include", "restir_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+HOST_CXX = "/usr/bin/g++"
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def nvcc_command(verbose: bool = False) -> list[str]:
+    cmd = [
+        NVCC, "-std=c++17", "-O3", "-shared",
+        "-ccbin", HOST_CXX,
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-lineinfo", "-fmad=false",
+        "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off,-fno-fast-math,-O2",
+        "-I", os.path.join(HERE, "..", "include"),
+        "-o", LIB,
+    ]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-lgomp"]
+    return cmd
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or _stale():
+        cmd = nvcc_command(verbose)
+        if verbose:
+            print(" ".join(cmd))
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed building librestir_b200.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv)
+    print(LIB)

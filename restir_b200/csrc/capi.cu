@@ -1,0 +1,495 @@
+// capi.cu -- the C ABI (include/restir_b200.h) over the host scene builder and the sm_100a kernels.
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace rs;
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(RSTR_ERR_CUDA, buf_);                                                      \
+        }                                                                                          \
+    } while (0)
+
+struct RstrScene {
+    HostScene hs;
+    DevScene dev{};
+    void* dNodes = nullptr; void* dTriGeom = nullptr; void* dTriNorm = nullptr;
+    void* dMaterials = nullptr; void* dAlias = nullptr; void* dLights = nullptr;
+    size_t deviceBytes = 0;
+};
+
+struct RstrFrame {
+    RstrScene* sc = nullptr;
+    int W = 0, H = 0, row0 = 0, row1 = 0, halo = 0, bufRow0 = 0, bufRows = 0;
+    size_t nBuf = 0;
+    float4* geom[2] = {nullptr, nullptr};
+    int* matId[2] = {nullptr, nullptr};
+    float4* albedoMotion = nullptr;
+    float* radiance = nullptr;
+    ResvD* resv[2] = {nullptr, nullptr};
+    ResvD* resvTemp = nullptr;
+    HitRec* hit = nullptr;
+    uchar4* ldr = nullptr;
+    unsigned int* haloMiss = nullptr;
+    void* scratch = nullptr; size_t scratchBytes = 0;
+    int cur = 0;        // GBuffer::frameIdx
+    int resvOut = 0;    // which of resv[] is devDirectReservoir (written this frame)
+    RstrCamera lastCamera{};
+    bool haveLast = false;
+    bool first = true;  // ReSTIRFirstFrame
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2 * RSTR_T_COUNT] = {};
+    bool ran[RSTR_T_COUNT] = {};
+};
+
+static CamDev toCamDev(const RstrCamera& c) {
+    CamDev d;
+    memcpy(d.position, c.position, 12); memcpy(d.right, c.right, 12); memcpy(d.up, c.up, 12); memcpy(d.view, c.view, 12);
+    memcpy(d.rotInv, c.rotationMatInv, 36);
+    d.aspect = (float)c.resolution[0] / c.resolution[1];                 // sceneStructs.h:71
+    d.tanFovY = tanf(radians(c.fov[1]));                                 // sceneStructs.h:72 (evaluated once on the host)
+    d.focalDist = c.focalDist;
+    d.pixelSizeX = 1.f / (float)c.resolution[0];                         // sceneStructs.h:73
+    d.pixelSizeY = 1.f / (float)c.resolution[1];
+    d.resX = (float)c.resolution[0]; d.resY = (float)c.resolution[1];
+    return d;
+}
+
+static FrameDev toFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
+    FrameDev d{};
+    d.W = f->W; d.H = f->H; d.rowLo = rowLo; d.rowHi = rowHi; d.bufRow0 = f->bufRow0; d.bufRows = f->bufRows;
+    d.geom[0] = f->geom[f->cur]; d.geom[1] = f->geom[f->cur ^ 1];
+    d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
+    d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
+    d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
+    d.hit = f->hit; d.haloMiss = f->haloMiss;
+    return d;
+}
+
+template <typename T>
+static cudaError_t upload(void** dst, const std::vector<T>& v, size_t& total) {
+    size_t bytes = v.size() * sizeof(T);
+    if (bytes == 0) bytes = 64;
+    cudaError_t e = cudaMalloc(dst, bytes);
+    if (e != cudaSuccess) return e;
+    total += bytes;
+    if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+// host build only; the device copy is made by ensureUploaded() when the first frame is created, so that
+// scene construction / inspection (rstr_scene_read, rstr_scene_info) also work on a machine without a GPU
+static int finishScene(RstrScene* sc, RstrScene** out) {
+    std::string err;
+    if (!buildHostScene(sc->hs, err)) { delete sc; return fail(RSTR_ERR_ARG, err); }
+    if (sc->hs.bvhDepth > RS_STACK_DEPTH) {
+        char b[160];
+        snprintf(b, sizeof b, "BVH depth %d exceeds the traversal stack (%d); coincident centroids? (SURVEY App. C4)", sc->hs.bvhDepth, RS_STACK_DEPTH);
+        delete sc;
+        return fail(RSTR_ERR_LIMIT, b);
+    }
+    *out = sc;
+    return RSTR_OK;
+}
+
+static int ensureUploaded(RstrScene* sc) {
+    if (sc->dNodes) return RSTR_OK;
+    HostScene& hs = sc->hs;
+    size_t total = 0;
+    cudaError_t e;
+    if ((e = upload(&sc->dNodes, hs.packed, total)) != cudaSuccess || (e = upload(&sc->dTriGeom, hs.triGeom, total)) != cudaSuccess ||
+        (e = upload(&sc->dTriNorm, hs.triNorm, total)) != cudaSuccess || (e = upload(&sc->dMaterials, hs.materials, total)) != cudaSuccess ||
+        (e = upload(&sc->dAlias, hs.alias, total)) != cudaSuccess || (e = upload(&sc->dLights, hs.lights, total)) != cudaSuccess) {
+        std::string m = std::string("scene upload failed: ") + cudaGetErrorString(e);
+        cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
+        sc->dNodes = sc->dTriGeom = sc->dTriNorm = sc->dMaterials = sc->dAlias = sc->dLights = nullptr;
+        return fail(RSTR_ERR_CUDA, m);
+    }
+    sc->deviceBytes = total;
+    DevScene& d = sc->dev;
+    d.nodes = (const float4*)sc->dNodes; d.triGeom = (const float4*)sc->dTriGeom; d.triNorm = (const float4*)sc->dTriNorm;
+    d.materials = (const RstrMaterial*)sc->dMaterials; d.alias = (const float2*)sc->dAlias; d.lights = (const float4*)sc->dLights;
+    d.numLights = (int)hs.lights.size();
+    d.rootRef = hs.rootRef;
+    memcpy(d.rootMin, &hs.rootBox.pMin, 12); memcpy(d.rootMax, &hs.rootBox.pMax, 12);
+    return RSTR_OK;
+}
+
+extern "C" {
+
+const char* rstr_last_error(void) { return g_err.c_str(); }
+
+int rstr_init(int device) {
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(RSTR_ERR_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+    CU(cudaFree(0));
+    return RSTR_OK;
+}
+
+void rstr_params_default(RstrParams* p) {
+    p->numCandidates = 32; p->temporalCap = 20; p->numSpatial = 5; p->spatialRadius = 5.f; p->reuse = RSTR_REUSE_TEMPORAL;   // common.cpp:14
+}
+
+int rstr_scene_create(const RstrSceneDesc* desc, RstrScene** out) {
+    if (!desc || !out || desc->numTris <= 0 || !desc->vertices || !desc->normals || !desc->materialIds || !desc->materials || desc->numMaterials <= 0)
+        return fail(RSTR_ERR_ARG, "rstr_scene_create: bad descriptor");
+    RstrScene* sc = new RstrScene;
+    HostScene& hs = sc->hs;
+    const int T = desc->numTris;
+    hs.T = T;
+    hs.vertices.resize(3 * (size_t)T); hs.normals.resize(3 * (size_t)T); hs.texcoords.assign(6 * (size_t)T, 0.f);
+    memcpy(hs.vertices.data(), desc->vertices, 36 * (size_t)T);
+    memcpy(hs.normals.data(), desc->normals, 36 * (size_t)T);
+    if (desc->texcoords) memcpy(hs.texcoords.data(), desc->texcoords, 24 * (size_t)T);
+    hs.materialIds.assign(desc->materialIds, desc->materialIds + T);
+    hs.materials.assign(desc->materials, desc->materials + desc->numMaterials);
+    return finishScene(sc, out);
+}
+
+int rstr_scene_load_file(const char* path, RstrScene** out, RstrCamera* cameraOut) {
+    if (!path || !out) return fail(RSTR_ERR_ARG, "rstr_scene_load_file: bad argument");
+    RstrScene* sc = new RstrScene;
+    RstrCamera cam;
+    memset(&cam, 0, sizeof cam);
+    std::string err;
+    if (!loadSceneFile(path, sc->hs, cam, err)) { delete sc; return fail(RSTR_ERR_IO, err); }
+    if (cameraOut) *cameraOut = cam;
+    return finishScene(sc, out);
+}
+
+int rstr_scene_destroy(RstrScene* sc) {
+    if (!sc) return RSTR_OK;
+    cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
+    delete sc;
+    return RSTR_OK;
+}
+
+int rstr_scene_info(const RstrScene* sc, RstrSceneInfo* info) {
+    if (!sc || !info) return fail(RSTR_ERR_ARG, "rstr_scene_info: bad argument");
+    info->numTris = sc->hs.T; info->numLights = (int)sc->hs.lightPrimIds.size(); info->bvhSize = sc->hs.bvhSize;
+    info->bvhDepth = sc->hs.bvhDepth; info->numMaterials = (int)sc->hs.materials.size(); info->sumLightPower = sc->hs.sumAll;
+    info->buildSeconds = sc->hs.buildSeconds; info->deviceBytes = sc->deviceBytes;
+    return RSTR_OK;
+}
+
+int rstr_scene_read(const RstrScene* sc, int which, void* host, size_t bytes) {
+    if (!sc || !host) return fail(RSTR_ERR_ARG, "rstr_scene_read: bad argument");
+    const HostScene& hs = sc->hs;
+    const void* src = nullptr;
+    size_t need = 0;
+    std::vector<MTNode> mt;
+    switch (which) {
+    case RSTR_SCENE_BOXES: src = hs.boxes.data(); need = hs.boxes.size() * sizeof(Box); break;
+    case RSTR_SCENE_LIGHT_PRIM_IDS: src = hs.lightPrimIds.data(); need = hs.lightPrimIds.size() * 4; break;
+    case RSTR_SCENE_LIGHT_RADIANCE: src = hs.lightUnitRadiance.data(); need = hs.lightUnitRadiance.size() * 12; break;
+    case RSTR_SCENE_ALIAS: src = hs.alias.data(); need = hs.alias.size() * 8; break;
+    case RSTR_SCENE_VERTICES: src = hs.vertices.data(); need = hs.vertices.size() * 12; break;
+    case RSTR_SCENE_NORMALS: src = hs.normals.data(); need = hs.normals.size() * 12; break;
+    case RSTR_SCENE_TEXCOORDS: src = hs.texcoords.data(); need = hs.texcoords.size() * 4; break;
+    case RSTR_SCENE_MATERIAL_IDS: src = hs.materialIds.data(); need = hs.materialIds.size() * 4; break;
+    case RSTR_SCENE_MATERIALS: src = hs.materials.data(); need = hs.materials.size() * sizeof(RstrMaterial); break;
+    default:
+        if (which >= RSTR_SCENE_MTBVH0 && which < RSTR_SCENE_MTBVH0 + 6) {
+            exportMTBVH(hs, which - RSTR_SCENE_MTBVH0, mt);
+            src = mt.data(); need = mt.size() * sizeof(MTNode);
+        } else return fail(RSTR_ERR_ARG, "rstr_scene_read: unknown array");
+    }
+    if (bytes != need) return fail(RSTR_ERR_ARG, "rstr_scene_read: size mismatch");
+    if (need) memcpy(host, src, need);
+    return RSTR_OK;
+}
+
+int rstr_camera_update(RstrCamera* c) {
+    if (!c) return fail(RSTR_ERR_ARG, "rstr_camera_update: null");
+    cameraUpdate(*c);
+    return RSTR_OK;
+}
+
+int rstr_frame_destroy(RstrFrame* f) {
+    if (!f) return RSTR_OK;
+    if (f->stream) cudaStreamSynchronize(f->stream);
+    for (int i = 0; i < 2; i++) { cudaFree(f->geom[i]); cudaFree(f->matId[i]); cudaFree(f->resv[i]); }
+    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->hit); cudaFree(f->ldr);
+    cudaFree(f->haloMiss); cudaFree(f->scratch);
+    for (auto& e : f->ev) if (e) cudaEventDestroy(e);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+    return RSTR_OK;
+}
+
+int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int halo, RstrFrame** out) {
+    if (!sc || !out || W <= 0 || H <= 0 || row0 < 0 || row1 > H || row0 >= row1 || halo < 0)
+        return fail(RSTR_ERR_ARG, "rstr_frame_create: bad argument");
+    int urc = ensureUploaded(sc);
+    if (urc) return urc;
+    RstrFrame* f = new RstrFrame;
+    f->sc = sc; f->W = W; f->H = H; f->row0 = row0; f->row1 = row1; f->halo = halo;
+    f->bufRow0 = row0 - halo < 0 ? 0 : row0 - halo;
+    int bufRow1 = row1 + halo > H ? H : row1 + halo;
+    f->bufRows = bufRow1 - f->bufRow0;
+    f->nBuf = (size_t)f->bufRows * W;
+    const size_t n = f->nBuf;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);      // restir.cu:482-489 zero-fills the reservoirs
+    };
+    for (int i = 0; i < 2; i++) {
+        alloc((void**)&f->geom[i], n * sizeof(float4));
+        alloc((void**)&f->matId[i], n * sizeof(int));
+        alloc((void**)&f->resv[i], n * sizeof(ResvD));
+    }
+    alloc((void**)&f->albedoMotion, n * sizeof(float4));
+    alloc((void**)&f->radiance, n * 3 * sizeof(float));
+    alloc((void**)&f->resvTemp, n * sizeof(ResvD));
+    alloc((void**)&f->hit, n * sizeof(HitRec));
+    alloc((void**)&f->ldr, n * sizeof(uchar4));
+    alloc((void**)&f->haloMiss, sizeof(unsigned int));
+    if (e == cudaSuccess) {
+        // a zero-filled reference reservoir has no sample: lightId must read as "none"
+        std::vector<ResvD> init(n);
+        memset(init.data(), 0, n * sizeof(ResvD));
+        for (size_t i = 0; i < n; i++) init[i].lightId = -1;
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaMemcpy(f->resv[i], init.data(), n * sizeof(ResvD), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(f->resvTemp, init.data(), n * sizeof(ResvD), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    for (auto& ev : f->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) {
+        std::string m = std::string("rstr_frame_create: ") + cudaGetErrorString(e);
+        rstr_frame_destroy(f);
+        return fail(RSTR_ERR_CUDA, m);
+    }
+    *out = f;
+    return RSTR_OK;
+}
+
+int rstr_frame_create(RstrScene* sc, int W, int H, RstrFrame** out) { return rstr_frame_create_strip(sc, W, H, 0, H, 0, out); }
+
+int rstr_frame_reset(RstrFrame* f) {
+    if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    f->first = true;
+    return RSTR_OK;
+}
+
+static int checkCam(const RstrFrame* f, const RstrCamera* cam) {
+    if (!f || !cam) return fail(RSTR_ERR_ARG, "null frame/camera");
+    if (cam->resolution[0] != f->W || cam->resolution[1] != f->H) return fail(RSTR_ERR_ARG, "camera resolution differs from the frame");
+    return RSTR_OK;
+}
+
+static inline void stageBegin(RstrFrame* f, int s) { cudaEventRecord(f->ev[2 * s], f->stream); f->ran[s] = true; }
+static inline void stageEnd(RstrFrame* f, int s) { cudaEventRecord(f->ev[2 * s + 1], f->stream); }
+
+int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
+    int rc = checkCam(f, cam);
+    if (rc) return rc;
+    // the reference reads an uninitialised lastCamera before the first GBuffer::update (gbuffer.h:56); use cam
+    CamDev c = toCamDev(*cam), lc = toCamDev(f->haveLast ? f->lastCamera : *cam);
+    FrameDev d = toFrameDev(f, f->bufRow0, f->bufRow0 + f->bufRows);      // halo rows are rendered locally, not exchanged
+    for (bool& r : f->ran) r = false;
+    stageBegin(f, RSTR_T_GBUFFER);
+    launchGBuffer(f->sc->dev, d, c, lc, f->stream);
+    stageEnd(f, RSTR_T_GBUFFER);
+    g_launches++;
+    CU(cudaGetLastError());
+    return RSTR_OK;
+}
+
+int rstr_gbuffer_update(RstrFrame* f, const RstrCamera* cam) {
+    if (!f || !cam) return fail(RSTR_ERR_ARG, "null frame/camera");
+    f->lastCamera = *cam; f->haveLast = true; f->cur ^= 1;                // gbuffer.cu:75-78
+    return RSTR_OK;
+}
+
+int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
+    int rc = checkCam(f, cam);
+    if (rc) return rc;
+    if (!prm || prm->numCandidates < 0 || prm->numSpatial < 0 || prm->temporalCap < 1) return fail(RSTR_ERR_ARG, "bad RstrParams");
+    FrameDev d = toFrameDev(f, f->row0, f->row1);
+    stageBegin(f, RSTR_T_RIS);
+    launchRestirA(f->sc->dev, d, toCamDev(*cam), *prm, looper, iter, f->first ? 1 : 0, f->stream);
+    stageEnd(f, RSTR_T_RIS);
+    g_launches++;
+    CU(cudaGetLastError());
+    return RSTR_OK;
+}
+
+int rstr_restir_phase_b(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
+    int rc = checkCam(f, cam);
+    if (rc) return rc;
+    (void)looper;
+    if (prm->reuse & 2) {
+        FrameDev d = toFrameDev(f, f->row0, f->row1);
+        stageBegin(f, RSTR_T_SPATIAL);
+        launchRestirB(f->sc->dev, d, *prm, iter, f->stream);
+        stageEnd(f, RSTR_T_SPATIAL);
+        g_launches++;
+        CU(cudaGetLastError());
+    }
+    f->resvOut ^= 1;                                                       // std::swap, restir.cu:434
+    f->first = false;                                                      // restir.cu:436-438
+    return RSTR_OK;
+}
+
+int rstr_restir_direct(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
+    int rc = rstr_restir_phase_a(f, cam, prm, looper, iter);
+    if (rc) return rc;
+    return rstr_restir_phase_b(f, cam, prm, looper, iter);
+}
+
+int rstr_pathtrace_direct(RstrFrame* f, const RstrCamera* cam, int looper, int iter) {
+    int rc = checkCam(f, cam);
+    if (rc) return rc;
+    FrameDev d = toFrameDev(f, f->row0, f->row1);
+    stageBegin(f, RSTR_T_PTDIRECT);
+    launchPTDirect(f->sc->dev, d, toCamDev(*cam), looper, iter, f->stream);
+    stageEnd(f, RSTR_T_PTDIRECT);
+    g_launches++;
+    CU(cudaGetLastError());
+    return RSTR_OK;
+}
+
+int rstr_tonemap(RstrFrame* f, int toneMapping, float scale) {
+    if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
+    stageBegin(f, RSTR_T_TONEMAP);
+    launchTonemap(f->radiance + 3 * off, f->ldr + off, n, toneMapping, scale, f->stream);
+    stageEnd(f, RSTR_T_TONEMAP);
+    g_launches++;
+    CU(cudaGetLastError());
+    return RSTR_OK;
+}
+
+int rstr_render_frame_host(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter, int toneMapping, void* hostLdr, size_t bytes) {
+    int rc = rstr_gbuffer_render(f, cam);
+    if (rc) return rc;
+    rc = prm ? rstr_restir_direct(f, cam, prm, looper, iter) : rstr_pathtrace_direct(f, cam, looper, iter);
+    if (rc) return rc;
+    rc = rstr_tonemap(f, toneMapping, 1.f);
+    if (rc) return rc;
+    rstr_gbuffer_update(f, cam);
+    size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
+    if (hostLdr) {
+        if (bytes != n * sizeof(uchar4)) return fail(RSTR_ERR_ARG, "rstr_render_frame_host: size mismatch");
+        CU(cudaMemcpyAsync(hostLdr, f->ldr + off, bytes, cudaMemcpyDeviceToHost, f->stream));
+    }
+    CU(cudaStreamSynchronize(f->stream));
+    return RSTR_OK;
+}
+
+int rstr_frame_sync(RstrFrame* f) {
+    if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    CU(cudaStreamSynchronize(f->stream));
+    return RSTR_OK;
+}
+
+static int ensureScratch(RstrFrame* f, size_t bytes) {
+    if (f->scratchBytes >= bytes) return RSTR_OK;
+    cudaFree(f->scratch); f->scratch = nullptr; f->scratchBytes = 0;
+    CU(cudaMalloc(&f->scratch, bytes));
+    f->scratchBytes = bytes;
+    return RSTR_OK;
+}
+
+int rstr_frame_read(RstrFrame* f, int which, void* host, size_t bytes) {
+    if (!f || !host) return fail(RSTR_ERR_ARG, "rstr_frame_read: bad argument");
+    const size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
+    size_t elem = 0;
+    switch (which) {
+    case RSTR_BUF_ALBEDO: case RSTR_BUF_NORMAL: case RSTR_BUF_RADIANCE: elem = 12; break;
+    case RSTR_BUF_MATID: case RSTR_BUF_DEPTH: case RSTR_BUF_MOTION: case RSTR_BUF_LIGHT_INDEX: case RSTR_BUF_LDR: elem = 4; break;
+    case RSTR_BUF_RESERVOIR: case RSTR_BUF_RESERVOIR_TEMP: elem = 36; break;
+    default: return fail(RSTR_ERR_ARG, "rstr_frame_read: unknown buffer");
+    }
+    if (bytes != n * elem) return fail(RSTR_ERR_ARG, "rstr_frame_read: size mismatch");
+    const void* src = nullptr;
+    cudaStream_t st = f->stream;
+    if (which == RSTR_BUF_RADIANCE) src = f->radiance + 3 * off;
+    else if (which == RSTR_BUF_MATID) src = f->matId[f->cur] + off;
+    else if (which == RSTR_BUF_LDR) src = f->ldr + off;
+    else {
+        int rc = ensureScratch(f, bytes);
+        if (rc) return rc;
+        const float4* g = f->geom[f->cur] + off;
+        const float4* am = f->albedoMotion + off;
+        // after the swap the history written by the last frame is resv[resvOut ^ 1]
+        const ResvD* hist = f->resv[f->resvOut ^ 1] + off;
+        switch (which) {
+        case RSTR_BUF_ALBEDO: launchExportGeom(g, am, (float*)f->scratch, nullptr, nullptr, nullptr, n, st); break;
+        case RSTR_BUF_NORMAL: launchExportGeom(g, am, nullptr, (float*)f->scratch, nullptr, nullptr, n, st); break;
+        case RSTR_BUF_DEPTH: launchExportGeom(g, am, nullptr, nullptr, (float*)f->scratch, nullptr, n, st); break;
+        case RSTR_BUF_MOTION: launchExportGeom(g, am, nullptr, nullptr, nullptr, (int*)f->scratch, n, st); break;
+        case RSTR_BUF_RESERVOIR: launchExportResv(f->sc->dev, hist, (float*)f->scratch, nullptr, n, st); break;
+        case RSTR_BUF_RESERVOIR_TEMP: launchExportResv(f->sc->dev, f->resvTemp + off, (float*)f->scratch, nullptr, n, st); break;
+        case RSTR_BUF_LIGHT_INDEX: launchExportResv(f->sc->dev, hist, nullptr, (int*)f->scratch, n, st); break;
+        }
+        g_launches++;
+        CU(cudaGetLastError());
+        src = f->scratch;
+    }
+    CU(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return RSTR_OK;
+}
+
+int rstr_frame_stage_ms(RstrFrame* f, float* ms, int n) {
+    if (!f || !ms) return fail(RSTR_ERR_ARG, "rstr_frame_stage_ms: bad argument");
+    CU(cudaStreamSynchronize(f->stream));
+    for (int s = 0; s < n && s < RSTR_T_COUNT; s++) {
+        ms[s] = 0.f;
+        if (f->ran[s]) CU(cudaEventElapsedTime(&ms[s], f->ev[2 * s], f->ev[2 * s + 1]));
+    }
+    return RSTR_OK;
+}
+
+uint64_t rstr_launch_count(void) { return g_launches.load(); }
+void* rstr_frame_stream(RstrFrame* f) { return f ? (void*)f->stream : nullptr; }
+
+int rstr_frame_halo_miss(RstrFrame* f, unsigned int* out) {
+    if (!f || !out) return fail(RSTR_ERR_ARG, "rstr_frame_halo_miss: bad argument");
+    CU(cudaMemcpyAsync(out, f->haloMiss, sizeof(unsigned int), cudaMemcpyDeviceToHost, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+    return RSTR_OK;
+}
+
+int rstr_frame_plane_row(RstrFrame* f, int plane, int row, void** devPtr, size_t* rowBytes) {
+    if (!f || !devPtr || !rowBytes) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: bad argument");
+    if (row < f->bufRow0 || row > f->bufRow0 + f->bufRows) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: row not resident");
+    size_t off = (size_t)(row - f->bufRow0) * f->W;
+    switch (plane) {
+    case RSTR_PLANE_GEOM_CUR: *devPtr = f->geom[f->cur] + off; *rowBytes = (size_t)f->W * sizeof(float4); break;
+    case RSTR_PLANE_MATID_CUR: *devPtr = f->matId[f->cur] + off; *rowBytes = (size_t)f->W * sizeof(int); break;
+    case RSTR_PLANE_RESV_HISTORY: *devPtr = f->resv[f->resvOut ^ 1] + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
+    case RSTR_PLANE_RESV_TEMP: *devPtr = f->resvTemp + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
+    default: return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: unknown plane");
+    }
+    return RSTR_OK;
+}
+
+void* rstr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+}
+void rstr_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

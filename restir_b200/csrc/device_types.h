@@ -1,0 +1,72 @@
+// device_types.h -- device-side scene / frame descriptors shared by kernels.cu and capi.cu.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "scene_host.h"
+
+namespace rs {
+
+#define RS_STACK_DEPTH 96      /* traversal stack entries; deeper trees are rejected at scene creation */
+
+struct DevScene {
+    const float4* nodes;       // PackedNode[], 4 x float4 each
+    const float4* triGeom;     // TriGeom[], 3 x float4 each
+    const float4* triNorm;     // TriNorm[], 3 x float4 each
+    const RstrMaterial* materials;
+    const float2* alias;       // AliasEntry[] as {prob, failId bits}
+    const float4* lights;      // LightRec[], 4 x float4 each
+    int numLights;
+    int rootRef;               // packed index of the root, or ~primId when the scene is a single triangle
+    float rootMin[3], rootMax[3];
+};
+
+// Reservoir in HBM: 32 B, one aligned sector, 2 x LDG/STG.128.  Li is not stored: it is the per-light constant
+// lights[lightId].Le (the reference stores Li = lightUnitRadiance[lightId], scene.h:420), lightId < 0 <=> Li = 0.
+struct alignas(16) ResvD {
+    float wi[3];
+    float dist;
+    float weight;
+    int M;
+    int lightId;
+    int pad;
+};
+static_assert(sizeof(ResvD) == 32, "ResvD");
+
+// per-pixel state handed from phase A to phase B when spatial reuse is on (32 B)
+struct alignas(16) HitRec {
+    float n[3];
+    int matId;       // >= 0: shaded pixel; -1: phase A already wrote the radiance (miss / emitter)
+    float wo[3];
+    uint32_t rng;
+};
+static_assert(sizeof(HitRec) == 32, "HitRec");
+
+struct CamDev {
+    float position[3];
+    float right[3], up[3], view[3];
+    float rotInv[9];           // column-major
+    float aspect, tanFovY, focalDist;
+    float pixelSizeX, pixelSizeY;
+    float resX, resY;
+};
+
+struct FrameDev {
+    int W, H;                  // full image
+    int rowLo, rowHi;          // rows this launch computes
+    int bufRow0, bufRows;      // rows resident in the per-pixel planes (strip + halo)
+    // G-buffer planes (index = (y - bufRow0) * W + x)
+    float4* geom[2];           // {n.xyz, depth}; [cur], [last]
+    int* matId[2];
+    float4* albedoMotion;      // {albedo.xyz, motion (int bits)}
+    float4* radiance4;         // unused
+    float* radiance;           // 3 floats per pixel (devDirectIllum layout)
+    ResvD* resvOut;            // history written this frame
+    const ResvD* resvIn;       // history of the previous frame
+    ResvD* resvTemp;
+    HitRec* hit;
+    unsigned int* haloMiss;    // count of neighbour / reprojection reads that fell outside the resident rows
+};
+
+}  // namespace rs

@@ -1,0 +1,684 @@
+// kernels.cu -- sm_100a kernels of the ReSTIR DI frame.
+//
+//   k_gbuffer     primary pixel-centre ray -> G-buffer                      (gbuffer.cu:3-73)
+//   k_restir_a    jittered primary ray, RIS candidates, shadow ray, temporal reuse; in non-spatial modes
+//                 also the final shade                                       (restir.cu:119-192, 211-230)
+//   k_restir_b    spatial reuse as a true second pass + final shade         (restir.cu:196-230)
+//   k_ptdirect    one-sample NEE reference image                            (pathtrace.cu:279-328)
+//   k_tonemap     tone-map + gamma + 8-bit pack                             (pathtrace.cu:30-56)
+//   k_export_*    device-internal planes -> reference host layouts
+//
+// Compiled with -fmad=false: every fp32 operation that feeds a discrete decision (hit selection, reservoir
+// selection, similarity tests, pixel truncation) is a plain IEEE mul/add/div/sqrt in the reference's order,
+// so results are bit-comparable with the CPU oracle.  Traversal walks ONE packed tree in the reference's
+// per-ray child order (bvh.cpp:184-188 + scene.h:101-119) with the reference's exact box predicate
+// (bvh.h:85-157), which makes the visited-leaf sequence, tie-breaking and pruning identical to the
+// reference's 6-copy threaded MTBVH walk.
+#include "kernels.h"
+
+namespace rs {
+
+// ------------------------------------------------------------------------------------------------ rays
+struct RayT {
+    f3 o, d, inv;
+    int flags;     // 0: general path. bits0-1: axis with |d| > 1-1e-6 (1 x, 2 y, 3 z); bit2/3/4: |d.x|,|d.y|,|d.z| < 1e-6
+    int dim;       // major axis of -d (scene.h:101-119)
+    int lesser;    // ordering parity: 1 when -d[dim] <= 0
+};
+
+RS_D RayT makeRayT(f3 o, f3 d) {
+    RayT r;
+    r.o = o; r.d = d;
+    r.inv = mk3(1.f / d.x, 1.f / d.y, 1.f / d.z);
+    const float Eps = 1e-6f;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int big = ax > 1.f - Eps ? 1 : (ay > 1.f - Eps ? 2 : (az > 1.f - Eps ? 3 : 0));
+    r.flags = big | (ax < Eps ? 4 : 0) | (ay < Eps ? 8 : 0) | (az < Eps ? 16 : 0);
+    // getMTBVHId(-ray.direction)
+    f3 nd = -d;
+    int id;
+    if (ax > ay) {
+        if (ax > az) id = nd.x > 0 ? 0 : 1;
+        else id = nd.z > 0 ? 4 : 5;
+    } else {
+        if (ay > az) id = nd.y > 0 ? 2 : 3;
+        else id = nd.z > 0 ? 4 : 5;
+    }
+    r.dim = id >> 1;
+    r.lesser = id & 1;
+    return r;
+}
+
+RS_D bool distMinMax(float a1, float a2, float b1, float b2, float& tMin) {   // bvh.h:69
+    tMin = fminf(a1, a2);
+    float tMax = fmaxf(b1, b2);
+    return tMax >= 0.f && tMax >= tMin;
+}
+RS_D bool distMaxMin(float a1, float a2, float b1, float b2, float& tMin) {   // bvh.h:75
+    tMin = fmaxf(a1, a2);
+    float tMax = fminf(b1, b2);
+    return tMax >= 0.f && tMax >= tMin;
+}
+RS_D bool between(float x, float lo, float hi) { return x >= lo && x <= hi; }
+
+// bvh.h:85-157, all special cases (rare rays: axis-aligned or with a vanishing component)
+__device__ __noinline__ bool boxHitSlow(const RayT& r, f3 pMin, f3 pMax, float& tMin) {
+    f3 ori = r.o;
+    int big = r.flags & 3;
+    if (big == 1) {
+        if (between(ori.y, pMin.y, pMax.y) && between(ori.z, pMin.z, pMax.z)) {
+            float t1 = (pMin.x - ori.x) * r.inv.x, t2 = (pMax.x - ori.x) * r.inv.x;
+            return distMinMax(t1, t2, t1, t2, tMin);
+        }
+        return false;
+    } else if (big == 2) {
+        if (between(ori.z, pMin.z, pMax.z) && between(ori.x, pMin.x, pMax.x)) {
+            float t1 = (pMin.y - ori.y) * r.inv.y, t2 = (pMax.y - ori.y) * r.inv.y;
+            return distMinMax(t1, t2, t1, t2, tMin);
+        }
+        return false;
+    } else if (big == 3) {
+        if (between(ori.x, pMin.x, pMax.x) && between(ori.y, pMin.y, pMax.y)) {
+            float t1 = (pMin.z - ori.z) * r.inv.z, t2 = (pMax.z - ori.z) * r.inv.z;
+            return distMinMax(t1, t2, t1, t2, tMin);
+        }
+        return false;
+    }
+    f3 t1 = (pMin - ori) * r.inv;
+    f3 t2 = (pMax - ori) * r.inv;
+    f3 tNear = gmin(t1, t2);
+    f3 tFar = gmax(t1, t2);
+    f3 tDist = tFar - tNear;
+    float yz = tFar.z - tNear.y;
+    float zx = tFar.x - tNear.z;
+    float xy = tFar.y - tNear.x;
+    if ((r.flags & 4) && tDist.y + tDist.z > yz) return distMaxMin(tNear.y, tNear.z, tFar.y, tFar.z, tMin);
+    if ((r.flags & 8) && tDist.z + tDist.x > zx) return distMaxMin(tNear.z, tNear.x, tFar.z, tFar.x, tMin);
+    if ((r.flags & 16) && tDist.x + tDist.y > xy) return distMaxMin(tNear.x, tNear.y, tFar.x, tFar.y, tMin);
+    if (tDist.y + tDist.z > yz && tDist.z + tDist.x > zx && tDist.x + tDist.y > xy)
+        return distMaxMin(fmaxf(tNear.x, tNear.y), tNear.z, fminf(tFar.x, tFar.y), tFar.z, tMin);
+    return false;
+}
+
+// general path of bvh.h:124-156 (no special-case flag set: every 1/d is finite)
+RS_D bool boxHit(const RayT& r, f3 pMin, f3 pMax, float& tMin) {
+    if (r.flags != 0) return boxHitSlow(r, pMin, pMax, tMin);
+    f3 t1 = (pMin - r.o) * r.inv;
+    f3 t2 = (pMax - r.o) * r.inv;
+    f3 tNear = gmin(t1, t2);
+    f3 tFar = gmax(t1, t2);
+    f3 tDist = tFar - tNear;
+    float yz = tFar.z - tNear.y;
+    float zx = tFar.x - tNear.z;
+    float xy = tFar.y - tNear.x;
+    bool pre = (tDist.y + tDist.z > yz) & (tDist.z + tDist.x > zx) & (tDist.x + tDist.y > xy);
+    tMin = fmaxf(fmaxf(tNear.x, tNear.y), tNear.z);
+    float tMax = fminf(fminf(tFar.x, tFar.y), tFar.z);
+    return pre && tMax >= 0.f && tMax >= tMin;
+}
+
+// intersections.h:17-53
+RS_D bool triHit(const RayT& r, f3 v0, f3 v1, f3 v2, float& bx, float& by, float& dist) {
+    f3 e01 = v1 - v0, e02 = v2 - v0;
+    f3 p = cross(r.d, e02);
+    float det = dot(p, e01);
+    if (fabsf(det) < FLT_EPSILON) return false;
+    f3 v0ToOri = r.o - v0;
+    if (det < 0.f) { det = -det; v0ToOri = -v0ToOri; }
+    bx = dot(v0ToOri, p);
+    if (bx < 0.f || bx > det) return false;
+    f3 perp = cross(v0ToOri, e01);
+    by = dot(r.d, perp);
+    if (by < 0.f || bx + by > det) return false;
+    float detInv = 1.f / det;
+    dist = dot(e02, perp) * detInv;
+    bx *= detInv; by *= detInv;
+    return dist > 0.f;
+}
+
+struct Tri { f3 v0, v1, v2; int matId; };
+
+RS_D Tri loadTri(const DevScene& s, int prim) {
+    const float4* p = s.triGeom + 3 * (size_t)prim;
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    Tri t;
+    t.v0 = mk3(a.x, a.y, a.z); t.v1 = mk3(a.w, b.x, b.y); t.v2 = mk3(b.z, b.w, c.x);
+    t.matId = __float_as_int(c.y);
+    return t;
+}
+
+struct Hit { float t, bx, by; int prim; };
+
+struct StackEntry { int ref; float t; };
+
+// scene.h:245-278 on the packed tree.  Children are visited in the reference's order for this ray; the deferred
+// child is re-tested against the current closest distance when popped (= the reference's test on arrival).
+RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h) {
+    h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
+    float tRoot;
+    if (!(boxHit(r, mk3(s.rootMin[0], s.rootMin[1], s.rootMin[2]), mk3(s.rootMax[0], s.rootMax[1], s.rootMax[2]), tRoot) && tRoot < h.t)) return;
+    StackEntry stack[RS_STACK_DEPTH];
+    int sp = 0;
+    int cur = s.rootRef;
+    for (;;) {
+        if (cur < 0) {
+            int prim = ~cur;
+            Tri t = loadTri(s, prim);
+            float bx, by, d;
+            if (triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < h.t) { h.t = d; h.bx = bx; h.by = by; h.prim = prim; }
+        } else {
+            const float4* np = s.nodes + 4 * (size_t)cur;
+            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+            int4 l = __ldg((const int4*)(np + 3));
+            float tL = 0.f, tR = 0.f;
+            bool hL = boxHit(r, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), tL);
+            bool hR = boxHit(r, mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), tR);
+            bool swp = (((l.z >> r.dim) & 1) ^ r.lesser) != 0;
+            int first = swp ? l.y : l.x, second = swp ? l.x : l.y;
+            float tF = swp ? tR : tL, tS = swp ? tL : tR;
+            bool goF = (swp ? hR : hL) && tF < h.t;
+            bool goS = (swp ? hL : hR) && tS < h.t;
+            if (goF) {
+                if (goS) { stack[sp].ref = second; stack[sp].t = tS; sp++; }
+                cur = first;
+                continue;
+            }
+            if (goS) { cur = second; continue; }
+        }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (stack[sp].t < h.t) { cur = stack[sp].ref; found = true; break; }
+        }
+        if (!found) break;
+    }
+}
+
+// scene.h:286-316.  Any-hit: the answer does not depend on the visiting order.
+RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y) {
+    const float Eps = 1e-4f;
+    f3 dir = y - x;
+    float dist = length(dir);
+    dir = dir / dist;
+    RayT r = makeRayT(x + dir * 1e-5f, dir);                                   // makeOffsetedRay, intersections.h:12
+    dist -= Eps * 2.f;
+    float tRoot;
+    if (!(boxHit(r, mk3(s.rootMin[0], s.rootMin[1], s.rootMin[2]), mk3(s.rootMax[0], s.rootMax[1], s.rootMax[2]), tRoot) && tRoot < dist)) return false;
+    int stack[RS_STACK_DEPTH];
+    int sp = 0;
+    int cur = s.rootRef;
+    for (;;) {
+        if (cur < 0) {
+            Tri t = loadTri(s, ~cur);
+            float bx, by, d;
+            if (triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist) return true;
+        } else {
+            const float4* np = s.nodes + 4 * (size_t)cur;
+            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+            int4 l = __ldg((const int4*)(np + 3));
+            float tL = 0.f, tR = 0.f;
+            bool goL = boxHit(r, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), tL) && tL < dist;
+            bool goR = boxHit(r, mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), tR) && tR < dist;
+            if (goL) {
+                if (goR) stack[sp++] = l.y;
+                cur = l.x;
+                continue;
+            }
+            if (goR) { cur = l.y; continue; }
+        }
+        if (sp == 0) return false;
+        cur = stack[--sp];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ camera
+// Camera::sample (sceneStructs.h:69-86); gbuffer.cu:11-23 is the same expression with r = (.5, .5)
+RS_D void cameraRay(const CamDev& c, int x, int y, float rx, float ry, f3& o, f3& d) {
+    float sx = (float)x * c.pixelSizeX, sy = (float)y * c.pixelSizeY;
+    float ux = sx + c.pixelSizeX * rx, uy = sy + c.pixelSizeY * ry;
+    ux = 1.f - ux * 2.f; uy = 1.f - uy * 2.f;
+    f3 pf = mk3(ux * c.aspect * c.tanFovY, uy * 1.f * c.tanFovY, 1.f) * c.focalDist;
+    f3 dir = pf - mk3(0.f);
+    f3 right = mk3(c.right[0], c.right[1], c.right[2]), up = mk3(c.up[0], c.up[1], c.up[2]), view = mk3(c.view[0], c.view[1], c.view[2]);
+    f3 w = mk3(right.x * dir.x + up.x * dir.y + view.x * dir.z,
+               right.y * dir.x + up.y * dir.y + view.y * dir.z,
+               right.z * dir.x + up.z * dir.y + view.z * dir.z);
+    d = normalize(w);
+    o = mk3(c.position[0], c.position[1], c.position[2]) + right * 0.f + up * 0.f;
+}
+
+// Camera::getRasterCoord (sceneStructs.h:23-46); float->int is cvt.rzi (saturating, NaN -> 0) as in the reference's kernel
+RS_D void rasterCoord(const CamDev& c, f3 pos, int& ox, int& oy) {
+    f3 dir = normalize(pos - mk3(c.position[0], c.position[1], c.position[2]));
+    float dd = 1.f / dot(dir, mk3(c.view[0], c.view[1], c.view[2]));
+    f3 q = dir * dd;
+    const float* m = c.rotInv;
+    f3 p = mk3(m[0] * q.x + m[3] * q.y + m[6] * q.z, m[1] * q.x + m[4] * q.y + m[7] * q.z, m[2] * q.x + m[5] * q.y + m[8] * q.z);
+    p = p / mk3(c.aspect * c.tanFovY, 1.f * c.tanFovY, 1.f);
+    float nx = -p.x, ny = -p.y;
+    nx = nx * .5f + .5f; ny = ny * .5f + .5f;
+    ox = __float2int_rz(c.resX * nx);
+    oy = __float2int_rz(c.resY * ny);
+}
+
+// ------------------------------------------------------------------------------------------------ shading
+RS_D float schlickG(float c, float alpha) { float a = alpha * .5f; return c / (c * (1.f - a) + a); }   // material.h:62
+RS_D float GTR2Distrib(float c, float alpha) {                                                          // material.h:71
+    if (c < 1e-6f) return 0.f;
+    float aa = alpha * alpha;
+    float denom = c * c * (aa - 1.f) + 1.f;
+    denom = denom * denom * RS_PI;
+    return aa / denom;
+}
+// Material::BSDF (material.h:218-228; :122 lambertian, :171-186 metallic workflow, :137 dielectric)
+RS_D f3 materialBSDF(int type, float metallic, float roughness, f3 baseColor, f3 n, f3 wo, f3 wi) {
+    if (type == 0) return baseColor * 1.f / RS_PI;
+    if (type == 1) {
+        float alpha = roughness * roughness;
+        f3 h = normalize(wo + wi);
+        float cosO = dot(n, wo), cosI = dot(n, wi);
+        if (cosI * cosO < 1e-7f) return mk3(0.f);
+        f3 f0 = mix(mk3(.08f), baseColor, metallic);
+        f3 f = mix(f0, mk3(1.f), pow5(1.f - dot(h, wo)));
+        float g = schlickG(fabsf(cosO), alpha) * schlickG(fabsf(cosI), alpha);
+        float d = GTR2Distrib(dot(n, h), alpha);
+        return mix(baseColor * 1.f / RS_PI * (1.f - metallic), mk3(g * d / (4.f * cosI * cosO)), f);
+    }
+    return mk3(0.f);
+}
+
+struct Resv {       // register-resident reservoir (restir.h:29-117); Li is implied by lightId
+    f3 wi; float dist; float w; int M; int lightId;
+};
+RS_D Resv emptyResv() { Resv r; r.wi = mk3(0.f); r.dist = 0.f; r.w = 0.f; r.M = 0; r.lightId = -1; return r; }
+RS_D bool resvInvalid(const Resv& r) { return isNanOrInf(r.w) || r.w < 0.f; }                           // :51
+RS_D void resvCheck(Resv& r) { if (resvInvalid(r)) { r.w = 0.f; r.M = 0; } }                            // :55
+RS_D void resvMerge(Resv& a, const Resv& b, float rnd) {                                                 // :61
+    a.w += b.w; a.M += b.M;
+    if (rnd * a.w < b.w) { a.wi = b.wi; a.dist = b.dist; a.lightId = b.lightId; }
+}
+RS_D void resvClamp(Resv& r, int val) { if (r.M > val) { r.w *= (float)val / r.M; r.M = val; } }        // :88
+RS_D Resv loadResv(const ResvD* p) {
+    const float4* q = (const float4*)p;
+    float4 a = q[0], b = q[1];
+    Resv r; r.wi = mk3(a.x, a.y, a.z); r.dist = a.w; r.w = b.x; r.M = __float_as_int(b.y); r.lightId = __float_as_int(b.z);
+    return r;
+}
+RS_D void storeResv(ResvD* p, const Resv& r) {
+    float4* q = (float4*)p;
+    q[0] = make_float4(r.wi.x, r.wi.y, r.wi.z, r.dist);
+    q[1] = make_float4(r.w, __int_as_float(r.M), __int_as_float(r.lightId), 0.f);
+}
+RS_D f3 lightLe(const DevScene& s, int lightId) {
+    if (lightId < 0) return mk3(0.f);
+    float4 d = __ldg(s.lights + 4 * (size_t)lightId + 3);       // LightRec words 12..15 = {Le.x, Le.y, Le.z, pdfArea}
+    return mk3(d.x, d.y, d.z);
+}
+
+// pixel owned by this thread: 128-thread blocks = 4 warps of 8x4 pixels, block tile 16x8
+RS_D bool pixelOf(const FrameDev& f, int& x, int& y) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    y = f.rowLo + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    return x < f.W && y < f.rowHi;
+}
+RS_D size_t planeIndex(const FrameDev& f, int x, int y) { return (size_t)(y - f.bufRow0) * f.W + x; }
+RS_D bool rowResident(const FrameDev& f, int y) { return y >= f.bufRow0 && y < f.bufRow0 + f.bufRows; }
+
+// restir.cu:216-230: final shade of a reservoir and accumulation into the radiance image
+RS_D void writeRadiance(const FrameDev& f, size_t li, f3 direct, int iter) {
+    float4 am = f.albedoMotion[li];
+    direct = direct * mk3(am.x, am.y, am.z);                                     // :229
+    float* out = f.radiance + 3 * li;
+    f3 prev = mk3(out[0], out[1], out[2]);
+    f3 v = (prev * (float)iter + direct) / (float)(iter + 1);                    // :230
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+}
+RS_D f3 shadeReservoir(const DevScene& s, const Resv& r, int type, float metallic, float roughness, f3 n, f3 wo) {
+    f3 direct = mk3(0.f);
+    if (!resvInvalid(r)) {
+        f3 LiBSDF = lightLe(s, r.lightId) * materialBSDF(type, metallic, roughness, mk3(1.f), n, wo, r.wi);
+        direct = LiBSDF / luminance(LiBSDF) * r.w / (float)r.M;
+    }
+    if (hasNanOrInf(direct)) direct = mk3(0.f);
+    return direct;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(128) k_gbuffer(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                 const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
+    int x, y;
+    if (!pixelOf(f, x, y)) return;
+    size_t li = planeIndex(f, x, y);
+    f3 o, d;
+    cameraRay(cam, x, y, .5f, .5f, o, d);
+    RayT r = makeRayT(o, d);
+    Hit h;
+    traceClosest(s, r, h);
+    if (h.prim >= 0) {
+        Tri t = loadTri(s, h.prim);
+        const float4* np = s.triNorm + 3 * (size_t)h.prim;
+        float4 na4 = __ldg(np), nb4 = __ldg(np + 1), nc4 = __ldg(np + 2);
+        f3 na = mk3(na4.x, na4.y, na4.z), nb = mk3(na4.w, nb4.x, nb4.y), nc = mk3(nb4.z, nb4.w, nc4.x);
+        float bz = 1.f - h.bx - h.by;
+        f3 pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;                              // scene.h:148
+        f3 nrm = normalize(nb * h.bx + nc * h.by + na * bz);                         // scene.h:149
+        const RstrMaterial* m = s.materials + t.matId;
+        int type = __ldg(&m->type);
+        int matId = type == 4 ? -2 : t.matId;                                        // gbuffer.cu:29-31
+        f3 albedo = mk3(__ldg(&m->baseColor[0]), __ldg(&m->baseColor[1]), __ldg(&m->baseColor[2]));
+        float depth = length(o - pos);                                               // gbuffer.cu:44
+        int lx, ly;
+        rasterCoord(lastCam, pos, lx, ly);                                           // gbuffer.cu:49-55
+        int motion = (lx >= 0 && lx < f.W && ly >= 0 && ly < f.H) ? ly * f.W + lx : -1;
+        f.geom[0][li] = make_float4(nrm.x, nrm.y, nrm.z, depth);
+        f.matId[0][li] = matId;
+        f.albedoMotion[li] = make_float4(albedo.x, albedo.y, albedo.z, __int_as_float(motion));
+    } else {
+        f.geom[0][li] = make_float4(0.f, 0.f, 0.f, 1.f);                             // gbuffer.cu:57-72
+        f.matId[0][li] = -1;
+        f.albedoMotion[li] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+    }
+}
+
+// scene.h:394-425 on the packed light record; returns the pdf (<= 0: invalid), fills wi / dist / lightId
+RS_D float sampleLight(const DevScene& s, f3 pos, float r0, float r1, float r2, float r3, f3& Li, f3& wi, float& dist, int& lightId) {
+    int len = s.numLights;
+    int pass = min(__float2int_rz((float)len * r0), len - 1);                       // sampler.h:204
+    float2 e = __ldg(s.alias + pass);
+    lightId = (r1 < e.x) ? pass : __float_as_int(e.y);
+    const float4* lp = s.lights + 4 * (size_t)lightId;
+    float4 a = __ldg(lp), b = __ldg(lp + 1), c = __ldg(lp + 2), d4 = __ldg(lp + 3);
+    f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(a.w, b.x, b.y), v2 = mk3(b.z, b.w, c.x);
+    f3 n = mk3(c.y, c.z, c.w);
+    float sr = sqrtf(r3);                                                            // mathUtil.h:94-100 (ru = r.z, rv = r.w)
+    float u = 1.f - sr;
+    float v = r2 * sr;
+    f3 sampled = v1 * u + v2 * v + v0 * (1.f - u - v);
+    f3 pts = sampled - pos;
+    if (dot(n, pts) > -1e-6f) return -1.f;                                           // scene.h:415
+    Li = mk3(d4.x, d4.y, d4.z);
+    float len2 = dot(pts, pts);
+    float sq = sqrtf(len2);
+    wi = pts * (1.f / sq);                                                           // normalize(posToSampled)
+    dist = sq;                                                                       // length(posToSampled)
+    // pdfAreaToSolidAngle(pdfArea, pos, sampled, n): yx = pos - sampled = -pts exactly, so dot(yx,yx) = len2 and
+    // normalize(yx) = -wi bit for bit; |dot(n, -wi)| = |dot(n, wi)|
+    return d4.w * len2 / fabsf(dot(n, wi));
+}
+
+// restir.cu:20-45
+RS_D Resv findTemporal(const FrameDev& f, size_t li, int idx) {
+    int primId = f.matId[0][li];
+    int lastIdx = __float_as_int(f.albedoMotion[li].w);
+    if (lastIdx < 0 || primId <= -1) return emptyResv();
+    int ly = lastIdx / f.W;
+    if (!rowResident(f, ly)) { atomicAdd(f.haloMiss, 1u); return emptyResv(); }
+    size_t lli = (size_t)lastIdx - (size_t)f.bufRow0 * f.W;
+    if (f.matId[1][lli] != primId) return emptyResv();
+    float4 g = f.geom[0][li], lg = f.geom[1][lli];
+    if (absDot(mk3(g.x, g.y, g.z), mk3(lg.x, lg.y, lg.z)) < .9f || fabsf(lg.w - g.w) > g.w * .1f) return emptyResv();
+    return loadResv(f.resvIn + lli);
+}
+
+template <bool SPATIAL>
+__global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                  const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
+                                                  int looper, int iter, int first) {
+    int x, y;
+    if (!pixelOf(f, x, y)) return;
+    size_t li = planeIndex(f, x, y);
+    int index = y * f.W + x;
+    Rng rng;
+    rng.seed(looper, index);
+    float r0 = rng.next(), r1 = rng.next();
+    rng.next(); rng.next();                                                          // r.z, r.w of sample4D are drawn and unused (restir.cu:129)
+    f3 o, d;
+    cameraRay(cam, x, y, r0, r1, o, d);
+    RayT ray = makeRayT(o, d);
+    Hit h;
+    traceClosest(s, ray, h);
+    int status = 0;      // 0 miss, 1 emitter, 2 shaded
+    f3 pos, nrm;
+    int matId = -1, type = 0;
+    float metallic = 0.f, roughness = 1.f;
+    if (h.prim >= 0) {
+        Tri t = loadTri(s, h.prim);
+        const float4* np = s.triNorm + 3 * (size_t)h.prim;
+        float4 na4 = __ldg(np), nb4 = __ldg(np + 1), nc4 = __ldg(np + 2);
+        f3 na = mk3(na4.x, na4.y, na4.z), nb = mk3(na4.w, nb4.x, nb4.y), nc = mk3(nb4.z, nb4.w, nc4.x);
+        float bz = 1.f - h.bx - h.by;
+        pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;
+        nrm = normalize(nb * h.bx + nc * h.by + na * bz);
+        matId = t.matId;
+        const RstrMaterial* m = s.materials + matId;
+        type = __ldg(&m->type);
+        metallic = __ldg(&m->metallic);
+        roughness = __ldg(&m->roughness);
+        status = type == 4 ? 1 : 2;
+    }
+    if (status != 2) {                                                               // restir.cu:133-146 -> WriteRadiance
+        writeRadiance(f, li, status == 1 ? mk3(1.f) : mk3(0.f), iter);
+        if (SPATIAL) {
+            float4* q = (float4*)(f.hit + li);
+            q[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    f3 wo = -d;
+    if (type != 2 && dot(nrm, wo) < 0.f) nrm = -nrm;                                 // restir.cu:150-153
+    Resv R = emptyResv();
+    const int nc = prm.numCandidates;
+    for (int i = 0; i < nc; i++) {                                                   // restir.cu:156-169
+        float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
+        f3 Li = mk3(0.f), wi = mk3(0.f);
+        float dist = 0.f;
+        int lid = -1;
+        float p = s.numLights > 0 ? sampleLight(s, pos, c0, c1, c2, c3, Li, wi, dist, lid) : -1.f;
+        f3 g = Li * materialBSDF(type, metallic, roughness, mk3(1.f), nrm, wo, wi) * satDot(nrm, wi);
+        float weight = luminance(g / p);
+        if (isNanOrInf(weight) || p <= 0.f) weight = 0.f;
+        float rnd = rng.next();
+        R.w += weight; R.M++;                                                        // Reservoir::update, restir.h:38
+        if (rnd * R.w < weight) { R.wi = wi; R.dist = dist; R.lightId = lid; }
+    }
+    // restir.cu:172-176.  With weight == 0 the test cannot change anything, so the ray is skipped.
+    if (R.w != 0.f && traceOccluded(s, pos, pos + R.wi * R.dist)) R.w = 0.f;
+    if (!first && (prm.reuse & 1)) {                                                 // restir.cu:180-185
+        Resv T = findTemporal(f, li, index);
+        if (!resvInvalid(T)) {
+            float rnd = rng.next();
+            if (R.M > 0) resvClamp(T, (prm.temporalCap - 1) * R.M);                  // preClampedMerge, restir.h:96
+            resvMerge(R, T, rnd);
+        }
+    }
+    Resv hist = R;                                                                   // tempReservoir, restir.cu:188
+    resvCheck(hist);
+    storeResv(f.resvOut + li, hist);                                                 // restir.cu:211-212
+    if (SPATIAL) {
+        resvCheck(R);                                                                // restir.cu:191-192
+        storeResv(f.resvTemp + li, R);
+        float4* q = (float4*)(f.hit + li);
+        q[0] = make_float4(nrm.x, nrm.y, nrm.z, __int_as_float(matId));
+        q[1] = make_float4(wo.x, wo.y, wo.z, __uint_as_float(rng.x));
+    } else {
+        writeRadiance(f, li, shadeReservoir(s, R, type, metallic, roughness, nrm, wo), iter);
+    }
+}
+
+// restir.cu:47-85 (+ mathUtil.h:128-132 toConcentricDisk)
+RS_D Resv findSpatial(const FrameDev& f, int x, int y, size_t li, float rx, float ry, float radius) {
+    float rr = sqrtf(rx);
+    float theta = ry * RS_PI * 2.0f;
+    float px_ = cosf(theta) * rr * radius, py_ = sinf(theta) * rr * radius;
+    int px = __float2int_rz((float)x + .5f + px_);
+    int py = __float2int_rz((float)y + .5f + py_);
+    if (px < 0 || px >= f.W || py < 0 || py >= f.H || (px == x && py == y)) return emptyResv();
+    if (!rowResident(f, py)) { atomicAdd(f.haloMiss, 1u); return emptyResv(); }
+    size_t pli = planeIndex(f, px, py);
+    if (f.matId[0][pli] != f.matId[0][li]) return emptyResv();
+    float4 g = f.geom[0][li], pg = f.geom[0][pli];
+    bool diff = dot(mk3(g.x, g.y, g.z), mk3(pg.x, pg.y, pg.z)) < .9f;
+    if (fabsf(g.w - pg.w) > g.w * .1f) diff = true;
+    if (diff) return emptyResv();
+    return loadResv(f.resvTemp + pli);
+}
+
+__global__ void __launch_bounds__(128) k_restir_b(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                  const __grid_constant__ RstrParams prm, int iter) {
+    int x, y;
+    if (!pixelOf(f, x, y)) return;
+    size_t li = planeIndex(f, x, y);
+    const float4* q = (const float4*)(f.hit + li);
+    float4 h0 = q[0], h1 = q[1];
+    int matId = __float_as_int(h0.w);
+    if (matId < 0) return;                          // phase A already wrote this pixel's radiance
+    Rng rng; rng.x = __float_as_uint(h1.w);
+    f3 nrm = mk3(h0.x, h0.y, h0.z), wo = mk3(h1.x, h1.y, h1.z);
+    const RstrMaterial* m = s.materials + matId;
+    int type = __ldg(&m->type);
+    float metallic = __ldg(&m->metallic), roughness = __ldg(&m->roughness);
+    Resv R = loadResv(f.resvTemp + li);
+    Resv S = emptyResv();                                                            // restir.cu:87-100
+    for (int i = 0; i < prm.numSpatial; i++) {
+        float rx = rng.next(), ry = rng.next();
+        Resv N = findSpatial(f, x, y, li, rx, ry, prm.spatialRadius);
+        if (!resvInvalid(N)) resvMerge(S, N, rng.next());
+    }
+    if (!resvInvalid(S) && !resvInvalid(R)) resvMerge(R, S, rng.next());             // restir.cu:197-199
+    writeRadiance(f, li, shadeReservoir(s, R, type, metallic, roughness, nrm, wo), iter);
+}
+
+// pathtrace.cu:279-328 with scene.h:427-459 (occlusion test BEFORE the facing test)
+__global__ void __launch_bounds__(128) k_ptdirect(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                  const __grid_constant__ CamDev cam, int looper, int iter) {
+    int x, y;
+    if (!pixelOf(f, x, y)) return;
+    size_t li = planeIndex(f, x, y);
+    int index = y * f.W + x;
+    Rng rng;
+    rng.seed(looper, index);
+    float r0 = rng.next(), r1 = rng.next();
+    rng.next(); rng.next();
+    f3 o, d;
+    cameraRay(cam, x, y, r0, r1, o, d);
+    RayT ray = makeRayT(o, d);
+    Hit h;
+    traceClosest(s, ray, h);
+    f3 direct = mk3(0.f);
+    if (h.prim >= 0) {
+        Tri t = loadTri(s, h.prim);
+        const RstrMaterial* m = s.materials + t.matId;
+        int type = __ldg(&m->type);
+        f3 baseColor = mk3(__ldg(&m->baseColor[0]), __ldg(&m->baseColor[1]), __ldg(&m->baseColor[2]));
+        if (type == 4) direct = baseColor;
+        else if (type != 2 && s.numLights > 0) {
+            const float4* np = s.triNorm + 3 * (size_t)h.prim;
+            float4 na4 = __ldg(np), nb4 = __ldg(np + 1), nc4 = __ldg(np + 2);
+            f3 na = mk3(na4.x, na4.y, na4.z), nb = mk3(na4.w, nb4.x, nb4.y), nc = mk3(nb4.z, nb4.w, nc4.x);
+            float bz = 1.f - h.bx - h.by;
+            f3 pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;
+            f3 nrm = normalize(nb * h.bx + nc * h.by + na * bz);
+            f3 wo = -d;
+            if (dot(nrm, wo) < 0.f) nrm = -nrm;
+            float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
+            int len = s.numLights;
+            int pass = min(__float2int_rz((float)len * c0), len - 1);
+            float2 e = __ldg(s.alias + pass);
+            int lightId = (c1 < e.x) ? pass : __float_as_int(e.y);
+            const float4* lp = s.lights + 4 * (size_t)lightId;
+            float4 a = __ldg(lp), b = __ldg(lp + 1), c = __ldg(lp + 2), d4 = __ldg(lp + 3);
+            f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(a.w, b.x, b.y), v2 = mk3(b.z, b.w, c.x);
+            f3 n = mk3(c.y, c.z, c.w);
+            float sr = sqrtf(c3);
+            float u = 1.f - sr, v = c2 * sr;
+            f3 sampled = v1 * u + v2 * v + v0 * (1.f - u - v);
+            if (!traceOccluded(s, pos, sampled)) {
+                f3 pts = sampled - pos;
+                if (!(dot(n, pts) > -1e-6f)) {
+                    f3 Li = mk3(d4.x, d4.y, d4.z);
+                    float len2 = dot(pts, pts);
+                    f3 wi = pts * (1.f / sqrtf(len2));
+                    float pdf = d4.w * len2 / fabsf(dot(n, wi));
+                    if (pdf > 0.f)
+                        direct = Li * materialBSDF(type, __ldg(&m->metallic), __ldg(&m->roughness), baseColor, nrm, wo, wi) * satDot(nrm, wi) / pdf;
+                }
+            }
+        }
+    }
+    float* out = f.radiance + 3 * li;
+    f3 prev = mk3(out[0], out[1], out[2]);
+    f3 v = (prev * (float)iter + direct) / (float)(iter + 1);
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+}
+
+// pathtrace.cu:30-56 (Math::filmic / ACES / correctGamma: mathUtil.h:103-117)
+RS_D float calcFilmic(float c) { return (c * (c * 0.22f + 0.03f) + 0.002f) / (c * (c * 0.22f + 0.3f) + 0.06f) - 1.f / 30.f; }
+__global__ void __launch_bounds__(256) k_tonemap(const float* __restrict__ radiance, uchar4* __restrict__ ldr, size_t n, int toneMapping, float scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 c = mk3(radiance[3 * i], radiance[3 * i + 1], radiance[3 * i + 2]) * scale;
+    if (toneMapping == 1) {
+        float w = calcFilmic(11.2f);
+        c = mk3(calcFilmic(c.x * 1.6f), calcFilmic(c.y * 1.6f), calcFilmic(c.z * 1.6f)) / w;
+    } else if (toneMapping == 2) {
+        c = (c * (c * 2.51f + mk3(0.03f))) / (c * (c * 2.43f + mk3(0.59f)) + mk3(0.14f));
+    }
+    c = mk3(powf(c.x, 1.f / 2.2f), powf(c.y, 1.f / 2.2f), powf(c.z, 1.f / 2.2f));
+    int r = min(max(__float2int_rz(c.x * 255.f), 0), 255);
+    int g = min(max(__float2int_rz(c.y * 255.f), 0), 255);
+    int b = min(max(__float2int_rz(c.z * 255.f), 0), 255);
+    ldr[i] = make_uchar4((unsigned char)r, (unsigned char)g, (unsigned char)b, 0);
+}
+
+// ---- device-internal planes -> reference host layouts ----
+__global__ void k_export_geom(const float4* __restrict__ geom, const float4* __restrict__ am, float* albedo, float* normal, float* depth, int* motion, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 g = geom[i], a = am[i];
+    if (albedo) { albedo[3 * i] = a.x; albedo[3 * i + 1] = a.y; albedo[3 * i + 2] = a.z; }
+    if (normal) { normal[3 * i] = g.x; normal[3 * i + 1] = g.y; normal[3 * i + 2] = g.z; }
+    if (depth) depth[i] = g.w;
+    if (motion) motion[i] = __float_as_int(a.w);
+}
+__global__ void k_export_resv(const DevScene s, const ResvD* __restrict__ src, float* out36, int* lightIdx, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Resv r = loadResv(src + i);
+    if (lightIdx) lightIdx[i] = r.lightId;
+    if (out36) {
+        f3 Li = lightLe(s, r.lightId);
+        float* o = out36 + 9 * i;
+        o[0] = Li.x; o[1] = Li.y; o[2] = Li.z; o[3] = r.wi.x; o[4] = r.wi.y; o[5] = r.wi.z; o[6] = r.dist;
+        o[7] = __int_as_float(r.M); o[8] = r.w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static inline dim3 pixelGrid(const FrameDev& f) { return dim3((f.W + 15) / 16, (f.rowHi - f.rowLo + 7) / 8); }
+
+void launchGBuffer(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, cudaStream_t st) {
+    k_gbuffer<<<pixelGrid(f), 128, 0, st>>>(s, f, cam, lastCam);
+}
+void launchRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& p, int looper, int iter, int first, cudaStream_t st) {
+    if (p.reuse & 2) k_restir_a<true><<<pixelGrid(f), 128, 0, st>>>(s, f, cam, p, looper, iter, first);
+    else k_restir_a<false><<<pixelGrid(f), 128, 0, st>>>(s, f, cam, p, looper, iter, first);
+}
+void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, cudaStream_t st) {
+    k_restir_b<<<pixelGrid(f), 128, 0, st>>>(s, f, p, iter);
+}
+void launchPTDirect(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, cudaStream_t st) {
+    k_ptdirect<<<pixelGrid(f), 128, 0, st>>>(s, f, cam, looper, iter);
+}
+void launchTonemap(const float* radiance, uchar4* ldr, size_t n, int toneMapping, float scale, cudaStream_t st) {
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(radiance, ldr, n, toneMapping, scale);
+}
+void launchExportGeom(const float4* geom, const float4* am, float* albedo, float* normal, float* depth, int* motion, size_t n, cudaStream_t st) {
+    k_export_geom<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(geom, am, albedo, normal, depth, motion, n);
+}
+void launchExportResv(const DevScene& s, const ResvD* src, float* out36, int* lightIdx, size_t n, cudaStream_t st) {
+    k_export_resv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, src, out36, lightIdx, n);
+}
+
+}  // namespace rs

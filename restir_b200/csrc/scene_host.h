@@ -1,0 +1,100 @@
+// scene_host.h -- host-side scene build: light list, alias table, BVH (bit-identical to the
+// reference's builder output), and the cache-line-packed device layouts derived from it.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "../../include/restir_b200.h"
+#include "vecmath.h"
+
+namespace rs {
+
+struct Box {            // reference AABB, 24 B (bvh.h:159-160)
+    f3 pMin, pMax;
+};
+
+// ---- device-facing packed layouts ----
+// One 64-byte record per INTERNAL node: both children's boxes + links, fetched as 4 x LDG.128.
+struct alignas(16) PackedNode {
+    float lmin[3], lmax[3];   // left child box
+    float rmin[3], rmax[3];   // right child box
+    int left, right;          // >= 0: packed index of an internal child; < 0: ~primId of a leaf child
+    int orderMask;            // bit d: center(left)[d] < center(right)[d]  (bvh.cpp:184-188)
+    int pad;
+};
+static_assert(sizeof(PackedNode) == 64, "PackedNode");
+
+struct alignas(16) TriGeom {  // 48 B: raw vertices (Moller-Trumbore recomputes the edges exactly as intersections.h:20-21)
+    float v0[3], v1[3], v2[3];
+    int matId;
+    int pad[2];
+};
+static_assert(sizeof(TriGeom) == 48, "TriGeom");
+
+struct alignas(16) TriNorm {  // 48 B: vertex normals, read once per ray at the hit
+    float n0[3], n1[3], n2[3];
+    float pad[3];
+};
+static_assert(sizeof(TriNorm) == 48, "TriNorm");
+
+struct alignas(16) LightRec { // 64 B: everything sampleDirectLightNoVisibility needs after the alias lookup
+    float v0[3], v1[3], v2[3];
+    float n[3];               // Math::triangleNormal(v0,v1,v2)                    (scene.h:411)
+    float Le[3];              // lightUnitRadiance                                 (scene.h:420)
+    float pdfArea;            // luminance(Le) / (area*2*pi) * sumLightPowerInv    (scene.h:423-424)
+};
+static_assert(sizeof(LightRec) == 64, "LightRec");
+
+struct AliasEntry {           // sampler.h:63-67
+    float prob;
+    int failId;
+};
+
+struct MTNode {               // bvh.h:163-171
+    int prim, box, miss;
+};
+
+struct HostScene {
+    int T = 0;
+    std::vector<f3> vertices, normals;
+    std::vector<float> texcoords;          // 2 per vertex
+    std::vector<int> materialIds;
+    std::vector<RstrMaterial> materials;
+
+    // reference-format build outputs
+    int bvhSize = 0, bvhDepth = 0;
+    std::vector<Box> boxes;                // pre-order, Scene::boundingBoxes
+    std::vector<int> nodeInfo;             // pre-order: > 0 subtree size (internal), <= 0: -(primId) - 1 ... see isLeaf()
+    std::vector<int> lightPrimIds;
+    std::vector<f3> lightUnitRadiance;
+    std::vector<float> lightPower;
+    std::vector<AliasEntry> alias;
+    float sumAll = 0.f, sumLightPowerInv = 0.f;
+
+    // packed device layouts
+    Box rootBox;
+    int rootRef = 0;
+    std::vector<PackedNode> packed;
+    std::vector<TriGeom> triGeom;
+    std::vector<TriNorm> triNorm;
+    std::vector<LightRec> lights;
+    double buildSeconds = 0.0;
+
+    static bool isLeaf(int info) { return info < 0; }
+    static int leafPrim(int info) { return -info - 1; }
+};
+
+// scene.cpp:159-215 minus the upload.  Returns false (and sets err) on invalid input.
+bool buildHostScene(HostScene& hs, std::string& err);
+// bvh.cpp:133-201: the reference's i-th threaded ordering, regenerated from the single tree
+void exportMTBVH(const HostScene& hs, int ordering, std::vector<MTNode>& out);
+// sampler.h:79-121
+void buildAliasTable(const std::vector<float>& values, std::vector<AliasEntry>& table, float& sumAll);
+
+// Scene::Scene(filename): scene text + OBJ -> flattened arrays + camera (scene.cpp:96-131, 222-433, 159-190)
+bool loadSceneFile(const std::string& path, HostScene& hs, RstrCamera& cam, std::string& err);
+// Camera::update (sceneStructs.h:88-102)
+void cameraUpdate(RstrCamera& c);
+
+}  // namespace rs
