@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- ReSTIR DI frame throughput on B200 (contract: see the task statement / DESIGN.md section 7).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2] [--impl b200|reference]
+
+A step is one frame of the hot path (G-buffer + ReSTIR DI, main.cpp:164-167) of the workload's camera orbit.
+Default workload = BASELINE.json configs[1]: Cornell box, 1920x1080, spatiotemporal reuse (temporal cap 20,
+5 spatial neighbours, r = 30 px), 60-frame orbiting camera.  metric = Mpixel/s (higher is better), ms_per_step =
+ms/frame.  `value` is timed on the device (CUDA events on the launching stream) with everything resident in HBM;
+`e2e` goes through rstr_render_frame_host (camera in from the host, tone-mapped 8-bit frame back into pinned host
+memory every step).  N > 1: one process per GPU under torchrun, horizontal image strips, reservoir halo rows
+exchanged with NCCL send/recv; strong scaling (the image is fixed).
+
+--impl reference times the reference's own CPU implementation of the same path (oracle/_ref/libref_harness.so when
+it was built from /root/reference, else the oracle port) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (description, scene factory args, resolution, reuse, radius)
+    "config1": ("Cornell box 800x800 RIS-only (32 candidates, 1 spp)", ("cornell",), (800, 800), 0, 5.0),
+    "config2": ("Cornell box 1920x1080 spatiotemporal (cap 20, k=5, r=30px), 60-frame orbit", ("cornell",), (1920, 1080), 3, 30.0),
+    "config3": ("procedural 200k tris / 10k emissive, 1080p spatiotemporal (r=30px), orbit", ("gen", 1, 200_000, 10_000), (1920, 1080), 3, 30.0),
+    "config4": ("procedural 1M tris / 100k emissive, 3840x2160 spatiotemporal (r=30px), orbit", ("gen", 1, 1_000_000, 100_000), (3840, 2160), 3, 30.0),
+    "config4_1080p": ("procedural 1M tris / 100k emissive, 1080p spatiotemporal (r=30px), orbit", ("gen", 1, 1_000_000, 100_000), (1920, 1080), 3, 30.0),
+}
+# algorithmic HBM bytes per pixel per frame with the reference's fp32 layouts (SURVEY.md 8d / BASELINE.md section 4)
+BYTES_PER_PIXEL = {0: 96, 1: 176, 2: 248, 3: 248}
+# ... split per kernel for the spatiotemporal frame: G-buffer write 36 | phase A: own G-buffer 24 + previous G-buffer 20 +
+# previous reservoir 36 + post-temporal reservoir 36 + history reservoir 36 = 152 | phase B: reservoir 36 + albedo 12 + radiance 12 = 60
+KERNEL_BYTES_PER_PIXEL = {"gbuffer": 36, "ris": {0: 60, 1: 140, 2: 116, 3: 152}, "spatial": 60}
+
+
+def make_scene(spec, resolution):
+    from restir_b200 import scenes
+
+    if spec[0] == "cornell":
+        return scenes.cornell_box(resolution)
+    return scenes.procedural(spec[1], spec[2], spec[3], resolution)
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path).read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for i, n in enumerate(names):
+                if f[5 + i].lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class quiet_stdout:
+    """The reference's host code prints progress with std::cout (bvh.cpp:15,128); keep the JSON line alone on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_frames(kind, sd, reuse, radius, frames, warmup):
+    with quiet_stdout():
+        return _cpu_frames(kind, sd, reuse, radius, frames, warmup)
+
+
+def _cpu_frames(kind: str, sd, reuse: float, radius: float, frames: int, warmup: int):
+    """Times `frames` frames of the orbit on the host cores; returns (seconds, threads)."""
+    from oracle.oracle import Oracle, default_params, make_camera, orbit_camera
+
+    orc = Oracle(kind)
+    W, H = sd.resolution
+    so = orc.scene(sd)
+    fo = so.frame(W, H)
+    base = make_camera(sd)
+    orc.lib.orc_camera_update(C.byref(base))
+    prm = default_params(reuse=reuse, radius=radius)
+    t0 = None
+    for k in range(warmup + frames):
+        if k == warmup:
+            t0 = time.perf_counter()
+        cam = orbit_camera(orc, base, k)
+        fo.gbuffer_render(cam)
+        fo.restir_direct(cam, prm, k, 0)
+        fo.gbuffer_update(cam)
+    dt = time.perf_counter() - t0
+    return dt, orc.threads()
+
+
+def reference_kind() -> str:
+    from oracle.oracle import have_reference
+
+    return "reference" if have_reference() else "port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, spec, res, reuse, radius = WORKLOADS[args.workload]
+    sd = make_scene(spec, res)
+    kind = reference_kind()
+    P = res[0] * res[1]
+    # bound the sample so that the whole run stays within minutes: estimate from one frame
+    t1, threads = cpu_frames(kind, sd, reuse, radius, 1, 0)
+    steps = args.steps
+    budget = 150.0
+    if t1 * (steps + args.warmup) > budget:
+        steps = max(1, int(budget / t1) - args.warmup)
+    warm = min(args.warmup, max(0, int(budget / t1) - steps))
+    dt, threads = cpu_frames(kind, sd, reuse, radius, steps, warm)
+    ms = dt / steps * 1e3
+    val = P / (ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "ReSTIR DI Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "resolution": list(res), "triangles": sd.num_tris, "emissive_triangles": sd.num_lights},
+        "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": threads, "kind": kind,
+                         "sample": "%d frames of the orbit at %dx%d (OpenMP over rows, %d threads)" % (steps, res[0], res[1], threads)},
+        "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- B200 arm
+class _DevMem:
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def run_b200(args):
+    import restir_b200 as rb
+    from restir_b200 import strips
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rb.init(local)
+    desc, spec, res, reuse, radius = WORKLOADS[args.workload]
+    W, H = res
+    P = W * H
+    sd = make_scene(spec, res)
+    sc = rb.Scene.from_arrays(sd)
+    halo = strips.default_halo(radius) if world > 1 else 0
+    rows = strips.strip_rows(H, world, rank)
+    fr = sc.frame(W, H, rows=rows, halo=halo)
+    base = rb.Camera.from_scene(sd)
+    prm = rb.default_params(reuse=reuse, radius=radius)
+
+    plan = strips.exchange_plan(H, world, halo) if world > 1 else []
+    if world > 1:
+        fr.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def exchange(plane):
+        ops, keep = [], []
+        for src, dst, r0, r1 in plan:
+            if rank not in (src, dst):
+                continue
+            ptr, rb_ = fr.plane_row(plane, r0)
+            t = torch.as_tensor(_DevMem(ptr, rb_ * (r1 - r0)), device="cuda")
+            keep.append(t)
+            ops.append(dist.P2POp(dist.isend if rank == src else dist.irecv, t, dst if rank == src else src))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def frame(k):
+        cam = base.orbit(k)
+        fr.gbuffer_render(cam)
+        if world == 1:
+            fr.restir_direct(cam, prm, k, 0)
+        else:
+            fr.restir_phase_a(cam, prm, k, 0)
+            if reuse & 2:
+                exchange("resv_temp")
+            fr.restir_phase_b(cam, prm, k, 0)
+            if reuse & 1:
+                exchange("resv_history")
+        fr.gbuffer_update(cam)
+
+    def barrier():
+        fr.sync()
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    k = 0
+    for _ in range(args.warmup):
+        frame(k); k += 1
+    # ---- pass 1: device-timed throughput (no per-frame synchronisation)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = rb.launch_count()
+    fr.mark(0)
+    for _ in range(args.steps):
+        frame(k); k += 1
+    fr.mark(1)
+    barrier()
+    ms_total = max_over_ranks(fr.elapsed_ms(0, 1))
+    launches = rb.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = P / (ms_step * 1e-3) / 1e6
+    # ---- pass 2: per-kernel durations (CUDA events around every launch on the launching stream)
+    stage = {"gbuffer": [], "ris": [], "spatial": []}
+    for _ in range(min(args.steps, 20)):
+        frame(k); k += 1
+        for n, v in fr.stage_ms().items():
+            if n in stage and v > 0:
+                stage[n].append(v)
+    stage_ms = {n: (sum(v) / len(v) if v else 0.0) for n, v in stage.items()}
+    # ---- pass 3: end to end through the host-facing call (N = 1) / strips gathered to rank 0 (N > 1)
+    npix_local = (rows[1] - rows[0]) * W
+    e2e_ms = None
+    if world == 1:
+        out = rb.pinned_empty(npix_local * 4)
+        for _ in range(3):
+            fr.render_frame_host(base.orbit(k), prm, k, 0, rb.TONEMAP_ACES, out); k += 1
+        fr.sync()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fr.render_frame_host(base.orbit(k), prm, k, 0, rb.TONEMAP_ACES, out); k += 1
+        e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        assert out.max() > 0
+        rb.pinned_free(out)
+    else:
+        host = torch.empty(P * 4, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        counts = [(strips.strip_rows(H, world, r)[1] - strips.strip_rows(H, world, r)[0]) * W * 4 for r in range(world)]
+        gathered = [torch.empty(c, dtype=torch.uint8, device="cuda") for c in counts] if rank == 0 else None
+
+        # gather of LDR strips to GPU 0 (NCCL) followed by one D2H on rank 0
+        ldr_dev = torch.empty(counts[rank], dtype=torch.uint8, device="cuda")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            frame(k); k += 1
+            fr.tonemap(rb.TONEMAP_ACES, 1.0)
+            fr.read_into_device("ldr", ldr_dev.data_ptr(), counts[rank])
+            dist.gather(ldr_dev, gathered, dst=0)
+            if rank == 0:
+                host.copy_(torch.cat(gathered), non_blocking=False)
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
+    halo_miss = fr.halo_miss()
+    if world > 1:
+        t = torch.tensor([halo_miss], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        halo_miss = int(t.item())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        dom = max(stage_ms, key=lambda n: stage_ms[n])
+        bpp = KERNEL_BYTES_PER_PIXEL[dom]
+        bpp = bpp[reuse] if isinstance(bpp, dict) else bpp
+        strip_px = npix_local
+        achieved = bpp * strip_px / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+        frame_bytes = BYTES_PER_PIXEL[reuse] * P
+        info = sc.info
+        line = {
+            "metric": "ReSTIR DI Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": desc, "resolution": [W, H], "triangles": info.numTris, "emissive_triangles": info.numLights,
+                       "reuse": reuse, "candidates": 32, "temporal_cap": 20, "spatial_neighbours": 5, "spatial_radius_px": radius,
+                       "parallelism": "strips%d" % world, "halo_rows": halo,
+                       "l2": "no explicit flush: the per-frame pixel planes (%.0f MB) exceed the 126 MB L2" % (P * 212 / 1e6)},
+            "e2e": {"value": P / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": C.sizeof(rb.api.RstrCamera) + C.sizeof(rb.RstrParams), "d2h_bytes_per_step": P * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": "k_restir_a", "spatial": "k_restir_b"}[dom],
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_pixel": bpp, "kernel_ms": stage_ms[dom],
+                         "note": "traversal / light-gather bound kernel; HBM fraction reported as required, rays/s below is the telling figure"},
+            "stage_ms": stage_ms,
+            "frame_hbm": {"algorithmic_bytes_per_frame": frame_bytes, "achieved_gbs": frame_bytes / (ms_step * 1e-3) / 1e9, "frac_of_peak": frame_bytes / (ms_step * 1e-3) / 1e9 / peak},
+            "rays_per_s": 3.0 * P / (ms_step * 1e-3),
+            "halo_miss": halo_miss,
+            "host_build_s": info.buildSeconds,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            kind = reference_kind()
+            t1, threads = cpu_frames(kind, sd, reuse, radius, 1, 0)
+            n = max(1, min(args.steps, int(15.0 / max(t1, 1e-3))))
+            dt, threads = cpu_frames(kind, sd, reuse, radius, n, 1 if t1 < 5 else 0)
+            line["cpu_baseline"] = {"value": P / (dt / n) / 1e6, "unit": "Mpixel/s", "cores": threads, "kind": kind,
+                                    "sample": "%d frames of the same orbit at %dx%d, OpenMP over rows" % (n, W, H)}
+        print(json.dumps(line))
+    fr.close()
+    sc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

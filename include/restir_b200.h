@@ -169,11 +169,18 @@ int rstr_render_frame_host(RstrFrame*, const RstrCamera*, const RstrParams*, int
 
 int rstr_frame_sync(RstrFrame*);
 int rstr_frame_read(RstrFrame*, int which, void* host, size_t bytes);
+/* same conversion into DEVICE memory, stream-ordered and without host synchronisation (strip gather to GPU 0) */
+int rstr_frame_read_device(RstrFrame*, int which, void* dev, size_t bytes);
 
 /* ---- instrumentation / plumbing ---- */
 /* device time (ms, CUDA events on the frame's stream) of the stages of the last frame */
 enum { RSTR_T_GBUFFER = 0, RSTR_T_RIS = 1, RSTR_T_SPATIAL = 2, RSTR_T_PTDIRECT = 3, RSTR_T_TONEMAP = 4, RSTR_T_COUNT = 5 };
 int rstr_frame_stage_ms(RstrFrame*, float* ms, int n);
+/* timing marks: cudaEventRecord on the frame's stream into slot 0..7, and the elapsed device time between two */
+int rstr_frame_mark(RstrFrame*, int slot);
+int rstr_frame_elapsed_ms(RstrFrame*, int slotA, int slotB, float* ms);
+/* make the frame enqueue its work on a caller-owned cudaStream_t (NULL = the legacy default stream) */
+int rstr_frame_set_stream(RstrFrame*, void* stream);
 /* number of kernel launches issued by this library so far (all frames of this process) */
 uint64_t rstr_launch_count(void);
 /* the frame's CUDA stream (cudaStream_t) for callers that enqueue their own work */
@@ -196,6 +203,9 @@ enum {
     RSTR_PLANE_RESV_TEMP = 3   /* 32 B post-temporal reservoirs (input of the spatial pass) */
 };
 int rstr_frame_plane_row(RstrFrame*, int plane, int row, void** devPtr, size_t* rowBytes);
+/* copy rows [row0,row1) of `plane` from src to dst (same device or a peer device), ordered after the work queued on
+ * src's stream and before work queued later on dst's stream: the single-process form of the halo exchange */
+int rstr_frame_copy_rows(RstrFrame* dst, RstrFrame* src, int plane, int row0, int row1);
 /* split form of rstr_restir_direct for strips: phase A (candidates + shadow + temporal), then the caller
  * exchanges RESV_TEMP / GEOM_CUR / MATID_CUR halo rows, then phase B (spatial + shade). */
 int rstr_restir_phase_a(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter);

@@ -109,6 +109,8 @@ class Oracle:
         L.orc_occluded.restype = ip
         L.orc_occluded.argtypes = [vp, vp, vp]
         L.orc_last_trace_stats.argtypes = [vp, vp, vp, vp]
+        L.orc_alias_build.restype = fp
+        L.orc_alias_build.argtypes = [ip, vp, vp]
         if kind == "reference":
             L.ref_scene_load_file.restype = vp
             L.ref_scene_load_file.argtypes = [C.c_char_p]
@@ -139,6 +141,12 @@ class Oracle:
         out = np.zeros(n, np.float32)
         self.lib.orc_rng_draws(looper, index, n, out.ctypes.data)
         return out
+
+    def alias_build(self, values):
+        v = np.ascontiguousarray(values, np.float32)
+        out = np.zeros(v.shape[0], np.dtype([("prob", "<f4"), ("failId", "<i4")]))
+        total = self.lib.orc_alias_build(v.shape[0], v.ctypes.data, out.ctypes.data)
+        return out, float(total)
 
     def scene(self, sd) -> "OracleScene":
         return OracleScene(self, sd)

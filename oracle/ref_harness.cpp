@@ -428,6 +428,12 @@ const void* orc_frame_buffer(OrcFrame* f, int which) {
     return nullptr;     /* ORC_BUF_LIGHT_INDEX: the reference keeps no light index (restir.h:7-11) */
 }
 
+float orc_alias_build(int n, const float* values, void* outTable) {
+    DiscreteSampler1D<float> smp(std::vector<float>(values, values + n));
+    memcpy(outTable, smp.binomDistribs.data(), sizeof(BinomialDistrib<float>) * n);
+    return smp.sumAll;
+}
+
 void orc_rng_draws(int looper, int index, int n, float* out) {
     Sampler rng = makeSeededRandomEngine(looper, index, 0, nullptr);
     for (int i = 0; i < n; i++) out[i] = sample1D(rng);

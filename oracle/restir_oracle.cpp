@@ -463,8 +463,11 @@ void sceneIntersect(const OrcScene& sc, const Ray& ray, Isect& is, TraceStats* s
 }
 
 /* scene.h:286-316 + intersections.h:12-14 (makeOffsetedRay) + scene.h:165-173 */
-bool sceneOccluded(const OrcScene& sc, V3 x, V3 y) {
+struct ShadowStats { uint64_t rays = 0, nodes = 0, maxNodes = 0; };
+bool sceneOccluded(const OrcScene& sc, V3 x, V3 y, ShadowStats* st = nullptr) {
     const float Eps = 1e-4f;
+    uint64_t visited = 0;
+    struct Tally { ShadowStats* st; uint64_t& v; ~Tally() { if (st) { st->rays++; st->nodes += v; if (v > st->maxNodes) st->maxNodes = v; } } } tally{st, visited};
     V3 dir = y - x;
     float dist = length(dir);
     dir = dir / dist;
@@ -474,6 +477,7 @@ bool sceneOccluded(const OrcScene& sc, V3 x, V3 y) {
     int node = 0;
     while (node != sc.bvhSize) {
         float bd;
+        visited++;
         bool hit = aabbIntersect(sc.boxes[nodes[node].box], ray, bd);
         if (hit && bd < dist) {
             int prim = nodes[node].prim;
@@ -633,6 +637,7 @@ struct OrcFrame {
     std::vector<ResvPacked> exportBuf;
     std::vector<int> exportIds;
     TraceStats stats;
+    ShadowStats shadow;
     /* per-pixel state carried across the two phases of spatial reuse */
     struct Carry { uint32_t rng; int status; Resv r; V3 n, wo; int matId; };
     std::vector<Carry> carry;
@@ -793,6 +798,8 @@ void orc_gbuffer_update(OrcFrame* f, const OrcCamera* cam) {   /* gbuffer.cu:75-
     f->frameIdx ^= 1;
 }
 
+/* shadow-ray traversal statistics of the last restir_direct: rays, total node visits, max node visits of one ray */
+void orc_last_shadow_stats(OrcFrame* f, uint64_t* rays, uint64_t* nodes, uint64_t* maxNodes) { *rays = f->shadow.rays; *nodes = f->shadow.nodes; *maxNodes = f->shadow.maxNodes; }
 void orc_last_trace_stats(OrcFrame* f, uint64_t* n, uint64_t* t, uint64_t* r) { *n = f->stats.nodes; *t = f->stats.tris; *r = f->stats.rays; }
 
 /* restir.cu:20-45 */
@@ -845,7 +852,11 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
     std::vector<Resv>& in = f->lastResv;     /* reservoirIn  */
     std::vector<Resv>& tmp = f->temp;        /* reservoirTemp */
     /* ---- phase A: :119-192 */
-#pragma omp parallel for schedule(dynamic, 4)
+    ShadowStats shTotal;
+#pragma omp parallel
+    {
+    ShadowStats sh;
+#pragma omp for schedule(dynamic, 4)
     for (int y = 0; y < H; y++) {
         for (int x = 0; x < W; x++) {
             int index = y * W + x;
@@ -874,7 +885,7 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
                 reservoir.update(Sample{Li, wi, dist}, lid, weight, rng.next());
             }
             Sample s = reservoir.s;
-            if (sceneOccluded(sc, is.pos, is.pos + s.wi * s.dist)) reservoir.w = 0.f;   /* :172-176 */
+            if (sceneOccluded(sc, is.pos, is.pos + s.wi * s.dist, &sh)) reservoir.w = 0.f;   /* :172-176 */
             if (!first && (reuse & 1)) {                                       /* :180-185 */
                 Resv temporal = findTemporalNeighbor(f, in, index);
                 if (!temporal.invalid()) reservoir.preClampedMerge(prm->temporalCap, temporal, rng.next());
@@ -889,6 +900,10 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
             c.status = 2; c.rng = rng.x; c.r = reservoir; c.n = is.norm; c.wo = is.wo; c.matId = is.matId;
         }
     }
+#pragma omp critical
+    { shTotal.rays += sh.rays; shTotal.nodes += sh.nodes; if (sh.maxNodes > shTotal.maxNodes) shTotal.maxNodes = sh.maxNodes; }
+    }
+    f->shadow = shTotal;
     /* ---- phase B: :196-230 */
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < H; y++) {
@@ -995,6 +1010,16 @@ const void* orc_frame_buffer(OrcFrame* f, int which) {
     }
     }
     return nullptr;
+}
+
+/* sampler.h:79-121 exposed directly (known-answer tests) */
+float orc_alias_build(int n, const float* values, void* outTable) {
+    std::vector<float> v(values, values + n);
+    std::vector<Alias> t;
+    float sum = 0.f;
+    buildAlias(v, t, sum);
+    memcpy(outTable, t.data(), sizeof(Alias) * n);
+    return sum;
 }
 
 void orc_rng_draws(int looper, int index, int n, float* out) {

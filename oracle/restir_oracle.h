@@ -105,6 +105,9 @@ void orc_last_trace_stats(OrcFrame*, uint64_t* nodesVisited, uint64_t* trisTeste
 /* RNG known-answer helper: n draws of sample1D for (looper, pixel index) */
 void orc_rng_draws(int looper, int index, int n, float* out);
 
+/* alias table of arbitrary weights (sampler.h:79-121); returns sumAll */
+float orc_alias_build(int n, const float* values, void* outTable);
+
 /* closest-hit / any-hit probes for unit tests */
 int  orc_intersect(const OrcScene*, const float* origin, const float* dir, float* outPosNormUv8, int* outMatId);
 int  orc_occluded(const OrcScene*, const float* x, const float* y);

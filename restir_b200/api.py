@@ -135,6 +135,11 @@ def lib() -> C.CDLL:
     L.rstr_frame_stream.argtypes = [vp]
     L.rstr_frame_halo_miss.argtypes = [vp, C.POINTER(C.c_uint)]
     L.rstr_frame_plane_row.argtypes = [vp, ip, ip, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.rstr_frame_copy_rows.argtypes = [vp, vp, ip, ip, ip]
+    L.rstr_frame_read_device.argtypes = [vp, ip, vp, C.c_size_t]
+    L.rstr_frame_mark.argtypes = [vp, ip]
+    L.rstr_frame_elapsed_ms.argtypes = [vp, ip, ip, C.POINTER(fp)]
+    L.rstr_frame_set_stream.argtypes = [vp, vp]
     L.rstr_host_alloc.restype = vp
     L.rstr_host_alloc.argtypes = [C.c_size_t]
     L.rstr_host_free.argtypes = [vp]
@@ -326,6 +331,23 @@ class Frame:
         p, nb = C.c_void_p(), C.c_size_t()
         _check(lib().rstr_frame_plane_row(self.f, PLANES[plane], row, C.byref(p), C.byref(nb)))
         return int(p.value or 0), int(nb.value)
+
+    def mark(self, slot: int) -> None:
+        _check(lib().rstr_frame_mark(self.f, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(0)
+        _check(lib().rstr_frame_elapsed_ms(self.f, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def set_stream(self, stream: int) -> None:
+        _check(lib().rstr_frame_set_stream(self.f, C.c_void_p(stream)))
+
+    def copy_rows_from(self, src: "Frame", plane: str, row0: int, row1: int) -> None:
+        _check(lib().rstr_frame_copy_rows(self.f, src.f, PLANES[plane], row0, row1))
+
+    def read_into_device(self, name: str, dev_ptr: int, nbytes: int) -> None:
+        _check(lib().rstr_frame_read_device(self.f, FRAME_BUFFERS[name], C.c_void_p(dev_ptr), nbytes))
 
     def read(self, name: str) -> np.ndarray:
         P = self.npix

@@ -54,6 +54,9 @@ struct RstrFrame {
     bool first = true;  // ReSTIRFirstFrame
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2 * RSTR_T_COUNT] = {};
+    cudaEvent_t xfer = nullptr;
+    cudaEvent_t marks[8] = {};
+    bool ownStream = true;
     bool ran[RSTR_T_COUNT] = {};
 };
 
@@ -229,7 +232,9 @@ int rstr_frame_destroy(RstrFrame* f) {
     cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->hit); cudaFree(f->ldr);
     cudaFree(f->haloMiss); cudaFree(f->scratch);
     for (auto& e : f->ev) if (e) cudaEventDestroy(e);
-    if (f->stream) cudaStreamDestroy(f->stream);
+    if (f->xfer) cudaEventDestroy(f->xfer);
+    for (auto& e : f->marks) if (e) cudaEventDestroy(e);
+    if (f->stream && f->ownStream) cudaStreamDestroy(f->stream);
     delete f;
     return RSTR_OK;
 }
@@ -273,6 +278,7 @@ int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     for (auto& ev : f->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->xfer, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         std::string m = std::string("rstr_frame_create: ") + cudaGetErrorString(e);
         rstr_frame_destroy(f);
@@ -410,7 +416,12 @@ static int ensureScratch(RstrFrame* f, size_t bytes) {
     return RSTR_OK;
 }
 
-int rstr_frame_read(RstrFrame* f, int which, void* host, size_t bytes) {
+static int frameReadImpl(RstrFrame* f, int which, void* host, size_t bytes, bool toDevice);
+int rstr_frame_read(RstrFrame* f, int which, void* host, size_t bytes) { return frameReadImpl(f, which, host, bytes, false); }
+// same conversion, but into DEVICE memory and without synchronising (stream-ordered): strip gather to GPU 0
+int rstr_frame_read_device(RstrFrame* f, int which, void* dev, size_t bytes) { return frameReadImpl(f, which, dev, bytes, true); }
+
+static int frameReadImpl(RstrFrame* f, int which, void* host, size_t bytes, bool toDevice) {
     if (!f || !host) return fail(RSTR_ERR_ARG, "rstr_frame_read: bad argument");
     const size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
     size_t elem = 0;
@@ -446,8 +457,8 @@ int rstr_frame_read(RstrFrame* f, int which, void* host, size_t bytes) {
         CU(cudaGetLastError());
         src = f->scratch;
     }
-    CU(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpyAsync(host, src, bytes, toDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!toDevice) CU(cudaStreamSynchronize(st));
     return RSTR_OK;
 }
 
@@ -458,6 +469,28 @@ int rstr_frame_stage_ms(RstrFrame* f, float* ms, int n) {
         ms[s] = 0.f;
         if (f->ran[s]) CU(cudaEventElapsedTime(&ms[s], f->ev[2 * s], f->ev[2 * s + 1]));
     }
+    return RSTR_OK;
+}
+
+// user timing marks on the frame's stream (bench.py: CUDA events on the stream the kernels are launched on)
+int rstr_frame_mark(RstrFrame* f, int slot) {
+    if (!f || slot < 0 || slot >= 8) return fail(RSTR_ERR_ARG, "rstr_frame_mark: bad argument");
+    if (!f->marks[slot]) CU(cudaEventCreate(&f->marks[slot]));
+    CU(cudaEventRecord(f->marks[slot], f->stream));
+    return RSTR_OK;
+}
+int rstr_frame_elapsed_ms(RstrFrame* f, int slotA, int slotB, float* ms) {
+    if (!f || !ms || slotA < 0 || slotA >= 8 || slotB < 0 || slotB >= 8 || !f->marks[slotA] || !f->marks[slotB]) return fail(RSTR_ERR_ARG, "rstr_frame_elapsed_ms: bad argument");
+    CU(cudaEventSynchronize(f->marks[slotB]));
+    CU(cudaEventElapsedTime(ms, f->marks[slotA], f->marks[slotB]));
+    return RSTR_OK;
+}
+// run the frame's work on a caller-owned stream (e.g. torch's current stream, so NCCL calls order naturally)
+int rstr_frame_set_stream(RstrFrame* f, void* stream) {
+    if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    CU(cudaStreamSynchronize(f->stream));
+    if (f->ownStream) { cudaStreamDestroy(f->stream); f->ownStream = false; }
+    f->stream = (cudaStream_t)stream;
     return RSTR_OK;
 }
 
@@ -482,6 +515,22 @@ int rstr_frame_plane_row(RstrFrame* f, int plane, int row, void** devPtr, size_t
     case RSTR_PLANE_RESV_TEMP: *devPtr = f->resvTemp + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
     default: return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: unknown plane");
     }
+    return RSTR_OK;
+}
+
+int rstr_frame_copy_rows(RstrFrame* dst, RstrFrame* src, int plane, int row0, int row1) {
+    if (!dst || !src || dst->W != src->W || row0 >= row1) return fail(RSTR_ERR_ARG, "rstr_frame_copy_rows: bad argument");
+    void *ps = nullptr, *pd = nullptr;
+    size_t rb = 0;
+    int rc = rstr_frame_plane_row(src, plane, row0, &ps, &rb);
+    if (rc) return rc;
+    rc = rstr_frame_plane_row(dst, plane, row0, &pd, &rb);
+    if (rc) return rc;
+    if (row1 > src->bufRow0 + src->bufRows || row1 > dst->bufRow0 + dst->bufRows) return fail(RSTR_ERR_ARG, "rstr_frame_copy_rows: rows not resident");
+    // order: after everything queued on src's stream, before anything queued later on dst's stream
+    CU(cudaEventRecord(src->xfer, src->stream));
+    CU(cudaStreamWaitEvent(dst->stream, src->xfer, 0));
+    CU(cudaMemcpyAsync(pd, ps, rb * (size_t)(row1 - row0), cudaMemcpyDefault, dst->stream));
     return RSTR_OK;
 }
 

@@ -61,6 +61,18 @@ RS_D bool distMaxMin(float a1, float a2, float b1, float b2, float& tMin) {   //
 }
 RS_D bool between(float x, float lo, float hi) { return x >= lo && x <= hi; }
 
+// A ray with |d_a| < 1e-6 makes the reference drop axis a's slab altogether (bvh.h:137-147), so it walks every box
+// of the sheet spanned by the other two axes -- tens of thousands of nodes for the 2-3 such pixels each frame has
+// (image centre column / horizon row), a multi-millisecond single-thread tail.  A triangle can only be hit inside
+// its box, so requiring the ray's a-coordinate over the box's [tMin,tMax] interval to overlap the box (padded for
+// rounding) prunes that sheet without changing which triangles are found.
+RS_D bool axisGuard(float o, float d, float lo, float hi, float t0, float t1) {
+    float ta = fmaxf(t0, 0.f);
+    float a0 = o + ta * d, a1 = o + t1 * d;
+    float pad = 1e-5f * (fabsf(o) + fabsf(lo) + fabsf(hi) + 1.f);
+    return fmaxf(a0, a1) >= lo - pad && fminf(a0, a1) <= hi + pad;
+}
+
 // bvh.h:85-157, all special cases (rare rays: axis-aligned or with a vanishing component)
 __device__ __noinline__ bool boxHitSlow(const RayT& r, f3 pMin, f3 pMax, float& tMin) {
     f3 ori = r.o;
@@ -92,9 +104,12 @@ __device__ __noinline__ bool boxHitSlow(const RayT& r, f3 pMin, f3 pMax, float& 
     float yz = tFar.z - tNear.y;
     float zx = tFar.x - tNear.z;
     float xy = tFar.y - tNear.x;
-    if ((r.flags & 4) && tDist.y + tDist.z > yz) return distMaxMin(tNear.y, tNear.z, tFar.y, tFar.z, tMin);
-    if ((r.flags & 8) && tDist.z + tDist.x > zx) return distMaxMin(tNear.z, tNear.x, tFar.z, tFar.x, tMin);
-    if ((r.flags & 16) && tDist.x + tDist.y > xy) return distMaxMin(tNear.x, tNear.y, tFar.x, tFar.y, tMin);
+    if ((r.flags & 4) && tDist.y + tDist.z > yz)
+        return distMaxMin(tNear.y, tNear.z, tFar.y, tFar.z, tMin) && axisGuard(ori.x, r.d.x, pMin.x, pMax.x, tMin, fminf(tFar.y, tFar.z));
+    if ((r.flags & 8) && tDist.z + tDist.x > zx)
+        return distMaxMin(tNear.z, tNear.x, tFar.z, tFar.x, tMin) && axisGuard(ori.y, r.d.y, pMin.y, pMax.y, tMin, fminf(tFar.z, tFar.x));
+    if ((r.flags & 16) && tDist.x + tDist.y > xy)
+        return distMaxMin(tNear.x, tNear.y, tFar.x, tFar.y, tMin) && axisGuard(ori.z, r.d.z, pMin.z, pMax.z, tMin, fminf(tFar.x, tFar.y));
     if (tDist.y + tDist.z > yz && tDist.z + tDist.x > zx && tDist.x + tDist.y > xy)
         return distMaxMin(fmaxf(tNear.x, tNear.y), tNear.z, fminf(tFar.x, tFar.y), tFar.z, tMin);
     return false;
@@ -149,15 +164,40 @@ RS_D Tri loadTri(const DevScene& s, int prim) {
 
 struct Hit { float t, bx, by; int prim; };
 
-struct StackEntry { int ref; float t; };
+// Traversal stack: the first RS_SMEM_STACK entries of every thread live in shared memory, laid out [entry][thread] so
+// that a lane always hits its own bank whatever its stack depth (divergent depths cost nothing); deeper entries
+// spill to a per-thread local array.
+#define RS_SMEM_STACK 24
+#define RS_BLOCK 128
+struct Stack {
+    int* sRef;      // &smemRef[0][tid]
+    float* sT;      // &smemT[0][tid]
+    int lRef[RS_STACK_DEPTH - RS_SMEM_STACK];
+    float lT[RS_STACK_DEPTH - RS_SMEM_STACK];
+    RS_D void push(int sp, int ref, float t) {
+        if (sp < RS_SMEM_STACK) { sRef[sp * RS_BLOCK] = ref; sT[sp * RS_BLOCK] = t; }
+        else { lRef[sp - RS_SMEM_STACK] = ref; lT[sp - RS_SMEM_STACK] = t; }
+    }
+    RS_D void pushRef(int sp, int ref) {
+        if (sp < RS_SMEM_STACK) sRef[sp * RS_BLOCK] = ref;
+        else lRef[sp - RS_SMEM_STACK] = ref;
+    }
+    RS_D int ref(int sp) const { return sp < RS_SMEM_STACK ? sRef[sp * RS_BLOCK] : lRef[sp - RS_SMEM_STACK]; }
+    RS_D float t(int sp) const { return sp < RS_SMEM_STACK ? sT[sp * RS_BLOCK] : lT[sp - RS_SMEM_STACK]; }
+};
+#define RS_DECLARE_STACK(name)                                         \
+    __shared__ int name##_ref[RS_SMEM_STACK][RS_BLOCK];                \
+    __shared__ float name##_t[RS_SMEM_STACK][RS_BLOCK];                \
+    Stack name;                                                        \
+    name.sRef = &name##_ref[0][threadIdx.x];                           \
+    name.sT = &name##_t[0][threadIdx.x]
 
 // scene.h:245-278 on the packed tree.  Children are visited in the reference's order for this ray; the deferred
 // child is re-tested against the current closest distance when popped (= the reference's test on arrival).
-RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h) {
+RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
     h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
     float tRoot;
     if (!(boxHit(r, mk3(s.rootMin[0], s.rootMin[1], s.rootMin[2]), mk3(s.rootMax[0], s.rootMax[1], s.rootMax[2]), tRoot) && tRoot < h.t)) return;
-    StackEntry stack[RS_STACK_DEPTH];
     int sp = 0;
     int cur = s.rootRef;
     for (;;) {
@@ -179,7 +219,7 @@ RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h) {
             bool goF = (swp ? hR : hL) && tF < h.t;
             bool goS = (swp ? hL : hR) && tS < h.t;
             if (goF) {
-                if (goS) { stack[sp].ref = second; stack[sp].t = tS; sp++; }
+                if (goS) { stack.push(sp, second, tS); sp++; }
                 cur = first;
                 continue;
             }
@@ -188,14 +228,14 @@ RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h) {
         bool found = false;
         while (sp > 0) {
             --sp;
-            if (stack[sp].t < h.t) { cur = stack[sp].ref; found = true; break; }
+            if (stack.t(sp) < h.t) { cur = stack.ref(sp); found = true; break; }
         }
         if (!found) break;
     }
 }
 
 // scene.h:286-316.  Any-hit: the answer does not depend on the visiting order.
-RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y) {
+RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y, Stack& stack) {
     const float Eps = 1e-4f;
     f3 dir = y - x;
     float dist = length(dir);
@@ -204,7 +244,6 @@ RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y) {
     dist -= Eps * 2.f;
     float tRoot;
     if (!(boxHit(r, mk3(s.rootMin[0], s.rootMin[1], s.rootMin[2]), mk3(s.rootMax[0], s.rootMax[1], s.rootMax[2]), tRoot) && tRoot < dist)) return false;
-    int stack[RS_STACK_DEPTH];
     int sp = 0;
     int cur = s.rootRef;
     for (;;) {
@@ -220,14 +259,14 @@ RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y) {
             bool goL = boxHit(r, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), tL) && tL < dist;
             bool goR = boxHit(r, mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), tR) && tR < dist;
             if (goL) {
-                if (goR) stack[sp++] = l.y;
+                if (goR) { stack.pushRef(sp, l.y); sp++; }
                 cur = l.x;
                 continue;
             }
             if (goR) { cur = l.y; continue; }
         }
         if (sp == 0) return false;
-        cur = stack[--sp];
+        cur = stack.ref(--sp);
     }
 }
 
@@ -347,6 +386,7 @@ RS_D f3 shadeReservoir(const DevScene& s, const Resv& r, int type, float metalli
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(128) k_gbuffer(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                  const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
+    RS_DECLARE_STACK(stack);
     int x, y;
     if (!pixelOf(f, x, y)) return;
     size_t li = planeIndex(f, x, y);
@@ -354,7 +394,7 @@ __global__ void __launch_bounds__(128) k_gbuffer(const __grid_constant__ DevScen
     cameraRay(cam, x, y, .5f, .5f, o, d);
     RayT r = makeRayT(o, d);
     Hit h;
-    traceClosest(s, r, h);
+    traceClosest(s, r, h, stack);
     if (h.prim >= 0) {
         Tri t = loadTri(s, h.prim);
         const float4* np = s.triNorm + 3 * (size_t)h.prim;
@@ -425,6 +465,7 @@ template <bool SPATIAL>
 __global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                   const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
                                                   int looper, int iter, int first) {
+    RS_DECLARE_STACK(stack);
     int x, y;
     if (!pixelOf(f, x, y)) return;
     size_t li = planeIndex(f, x, y);
@@ -437,7 +478,7 @@ __global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevSce
     cameraRay(cam, x, y, r0, r1, o, d);
     RayT ray = makeRayT(o, d);
     Hit h;
-    traceClosest(s, ray, h);
+    traceClosest(s, ray, h, stack);
     int status = 0;      // 0 miss, 1 emitter, 2 shaded
     f3 pos, nrm;
     int matId = -1, type = 0;
@@ -484,7 +525,7 @@ __global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevSce
         if (rnd * R.w < weight) { R.wi = wi; R.dist = dist; R.lightId = lid; }
     }
     // restir.cu:172-176.  With weight == 0 the test cannot change anything, so the ray is skipped.
-    if (R.w != 0.f && traceOccluded(s, pos, pos + R.wi * R.dist)) R.w = 0.f;
+    if (R.w != 0.f && traceOccluded(s, pos, pos + R.wi * R.dist, stack)) R.w = 0.f;
     if (!first && (prm.reuse & 1)) {                                                 // restir.cu:180-185
         Resv T = findTemporal(f, li, index);
         if (!resvInvalid(T)) {
@@ -553,6 +594,7 @@ __global__ void __launch_bounds__(128) k_restir_b(const __grid_constant__ DevSce
 // pathtrace.cu:279-328 with scene.h:427-459 (occlusion test BEFORE the facing test)
 __global__ void __launch_bounds__(128) k_ptdirect(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                   const __grid_constant__ CamDev cam, int looper, int iter) {
+    RS_DECLARE_STACK(stack);
     int x, y;
     if (!pixelOf(f, x, y)) return;
     size_t li = planeIndex(f, x, y);
@@ -565,7 +607,7 @@ __global__ void __launch_bounds__(128) k_ptdirect(const __grid_constant__ DevSce
     cameraRay(cam, x, y, r0, r1, o, d);
     RayT ray = makeRayT(o, d);
     Hit h;
-    traceClosest(s, ray, h);
+    traceClosest(s, ray, h, stack);
     f3 direct = mk3(0.f);
     if (h.prim >= 0) {
         Tri t = loadTri(s, h.prim);
@@ -594,7 +636,7 @@ __global__ void __launch_bounds__(128) k_ptdirect(const __grid_constant__ DevSce
             float sr = sqrtf(c3);
             float u = 1.f - sr, v = c2 * sr;
             f3 sampled = v1 * u + v2 * v + v0 * (1.f - u - v);
-            if (!traceOccluded(s, pos, sampled)) {
+            if (!traceOccluded(s, pos, sampled, stack)) {
                 f3 pts = sampled - pos;
                 if (!(dot(n, pts) > -1e-6f)) {
                     f3 Li = mk3(d4.x, d4.y, d4.z);

@@ -1,0 +1,96 @@
+"""Generates the committed golden fixtures from THE REFERENCE'S OWN CODE (oracle/_ref/libref_harness.so, i.e.
+/root/reference/src compiled with g++ by oracle/Makefile).  Run in the build container only:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Outputs (small, committed): tests/golden/*.npz.  The reference ships no golden vectors of its own
+(SURVEY.md section 4); these pin the oracle restatement and, through it, the CUDA path.
+"""
+import ctypes as C
+import os
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+import numpy as np
+
+import helpers
+from oracle.oracle import Oracle
+from restir_b200 import scenes
+
+
+def main():
+    ref = Oracle("reference")
+    # 1. RNG, alias known answers
+    rng = {"l%d_i%d" % (l, i): ref.rng_draws(l, i, 8) for l, i in ((7, 12345), (0, 0), (59, 2073599), (1023, 8294399))}
+    alias, total = ref.alias_build([1, 2, 3, 10])
+    alias2, total2 = ref.alias_build(np.linspace(0.1, 7.3, 37) ** 2)
+    np.savez_compressed(os.path.join(HERE, "known_answers.npz"), alias_prob=alias["prob"], alias_fail=alias["failId"], alias_sum=total,
+                        alias2_prob=alias2["prob"], alias2_fail=alias2["failId"], alias2_sum=total2, **{"rng_" + k: v for k, v in rng.items()})
+    # 2. host build outputs
+    for name, sd in helpers.test_scenes().items():
+        so = ref.scene(sd)
+        d = dict(boxes=so.boxes(), light_prim_ids=so.light_prim_ids(), light_radiance=so.light_radiance(),
+                 alias_prob=so.alias_table()["prob"], alias_fail=so.alias_table()["failId"], sum_power=so.sum_light_power())
+        for i in range(6):
+            d["mtbvh%d" % i] = so.mtbvh(i)
+        np.savez_compressed(os.path.join(HERE, "host_%s.npz" % name), **d)
+        so.close()
+    # 3. frame loops: 3 frames, orbiting camera, every reuse mode
+    for name, sd in helpers.test_scenes().items():
+        d = {}
+        for mode, reuse, radius in (("ris", 0, 5.0), ("temporal", 1, 5.0), ("spatial", 2, 5.0), ("st", 3, 5.0), ("st_r30", 3, 30.0)):
+            frames = helpers.run_oracle(ref, sd, 3, reuse, radius=radius)
+            for f, bufs in enumerate(frames):
+                for n, a in bufs.items():
+                    if n == "reservoir_temp" and not (reuse & 2):
+                        continue
+                    d["%s_f%d_%s" % (mode, f, n)] = a.view(np.uint8).reshape(a.shape[0], -1) if a.dtype.fields else a
+        np.savez_compressed(os.path.join(HERE, "frames_%s.npz" % name), **d)
+    # 4. PTDirect accumulation (2 iterations)
+    d = {}
+    for name, sd in helpers.test_scenes().items():
+        so = ref.scene(sd)
+        W, H = sd.resolution
+        fo = so.frame(W, H)
+        from oracle.oracle import make_camera
+        cam = make_camera(sd)
+        ref.lib.orc_camera_update(C.byref(cam))
+        for it in range(2):
+            fo.pathtrace_direct(cam, 100 + it, it)
+        d[name] = fo.buffer("radiance")
+    np.savez_compressed(os.path.join(HERE, "ptdirect.npz"), **d)
+    # 5. scene-file parser + flattening with a rotated / scaled / translated instance
+    tmp = tempfile.mkdtemp()
+    sd = scenes.cornell_box((48, 36), metal_tall_box=True)
+    path = scenes.write_scene_files(sd, tmp, "cornell_file")
+    txt = open(path).read()
+    # transform the first object; keep the rest at identity
+    txt = txt.replace("Translate 0 0 0\nRotate 0 0 0\nScale 1 1 1", "Translate 0.25 -0.125 0.5\nRotate 17.5 -33 8.25\nScale 1.5 0.75 1.125", 1)
+    txt = txt.replace(tmp + "/", "")      # relative OBJ paths: resolved against the scene file's directory
+    open(path, "w").write(txt)
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    rs = ref.lib.ref_scene_load_file(os.path.basename(path).encode())
+    os.chdir(cwd)
+    T = ref.lib.ref_scene_num_tris(rs)
+    cam = type(make_camera(sd))()
+    ref.lib.ref_scene_camera(rs, C.byref(cam))
+    files = {f: open(os.path.join(tmp, f)).read() for f in sorted(os.listdir(tmp))}
+    np.savez_compressed(
+        os.path.join(HERE, "scene_file.npz"),
+        vertices=Oracle._view(ref.lib.ref_scene_array(rs, 0), np.float32, (3 * T, 3)),
+        normals=Oracle._view(ref.lib.ref_scene_array(rs, 1), np.float32, (3 * T, 3)),
+        texcoords=Oracle._view(ref.lib.ref_scene_array(rs, 2), np.float32, (3 * T, 2)),
+        material_ids=Oracle._view(ref.lib.ref_scene_array(rs, 3), np.int32, (T,)),
+        materials=np.frombuffer(Oracle._view(ref.lib.ref_scene_array(rs, 4), np.dtype("V44"), (ref.lib.ref_scene_num_materials(rs),)).tobytes(), np.uint8),
+        camera=np.frombuffer(bytes(cam), np.uint8),
+        file_names=np.array(list(files.keys())), file_texts=np.array(list(files.values())),
+    )
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,98 @@
+"""Shared drivers for the parity tests: the same frame loop (main.cpp:146-185 with a fixed animation clock)
+run through the oracle (CPU) and through the C ABI (GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from oracle import oracle as orc_mod
+from restir_b200 import scenes
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GBUF = ("albedo", "normal", "matid", "depth", "motion")
+ALL_BUFS = GBUF + ("radiance", "reservoir", "reservoir_temp")
+
+
+def five_triangles() -> scenes.SceneData:
+    """SURVEY.md App. D probe (i): triangles i=0..4, x = 1.5 i: (x,0,0) (x+1,0,0) (x,1,i)."""
+    tris = []
+    for i in range(5):
+        x = 1.5 * i
+        tris += [(x, 0, 0), (x + 1, 0, 0), (x, 1, i)]
+    v = np.asarray(tris, np.float32)
+    return scenes.SceneData("five", v, scenes._face_normals(v), np.zeros((15, 2), np.float32), np.zeros(5, np.int32),
+                            scenes.make_materials([(scenes.LAMBERTIAN, (0.9, 0.9, 0.9), 0.0, 1.0)]), ["m0"],
+                            eye=(3.0, 0.5, 8.0), rotation=(-90.0, 0.0, 0.0), fovy=30.0, resolution=(32, 24))
+
+
+def test_scenes():
+    """name -> SceneData for the small parity cases."""
+    return {
+        "cornell": scenes.cornell_box((48, 36)),
+        "cornell_metal": scenes.cornell_box((48, 36), metal_tall_box=True),
+        "gen2000": scenes.procedural(1, 2000, 100, (48, 36)),
+        "five": five_triangles(),
+    }
+
+
+def run_oracle(orc, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=ALL_BUFS, light_index=False):
+    """Returns a list (per frame) of {buffer name: array}."""
+    W, H = sd.resolution
+    so = orc.scene(sd)
+    fo = so.frame(W, H)
+    base = orc_mod.make_camera(sd)
+    orc.lib.orc_camera_update(C.byref(base))
+    prm = orc_mod.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates)
+    out = []
+    for f in range(frames):
+        cam = orc_mod.orbit_camera(orc, base, f) if orbit else base
+        fo.gbuffer_render(cam)
+        fo.restir_direct(cam, prm, f, f if accumulate else 0)
+        names = list(want) + (["light_index"] if light_index else [])
+        out.append({n: fo.buffer(n) for n in names})
+        fo.gbuffer_update(cam)
+    fo.close()
+    so.close()
+    return out
+
+
+def run_gpu(rb, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=ALL_BUFS, light_index=False,
+            rows=None, halo=0, scene=None):
+    W, H = sd.resolution
+    sc = scene or rb.Scene.from_arrays(sd)
+    fr = sc.frame(W, H, rows=rows, halo=halo)
+    base = rb.Camera.from_scene(sd)
+    prm = rb.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates)
+    out = []
+    for f in range(frames):
+        cam = base.orbit(f) if orbit else base
+        fr.gbuffer_render(cam)
+        fr.restir_direct(cam, prm, f, f if accumulate else 0)
+        names = list(want) + (["light_index"] if light_index else [])
+        out.append({n: fr.read(n) for n in names})
+        fr.gbuffer_update(cam)
+    miss = fr.halo_miss()
+    fr.close()
+    if scene is None:
+        sc.close()
+    return out, miss
+
+
+def mismatches(a: np.ndarray, b: np.ndarray) -> int:
+    """Number of pixels whose bytes differ."""
+    av = np.ascontiguousarray(a).view(np.uint8).reshape(a.shape[0], -1)
+    bv = np.ascontiguousarray(b).view(np.uint8).reshape(b.shape[0], -1)
+    assert av.shape == bv.shape, (a.shape, a.dtype, b.shape, b.dtype)
+    return int((av != bv).any(1).sum())
+
+
+def assert_frames_equal(got, want, what=""):
+    assert len(got) == len(want)
+    for f, (g, w) in enumerate(zip(got, want)):
+        for n in w:
+            if n not in g:
+                continue
+            bad = mismatches(g[n], w[n])
+            assert bad == 0, "%s frame %d buffer %s: %d pixels differ" % (what, f, n, bad)

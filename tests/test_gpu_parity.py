@@ -1,0 +1,237 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the CPU oracle and the golden fixtures.
+
+Bar: bit-exact for every integer / index buffer (material id, motion index, reservoir M, selected light index) and,
+because the kernels keep the reference's fp32 operation order with FMA contraction off, also bit-exact for the fp32
+buffers (depth, normal, reservoir wi/dist/weight, radiance).  The only arithmetic that is NOT shared bit for bit
+with the CPU oracle is sinf/cosf of the spatial disk sample (CUDA libdevice vs glibc, <= 2 ulp): a neighbour pixel
+can flip when a coordinate lands within an ulp of an integer, so spatial modes allow MAX_TRIG_FLIP_FRACTION of
+pixels to differ; everything else allows zero.  The north star's floating-point tolerance (1e-4 relative per-pixel
+radiance, or mean relMSE <= 1e-5) is asserted on top.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from restir_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+G = helpers.GOLDEN
+MAX_TRIG_FLIP_FRACTION = 2e-5
+REL_TOL = 1e-4          # BASELINE.json north_star: per-pixel radiance within 1e-4 relative
+RELMSE_TOL = 1e-5       # ... or mean relMSE <= 1e-5
+
+MODES = (("ris", 0, 5.0), ("temporal", 1, 5.0), ("spatial", 2, 5.0), ("st", 3, 5.0), ("st_r30", 3, 30.0))
+
+
+def check(got, want, reuse, what):
+    for f, (g, w) in enumerate(zip(got, want)):
+        P = next(iter(w.values())).shape[0]
+        allowed = int(np.ceil(MAX_TRIG_FLIP_FRACTION * P)) if (reuse & 2) else 0
+        for n in w:
+            bad = helpers.mismatches(g[n], w[n])
+            lim = allowed if n in ("radiance",) else 0
+            if n in ("reservoir", "reservoir_temp", "light_index") and (reuse & 2) and f > 0:
+                lim = allowed       # a flipped neighbour choice propagates into later history
+            assert bad <= lim, "%s frame %d buffer %s: %d pixels differ (allowed %d)" % (what, f, n, bad, lim)
+        a, b = g["radiance"].astype(np.float64), w["radiance"].astype(np.float64)
+        relmse = np.mean(((a - b) ** 2).sum(1) / (b.sum(1) ** 2 + 1e-3))
+        assert relmse <= RELMSE_TOL, "%s frame %d relMSE %.3g" % (what, f, relmse)
+        same = ~(np.ascontiguousarray(g["radiance"]).view(np.uint8).reshape(P, -1) != np.ascontiguousarray(w["radiance"]).view(np.uint8).reshape(P, -1)).any(1)
+        assert np.all(np.abs(a[same] - b[same]) <= REL_TOL * np.abs(b[same]) + 1e-12)
+
+
+@pytest.mark.parametrize("name", ["cornell", "cornell_metal", "gen2000", "five"])
+def test_against_golden_fixtures(gpu, name):
+    """Fixtures were produced by the reference's own code (tests/golden/make_golden.py)."""
+    sd = helpers.test_scenes()[name]
+    g = np.load(os.path.join(G, "frames_%s.npz" % name))
+    for mode, reuse, radius in MODES:
+        frames, miss = helpers.run_gpu(gpu, sd, 3, reuse, radius=radius)
+        assert miss == 0
+        want = [{n: g["%s_f%d_%s" % (mode, f, n)] for n in frames[f] if "%s_f%d_%s" % (mode, f, n) in g.files} for f in range(3)]
+        check(frames, want, reuse, "%s/%s vs golden" % (name, mode))
+
+
+@pytest.mark.parametrize("reuse", [0, 1, 2, 3])
+def test_cornell_800_against_oracle(gpu, port_oracle, reuse):
+    """BASELINE config 1 geometry (800x800 Cornell); every reuse mode, 3 frames of the orbit."""
+    sd = scenes.cornell_box((800, 800))
+    got, miss = helpers.run_gpu(gpu, sd, 3, reuse, light_index=True)
+    want = helpers.run_oracle(port_oracle, sd, 3, reuse, light_index=True)
+    assert miss == 0
+    check(got, want, reuse, "cornell800 reuse=%d" % reuse)
+
+
+def test_config2_slice_against_oracle(gpu, port_oracle):
+    """BASELINE config 2 at reduced length: Cornell 1920x1080 spatiotemporal, radius 30, first 4 frames."""
+    sd = scenes.cornell_box((1920, 1080), metal_tall_box=True)
+    got, miss = helpers.run_gpu(gpu, sd, 4, 3, radius=30.0, light_index=True)
+    want = helpers.run_oracle(port_oracle, sd, 4, 3, radius=30.0, light_index=True)
+    assert miss == 0
+    check(got, want, 3, "config2")
+
+
+@pytest.mark.parametrize("k,cap,cands,radius", [(1, 20, 32, 5.0), (8, 4, 16, 12.0), (0, 2, 1, 5.0), (5, 20, 0, 5.0)])
+def test_knob_sweep_many_light(gpu, port_oracle, k, cap, cands, radius):
+    """BASELINE config 3/5 style scene at a size the oracle finishes in seconds; knobs the reference hard-codes."""
+    sd = scenes.procedural(1, 20000, 1000, (320, 180))
+    got, miss = helpers.run_gpu(gpu, sd, 3, 3, radius=radius, k=k, cap=cap, candidates=cands, accumulate=True, light_index=True)
+    want = helpers.run_oracle(port_oracle, sd, 3, 3, radius=radius, k=k, cap=cap, candidates=cands, accumulate=True, light_index=True)
+    assert miss == 0
+    check(got, want, 3, "sweep k=%d cap=%d cands=%d" % (k, cap, cands))
+
+
+def test_ptdirect_against_golden_and_oracle(gpu, port_oracle):
+    import ctypes as C
+
+    from oracle.oracle import make_camera
+
+    g = np.load(os.path.join(G, "ptdirect.npz"))
+    for name, sd in helpers.test_scenes().items():
+        sc = gpu.Scene.from_arrays(sd)
+        fr = sc.frame(*sd.resolution)
+        cam = gpu.Camera.from_scene(sd)
+        for it in range(2):
+            fr.pathtrace_direct(cam, 100 + it, it)
+        assert helpers.mismatches(fr.read("radiance"), g[name]) == 0, name
+        fr.close()
+        sc.close()
+    sd = scenes.procedural(4, 20000, 1000, (320, 180))
+    sc, so = gpu.Scene.from_arrays(sd), port_oracle.scene(sd)
+    fr, fo = sc.frame(320, 180), so.frame(320, 180)
+    cam, oc = gpu.Camera.from_scene(sd), make_camera(sd)
+    port_oracle.lib.orc_camera_update(C.byref(oc))
+    for it in range(3):
+        fr.pathtrace_direct(cam, it, it)
+        fo.pathtrace_direct(oc, it, it)
+    assert helpers.mismatches(fr.read("radiance"), fo.buffer("radiance")) == 0
+
+
+def test_edge_cases(gpu, port_oracle):
+    """Ragged resolutions, single-triangle scene, no lights, camera seeing nothing, axis-aligned primary rays,
+    dielectric surfaces."""
+    # (a) resolution that is not a multiple of the 16x8 block tile
+    sd = scenes.cornell_box((37, 23), metal_tall_box=True)
+    got, _ = helpers.run_gpu(gpu, sd, 3, 3)
+    check(got, helpers.run_oracle(port_oracle, sd, 3, 3), 3, "ragged")
+    # (b) one emissive triangle only (root of the BVH is a leaf)
+    v = np.asarray([(-1, 0, -2), (1, 0, -2), (0, 1.5, -2)], np.float32)
+    one = scenes.SceneData("one", v, scenes._face_normals(v), np.zeros((3, 2), np.float32), np.zeros(1, np.int32),
+                           scenes.make_materials([(scenes.LIGHT, (5, 5, 5), 0.0, 1.0)]), ["l"], eye=(0, 0.5, 2), rotation=(-90, 0, 0), fovy=30.0, resolution=(40, 32))
+    got, _ = helpers.run_gpu(gpu, one, 2, 3)
+    check(got, helpers.run_oracle(port_oracle, one, 2, 3), 3, "single triangle")
+    # (c) no lights at all
+    five = helpers.five_triangles()
+    got, _ = helpers.run_gpu(gpu, five, 2, 3)
+    check(got, helpers.run_oracle(port_oracle, five, 2, 3), 3, "no lights")
+    # (d) camera looking away from everything
+    away = scenes.cornell_box((48, 36))
+    away.rotation = (90.0, 0.0, 0.0)
+    got, _ = helpers.run_gpu(gpu, away, 2, 3)
+    want = helpers.run_oracle(port_oracle, away, 2, 3)
+    check(got, want, 3, "all miss")
+    assert (want[0]["matid"] == -1).all()
+    # (e) odd resolution => the centre pixel's primary ray is exactly axis aligned (bvh.h:91-123 special cases);
+    #     plus a camera looking straight down (-y)
+    axis = scenes.cornell_box((33, 33))
+    got, _ = helpers.run_gpu(gpu, axis, 2, 3, orbit=False)
+    check(got, helpers.run_oracle(port_oracle, axis, 2, 3, orbit=False), 3, "axis-aligned centre ray")
+    down = scenes.cornell_box((33, 33))
+    down.eye, down.rotation = (0.05, 1.9, 0.02), (-90.0, -89.99, 0.0)
+    got, _ = helpers.run_gpu(gpu, down, 2, 3, orbit=False)
+    check(got, helpers.run_oracle(port_oracle, down, 2, 3, orbit=False), 3, "looking down")
+    # (f) dielectric tall box (delta BSDF: evaluates to zero, normal not flipped; restir.cu:150-153)
+    glass = scenes.cornell_box((64, 48))
+    glass.materials[4]["type"] = scenes.DIELECTRIC
+    got, _ = helpers.run_gpu(gpu, glass, 2, 3)
+    check(got, helpers.run_oracle(port_oracle, glass, 2, 3), 3, "dielectric")
+
+
+def test_reset_and_determinism(gpu):
+    sd = scenes.cornell_box((160, 120))
+    a, _ = helpers.run_gpu(gpu, sd, 3, 3)
+    b, _ = helpers.run_gpu(gpu, sd, 3, 3)
+    helpers.assert_frames_equal(a, b, "run-to-run")
+    # ReSTIRReset: the frame after a reset ignores history exactly like a first frame (restir.cu:180, 516)
+    sc = gpu.Scene.from_arrays(sd)
+    fr = sc.frame(160, 120)
+    cam = gpu.Camera.from_scene(sd)
+    prm = gpu.default_params(reuse=1)
+    fr.gbuffer_render(cam); fr.restir_direct(cam, prm, 5); fr.gbuffer_update(cam)
+    first = fr.read("radiance")
+    fr.gbuffer_render(cam); fr.restir_direct(cam, prm, 6); fr.gbuffer_update(cam)
+    fr.reset()
+    fr.gbuffer_render(cam); fr.restir_direct(cam, prm, 5); fr.gbuffer_update(cam)
+    assert helpers.mismatches(fr.read("radiance"), first) == 0
+    fr.close(); sc.close()
+
+
+def test_strips_equal_full_frame_at_full_size(gpu):
+    """Size-independent property at BASELINE's full 1080p size: rendering the image as horizontal strips with halo
+    rows (the multi-GPU decomposition) gives bit-identical buffers to the single full frame."""
+    sd = scenes.procedural(1, 200000, 10000, (1920, 1080))
+    sc = gpu.Scene.from_arrays(sd)
+    W, H = sd.resolution
+    base = gpu.Camera.from_scene(sd)
+    prm = gpu.default_params(reuse=3, radius=30.0)
+    full = sc.frame(W, H)
+    strips = [sc.frame(W, H, rows=(r0, r1), halo=40) for r0, r1 in ((0, 270), (270, 540), (540, 810), (810, 1080))]
+    for k in range(3):
+        cam = base.orbit(k)
+        full.gbuffer_render(cam); full.restir_direct(cam, prm, k); full.gbuffer_update(cam)
+        for s in strips:
+            s.gbuffer_render(cam); s.restir_phase_a(cam, prm, k)
+        exchange_halos(gpu, strips, "resv_temp")
+        for s in strips:
+            s.restir_phase_b(cam, prm, k)
+        exchange_halos(gpu, strips, "resv_history")
+        for s in strips:
+            s.gbuffer_update(cam)
+        for n in ("matid", "motion", "depth", "radiance", "reservoir", "light_index"):
+            whole = full.read(n)
+            parts = np.concatenate([s.read(n) for s in strips])
+            assert helpers.mismatches(whole, parts) == 0, "frame %d %s" % (k, n)
+    assert all(s.halo_miss() == 0 for s in strips)
+    # sanity of the full-size frame itself: M bounds (restir.cu:3, restir.h:96-102) and finite, non-negative weights
+    r = full.read("reservoir")
+    assert r["M"].min() >= 0 and r["M"].max() <= 32 + 19 * 32
+    assert np.isfinite(r["w"]).all() and (r["w"] >= 0).all()
+    for s in strips:
+        s.close()
+    full.close(); sc.close()
+
+
+def exchange_halos(gpu, strips, plane):
+    """Single-process form of the neighbour exchange: each strip's edge rows are copied into the halo rows of the
+    strips above / below (rstr_frame_copy_rows; the multi-process version sends the same rows over NCCL)."""
+    for i, s in enumerate(strips):
+        for j in (i - 1, i + 1):
+            if j < 0 or j >= len(strips):
+                continue
+            d = strips[j]
+            lo = max(s.rows[0], d.rows[0] - d.halo)
+            hi = min(s.rows[1], d.rows[1] + d.halo)
+            if lo < hi:
+                d.copy_rows_from(s, plane, lo, hi)
+    for s in strips:
+        s.sync()
+
+
+def test_end_to_end_host_call(gpu):
+    """rstr_render_frame_host: camera in, tone-mapped 8-bit image out (copyImageToPBO semantics, pathtrace.cu:30-56)."""
+    sd = scenes.cornell_box((320, 240))
+    sc = gpu.Scene.from_arrays(sd)
+    fr = sc.frame(320, 240)
+    cam = gpu.Camera.from_scene(sd)
+    out = gpu.pinned_empty(320 * 240 * 4)
+    fr.render_frame_host(cam, gpu.default_params(reuse=3), 0, 0, gpu.TONEMAP_ACES, out)
+    ldr = out.reshape(-1, 4).copy()
+    hdr = fr.read("radiance").astype(np.float64)
+    c = (hdr * (hdr * 2.51 + 0.03)) / (hdr * (hdr * 2.43 + 0.59) + 0.14)
+    want = np.clip((np.power(np.maximum(c, 0), 1 / 2.2) * 255).astype(np.int64), 0, 255)
+    assert np.abs(ldr[:, :3].astype(np.int64) - want).max() <= 1 and (ldr[:, 3] == 0).all()
+    assert ldr[:, :3].max() > 100
+    gpu.pinned_free(out)
+    fr.close(); sc.close()

@@ -1,0 +1,116 @@
+"""CPU: the product's host layer (C++ behind the C ABI) -- scene build, scene-file parser, camera -- against the
+oracle and the golden fixtures; and the C-ABI surface itself.  No GPU: no compute entry point is called."""
+import ctypes as C
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+import restir_b200 as rb
+from restir_b200 import scenes
+
+G = helpers.GOLDEN
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = rb.lib()
+    hdr = open(os.path.join(ROOT, "include", "restir_b200.h")).read()
+    names = set(re.findall(r"\b(rstr_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 25
+    for n in sorted(names):
+        assert hasattr(L, n), "librestir_b200.so does not export %s" % n
+
+
+def test_struct_layouts():
+    assert C.sizeof(rb.api.RstrCamera) == 196 and rb.api.RstrCamera.rotationMatInv.offset == 84 and rb.api.RstrCamera.lensRadius.offset == 184
+    assert scenes.MATERIAL_DTYPE.itemsize == 44 and rb.api.RESERVOIR_DTYPE.itemsize == 36
+    assert C.sizeof(rb.RstrParams) == 20
+
+
+@pytest.mark.parametrize("name", ["cornell", "cornell_metal", "gen2000", "five"])
+def test_host_build_matches_golden_and_oracle(port_oracle, name):
+    sd = helpers.test_scenes()[name]
+    g = np.load(os.path.join(G, "host_%s.npz" % name))
+    sc = rb.Scene.from_arrays(sd)
+    assert sc.info.numTris == sd.num_tris and sc.info.bvhSize == 2 * sd.num_tris - 1
+    assert np.array_equal(sc.read("boxes").view(np.uint32), g["boxes"].view(np.uint32))
+    for i in range(6):
+        assert np.array_equal(sc.read("mtbvh", i), g["mtbvh%d" % i]), "ordering %d" % i
+    assert np.array_equal(sc.read("light_prim_ids"), g["light_prim_ids"])
+    assert np.array_equal(sc.read("light_radiance"), g["light_radiance"])
+    al = sc.read("alias")
+    assert np.array_equal(al["prob"].view(np.uint32), g["alias_prob"].view(np.uint32)) and np.array_equal(al["failId"], g["alias_fail"])
+    if sc.info.numLights:
+        assert sc.info.sumLightPower == float(g["sum_power"])
+    so = port_oracle.scene(sd)
+    assert sc.info.bvhDepth >= 1 and np.array_equal(sc.read("boxes").view(np.uint32), so.boxes().view(np.uint32))
+    sc.close()
+
+
+def test_host_build_large_matches_oracle(port_oracle):
+    sd = scenes.procedural(2, 60000, 3000, (64, 48))
+    sc = rb.Scene.from_arrays(sd)
+    so = port_oracle.scene(sd)
+    assert np.array_equal(sc.read("boxes").view(np.uint32), so.boxes().view(np.uint32))
+    for i in (0, 3, 5):
+        assert np.array_equal(sc.read("mtbvh", i), so.mtbvh(i))
+    assert np.array_equal(sc.read("alias").view(np.uint8), so.alias_table().view(np.uint8))
+    sc.close()
+
+
+def test_camera_update_matches_oracle(port_oracle):
+    from oracle.oracle import make_camera, orbit_camera
+
+    for sd in helpers.test_scenes().values():
+        cam = rb.Camera.from_scene(sd)
+        oc = make_camera(sd)
+        port_oracle.lib.orc_camera_update(C.byref(oc))
+        assert bytes(cam)[:120] == bytes(oc)[:120] and bytes(cam)[184:] == bytes(oc)[184:]
+        for k in (1, 17, 59):
+            assert bytes(cam.orbit(k))[:120] == bytes(orbit_camera(port_oracle, oc, k))[:120]
+
+
+def test_scene_file_parser_matches_reference_fixture():
+    g = np.load(os.path.join(G, "scene_file.npz"))
+    tmp = tempfile.mkdtemp()
+    for n, t in zip(g["file_names"], g["file_texts"]):
+        open(os.path.join(tmp, str(n)), "w").write(str(t))
+    sc = rb.Scene.from_file(os.path.join(tmp, "cornell_file.txt"))
+    for n in ("vertices", "normals", "texcoords", "material_ids"):
+        assert np.array_equal(sc.read(n).view(np.uint32), g[n].view(np.uint32)), n
+    assert sc.read("materials").tobytes() == g["materials"].tobytes()
+    cam = g["camera"].tobytes()
+    assert bytes(sc.camera)[:120] == cam[:120] and bytes(sc.camera)[184:] == cam[184:]
+    sc.close()
+
+
+def test_scene_file_errors_are_reported_not_fatal():
+    tmp = tempfile.mkdtemp()
+    with pytest.raises(rb.RestirError):
+        rb.Scene.from_file(os.path.join(tmp, "missing.txt"))
+    p = os.path.join(tmp, "bad.txt")
+    open(p, "w").write("Object 0\nnope.obj\nMaterial Null\nScale 1 1 1\n\n")
+    with pytest.raises(rb.RestirError):
+        rb.Scene.from_file(p)
+    open(p, "w").write("Camera\nResolution 8 8\nFovY 20\nLensRadius 0\nFocalDist 1\nApertureMask Null\nSample 1\nDepth 1\nFile x\nEye 0 0 0\n\n")
+    with pytest.raises(rb.RestirError):      # no mesh data (scene.cpp:192-195 exits; here an error code)
+        rb.Scene.from_file(p)
+
+
+def test_bad_arguments():
+    sd = helpers.test_scenes()["five"]
+    bad = scenes.SceneData(sd.name, sd.vertices, sd.normals, sd.texcoords, np.full(5, 7, np.int32), sd.materials, sd.material_names)
+    with pytest.raises(rb.RestirError):
+        rb.Scene.from_arrays(bad)
+
+
+def test_scene_generators_are_deterministic():
+    a, b = scenes.procedural(1, 5000, 300), scenes.procedural(1, 5000, 300)
+    assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.material_ids, b.material_ids)
+    assert a.num_tris == 5000 and a.num_lights == 300
+    c = scenes.cornell_box()
+    assert c.num_tris == 36 and c.num_lights == 2
