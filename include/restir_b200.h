@@ -86,8 +86,10 @@ typedef struct RstrSceneDesc {
 typedef struct RstrSceneInfo {
     int numTris, numLights, bvhSize, bvhDepth, numMaterials;
     float sumLightPower;
-    double buildSeconds;       /* host BVH + tables */
+    double buildSeconds;       /* host: reference-identical BVH + tables + traced BVH */
     size_t deviceBytes;
+    int tracedBvhDepth;        /* depth of the binned-SAH tree the kernels trace */
+    double tracedBuildSeconds;
 } RstrSceneInfo;
 
 typedef struct RstrScene RstrScene;
@@ -134,6 +136,14 @@ int rstr_scene_load_file(const char* path, RstrScene**, RstrCamera* cameraOut);
 /* replaces Scene::clear() + DevScene::destroy() (scene.cpp:217-220, 511-532) */
 int rstr_scene_destroy(RstrScene*);
 int rstr_scene_info(const RstrScene*, RstrSceneInfo*);
+/* 0 (default): rays are traced through a binned-SAH tree; rays whose outcome depends on the reference's visiting order
+ * (two hits within a few ulps of each other) or on its non-conservative near-axis box test (bvh.h:91-123) are
+ * detected and re-traced with the reference-order walk.  1: every ray walks the reference tree in the reference's
+ * order with its exact box predicate (validation mode, ~2x slower). */
+int rstr_scene_set_traversal(RstrScene*, int mode);
+/* rays re-traced with the reference-order walk since the scene was created / last reset (instrumentation);
+ * count[4] = {near-axis rays, closest-hit near ties, closest hit on a leaf-box rim, shadow rays with rim hits only} */
+int rstr_scene_fallback_rays(RstrScene*, unsigned long long* count4, int reset);
 int rstr_scene_read(const RstrScene*, int which, void* host, size_t bytes);
 
 /* replaces Camera::update() (sceneStructs.h:88-102) */

@@ -76,6 +76,8 @@ class RstrSceneInfo(C.Structure):
         ("sumLightPower", C.c_float),
         ("buildSeconds", C.c_double),
         ("deviceBytes", C.c_size_t),
+        ("tracedBvhDepth", C.c_int),
+        ("tracedBuildSeconds", C.c_double),
     ]
 
 
@@ -114,6 +116,8 @@ def lib() -> C.CDLL:
     L.rstr_scene_destroy.argtypes = [vp]
     L.rstr_scene_info.argtypes = [vp, C.POINTER(RstrSceneInfo)]
     L.rstr_scene_read.argtypes = [vp, ip, vp, C.c_size_t]
+    L.rstr_scene_set_traversal.argtypes = [vp, ip]
+    L.rstr_scene_fallback_rays.argtypes = [vp, C.POINTER(C.c_ulonglong), ip]
     L.rstr_camera_update.argtypes = [C.POINTER(RstrCamera)]
     L.rstr_frame_create.argtypes = [vp, ip, ip, C.POINTER(vp)]
     L.rstr_frame_create_strip.argtypes = [vp, ip, ip, ip, ip, ip, C.POINTER(vp)]
@@ -242,6 +246,15 @@ class Scene:
         if self.h:
             lib().rstr_scene_destroy(self.h)
             self.h = None
+
+    def set_traversal(self, exact: bool) -> None:
+        """False (default): binned-SAH tree + rank tie-break; True: reference-order walk for every ray."""
+        _check(lib().rstr_scene_set_traversal(self.h, 1 if exact else 0))
+
+    def fallback_rays(self, reset: bool = True) -> dict:
+        v = (C.c_ulonglong * 4)()
+        _check(lib().rstr_scene_fallback_rays(self.h, v, 1 if reset else 0))
+        return dict(near_axis=int(v[0]), near_tie=int(v[1]), rim_closest=int(v[2]), rim_shadow=int(v[3]))
 
     def read(self, name: str, ordering: int = 0) -> np.ndarray:
         T, L, N = self.info.numTris, self.info.numLights, self.info.bvhSize

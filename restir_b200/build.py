@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librestir_b200.so")
-SOURCES = ["capi.cu", "kernels.cu", "scene_host.cpp", "scene_file.cpp"]
+SOURCES = ["capi.cu", "kernels.cu", "scene_host.cpp", "scene_file.cpp", "bvh_fast.cpp"]
 HEADERS = ["kernels.h", "device_types.h", "scene_host.h", "vecmath.h", os.path.join("..", "..", "include", "restir_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"

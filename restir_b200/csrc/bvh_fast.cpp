@@ -1,0 +1,179 @@
+// bvh_fast.cpp -- the acceleration structure the B200 kernels actually walk.
+//
+// The reference's tree (bvh.cpp:10-131) has to be REPRODUCED bit for bit (it is part of the host-facing surface and
+// fixes the tie-break order of coincident hits), but it is a poor structure to trace: its "SAH" compares single
+// neighbouring buckets (bvh.cpp:96-106), it stores one triangle per leaf and is 54-63 levels deep on the benchmark
+// scenes (~160 box tests per primary ray).  Hit results do not depend on the tree, only on
+//   (a) the triangle test arithmetic (intersections.h:17-53, kept exactly), and
+//   (b) which of several hits at (nearly) the same distance is kept: that follows the reference's visiting order and
+//       box-distance pruning (scene.h:260,267) -> such rays are detected during the walk and re-traced in reference order.
+// So the kernels trace a separately built binned-SAH BVH2 (all three axes, 32 bins, <= 4 triangles per leaf, boxes
+// padded by a few ulps so that the FMA slab test stays conservative w.r.t. the exact triangle test) and fall back to
+// the reference-order walk only for the rays whose reference box test is not a conservative slab test (|d_a| > 1-1e-6,
+// bvh.h:91-123).
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+
+#include "scene_host.h"
+
+namespace rs {
+
+namespace {
+
+struct FBox {
+    float lo[3], hi[3];
+    void reset() { lo[0] = lo[1] = lo[2] = FLT_MAX; hi[0] = hi[1] = hi[2] = -FLT_MAX; }
+    void grow(const FBox& b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    void grow(const float* p) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    float halfArea() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+struct Ref { FBox b; float c[3]; int prim; };
+
+struct FastBuilder {
+    static const int NBINS = 32;
+    static const int MAX_LEAF = 4;
+    static const int TASK_MIN = 4096;
+    std::vector<Ref> refs;
+    std::vector<FastNode>& nodes;
+    std::vector<int>& order;
+    std::atomic<int> maxDepth{0};
+
+    FastBuilder(std::vector<FastNode>& n, std::vector<int>& o) : nodes(n), order(o) {}
+
+    static int leafRef(int first, int count) { return (int)(0x80000000u | ((unsigned)(count - 1) << 27) | (unsigned)first); }
+
+    // builds the subtree over refs[start,end) and returns the child reference; the subtree's box goes to `box`
+    int build(int start, int end, int depth, FBox& box) {
+        const int n = end - start;
+        FBox cb;
+        box.reset(); cb.reset();
+        for (int i = start; i < end; i++) { box.grow(refs[i].b); cb.grow(refs[i].c); }
+        int d = maxDepth.load(std::memory_order_relaxed);
+        while (depth > d && !maxDepth.compare_exchange_weak(d, depth)) {}
+        auto makeLeaf = [&]() {
+            for (int i = start; i < end; i++) order[i] = refs[i].prim;
+            return leafRef(start, n);
+        };
+        if (n == 1) return makeLeaf();
+        // binned SAH over the three axes
+        float bestCost = FLT_MAX;
+        int bestAxis = -1, bestBin = -1;
+        const float parentArea = box.halfArea();
+        for (int axis = 0; axis < 3; axis++) {
+            float lo = cb.lo[axis], ext = cb.hi[axis] - cb.lo[axis];
+            if (!(ext > 0.f)) continue;
+            FBox bb[NBINS];
+            int cnt[NBINS];
+            for (int b = 0; b < NBINS; b++) { bb[b].reset(); cnt[b] = 0; }
+            const float scale = NBINS / ext;
+            for (int i = start; i < end; i++) {
+                int b = std::min(NBINS - 1, std::max(0, (int)((refs[i].c[axis] - lo) * scale)));
+                bb[b].grow(refs[i].b); cnt[b]++;
+            }
+            float rightArea[NBINS];
+            int rightCnt[NBINS];
+            FBox acc; acc.reset();
+            int c = 0;
+            for (int b = NBINS - 1; b > 0; b--) { acc.grow(bb[b]); c += cnt[b]; rightArea[b] = acc.halfArea(); rightCnt[b] = c; }
+            acc.reset(); c = 0;
+            for (int b = 0; b < NBINS - 1; b++) {
+                acc.grow(bb[b]); c += cnt[b];
+                if (c == 0 || rightCnt[b + 1] == 0) continue;
+                float cost = acc.halfArea() * c + rightArea[b + 1] * rightCnt[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+            }
+        }
+        // leaf when small and not worth splitting (traversal step ~ 1 triangle test)
+        if (n <= MAX_LEAF) {
+            float leafCost = (float)n * parentArea;
+            float splitCost = bestAxis < 0 ? FLT_MAX : 1.0f * parentArea + bestCost;
+            if (leafCost <= splitCost) return makeLeaf();
+        }
+        int mid;
+        if (bestAxis < 0) {                       // coincident centroids: split the range in the middle
+            mid = start + n / 2;
+        } else {
+            const float lo = cb.lo[bestAxis], scale = NBINS / (cb.hi[bestAxis] - cb.lo[bestAxis]);
+            auto it = std::partition(refs.begin() + start, refs.begin() + end, [&](const Ref& r) {
+                int b = std::min(NBINS - 1, std::max(0, (int)((r.c[bestAxis] - lo) * scale)));
+                return b <= bestBin;
+            });
+            mid = (int)(it - refs.begin());
+            if (mid == start || mid == end) mid = start + n / 2;
+        }
+        const int me = mid - 1;                   // every internal node has a distinct split position: deterministic, subtree-local index
+        FBox lb, rb;
+        int l, r;
+        if (n > TASK_MIN) {
+#pragma omp task default(shared)
+            l = build(start, mid, depth + 1, lb);
+            r = build(mid, end, depth + 1, rb);
+#pragma omp taskwait
+        } else {
+            l = build(start, mid, depth + 1, lb);
+            r = build(mid, end, depth + 1, rb);
+        }
+        FastNode& nd = nodes[me];
+        // pad: keeps the FMA slab test conservative w.r.t. the exact Moller-Trumbore arithmetic (flat boxes!)
+        auto put = [&](const FBox& b, float* mn, float* mx) {
+            for (int a = 0; a < 3; a++) {
+                float pad = 4e-6f * std::max(fabsf(b.lo[a]), fabsf(b.hi[a])) + 1e-7f;
+                mn[a] = b.lo[a] - pad; mx[a] = b.hi[a] + pad;
+            }
+        };
+        put(lb, nd.lmin, nd.lmax);
+        put(rb, nd.rmin, nd.rmax);
+        nd.left = l; nd.right = r; nd.pad[0] = nd.pad[1] = 0;
+        return me;
+    }
+};
+
+}  // namespace
+
+void buildFastBVH(HostScene& hs) {
+    auto t0 = std::chrono::steady_clock::now();
+    const int T = hs.T;
+    hs.fastNodes.assign(T > 1 ? T - 1 : 1, FastNode{});
+    hs.fastOrder.assign(T, 0);
+    FastBuilder b(hs.fastNodes, hs.fastOrder);
+    b.refs.resize(T);
+    for (int i = 0; i < T; i++) {
+        Ref& r = b.refs[i];
+        r.b.reset();
+        r.b.grow(&hs.vertices[3 * i].x); r.b.grow(&hs.vertices[3 * i + 1].x); r.b.grow(&hs.vertices[3 * i + 2].x);
+        for (int a = 0; a < 3; a++) r.c[a] = 0.5f * (r.b.lo[a] + r.b.hi[a]);
+        r.prim = i;
+    }
+    FBox root;
+    int rootRef;
+#pragma omp parallel
+#pragma omp single
+    rootRef = b.build(0, T, 1, root);
+    hs.fastRoot = rootRef;
+    hs.fastDepth = b.maxDepth.load();
+    for (int a = 0; a < 3; a++) {
+        float pad = 4e-6f * std::max(fabsf(root.lo[a]), fabsf(root.hi[a])) + 1e-7f;
+        hs.fastRootMin[a] = root.lo[a] - pad; hs.fastRootMax[a] = root.hi[a] + pad;
+    }
+    // triangles in leaf order; each record keeps its original primitive id
+    hs.fastTris.resize(T);
+    hs.primToFast.assign(T, 0);
+    for (int i = 0; i < T; i++) {
+        int p = hs.fastOrder[i];
+        TriGeom& g = hs.fastTris[i];
+        memcpy(g.v0, &hs.vertices[3 * p], 36);
+        g.matId = hs.materialIds[p];
+        g.pad[0] = p; g.pad[1] = 0;
+        hs.primToFast[p] = i;
+    }
+    hs.fastBuildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // namespace rs

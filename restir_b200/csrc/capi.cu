@@ -29,8 +29,10 @@ struct RstrScene {
     HostScene hs;
     DevScene dev{};
     void* dNodes = nullptr; void* dTriGeom = nullptr; void* dTriNorm = nullptr;
+    void* dFastNodes = nullptr; void* dPrimToFast = nullptr; void* dFallback = nullptr;
     void* dMaterials = nullptr; void* dAlias = nullptr; void* dLights = nullptr;
     size_t deviceBytes = 0;
+    int traversalMode = RS_TRAVERSAL_FAST;
 };
 
 struct RstrFrame {
@@ -115,18 +117,27 @@ static int ensureUploaded(RstrScene* sc) {
     HostScene& hs = sc->hs;
     size_t total = 0;
     cudaError_t e;
-    if ((e = upload(&sc->dNodes, hs.packed, total)) != cudaSuccess || (e = upload(&sc->dTriGeom, hs.triGeom, total)) != cudaSuccess ||
+    if ((e = upload(&sc->dNodes, hs.packed, total)) != cudaSuccess || (e = upload(&sc->dTriGeom, hs.fastTris, total)) != cudaSuccess ||
+        (e = upload(&sc->dFastNodes, hs.fastNodes, total)) != cudaSuccess || (e = upload(&sc->dPrimToFast, hs.primToFast, total)) != cudaSuccess ||
+
         (e = upload(&sc->dTriNorm, hs.triNorm, total)) != cudaSuccess || (e = upload(&sc->dMaterials, hs.materials, total)) != cudaSuccess ||
         (e = upload(&sc->dAlias, hs.alias, total)) != cudaSuccess || (e = upload(&sc->dLights, hs.lights, total)) != cudaSuccess) {
         std::string m = std::string("scene upload failed: ") + cudaGetErrorString(e);
         cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
-        sc->dNodes = sc->dTriGeom = sc->dTriNorm = sc->dMaterials = sc->dAlias = sc->dLights = nullptr;
+        cudaFree(sc->dFastNodes); cudaFree(sc->dPrimToFast);
+        sc->dNodes = sc->dTriGeom = sc->dTriNorm = sc->dMaterials = sc->dAlias = sc->dLights = sc->dFastNodes = sc->dPrimToFast = nullptr;
         return fail(RSTR_ERR_CUDA, m);
     }
+    if (cudaMalloc(&sc->dFallback, 4 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(sc->dFallback, 0, 4 * sizeof(unsigned int)) != cudaSuccess)
+        return fail(RSTR_ERR_CUDA, "scene upload failed: counter");
     sc->deviceBytes = total;
     DevScene& d = sc->dev;
+    d.fallbackRays = (unsigned int*)sc->dFallback;
     d.nodes = (const float4*)sc->dNodes; d.triGeom = (const float4*)sc->dTriGeom; d.triNorm = (const float4*)sc->dTriNorm;
     d.materials = (const RstrMaterial*)sc->dMaterials; d.alias = (const float2*)sc->dAlias; d.lights = (const float4*)sc->dLights;
+    d.fastNodes = (const float4*)sc->dFastNodes; d.primToFast = (const int*)sc->dPrimToFast;
+    d.numTris = hs.T; d.fastRoot = hs.fastRoot; d.traversal = sc->traversalMode;
+    memcpy(d.fastRootMin, hs.fastRootMin, 12); memcpy(d.fastRootMax, hs.fastRootMax, 12);
     d.numLights = (int)hs.lights.size();
     d.rootRef = hs.rootRef;
     memcpy(d.rootMin, &hs.rootBox.pMin, 12); memcpy(d.rootMax, &hs.rootBox.pMax, 12);
@@ -180,7 +191,27 @@ int rstr_scene_load_file(const char* path, RstrScene** out, RstrCamera* cameraOu
 int rstr_scene_destroy(RstrScene* sc) {
     if (!sc) return RSTR_OK;
     cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
+    cudaFree(sc->dFastNodes); cudaFree(sc->dPrimToFast); cudaFree(sc->dFallback);
     delete sc;
+    return RSTR_OK;
+}
+
+int rstr_scene_set_traversal(RstrScene* sc, int mode) {
+    if (!sc || (mode != RS_TRAVERSAL_FAST && mode != RS_TRAVERSAL_EXACT)) return fail(RSTR_ERR_ARG, "rstr_scene_set_traversal: bad argument");
+    sc->traversalMode = mode;
+    sc->dev.traversal = mode;
+    return RSTR_OK;
+}
+
+int rstr_scene_fallback_rays(RstrScene* sc, unsigned long long* count, int reset) {
+    if (!sc || !count) return fail(RSTR_ERR_ARG, "rstr_scene_fallback_rays: bad argument");
+    unsigned int v[4] = {0, 0, 0, 0};
+    if (sc->dFallback) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy(v, sc->dFallback, sizeof v, cudaMemcpyDeviceToHost));
+        if (reset) CU(cudaMemset(sc->dFallback, 0, sizeof v));
+    }
+    for (int i = 0; i < 4; i++) count[i] = v[i];
     return RSTR_OK;
 }
 
@@ -189,6 +220,7 @@ int rstr_scene_info(const RstrScene* sc, RstrSceneInfo* info) {
     info->numTris = sc->hs.T; info->numLights = (int)sc->hs.lightPrimIds.size(); info->bvhSize = sc->hs.bvhSize;
     info->bvhDepth = sc->hs.bvhDepth; info->numMaterials = (int)sc->hs.materials.size(); info->sumLightPower = sc->hs.sumAll;
     info->buildSeconds = sc->hs.buildSeconds; info->deviceBytes = sc->deviceBytes;
+    info->tracedBvhDepth = sc->hs.fastDepth; info->tracedBuildSeconds = sc->hs.fastBuildSeconds;
     return RSTR_OK;
 }
 

@@ -10,10 +10,20 @@ namespace rs {
 
 #define RS_STACK_DEPTH 96      /* traversal stack entries; deeper trees are rejected at scene creation */
 
+#define RS_TRAVERSAL_FAST 0     /* binned-SAH tree; reference-order walk only for near-axis and near-tie rays */
+#define RS_TRAVERSAL_EXACT 1    /* reference-order walk of the reference tree for every ray */
+
 struct DevScene {
-    const float4* nodes;       // PackedNode[], 4 x float4 each
-    const float4* triGeom;     // TriGeom[], 3 x float4 each
-    const float4* triNorm;     // TriNorm[], 3 x float4 each
+    const float4* nodes;       // PackedNode[] (reference tree), 4 x float4 each
+    const float4* fastNodes;   // FastNode[] (traced tree), 4 x float4 each
+    const float4* triGeom;     // TriGeom[] in the traced tree's leaf order, 3 x float4 each
+    const float4* triNorm;     // TriNorm[] in original primitive order, 3 x float4 each
+    const int* primToFast;     // original primitive id -> triGeom index
+    int numTris;
+    int fastRoot;
+    int traversal;             // RS_TRAVERSAL_*
+    unsigned int* fallbackRays;  // counter: rays re-traced with the reference-order walk
+    float fastRootMin[3], fastRootMax[3];
     const RstrMaterial* materials;
     const float2* alias;       // AliasEntry[] as {prob, failId bits}
     const float4* lights;      // LightRec[], 4 x float4 each

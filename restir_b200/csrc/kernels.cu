@@ -133,6 +133,14 @@ RS_D bool boxHit(const RayT& r, f3 pMin, f3 pMax, float& tMin) {
 }
 
 // intersections.h:17-53
+// Absolute error bound of the Moller-Trumbore distance of a hit: dist = dot(e02, cross(o - v0, e01)) / det, so the
+// rounding error is about |e02| |o - v0| |e01| / |det| ulps; 2^-20 = 16 ulps of safety.
+RS_D float triDistError(const RayT& r, f3 v0, f3 v1, f3 v2) {
+    f3 e01 = v1 - v0, e02 = v2 - v0, vo = r.o - v0;
+    float det = dot(cross(r.d, e02), e01);
+    return 9.5367431640625e-7f * sqrtf(dot(e01, e01) * dot(e02, e02) * dot(vo, vo)) / fabsf(det);
+}
+
 RS_D bool triHit(const RayT& r, f3 v0, f3 v1, f3 v2, float& bx, float& by, float& dist) {
     f3 e01 = v1 - v0, e02 = v2 - v0;
     f3 p = cross(r.d, e02);
@@ -151,16 +159,20 @@ RS_D bool triHit(const RayT& r, f3 v0, f3 v1, f3 v2, float& bx, float& by, float
     return dist > 0.f;
 }
 
-struct Tri { f3 v0, v1, v2; int matId; };
+struct Tri { f3 v0, v1, v2; int matId; int prim; };   // prim = original primitive id
 
-RS_D Tri loadTri(const DevScene& s, int prim) {
-    const float4* p = s.triGeom + 3 * (size_t)prim;
+// triangle record fi of the leaf-ordered array
+RS_D Tri loadTriFast(const DevScene& s, int fi) {
+    const float4* p = s.triGeom + 3 * (size_t)fi;
     float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     Tri t;
     t.v0 = mk3(a.x, a.y, a.z); t.v1 = mk3(a.w, b.x, b.y); t.v2 = mk3(b.z, b.w, c.x);
     t.matId = __float_as_int(c.y);
+    t.prim = __float_as_int(c.z);
     return t;
 }
+// by original primitive id
+RS_D Tri loadTri(const DevScene& s, int prim) { return loadTriFast(s, __ldg(s.primToFast + prim)); }
 
 struct Hit { float t, bx, by; int prim; };
 
@@ -194,7 +206,7 @@ struct Stack {
 
 // scene.h:245-278 on the packed tree.  Children are visited in the reference's order for this ray; the deferred
 // child is re-tested against the current closest distance when popped (= the reference's test on arrival).
-RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
+RS_D void traceClosestExact(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
     h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
     float tRoot;
     if (!(boxHit(r, mk3(s.rootMin[0], s.rootMin[1], s.rootMin[2]), mk3(s.rootMax[0], s.rootMax[1], s.rootMax[2]), tRoot) && tRoot < h.t)) return;
@@ -235,13 +247,7 @@ RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
 }
 
 // scene.h:286-316.  Any-hit: the answer does not depend on the visiting order.
-RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y, Stack& stack) {
-    const float Eps = 1e-4f;
-    f3 dir = y - x;
-    float dist = length(dir);
-    dir = dir / dist;
-    RayT r = makeRayT(x + dir * 1e-5f, dir);                                   // makeOffsetedRay, intersections.h:12
-    dist -= Eps * 2.f;
+RS_D bool traceOccludedExact(const DevScene& s, const RayT& r, float dist, Stack& stack) {
     float tRoot;
     if (!(boxHit(r, mk3(s.rootMin[0], s.rootMin[1], s.rootMin[2]), mk3(s.rootMax[0], s.rootMax[1], s.rootMax[2]), tRoot) && tRoot < dist)) return false;
     int sp = 0;
@@ -268,6 +274,166 @@ RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y, Stack& stack) {
         if (sp == 0) return false;
         cur = stack.ref(--sp);
     }
+}
+
+// ------------------------------------------------------------------------------------------------ traced tree
+// Standard slab test on the padded boxes of the binned-SAH tree: t = p * inv + (-o * inv), explicit FMAs.
+struct RayF { f3 inv, oi; };
+RS_D RayF makeRayF(const RayT& r) {
+    RayF f;
+    // a zero component would give inf * 0 = NaN; 1e-20 keeps "origin inside the slab <=> always inside" intact
+    float dx = fabsf(r.d.x) < 1e-20f ? copysignf(1e-20f, r.d.x) : r.d.x;
+    float dy = fabsf(r.d.y) < 1e-20f ? copysignf(1e-20f, r.d.y) : r.d.y;
+    float dz = fabsf(r.d.z) < 1e-20f ? copysignf(1e-20f, r.d.z) : r.d.z;
+    f.inv = mk3(1.f / dx, 1.f / dy, 1.f / dz);
+    f.oi = mk3(-r.o.x * f.inv.x, -r.o.y * f.inv.y, -r.o.z * f.inv.z);
+    return f;
+}
+RS_D bool slabHit(const RayF& f, float lx, float ly, float lz, float hx, float hy, float hz, float tLimit, float& tEntry) {
+    float x0 = __fmaf_rn(lx, f.inv.x, f.oi.x), x1 = __fmaf_rn(hx, f.inv.x, f.oi.x);
+    float y0 = __fmaf_rn(ly, f.inv.y, f.oi.y), y1 = __fmaf_rn(hy, f.inv.y, f.oi.y);
+    float z0 = __fmaf_rn(lz, f.inv.z, f.oi.z), z1 = __fmaf_rn(hz, f.inv.z, f.oi.z);
+    tEntry = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+    float tExit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tLimit));
+    return tEntry <= tExit;
+}
+
+// The reference reaches a triangle only through its leaf box = the triangle's own AABB (bvh.cpp:25), tested with the
+// strict, rounded predicate of bvh.h:131-155.  A hit on (or within rounding of) the rim of an axis-aligned triangle
+// fails that predicate, and the reference then does not see the triangle at all.  Checking the predicate on the hit
+// triangle's AABB tells whether the reference would have found this hit; if not, the ray is re-traced in reference order.
+RS_D bool leafBoxPasses(const RayT& r, const Tri& t) {
+    float tb;
+    return boxHit(r, gmin(gmin(t.v0, t.v1), t.v2), gmax(gmax(t.v0, t.v1), t.v2), tb);
+}
+
+// Closest hit over the traced tree.  Returns false when the result is AMBIGUOUS: two different triangles were hit at
+// distances within a few ulps of each other (a ray through a shared edge / coincident surfaces).  Which one the
+// reference keeps then depends on its visiting order and on its box-distance pruning (scene.h:260,267), so the caller
+// re-traces such a ray with the reference-order walk.  Outside that band both walks provably agree: the nearer hit wins.
+// Band width: the Moller-Trumbore distance of a small, distant triangle carries a relative error of about
+// |o - v0| / edge * 2^-24 (cancellation in dot(e02, cross(o - v0, e01))), i.e. up to ~1e-5 on the benchmark scenes,
+// while the reference prunes with box-entry distances that are accurate to an ulp (scene.h:260).
+#define RS_TIE_BAND 1e-4f
+RS_D bool traceClosestFast(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
+    h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
+    const RayF f = makeRayF(r);
+    float t0;
+    if (!slabHit(f, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], FLT_MAX, t0)) return true;
+    bool unambiguous = true, fragile = false;
+    float bestErr = 0.f;             // error bound of h.t
+    float limit = FLT_MAX;           // h.t widened by twice the tie band: near-tie candidates behind the current hit are still visited
+    int sp = 0;
+    int cur = s.fastRoot;
+    for (;;) {
+        if (cur < 0) {
+            int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            for (int i = 0; i < count; i++) {
+                Tri t = loadTriFast(s, first + i);
+                float bx, by, d;
+                if (triHit(r, t.v0, t.v1, t.v2, bx, by, d)) {
+                    float eb = -1.f;
+                    if (h.prim >= 0 && fabsf(d - h.t) <= RS_TIE_BAND * fmaxf(d, h.t)) {      // coarse band first, then the bound
+                        eb = triDistError(r, t.v0, t.v1, t.v2);
+                        if (fabsf(d - h.t) <= eb + bestErr + 1e-6f * fmaxf(d, h.t)) unambiguous = false;
+                    }
+                    if (d < h.t) {
+                        h.t = d; h.bx = bx; h.by = by; h.prim = t.prim; limit = d * (1.f + 2.f * RS_TIE_BAND);
+                        bestErr = eb >= 0.f ? eb : triDistError(r, t.v0, t.v1, t.v2);
+                        fragile = !leafBoxPasses(r, t);
+                    }
+                }
+            }
+        } else {
+            const float4* np = s.fastNodes + 4 * (size_t)cur;
+            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+            int4 l = __ldg((const int4*)(np + 3));
+            float tL, tR;
+            bool hL = slabHit(f, a.x, a.y, a.z, a.w, b.x, b.y, limit, tL);
+            bool hR = slabHit(f, b.z, b.w, c.x, c.y, c.z, c.w, limit, tR);
+            if (hL && hR) {
+                bool leftNear = tL <= tR;
+                stack.push(sp, leftNear ? l.y : l.x, leftNear ? tR : tL); sp++;
+                cur = leftNear ? l.x : l.y;
+                continue;
+            }
+            if (hL) { cur = l.x; continue; }
+            if (hR) { cur = l.y; continue; }
+        }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (stack.t(sp) <= limit) { cur = stack.ref(sp); found = true; break; }
+        }
+        if (!found) break;
+    }
+    if (!unambiguous) atomicAdd(s.fallbackRays + 1, 1u);
+    else if (fragile) atomicAdd(s.fallbackRays + 2, 1u);
+    return unambiguous && !fragile;
+}
+
+// returns 1 occluded, 0 free, -1 undecided (only rim hits were found: ask the reference-order walk)
+RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& stack) {
+    const RayF f = makeRayF(r);
+    float t0;
+    if (!slabHit(f, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], dist, t0)) return 0;
+    bool fragile = false;
+    int sp = 0;
+    int cur = s.fastRoot;
+    for (;;) {
+        if (cur < 0) {
+            int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            for (int i = 0; i < count; i++) {
+                Tri t = loadTriFast(s, first + i);
+                float bx, by, d;
+                if (triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist) {
+                    if (leafBoxPasses(r, t)) return true;      // the reference finds this occluder too
+                    fragile = true;                              // it may not: keep looking for a solid one
+                }
+            }
+        } else {
+            const float4* np = s.fastNodes + 4 * (size_t)cur;
+            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+            int4 l = __ldg((const int4*)(np + 3));
+            float tL, tR;
+            bool hL = slabHit(f, a.x, a.y, a.z, a.w, b.x, b.y, dist, tL);
+            bool hR = slabHit(f, b.z, b.w, c.x, c.y, c.z, c.w, dist, tR);
+            if (hL && hR) {
+                bool leftNear = tL <= tR;
+                stack.pushRef(sp, leftNear ? l.y : l.x); sp++;
+                cur = leftNear ? l.x : l.y;
+                continue;
+            }
+            if (hL) { cur = l.x; continue; }
+            if (hR) { cur = l.y; continue; }
+        }
+        if (sp == 0) return fragile ? -1 : 0;
+        cur = stack.ref(--sp);
+    }
+}
+
+// Rays with |d_a| > 1 - 1e-6 make the reference test "origin inside the other two slabs" instead of a slab test
+// (bvh.h:91-123), which is not conservative: those rays (a handful per frame) take the reference-order walk.
+RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
+    if (s.traversal == RS_TRAVERSAL_EXACT) { traceClosestExact(s, r, h, stack); return; }
+    if (r.flags & 3) atomicAdd(s.fallbackRays, 1u);
+    if ((r.flags & 3) || !traceClosestFast(s, r, h, stack)) traceClosestExact(s, r, h, stack);
+}
+
+// DevScene::testOcclusion (scene.h:286-316)
+RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y, Stack& stack) {
+    const float Eps = 1e-4f;
+    f3 dir = y - x;
+    float dist = length(dir);
+    if (!(dist > 0.f)) return false;          // x == y (or NaN): dir is NaN and every reference box test fails
+    dir = dir / dist;
+    RayT r = makeRayT(x + dir * 1e-5f, dir);                                   // makeOffsetedRay, intersections.h:12
+    dist -= Eps * 2.f;
+    if (s.traversal == RS_TRAVERSAL_EXACT) return traceOccludedExact(s, r, dist, stack);
+    int occ = (r.flags & 3) ? -1 : traceOccludedFast(s, r, dist, stack);
+    if (occ >= 0) return occ != 0;
+    atomicAdd(s.fallbackRays + ((r.flags & 3) ? 0 : 3), 1u);
+    return traceOccludedExact(s, r, dist, stack);
 }
 
 // ------------------------------------------------------------------------------------------------ camera

@@ -215,16 +215,14 @@ bool buildHostScene(HostScene& hs, std::string& err) {
     hs.bvhDepth = b.maxDepth.load();
     hs.rootBox = hs.boxes[0];
     hs.rootRef = T > 1 ? 0 : ~HostScene::leafPrim(hs.nodeInfo[0]);
-    // ---- packed triangles / lights ----
-    hs.triGeom.resize(T); hs.triNorm.resize(T);
+    // ---- packed normals / lights; traced tree + leaf-ordered triangles ----
+    hs.triNorm.resize(T);
     for (int p = 0; p < T; p++) {
-        TriGeom& g = hs.triGeom[p];
         TriNorm& nn = hs.triNorm[p];
-        memcpy(g.v0, &hs.vertices[3 * p], 36);
-        g.matId = hs.materialIds[p]; g.pad[0] = g.pad[1] = 0;
         memcpy(nn.n0, &hs.normals[3 * p], 36);
         nn.pad[0] = nn.pad[1] = nn.pad[2] = 0.f;
     }
+    buildFastBVH(hs);
     const int L = (int)hs.lightPrimIds.size();
     hs.lights.resize(L);
     for (int l = 0; l < L; l++) {

@@ -25,10 +25,19 @@ struct alignas(16) PackedNode {
 };
 static_assert(sizeof(PackedNode) == 64, "PackedNode");
 
+// One 64-byte record per internal node of the traced (binned-SAH) tree: both children's padded boxes + links.
+struct alignas(16) FastNode {
+    float lmin[3], lmax[3];
+    float rmin[3], rmax[3];
+    int left, right;          // >= 0: node index; < 0: leaf = 0x80000000 | (count-1) << 27 | firstTriangle
+    int pad[2];
+};
+static_assert(sizeof(FastNode) == 64, "FastNode");
+
 struct alignas(16) TriGeom {  // 48 B: raw vertices (Moller-Trumbore recomputes the edges exactly as intersections.h:20-21)
     float v0[3], v1[3], v2[3];
     int matId;
-    int pad[2];
+    int pad[2];               // pad[0] = original primitive id (records are stored in the traced tree's leaf order)
 };
 static_assert(sizeof(TriGeom) == 48, "TriGeom");
 
@@ -76,8 +85,16 @@ struct HostScene {
     Box rootBox;
     int rootRef = 0;
     std::vector<PackedNode> packed;
-    std::vector<TriGeom> triGeom;
-    std::vector<TriNorm> triNorm;
+    std::vector<TriNorm> triNorm;          // original primitive order
+
+    // traced tree (bvh_fast.cpp)
+    std::vector<FastNode> fastNodes;
+    std::vector<int> fastOrder;            // leaf order -> original primitive id
+    std::vector<int> primToFast;           // original primitive id -> position in fastTris
+    std::vector<TriGeom> fastTris;         // triangles in leaf order
+    int fastRoot = 0, fastDepth = 0;
+    float fastRootMin[3] = {0, 0, 0}, fastRootMax[3] = {0, 0, 0};
+    double fastBuildSeconds = 0.0;
     std::vector<LightRec> lights;
     double buildSeconds = 0.0;
 
@@ -87,6 +104,8 @@ struct HostScene {
 
 // scene.cpp:159-215 minus the upload.  Returns false (and sets err) on invalid input.
 bool buildHostScene(HostScene& hs, std::string& err);
+// binned-SAH BVH2 that the kernels trace + tie-break ranks (bvh_fast.cpp)
+void buildFastBVH(HostScene& hs);
 // bvh.cpp:133-201: the reference's i-th threaded ordering, regenerated from the single tree
 void exportMTBVH(const HostScene& hs, int ordering, std::vector<MTNode>& out);
 // sampler.h:79-121

@@ -54,6 +54,29 @@ def test_against_golden_fixtures(gpu, name):
         check(frames, want, reuse, "%s/%s vs golden" % (name, mode))
 
 
+def test_reference_order_walk_mode(gpu, port_oracle):
+    """RSTR traversal mode 1: every ray walks the reference tree in the reference's order (validation mode)."""
+    for sd in (scenes.cornell_box((320, 240), metal_tall_box=True), scenes.procedural(1, 20000, 1000, (320, 180))):
+        got, miss = helpers.run_gpu(gpu, sd, 3, 3, radius=12.0, light_index=True, exact=True)
+        want = helpers.run_oracle(port_oracle, sd, 3, 3, radius=12.0, light_index=True)
+        check(got, want, 3, "exact walk " + sd.name)
+
+
+def test_traced_tree_equals_reference_walk_at_full_size(gpu):
+    """Size-independent property at 1080p on the 200k-triangle scene: the binned-SAH tree (+ near-tie / near-axis
+    fallback) returns exactly what the reference-order walk returns, for primary and shadow rays alike."""
+    sd = scenes.procedural(1, 200000, 10000, (1920, 1080))
+    sc = gpu.Scene.from_arrays(sd)
+    fast, _ = helpers.run_gpu(gpu, sd, 4, 3, radius=30.0, light_index=True, scene=sc, exact=False)
+    exact, _ = helpers.run_gpu(gpu, sd, 4, 3, radius=30.0, light_index=True, scene=sc, exact=True)
+    helpers.assert_frames_equal(fast, exact, "traced tree vs reference walk")
+    sc.close()
+    sd = scenes.cornell_box((1920, 1080), metal_tall_box=True)
+    fast, _ = helpers.run_gpu(gpu, sd, 4, 3, radius=30.0, light_index=True, exact=False)
+    exact, _ = helpers.run_gpu(gpu, sd, 4, 3, radius=30.0, light_index=True, exact=True)
+    helpers.assert_frames_equal(fast, exact, "traced tree vs reference walk (cornell)")
+
+
 @pytest.mark.parametrize("reuse", [0, 1, 2, 3])
 def test_cornell_800_against_oracle(gpu, port_oracle, reuse):
     """BASELINE config 1 geometry (800x800 Cornell); every reuse mode, 3 frames of the orbit."""
