@@ -141,8 +141,8 @@ int rstr_scene_info(const RstrScene*, RstrSceneInfo*);
  * detected and re-traced with the reference-order walk.  1: every ray walks the reference tree in the reference's
  * order with its exact box predicate (validation mode, ~2x slower). */
 int rstr_scene_set_traversal(RstrScene*, int mode);
-/* rays re-traced with the reference-order walk since the scene was created / last reset (instrumentation);
- * count[4] = {near-axis rays, closest-hit near ties, closest hit on a leaf-box rim, shadow rays with rim hits only} */
+/* pixels recomputed with the reference-order walk since the scene was created / last reset (instrumentation);
+ * count[4] = {G-buffer pixels, ReSTIR phase-A pixels, PTDirect pixels, unused} */
 int rstr_scene_fallback_rays(RstrScene*, unsigned long long* count4, int reset);
 int rstr_scene_read(const RstrScene*, int which, void* host, size_t bytes);
 

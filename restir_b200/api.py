@@ -254,7 +254,7 @@ class Scene:
     def fallback_rays(self, reset: bool = True) -> dict:
         v = (C.c_ulonglong * 4)()
         _check(lib().rstr_scene_fallback_rays(self.h, v, 1 if reset else 0))
-        return dict(near_axis=int(v[0]), near_tie=int(v[1]), rim_closest=int(v[2]), rim_shadow=int(v[3]))
+        return dict(gbuffer=int(v[0]), restir_a=int(v[1]), ptdirect=int(v[2]))
 
     def read(self, name: str, ordering: int = 0) -> np.ndarray:
         T, L, N = self.info.numTris, self.info.numLights, self.info.bvhSize

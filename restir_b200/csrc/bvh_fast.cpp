@@ -173,6 +173,16 @@ void buildFastBVH(HostScene& hs) {
         g.pad[0] = p; g.pad[1] = 0;
         hs.primToFast[p] = i;
     }
+    // visiting rank of every triangle's leaf in each of the reference's 6 orderings (bvh.cpp:156-193)
+    hs.rank.assign(6 * (size_t)T, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int o = 0; o < 6; o++) {
+        std::vector<MTNode> mt;
+        exportMTBVH(hs, o, mt);
+        int* rk = hs.rank.data() + (size_t)o * T;
+        for (int i = 0; i < (int)mt.size(); i++)
+            if (mt[i].prim >= 0) rk[mt[i].prim] = i;
+    }
     hs.fastBuildSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 

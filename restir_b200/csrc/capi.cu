@@ -29,7 +29,7 @@ struct RstrScene {
     HostScene hs;
     DevScene dev{};
     void* dNodes = nullptr; void* dTriGeom = nullptr; void* dTriNorm = nullptr;
-    void* dFastNodes = nullptr; void* dPrimToFast = nullptr; void* dFallback = nullptr;
+    void* dFastNodes = nullptr; void* dPrimToFast = nullptr; void* dFallback = nullptr; void* dRank = nullptr;
     void* dMaterials = nullptr; void* dAlias = nullptr; void* dLights = nullptr;
     size_t deviceBytes = 0;
     int traversalMode = RS_TRAVERSAL_FAST;
@@ -48,6 +48,8 @@ struct RstrFrame {
     HitRec* hit = nullptr;
     uchar4* ldr = nullptr;
     unsigned int* haloMiss = nullptr;
+    int* queue = nullptr;
+    unsigned int* queueCount = nullptr;
     void* scratch = nullptr; size_t scratchBytes = 0;
     int cur = 0;        // GBuffer::frameIdx
     int resvOut = 0;    // which of resv[] is devDirectReservoir (written this frame)
@@ -82,7 +84,7 @@ static FrameDev toFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
     d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
     d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
-    d.hit = f->hit; d.haloMiss = f->haloMiss;
+    d.hit = f->hit; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount;
     return d;
 }
 
@@ -118,7 +120,7 @@ static int ensureUploaded(RstrScene* sc) {
     size_t total = 0;
     cudaError_t e;
     if ((e = upload(&sc->dNodes, hs.packed, total)) != cudaSuccess || (e = upload(&sc->dTriGeom, hs.fastTris, total)) != cudaSuccess ||
-        (e = upload(&sc->dFastNodes, hs.fastNodes, total)) != cudaSuccess || (e = upload(&sc->dPrimToFast, hs.primToFast, total)) != cudaSuccess ||
+        (e = upload(&sc->dFastNodes, hs.fastNodes, total)) != cudaSuccess || (e = upload(&sc->dRank, hs.rank, total)) != cudaSuccess || (e = upload(&sc->dPrimToFast, hs.primToFast, total)) != cudaSuccess ||
 
         (e = upload(&sc->dTriNorm, hs.triNorm, total)) != cudaSuccess || (e = upload(&sc->dMaterials, hs.materials, total)) != cudaSuccess ||
         (e = upload(&sc->dAlias, hs.alias, total)) != cudaSuccess || (e = upload(&sc->dLights, hs.lights, total)) != cudaSuccess) {
@@ -135,7 +137,7 @@ static int ensureUploaded(RstrScene* sc) {
     d.fallbackRays = (unsigned int*)sc->dFallback;
     d.nodes = (const float4*)sc->dNodes; d.triGeom = (const float4*)sc->dTriGeom; d.triNorm = (const float4*)sc->dTriNorm;
     d.materials = (const RstrMaterial*)sc->dMaterials; d.alias = (const float2*)sc->dAlias; d.lights = (const float4*)sc->dLights;
-    d.fastNodes = (const float4*)sc->dFastNodes; d.primToFast = (const int*)sc->dPrimToFast;
+    d.fastNodes = (const float4*)sc->dFastNodes; d.primToFast = (const int*)sc->dPrimToFast; d.rank = (const int*)sc->dRank;
     d.numTris = hs.T; d.fastRoot = hs.fastRoot; d.traversal = sc->traversalMode;
     memcpy(d.fastRootMin, hs.fastRootMin, 12); memcpy(d.fastRootMax, hs.fastRootMax, 12);
     d.numLights = (int)hs.lights.size();
@@ -191,7 +193,7 @@ int rstr_scene_load_file(const char* path, RstrScene** out, RstrCamera* cameraOu
 int rstr_scene_destroy(RstrScene* sc) {
     if (!sc) return RSTR_OK;
     cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
-    cudaFree(sc->dFastNodes); cudaFree(sc->dPrimToFast); cudaFree(sc->dFallback);
+    cudaFree(sc->dFastNodes); cudaFree(sc->dPrimToFast); cudaFree(sc->dFallback); cudaFree(sc->dRank);
     delete sc;
     return RSTR_OK;
 }
@@ -262,7 +264,7 @@ int rstr_frame_destroy(RstrFrame* f) {
     if (f->stream) cudaStreamSynchronize(f->stream);
     for (int i = 0; i < 2; i++) { cudaFree(f->geom[i]); cudaFree(f->matId[i]); cudaFree(f->resv[i]); }
     cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->hit); cudaFree(f->ldr);
-    cudaFree(f->haloMiss); cudaFree(f->scratch);
+    cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->queueCount);
     for (auto& e : f->ev) if (e) cudaEventDestroy(e);
     if (f->xfer) cudaEventDestroy(f->xfer);
     for (auto& e : f->marks) if (e) cudaEventDestroy(e);
@@ -300,6 +302,8 @@ int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int
     alloc((void**)&f->hit, n * sizeof(HitRec));
     alloc((void**)&f->ldr, n * sizeof(uchar4));
     alloc((void**)&f->haloMiss, sizeof(unsigned int));
+    alloc((void**)&f->queue, n * sizeof(int));
+    alloc((void**)&f->queueCount, sizeof(unsigned int));
     if (e == cudaSuccess) {
         // a zero-filled reference reservoir has no sample: lightId must read as "none"
         std::vector<ResvD> init(n);
@@ -345,9 +349,8 @@ int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
     FrameDev d = toFrameDev(f, f->bufRow0, f->bufRow0 + f->bufRows);      // halo rows are rendered locally, not exchanged
     for (bool& r : f->ran) r = false;
     stageBegin(f, RSTR_T_GBUFFER);
-    launchGBuffer(f->sc->dev, d, c, lc, f->stream);
+    g_launches += launchGBuffer(f->sc->dev, d, c, lc, f->stream);
     stageEnd(f, RSTR_T_GBUFFER);
-    g_launches++;
     CU(cudaGetLastError());
     return RSTR_OK;
 }
@@ -364,9 +367,8 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     if (!prm || prm->numCandidates < 0 || prm->numSpatial < 0 || prm->temporalCap < 1) return fail(RSTR_ERR_ARG, "bad RstrParams");
     FrameDev d = toFrameDev(f, f->row0, f->row1);
     stageBegin(f, RSTR_T_RIS);
-    launchRestirA(f->sc->dev, d, toCamDev(*cam), *prm, looper, iter, f->first ? 1 : 0, f->stream);
+    g_launches += launchRestirA(f->sc->dev, d, toCamDev(*cam), *prm, looper, iter, f->first ? 1 : 0, f->stream);
     stageEnd(f, RSTR_T_RIS);
-    g_launches++;
     CU(cudaGetLastError());
     return RSTR_OK;
 }
@@ -399,9 +401,8 @@ int rstr_pathtrace_direct(RstrFrame* f, const RstrCamera* cam, int looper, int i
     if (rc) return rc;
     FrameDev d = toFrameDev(f, f->row0, f->row1);
     stageBegin(f, RSTR_T_PTDIRECT);
-    launchPTDirect(f->sc->dev, d, toCamDev(*cam), looper, iter, f->stream);
+    g_launches += launchPTDirect(f->sc->dev, d, toCamDev(*cam), looper, iter, f->stream);
     stageEnd(f, RSTR_T_PTDIRECT);
-    g_launches++;
     CU(cudaGetLastError());
     return RSTR_OK;
 }

@@ -19,10 +19,11 @@ struct DevScene {
     const float4* triGeom;     // TriGeom[] in the traced tree's leaf order, 3 x float4 each
     const float4* triNorm;     // TriNorm[] in original primitive order, 3 x float4 each
     const int* primToFast;     // original primitive id -> triGeom index
+    const int* rank;           // [6][numTris] visiting rank in the reference's orderings (near-tie resolution)
     int numTris;
     int fastRoot;
     int traversal;             // RS_TRAVERSAL_*
-    unsigned int* fallbackRays;  // counter: rays re-traced with the reference-order walk
+    unsigned int* fallbackRays;  // [3] pixels recomputed with the reference-order walk: G-buffer, ReSTIR phase A, PTDirect
     float fastRootMin[3], fastRootMax[3];
     const RstrMaterial* materials;
     const float2* alias;       // AliasEntry[] as {prob, failId bits}
@@ -76,6 +77,8 @@ struct FrameDev {
     const ResvD* resvIn;       // history of the previous frame
     ResvD* resvTemp;
     HitRec* hit;
+    int* queue;                // pixels deferred to the reference-order fix-up kernel
+    unsigned int* queueCount;
     unsigned int* haloMiss;    // count of neighbour / reprojection reads that fell outside the resident rows
 };
 

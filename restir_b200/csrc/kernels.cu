@@ -298,56 +298,47 @@ RS_D bool slabHit(const RayF& f, float lx, float ly, float lz, float hx, float h
     return tEntry <= tExit;
 }
 
-// The reference reaches a triangle only through its leaf box = the triangle's own AABB (bvh.cpp:25), tested with the
-// strict, rounded predicate of bvh.h:131-155.  A hit on (or within rounding of) the rim of an axis-aligned triangle
-// fails that predicate, and the reference then does not see the triangle at all.  Checking the predicate on the hit
-// triangle's AABB tells whether the reference would have found this hit; if not, the ray is re-traced in reference order.
-RS_D bool leafBoxPasses(const RayT& r, const Tri& t) {
-    float tb;
-    return boxHit(r, gmin(gmin(t.v0, t.v1), t.v2), gmax(gmax(t.v0, t.v1), t.v2), tb);
+// ---- what the reference's walk finds, without walking its tree ----
+// The reference reaches a triangle only through nested boxes that end in the triangle's own AABB (1 triangle per leaf,
+// bvh.cpp:25), each tested with the predicate of bvh.h:85-157 and pruned by "box distance < closest" (scene.h:260).
+// Both the predicate and the box distance are monotone along the nesting (an enclosing box passes whenever the enclosed
+// one does, and is entered no later), so the whole chain reduces to the leaf box: the reference finds triangle T iff
+//   T is hit (intersections.h:17-53),  the predicate holds for AABB(T),  boxDistance(AABB(T)) < closest  and  d < closest,
+// with candidates visited in the order of the ray's MTBVH ordering (bvh.cpp:156-193 -> DevScene::rank).  Because
+// boxDistance <= d up to rounding, the order only matters between hits whose distances differ by less than the
+// Moller-Trumbore rounding error; the traced-tree walk keeps the best hit plus one such runner-up and replays the
+// reference's two visits.  Three or more mutually near hits are left to the reference-order walk (fix-up kernel).
+struct Cand { float d, bx, by, tBox, err; int prim; };
+
+RS_D bool leafBox(const RayT& r, const Tri& t, float& tBox) {
+    return boxHit(r, gmin(gmin(t.v0, t.v1), t.v2), gmax(gmax(t.v0, t.v1), t.v2), tBox);
 }
 
-// Closest hit over the traced tree.  Returns false when the result is AMBIGUOUS: two different triangles were hit at
-// distances within a few ulps of each other (a ray through a shared edge / coincident surfaces).  Which one the
-// reference keeps then depends on its visiting order and on its box-distance pruning (scene.h:260,267), so the caller
-// re-traces such a ray with the reference-order walk.  Outside that band both walks provably agree: the nearer hit wins.
-// Band width: the Moller-Trumbore distance of a small, distant triangle carries a relative error of about
-// |o - v0| / edge * 2^-24 (cancellation in dot(e02, cross(o - v0, e01))), i.e. up to ~1e-5 on the benchmark scenes,
-// while the reference prunes with box-entry distances that are accurate to an ulp (scene.h:260).
-#define RS_TIE_BAND 1e-4f
+#define RS_TIE_BAND 1e-4f     /* coarse relative band that triggers the error-bound computation */
+RS_D bool nearTie(const Cand& a, const Cand& b) {
+    return fabsf(a.d - b.d) <= a.err + b.err + 1e-6f * fmaxf(a.d, b.d);
+}
+
+// Closest hit over the traced tree ("while-while": lanes first descend to a leaf, then test triangles together).
+// Returns false when undecided (>= 3 mutually near hits).
 RS_D bool traceClosestFast(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
     h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
     const RayF f = makeRayF(r);
     float t0;
     if (!slabHit(f, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], FLT_MAX, t0)) return true;
-    bool unambiguous = true, fragile = false;
-    float bestErr = 0.f;             // error bound of h.t
-    float limit = FLT_MAX;           // h.t widened by twice the tie band: near-tie candidates behind the current hit are still visited
+    Cand best, second;
+    best.d = FLT_MAX; best.prim = -1; best.bx = best.by = best.tBox = best.err = 0.f;
+    second = best;
+    bool triple = false;
+    float limit = FLT_MAX;           // best.d widened by twice the coarse band: near-tie candidates behind the best hit are still visited
     int sp = 0;
     int cur = s.fastRoot;
     for (;;) {
-        if (cur < 0) {
-            int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
-            for (int i = 0; i < count; i++) {
-                Tri t = loadTriFast(s, first + i);
-                float bx, by, d;
-                if (triHit(r, t.v0, t.v1, t.v2, bx, by, d)) {
-                    float eb = -1.f;
-                    if (h.prim >= 0 && fabsf(d - h.t) <= RS_TIE_BAND * fmaxf(d, h.t)) {      // coarse band first, then the bound
-                        eb = triDistError(r, t.v0, t.v1, t.v2);
-                        if (fabsf(d - h.t) <= eb + bestErr + 1e-6f * fmaxf(d, h.t)) unambiguous = false;
-                    }
-                    if (d < h.t) {
-                        h.t = d; h.bx = bx; h.by = by; h.prim = t.prim; limit = d * (1.f + 2.f * RS_TIE_BAND);
-                        bestErr = eb >= 0.f ? eb : triDistError(r, t.v0, t.v1, t.v2);
-                        fragile = !leafBoxPasses(r, t);
-                    }
-                }
-            }
-        } else {
+        // ---- descend through internal nodes
+        while (cur >= 0) {
             const float4* np = s.fastNodes + 4 * (size_t)cur;
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
-            int4 l = __ldg((const int4*)(np + 3));
+            int2 l = __ldg((const int2*)(np + 3));
             float tL, tR;
             bool hL = slabHit(f, a.x, a.y, a.z, a.w, b.x, b.y, limit, tL);
             bool hR = slabHit(f, b.z, b.w, c.x, c.y, c.z, c.w, limit, tR);
@@ -355,46 +346,81 @@ RS_D bool traceClosestFast(const DevScene& s, const RayT& r, Hit& h, Stack& stac
                 bool leftNear = tL <= tR;
                 stack.push(sp, leftNear ? l.y : l.x, leftNear ? tR : tL); sp++;
                 cur = leftNear ? l.x : l.y;
-                continue;
+            } else if (hL) cur = l.x;
+            else if (hR) cur = l.y;
+            else {
+                cur = 0x7fffffff;                                   // nothing below: pop
+                while (sp > 0) {
+                    --sp;
+                    if (stack.t(sp) <= limit) { cur = stack.ref(sp); break; }
+                }
+                if (cur == 0x7fffffff) goto done;
             }
-            if (hL) { cur = l.x; continue; }
-            if (hR) { cur = l.y; continue; }
         }
-        bool found = false;
+        // ---- leaf
+        {
+            int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            for (int i = 0; i < count; i++) {
+                Tri t = loadTriFast(s, first + i);
+                Cand x;
+                if (!triHit(r, t.v0, t.v1, t.v2, x.bx, x.by, x.d)) continue;
+                if (!(x.d <= limit)) continue;
+                if (!leafBox(r, t, x.tBox)) continue;               // the reference never sees this triangle
+                x.prim = t.prim;
+                x.err = -1.f;
+                if (best.prim >= 0 && fabsf(x.d - best.d) <= RS_TIE_BAND * fmaxf(x.d, best.d)) {
+                    x.err = triDistError(r, t.v0, t.v1, t.v2);
+                    if (nearTie(x, best)) {
+                        if (second.prim >= 0) triple = true;
+                        if (x.d < best.d) { second = best; best = x; limit = x.d * (1.f + 2.f * RS_TIE_BAND); }
+                        else second = x;
+                        continue;
+                    }
+                }
+                if (x.d < best.d) {
+                    if (x.err < 0.f) x.err = triDistError(r, t.v0, t.v1, t.v2);
+                    best = x; second.prim = -1; triple = false;     // anything near the old best is now irrelevant
+                    limit = x.d * (1.f + 2.f * RS_TIE_BAND);
+                }
+            }
+        }
+        cur = 0x7fffffff;
         while (sp > 0) {
             --sp;
-            if (stack.t(sp) <= limit) { cur = stack.ref(sp); found = true; break; }
+            if (stack.t(sp) <= limit) { cur = stack.ref(sp); break; }
         }
-        if (!found) break;
+        if (cur == 0x7fffffff) break;
     }
-    if (!unambiguous) atomicAdd(s.fallbackRays + 1, 1u);
-    else if (fragile) atomicAdd(s.fallbackRays + 2, 1u);
-    return unambiguous && !fragile;
+done:
+    if (best.prim < 0) return true;
+    if (triple) return false;
+    if (second.prim >= 0 && nearTie(second, best)) {
+        // replay the reference's two visits in its order for this ray
+        const int* rank = s.rank + (size_t)(2 * r.dim + r.lesser) * s.numTris;
+        bool bestFirst = __ldg(rank + best.prim) < __ldg(rank + second.prim);
+        const Cand& c1 = bestFirst ? best : second;
+        const Cand& c2 = bestFirst ? second : best;
+        bool take2 = c2.tBox < c1.d && c2.d < c1.d;
+        const Cand& w = take2 ? c2 : c1;
+        h.t = w.d; h.bx = w.bx; h.by = w.by; h.prim = w.prim;
+        return true;
+    }
+    h.t = best.d; h.bx = best.bx; h.by = best.by; h.prim = best.prim;
+    return true;
 }
 
-// returns 1 occluded, 0 free, -1 undecided (only rim hits were found: ask the reference-order walk)
+// any hit: order does not matter, the criterion above is exact per triangle
 RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& stack) {
     const RayF f = makeRayF(r);
     float t0;
     if (!slabHit(f, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], dist, t0)) return 0;
-    bool fragile = false;
     int sp = 0;
     int cur = s.fastRoot;
     for (;;) {
-        if (cur < 0) {
-            int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
-            for (int i = 0; i < count; i++) {
-                Tri t = loadTriFast(s, first + i);
-                float bx, by, d;
-                if (triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist) {
-                    if (leafBoxPasses(r, t)) return true;      // the reference finds this occluder too
-                    fragile = true;                              // it may not: keep looking for a solid one
-                }
-            }
-        } else {
+        while (cur >= 0) {
             const float4* np = s.fastNodes + 4 * (size_t)cur;
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
-            int4 l = __ldg((const int4*)(np + 3));
+            int2 l = __ldg((const int2*)(np + 3));
             float tL, tR;
             bool hL = slabHit(f, a.x, a.y, a.z, a.w, b.x, b.y, dist, tL);
             bool hR = slabHit(f, b.z, b.w, c.x, c.y, c.z, c.w, dist, tR);
@@ -402,38 +428,44 @@ RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& 
                 bool leftNear = tL <= tR;
                 stack.pushRef(sp, leftNear ? l.y : l.x); sp++;
                 cur = leftNear ? l.x : l.y;
-                continue;
+            } else if (hL) cur = l.x;
+            else if (hR) cur = l.y;
+            else {
+                if (sp == 0) return 0;
+                cur = stack.ref(--sp);
             }
-            if (hL) { cur = l.x; continue; }
-            if (hR) { cur = l.y; continue; }
         }
-        if (sp == 0) return fragile ? -1 : 0;
+        int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+        for (int i = 0; i < count; i++) {
+            Tri t = loadTriFast(s, first + i);
+            float bx, by, d, tb;
+            if (triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist && leafBox(r, t, tb) && tb < dist) return 1;
+        }
+        if (sp == 0) return 0;
         cur = stack.ref(--sp);
     }
 }
 
-// Rays with |d_a| > 1 - 1e-6 make the reference test "origin inside the other two slabs" instead of a slab test
-// (bvh.h:91-123), which is not conservative: those rays (a handful per frame) take the reference-order walk.
-RS_D void traceClosest(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
-    if (s.traversal == RS_TRAVERSAL_EXACT) { traceClosestExact(s, r, h, stack); return; }
-    if (r.flags & 3) atomicAdd(s.fallbackRays, 1u);
-    if ((r.flags & 3) || !traceClosestFast(s, r, h, stack)) traceClosestExact(s, r, h, stack);
+// EXACT = false: walk the traced tree; a ray with three or more mutually near hits is reported undecided (its pixel is
+// queued and recomputed by the fix-up kernel).  EXACT = true: reference-order walk of the reference tree.
+template <bool EXACT>
+RS_D bool traceClosest(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
+    if (EXACT) { traceClosestExact(s, r, h, stack); return true; }
+    return traceClosestFast(s, r, h, stack);
 }
 
-// DevScene::testOcclusion (scene.h:286-316)
-RS_D bool traceOccluded(const DevScene& s, f3 x, f3 y, Stack& stack) {
+// DevScene::testOcclusion (scene.h:286-316): 1 occluded, 0 free, -1 undecided (never with EXACT)
+template <bool EXACT>
+RS_D int traceOccluded(const DevScene& s, f3 x, f3 y, Stack& stack) {
     const float Eps = 1e-4f;
     f3 dir = y - x;
     float dist = length(dir);
-    if (!(dist > 0.f)) return false;          // x == y (or NaN): dir is NaN and every reference box test fails
+    if (!(dist > 0.f)) return 0;              // x == y (or NaN): dir is NaN and every reference box test fails
     dir = dir / dist;
     RayT r = makeRayT(x + dir * 1e-5f, dir);                                   // makeOffsetedRay, intersections.h:12
     dist -= Eps * 2.f;
-    if (s.traversal == RS_TRAVERSAL_EXACT) return traceOccludedExact(s, r, dist, stack);
-    int occ = (r.flags & 3) ? -1 : traceOccludedFast(s, r, dist, stack);
-    if (occ >= 0) return occ != 0;
-    atomicAdd(s.fallbackRays + ((r.flags & 3) ? 0 : 3), 1u);
-    return traceOccludedExact(s, r, dist, stack);
+    if (EXACT) return traceOccludedExact(s, r, dist, stack) ? 1 : 0;
+    return traceOccludedFast(s, r, dist, stack);
 }
 
 // ------------------------------------------------------------------------------------------------ camera
@@ -527,6 +559,8 @@ RS_D bool pixelOf(const FrameDev& f, int& x, int& y) {
     y = f.rowLo + blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     return x < f.W && y < f.rowHi;
 }
+// pixels whose outcome depends on the reference's visiting order are deferred to the fix-up kernel
+RS_D void enqueuePixel(const FrameDev& f, int x, int y) { f.queue[atomicAdd(f.queueCount, 1u)] = y * f.W + x; }
 RS_D size_t planeIndex(const FrameDev& f, int x, int y) { return (size_t)(y - f.bufRow0) * f.W + x; }
 RS_D bool rowResident(const FrameDev& f, int y) { return y >= f.bufRow0 && y < f.bufRow0 + f.bufRows; }
 
@@ -550,17 +584,15 @@ RS_D f3 shadeReservoir(const DevScene& s, const Resv& r, int type, float metalli
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(128) k_gbuffer(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
-                                                 const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
-    RS_DECLARE_STACK(stack);
-    int x, y;
-    if (!pixelOf(f, x, y)) return;
+// gbuffer.cu:3-73 for one pixel; false = undecided, nothing written
+template <bool EXACT>
+RS_D bool gbufferPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, int x, int y, Stack& stack) {
     size_t li = planeIndex(f, x, y);
     f3 o, d;
     cameraRay(cam, x, y, .5f, .5f, o, d);
     RayT r = makeRayT(o, d);
     Hit h;
-    traceClosest(s, r, h, stack);
+    if (!traceClosest<EXACT>(s, r, h, stack)) return false;
     if (h.prim >= 0) {
         Tri t = loadTri(s, h.prim);
         const float4* np = s.triNorm + 3 * (size_t)h.prim;
@@ -585,6 +617,30 @@ __global__ void __launch_bounds__(128) k_gbuffer(const __grid_constant__ DevScen
         f.matId[0][li] = -1;
         f.albedoMotion[li] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
     }
+    return true;
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(RS_BLOCK) k_gbuffer(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                      const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
+    RS_DECLARE_STACK(stack);
+    int x, y;
+    if (!pixelOf(f, x, y)) return;
+    if (!gbufferPixel<EXACT>(s, f, cam, lastCam, x, y, stack)) enqueuePixel(f, x, y);
+}
+// recomputes the queued pixels with the reference-order walk
+__global__ void __launch_bounds__(RS_BLOCK) k_gbuffer_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                          const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
+    RS_DECLARE_STACK(stack);
+    const unsigned n = *f.queueCount;
+    // entry i -> lane i / numWarps of warp i % numWarps: the first numWarps entries each get a warp of their own
+    // (reference-order walks diverge completely, sharing a warp would serialise them)
+    const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
+    for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
+        int idx = f.queue[i];
+        gbufferPixel<true>(s, f, cam, lastCam, idx % f.W, idx / f.W, stack);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.fallbackRays + 0, n);
 }
 
 // scene.h:394-425 on the packed light record; returns the pdf (<= 0: invalid), fills wi / dist / lightId
@@ -627,13 +683,10 @@ RS_D Resv findTemporal(const FrameDev& f, size_t li, int idx) {
     return loadResv(f.resvIn + lli);
 }
 
-template <bool SPATIAL>
-__global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
-                                                  const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
-                                                  int looper, int iter, int first) {
-    RS_DECLARE_STACK(stack);
-    int x, y;
-    if (!pixelOf(f, x, y)) return;
+// restir.cu:119-192 (+ :211-230 when spatial reuse is off) for one pixel; false = undecided, nothing written
+template <bool EXACT, bool SPATIAL>
+RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& prm, int looper, int iter, int first,
+                       int x, int y, Stack& stack) {
     size_t li = planeIndex(f, x, y);
     int index = y * f.W + x;
     Rng rng;
@@ -644,7 +697,7 @@ __global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevSce
     cameraRay(cam, x, y, r0, r1, o, d);
     RayT ray = makeRayT(o, d);
     Hit h;
-    traceClosest(s, ray, h, stack);
+    if (!traceClosest<EXACT>(s, ray, h, stack)) return false;
     int status = 0;      // 0 miss, 1 emitter, 2 shaded
     f3 pos, nrm;
     int matId = -1, type = 0;
@@ -671,7 +724,7 @@ __global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevSce
             q[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
             q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        return;
+        return true;
     }
     f3 wo = -d;
     if (type != 2 && dot(nrm, wo) < 0.f) nrm = -nrm;                                 // restir.cu:150-153
@@ -691,7 +744,11 @@ __global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevSce
         if (rnd * R.w < weight) { R.wi = wi; R.dist = dist; R.lightId = lid; }
     }
     // restir.cu:172-176.  With weight == 0 the test cannot change anything, so the ray is skipped.
-    if (R.w != 0.f && traceOccluded(s, pos, pos + R.wi * R.dist, stack)) R.w = 0.f;
+    if (R.w != 0.f) {
+        int occ = traceOccluded<EXACT>(s, pos, pos + R.wi * R.dist, stack);
+        if (occ < 0) return false;
+        if (occ) R.w = 0.f;
+    }
     if (!first && (prm.reuse & 1)) {                                                 // restir.cu:180-185
         Resv T = findTemporal(f, li, index);
         if (!resvInvalid(T)) {
@@ -712,6 +769,32 @@ __global__ void __launch_bounds__(128) k_restir_a(const __grid_constant__ DevSce
     } else {
         writeRadiance(f, li, shadeReservoir(s, R, type, metallic, roughness, nrm, wo), iter);
     }
+    return true;
+}
+
+template <bool EXACT, bool SPATIAL>
+__global__ void __launch_bounds__(RS_BLOCK) k_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                       const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
+                                                       int looper, int iter, int first) {
+    RS_DECLARE_STACK(stack);
+    int x, y;
+    if (!pixelOf(f, x, y)) return;
+    if (!restirAPixel<EXACT, SPATIAL>(s, f, cam, prm, looper, iter, first, x, y, stack)) enqueuePixel(f, x, y);
+}
+template <bool SPATIAL>
+__global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                           const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
+                                                           int looper, int iter, int first) {
+    RS_DECLARE_STACK(stack);
+    const unsigned n = *f.queueCount;
+    // entry i -> lane i / numWarps of warp i % numWarps: the first numWarps entries each get a warp of their own
+    // (reference-order walks diverge completely, sharing a warp would serialise them)
+    const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
+    for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
+        int idx = f.queue[i];
+        restirAPixel<true, SPATIAL>(s, f, cam, prm, looper, iter, first, idx % f.W, idx / f.W, stack);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.fallbackRays + 1, n);
 }
 
 // restir.cu:47-85 (+ mathUtil.h:128-132 toConcentricDisk)
@@ -758,11 +841,8 @@ __global__ void __launch_bounds__(128) k_restir_b(const __grid_constant__ DevSce
 }
 
 // pathtrace.cu:279-328 with scene.h:427-459 (occlusion test BEFORE the facing test)
-__global__ void __launch_bounds__(128) k_ptdirect(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
-                                                  const __grid_constant__ CamDev cam, int looper, int iter) {
-    RS_DECLARE_STACK(stack);
-    int x, y;
-    if (!pixelOf(f, x, y)) return;
+template <bool EXACT>
+RS_D bool ptdirectPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, int x, int y, Stack& stack) {
     size_t li = planeIndex(f, x, y);
     int index = y * f.W + x;
     Rng rng;
@@ -773,7 +853,7 @@ __global__ void __launch_bounds__(128) k_ptdirect(const __grid_constant__ DevSce
     cameraRay(cam, x, y, r0, r1, o, d);
     RayT ray = makeRayT(o, d);
     Hit h;
-    traceClosest(s, ray, h, stack);
+    if (!traceClosest<EXACT>(s, ray, h, stack)) return false;
     f3 direct = mk3(0.f);
     if (h.prim >= 0) {
         Tri t = loadTri(s, h.prim);
@@ -802,7 +882,9 @@ __global__ void __launch_bounds__(128) k_ptdirect(const __grid_constant__ DevSce
             float sr = sqrtf(c3);
             float u = 1.f - sr, v = c2 * sr;
             f3 sampled = v1 * u + v2 * v + v0 * (1.f - u - v);
-            if (!traceOccluded(s, pos, sampled, stack)) {
+            int occ = traceOccluded<EXACT>(s, pos, sampled, stack);
+            if (occ < 0) return false;
+            if (!occ) {
                 f3 pts = sampled - pos;
                 if (!(dot(n, pts) > -1e-6f)) {
                     f3 Li = mk3(d4.x, d4.y, d4.z);
@@ -819,6 +901,29 @@ __global__ void __launch_bounds__(128) k_ptdirect(const __grid_constant__ DevSce
     f3 prev = mk3(out[0], out[1], out[2]);
     f3 v = (prev * (float)iter + direct) / (float)(iter + 1);
     out[0] = v.x; out[1] = v.y; out[2] = v.z;
+    return true;
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(RS_BLOCK) k_ptdirect(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                       const __grid_constant__ CamDev cam, int looper, int iter) {
+    RS_DECLARE_STACK(stack);
+    int x, y;
+    if (!pixelOf(f, x, y)) return;
+    if (!ptdirectPixel<EXACT>(s, f, cam, looper, iter, x, y, stack)) enqueuePixel(f, x, y);
+}
+__global__ void __launch_bounds__(RS_BLOCK) k_ptdirect_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                           const __grid_constant__ CamDev cam, int looper, int iter) {
+    RS_DECLARE_STACK(stack);
+    const unsigned n = *f.queueCount;
+    // entry i -> lane i / numWarps of warp i % numWarps: the first numWarps entries each get a warp of their own
+    // (reference-order walks diverge completely, sharing a warp would serialise them)
+    const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
+    for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
+        int idx = f.queue[i];
+        ptdirectPixel<true>(s, f, cam, looper, iter, idx % f.W, idx / f.W, stack);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.fallbackRays + 2, n);
 }
 
 // pathtrace.cu:30-56 (Math::filmic / ACES / correctGamma: mathUtil.h:103-117)
@@ -866,18 +971,41 @@ __global__ void k_export_resv(const DevScene s, const ResvD* __restrict__ src, f
 // ------------------------------------------------------------------------------------------------ launchers
 static inline dim3 pixelGrid(const FrameDev& f) { return dim3((f.W + 15) / 16, (f.rowHi - f.rowLo + 7) / 8); }
 
-void launchGBuffer(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, cudaStream_t st) {
-    k_gbuffer<<<pixelGrid(f), 128, 0, st>>>(s, f, cam, lastCam);
+#define RS_FIX_BLOCKS 296   /* 2 per SM; the fix-up kernels stride over the queue */
+
+int launchGBuffer(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, cudaStream_t st) {
+    if (s.traversal == RS_TRAVERSAL_EXACT) { k_gbuffer<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam); return 1; }
+    cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
+    k_gbuffer<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
+    k_gbuffer_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
+    return 2;
 }
-void launchRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& p, int looper, int iter, int first, cudaStream_t st) {
-    if (p.reuse & 2) k_restir_a<true><<<pixelGrid(f), 128, 0, st>>>(s, f, cam, p, looper, iter, first);
-    else k_restir_a<false><<<pixelGrid(f), 128, 0, st>>>(s, f, cam, p, looper, iter, first);
+int launchRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& p, int looper, int iter, int first, cudaStream_t st) {
+    const bool sp = (p.reuse & 2) != 0;
+    if (s.traversal == RS_TRAVERSAL_EXACT) {
+        if (sp) k_restir_a<true, true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+        else k_restir_a<true, false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+        return 1;
+    }
+    cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
+    if (sp) {
+        k_restir_a<false, true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+        k_restir_a_fix<true><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+    } else {
+        k_restir_a<false, false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+        k_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+    }
+    return 2;
 }
 void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, cudaStream_t st) {
     k_restir_b<<<pixelGrid(f), 128, 0, st>>>(s, f, p, iter);
 }
-void launchPTDirect(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, cudaStream_t st) {
-    k_ptdirect<<<pixelGrid(f), 128, 0, st>>>(s, f, cam, looper, iter);
+int launchPTDirect(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, cudaStream_t st) {
+    if (s.traversal == RS_TRAVERSAL_EXACT) { k_ptdirect<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, looper, iter); return 1; }
+    cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
+    k_ptdirect<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, looper, iter);
+    k_ptdirect_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, looper, iter);
+    return 2;
 }
 void launchTonemap(const float* radiance, uchar4* ldr, size_t n, int toneMapping, float scale, cudaStream_t st) {
     k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(radiance, ldr, n, toneMapping, scale);

@@ -1,14 +1,14 @@
-// kernels.h -- launchers of the sm_100a kernels (kernels.cu)
+// kernels.h -- launchers of the sm_100a kernels (kernels.cu); the int-returning ones report how many kernels they launched
 #pragma once
 
 #include "device_types.h"
 
 namespace rs {
 
-void launchGBuffer(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, cudaStream_t st);
-void launchRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& p, int looper, int iter, int first, cudaStream_t st);
+int launchGBuffer(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, cudaStream_t st);
+int launchRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& p, int looper, int iter, int first, cudaStream_t st);
 void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, cudaStream_t st);
-void launchPTDirect(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, cudaStream_t st);
+int launchPTDirect(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, cudaStream_t st);
 void launchTonemap(const float* radiance, uchar4* ldr, size_t n, int toneMapping, float scale, cudaStream_t st);
 void launchExportGeom(const float4* geom, const float4* am, float* albedo, float* normal, float* depth, int* motion, size_t n, cudaStream_t st);
 void launchExportResv(const DevScene& s, const ResvD* src, float* out36, int* lightIdx, size_t n, cudaStream_t st);

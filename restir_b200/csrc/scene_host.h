@@ -92,6 +92,7 @@ struct HostScene {
     std::vector<int> fastOrder;            // leaf order -> original primitive id
     std::vector<int> primToFast;           // original primitive id -> position in fastTris
     std::vector<TriGeom> fastTris;         // triangles in leaf order
+    std::vector<int> rank;                 // [6][T]: visiting rank of each primitive's leaf in the reference's 6 orderings
     int fastRoot = 0, fastDepth = 0;
     float fastRootMin[3] = {0, 0, 0}, fastRootMax[3] = {0, 0, 0};
     double fastBuildSeconds = 0.0;
