@@ -1,0 +1,78 @@
+"""torchrun -n N scripts/verify_multigpu.py : strips over N GPUs (NCCL halo exchange) == the single-GPU frame, bit for bit.
+
+Every rank renders its strip of a 1080p spatiotemporal orbit for a few frames; rank 0 additionally renders the full
+frame on its own GPU; the strips' radiance / history reservoirs / light indices are gathered and compared."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import restir_b200 as rb
+from bench import _DevMem
+from restir_b200 import scenes, strips
+
+world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rb.init(local)
+W, H, radius, frames = 1920, 1080, 30.0, 4
+sd = scenes.procedural(1, 200000, 10000, (W, H))
+sc = rb.Scene.from_arrays(sd)
+halo = strips.default_halo(radius)
+rows = strips.strip_rows(H, world, rank)
+fr = sc.frame(W, H, rows=rows, halo=halo)
+fr.set_stream(torch.cuda.current_stream().cuda_stream)
+full = sc.frame(W, H) if rank == 0 else None
+base = rb.Camera.from_scene(sd)
+prm = rb.default_params(reuse=3, radius=radius)
+plan = strips.exchange_plan(H, world, halo)
+
+
+def exchange(plane):
+    ops, keep = [], []
+    for src, dst, r0, r1 in plan:
+        if rank not in (src, dst):
+            continue
+        ptr, rbytes = fr.plane_row(plane, r0)
+        t = torch.as_tensor(_DevMem(ptr, rbytes * (r1 - r0)), device="cuda")
+        keep.append(t)
+        ops.append(dist.P2POp(dist.isend if rank == src else dist.irecv, t, dst if rank == src else src))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+bad_total = 0
+for k in range(frames):
+    cam = base.orbit(k)
+    fr.gbuffer_render(cam)
+    fr.restir_phase_a(cam, prm, k, 0)
+    exchange("resv_temp")
+    fr.restir_phase_b(cam, prm, k, 0)
+    exchange("resv_history")
+    fr.gbuffer_update(cam)
+    if full is not None:
+        full.gbuffer_render(cam); full.restir_direct(cam, prm, k, 0); full.gbuffer_update(cam)
+    for name in ("radiance", "reservoir", "light_index", "matid", "motion"):
+        mine = torch.from_numpy(np.ascontiguousarray(fr.read(name)).view(np.uint8).reshape(-1).copy())
+        sizes = [(strips.strip_rows(H, world, r)[1] - strips.strip_rows(H, world, r)[0]) * W * (mine.numel() // fr.npix) for r in range(world)]
+        parts = [torch.empty(s, dtype=torch.uint8, device="cuda") for s in sizes] if rank == 0 else None
+        dist.gather(mine.cuda(), parts, dst=0)
+        if rank == 0:
+            whole = np.ascontiguousarray(full.read(name)).view(np.uint8).reshape(H * W, -1)
+            got = torch.cat(parts).cpu().numpy().reshape(H * W, -1)
+            bad = int((whole != got).any(1).sum())
+            bad_total += bad
+            if bad:
+                print("frame", k, name, "pixels differing:", bad)
+miss = torch.tensor([fr.halo_miss()], device="cuda")
+dist.all_reduce(miss)
+if rank == 0:
+    print(json.dumps({"verify_multigpu": "ok" if bad_total == 0 and int(miss.item()) == 0 else "MISMATCH", "n_gpus": world, "frames": frames,
+                      "resolution": [W, H], "pixels_differing": bad_total, "halo_miss": int(miss.item()), "halo_rows": halo}))
+dist.destroy_process_group()

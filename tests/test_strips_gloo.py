@@ -1,0 +1,85 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU strip decomposition (restir_b200/strips.py) --
+row ownership, halo extents and the neighbour exchange plan -- moves exactly the rows each rank needs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from restir_b200 import strips
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_strip_rows_partition_every_height():
+    for H in (1, 7, 270, 1080, 2160, 1081):
+        for N in (1, 2, 3, 4, 8):
+            if N > H:
+                continue
+            rows = [strips.strip_rows(H, N, r) for r in range(N)]
+            assert rows[0][0] == 0 and rows[-1][1] == H
+            assert all(rows[i][1] == rows[i + 1][0] for i in range(N - 1))
+            sizes = [b - a for a, b in rows]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_exchange_plan_covers_exactly_the_halos():
+    for H, N, halo in ((1080, 4, 31), (2160, 8, 40), (64, 8, 20), (1080, 2, 0)):
+        plan = strips.exchange_plan(H, N, halo)
+        for dst in range(N):
+            lo, hi = strips.halo_rows(H, N, dst, halo)
+            own = strips.strip_rows(H, N, dst)
+            need = set(range(lo, hi)) - set(range(*own))
+            got = set()
+            for s, d, a, b in plan:
+                if d == dst:
+                    so = strips.strip_rows(H, N, s)
+                    assert so[0] <= a < b <= so[1]          # the sender owns what it sends
+                    assert not (got & set(range(a, b)))      # no row sent twice
+                    got |= set(range(a, b))
+            assert got == need, (H, N, halo, dst)
+    assert strips.default_halo(30.0) == 32 and strips.default_halo(5.0) == 32 and strips.default_halo(47.5) == 49
+
+
+def _worker(rank, world, port, H, W, halo, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = strips.halo_rows(H, world, rank, halo)
+    own = strips.strip_rows(H, world, rank)
+    # a "reservoir plane": 8 floats per pixel, value = global row index where owned, -1 in the halo
+    plane = torch.full((hi - lo, W, 8), -1.0)
+    for r in range(*own):
+        plane[r - lo] = float(r)
+    ops = []
+    for s, d, a, b in strips.exchange_plan(H, world, halo):
+        if rank == s:
+            ops.append(dist.P2POp(dist.isend, plane[a - lo:b - lo].contiguous(), d))
+        elif rank == d:
+            ops.append(dist.P2POp(dist.irecv, plane[a - lo:b - lo], s))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    ok = all(bool((plane[r - lo] == float(r)).all()) for r in range(lo, hi))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_two_ranks_gloo():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 37, 16, 5, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
