@@ -177,6 +177,13 @@ int rstr_tonemap(RstrFrame*, int toneMapping, float scale);
 int rstr_render_frame_host(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter,
                            int toneMapping, void* hostLdr, size_t bytes);
 
+/* Pipelined form: enqueue frame k into LDR slot (0/1) -- render, tone-map, D2H of the image on a copy stream -- and
+ * return at once; rstr_frame_wait_host(slot) blocks until that slot's image has arrived in hostLdr.  Lets the copy of
+ * frame k overlap the rendering of frame k+1 (the reference's GL interop path has no copy at all). */
+int rstr_render_frame_host_async(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter,
+                                 int toneMapping, void* hostLdr, size_t bytes, int slot);
+int rstr_frame_wait_host(RstrFrame*, int slot);
+
 int rstr_frame_sync(RstrFrame*);
 int rstr_frame_read(RstrFrame*, int which, void* host, size_t bytes);
 /* same conversion into DEVICE memory, stream-ordered and without host synchronisation (strip gather to GPU 0) */

@@ -428,6 +428,21 @@ const void* orc_frame_buffer(OrcFrame* f, int which) {
     return nullptr;     /* ORC_BUF_LIGHT_INDEX: the reference keeps no light index (restir.h:7-11) */
 }
 
+void ref_probe(OrcScene* sc, float* out) {
+    DevScene* scene = &sc->dev;
+    glm::vec3 Li(0.f), wi(0.f);
+    float dist = 0.f;
+    glm::vec3 pos(0.1f, 0.5f, 0.2f);
+    float p = scene->sampleDirectLightNoVisibility(pos, glm::vec4(0.3f, 0.6f, 0.2f, 0.7f), Li, wi, dist);
+    Material m = scene->materials[0];
+    m.baseColor = glm::vec3(1.f);
+    glm::vec3 n(0.f, 1.f, 0.f), wo(0.f, 1.f, 0.f);
+    glm::vec3 g = Li * m.BSDF(n, wo, wi) * Math::satDot(n, wi);
+    float w = Math::luminance(g / p);
+    out[0] = p; out[1] = Li.x; out[2] = wi.y; out[3] = dist; out[4] = scene->sumLightPowerInv; out[5] = (float)scene->lightSampler.length;
+    out[6] = w; out[7] = g.x; out[8] = m.BSDF(n, wo, wi).x; out[9] = Math::satDot(n, wi); out[10] = (float)sizeof(DevScene); out[11] = (float)m.type;
+}
+
 float orc_alias_build(int n, const float* values, void* outTable) {
     DiscreteSampler1D<float> smp(std::vector<float>(values, values + n));
     memcpy(outTable, smp.binomDistribs.data(), sizeof(BinomialDistrib<float>) * n);

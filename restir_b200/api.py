@@ -131,6 +131,8 @@ def lib() -> C.CDLL:
     L.rstr_pathtrace_direct.argtypes = [vp, C.POINTER(RstrCamera), ip, ip]
     L.rstr_tonemap.argtypes = [vp, ip, fp]
     L.rstr_render_frame_host.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip, vp, C.c_size_t]
+    L.rstr_render_frame_host_async.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip, vp, C.c_size_t, ip]
+    L.rstr_frame_wait_host.argtypes = [vp, ip]
     L.rstr_frame_sync.argtypes = [vp]
     L.rstr_frame_read.argtypes = [vp, ip, vp, C.c_size_t]
     L.rstr_frame_stage_ms.argtypes = [vp, C.POINTER(fp), ip]
@@ -323,6 +325,13 @@ class Frame:
         ptr, nbytes = (None, 0) if out is None else (out.ctypes.data, out.nbytes)
         p = C.byref(params) if params is not None else None
         _check(lib().rstr_render_frame_host(self.f, C.byref(cam), p, looper, it, tonemap, ptr, nbytes))
+
+    def render_frame_host_async(self, cam, params, looper: int, it: int, tonemap: int, out, slot: int) -> None:
+        p = C.byref(params) if params is not None else None
+        _check(lib().rstr_render_frame_host_async(self.f, C.byref(cam), p, looper, it, tonemap, out.ctypes.data, out.nbytes, slot))
+
+    def wait_host(self, slot: int) -> None:
+        _check(lib().rstr_frame_wait_host(self.f, slot))
 
     def sync(self) -> None:
         _check(lib().rstr_frame_sync(self.f))

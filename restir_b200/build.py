@@ -14,7 +14,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "librestir_b200.so")
+# RSTR_LIBNAME / RSTR_DEFINES: side-by-side experimental builds for A/B timing (scripts/gpu_ab.py); the default is the product
+LIB = os.path.join(HERE, os.environ.get("RSTR_LIBNAME", "librestir_b200.so"))
+EXTRA_DEFINES = [d for d in os.environ.get("RSTR_DEFINES", "").split() if d]
 SOURCES = ["capi.cu", "kernels.cu", "scene_host.cpp", "scene_file.cpp", "bvh_fast.cpp"]
 HEADERS = ["kernels.h", "device_types.h", "scene_host.h", "vecmath.h", os.path.join("..", "..", "include", "restir_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -39,6 +41,7 @@ def nvcc_command(verbose: bool = False) -> list[str]:
         "-I", os.path.join(HERE, "..", "include"),
         "-o", LIB,
     ]
+    cmd += EXTRA_DEFINES
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -47,6 +47,10 @@ struct RstrFrame {
     ResvD* resvTemp = nullptr;
     HitRec* hit = nullptr;
     uchar4* ldr = nullptr;
+    uchar4* ldrB[2] = {nullptr, nullptr};     // double-buffered LDR frames of the pipelined host call
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
+    bool slotBusy[2] = {false, false};
     unsigned int* haloMiss = nullptr;
     int* queue = nullptr;
     unsigned int* queueCount = nullptr;
@@ -84,7 +88,7 @@ static FrameDev toFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
     d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
     d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
-    d.hit = f->hit; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount;
+    d.hit = f->hit; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount; d.rayCounter = f->queueCount + 1;
     return d;
 }
 
@@ -265,6 +269,12 @@ int rstr_frame_destroy(RstrFrame* f) {
     for (int i = 0; i < 2; i++) { cudaFree(f->geom[i]); cudaFree(f->matId[i]); cudaFree(f->resv[i]); }
     cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->hit); cudaFree(f->ldr);
     cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->queueCount);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(f->ldrB[i]);
+        if (f->evRendered[i]) cudaEventDestroy(f->evRendered[i]);
+        if (f->evCopied[i]) cudaEventDestroy(f->evCopied[i]);
+    }
+    if (f->copyStream) cudaStreamDestroy(f->copyStream);
     for (auto& e : f->ev) if (e) cudaEventDestroy(e);
     if (f->xfer) cudaEventDestroy(f->xfer);
     for (auto& e : f->marks) if (e) cudaEventDestroy(e);
@@ -303,7 +313,7 @@ int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int
     alloc((void**)&f->ldr, n * sizeof(uchar4));
     alloc((void**)&f->haloMiss, sizeof(unsigned int));
     alloc((void**)&f->queue, n * sizeof(int));
-    alloc((void**)&f->queueCount, sizeof(unsigned int));
+    alloc((void**)&f->queueCount, 4 * sizeof(unsigned int));
     if (e == cudaSuccess) {
         // a zero-filled reference reservoir has no sample: lightId must read as "none"
         std::vector<ResvD> init(n);
@@ -432,6 +442,46 @@ int rstr_render_frame_host(RstrFrame* f, const RstrCamera* cam, const RstrParams
         CU(cudaMemcpyAsync(hostLdr, f->ldr + off, bytes, cudaMemcpyDeviceToHost, f->stream));
     }
     CU(cudaStreamSynchronize(f->stream));
+    return RSTR_OK;
+}
+
+// Pipelined form of rstr_render_frame_host: enqueues frame k (render + tone-map into LDR slot k&1 + D2H on a copy
+// stream) and returns without waiting; rstr_frame_wait_host(slot) blocks until that slot's image is in host memory.
+int rstr_render_frame_host_async(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter, int toneMapping,
+                                 void* hostLdr, size_t bytes, int slot) {
+    if (!f || slot < 0 || slot > 1 || !hostLdr) return fail(RSTR_ERR_ARG, "rstr_render_frame_host_async: bad argument");
+    const size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
+    if (bytes != n * sizeof(uchar4)) return fail(RSTR_ERR_ARG, "rstr_render_frame_host_async: size mismatch");
+    if (!f->copyStream) {
+        CU(cudaStreamCreateWithFlags(&f->copyStream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaMalloc((void**)&f->ldrB[i], n * sizeof(uchar4)));
+            CU(cudaEventCreateWithFlags(&f->evRendered[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&f->evCopied[i], cudaEventDisableTiming));
+        }
+    }
+    int rc = rstr_gbuffer_render(f, cam);
+    if (rc) return rc;
+    rc = prm ? rstr_restir_direct(f, cam, prm, looper, iter) : rstr_pathtrace_direct(f, cam, looper, iter);
+    if (rc) return rc;
+    if (f->slotBusy[slot]) CU(cudaStreamWaitEvent(f->stream, f->evCopied[slot], 0));   // the slot's previous image must have left the device
+    stageBegin(f, RSTR_T_TONEMAP);
+    launchTonemap(f->radiance + 3 * off, f->ldrB[slot], n, toneMapping, 1.f, f->stream);
+    stageEnd(f, RSTR_T_TONEMAP);
+    g_launches++;
+    CU(cudaGetLastError());
+    rstr_gbuffer_update(f, cam);
+    CU(cudaEventRecord(f->evRendered[slot], f->stream));
+    CU(cudaStreamWaitEvent(f->copyStream, f->evRendered[slot], 0));
+    CU(cudaMemcpyAsync(hostLdr, f->ldrB[slot], bytes, cudaMemcpyDeviceToHost, f->copyStream));
+    CU(cudaEventRecord(f->evCopied[slot], f->copyStream));
+    f->slotBusy[slot] = true;
+    return RSTR_OK;
+}
+
+int rstr_frame_wait_host(RstrFrame* f, int slot) {
+    if (!f || slot < 0 || slot > 1) return fail(RSTR_ERR_ARG, "rstr_frame_wait_host: bad argument");
+    if (f->slotBusy[slot]) CU(cudaEventSynchronize(f->evCopied[slot]));
     return RSTR_OK;
 }
 

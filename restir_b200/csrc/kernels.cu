@@ -16,6 +16,8 @@
 // reference's 6-copy threaded MTBVH walk.
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace rs {
 
 // ------------------------------------------------------------------------------------------------ rays
@@ -181,6 +183,12 @@ struct Hit { float t, bx, by; int prim; };
 // spill to a per-thread local array.
 #define RS_SMEM_STACK 24
 #define RS_BLOCK 128
+#ifndef RS_MINB_GBUF
+#define RS_MINB_GBUF 8      /* __launch_bounds__ minBlocks: 64 registers, 32 warps/SM (A/B on B200: -5 % vs uncapped 72) */
+#endif
+#ifndef RS_MINB_RESTIR
+#define RS_MINB_RESTIR 8    /* 64 registers instead of 94: -12 % on the 1M-triangle scene despite ~200 B of spills */
+#endif
 struct Stack {
     int* sRef;      // &smemRef[0][tid]
     float* sT;      // &smemT[0][tid]
@@ -319,84 +327,103 @@ RS_D bool nearTie(const Cand& a, const Cand& b) {
     return fabsf(a.d - b.d) <= a.err + b.err + 1e-6f * fmaxf(a.d, b.d);
 }
 
-// Closest hit over the traced tree ("while-while": lanes first descend to a leaf, then test triangles together).
-// Returns false when undecided (>= 3 mutually near hits).
-RS_D bool traceClosestFast(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
-    h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
-    const RayF f = makeRayF(r);
-    float t0;
-    if (!slabHit(f, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], FLT_MAX, t0)) return true;
+// Closest hit over the traced tree as a resumable state machine ("while-while": lanes first descend to a leaf, then
+// test triangles together).  closestRun returns true when the ray is finished, false when it suspended itself because
+// fewer than minActive lanes of the warp were still traversing (persistent kernels then refill the idle lanes).
+#define RS_DONE 0x7fffffff
+struct ClosestState {
+    RayT r;
+    RayF f;
     Cand best, second;
-    best.d = FLT_MAX; best.prim = -1; best.bx = best.by = best.tBox = best.err = 0.f;
-    second = best;
-    bool triple = false;
-    float limit = FLT_MAX;           // best.d widened by twice the coarse band: near-tie candidates behind the best hit are still visited
-    int sp = 0;
-    int cur = s.fastRoot;
+    float limit;     // best.d widened by twice the coarse band: near-tie candidates behind the best hit are still visited
+    int sp, cur;
+    bool triple;
+};
+
+RS_D void closestBegin(const DevScene& s, ClosestState& st) {
+    st.f = makeRayF(st.r);
+    st.best.d = FLT_MAX; st.best.prim = -1; st.best.bx = st.best.by = st.best.tBox = st.best.err = 0.f;
+    st.second = st.best;
+    st.triple = false;
+    st.limit = FLT_MAX;
+    st.sp = 0;
+    float t0;
+    st.cur = slabHit(st.f, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], FLT_MAX, t0)
+                 ? s.fastRoot : RS_DONE;
+}
+
+RS_D int closestPop(ClosestState& st, const Stack& stack) {
+    while (st.sp > 0) {
+        --st.sp;
+        if (stack.t(st.sp) <= st.limit) return stack.ref(st.sp);
+    }
+    return RS_DONE;
+}
+
+RS_D bool closestRun(const DevScene& s, ClosestState& st, Stack& stack, int minActive) {
+    const RayF f = st.f;
     for (;;) {
         // ---- descend through internal nodes
-        while (cur >= 0) {
-            const float4* np = s.fastNodes + 4 * (size_t)cur;
+        while (st.cur >= 0 && st.cur != RS_DONE) {
+            const float4* np = s.fastNodes + 4 * (size_t)st.cur;
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
             int2 l = __ldg((const int2*)(np + 3));
             float tL, tR;
-            bool hL = slabHit(f, a.x, a.y, a.z, a.w, b.x, b.y, limit, tL);
-            bool hR = slabHit(f, b.z, b.w, c.x, c.y, c.z, c.w, limit, tR);
+            bool hL = slabHit(f, a.x, a.y, a.z, a.w, b.x, b.y, st.limit, tL);
+            bool hR = slabHit(f, b.z, b.w, c.x, c.y, c.z, c.w, st.limit, tR);
             if (hL && hR) {
                 bool leftNear = tL <= tR;
-                stack.push(sp, leftNear ? l.y : l.x, leftNear ? tR : tL); sp++;
-                cur = leftNear ? l.x : l.y;
-            } else if (hL) cur = l.x;
-            else if (hR) cur = l.y;
-            else {
-                cur = 0x7fffffff;                                   // nothing below: pop
-                while (sp > 0) {
-                    --sp;
-                    if (stack.t(sp) <= limit) { cur = stack.ref(sp); break; }
-                }
-                if (cur == 0x7fffffff) goto done;
-            }
+                stack.push(st.sp, leftNear ? l.y : l.x, leftNear ? tR : tL); st.sp++;
+                st.cur = leftNear ? l.x : l.y;
+            } else if (hL) st.cur = l.x;
+            else if (hR) st.cur = l.y;
+            else st.cur = closestPop(st, stack);
         }
+        if (st.cur == RS_DONE) return true;
         // ---- leaf
         {
-            int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            const RayT& r = st.r;
+            int first = st.cur & 0x07ffffff, count = ((st.cur >> 27) & 7) + 1;
             for (int i = 0; i < count; i++) {
                 Tri t = loadTriFast(s, first + i);
                 Cand x;
                 if (!triHit(r, t.v0, t.v1, t.v2, x.bx, x.by, x.d)) continue;
-                if (!(x.d <= limit)) continue;
+                if (!(x.d <= st.limit)) continue;
                 if (!leafBox(r, t, x.tBox)) continue;               // the reference never sees this triangle
                 x.prim = t.prim;
                 x.err = -1.f;
-                if (best.prim >= 0 && fabsf(x.d - best.d) <= RS_TIE_BAND * fmaxf(x.d, best.d)) {
+                if (st.best.prim >= 0 && fabsf(x.d - st.best.d) <= RS_TIE_BAND * fmaxf(x.d, st.best.d)) {
                     x.err = triDistError(r, t.v0, t.v1, t.v2);
-                    if (nearTie(x, best)) {
-                        if (second.prim >= 0) triple = true;
-                        if (x.d < best.d) { second = best; best = x; limit = x.d * (1.f + 2.f * RS_TIE_BAND); }
-                        else second = x;
+                    if (nearTie(x, st.best)) {
+                        if (st.second.prim >= 0) st.triple = true;
+                        if (x.d < st.best.d) { st.second = st.best; st.best = x; st.limit = x.d * (1.f + 2.f * RS_TIE_BAND); }
+                        else st.second = x;
                         continue;
                     }
                 }
-                if (x.d < best.d) {
+                if (x.d < st.best.d) {
                     if (x.err < 0.f) x.err = triDistError(r, t.v0, t.v1, t.v2);
-                    best = x; second.prim = -1; triple = false;     // anything near the old best is now irrelevant
-                    limit = x.d * (1.f + 2.f * RS_TIE_BAND);
+                    st.best = x; st.second.prim = -1; st.triple = false;     // anything near the old best is now irrelevant
+                    st.limit = x.d * (1.f + 2.f * RS_TIE_BAND);
                 }
             }
         }
-        cur = 0x7fffffff;
-        while (sp > 0) {
-            --sp;
-            if (stack.t(sp) <= limit) { cur = stack.ref(sp); break; }
-        }
-        if (cur == 0x7fffffff) break;
+        st.cur = closestPop(st, stack);
+        if (st.cur == RS_DONE) return true;
+        if (minActive && __popc(__activemask()) < minActive) return false;
     }
-done:
+}
+
+// false = undecided (>= 3 mutually near hits)
+RS_D bool closestResolve(const DevScene& s, const ClosestState& st, Hit& h) {
+    h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
+    const Cand& best = st.best;
+    const Cand& second = st.second;
     if (best.prim < 0) return true;
-    if (triple) return false;
+    if (st.triple) return false;
     if (second.prim >= 0 && nearTie(second, best)) {
         // replay the reference's two visits in its order for this ray
-        const int* rank = s.rank + (size_t)(2 * r.dim + r.lesser) * s.numTris;
+        const int* rank = s.rank + (size_t)(2 * st.r.dim + st.r.lesser) * s.numTris;
         bool bestFirst = __ldg(rank + best.prim) < __ldg(rank + second.prim);
         const Cand& c1 = bestFirst ? best : second;
         const Cand& c2 = bestFirst ? second : best;
@@ -407,6 +434,14 @@ done:
     }
     h.t = best.d; h.bx = best.bx; h.by = best.by; h.prim = best.prim;
     return true;
+}
+
+RS_D bool traceClosestFast(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
+    ClosestState st;
+    st.r = r;
+    closestBegin(s, st);
+    closestRun(s, st, stack, 0);
+    return closestResolve(s, st, h);
 }
 
 // any hit: order does not matter, the criterion above is exact per triangle
@@ -585,14 +620,22 @@ RS_D f3 shadeReservoir(const DevScene& s, const Resv& r, int type, float metalli
 
 // ------------------------------------------------------------------------------------------------ kernels
 // gbuffer.cu:3-73 for one pixel; false = undecided, nothing written
+RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& lastCam, int x, int y, f3 o, const Hit& h);
+
 template <bool EXACT>
 RS_D bool gbufferPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, int x, int y, Stack& stack) {
-    size_t li = planeIndex(f, x, y);
     f3 o, d;
     cameraRay(cam, x, y, .5f, .5f, o, d);
     RayT r = makeRayT(o, d);
     Hit h;
     if (!traceClosest<EXACT>(s, r, h, stack)) return false;
+    gbufferFinish(s, f, lastCam, x, y, o, h);
+    return true;
+}
+
+// gbuffer.cu:28-72: what is stored for a pixel once its hit is known
+RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& lastCam, int x, int y, f3 o, const Hit& h) {
+    size_t li = planeIndex(f, x, y);
     if (h.prim >= 0) {
         Tri t = loadTri(s, h.prim);
         const float4* np = s.triNorm + 3 * (size_t)h.prim;
@@ -617,11 +660,63 @@ RS_D bool gbufferPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, 
         f.matId[0][li] = -1;
         f.albedoMotion[li] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
     }
-    return true;
+}
+
+// ---- persistent form: every lane owns one ray at a time; finished lanes are refilled from a global counter ----
+#define RS_REFILL_BELOW 24     /* a warp stops traversing and refills once fewer lanes than this are still busy */
+// ray index -> pixel: consecutive indices walk an 8x4 tile, then the next tile of the tile row
+RS_D bool pixelOfIndex(const FrameDev& f, unsigned idx, int& x, int& y) {
+    const unsigned tilesX = (unsigned)(f.W + 7) >> 3;
+    unsigned tile = idx >> 5, l = idx & 31;
+    x = (int)(tile % tilesX) * 8 + (int)(l & 7);
+    y = f.rowLo + (int)(tile / tilesX) * 4 + (int)(l >> 3);
+    return x < f.W && y < f.rowHi;
+}
+RS_D unsigned pixelIndexCount(const FrameDev& f) { return (((unsigned)(f.W + 7) >> 3) * ((unsigned)(f.rowHi - f.rowLo + 3) >> 2)) << 5; }
+
+__global__ void __launch_bounds__(RS_BLOCK) k_gbuffer_persist(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                              const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
+    RS_DECLARE_STACK(stack);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned total = pixelIndexCount(f);
+    bool active = false, exhausted = false;
+    int x = 0, y = 0;
+    f3 o = mk3(0.f);
+    ClosestState st;
+    for (;;) {
+        unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted) {
+            unsigned base = 0;
+            int leader = __ffs(idle) - 1;
+            if ((int)lane == leader) base = atomicAdd(f.rayCounter, (unsigned)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            exhausted = base + (unsigned)__popc(idle) >= total;
+            if (!active) {
+                unsigned idx = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
+                if (idx < total && pixelOfIndex(f, idx, x, y)) {
+                    f3 d;
+                    cameraRay(cam, x, y, .5f, .5f, o, d);
+                    st.r = makeRayT(o, d);
+                    closestBegin(s, st);
+                    active = true;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        if (active && closestRun(s, st, stack, RS_REFILL_BELOW)) {
+            Hit h;
+            if (closestResolve(s, st, h)) gbufferFinish(s, f, lastCam, x, y, o, h);
+            else enqueuePixel(f, x, y);
+            active = false;
+        }
+    }
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(RS_BLOCK) k_gbuffer(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GBUF) k_gbuffer(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                       const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
     RS_DECLARE_STACK(stack);
     int x, y;
@@ -773,7 +868,7 @@ RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, 
 }
 
 template <bool EXACT, bool SPATIAL>
-__global__ void __launch_bounds__(RS_BLOCK) k_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_RESTIR) k_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                        const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
                                                        int looper, int iter, int first) {
     RS_DECLARE_STACK(stack);
@@ -973,10 +1068,27 @@ static inline dim3 pixelGrid(const FrameDev& f) { return dim3((f.W + 15) / 16, (
 
 #define RS_FIX_BLOCKS 296   /* 2 per SM; the fix-up kernels stride over the queue */
 
+static bool usePersistent() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RSTR_PERSISTENT"); v = e ? atoi(e) : 0; }   // A/B on B200: the refill variant is 9-20 % slower than the plain grid (86 registers), default off
+    return v != 0;
+}
+static int persistentBlocks() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        n = sms * 6;
+    }
+    return n;
+}
+
 int launchGBuffer(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, cudaStream_t st) {
     if (s.traversal == RS_TRAVERSAL_EXACT) { k_gbuffer<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam); return 1; }
-    cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
-    k_gbuffer<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
+    cudaMemsetAsync(f.queueCount, 0, 2 * sizeof(unsigned int), st);      // queueCount and rayCounter are adjacent
+    if (usePersistent()) k_gbuffer_persist<<<persistentBlocks(), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
+    else k_gbuffer<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
     k_gbuffer_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
     return 2;
 }

@@ -430,8 +430,10 @@ bool loadSceneFile(const std::string& path, HostScene& hs, RstrCamera& cam, std:
         return false;
     }
     // ---- flatten (scene.cpp:159-190) ----
-    hs.vertices.clear(); hs.normals.clear(); hs.texcoords.clear(); hs.materialIds.clear();
+    hs.vertices.clear(); hs.normals.clear(); hs.texcoords.clear(); hs.materialIds.clear(); hs.lightPowerFromFile.clear();
     for (const Instance& inst : instances) {
+        const RstrMaterial& material = hs.materials[inst.materialId];
+        const float powerUnitArea = luminance(mk3(material.baseColor[0], material.baseColor[1], material.baseColor[2])) * 2.f * RS_GLM_PI;
         // Math::buildTransformationMatrix (mathUtil.cpp:13-19)
         M4 translationMat = translate(identity(), inst.translation);
         M4 rotationMat = rotate(identity(), inst.rotation.x * RS_PI / 180.f, mk3(1.f, 0.f, 0.f));
@@ -453,6 +455,11 @@ bool loadSceneFile(const std::string& path, HostScene& hs, RstrCamera& cam, std:
             hs.normals.push_back(normalize(q));
             hs.texcoords.push_back(mesh.t[2 * i]); hs.texcoords.push_back(mesh.t[2 * i + 1]);
             if (i % 3 == 0) hs.materialIds.push_back(inst.materialId);
+            else if (i % 3 == 2 && material.type == 4) {
+                // scene.cpp:176-180 (sic): the instance-local index i addresses the scene-wide array
+                float area = triangleArea(hs.vertices[i - 2], hs.vertices[i - 1], hs.vertices[i]);
+                hs.lightPowerFromFile.push_back(powerUnitArea * area);
+            }
         }
     }
     hs.T = (int)hs.materialIds.size();

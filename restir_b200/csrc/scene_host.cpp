@@ -190,6 +190,10 @@ bool buildHostScene(HostScene& hs, std::string& err) {
         hs.lightUnitRadiance.push_back(radianceUnitArea);
         hs.lightPower.push_back(powerUnitArea * area);
     }
+    if (!hs.lightPowerFromFile.empty()) {
+        if (hs.lightPowerFromFile.size() != hs.lightPower.size()) { err = "internal: light power list size"; return false; }
+        hs.lightPower = hs.lightPowerFromFile;
+    }
     hs.alias.clear(); hs.sumAll = 0.f; hs.sumLightPowerInv = 0.f;
     if (!hs.lightPower.empty()) {
         buildAliasTable(hs.lightPower, hs.alias, hs.sumAll);

@@ -78,6 +78,11 @@ struct HostScene {
     std::vector<int> lightPrimIds;
     std::vector<f3> lightUnitRadiance;
     std::vector<float> lightPower;
+    // Scene files only: power of every emissive triangle as the reference computes it.  scene.cpp:176-180 indexes the
+    // scene-wide flattened vertex array with the INSTANCE-LOCAL vertex index, so for every instance but the first the
+    // area comes from an unrelated triangle of the first instances.  The alias table and sumLightPowerInv inherit that;
+    // the per-candidate area in scene.h:419 does not.  Reproduced verbatim for drop-in parity.
+    std::vector<float> lightPowerFromFile;
     std::vector<AliasEntry> alias;
     float sumAll = 0.f, sumLightPowerInv = 0.f;
 

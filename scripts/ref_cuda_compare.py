@@ -1,0 +1,88 @@
+"""GPU box: the reference's OWN CUDA build (oracle/_ref/ref_headless_*, see oracle/build_ref_cuda.sh) next to this
+library -- timing (reference as shipped, device sync after every launch) and GPU-vs-GPU parity on the same scene file.
+
+    python scripts/ref_cuda_compare.py [config2|config3] [frames]
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+import restir_b200 as rb
+from bench import WORKLOADS, make_scene
+from restir_b200 import scenes
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def run_ref(binary, scene_txt, frames, warmup, reuse, dump=None, dump_frame=-1):
+    cmd = [os.path.join(REF, binary), scene_txt, str(frames), str(warmup), str(reuse)]
+    if dump:
+        cmd += [dump, str(dump_frame)]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(scene_txt))
+    if r.returncode != 0:
+        raise RuntimeError("ref_headless failed: " + r.stderr[-2000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def main():
+    work = sys.argv[1] if len(sys.argv) > 1 else "config2"
+    frames = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+    desc, spec, res, reuse, radius = WORKLOADS[work]
+    sd = make_scene(spec, res)
+    tmp = tempfile.mkdtemp()
+    txt = scenes.write_scene_files(sd, tmp, "scene")
+    out = {"workload": work, "description": desc}
+    # ---- timing: reference CUDA build vs this library, same scene file, same orbit
+    t = run_ref("ref_headless_r30" if radius == 30.0 else "ref_headless_r5", txt, frames, 5, reuse)
+    out["reference_cuda_ms_per_frame"] = t["ms_per_frame"]
+    rb.init(0)
+    sc = rb.Scene.from_file(txt)
+    fr = sc.frame(*res)
+    base = sc.camera
+    prm = rb.default_params(reuse=reuse, radius=radius)
+    for k in range(5):
+        cam = base.orbit(k); fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0); fr.gbuffer_update(cam)
+    fr.sync(); fr.mark(0)
+    for k in range(5, 5 + frames):
+        cam = base.orbit(k); fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0); fr.gbuffer_update(cam)
+    fr.mark(1); fr.sync()
+    out["restir_b200_ms_per_frame"] = fr.elapsed_ms(0, 1) / frames
+    out["speedup_vs_reference_cuda"] = out["reference_cuda_ms_per_frame"] / out["restir_b200_ms_per_frame"]
+    fr.close()
+    # ---- parity: temporal mode (deterministic in the reference), literal radius, frame 3 of the orbit
+    W, H = res
+    P = W * H
+    pre = os.path.join(tmp, "ref_")
+    run_ref("ref_headless_r5", txt, 4, 0, 1, pre, 3)
+    fr = sc.frame(W, H)
+    prm = rb.default_params(reuse=1)
+    for k in range(4):
+        cam = base.orbit(k); fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0)
+        if k < 3:
+            fr.gbuffer_update(cam)
+    ref = {n: np.fromfile(pre + n + ".bin", dt).reshape(shape) for n, dt, shape in
+           (("matid", np.int32, (P,)), ("motion", np.int32, (P,)), ("depth", np.float32, (P,)), ("normal", np.float32, (P, 3)), ("radiance", np.float32, (P, 3)))}
+    mine = {n: fr.read(n) for n in ref}
+    par = {}
+    par["matid_mismatch_pixels"] = int((ref["matid"] != mine["matid"]).sum())
+    par["motion_mismatch_pixels"] = int((ref["motion"] != mine["motion"]).sum())
+    d = np.abs(ref["depth"] - mine["depth"]) / np.maximum(np.abs(ref["depth"]), 1e-20)
+    par["depth_max_rel"] = float(d.max()); par["depth_bitexact_fraction"] = float((ref["depth"] == mine["depth"]).mean())
+    a, b = mine["radiance"].astype(np.float64), ref["radiance"].astype(np.float64)
+    rel = np.abs(a - b).sum(1) / np.maximum(np.abs(b).sum(1), 1e-6)
+    par["radiance_pixels_within_1e-4_rel"] = float((rel <= 1e-4).mean())
+    par["radiance_pixels_bitexact"] = float((mine["radiance"] == ref["radiance"]).all(1).mean())
+    par["radiance_mean_relMSE"] = float(np.mean(((a - b) ** 2).sum(1) / (b.sum(1) ** 2 + 1e-3)))
+    par["mean_radiance_ref"] = float(b.mean()); par["mean_radiance_b200"] = float(a.mean())
+    out["parity_vs_reference_cuda_temporal_frame3"] = par
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

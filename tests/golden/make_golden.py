@@ -87,6 +87,9 @@ def main():
         material_ids=Oracle._view(ref.lib.ref_scene_array(rs, 3), np.int32, (T,)),
         materials=np.frombuffer(Oracle._view(ref.lib.ref_scene_array(rs, 4), np.dtype("V44"), (ref.lib.ref_scene_num_materials(rs),)).tobytes(), np.uint8),
         camera=np.frombuffer(bytes(cam), np.uint8),
+        light_prim_ids=Oracle._view(ref.lib.orc_scene_light_prim_ids(rs), np.int32, (ref.lib.orc_scene_num_lights(rs),)),
+        alias=np.frombuffer(Oracle._view(ref.lib.orc_scene_alias_table(rs), np.dtype("V8"), (ref.lib.orc_scene_num_lights(rs),)).tobytes(), np.uint8),
+        sum_power=ref.lib.orc_scene_sum_light_power(rs),
         file_names=np.array(list(files.keys())), file_texts=np.array(list(files.values())),
     )
     print("golden fixtures written to", HERE)

@@ -85,6 +85,11 @@ def test_scene_file_parser_matches_reference_fixture():
     assert sc.read("materials").tobytes() == g["materials"].tobytes()
     cam = g["camera"].tobytes()
     assert bytes(sc.camera)[:120] == cam[:120] and bytes(sc.camera)[184:] == cam[184:]
+    # light tables: scene.cpp:176-180 computes the power of a later instance's emitters from the wrong triangle;
+    # the alias table and the power sum must reproduce that
+    assert np.array_equal(sc.read("light_prim_ids"), g["light_prim_ids"])
+    assert sc.read("alias").tobytes() == g["alias"].tobytes()
+    assert sc.info.sumLightPower == float(g["sum_power"])
     sc.close()
 
 
