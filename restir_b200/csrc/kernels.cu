@@ -543,8 +543,11 @@ RS_D float GTR2Distrib(float c, float alpha) {                                  
     return aa / denom;
 }
 // Material::BSDF (material.h:218-228; :122 lambertian, :171-186 metallic workflow, :137 dielectric)
-RS_D f3 materialBSDF(int type, float metallic, float roughness, f3 baseColor, f3 n, f3 wo, f3 wi) {
-    if (type == 0) return baseColor * 1.f / RS_PI;
+// `diffuse` = baseColor * 1.f / Pi ("baseColor * PiInv", material.h:123,185): three IEEE divisions that do not depend on
+// wi, hoisted out of the 32-candidate loop by the callers
+RS_D f3 diffuseTerm(f3 baseColor) { return baseColor * 1.f / RS_PI; }
+RS_D f3 materialBSDF(int type, float metallic, float roughness, f3 baseColor, f3 diffuse, f3 n, f3 wo, f3 wi) {
+    if (type == 0) return diffuse;
     if (type == 1) {
         float alpha = roughness * roughness;
         f3 h = normalize(wo + wi);
@@ -554,7 +557,7 @@ RS_D f3 materialBSDF(int type, float metallic, float roughness, f3 baseColor, f3
         f3 f = mix(f0, mk3(1.f), pow5(1.f - dot(h, wo)));
         float g = schlickG(fabsf(cosO), alpha) * schlickG(fabsf(cosI), alpha);
         float d = GTR2Distrib(dot(n, h), alpha);
-        return mix(baseColor * 1.f / RS_PI * (1.f - metallic), mk3(g * d / (4.f * cosI * cosO)), f);
+        return mix(diffuse * (1.f - metallic), mk3(g * d / (4.f * cosI * cosO)), f);
     }
     return mk3(0.f);
 }
@@ -611,7 +614,7 @@ RS_D void writeRadiance(const FrameDev& f, size_t li, f3 direct, int iter) {
 RS_D f3 shadeReservoir(const DevScene& s, const Resv& r, int type, float metallic, float roughness, f3 n, f3 wo) {
     f3 direct = mk3(0.f);
     if (!resvInvalid(r)) {
-        f3 LiBSDF = lightLe(s, r.lightId) * materialBSDF(type, metallic, roughness, mk3(1.f), n, wo, r.wi);
+        f3 LiBSDF = lightLe(s, r.lightId) * materialBSDF(type, metallic, roughness, mk3(1.f), diffuseTerm(mk3(1.f)), n, wo, r.wi);
         direct = LiBSDF / luminance(LiBSDF) * r.w / (float)r.M;
     }
     if (hasNanOrInf(direct)) direct = mk3(0.f);
@@ -824,6 +827,7 @@ RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, 
     f3 wo = -d;
     if (type != 2 && dot(nrm, wo) < 0.f) nrm = -nrm;                                 // restir.cu:150-153
     Resv R = emptyResv();
+    const f3 diffuse = diffuseTerm(mk3(1.f));                                        // material.baseColor = 1 (restir.cu:141)
     const int nc = prm.numCandidates;
     for (int i = 0; i < nc; i++) {                                                   // restir.cu:156-169
         float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
@@ -831,7 +835,7 @@ RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, 
         float dist = 0.f;
         int lid = -1;
         float p = s.numLights > 0 ? sampleLight(s, pos, c0, c1, c2, c3, Li, wi, dist, lid) : -1.f;
-        f3 g = Li * materialBSDF(type, metallic, roughness, mk3(1.f), nrm, wo, wi) * satDot(nrm, wi);
+        f3 g = Li * materialBSDF(type, metallic, roughness, mk3(1.f), diffuse, nrm, wo, wi) * satDot(nrm, wi);
         float weight = luminance(g / p);
         if (isNanOrInf(weight) || p <= 0.f) weight = 0.f;
         float rnd = rng.next();
@@ -987,7 +991,7 @@ RS_D bool ptdirectPixel(const DevScene& s, const FrameDev& f, const CamDev& cam,
                     f3 wi = pts * (1.f / sqrtf(len2));
                     float pdf = d4.w * len2 / fabsf(dot(n, wi));
                     if (pdf > 0.f)
-                        direct = Li * materialBSDF(type, __ldg(&m->metallic), __ldg(&m->roughness), baseColor, nrm, wo, wi) * satDot(nrm, wi) / pdf;
+                        direct = Li * materialBSDF(type, __ldg(&m->metallic), __ldg(&m->roughness), baseColor, diffuseTerm(baseColor), nrm, wo, wi) * satDot(nrm, wi) / pdf;
                 }
             }
         }
