@@ -43,6 +43,8 @@ WORKLOADS = {
 BYTES_PER_PIXEL = {0: 96, 1: 176, 2: 248, 3: 248}
 # ... split per kernel for the spatiotemporal frame: G-buffer write 36 | phase A: own G-buffer 24 + previous G-buffer 20 +
 # previous reservoir 36 + post-temporal reservoir 36 + history reservoir 36 = 152 | phase B: reservoir 36 + albedo 12 + radiance 12 = 60
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {("config2", "ris"): (372.6e6, "profiles/r01_prof_config2_r4.summary.txt")}
 KERNEL_BYTES_PER_PIXEL = {"gbuffer": 36, "ris": {0: 60, 1: 140, 2: 116, 3: 152}, "spatial": 60}
 
 
@@ -358,7 +360,9 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": "k_restir_a", "spatial": "k_restir_b"}[dom],
-                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC.get((args.workload, dom), (None, None))[0] if world == 1 else None,
+                         "traffic_source": NCU_TRAFFIC.get((args.workload, dom), (None, None))[1],
                          "algorithmic_bytes_per_pixel": bpp, "kernel_ms": stage_ms[dom],
                          "note": "traversal / light-gather bound kernel; HBM fraction reported as required, rays/s below is the telling figure"},
             "stage_ms": stage_ms,
@@ -370,7 +374,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             kind = reference_kind()
             t1, threads = cpu_frames(kind, sd, reuse, radius, 1, 0)
-            n = max(1, min(args.steps, int(15.0 / max(t1, 1e-3))))
+            n = max(1, min(args.steps, 60, int(15.0 / max(t1, 1e-3))))
             dt, threads = cpu_frames(kind, sd, reuse, radius, n, 1 if t1 < 5 else 0)
             line["cpu_baseline"] = {"value": P / (dt / n) / 1e6, "unit": "Mpixel/s", "cores": threads, "kind": kind,
                                     "sample": "%d frames of the same orbit at %dx%d, OpenMP over rows" % (n, W, H)}
@@ -384,8 +388,9 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=5)
+    # 600 frames = ten laps of the 60-frame orbit clock: ~0.3 s on the device, long enough for stable clocks / nvidia-smi samples
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
