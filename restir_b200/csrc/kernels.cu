@@ -315,7 +315,7 @@ RS_D bool slabHit(const RayF& f, float lx, float ly, float lz, float hx, float h
 // with candidates visited in the order of the ray's MTBVH ordering (bvh.cpp:156-193 -> DevScene::rank).  Because
 // boxDistance <= d up to rounding, the order only matters between hits whose distances differ by less than the
 // Moller-Trumbore rounding error; the traced-tree walk keeps the best hit plus one such runner-up and replays the
-// reference's two visits.  Three or more mutually near hits are left to the reference-order walk (fix-up kernel).
+// reference's two visits.  Up to four mutually near hits are replayed; more are left to the reference-order walk (fix-up kernel).
 struct Cand { float d, bx, by, tBox, err; int prim; };
 
 RS_D bool leafBox(const RayT& r, const Tri& t, float& tBox) {
@@ -331,19 +331,23 @@ RS_D bool nearTie(const Cand& a, const Cand& b) {
 // test triangles together).  closestRun returns true when the ray is finished, false when it suspended itself because
 // fewer than minActive lanes of the warp were still traversing (persistent kernels then refill the idle lanes).
 #define RS_DONE 0x7fffffff
+#define RS_MAX_EXTRA 2     /* near-tie candidates beyond best + second, kept in local memory (corners where 3-4 surfaces meet) */
 struct ClosestState {
     RayT r;
     RayF f;
     Cand best, second;
+    Cand extra[RS_MAX_EXTRA];
     float limit;     // best.d widened by twice the coarse band: near-tie candidates behind the best hit are still visited
     int sp, cur;
-    bool triple;
+    int nExtra;
+    bool triple;     // more mutually near hits than can be stored: undecided
 };
 
 RS_D void closestBegin(const DevScene& s, ClosestState& st) {
     st.f = makeRayF(st.r);
     st.best.d = FLT_MAX; st.best.prim = -1; st.best.bx = st.best.by = st.best.tBox = st.best.err = 0.f;
     st.second = st.best;
+    st.nExtra = 0;
     st.triple = false;
     st.limit = FLT_MAX;
     st.sp = 0;
@@ -395,15 +399,17 @@ RS_D bool closestRun(const DevScene& s, ClosestState& st, Stack& stack, int minA
                 if (st.best.prim >= 0 && fabsf(x.d - st.best.d) <= RS_TIE_BAND * fmaxf(x.d, st.best.d)) {
                     x.err = triDistError(r, t.v0, t.v1, t.v2);
                     if (nearTie(x, st.best)) {
-                        if (st.second.prim >= 0) st.triple = true;
-                        if (x.d < st.best.d) { st.second = st.best; st.best = x; st.limit = x.d * (1.f + 2.f * RS_TIE_BAND); }
-                        else st.second = x;
+                        Cand keep = x;                      // the candidate that does not become `best`
+                        if (x.d < st.best.d) { keep = st.best; st.best = x; st.limit = x.d * (1.f + 2.f * RS_TIE_BAND); }
+                        if (st.second.prim < 0) st.second = keep;
+                        else if (st.nExtra < RS_MAX_EXTRA) st.extra[st.nExtra++] = keep;
+                        else st.triple = true;
                         continue;
                     }
                 }
                 if (x.d < st.best.d) {
                     if (x.err < 0.f) x.err = triDistError(r, t.v0, t.v1, t.v2);
-                    st.best = x; st.second.prim = -1; st.triple = false;     // anything near the old best is now irrelevant
+                    st.best = x; st.second.prim = -1; st.nExtra = 0; st.triple = false;     // anything near the old best is now irrelevant
                     st.limit = x.d * (1.f + 2.f * RS_TIE_BAND);
                 }
             }
@@ -414,25 +420,35 @@ RS_D bool closestRun(const DevScene& s, ClosestState& st, Stack& stack, int minA
     }
 }
 
-// false = undecided (>= 3 mutually near hits)
+// false = undecided (more mutually near hits than RS_MAX_EXTRA + 2)
 RS_D bool closestResolve(const DevScene& s, const ClosestState& st, Hit& h) {
     h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
     const Cand& best = st.best;
-    const Cand& second = st.second;
     if (best.prim < 0) return true;
     if (st.triple) return false;
-    if (second.prim >= 0 && nearTie(second, best)) {
-        // replay the reference's two visits in its order for this ray
-        const int* rank = s.rank + (size_t)(2 * st.r.dim + st.r.lesser) * s.numTris;
-        bool bestFirst = __ldg(rank + best.prim) < __ldg(rank + second.prim);
-        const Cand& c1 = bestFirst ? best : second;
-        const Cand& c2 = bestFirst ? second : best;
-        bool take2 = c2.tBox < c1.d && c2.d < c1.d;
-        const Cand& w = take2 ? c2 : c1;
-        h.t = w.d; h.bx = w.bx; h.by = w.by; h.prim = w.prim;
-        return true;
-    }
     h.t = best.d; h.bx = best.bx; h.by = best.by; h.prim = best.prim;
+    if (st.second.prim < 0) return true;
+    // replay the reference's visits of the hits that are near the best one, in its order for this ray
+    const int* rank = s.rank + (size_t)(2 * st.r.dim + st.r.lesser) * s.numTris;
+    Cand c[RS_MAX_EXTRA + 2];
+    int rk[RS_MAX_EXTRA + 2];
+    int n = 0;
+    c[n] = best; rk[n] = __ldg(rank + best.prim); n++;
+    if (nearTie(st.second, best)) { c[n] = st.second; rk[n] = __ldg(rank + st.second.prim); n++; }
+    for (int i = 0; i < st.nExtra; i++)
+        if (nearTie(st.extra[i], best)) { c[n] = st.extra[i]; rk[n] = __ldg(rank + st.extra[i].prim); n++; }
+    if (n == 1) return true;
+    float closest = FLT_MAX;
+    for (int k = 0; k < n; k++) {                      // n <= 4: selection by increasing rank
+        int m = -1;
+        for (int i = 0; i < n; i++)
+            if (rk[i] >= 0 && (m < 0 || rk[i] < rk[m])) m = i;
+        if (c[m].tBox < closest && c[m].d < closest) {  // scene.h:260,267
+            closest = c[m].d;
+            h.t = c[m].d; h.bx = c[m].bx; h.by = c[m].by; h.prim = c[m].prim;
+        }
+        rk[m] = -1;
+    }
     return true;
 }
 
