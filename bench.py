@@ -212,12 +212,20 @@ def run_b200(args):
     sd = make_scene(spec, res)
     sc = rb.Scene.from_arrays(sd)
     halo = strips.default_halo(radius) if world > 1 else 0
-    rows = strips.strip_rows(H, world, rank)
-    fr = sc.frame(W, H, rows=rows, halo=halo)
     base = rb.Camera.from_scene(sd)
     prm = rb.default_params(reuse=reuse, radius=radius)
+    bounds = strips.uniform_bounds(H, world)
+    if world > 1 and not args.uniform_strips:
+        # every rank renders the first frame's G-buffer once (the scene is replicated anyway) and derives the same
+        # cost-balanced cuts from it: sky rows are almost free, ground rows carry the candidate loop and two more rays
+        probe = sc.frame(W, H)
+        probe.gbuffer_render(base.orbit(0))
+        bounds = strips.balanced_bounds(strips.row_cost_from_matid(probe.read("matid"), W), world, min_rows=max(8, halo))
+        probe.close()
+    rows = strips.strip_rows(H, world, rank, bounds)
+    fr = sc.frame(W, H, rows=rows, halo=halo)
 
-    plan = strips.exchange_plan(H, world, halo) if world > 1 else []
+    plan = strips.exchange_plan(H, world, halo, bounds) if world > 1 else []
     if world > 1:
         fr.set_stream(torch.cuda.current_stream().cuda_stream)
 
@@ -315,23 +323,46 @@ def run_b200(args):
         for o in outs:
             rb.pinned_free(o)
     else:
+        # strips -> GPU 0 -> pinned host frame, on a side stream so that it overlaps the next frame's rendering:
+        # ranks > 0 send their tone-mapped strip (NCCL over NVLink), rank 0 receives into place and copies D2H
+        counts = [(bounds[r + 1] - bounds[r]) * W * 4 for r in range(world)]
+        offs = [bounds[r] * W * 4 for r in range(world)]
         host = torch.empty(P * 4, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
-        counts = [(strips.strip_rows(H, world, r)[1] - strips.strip_rows(H, world, r)[0]) * W * 4 for r in range(world)]
-        gathered = [torch.empty(c, dtype=torch.uint8, device="cuda") for c in counts] if rank == 0 else None
+        full = torch.empty(P * 4, dtype=torch.uint8, device="cuda") if rank == 0 else None
+        mine = full[offs[0]:offs[0] + counts[0]] if rank == 0 else torch.empty(counts[rank], dtype=torch.uint8, device="cuda")
+        side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        ev_ldr, ev_sent = torch.cuda.Event(), torch.cuda.Event()
 
-        # gather of LDR strips to GPU 0 (NCCL) followed by one D2H on rank 0
-        ldr_dev = torch.empty(counts[rank], dtype=torch.uint8, device="cuda")
-        barrier()
+        def e2e_frame(kk):
+            frame(kk)
+            main.wait_event(ev_sent)                 # the previous frame's strip must have left `mine`
+            fr.tonemap(rb.TONEMAP_ACES, 1.0)
+            fr.read_into_device("ldr", mine.data_ptr(), counts[rank])
+            ev_ldr.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev_ldr)
+                if rank == 0:
+                    reqs = [dist.irecv(full[offs[r]:offs[r] + counts[r]], r) for r in range(1, world)]
+                    for q in reqs:
+                        q.wait()
+                    host.copy_(full, non_blocking=True)
+                else:
+                    dist.isend(mine, 0).wait()
+                ev_sent.record(side)
+
+        ev_sent.record(side)
+        for _ in range(3):
+            e2e_frame(k); k += 1
+        barrier(); side.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            frame(k); k += 1
-            fr.tonemap(rb.TONEMAP_ACES, 1.0)
-            fr.read_into_device("ldr", ldr_dev.data_ptr(), counts[rank])
-            dist.gather(ldr_dev, gathered, dst=0)
-            if rank == 0:
-                host.copy_(torch.cat(gathered), non_blocking=False)
+            e2e_frame(k); k += 1
+        side.synchronize()
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
+        if rank == 0:
+            assert int(host.max()) > 0
     halo_miss = fr.halo_miss()
     if world > 1:
         t = torch.tensor([halo_miss], device="cuda", dtype=torch.int64)
@@ -352,7 +383,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "description": desc, "resolution": [W, H], "triangles": info.numTris, "emissive_triangles": info.numLights,
                        "reuse": reuse, "candidates": 32, "temporal_cap": 20, "spatial_neighbours": 5, "spatial_radius_px": radius,
-                       "parallelism": "strips%d" % world, "halo_rows": halo,
+                       "parallelism": "strips%d" % world, "halo_rows": halo, "strip_bounds": bounds,
                        "l2": "no explicit flush: the per-frame pixel planes (%.0f MB) exceed the 126 MB L2" % (P * 212 / 1e6)},
             "e2e": {"value": P / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms, "ms_per_step_synchronous_call": e2e_sync_ms,
                     "api": "rstr_render_frame_host_async + rstr_frame_wait_host (two pinned host frames)" if world == 1 else "strips gathered to rank 0 over NCCL, one D2H",
@@ -394,6 +425,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -65,6 +65,8 @@ typedef struct RstrParams {
     int   numSpatial;      /* restir.cu:93   5 neighbours */
     float spatialRadius;   /* restir.cu:49   5 px */
     int   reuse;           /* Settings::reservoirReuse (common.h:36-43): bit0 temporal, bit1 spatial */
+    int   spatialPasses;   /* 1 = as shipped (restir.cu:196-199); 2..3 add the commented-out pass restir.cu:201-209
+                              (publish, barrier, new 5-neighbour aggregate, preClampedMerge<4>); values < 1 mean 1 */
 } RstrParams;
 
 #define RSTR_REUSE_NONE 0

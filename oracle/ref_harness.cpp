@@ -341,7 +341,35 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* ocam, const OrcParams* prm,
             c.status = 2; c.rng = rng; c.r = reservoir; c.is = intersec; c.mat = material;
         }
     }
-    /* phase B: restir.cu:196-230 */
+    /* phase B: restir.cu:196-230; passes 2..n = the commented-out block :201-209 (preClampedMerge<4>) */
+    const int passes = (reuseState & ReservoirReuse::Spatial) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
+    for (int pass = 1; pass <= passes; pass++) {
+        if (pass > 1) {
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < cam.resolution.x * cam.resolution.y; i++)
+                if (f->carry[i].status == 2) reservoirTemp[i] = f->carry[i].r;
+        }
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int y = 0; y < cam.resolution.y; y++) {
+            for (int x = 0; x < cam.resolution.x; x++) {
+                OrcFrame::Carry& c = f->carry[y * cam.resolution.x + x];
+                if (c.status != 2) continue;
+                Sampler rng = c.rng;
+                DirectReservoir agg;
+                for (int i = 0; i < prm->numSpatial; i++) {
+                    float rx = sample1D(rng), ry = sample1D(rng);
+                    DirectReservoir spatial = findSpatialNeighborDisk(reservoirTemp, x, y, gBuffer, glm::vec2(rx, ry), prm->spatialRadius);
+                    if (!spatial.invalid()) agg.merge(spatial, sample1D(rng));
+                }
+                if (pass == 1) {
+                    if (!agg.invalid() && !c.r.invalid()) c.r.merge(agg, sample1D(rng));
+                } else {
+                    if (!agg.invalid()) c.r.preClampedMerge<4>(agg, sample1D(rng));
+                }
+                c.rng = rng;
+            }
+        }
+    }
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < cam.resolution.y; y++) {
         for (int x = 0; x < cam.resolution.x; x++) {
@@ -350,19 +378,9 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* ocam, const OrcParams* prm,
             glm::vec3 direct(0.f);
             if (c.status == 1) direct = glm::vec3(1.f);
             if (c.status == 2) {
-                Sampler rng = c.rng;
                 DirectReservoir reservoir = c.r;
                 const Intersection& intersec = c.is;
                 const Material& material = c.mat;
-                if (reuseState & ReservoirReuse::Spatial) {
-                    DirectReservoir agg;
-                    for (int i = 0; i < prm->numSpatial; i++) {
-                        float rx = sample1D(rng), ry = sample1D(rng);
-                        DirectReservoir spatial = findSpatialNeighborDisk(reservoirTemp, x, y, gBuffer, glm::vec2(rx, ry), prm->spatialRadius);
-                        if (!spatial.invalid()) agg.merge(spatial, sample1D(rng));
-                    }
-                    if (!agg.invalid() && !reservoir.invalid()) reservoir.merge(agg, sample1D(rng));
-                }
                 DirectLiSample sample = reservoir.sample;
                 if (!reservoir.invalid()) {
                     glm::vec3 LiBSDF = sample.Li * material.BSDF(intersec.norm, intersec.wo, sample.wi);

@@ -904,7 +904,37 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
     { shTotal.rays += sh.rays; shTotal.nodes += sh.nodes; if (sh.maxNodes > shTotal.maxNodes) shTotal.maxNodes = sh.maxNodes; }
     }
     f->shadow = shTotal;
-    /* ---- phase B: :196-230 */
+    /* ---- phase B: :196-230.  Passes 2..n follow the commented-out block :201-209: the reservoir of the previous pass
+     * is published through reservoirTemp for every shaded pixel (no checkValidity), a grid barrier, a fresh 5-neighbour
+     * aggregate, and `if (!aggregate.invalid()) reservoir.preClampedMerge<4>(aggregate, sample1D(rng))`. */
+    const int passes = (reuse & 2) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
+    for (int pass = 1; pass <= passes; pass++) {
+        if (pass > 1) {
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < W * H; i++)
+                if (f->carry[i].status == 2) tmp[i] = f->carry[i].r;              /* :203 */
+        }
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int y = 0; y < H; y++) {
+            for (int x = 0; x < W; x++) {
+                OrcFrame::Carry& c = f->carry[y * W + x];
+                if (c.status != 2) continue;
+                Rng rng(0, 0); rng.x = c.rng;
+                Resv agg;                                                          /* :87-100 */
+                for (int i = 0; i < prm->numSpatial; i++) {
+                    float rx = rng.next(), ry = rng.next();
+                    Resv sp = findSpatialNeighborDisk(f, tmp, x, y, rx, ry, prm->spatialRadius);
+                    if (!sp.invalid()) agg.merge(sp, rng.next());
+                }
+                if (pass == 1) {
+                    if (!agg.invalid() && !c.r.invalid()) c.r.merge(agg, rng.next());        /* :197-199 */
+                } else {
+                    if (!agg.invalid()) c.r.preClampedMerge(4, agg, rng.next());             /* :206-208 */
+                }
+                c.rng = rng.x;
+            }
+        }
+    }
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < H; y++) {
         for (int x = 0; x < W; x++) {
@@ -913,18 +943,8 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
             V3 direct = v3(0.f);
             if (c.status == 1) direct = v3(1.f);
             if (c.status == 2) {
-                Rng rng(0, 0); rng.x = c.rng;
                 Resv reservoir = c.r;
                 const OrcMaterial& material = sc.materials[c.matId];
-                if (reuse & 2) {
-                    Resv agg;                                                  /* :87-100 */
-                    for (int i = 0; i < prm->numSpatial; i++) {
-                        float rx = rng.next(), ry = rng.next();
-                        Resv sp = findSpatialNeighborDisk(f, tmp, x, y, rx, ry, prm->spatialRadius);
-                        if (!sp.invalid()) agg.merge(sp, rng.next());
-                    }
-                    if (!agg.invalid() && !reservoir.invalid()) reservoir.merge(agg, rng.next());   /* :197-199 */
-                }
                 Sample s = reservoir.s;                                        /* :216-222 */
                 if (!reservoir.invalid()) {
                     V3 LiBSDF = s.Li * materialBSDF(material, v3(1.f), c.n, c.wo, s.wi);

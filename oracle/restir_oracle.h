@@ -53,6 +53,7 @@ typedef struct OrcParams {
     int   numSpatial;      /* restir.cu:93    5 */
     float spatialRadius;   /* restir.cu:49    5 */
     int   reuse;           /* common.h:36-43 bit0 temporal, bit1 spatial */
+    int   spatialPasses;   /* restir.cu:196-209: 1 = as shipped; 2..3 = the commented-out extra pass(es), preClampedMerge<4> */
 } OrcParams;
 
 /* buffer selectors for orc_frame_buffer */

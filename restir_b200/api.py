@@ -51,6 +51,7 @@ class RstrParams(C.Structure):
         ("numSpatial", C.c_int),
         ("spatialRadius", C.c_float),
         ("reuse", C.c_int),
+        ("spatialPasses", C.c_int),
     ]
 
 
@@ -163,9 +164,9 @@ def init(device: int = 0) -> None:
     _check(lib().rstr_init(device))
 
 
-def default_params(reuse: int = REUSE_TEMPORAL, radius: float = 5.0, k: int = 5, cap: int = 20, candidates: int = 32) -> RstrParams:
-    """restir.cu literals (32 candidates, cap 20, 5 neighbours, radius 5 px) unless overridden."""
-    return RstrParams(candidates, cap, k, radius, reuse)
+def default_params(reuse: int = REUSE_TEMPORAL, radius: float = 5.0, k: int = 5, cap: int = 20, candidates: int = 32, passes: int = 1) -> RstrParams:
+    """restir.cu literals (32 candidates, cap 20, 5 neighbours, radius 5 px, one spatial pass) unless overridden."""
+    return RstrParams(candidates, cap, k, radius, reuse, passes)
 
 
 def launch_count() -> int:

@@ -45,6 +45,7 @@ struct RstrFrame {
     float* radiance = nullptr;
     ResvD* resv[2] = {nullptr, nullptr};
     ResvD* resvTemp = nullptr;
+    ResvD* resvTemp2 = nullptr;    // second publication buffer, allocated when spatialPasses > 1
     HitRec* hit = nullptr;
     uchar4* ldr = nullptr;
     uchar4* ldrB[2] = {nullptr, nullptr};     // double-buffered LDR frames of the pipelined host call
@@ -165,6 +166,7 @@ int rstr_init(int device) {
 
 void rstr_params_default(RstrParams* p) {
     p->numCandidates = 32; p->temporalCap = 20; p->numSpatial = 5; p->spatialRadius = 5.f; p->reuse = RSTR_REUSE_TEMPORAL;   // common.cpp:14
+    p->spatialPasses = 1;
 }
 
 int rstr_scene_create(const RstrSceneDesc* desc, RstrScene** out) {
@@ -267,7 +269,7 @@ int rstr_frame_destroy(RstrFrame* f) {
     if (!f) return RSTR_OK;
     if (f->stream) cudaStreamSynchronize(f->stream);
     for (int i = 0; i < 2; i++) { cudaFree(f->geom[i]); cudaFree(f->matId[i]); cudaFree(f->resv[i]); }
-    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->hit); cudaFree(f->ldr);
+    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->resvTemp2); cudaFree(f->hit); cudaFree(f->ldr);
     cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->queueCount);
     for (int i = 0; i < 2; i++) {
         cudaFree(f->ldrB[i]);
@@ -388,11 +390,21 @@ int rstr_restir_phase_b(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     if (rc) return rc;
     (void)looper;
     if (prm->reuse & 2) {
+        const int passes = prm->spatialPasses < 1 ? 1 : prm->spatialPasses;
+        if (passes > 1 && f->bufRows != f->H)
+            return fail(RSTR_ERR_ARG, "spatialPasses > 1 needs a halo exchange per pass; not supported for strip frames yet");
+        if (passes > 1 && !f->resvTemp2) {
+            CU(cudaMalloc((void**)&f->resvTemp2, f->nBuf * sizeof(ResvD)));
+            CU(cudaMemcpyAsync(f->resvTemp2, f->resvTemp, f->nBuf * sizeof(ResvD), cudaMemcpyDeviceToDevice, f->stream));
+        }
         FrameDev d = toFrameDev(f, f->row0, f->row1);
+        ResvD* buf[2] = {f->resvTemp, f->resvTemp2};
         stageBegin(f, RSTR_T_SPATIAL);
-        launchRestirB(f->sc->dev, d, *prm, iter, f->stream);
+        for (int pass = 1; pass <= passes; pass++) {
+            launchRestirB(f->sc->dev, d, *prm, iter, buf[(pass - 1) & 1], buf[pass & 1], pass, pass == passes ? 1 : 0, f->stream);
+            g_launches++;
+        }
         stageEnd(f, RSTR_T_SPATIAL);
-        g_launches++;
         CU(cudaGetLastError());
     }
     f->resvOut ^= 1;                                                       // std::swap, restir.cu:434

@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant
 }
 
 // restir.cu:47-85 (+ mathUtil.h:128-132 toConcentricDisk)
-RS_D Resv findSpatial(const FrameDev& f, int x, int y, size_t li, float rx, float ry, float radius) {
+RS_D Resv findSpatial(const FrameDev& f, const ResvD* src, int x, int y, size_t li, float rx, float ry, float radius) {
     float rr = sqrtf(rx);
     float theta = ry * RS_PI * 2.0f;
     float px_ = cosf(theta) * rr * radius, py_ = sinf(theta) * rr * radius;
@@ -927,32 +927,53 @@ RS_D Resv findSpatial(const FrameDev& f, int x, int y, size_t li, float rx, floa
     bool diff = dot(mk3(g.x, g.y, g.z), mk3(pg.x, pg.y, pg.z)) < .9f;
     if (fabsf(g.w - pg.w) > g.w * .1f) diff = true;
     if (diff) return emptyResv();
-    return loadResv(f.resvTemp + pli);
+    return loadResv(src + pli);
 }
 
+// One spatial pass.  pass 1 = restir.cu:196-199; passes 2.. = the commented-out block restir.cu:201-209
+// (preClampedMerge<4>).  `src` holds every pixel's reservoir of the previous stage, `dst` receives this pass's result
+// when another pass follows; the last pass shades.  The reference publishes through ONE buffer (reservoirTemp) between
+// grid barriers; with two buffers the same content is kept by copying un-shaded pixels through and by leaving the
+// last published reservoir in f.resvTemp.
 __global__ void __launch_bounds__(128) k_restir_b(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
-                                                  const __grid_constant__ RstrParams prm, int iter) {
+                                                  const __grid_constant__ RstrParams prm, int iter,
+                                                  const ResvD* __restrict__ src, ResvD* __restrict__ dst, int pass, int last) {
     int x, y;
     if (!pixelOf(f, x, y)) return;
     size_t li = planeIndex(f, x, y);
-    const float4* q = (const float4*)(f.hit + li);
+    float4* q = (float4*)(f.hit + li);
     float4 h0 = q[0], h1 = q[1];
     int matId = __float_as_int(h0.w);
-    if (matId < 0) return;                          // phase A already wrote this pixel's radiance
+    if (matId < 0) {                                // phase A already wrote this pixel's radiance
+        if (!last) { const float4* a = (const float4*)(src + li); float4* b = (float4*)(dst + li); b[0] = a[0]; b[1] = a[1]; }
+        else if (src != f.resvTemp) { const float4* a = (const float4*)(src + li); float4* b = (float4*)(f.resvTemp + li); b[0] = a[0]; b[1] = a[1]; }
+        return;
+    }
     Rng rng; rng.x = __float_as_uint(h1.w);
-    f3 nrm = mk3(h0.x, h0.y, h0.z), wo = mk3(h1.x, h1.y, h1.z);
-    const RstrMaterial* m = s.materials + matId;
-    int type = __ldg(&m->type);
-    float metallic = __ldg(&m->metallic), roughness = __ldg(&m->roughness);
-    Resv R = loadResv(f.resvTemp + li);
+    Resv R = loadResv(src + li);
+    const Resv published = R;
     Resv S = emptyResv();                                                            // restir.cu:87-100
     for (int i = 0; i < prm.numSpatial; i++) {
         float rx = rng.next(), ry = rng.next();
-        Resv N = findSpatial(f, x, y, li, rx, ry, prm.spatialRadius);
+        Resv N = findSpatial(f, src, x, y, li, rx, ry, prm.spatialRadius);
         if (!resvInvalid(N)) resvMerge(S, N, rng.next());
     }
-    if (!resvInvalid(S) && !resvInvalid(R)) resvMerge(R, S, rng.next());             // restir.cu:197-199
-    writeRadiance(f, li, shadeReservoir(s, R, type, metallic, roughness, nrm, wo), iter);
+    if (pass == 1) {
+        if (!resvInvalid(S) && !resvInvalid(R)) resvMerge(R, S, rng.next());         // restir.cu:197-199
+    } else if (!resvInvalid(S)) {                                                    // restir.cu:206-208
+        float rnd = rng.next();
+        if (R.M > 0) resvClamp(S, (4 - 1) * R.M);
+        resvMerge(R, S, rnd);
+    }
+    if (!last) {
+        storeResv(dst + li, R);
+        q[1] = make_float4(h1.x, h1.y, h1.z, __uint_as_float(rng.x));
+        return;
+    }
+    if (src != f.resvTemp) storeResv(f.resvTemp + li, published);
+    f3 nrm = mk3(h0.x, h0.y, h0.z), wo = mk3(h1.x, h1.y, h1.z);
+    const RstrMaterial* m = s.materials + matId;
+    writeRadiance(f, li, shadeReservoir(s, R, __ldg(&m->type), __ldg(&m->metallic), __ldg(&m->roughness), nrm, wo), iter);
 }
 
 // pathtrace.cu:279-328 with scene.h:427-459 (occlusion test BEFORE the facing test)
@@ -1129,8 +1150,8 @@ int launchRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const
     }
     return 2;
 }
-void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, cudaStream_t st) {
-    k_restir_b<<<pixelGrid(f), 128, 0, st>>>(s, f, p, iter);
+void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, const ResvD* src, ResvD* dst, int pass, int last, cudaStream_t st) {
+    k_restir_b<<<pixelGrid(f), 128, 0, st>>>(s, f, p, iter, src, dst, pass, last);
 }
 int launchPTDirect(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, cudaStream_t st) {
     if (s.traversal == RS_TRAVERSAL_EXACT) { k_ptdirect<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, looper, iter); return 1; }

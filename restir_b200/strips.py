@@ -6,33 +6,74 @@ exchanges per frame carry reservoir rows only (the G-buffer of the halo rows is 
 
 * E2, between phase A and phase B: post-temporal reservoirs (plane ``resv_temp``) for the spatial radius;
 * E1, after phase B: history reservoirs (plane ``resv_history``) for next frame's temporal reprojection.
+
+Strips are described by ``bounds``: N+1 increasing row indices, rank r owns rows [bounds[r], bounds[r+1]).
+Equal-height strips balance badly (sky rows cost almost nothing, ground rows everything), so ``balanced_bounds``
+places the cuts by a per-row cost estimate taken from one G-buffer of the first frame.
 """
 from __future__ import annotations
 
+import math
 
-def strip_rows(height: int, world: int, rank: int) -> tuple[int, int]:
-    """Rows [r0, r1) owned by ``rank``; the first ``height % world`` strips get one extra row."""
+import numpy as np
+
+
+def uniform_bounds(height: int, world: int) -> list[int]:
+    """Equal-height strips; the first ``height % world`` strips get one extra row."""
     base, extra = divmod(height, world)
-    r0 = rank * base + min(rank, extra)
-    return r0, r0 + base + (1 if rank < extra else 0)
+    b = [0]
+    for r in range(world):
+        b.append(b[-1] + base + (1 if r < extra else 0))
+    return b
 
 
-def halo_rows(height: int, world: int, rank: int, halo: int) -> tuple[int, int]:
+def balanced_bounds(row_cost, world: int, min_rows: int = 8) -> list[int]:
+    """Cuts that give every rank (about) the same summed row cost; every strip keeps at least ``min_rows`` rows."""
+    cost = np.asarray(row_cost, np.float64)
+    H = int(cost.shape[0])
+    if world * min_rows > H:
+        return uniform_bounds(H, world)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    total = cum[-1]
+    b = [0]
+    for r in range(1, world):
+        target = total * r / world
+        cut = int(np.searchsorted(cum, target))
+        cut = max(cut, b[-1] + min_rows)
+        cut = min(cut, H - (world - r) * min_rows)
+        b.append(cut)
+    b.append(H)
+    return b
+
+
+def row_cost_from_matid(matid, width: int, shaded_weight: float = 1.0, base_weight: float = 0.03):
+    """Per-row cost estimate from a G-buffer material-id plane: shaded pixels (id >= 0) run the candidate loop and two
+    more rays, the others only a primary ray that leaves the scene box."""
+    m = np.asarray(matid).reshape(-1, width)
+    return (m >= 0).sum(1) * shaded_weight + width * base_weight
+
+
+def strip_rows(height: int, world: int, rank: int, bounds=None) -> tuple[int, int]:
+    b = bounds or uniform_bounds(height, world)
+    return b[rank], b[rank + 1]
+
+
+def halo_rows(height: int, world: int, rank: int, halo: int, bounds=None) -> tuple[int, int]:
     """Rows resident on ``rank`` (own strip + halo, clipped to the image)."""
-    r0, r1 = strip_rows(height, world, rank)
+    r0, r1 = strip_rows(height, world, rank, bounds)
     return max(0, r0 - halo), min(height, r1 + halo)
 
 
-def exchange_plan(height: int, world: int, halo: int) -> list[tuple[int, int, int, int]]:
+def exchange_plan(height: int, world: int, halo: int, bounds=None) -> list[tuple[int, int, int, int]]:
     """All (src, dst, row0, row1) messages of one halo exchange: rows owned by ``src`` that ``dst`` keeps as halo.
     With halo <= strip height only adjacent ranks talk; taller halos reach further ranks."""
     plan = []
     for dst in range(world):
-        lo, hi = halo_rows(height, world, dst, halo)
+        lo, hi = halo_rows(height, world, dst, halo, bounds)
         for src in range(world):
             if src == dst:
                 continue
-            s0, s1 = strip_rows(height, world, src)
+            s0, s1 = strip_rows(height, world, src, bounds)
             a, b = max(lo, s0), min(hi, s1)
             if a < b:
                 plan.append((src, dst, a, b))
@@ -41,6 +82,4 @@ def exchange_plan(height: int, world: int, halo: int) -> list[tuple[int, int, in
 
 def default_halo(spatial_radius: float, temporal_margin: int = 32) -> int:
     """Halo rows: ceil(radius)+1 for the spatial disk (restir.cu:53-55), >= temporal_margin for reprojection."""
-    import math
-
     return max(int(math.ceil(spatial_radius)) + 1, int(temporal_margin))

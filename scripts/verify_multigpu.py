@@ -24,13 +24,17 @@ W, H, radius, frames = 1920, 1080, 30.0, 4
 sd = scenes.procedural(1, 200000, 10000, (W, H))
 sc = rb.Scene.from_arrays(sd)
 halo = strips.default_halo(radius)
-rows = strips.strip_rows(H, world, rank)
+base = rb.Camera.from_scene(sd)
+probe = sc.frame(W, H)
+probe.gbuffer_render(base.orbit(0))
+bounds = strips.balanced_bounds(strips.row_cost_from_matid(probe.read("matid"), W), world, min_rows=halo)
+probe.close()
+rows = strips.strip_rows(H, world, rank, bounds)
 fr = sc.frame(W, H, rows=rows, halo=halo)
 fr.set_stream(torch.cuda.current_stream().cuda_stream)
 full = sc.frame(W, H) if rank == 0 else None
-base = rb.Camera.from_scene(sd)
 prm = rb.default_params(reuse=3, radius=radius)
-plan = strips.exchange_plan(H, world, halo)
+plan = strips.exchange_plan(H, world, halo, bounds)
 
 
 def exchange(plane):
@@ -60,7 +64,7 @@ for k in range(frames):
         full.gbuffer_render(cam); full.restir_direct(cam, prm, k, 0); full.gbuffer_update(cam)
     for name in ("radiance", "reservoir", "light_index", "matid", "motion"):
         mine = torch.from_numpy(np.ascontiguousarray(fr.read(name)).view(np.uint8).reshape(-1).copy())
-        sizes = [(strips.strip_rows(H, world, r)[1] - strips.strip_rows(H, world, r)[0]) * W * (mine.numel() // fr.npix) for r in range(world)]
+        sizes = [(bounds[r + 1] - bounds[r]) * W * (mine.numel() // fr.npix) for r in range(world)]
         parts = [torch.empty(s, dtype=torch.uint8, device="cuda") for s in sizes] if rank == 0 else None
         dist.gather(mine.cuda(), parts, dst=0)
         if rank == 0:
@@ -74,5 +78,5 @@ miss = torch.tensor([fr.halo_miss()], device="cuda")
 dist.all_reduce(miss)
 if rank == 0:
     print(json.dumps({"verify_multigpu": "ok" if bad_total == 0 and int(miss.item()) == 0 else "MISMATCH", "n_gpus": world, "frames": frames,
-                      "resolution": [W, H], "pixels_differing": bad_total, "halo_miss": int(miss.item()), "halo_rows": halo}))
+                      "resolution": [W, H], "pixels_differing": bad_total, "halo_miss": int(miss.item()), "halo_rows": halo, "strip_bounds": bounds}))
 dist.destroy_process_group()

@@ -106,6 +106,16 @@ def test_knob_sweep_many_light(gpu, port_oracle, k, cap, cands, radius):
     check(got, want, 3, "sweep k=%d cap=%d cands=%d" % (k, cap, cands))
 
 
+@pytest.mark.parametrize("passes,k", [(2, 5), (3, 3)])
+def test_multi_pass_spatial(gpu, port_oracle, passes, k):
+    """BASELINE config 5's "1-3 spatial passes": passes 2.. follow the block the reference ships commented out
+    (restir.cu:201-209, preClampedMerge<4>); the oracle's version of it is pinned against the reference harness."""
+    for sd in (scenes.cornell_box((320, 240), metal_tall_box=True), scenes.procedural(3, 20000, 1000, (320, 180))):
+        got, _ = helpers.run_gpu(gpu, sd, 3, 3, radius=12.0, k=k, passes=passes, light_index=True)
+        want = helpers.run_oracle(port_oracle, sd, 3, 3, radius=12.0, k=k, passes=passes, light_index=True)
+        check(got, want, 3, "passes=%d %s" % (passes, sd.name))
+
+
 def test_ptdirect_against_golden_and_oracle(gpu, port_oracle):
     import ctypes as C
 

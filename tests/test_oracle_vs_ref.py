@@ -26,6 +26,14 @@ def test_frames_other_knobs(port_oracle, ref_oracle, reuse, radius, k, cap):
     helpers.assert_frames_equal(a, b, "port vs reference")
 
 
+@pytest.mark.parametrize("passes", [2, 3])
+def test_multi_pass_spatial(port_oracle, ref_oracle, passes):
+    sd = scenes.procedural(7, 3000, 150, (56, 40))
+    a = helpers.run_oracle(port_oracle, sd, 3, 3, radius=8.0, passes=passes)
+    b = helpers.run_oracle(ref_oracle, sd, 3, 3, radius=8.0, passes=passes)
+    helpers.assert_frames_equal(a, b, "port vs reference, %d passes" % passes)
+
+
 def test_probe_rays(port_oracle, ref_oracle):
     sd = scenes.cornell_box((8, 8), metal_tall_box=True)
     a, b = port_oracle.scene(sd), ref_oracle.scene(sd)

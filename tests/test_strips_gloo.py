@@ -24,6 +24,28 @@ def test_strip_rows_partition_every_height():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_balanced_bounds():
+    H, W = 1080, 64
+    matid = np.full((H, W), -1, np.int32)
+    matid[500:] = 3                                     # sky above row 500, ground below
+    cost = strips.row_cost_from_matid(matid, W)
+    for N in (2, 4, 8):
+        b = strips.balanced_bounds(cost, N)
+        assert b[0] == 0 and b[-1] == H and all(b[i + 1] - b[i] >= 8 for i in range(N))
+        per = [cost[b[i]:b[i + 1]].sum() for i in range(N)]
+        assert max(per) / (sum(per) / N) < 1.15           # equal-height strips would give 1.8 - 2.0 here
+        plan = strips.exchange_plan(H, N, 32, b)
+        for dst in range(N):
+            lo, hi = strips.halo_rows(H, N, dst, 32, b)
+            need = set(range(lo, hi)) - set(range(b[dst], b[dst + 1]))
+            got = set()
+            for s_, d_, a, e in plan:
+                if d_ == dst:
+                    got |= set(range(a, e))
+            assert got == need
+    assert strips.balanced_bounds(np.ones(10), 4, min_rows=8) == strips.uniform_bounds(10, 4)
+
+
 def test_exchange_plan_covers_exactly_the_halos():
     for H, N, halo in ((1080, 4, 31), (2160, 8, 40), (64, 8, 20), (1080, 2, 0)):
         plan = strips.exchange_plan(H, N, halo)
