@@ -216,12 +216,27 @@ def run_b200(args):
     prm = rb.default_params(reuse=reuse, radius=radius)
     bounds = strips.uniform_bounds(H, world)
     if world > 1 and not args.uniform_strips:
-        # every rank renders the first frame's G-buffer once (the scene is replicated anyway) and derives the same
-        # cost-balanced cuts from it: sky rows are almost free, ground rows carry the candidate loop and two more rays
-        probe = sc.frame(W, H)
-        probe.gbuffer_render(base.orbit(0))
-        bounds = strips.balanced_bounds(strips.row_cost_from_matid(probe.read("matid"), W), world, min_rows=max(8, halo))
-        probe.close()
+        # measured cost profile: the image is cut into 8*N bands, every rank times its share of them (two frames of the
+        # real pipeline on a throw-away strip frame), the per-band device times are all-gathered and the cuts are placed
+        # so that every rank gets the same summed cost.  Equal-height strips balance badly: sky rows are almost free.
+        nb = 8 * world
+        bb = strips.uniform_bounds(H, nb)
+        mine = torch.zeros(nb, dtype=torch.float64, device="cuda")
+        pprm = rb.default_params(reuse=reuse & 1, radius=radius)
+        for band in range(rank, nb, world):
+            pf = sc.frame(W, H, rows=(bb[band], bb[band + 1]), halo=0)
+            tot = 0.0
+            for kk in range(3):
+                cam = base.orbit(kk)
+                pf.gbuffer_render(cam); pf.restir_direct(cam, pprm, kk, 0); pf.gbuffer_update(cam)
+                if kk:
+                    tot += sum(pf.stage_ms().values())
+            mine[band] = tot
+            pf.close()
+        dist.all_reduce(mine)
+        per_band = mine.cpu().numpy()
+        row_cost = np.concatenate([np.full(bb[i + 1] - bb[i], per_band[i] / (bb[i + 1] - bb[i])) for i in range(nb)])
+        bounds = strips.balanced_bounds(row_cost, world, min_rows=max(8, halo))
     rows = strips.strip_rows(H, world, rank, bounds)
     fr = sc.frame(W, H, rows=rows, halo=halo)
 

@@ -89,7 +89,7 @@ static FrameDev toFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
     d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
     d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
-    d.hit = f->hit; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount; d.rayCounter = f->queueCount + 1;
+    d.hit = f->hit; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount;
     return d;
 }
 

@@ -79,7 +79,6 @@ struct FrameDev {
     HitRec* hit;
     int* queue;                // pixels deferred to the reference-order fix-up kernel
     unsigned int* queueCount;
-    unsigned int* rayCounter;  // next ray index of the persistent kernels (queueCount + 1)
     unsigned int* haloMiss;    // count of neighbour / reprojection reads that fell outside the resident rows
 };
 

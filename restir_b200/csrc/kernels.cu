@@ -16,8 +16,6 @@
 // reference's 6-copy threaded MTBVH walk.
 #include "kernels.h"
 
-#include <stdlib.h>
-
 namespace rs {
 
 // ------------------------------------------------------------------------------------------------ rays
@@ -328,8 +326,9 @@ RS_D bool nearTie(const Cand& a, const Cand& b) {
 }
 
 // Closest hit over the traced tree as a resumable state machine ("while-while": lanes first descend to a leaf, then
-// test triangles together).  closestRun returns true when the ray is finished, false when it suspended itself because
-// fewer than minActive lanes of the warp were still traversing (persistent kernels then refill the idle lanes).
+// test triangles together).  closestRun returns true when the ray is finished; with minActive > 0 it returns false
+// once fewer lanes than that are still traversing, so that a caller can refill idle lanes (a persistent-threads
+// G-buffer kernel built on this was 9-20 % SLOWER than the plain grid on B200 and was removed, profiles/README.md).
 #define RS_DONE 0x7fffffff
 #define RS_MAX_EXTRA 2     /* near-tie candidates beyond best + second, kept in local memory (corners where 3-4 surfaces meet) */
 struct ClosestState {
@@ -678,59 +677,6 @@ RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& last
         f.geom[0][li] = make_float4(0.f, 0.f, 0.f, 1.f);                             // gbuffer.cu:57-72
         f.matId[0][li] = -1;
         f.albedoMotion[li] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-    }
-}
-
-// ---- persistent form: every lane owns one ray at a time; finished lanes are refilled from a global counter ----
-#define RS_REFILL_BELOW 24     /* a warp stops traversing and refills once fewer lanes than this are still busy */
-// ray index -> pixel: consecutive indices walk an 8x4 tile, then the next tile of the tile row
-RS_D bool pixelOfIndex(const FrameDev& f, unsigned idx, int& x, int& y) {
-    const unsigned tilesX = (unsigned)(f.W + 7) >> 3;
-    unsigned tile = idx >> 5, l = idx & 31;
-    x = (int)(tile % tilesX) * 8 + (int)(l & 7);
-    y = f.rowLo + (int)(tile / tilesX) * 4 + (int)(l >> 3);
-    return x < f.W && y < f.rowHi;
-}
-RS_D unsigned pixelIndexCount(const FrameDev& f) { return (((unsigned)(f.W + 7) >> 3) * ((unsigned)(f.rowHi - f.rowLo + 3) >> 2)) << 5; }
-
-__global__ void __launch_bounds__(RS_BLOCK) k_gbuffer_persist(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
-                                                              const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
-    RS_DECLARE_STACK(stack);
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned total = pixelIndexCount(f);
-    bool active = false, exhausted = false;
-    int x = 0, y = 0;
-    f3 o = mk3(0.f);
-    ClosestState st;
-    for (;;) {
-        unsigned idle = __ballot_sync(0xffffffffu, !active);
-        if (idle && !exhausted) {
-            unsigned base = 0;
-            int leader = __ffs(idle) - 1;
-            if ((int)lane == leader) base = atomicAdd(f.rayCounter, (unsigned)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            exhausted = base + (unsigned)__popc(idle) >= total;
-            if (!active) {
-                unsigned idx = base + (unsigned)__popc(idle & ((1u << lane) - 1u));
-                if (idx < total && pixelOfIndex(f, idx, x, y)) {
-                    f3 d;
-                    cameraRay(cam, x, y, .5f, .5f, o, d);
-                    st.r = makeRayT(o, d);
-                    closestBegin(s, st);
-                    active = true;
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, active) == 0u) {
-            if (exhausted) break;
-            continue;
-        }
-        if (active && closestRun(s, st, stack, RS_REFILL_BELOW)) {
-            Hit h;
-            if (closestResolve(s, st, h)) gbufferFinish(s, f, lastCam, x, y, o, h);
-            else enqueuePixel(f, x, y);
-            active = false;
-        }
     }
 }
 
@@ -1109,27 +1055,10 @@ static inline dim3 pixelGrid(const FrameDev& f) { return dim3((f.W + 15) / 16, (
 
 #define RS_FIX_BLOCKS 296   /* 2 per SM; the fix-up kernels stride over the queue */
 
-static bool usePersistent() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("RSTR_PERSISTENT"); v = e ? atoi(e) : 0; }   // A/B on B200: the refill variant is 9-20 % slower than the plain grid (86 registers), default off
-    return v != 0;
-}
-static int persistentBlocks() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        n = sms * 6;
-    }
-    return n;
-}
-
 int launchGBuffer(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, cudaStream_t st) {
     if (s.traversal == RS_TRAVERSAL_EXACT) { k_gbuffer<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam); return 1; }
-    cudaMemsetAsync(f.queueCount, 0, 2 * sizeof(unsigned int), st);      // queueCount and rayCounter are adjacent
-    if (usePersistent()) k_gbuffer_persist<<<persistentBlocks(), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
-    else k_gbuffer<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
+    cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
+    k_gbuffer<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
     k_gbuffer_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
     return 2;
 }

@@ -65,11 +65,14 @@ for k in range(frames):
     for name in ("radiance", "reservoir", "light_index", "matid", "motion"):
         mine = torch.from_numpy(np.ascontiguousarray(fr.read(name)).view(np.uint8).reshape(-1).copy())
         sizes = [(bounds[r + 1] - bounds[r]) * W * (mine.numel() // fr.npix) for r in range(world)]
-        parts = [torch.empty(s, dtype=torch.uint8, device="cuda") for s in sizes] if rank == 0 else None
-        dist.gather(mine.cuda(), parts, dst=0)
+        mx = max(sizes)                                   # strips are uneven: gather padded, then trim
+        padded = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+        padded[:mine.numel()] = mine.cuda()
+        parts = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in sizes] if rank == 0 else None
+        dist.gather(padded, parts, dst=0)
         if rank == 0:
             whole = np.ascontiguousarray(full.read(name)).view(np.uint8).reshape(H * W, -1)
-            got = torch.cat(parts).cpu().numpy().reshape(H * W, -1)
+            got = torch.cat([p_[:n_] for p_, n_ in zip(parts, sizes)]).cpu().numpy().reshape(H * W, -1)
             bad = int((whole != got).any(1).sum())
             bad_total += bad
             if bad:

@@ -268,3 +268,39 @@ def test_end_to_end_host_call(gpu):
     assert ldr[:, :3].max() > 100
     gpu.pinned_free(out)
     fr.close(); sc.close()
+
+
+def test_cpp_host_example_renders(gpu):
+    """examples/headless_main.cpp: the reference's runCuda() loop in C++ over the shim, from a scene FILE."""
+    import json
+    import subprocess
+    import tempfile
+
+    from test_host_layer import _build_cpp_example
+
+    tmp = tempfile.mkdtemp()
+    exe = _build_cpp_example(tmp)
+    txt = scenes.write_scene_files(scenes.cornell_box((160, 120)), tmp, "cornell")
+    out = subprocess.run([exe, txt, "3", os.path.join(tmp, "out.ppm"), "3"], capture_output=True, text=True, check=True)
+    info = json.loads(out.stdout.strip().splitlines()[-1])
+    assert info["frames"] == 3 and info["mean_ldr"] > 5.0
+    assert os.path.getsize(os.path.join(tmp, "out.ppm")) > 160 * 120 * 3
+
+
+def test_pipelined_host_call_matches_synchronous_call(gpu):
+    sd = scenes.cornell_box((320, 240))
+    sc = gpu.Scene.from_arrays(sd)
+    base = gpu.Camera.from_scene(sd)
+    prm = gpu.default_params(reuse=3)
+    a, b = sc.frame(320, 240), sc.frame(320, 240)
+    outs = [gpu.pinned_empty(320 * 240 * 4), gpu.pinned_empty(320 * 240 * 4)]
+    ref = gpu.pinned_empty(320 * 240 * 4)
+    for k in range(4):
+        cam = base.orbit(k)
+        a.render_frame_host_async(cam, prm, k, 0, gpu.TONEMAP_ACES, outs[k & 1], k & 1)
+        b.render_frame_host(cam, prm, k, 0, gpu.TONEMAP_ACES, ref)
+        a.wait_host(k & 1)
+        assert np.array_equal(outs[k & 1], ref), k
+    for o in outs + [ref]:
+        gpu.pinned_free(o)
+    a.close(); b.close(); sc.close()

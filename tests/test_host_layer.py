@@ -119,3 +119,22 @@ def test_scene_generators_are_deterministic():
     assert a.num_tris == 5000 and a.num_lights == 300
     c = scenes.cornell_box()
     assert c.num_tris == 36 and c.num_lights == 2
+
+
+def _build_cpp_example(tmp):
+    import subprocess
+
+    exe = os.path.join(tmp, "headless")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "examples"),
+           os.path.join(ROOT, "examples", "headless_main.cpp"), "-L" + os.path.join(ROOT, "restir_b200"), "-lrestir_b200",
+           "-Wl,-rpath," + os.path.join(ROOT, "restir_b200"), "-o", exe]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+def test_cpp_host_example_links_against_the_c_abi():
+    """The reference-named C++ shim (examples/restir_shim.hpp) + a runCuda()-style driver compile with plain g++ and
+    link against the C ABI: host code stays C++ and needs neither CUDA headers nor nvcc."""
+    rb.lib()
+    exe = _build_cpp_example(tempfile.mkdtemp())
+    assert os.path.exists(exe)
