@@ -150,6 +150,9 @@ int rstr_scene_read(const RstrScene*, int which, void* host, size_t bytes);
 
 /* replaces Camera::update() (sceneStructs.h:88-102) */
 int rstr_camera_update(RstrCamera*);
+/* runCuda()'s camera animation (main.cpp:149-153 + update()): position = base + (cos t, 0, sin t) * radius with the wall
+ * clock replaced by t = frame / fps * speed (Settings::animateSpeed 2.7, animateRadius 1, common.cpp:9-10) */
+int rstr_camera_orbit(const RstrCamera* base, int frame, float speed, float radius, float fps, RstrCamera* out);
 
 /* replaces GBuffer::create (denoiser.cu:373) + ReSTIRInit (restir.cu:478) + the devDirectIllum allocation
  * (main.cpp:38).  The strip variant owns image rows [row0,row1) of a W x H image plus `halo` rows on each
@@ -179,7 +182,8 @@ int rstr_tonemap(RstrFrame*, int toneMapping, float scale);
 int rstr_render_frame_host(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter,
                            int toneMapping, void* hostLdr, size_t bytes);
 
-/* Pipelined form: enqueue frame k into LDR slot (0/1) -- render, tone-map, D2H of the image on a copy stream -- and
+#define RSTR_LDR_SLOTS 3
+/* Pipelined form: enqueue frame k into LDR slot (0 .. RSTR_LDR_SLOTS-1) -- render, tone-map, D2H of the image on a copy stream -- and
  * return at once; rstr_frame_wait_host(slot) blocks until that slot's image has arrived in hostLdr.  Lets the copy of
  * frame k overlap the rendering of frame k+1 (the reference's GL interop path has no copy at all). */
 int rstr_render_frame_host_async(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter,

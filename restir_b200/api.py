@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.rstr_scene_set_traversal.argtypes = [vp, ip]
     L.rstr_scene_fallback_rays.argtypes = [vp, C.POINTER(C.c_ulonglong), ip]
     L.rstr_camera_update.argtypes = [C.POINTER(RstrCamera)]
+    L.rstr_camera_orbit.argtypes = [C.POINTER(RstrCamera), ip, fp, fp, fp, C.POINTER(RstrCamera)]
     L.rstr_frame_create.argtypes = [vp, ip, ip, C.POINTER(vp)]
     L.rstr_frame_create_strip.argtypes = [vp, ip, ip, ip, ip, ip, C.POINTER(vp)]
     L.rstr_frame_destroy.argtypes = [vp]
@@ -206,12 +207,8 @@ class Camera(RstrCamera):
 
     def orbit(self, k: int, speed: float = 2.7, radius: float = 1.0, fps: float = 60.0) -> "Camera":
         """runCuda's camera animation with the fixed clock t_k = k*speed/fps (main.cpp:149-162)."""
-        cam = self.copy()
-        t = np.float32(np.float32(k / fps) * np.float32(speed))
-        cam.position[0] = float(np.float32(self.position[0]) + np.float32(np.cos(t)) * np.float32(radius))
-        cam.position[1] = float(np.float32(self.position[1]) + np.float32(0.0) * np.float32(radius))
-        cam.position[2] = float(np.float32(self.position[2]) + np.float32(np.sin(t)) * np.float32(radius))
-        cam.update()
+        cam = Camera()
+        _check(lib().rstr_camera_orbit(C.byref(self), int(k), speed, radius, fps, C.byref(cam)))
         return cam
 
 

@@ -48,10 +48,10 @@ struct RstrFrame {
     ResvD* resvTemp2 = nullptr;    // second publication buffer, allocated when spatialPasses > 1
     HitRec* hit = nullptr;
     uchar4* ldr = nullptr;
-    uchar4* ldrB[2] = {nullptr, nullptr};     // double-buffered LDR frames of the pipelined host call
+    uchar4* ldrB[RSTR_LDR_SLOTS] = {};        // LDR frames in flight of the pipelined host call
     cudaStream_t copyStream = nullptr;
-    cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
-    bool slotBusy[2] = {false, false};
+    cudaEvent_t evRendered[RSTR_LDR_SLOTS] = {}, evCopied[RSTR_LDR_SLOTS] = {};
+    bool slotBusy[RSTR_LDR_SLOTS] = {};
     unsigned int* haloMiss = nullptr;
     int* queue = nullptr;
     unsigned int* queueCount = nullptr;
@@ -259,6 +259,18 @@ int rstr_scene_read(const RstrScene* sc, int which, void* host, size_t bytes) {
     return RSTR_OK;
 }
 
+// runCuda()'s camera animation (main.cpp:149-153, 160) with the clock replaced by t = frame / fps * speed
+int rstr_camera_orbit(const RstrCamera* base, int frame, float speed, float radius, float fps, RstrCamera* out) {
+    if (!base || !out) return fail(RSTR_ERR_ARG, "rstr_camera_orbit: null");
+    *out = *base;
+    float t = (float)frame / fps * speed;
+    out->position[0] = base->position[0] + cosf(t) * radius;
+    out->position[1] = base->position[1] + 0.f * radius;
+    out->position[2] = base->position[2] + sinf(t) * radius;
+    cameraUpdate(*out);
+    return RSTR_OK;
+}
+
 int rstr_camera_update(RstrCamera* c) {
     if (!c) return fail(RSTR_ERR_ARG, "rstr_camera_update: null");
     cameraUpdate(*c);
@@ -271,7 +283,7 @@ int rstr_frame_destroy(RstrFrame* f) {
     for (int i = 0; i < 2; i++) { cudaFree(f->geom[i]); cudaFree(f->matId[i]); cudaFree(f->resv[i]); }
     cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->resvTemp2); cudaFree(f->hit); cudaFree(f->ldr);
     cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->queueCount);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < RSTR_LDR_SLOTS; i++) {
         cudaFree(f->ldrB[i]);
         if (f->evRendered[i]) cudaEventDestroy(f->evRendered[i]);
         if (f->evCopied[i]) cudaEventDestroy(f->evCopied[i]);
@@ -461,12 +473,12 @@ int rstr_render_frame_host(RstrFrame* f, const RstrCamera* cam, const RstrParams
 // stream) and returns without waiting; rstr_frame_wait_host(slot) blocks until that slot's image is in host memory.
 int rstr_render_frame_host_async(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter, int toneMapping,
                                  void* hostLdr, size_t bytes, int slot) {
-    if (!f || slot < 0 || slot > 1 || !hostLdr) return fail(RSTR_ERR_ARG, "rstr_render_frame_host_async: bad argument");
+    if (!f || slot < 0 || slot >= RSTR_LDR_SLOTS || !hostLdr) return fail(RSTR_ERR_ARG, "rstr_render_frame_host_async: bad argument");
     const size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
     if (bytes != n * sizeof(uchar4)) return fail(RSTR_ERR_ARG, "rstr_render_frame_host_async: size mismatch");
     if (!f->copyStream) {
         CU(cudaStreamCreateWithFlags(&f->copyStream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < RSTR_LDR_SLOTS; i++) {
             CU(cudaMalloc((void**)&f->ldrB[i], n * sizeof(uchar4)));
             CU(cudaEventCreateWithFlags(&f->evRendered[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&f->evCopied[i], cudaEventDisableTiming));
@@ -492,7 +504,7 @@ int rstr_render_frame_host_async(RstrFrame* f, const RstrCamera* cam, const Rstr
 }
 
 int rstr_frame_wait_host(RstrFrame* f, int slot) {
-    if (!f || slot < 0 || slot > 1) return fail(RSTR_ERR_ARG, "rstr_frame_wait_host: bad argument");
+    if (!f || slot < 0 || slot >= RSTR_LDR_SLOTS) return fail(RSTR_ERR_ARG, "rstr_frame_wait_host: bad argument");
     if (f->slotBusy[slot]) CU(cudaEventSynchronize(f->evCopied[slot]));
     return RSTR_OK;
 }
