@@ -55,8 +55,16 @@ typedef struct RstrMaterial {
     int   type;               /* 0 Lambertian, 1 MetallicWorkflow, 2 Dielectric, 3 Disney, 4 Light (material.h:114-120) */
     float baseColor[3];       /* for Light: emitted radiance */
     float metallic, roughness, ior;
-    int   baseColorMapId, metallicMapId, roughnessMapId, normalMapId;  /* -1 none; textures are not supported yet */
+    int   baseColorMapId, metallicMapId, roughnessMapId, normalMapId;  /* index into RstrSceneDesc::textures; -1 none
+                                                                          (material.h:11); baseColorMapId -2 = procedural
+                                                                          pattern (material.h:13, scene.h:68-76) */
 } RstrMaterial;
+
+/* Texture in the reference's host form (image.h:7-39): width x height texels, 3 x f32 linear RGB, row-major */
+typedef struct RstrTexture {
+    int width, height;
+    const float* rgb;
+} RstrTexture;
 
 /* Knobs that are literals in restir.cu; rstr_params_default() reproduces the reference. */
 typedef struct RstrParams {
@@ -83,6 +91,11 @@ typedef struct RstrSceneDesc {
     const int*   materialIds;  /* T */
     int numMaterials;
     const RstrMaterial* materials;
+    int numTextures;             /* Scene::textures (scene.cpp:362-375); 0 = none */
+    const RstrTexture* textures;
+    int envMap;                  /* 0 = none, else 1 + index of the environment map texture (Scene::envMapTexId,
+                                    scene.cpp:122-128): sampled as the last entry of the light sampler (scene.cpp:136-152,
+                                    scene.h:364-375, 400-403) and shown behind the scene (gbuffer.cu:59-62, restir.cu:134) */
 } RstrSceneDesc;
 
 typedef struct RstrSceneInfo {
@@ -92,6 +105,8 @@ typedef struct RstrSceneInfo {
     size_t deviceBytes;
     int tracedBvhDepth;        /* depth of the binned-SAH tree the kernels trace */
     double tracedBuildSeconds;
+    int numEmissiveTris;       /* numLights counts the light sampler's entries: emissive triangles + 1 for an environment map */
+    int numTextures, envWidth, envHeight;
 } RstrSceneInfo;
 
 typedef struct RstrScene RstrScene;
@@ -108,7 +123,8 @@ enum {
     RSTR_SCENE_NORMALS = 11,
     RSTR_SCENE_TEXCOORDS = 12,     /* 3T x 8 B */
     RSTR_SCENE_MATERIAL_IDS = 13,  /* T x i32 */
-    RSTR_SCENE_MATERIALS = 14      /* numMaterials x 44 B */
+    RSTR_SCENE_MATERIALS = 14,     /* numMaterials x 44 B */
+    RSTR_SCENE_ENV_ALIAS = 15      /* envW*envH x {f32 prob, i32 failId}  envMapSampler, scene.cpp:147 */
 };
 
 /* frame buffers readable through rstr_frame_read (reference layouts, full image rows of this frame/strip) */

@@ -81,6 +81,10 @@ class Oracle:
         L.orc_scene_create.restype = vp
         L.orc_scene_create.argtypes = [ip, vp, vp, vp, vp, ip, vp]
         L.orc_scene_destroy.argtypes = [vp]
+        L.orc_scene_set_textures.restype = ip
+        L.orc_scene_set_textures.argtypes = [vp, ip, vp, vp, vp, ip]
+        L.orc_scene_env_alias.restype = vp
+        L.orc_scene_env_alias.argtypes = [vp, vp, vp]
         for n in ("orc_scene_bvh_size", "orc_scene_num_lights", "orc_scene_bvh_depth"):
             getattr(L, n).restype = ip
             getattr(L, n).argtypes = [vp]
@@ -184,8 +188,18 @@ class OracleScene:
                       np.ascontiguousarray(sd.materials)]
         v, n, t, m, mats = self._keep
         self.h = L.orc_scene_create(sd.num_tris, v.ctypes.data, n.ctypes.data, t.ctypes.data, m.ctypes.data, len(mats), mats.ctypes.data)
+        texs = [np.ascontiguousarray(x, np.float32) for x in getattr(sd, "textures", [])]
+        env = int(getattr(sd, "env_map", -1))
+        if texs or env >= 0:
+            self._keep += texs
+            ws = (C.c_int * len(texs))(*[x.shape[1] for x in texs])
+            hs = (C.c_int * len(texs))(*[x.shape[0] for x in texs])
+            ptrs = (C.c_void_p * len(texs))(*[x.ctypes.data for x in texs])
+            if L.orc_scene_set_textures(self.h, len(texs), ws, hs, ptrs, env) != 0:
+                raise ValueError("texture id out of range")
         self.bvh_size = L.orc_scene_bvh_size(self.h)
-        self.num_lights = L.orc_scene_num_lights(self.h)
+        self.num_lights = L.orc_scene_num_lights(self.h)          # light sampler length (emissive triangles + environment map)
+        self.num_emissive = self.num_lights - (1 if env >= 0 else 0)
 
     def close(self):
         if self.h:
@@ -199,13 +213,18 @@ class OracleScene:
         return Oracle._view(self.orc.lib.orc_scene_mtbvh(self.h, i), np.int32, (self.bvh_size, 3))
 
     def light_prim_ids(self):
-        return Oracle._view(self.orc.lib.orc_scene_light_prim_ids(self.h), np.int32, (self.num_lights,))
+        return Oracle._view(self.orc.lib.orc_scene_light_prim_ids(self.h), np.int32, (self.num_emissive,))
 
     def light_radiance(self):
-        return Oracle._view(self.orc.lib.orc_scene_light_radiance(self.h), np.float32, (self.num_lights, 3))
+        return Oracle._view(self.orc.lib.orc_scene_light_radiance(self.h), np.float32, (self.num_emissive, 3))
 
     def alias_table(self):
         return Oracle._view(self.orc.lib.orc_scene_alias_table(self.h), np.dtype([("prob", "<f4"), ("failId", "<i4")]), (self.num_lights,))
+
+    def env_alias(self):
+        n, total = C.c_int(0), C.c_float(0)
+        p = self.orc.lib.orc_scene_env_alias(self.h, C.addressof(n), C.addressof(total))
+        return Oracle._view(p, np.dtype([("prob", "<f4"), ("failId", "<i4")]), (n.value,)), float(total.value)
 
     def sum_light_power(self):
         return float(self.orc.lib.orc_scene_sum_light_power(self.h))

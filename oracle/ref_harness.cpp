@@ -54,7 +54,10 @@ struct OrcScene {
     std::vector<std::vector<MTBVHNode>> nodes;
     std::vector<int> lightPrimIds;
     std::vector<glm::vec3> lightUnitRadiance;
-    DiscreteSampler1D<float> lightSampler;
+    DiscreteSampler1D<float> lightSampler, envMapSampler;
+    std::vector<float> lightPower;
+    std::vector<std::vector<glm::vec3>> texData;
+    std::vector<DevTextureObj> texObjs;
     int T = 0;
 };
 
@@ -67,7 +70,7 @@ struct OrcFrame {
     bool haveLast = false;
     std::vector<DirectReservoir> resv, lastResv, temp;
     bool first = true;
-    struct Carry { Sampler rng; int status; DirectReservoir r; Intersection is; Material mat; };
+    struct Carry { Sampler rng; int status; DirectReservoir r; Intersection is; Material mat; glm::vec3 direct; };
     std::vector<Carry> carry;
 };
 
@@ -115,7 +118,7 @@ OrcScene* orc_scene_create(int T, const float* vertices, const float* normals, c
     sc->materialIds.assign(materialIds, materialIds + T);
     sc->materials.resize(numMaterials);
     memcpy((void*)sc->materials.data(), materials, sizeof(Material) * numMaterials);
-    std::vector<float> lightPower;
+    std::vector<float>& lightPower = sc->lightPower;
     for (int p = 0; p < T; p++) {                                      /* scene.cpp:163-186 */
         const Material& material = sc->materials[sc->materialIds[p]];
         if (material.type != Material::Light) continue;
@@ -130,6 +133,49 @@ OrcScene* orc_scene_create(int T, const float* vertices, const float* normals, c
     sc->dev.BVHSize = BVHBuilder::build(sc->vertices, sc->boxes, sc->nodes);            /* scene.cpp:199 */
     finishScene(sc);
     return sc;
+}
+
+/* Scene::textures / envMapTexId as Scene::addTexture + createLightSampler (scene.cpp:136-157) would leave them, with
+ * DevTextureObj / DevDiscreteSampler1D pointing at host memory */
+int orc_scene_set_textures(OrcScene* sc, int numTextures, const int* widths, const int* heights, const float* const* rgb, int envMapTexId) {
+    sc->texData.resize(numTextures); sc->texObjs.resize(numTextures);
+    for (int t = 0; t < numTextures; t++) {
+        size_t n = (size_t)widths[t] * heights[t];
+        sc->texData[t].resize(n);
+        memcpy((void*)sc->texData[t].data(), rgb[t], n * sizeof(glm::vec3));
+        sc->texObjs[t].width = widths[t]; sc->texObjs[t].height = heights[t]; sc->texObjs[t].devData = sc->texData[t].data();
+    }
+    for (const Material& m : sc->materials) {
+        const int ids[4] = {m.baseColorMapId, m.metallicMapId, m.roughnessMapId, m.normalMapId};
+        for (int k = 0; k < 4; k++)
+            if (ids[k] >= numTextures || ids[k] < (k == 0 ? ProceduralTexId : NullTextureId)) return -1;
+    }
+    if (envMapTexId >= numTextures) return -1;
+    sc->dev.textures = sc->texObjs.data();
+    if (envMapTexId >= 0) {
+        const DevTextureObj& envMap = sc->texObjs[envMapTexId];
+        std::vector<float> pdf(envMap.width * envMap.height);
+        for (int i = 0; i < envMap.height; i++) {                                       /* scene.cpp:141-146 */
+            for (int j = 0; j < envMap.width; j++) {
+                int idx = i * envMap.width + j;
+                pdf[idx] = Math::luminance(envMap.devData[idx]) * glm::sin((.5f + i) / envMap.height * Pi);
+            }
+        }
+        sc->envMapSampler = DiscreteSampler1D<float>(pdf);
+        sc->lightPower.push_back(sc->envMapSampler.sumAll);                             /* scene.cpp:151 */
+        sc->lightSampler = DiscreteSampler1D<float>(sc->lightPower);                    /* scene.cpp:154 */
+        sc->dev.envMap = sc->texObjs.data() + envMapTexId;                              /* scene.cpp:496-499 */
+        sc->dev.envMapSampler.devBinomDistribs = sc->envMapSampler.binomDistribs.data();
+        sc->dev.envMapSampler.length = (int)sc->envMapSampler.binomDistribs.size();
+        sc->dev.envMapSampler.sumAll = sc->envMapSampler.sumAll;
+        finishScene(sc);
+    }
+    return 0;
+}
+const void* orc_scene_env_alias(const OrcScene* s, int* lengthOut, float* sumAllOut) {
+    if (lengthOut) *lengthOut = s->dev.envMapSampler.length;
+    if (sumAllOut) *sumAllOut = s->dev.envMapSampler.sumAll;
+    return s->dev.envMapSampler.devBinomDistribs;
 }
 
 /* the reference's own parser + flattening + upload (over fake cudart) */
@@ -225,7 +271,12 @@ void orc_gbuffer_render(OrcFrame* f, const OrcCamera* ocam) {
                 else
                     gBuffer.devMotion[idx] = -1;
             } else {
-                gBuffer.devAlbedo[idx] = glm::vec3(0.f);
+                glm::vec3 albedo(0.f);
+                if (scene->envMap != nullptr) {                                          /* gbuffer.cu:59-62 */
+                    glm::vec2 uv = Math::toPlane(ray.direction);
+                    albedo = scene->envMap->linearSample(uv);
+                }
+                gBuffer.devAlbedo[idx] = albedo;
                 gBuffer.normal()[idx] = GBuffer::NormT(0.f);
                 gBuffer.primId()[idx] = NullPrimitive;
                 gBuffer.depth()[idx] = 1.f;
@@ -306,7 +357,11 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* ocam, const OrcParams* prm,
             Ray ray = cam.sample(x, y, draw4(rng));
             Intersection intersec;
             scene->intersect(ray, intersec);
-            if (intersec.primId == NullPrimitive) { c.status = 0; continue; }
+            if (intersec.primId == NullPrimitive) {                                      /* restir.cu:133-138 */
+                c.status = 0; c.direct = glm::vec3(0.f);
+                if (scene->envMap != nullptr) c.direct = scene->envMap->linearSample(Math::toPlane(ray.direction));
+                continue;
+            }
             Material material = scene->getTexturedMaterialAndSurface(intersec);
             material.baseColor = glm::vec3(1.f);
             if (material.type == Material::Type::Light) { c.status = 1; continue; }
@@ -376,6 +431,7 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* ocam, const OrcParams* prm,
             int index = y * cam.resolution.x + x;
             OrcFrame::Carry& c = f->carry[index];
             glm::vec3 direct(0.f);
+            if (c.status == 0) direct = c.direct;
             if (c.status == 1) direct = glm::vec3(1.f);
             if (c.status == 2) {
                 DirectReservoir reservoir = c.r;
@@ -409,7 +465,9 @@ void orc_pathtrace_direct(OrcFrame* f, const OrcCamera* ocam, int looper, int it
             Ray ray = cam.sample(x, y, draw4(rng));
             Intersection intersec;
             scene->intersect(ray, intersec);
-            if (intersec.primId != NullPrimitive) {
+            if (intersec.primId == NullPrimitive) {
+                if (scene->envMap != nullptr) direct = scene->envMap->linearSample(Math::toPlane(ray.direction));   /* pathtrace.cu:295-300 */
+            } else {
                 Material material = scene->getTexturedMaterialAndSurface(intersec);
                 if (material.type == Material::Type::Light) direct = material.baseColor;
                 else {

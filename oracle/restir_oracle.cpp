@@ -261,6 +261,12 @@ struct OrcScene {
     std::vector<float> lightPower;
     std::vector<Alias> alias;
     float sumAll = 0.f, sumLightPowerInv = 0.f;
+    /* textures (image.h:7-39, linear RGB float) and the environment map (scene.cpp:136-152) */
+    struct Tex { int w = 0, h = 0; std::vector<V3> data; };
+    std::vector<Tex> textures;
+    int envMapTexId = -1;
+    std::vector<Alias> envAlias;
+    float envSumAll = 0.f;
 };
 
 namespace {
@@ -494,6 +500,91 @@ bool sceneOccluded(const OrcScene& sc, V3 x, V3 y, ShadowStats* st = nullptr) {
     return false;
 }
 
+
+/* ---------------------------------------------------------------- textures (image.h:41-74, scene.h:68-99, mathUtil.h:134-155) */
+inline float fractf(float x) { return x - floorf(x); }                            /* func_common.inl:332 */
+inline V3 linearSample(const OrcScene::Tex& t, V2 uv) {                          /* image.h:41-74 */
+    const int width = t.w, height = t.h;
+    uv = {fractf(uv.x), fractf(uv.y)};
+    float fx = uv.x * ((float)width - FLT_MIN) + .5f;
+    float fy = uv.y * ((float)height - FLT_MIN) + .5f;
+    int ix = f2i_cuda(fractf(fx) > .5f ? fx : fx - 1);
+    if (ix < 0) ix += width;
+    int iy = f2i_cuda(fractf(fy) > .5f ? fy : fy - 1);
+    if (iy < 0) iy += height;
+    int ux = ix + 1;
+    if (ux >= width) ux -= width;
+    int uy = iy + 1;
+    if (uy >= height) uy -= height;
+    float lx = fractf(fx + .5f);
+    float ly = fractf(fy + .5f);
+    V3 c1 = mix(t.data[iy * width + ix], t.data[iy * width + ux], lx);
+    V3 c2 = mix(t.data[uy * width + ix], t.data[uy * width + ux], lx);
+    return mix(c1, c2, ly);
+}
+inline V3 proceduralTexture(V2 uv) {                                              /* scene.h:68-76 */
+    Rng rng(0, 0);
+    uint32_t seed = (uint32_t)(f2i_cuda(uv.x * 1024) * 1024 + f2i_cuda(uv.y * 1024));
+    rng.x = seed % 2147483647u;
+    if (rng.x == 0) rng.x = 1;
+    float rx = rng.next();
+    float ry = rng.next();
+    const float PiTwo = 6.2831853071795864769252867665590057683943f;
+    float f = (sinf(uv.x * 10.f * PiTwo + rx * PiTwo) + 1.f) * .5f;
+    float g = (sinf(uv.y * 10.f * PiTwo + ry * PiTwo) + 1.f) * .5f;
+    return v3(f * g);
+}
+inline V3 localToWorld(V3 n, V3 v) {                                              /* mathUtil.h:146-155 */
+    V3 t = (fabsf(n.y) > 0.9999f) ? v3(0.f, 0.f, 1.f) : v3(0.f, 1.f, 0.f);
+    V3 b = normalize(cross(n, t));
+    t = cross(b, n);
+    /* mat3(t, b, n) * v: type_mat3x3.inl operator*(mat, vec) = m[0][i]*v.x + m[1][i]*v.y + m[2][i]*v.z */
+    V3 r = {t.x * v.x + b.x * v.y + n.x * v.z, t.y * v.x + b.y * v.y + n.y * v.z, t.z * v.x + b.z * v.y + n.z * v.z};
+    return normalize(r);
+}
+inline V2 toPlane(V3 v) {                                                         /* mathUtil.h:139-144 (PiInv = 1.f / Pi unparenthesised) */
+    return {fractf(atan2f(v.z, v.x) * 1.f / Pi * .5f + 1.f), atan2f(sqrtf(v.x * v.x + v.z * v.z), v.y) * 1.f / Pi};
+}
+inline V3 toSphere(V2 v) {                                                        /* mathUtil.h:134-137 */
+    const float PiTwo = 6.2831853071795864769252867665590057683943f;
+    v = {v.x * PiTwo, v.y * Pi};
+    return {cosf(v.x) * sinf(v.y), cosf(v.y), sinf(v.x) * sinf(v.y)};
+}
+/* scene.h:78-99: the material with its maps applied; may replace is.norm (normal map) */
+inline OrcMaterial texturedMaterial(const OrcScene& sc, Isect& is) {
+    OrcMaterial mat = sc.materials[is.matId];
+    if (mat.baseColorMapId != -1) {
+        V3 c = mat.baseColorMapId == -2 ? proceduralTexture(is.uv) : linearSample(sc.textures[mat.baseColorMapId], is.uv);
+        mat.baseColor[0] = c.x; mat.baseColor[1] = c.y; mat.baseColor[2] = c.z;
+    }
+    if (mat.metallicMapId > -1) mat.metallic = linearSample(sc.textures[mat.metallicMapId], is.uv).x;
+    if (mat.roughnessMapId > -1) mat.roughness = linearSample(sc.textures[mat.roughnessMapId], is.uv).x;
+    if (mat.normalMapId != -1) {
+        V3 mapped = linearSample(sc.textures[mat.normalMapId], is.uv);
+        V3 localNorm = normalize(v3(mapped.x * 1.f - 0.5f, mapped.y * 1.f - 0.5f, mapped.z * 1.f - 0.5f));
+        is.norm = localToWorld(is.norm, localNorm);
+    }
+    return mat;
+}
+inline V3 envMapLookup(const OrcScene& sc, V3 dir) { return linearSample(sc.textures[sc.envMapTexId], toPlane(dir)); }
+inline int envAliasSample(const OrcScene& sc, float r1, float r2) {               /* sampler.h:203-207 on envMapSampler */
+    int len = (int)sc.envAlias.size();
+    int pass = f2i_cuda((float)len * r1);
+    pass = pass < len - 1 ? pass : len - 1;
+    Alias d = sc.envAlias[pass];
+    return (r2 < d.prob) ? pass : d.failId;
+}
+/* scene.h:364-375 (and the unoccluded part of :377-392): pixel of the map -> radiance, direction, pdf */
+inline float sampleEnvironmentMap(const OrcScene& sc, float r1, float r2, V3& radiance, V3& wi, int& pixId) {
+    const OrcScene::Tex& env = sc.textures[sc.envMapTexId];
+    pixId = envAliasSample(sc, r1, r2);
+    int y = pixId / env.w;
+    int x = pixId - y * env.w;
+    radiance = env.data[pixId];
+    wi = toSphere({(.5f + x) / env.w, (.5f + y) / env.h});
+    return luminance(radiance) * sc.sumLightPowerInv * env.w * env.h * 1.f / Pi * 1.f / Pi * .5f;
+}
+
 /* sampler.h:203-207 (device lookup; the float->int runs on the GPU) */
 inline int aliasSample(const OrcScene& sc, float r1, float r2) {
     int len = (int)sc.alias.size();
@@ -503,11 +594,18 @@ inline int aliasSample(const OrcScene& sc, float r1, float r2) {
     return (r2 < d.prob) ? pass : d.failId;
 }
 
-/* scene.h:394-425; r = (x,y,z,w); envmap branch (:400-403) is out of scope ("next") */
+/* scene.h:394-425; r = (x,y,z,w).  lightIdOut for the environment map (:400-403) is (L-1) + pixel id. */
 float sampleDirectLightNoVisibility(const OrcScene& sc, V3 pos, const float r[4], V3& radiance, V3& wi, float& dist, int& lightIdOut) {
     if (sc.alias.empty()) return -1.f;
     int lightId = aliasSample(sc, r[0], r[1]);
     lightIdOut = lightId;
+    if (lightId == (int)sc.alias.size() - 1 && !sc.envAlias.empty()) {
+        dist = 1e10f;
+        int pix;
+        float pdf = sampleEnvironmentMap(sc, r[2], r[3], radiance, wi, pix);
+        lightIdOut = lightId + pix;
+        return pdf;
+    }
     int prim = sc.lightPrimIds[lightId];
     V3 v0 = sc.vertices[prim * 3], v1 = sc.vertices[prim * 3 + 1], v2 = sc.vertices[prim * 3 + 2];
     /* mathUtil.h:94-100 sampleTriangleUniform(v0,v1,v2, ru = r.z, rv = r.w) */
@@ -533,6 +631,12 @@ float sampleDirectLightNoVisibility(const OrcScene& sc, V3 pos, const float r[4]
 float sampleDirectLight(const OrcScene& sc, V3 pos, const float r[4], V3& radiance, V3& wi) {
     if (sc.alias.empty()) return -1.f;
     int lightId = aliasSample(sc, r[0], r[1]);
+    if (lightId == (int)sc.alias.size() - 1 && !sc.envAlias.empty()) {    /* :433-435 -> sampleEnvironmentMap :377-392 */
+        int pix;
+        float pdf = sampleEnvironmentMap(sc, r[2], r[3], radiance, wi, pix);
+        if (sceneOccluded(sc, pos, pos + wi * 1e6f)) return -1.f;
+        return pdf;
+    }
     int prim = sc.lightPrimIds[lightId];
     V3 v0 = sc.vertices[prim * 3], v1 = sc.vertices[prim * 3 + 1], v2 = sc.vertices[prim * 3 + 2];
     float sr = sqrtf(r[3]);
@@ -639,7 +743,7 @@ struct OrcFrame {
     TraceStats stats;
     ShadowStats shadow;
     /* per-pixel state carried across the two phases of spatial reuse */
-    struct Carry { uint32_t rng; int status; Resv r; V3 n, wo; int matId; };
+    struct Carry { uint32_t rng; int status; Resv r; V3 n, wo, direct; OrcMaterial mat; };
     std::vector<Carry> carry;
 };
 
@@ -690,12 +794,48 @@ OrcScene* orc_scene_create(int numTris, const float* vertices, const float* norm
     buildBVH(*sc);                                                    /* scene.cpp:199 */
     return sc;
 }
+/* Scene::addTexture results + Scene::createLightSampler (scene.cpp:136-157): call once, right after orc_scene_create */
+int orc_scene_set_textures(OrcScene* sc, int numTextures, const int* widths, const int* heights, const float* const* rgb, int envMapTexId) {
+    sc->textures.resize(numTextures);
+    for (int t = 0; t < numTextures; t++) {
+        OrcScene::Tex& tx = sc->textures[t];
+        tx.w = widths[t]; tx.h = heights[t];
+        tx.data.resize((size_t)tx.w * tx.h);
+        memcpy(tx.data.data(), rgb[t], sizeof(V3) * tx.data.size());
+    }
+    for (const OrcMaterial& m : sc->materials) {
+        const int ids[4] = {m.baseColorMapId, m.metallicMapId, m.roughnessMapId, m.normalMapId};
+        for (int k = 0; k < 4; k++)
+            if (ids[k] >= numTextures || ids[k] < (k == 0 ? -2 : -1)) return -1;
+    }
+    if (envMapTexId >= numTextures) return -1;
+    sc->envMapTexId = envMapTexId < 0 ? -1 : envMapTexId;
+    if (sc->envMapTexId >= 0) {
+        const OrcScene::Tex& env = sc->textures[envMapTexId];
+        std::vector<float> pdf((size_t)env.w * env.h);
+        for (int i = 0; i < env.h; i++)
+            for (int j = 0; j < env.w; j++) {
+                int idx = i * env.w + j;
+                pdf[idx] = luminance(env.data[idx]) * sinf((.5f + i) / env.h * Pi);       /* scene.cpp:144 */
+            }
+        buildAlias(pdf, sc->envAlias, sc->envSumAll);
+        sc->lightPower.push_back(sc->envSumAll);                                        /* scene.cpp:151 */
+        buildAlias(sc->lightPower, sc->alias, sc->sumAll);                              /* scene.cpp:154 */
+        sc->sumLightPowerInv = 1.f / sc->sumAll;
+    }
+    return 0;
+}
+const void* orc_scene_env_alias(const OrcScene* s, int* lengthOut, float* sumAllOut) {
+    if (lengthOut) *lengthOut = (int)s->envAlias.size();
+    if (sumAllOut) *sumAllOut = s->envSumAll;
+    return s->envAlias.data();
+}
 void orc_scene_destroy(OrcScene* s) { delete s; }
 int orc_scene_bvh_size(const OrcScene* s) { return s->bvhSize; }
 int orc_scene_bvh_depth(const OrcScene* s) { return s->bvhDepth; }
 const float* orc_scene_boxes(const OrcScene* s) { return (const float*)s->boxes.data(); }
 const int* orc_scene_mtbvh(const OrcScene* s, int i) { return (const int*)s->nodes[i].data(); }
-int orc_scene_num_lights(const OrcScene* s) { return (int)s->lightPrimIds.size(); }
+int orc_scene_num_lights(const OrcScene* s) { return (int)s->alias.size(); }    /* lightSampler.length: emissive triangles (+1 for an environment map) */
 const int* orc_scene_light_prim_ids(const OrcScene* s) { return s->lightPrimIds.data(); }
 const float* orc_scene_light_radiance(const OrcScene* s) { return (const float*)s->lightUnitRadiance.data(); }
 const void* orc_scene_alias_table(const OrcScene* s) { return s->alias.data(); }
@@ -768,9 +908,9 @@ void orc_gbuffer_render(OrcFrame* f, const OrcCamera* cam) {
                 sceneIntersect(sc, ray, is, &st);
                 if (is.primId != -1) {
                     int matId = is.matId;
-                    const OrcMaterial& m = sc.materials[is.matId];
-                    if (m.type == 4) matId = -2;                       /* :29-31 */
-                    f->albedo[idx] = {m.baseColor[0], m.baseColor[1], m.baseColor[2]};   /* untextured (textures: "next") */
+                    if (sc.materials[is.matId].type == 4) matId = -2;  /* :29-31 */
+                    const OrcMaterial m = texturedMaterial(sc, is);    /* :37 (may replace is.norm) */
+                    f->albedo[idx] = {m.baseColor[0], m.baseColor[1], m.baseColor[2]};
                     f->normal[cur][idx] = is.norm;
                     f->matId[cur][idx] = matId;
                     f->depth[cur][idx] = length(ray.origin - is.pos);  /* glm::distance(pos, origin) = length(origin - pos) */
@@ -778,7 +918,7 @@ void orc_gbuffer_render(OrcFrame* f, const OrcCamera* cam) {
                     rasterCoord(lastCam, is.pos, lx, ly);
                     f->motion[idx] = (lx >= 0 && lx < f->w && ly >= 0 && ly < f->h) ? ly * W + lx : -1;
                 } else {
-                    f->albedo[idx] = v3(0.f);
+                    f->albedo[idx] = sc.envMapTexId >= 0 ? envMapLookup(sc, ray.direction) : v3(0.f);   /* :58-63 */
                     f->normal[cur][idx] = v3(0.f);
                     f->matId[cur][idx] = -1;
                     f->depth[cur][idx] = 1.f;
@@ -867,8 +1007,12 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
             Ray ray = cameraRay(*cam, x, y, r4[0], r4[1], tanFovY);
             Isect is;
             sceneIntersect(sc, ray, is);
-            if (is.primId == -1) { c.status = 0; continue; }                  /* :133-138 (no envmap) */
-            const OrcMaterial& material = sc.materials[is.matId];
+            if (is.primId == -1) {                                             /* :133-138 */
+                c.status = 0;
+                c.direct = sc.envMapTexId >= 0 ? envMapLookup(sc, ray.direction) : v3(0.f);
+                continue;
+            }
+            const OrcMaterial material = texturedMaterial(sc, is);            /* :140 */
             const V3 baseColor = v3(1.f);                                      /* :141 */
             if (material.type == 4) { c.status = 1; continue; }               /* :143-146 */
             is.wo = -ray.direction;
@@ -897,7 +1041,7 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
             }
             tempReservoir.checkValidity();                                     /* :211-212 */
             out[index] = tempReservoir;
-            c.status = 2; c.rng = rng.x; c.r = reservoir; c.n = is.norm; c.wo = is.wo; c.matId = is.matId;
+            c.status = 2; c.rng = rng.x; c.r = reservoir; c.n = is.norm; c.wo = is.wo; c.mat = material;
         }
     }
 #pragma omp critical
@@ -941,10 +1085,11 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
             int index = y * W + x;
             OrcFrame::Carry& c = f->carry[index];
             V3 direct = v3(0.f);
+            if (c.status == 0) direct = c.direct;
             if (c.status == 1) direct = v3(1.f);
             if (c.status == 2) {
                 Resv reservoir = c.r;
-                const OrcMaterial& material = sc.materials[c.matId];
+                const OrcMaterial& material = c.mat;
                 Sample s = reservoir.s;                                        /* :216-222 */
                 if (!reservoir.invalid()) {
                     V3 LiBSDF = s.Li * materialBSDF(material, v3(1.f), c.n, c.wo, s.wi);
@@ -976,8 +1121,10 @@ void orc_pathtrace_direct(OrcFrame* f, const OrcCamera* cam, int looper, int ite
             Ray ray = cameraRay(*cam, x, y, r4[0], r4[1], tanFovY);
             Isect is;
             sceneIntersect(sc, ray, is);
-            if (is.primId != -1) {
-                const OrcMaterial& material = sc.materials[is.matId];
+            if (is.primId == -1) {
+                if (sc.envMapTexId >= 0) direct = envMapLookup(sc, ray.direction);      /* :295-300 */
+            } else {
+                const OrcMaterial material = texturedMaterial(sc, is);                  /* :302 */
                 V3 baseColor = {material.baseColor[0], material.baseColor[1], material.baseColor[2]};
                 if (material.type == 4) direct = baseColor;
                 else {

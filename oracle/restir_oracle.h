@@ -77,6 +77,11 @@ typedef struct OrcFrame OrcFrame;
 OrcScene* orc_scene_create(int numTris, const float* vertices, const float* normals,
                            const float* texcoords, const int* materialIds,
                            int numMaterials, const OrcMaterial* materials);
+/* Textures (linear RGB float, width x height x 3, row-major; image.h:7-39) referenced by the materials' map ids, and
+ * the environment map (texture index or -1).  Call once, right after orc_scene_create: an environment map becomes the
+ * last entry of the light sampler (scene.cpp:136-157).  Returns 0, or -1 for an out-of-range texture id. */
+int  orc_scene_set_textures(OrcScene*, int numTextures, const int* widths, const int* heights, const float* const* rgb, int envMapTexId);
+const void* orc_scene_env_alias(const OrcScene*, int* lengthOut, float* sumAllOut);   /* envMapSampler table, W*H x {f32, i32} */
 void orc_scene_destroy(OrcScene*);
 int  orc_scene_bvh_size(const OrcScene*);
 const float* orc_scene_boxes(const OrcScene*);          /* bvhSize x 6 f32 */

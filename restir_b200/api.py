@@ -64,7 +64,14 @@ class RstrSceneDesc(C.Structure):
         ("materialIds", C.c_void_p),
         ("numMaterials", C.c_int),
         ("materials", C.c_void_p),
+        ("numTextures", C.c_int),
+        ("textures", C.c_void_p),
+        ("envMap", C.c_int),
     ]
+
+
+class RstrTexture(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("rgb", C.c_void_p)]
 
 
 class RstrSceneInfo(C.Structure):
@@ -79,6 +86,10 @@ class RstrSceneInfo(C.Structure):
         ("deviceBytes", C.c_size_t),
         ("tracedBvhDepth", C.c_int),
         ("tracedBuildSeconds", C.c_double),
+        ("numEmissiveTris", C.c_int),
+        ("numTextures", C.c_int),
+        ("envWidth", C.c_int),
+        ("envHeight", C.c_int),
     ]
 
 
@@ -89,7 +100,7 @@ RESERVOIR_DTYPE = np.dtype([("Li", "<f4", (3,)), ("wi", "<f4", (3,)), ("dist", "
 ALIAS_DTYPE = np.dtype([("prob", "<f4"), ("failId", "<i4")])
 
 SCENE_ARRAYS = dict(boxes=0, mtbvh0=1, light_prim_ids=7, light_radiance=8, alias=9, vertices=10, normals=11,
-                    texcoords=12, material_ids=13, materials=14)
+                    texcoords=12, material_ids=13, materials=14, env_alias=15)
 FRAME_BUFFERS = dict(albedo=0, normal=1, matid=2, depth=3, motion=4, radiance=5, reservoir=6, reservoir_temp=7,
                      light_index=8, ldr=9)
 STAGES = ("gbuffer", "ris", "spatial", "ptdirect", "tonemap")
@@ -229,7 +240,12 @@ class Scene:
         t = np.ascontiguousarray(sd.texcoords, np.float32)
         m = np.ascontiguousarray(sd.material_ids, np.int32)
         mats = np.ascontiguousarray(sd.materials)
-        desc = RstrSceneDesc(int(m.shape[0]), v.ctypes.data, n.ctypes.data, t.ctypes.data, m.ctypes.data, len(mats), mats.ctypes.data)
+        texs = [np.ascontiguousarray(x, np.float32) for x in getattr(sd, "textures", [])]
+        tarr = (RstrTexture * max(len(texs), 1))()
+        for i, x in enumerate(texs):
+            tarr[i] = RstrTexture(int(x.shape[1]), int(x.shape[0]), x.ctypes.data)
+        desc = RstrSceneDesc(int(m.shape[0]), v.ctypes.data, n.ctypes.data, t.ctypes.data, m.ctypes.data, len(mats), mats.ctypes.data,
+                             len(texs), C.cast(tarr, C.c_void_p) if texs else None, int(getattr(sd, "env_map", -1)) + 1)
         h = C.c_void_p()
         _check(lib().rstr_scene_create(C.byref(desc), C.byref(h)))
         return cls(h)
@@ -257,10 +273,11 @@ class Scene:
         return dict(gbuffer=int(v[0]), restir_a=int(v[1]), ptdirect=int(v[2]))
 
     def read(self, name: str, ordering: int = 0) -> np.ndarray:
-        T, L, N = self.info.numTris, self.info.numLights, self.info.bvhSize
+        T, L, N, E = self.info.numTris, self.info.numLights, self.info.bvhSize, self.info.numEmissiveTris
         spec = {
-            "boxes": (np.float32, (N, 6)), "mtbvh": (np.int32, (N, 3)), "light_prim_ids": (np.int32, (L,)),
-            "light_radiance": (np.float32, (L, 3)), "alias": (ALIAS_DTYPE, (L,)), "vertices": (np.float32, (3 * T, 3)),
+            "boxes": (np.float32, (N, 6)), "mtbvh": (np.int32, (N, 3)), "light_prim_ids": (np.int32, (E,)),
+            "light_radiance": (np.float32, (E, 3)), "alias": (ALIAS_DTYPE, (L,)), "vertices": (np.float32, (3 * T, 3)),
+            "env_alias": (ALIAS_DTYPE, (self.info.envWidth * self.info.envHeight,)),
             "normals": (np.float32, (3 * T, 3)), "texcoords": (np.float32, (3 * T, 2)), "material_ids": (np.int32, (T,)),
             "materials": (np.dtype("V44"), (self.info.numMaterials,)),
         }[name]

@@ -31,6 +31,7 @@ struct RstrScene {
     void* dNodes = nullptr; void* dTriGeom = nullptr; void* dTriNorm = nullptr;
     void* dFastNodes = nullptr; void* dPrimToFast = nullptr; void* dFallback = nullptr; void* dRank = nullptr;
     void* dMaterials = nullptr; void* dAlias = nullptr; void* dLights = nullptr;
+    void* dTexData = nullptr; void* dTexInfo = nullptr; void* dTriUV = nullptr; void* dEnvAlias = nullptr; void* dEnvDir = nullptr;
     size_t deviceBytes = 0;
     int traversalMode = RS_TRAVERSAL_FAST;
 };
@@ -47,6 +48,7 @@ struct RstrFrame {
     ResvD* resvTemp = nullptr;
     ResvD* resvTemp2 = nullptr;    // second publication buffer, allocated when spatialPasses > 1
     HitRec* hit = nullptr;
+    float2* hitMR = nullptr;       // allocated when the scene has metallic / roughness maps
     uchar4* ldr = nullptr;
     uchar4* ldrB[RSTR_LDR_SLOTS] = {};        // LDR frames in flight of the pipelined host call
     cudaStream_t copyStream = nullptr;
@@ -89,7 +91,7 @@ static FrameDev toFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
     d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
     d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
-    d.hit = f->hit; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount;
+    d.hit = f->hit; d.hitMR = f->hitMR; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount;
     return d;
 }
 
@@ -128,10 +130,15 @@ static int ensureUploaded(RstrScene* sc) {
         (e = upload(&sc->dFastNodes, hs.fastNodes, total)) != cudaSuccess || (e = upload(&sc->dRank, hs.rank, total)) != cudaSuccess || (e = upload(&sc->dPrimToFast, hs.primToFast, total)) != cudaSuccess ||
 
         (e = upload(&sc->dTriNorm, hs.triNorm, total)) != cudaSuccess || (e = upload(&sc->dMaterials, hs.materials, total)) != cudaSuccess ||
-        (e = upload(&sc->dAlias, hs.alias, total)) != cudaSuccess || (e = upload(&sc->dLights, hs.lights, total)) != cudaSuccess) {
+        (e = upload(&sc->dAlias, hs.alias, total)) != cudaSuccess || (e = upload(&sc->dLights, hs.lights, total)) != cudaSuccess ||
+        (e = upload(&sc->dTexData, hs.texData, total)) != cudaSuccess || (e = upload(&sc->dTexInfo, hs.texInfo, total)) != cudaSuccess ||
+        (e = upload(&sc->dTriUV, hs.triUV, total)) != cudaSuccess || (e = upload(&sc->dEnvAlias, hs.envAlias, total)) != cudaSuccess ||
+        (e = upload(&sc->dEnvDir, hs.envDir, total)) != cudaSuccess) {
         std::string m = std::string("scene upload failed: ") + cudaGetErrorString(e);
         cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
         cudaFree(sc->dFastNodes); cudaFree(sc->dPrimToFast);
+        cudaFree(sc->dTexData); cudaFree(sc->dTexInfo); cudaFree(sc->dTriUV); cudaFree(sc->dEnvAlias); cudaFree(sc->dEnvDir);
+        sc->dTexData = sc->dTexInfo = sc->dTriUV = sc->dEnvAlias = sc->dEnvDir = nullptr;
         sc->dNodes = sc->dTriGeom = sc->dTriNorm = sc->dMaterials = sc->dAlias = sc->dLights = sc->dFastNodes = sc->dPrimToFast = nullptr;
         return fail(RSTR_ERR_CUDA, m);
     }
@@ -145,7 +152,12 @@ static int ensureUploaded(RstrScene* sc) {
     d.fastNodes = (const float4*)sc->dFastNodes; d.primToFast = (const int*)sc->dPrimToFast; d.rank = (const int*)sc->dRank;
     d.numTris = hs.T; d.fastRoot = hs.fastRoot; d.traversal = sc->traversalMode;
     memcpy(d.fastRootMin, hs.fastRootMin, 12); memcpy(d.fastRootMax, hs.fastRootMax, 12);
-    d.numLights = (int)hs.lights.size();
+    d.numLights = (int)hs.alias.size();           // lightSampler.length: emissive triangles (+ the environment map, last)
+    d.texData = (const float4*)sc->dTexData; d.texInfo = (const int4*)sc->dTexInfo; d.triUV = (const float4*)sc->dTriUV;
+    d.anyMaps = hs.anyMaps ? 1 : 0;
+    d.envTex = hs.envMapTexId; d.envLen = (int)hs.envAlias.size();
+    d.envAlias = (const float2*)sc->dEnvAlias; d.envDir = (const float4*)sc->dEnvDir;
+    d.sumLightPowerInv = hs.sumLightPowerInv;
     d.rootRef = hs.rootRef;
     memcpy(d.rootMin, &hs.rootBox.pMin, 12); memcpy(d.rootMax, &hs.rootBox.pMax, 12);
     return RSTR_OK;
@@ -182,6 +194,19 @@ int rstr_scene_create(const RstrSceneDesc* desc, RstrScene** out) {
     if (desc->texcoords) memcpy(hs.texcoords.data(), desc->texcoords, 24 * (size_t)T);
     hs.materialIds.assign(desc->materialIds, desc->materialIds + T);
     hs.materials.assign(desc->materials, desc->materials + desc->numMaterials);
+    if (desc->numTextures < 0 || (desc->numTextures > 0 && !desc->textures) || desc->envMap < 0 || desc->envMap > desc->numTextures) {
+        delete sc;
+        return fail(RSTR_ERR_ARG, "rstr_scene_create: bad texture list / environment map index");
+    }
+    hs.textures.resize(desc->numTextures);
+    for (int t = 0; t < desc->numTextures; t++) {
+        const RstrTexture& src = desc->textures[t];
+        if (src.width <= 0 || src.height <= 0 || !src.rgb) { delete sc; return fail(RSTR_ERR_ARG, "rstr_scene_create: empty texture"); }
+        hs.textures[t].w = src.width; hs.textures[t].h = src.height;
+        hs.textures[t].rgb.resize((size_t)src.width * src.height);
+        memcpy(hs.textures[t].rgb.data(), src.rgb, 12 * hs.textures[t].rgb.size());
+    }
+    hs.envMapTexId = desc->envMap - 1;
     return finishScene(sc, out);
 }
 
@@ -200,6 +225,7 @@ int rstr_scene_destroy(RstrScene* sc) {
     if (!sc) return RSTR_OK;
     cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
     cudaFree(sc->dFastNodes); cudaFree(sc->dPrimToFast); cudaFree(sc->dFallback); cudaFree(sc->dRank);
+    cudaFree(sc->dTexData); cudaFree(sc->dTexInfo); cudaFree(sc->dTriUV); cudaFree(sc->dEnvAlias); cudaFree(sc->dEnvDir);
     delete sc;
     return RSTR_OK;
 }
@@ -225,10 +251,13 @@ int rstr_scene_fallback_rays(RstrScene* sc, unsigned long long* count, int reset
 
 int rstr_scene_info(const RstrScene* sc, RstrSceneInfo* info) {
     if (!sc || !info) return fail(RSTR_ERR_ARG, "rstr_scene_info: bad argument");
-    info->numTris = sc->hs.T; info->numLights = (int)sc->hs.lightPrimIds.size(); info->bvhSize = sc->hs.bvhSize;
+    info->numTris = sc->hs.T; info->numLights = (int)sc->hs.alias.size(); info->bvhSize = sc->hs.bvhSize;
     info->bvhDepth = sc->hs.bvhDepth; info->numMaterials = (int)sc->hs.materials.size(); info->sumLightPower = sc->hs.sumAll;
     info->buildSeconds = sc->hs.buildSeconds; info->deviceBytes = sc->deviceBytes;
     info->tracedBvhDepth = sc->hs.fastDepth; info->tracedBuildSeconds = sc->hs.fastBuildSeconds;
+    info->numEmissiveTris = (int)sc->hs.lightPrimIds.size(); info->numTextures = (int)sc->hs.textures.size();
+    info->envWidth = info->envHeight = 0;
+    if (sc->hs.envMapTexId >= 0) { info->envWidth = sc->hs.textures[sc->hs.envMapTexId].w; info->envHeight = sc->hs.textures[sc->hs.envMapTexId].h; }
     return RSTR_OK;
 }
 
@@ -248,6 +277,7 @@ int rstr_scene_read(const RstrScene* sc, int which, void* host, size_t bytes) {
     case RSTR_SCENE_TEXCOORDS: src = hs.texcoords.data(); need = hs.texcoords.size() * 4; break;
     case RSTR_SCENE_MATERIAL_IDS: src = hs.materialIds.data(); need = hs.materialIds.size() * 4; break;
     case RSTR_SCENE_MATERIALS: src = hs.materials.data(); need = hs.materials.size() * sizeof(RstrMaterial); break;
+    case RSTR_SCENE_ENV_ALIAS: src = hs.envAlias.data(); need = hs.envAlias.size() * 8; break;
     default:
         if (which >= RSTR_SCENE_MTBVH0 && which < RSTR_SCENE_MTBVH0 + 6) {
             exportMTBVH(hs, which - RSTR_SCENE_MTBVH0, mt);
@@ -281,7 +311,7 @@ int rstr_frame_destroy(RstrFrame* f) {
     if (!f) return RSTR_OK;
     if (f->stream) cudaStreamSynchronize(f->stream);
     for (int i = 0; i < 2; i++) { cudaFree(f->geom[i]); cudaFree(f->matId[i]); cudaFree(f->resv[i]); }
-    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->resvTemp2); cudaFree(f->hit); cudaFree(f->ldr);
+    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->resvTemp2); cudaFree(f->hit); cudaFree(f->hitMR); cudaFree(f->ldr);
     cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->queueCount);
     for (int i = 0; i < RSTR_LDR_SLOTS; i++) {
         cudaFree(f->ldrB[i]);
@@ -324,6 +354,7 @@ int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int
     alloc((void**)&f->radiance, n * 3 * sizeof(float));
     alloc((void**)&f->resvTemp, n * sizeof(ResvD));
     alloc((void**)&f->hit, n * sizeof(HitRec));
+    if (sc->hs.anyMRMaps) alloc((void**)&f->hitMR, n * sizeof(float2));
     alloc((void**)&f->ldr, n * sizeof(uchar4));
     alloc((void**)&f->haloMiss, sizeof(unsigned int));
     alloc((void**)&f->queue, n * sizeof(int));

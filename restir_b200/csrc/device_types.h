@@ -31,6 +31,16 @@ struct DevScene {
     int numLights;
     int rootRef;               // packed index of the root, or ~primId when the scene is a single triangle
     float rootMin[3], rootMax[3];
+    // textures / environment map (all null / 0 / -1 for scenes without them: the kernels then skip that code)
+    const float4* texData;     // float4 texels of all textures
+    const int4* texInfo;       // per texture {w, h, first texel, 0}
+    const float4* triUV;       // TriUV[] in original primitive order, 2 x float4 each
+    int anyMaps;               // some material has a map id != -1
+    int envTex;                // texture index of the environment map, or -1
+    int envLen;                // envW * envH
+    const float2* envAlias;    // envMapSampler
+    const float4* envDir;      // per texel: direction of its centre
+    float sumLightPowerInv;
 };
 
 // Reservoir in HBM: 32 B, one aligned sector, 2 x LDG/STG.128.  Li is not stored: it is the per-light constant
@@ -77,6 +87,7 @@ struct FrameDev {
     const ResvD* resvIn;       // history of the previous frame
     ResvD* resvTemp;
     HitRec* hit;
+    float2* hitMR;             // {metallic, roughness} of the shaded point; only allocated for scenes with such maps
     int* queue;                // pixels deferred to the reference-order fix-up kernel
     unsigned int* queueCount;
     unsigned int* haloMiss;    // count of neighbour / reprojection reads that fell outside the resident rows

@@ -577,6 +577,88 @@ RS_D f3 materialBSDF(int type, float metallic, float roughness, f3 baseColor, f3
     return mk3(0.f);
 }
 
+
+// ------------------------------------------------------------------------------------------------ textures
+// image.h:41-74 linearSample on the float4-texel copy of texture `id`
+RS_D float fractf_(float x) { return x - floorf(x); }                                                   // func_common.inl:332
+RS_D f3 texLinear(const DevScene& s, int id, float u, float v) {
+    int4 info = __ldg(s.texInfo + id);
+    const int width = info.x, height = info.y;
+    const float4* data = s.texData + info.z;
+    u = fractf_(u); v = fractf_(v);
+    float fx = u * ((float)width - 1.17549435e-38f) + .5f;
+    float fy = v * ((float)height - 1.17549435e-38f) + .5f;
+    int ix = __float2int_rz(fractf_(fx) > .5f ? fx : fx - 1);
+    if (ix < 0) ix += width;
+    int iy = __float2int_rz(fractf_(fy) > .5f ? fy : fy - 1);
+    if (iy < 0) iy += height;
+    int ux = ix + 1;
+    if (ux >= width) ux -= width;
+    int uy = iy + 1;
+    if (uy >= height) uy -= height;
+    float lx = fractf_(fx + .5f);
+    float ly = fractf_(fy + .5f);
+    float4 a = __ldg(data + iy * width + ix), b = __ldg(data + iy * width + ux);
+    float4 c = __ldg(data + uy * width + ix), d = __ldg(data + uy * width + ux);
+    f3 c1 = mix(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), lx);
+    f3 c2 = mix(mk3(c.x, c.y, c.z), mk3(d.x, d.y, d.z), lx);
+    return mix(c1, c2, ly);
+}
+// scene.h:68-76; thrust::default_random_engine seeded with the texel hash, two uniform draws
+RS_D f3 proceduralTex(float u, float v) {
+    Rng rng;
+    uint32_t seed = (uint32_t)(__float2int_rz(u * 1024) * 1024 + __float2int_rz(v * 1024));
+    rng.x = seed % 2147483647u;
+    if (rng.x == 0) rng.x = 1;
+    float rx = rng.next();
+    float ry = rng.next();
+    const float PiTwo = 6.2831853071795864769252867665590057683943f;
+    float f = (sinf(u * 10.f * PiTwo + rx * PiTwo) + 1.f) * .5f;
+    float g = (sinf(v * 10.f * PiTwo + ry * PiTwo) + 1.f) * .5f;
+    return mk3(f * g);
+}
+RS_D f3 localToWorld(f3 n, f3 v) {                                                                      // mathUtil.h:146-155
+    f3 t = (fabsf(n.y) > 0.9999f) ? mk3(0.f, 0.f, 1.f) : mk3(0.f, 1.f, 0.f);
+    f3 b = normalize(cross(n, t));
+    t = cross(b, n);
+    f3 r = mk3(t.x * v.x + b.x * v.y + n.x * v.z, t.y * v.x + b.y * v.y + n.y * v.z, t.z * v.x + b.z * v.y + n.z * v.z);
+    return normalize(r);
+}
+// gbuffer.cu:60-61 / restir.cu:135: envMap->linearSample(Math::toPlane(dir)), mathUtil.h:139-144
+RS_D f3 envLookup(const DevScene& s, f3 d) {
+    float u = fractf_(atan2f(d.z, d.x) * 1.f / RS_PI * .5f + 1.f);
+    float v = atan2f(sqrtf(d.x * d.x + d.z * d.z), d.y) * 1.f / RS_PI;
+    return texLinear(s, s.envTex, u, v);
+}
+// DevScene::getTexturedMaterialAndSurface (scene.h:78-99) at the hit (prim, bary): material with its maps applied;
+// a normal map replaces nrm
+struct Surf { int type; f3 baseColor; float metallic, roughness; };
+RS_D Surf texturedMaterial(const DevScene& s, int matId, int prim, float bx, float by, f3& nrm) {
+    const RstrMaterial* m = s.materials + matId;
+    Surf r;
+    r.type = __ldg(&m->type);
+    r.baseColor = mk3(__ldg(&m->baseColor[0]), __ldg(&m->baseColor[1]), __ldg(&m->baseColor[2]));
+    r.metallic = __ldg(&m->metallic);
+    r.roughness = __ldg(&m->roughness);
+    if (!s.anyMaps) return r;
+    const int bcMap = __ldg(&m->baseColorMapId), mMap = __ldg(&m->metallicMapId), rMap = __ldg(&m->roughnessMapId), nMap = __ldg(&m->normalMapId);
+    if (bcMap == -1 && mMap <= -1 && rMap <= -1 && nMap == -1) return r;
+    const float4* tp = s.triUV + 2 * (size_t)prim;
+    float4 t01 = __ldg(tp), t2 = __ldg(tp + 1);
+    float bz = 1.f - bx - by;
+    float u = t01.z * bx + t2.x * by + t01.x * bz;                                                      // scene.h:150
+    float v = t01.w * bx + t2.y * by + t01.y * bz;
+    if (bcMap != -1) r.baseColor = bcMap == -2 ? proceduralTex(u, v) : texLinear(s, bcMap, u, v);
+    if (mMap > -1) r.metallic = texLinear(s, mMap, u, v).x;
+    if (rMap > -1) r.roughness = texLinear(s, rMap, u, v).x;
+    if (nMap != -1) {
+        f3 mapped = texLinear(s, nMap, u, v);
+        f3 localNorm = normalize(mk3(mapped.x * 1.f - 0.5f, mapped.y * 1.f - 0.5f, mapped.z * 1.f - 0.5f));
+        nrm = localToWorld(nrm, localNorm);
+    }
+    return r;
+}
+
 struct Resv {       // register-resident reservoir (restir.h:29-117); Li is implied by lightId
     f3 wi; float dist; float w; int M; int lightId;
 };
@@ -601,6 +683,10 @@ RS_D void storeResv(ResvD* p, const Resv& r) {
 }
 RS_D f3 lightLe(const DevScene& s, int lightId) {
     if (lightId < 0) return mk3(0.f);
+    if (s.envTex >= 0 && lightId >= s.numLights - 1) {          // environment map: lightId = (L-1) + texel
+        float4 e = __ldg(s.texData + __ldg(s.texInfo + s.envTex).z + (lightId - (s.numLights - 1)));
+        return mk3(e.x, e.y, e.z);
+    }
     float4 d = __ldg(s.lights + 4 * (size_t)lightId + 3);       // LightRec words 12..15 = {Le.x, Le.y, Le.z, pdfArea}
     return mk3(d.x, d.y, d.z);
 }
@@ -638,7 +724,7 @@ RS_D f3 shadeReservoir(const DevScene& s, const Resv& r, int type, float metalli
 
 // ------------------------------------------------------------------------------------------------ kernels
 // gbuffer.cu:3-73 for one pixel; false = undecided, nothing written
-RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& lastCam, int x, int y, f3 o, const Hit& h);
+RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& lastCam, int x, int y, f3 o, f3 d, const Hit& h);
 
 template <bool EXACT>
 RS_D bool gbufferPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, int x, int y, Stack& stack) {
@@ -647,12 +733,12 @@ RS_D bool gbufferPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, 
     RayT r = makeRayT(o, d);
     Hit h;
     if (!traceClosest<EXACT>(s, r, h, stack)) return false;
-    gbufferFinish(s, f, lastCam, x, y, o, h);
+    gbufferFinish(s, f, lastCam, x, y, o, d, h);
     return true;
 }
 
 // gbuffer.cu:28-72: what is stored for a pixel once its hit is known
-RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& lastCam, int x, int y, f3 o, const Hit& h) {
+RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& lastCam, int x, int y, f3 o, f3 d, const Hit& h) {
     size_t li = planeIndex(f, x, y);
     if (h.prim >= 0) {
         Tri t = loadTri(s, h.prim);
@@ -662,10 +748,9 @@ RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& last
         float bz = 1.f - h.bx - h.by;
         f3 pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;                              // scene.h:148
         f3 nrm = normalize(nb * h.bx + nc * h.by + na * bz);                         // scene.h:149
-        const RstrMaterial* m = s.materials + t.matId;
-        int type = __ldg(&m->type);
-        int matId = type == 4 ? -2 : t.matId;                                        // gbuffer.cu:29-31
-        f3 albedo = mk3(__ldg(&m->baseColor[0]), __ldg(&m->baseColor[1]), __ldg(&m->baseColor[2]));
+        Surf m = texturedMaterial(s, t.matId, h.prim, h.bx, h.by, nrm);              // gbuffer.cu:37
+        int matId = m.type == 4 ? -2 : t.matId;                                      // gbuffer.cu:29-31
+        f3 albedo = m.baseColor;
         float depth = length(o - pos);                                               // gbuffer.cu:44
         int lx, ly;
         rasterCoord(lastCam, pos, lx, ly);                                           // gbuffer.cu:49-55
@@ -676,7 +761,8 @@ RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& last
     } else {
         f.geom[0][li] = make_float4(0.f, 0.f, 0.f, 1.f);                             // gbuffer.cu:57-72
         f.matId[0][li] = -1;
-        f.albedoMotion[li] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        f3 albedo = s.envTex >= 0 ? envLookup(s, d) : mk3(0.f);                      // gbuffer.cu:58-63
+        f.albedoMotion[li] = make_float4(albedo.x, albedo.y, albedo.z, __int_as_float(0));
     }
 }
 
@@ -703,12 +789,34 @@ __global__ void __launch_bounds__(RS_BLOCK) k_gbuffer_fix(const __grid_constant_
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.fallbackRays + 0, n);
 }
 
+// scene.h:364-375: texel of the environment map drawn from envMapSampler -> radiance and direction of its centre
+RS_D int envSample(const DevScene& s, float r1, float r2, f3& radiance, f3& wi) {
+    int len = s.envLen;
+    int pass = min(__float2int_rz((float)len * r1), len - 1);                       // sampler.h:204
+    float2 e = __ldg(s.envAlias + pass);
+    int pix = (r2 < e.x) ? pass : __float_as_int(e.y);
+    int4 info = __ldg(s.texInfo + s.envTex);
+    float4 c = __ldg(s.texData + info.z + pix), w = __ldg(s.envDir + pix);
+    radiance = mk3(c.x, c.y, c.z);
+    wi = mk3(w.x, w.y, w.z);
+    return pix;
+}
+RS_D float envPdf(const DevScene& s, f3 radiance) {                                  // scene.h:373-374 (PiInv = 1.f / Pi)
+    int4 info = __ldg(s.texInfo + s.envTex);
+    return luminance(radiance) * s.sumLightPowerInv * (float)info.x * (float)info.y * 1.f / RS_PI * 1.f / RS_PI * .5f;
+}
 // scene.h:394-425 on the packed light record; returns the pdf (<= 0: invalid), fills wi / dist / lightId
 RS_D float sampleLight(const DevScene& s, f3 pos, float r0, float r1, float r2, float r3, f3& Li, f3& wi, float& dist, int& lightId) {
     int len = s.numLights;
     int pass = min(__float2int_rz((float)len * r0), len - 1);                       // sampler.h:204
     float2 e = __ldg(s.alias + pass);
     lightId = (r1 < e.x) ? pass : __float_as_int(e.y);
+    if (s.envTex >= 0 && lightId == len - 1) {                                       // scene.h:400-403
+        dist = 1e10f;
+        int pix = envSample(s, r2, r3, Li, wi);
+        lightId = len - 1 + pix;
+        return envPdf(s, Li);
+    }
     const float4* lp = s.lights + 4 * (size_t)lightId;
     float4 a = __ldg(lp), b = __ldg(lp + 1), c = __ldg(lp + 2), d4 = __ldg(lp + 3);
     f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(a.w, b.x, b.y), v2 = mk3(b.z, b.w, c.x);
@@ -771,14 +879,15 @@ RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, 
         pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;
         nrm = normalize(nb * h.bx + nc * h.by + na * bz);
         matId = t.matId;
-        const RstrMaterial* m = s.materials + matId;
-        type = __ldg(&m->type);
-        metallic = __ldg(&m->metallic);
-        roughness = __ldg(&m->roughness);
+        Surf m = texturedMaterial(s, matId, h.prim, h.bx, h.by, nrm);                // restir.cu:140
+        type = m.type;
+        metallic = m.metallic;
+        roughness = m.roughness;
         status = type == 4 ? 1 : 2;
     }
     if (status != 2) {                                                               // restir.cu:133-146 -> WriteRadiance
-        writeRadiance(f, li, status == 1 ? mk3(1.f) : mk3(0.f), iter);
+        f3 direct = status == 1 ? mk3(1.f) : (s.envTex >= 0 ? envLookup(s, d) : mk3(0.f));
+        writeRadiance(f, li, direct, iter);
         if (SPATIAL) {
             float4* q = (float4*)(f.hit + li);
             q[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
@@ -827,6 +936,7 @@ RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, 
         float4* q = (float4*)(f.hit + li);
         q[0] = make_float4(nrm.x, nrm.y, nrm.z, __int_as_float(matId));
         q[1] = make_float4(wo.x, wo.y, wo.z, __uint_as_float(rng.x));
+        if (f.hitMR) f.hitMR[li] = make_float2(metallic, roughness);
     } else {
         writeRadiance(f, li, shadeReservoir(s, R, type, metallic, roughness, nrm, wo), iter);
     }
@@ -919,7 +1029,10 @@ __global__ void __launch_bounds__(128) k_restir_b(const __grid_constant__ DevSce
     if (src != f.resvTemp) storeResv(f.resvTemp + li, published);
     f3 nrm = mk3(h0.x, h0.y, h0.z), wo = mk3(h1.x, h1.y, h1.z);
     const RstrMaterial* m = s.materials + matId;
-    writeRadiance(f, li, shadeReservoir(s, R, __ldg(&m->type), __ldg(&m->metallic), __ldg(&m->roughness), nrm, wo), iter);
+    float metallic, roughness;
+    if (f.hitMR) { float2 mr = f.hitMR[li]; metallic = mr.x; roughness = mr.y; }
+    else { metallic = __ldg(&m->metallic); roughness = __ldg(&m->roughness); }
+    writeRadiance(f, li, shadeReservoir(s, R, __ldg(&m->type), metallic, roughness, nrm, wo), iter);
 }
 
 // pathtrace.cu:279-328 with scene.h:427-459 (occlusion test BEFORE the facing test)
@@ -937,19 +1050,21 @@ RS_D bool ptdirectPixel(const DevScene& s, const FrameDev& f, const CamDev& cam,
     Hit h;
     if (!traceClosest<EXACT>(s, ray, h, stack)) return false;
     f3 direct = mk3(0.f);
-    if (h.prim >= 0) {
+    if (h.prim < 0) {
+        if (s.envTex >= 0) direct = envLookup(s, d);                                 // pathtrace.cu:295-300
+    } else {
         Tri t = loadTri(s, h.prim);
-        const RstrMaterial* m = s.materials + t.matId;
-        int type = __ldg(&m->type);
-        f3 baseColor = mk3(__ldg(&m->baseColor[0]), __ldg(&m->baseColor[1]), __ldg(&m->baseColor[2]));
+        const float4* np = s.triNorm + 3 * (size_t)h.prim;
+        float4 na4 = __ldg(np), nb4 = __ldg(np + 1), nc4 = __ldg(np + 2);
+        f3 na = mk3(na4.x, na4.y, na4.z), nb = mk3(na4.w, nb4.x, nb4.y), nc = mk3(nb4.z, nb4.w, nc4.x);
+        float bz = 1.f - h.bx - h.by;
+        f3 pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;
+        f3 nrm = normalize(nb * h.bx + nc * h.by + na * bz);
+        Surf m = texturedMaterial(s, t.matId, h.prim, h.bx, h.by, nrm);              // pathtrace.cu:302
+        const int type = m.type;
+        const f3 baseColor = m.baseColor;
         if (type == 4) direct = baseColor;
         else if (type != 2 && s.numLights > 0) {
-            const float4* np = s.triNorm + 3 * (size_t)h.prim;
-            float4 na4 = __ldg(np), nb4 = __ldg(np + 1), nc4 = __ldg(np + 2);
-            f3 na = mk3(na4.x, na4.y, na4.z), nb = mk3(na4.w, nb4.x, nb4.y), nc = mk3(nb4.z, nb4.w, nc4.x);
-            float bz = 1.f - h.bx - h.by;
-            f3 pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;
-            f3 nrm = normalize(nb * h.bx + nc * h.by + na * bz);
             f3 wo = -d;
             if (dot(nrm, wo) < 0.f) nrm = -nrm;
             float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
@@ -957,24 +1072,34 @@ RS_D bool ptdirectPixel(const DevScene& s, const FrameDev& f, const CamDev& cam,
             int pass = min(__float2int_rz((float)len * c0), len - 1);
             float2 e = __ldg(s.alias + pass);
             int lightId = (c1 < e.x) ? pass : __float_as_int(e.y);
-            const float4* lp = s.lights + 4 * (size_t)lightId;
-            float4 a = __ldg(lp), b = __ldg(lp + 1), c = __ldg(lp + 2), d4 = __ldg(lp + 3);
-            f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(a.w, b.x, b.y), v2 = mk3(b.z, b.w, c.x);
-            f3 n = mk3(c.y, c.z, c.w);
-            float sr = sqrtf(c3);
-            float u = 1.f - sr, v = c2 * sr;
-            f3 sampled = v1 * u + v2 * v + v0 * (1.f - u - v);
-            int occ = traceOccluded<EXACT>(s, pos, sampled, stack);
-            if (occ < 0) return false;
-            if (!occ) {
-                f3 pts = sampled - pos;
-                if (!(dot(n, pts) > -1e-6f)) {
-                    f3 Li = mk3(d4.x, d4.y, d4.z);
-                    float len2 = dot(pts, pts);
-                    f3 wi = pts * (1.f / sqrtf(len2));
-                    float pdf = d4.w * len2 / fabsf(dot(n, wi));
-                    if (pdf > 0.f)
-                        direct = Li * materialBSDF(type, __ldg(&m->metallic), __ldg(&m->roughness), baseColor, diffuseTerm(baseColor), nrm, wo, wi) * satDot(nrm, wi) / pdf;
+            if (s.envTex >= 0 && lightId == len - 1) {                               // scene.h:433-435 -> :377-392
+                f3 Li, wi;
+                envSample(s, c2, c3, Li, wi);
+                int occ = traceOccluded<EXACT>(s, pos, pos + wi * 1e6f, stack);
+                if (occ < 0) return false;
+                float pdf = envPdf(s, Li);
+                if (!occ && pdf > 0.f)
+                    direct = Li * materialBSDF(type, m.metallic, m.roughness, baseColor, diffuseTerm(baseColor), nrm, wo, wi) * satDot(nrm, wi) / pdf;
+            } else {
+                const float4* lp = s.lights + 4 * (size_t)lightId;
+                float4 a = __ldg(lp), b = __ldg(lp + 1), c = __ldg(lp + 2), d4 = __ldg(lp + 3);
+                f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(a.w, b.x, b.y), v2 = mk3(b.z, b.w, c.x);
+                f3 n = mk3(c.y, c.z, c.w);
+                float sr = sqrtf(c3);
+                float u = 1.f - sr, v = c2 * sr;
+                f3 sampled = v1 * u + v2 * v + v0 * (1.f - u - v);
+                int occ = traceOccluded<EXACT>(s, pos, sampled, stack);
+                if (occ < 0) return false;
+                if (!occ) {
+                    f3 pts = sampled - pos;
+                    if (!(dot(n, pts) > -1e-6f)) {
+                        f3 Li = mk3(d4.x, d4.y, d4.z);
+                        float len2 = dot(pts, pts);
+                        f3 wi = pts * (1.f / sqrtf(len2));
+                        float pdf = d4.w * len2 / fabsf(dot(n, wi));
+                        if (pdf > 0.f)
+                            direct = Li * materialBSDF(type, m.metallic, m.roughness, baseColor, diffuseTerm(baseColor), nrm, wo, wi) * satDot(nrm, wi) / pdf;
+                    }
                 }
             }
         }

@@ -173,11 +173,19 @@ bool buildHostScene(HostScene& hs, std::string& err) {
         int m = hs.materialIds[p];
         if (m < 0 || m >= (int)hs.materials.size()) { err = "material id out of range"; return false; }
     }
+    const int numTex = (int)hs.textures.size();
+    hs.anyMaps = hs.anyMRMaps = false;
     for (const RstrMaterial& m : hs.materials) {
-        if (m.baseColorMapId != -1 || m.metallicMapId != -1 || m.roughnessMapId != -1 || m.normalMapId != -1) {
-            err = "textured materials are not supported yet (DESIGN.md: out of scope this round)"; return false;
+        const int ids[4] = {m.baseColorMapId, m.metallicMapId, m.roughnessMapId, m.normalMapId};
+        for (int k = 0; k < 4; k++) {
+            if (ids[k] >= numTex || ids[k] < (k == 0 ? -2 : -1)) { err = "material references a texture that does not exist"; return false; }
+            if (ids[k] != -1) hs.anyMaps = true;
         }
+        if (m.metallicMapId > -1 || m.roughnessMapId > -1) hs.anyMRMaps = true;
     }
+    if (hs.envMapTexId >= numTex) { err = "environment map references a texture that does not exist"; return false; }
+    for (const HostTexture& t : hs.textures)
+        if (t.w <= 0 || t.h <= 0 || t.rgb.size() != (size_t)t.w * t.h) { err = "texture has inconsistent size"; return false; }
     // ---- light list (scene.cpp:163-186) + alias table (scene.cpp:154) ----
     hs.lightPrimIds.clear(); hs.lightUnitRadiance.clear(); hs.lightPower.clear();
     for (int p = 0; p < T; p++) {
@@ -193,6 +201,28 @@ bool buildHostScene(HostScene& hs, std::string& err) {
     if (!hs.lightPowerFromFile.empty()) {
         if (hs.lightPowerFromFile.size() != hs.lightPower.size()) { err = "internal: light power list size"; return false; }
         hs.lightPower = hs.lightPowerFromFile;
+    }
+    // ---- environment map sampler (scene.cpp:136-152): one more light, appended last ----
+    hs.envAlias.clear(); hs.envSumAll = 0.f; hs.envDir.clear();
+    if (hs.envMapTexId >= 0) {
+        const HostTexture& env = hs.textures[hs.envMapTexId];
+        std::vector<float> pdf((size_t)env.w * env.h);
+        hs.envDir.resize(pdf.size() * 4);
+        const float PiTwo = 6.2831853071795864769252867665590057683943f;
+        for (int i = 0; i < env.h; i++) {
+            for (int j = 0; j < env.w; j++) {
+                int idx = i * env.w + j;
+                pdf[idx] = luminance(env.rgb[idx]) * sinf((.5f + i) / env.h * RS_PI);           // scene.cpp:144
+                // scene.h:371 wi = toSphere(((.5+x)/W, (.5+y)/H)), mathUtil.h:134-137: depends on the texel only
+                float vx = (.5f + j) / env.w * PiTwo, vy = (.5f + i) / env.h * RS_PI;
+                hs.envDir[4 * idx + 0] = cosf(vx) * sinf(vy);
+                hs.envDir[4 * idx + 1] = cosf(vy);
+                hs.envDir[4 * idx + 2] = sinf(vx) * sinf(vy);
+                hs.envDir[4 * idx + 3] = 0.f;
+            }
+        }
+        buildAliasTable(pdf, hs.envAlias, hs.envSumAll);
+        hs.lightPower.push_back(hs.envSumAll);                                                   // scene.cpp:151
     }
     hs.alias.clear(); hs.sumAll = 0.f; hs.sumLightPowerInv = 0.f;
     if (!hs.lightPower.empty()) {
@@ -225,6 +255,20 @@ bool buildHostScene(HostScene& hs, std::string& err) {
         TriNorm& nn = hs.triNorm[p];
         memcpy(nn.n0, &hs.normals[3 * p], 36);
         nn.pad[0] = nn.pad[1] = nn.pad[2] = 0.f;
+    }
+    // ---- textures as float4 texels; per-triangle texture coordinates ----
+    hs.texData.clear(); hs.texInfo.clear(); hs.triUV.clear();
+    for (const HostTexture& t : hs.textures) {
+        int first = (int)(hs.texData.size() / 4);
+        hs.texInfo.insert(hs.texInfo.end(), {t.w, t.h, first, 0});
+        for (const f3& c : t.rgb) hs.texData.insert(hs.texData.end(), {c.x, c.y, c.z, 0.f});
+    }
+    if (hs.anyMaps) {
+        hs.triUV.resize(T);
+        for (int p = 0; p < T; p++) {
+            memcpy(hs.triUV[p].t0, &hs.texcoords[6 * (size_t)p], 24);
+            hs.triUV[p].pad[0] = hs.triUV[p].pad[1] = 0.f;
+        }
     }
     buildFastBVH(hs);
     const int L = (int)hs.lightPrimIds.size();

@@ -64,6 +64,17 @@ struct MTNode {               // bvh.h:163-171
     int prim, box, miss;
 };
 
+struct HostTexture {          // image.h:7-39: width x height linear-RGB texels
+    int w = 0, h = 0;
+    std::vector<f3> rgb;
+};
+
+struct alignas(16) TriUV {    // 32 B: texture coordinates of the three vertices (scene.h:144-150), read only for mapped materials
+    float t0[2], t1[2], t2[2];
+    float pad[2];
+};
+static_assert(sizeof(TriUV) == 32, "TriUV");
+
 struct HostScene {
     int T = 0;
     std::vector<f3> vertices, normals;
@@ -83,8 +94,19 @@ struct HostScene {
     // area comes from an unrelated triangle of the first instances.  The alias table and sumLightPowerInv inherit that;
     // the per-candidate area in scene.h:419 does not.  Reproduced verbatim for drop-in parity.
     std::vector<float> lightPowerFromFile;
-    std::vector<AliasEntry> alias;
+    std::vector<AliasEntry> alias;         // lightSampler: emissive triangles, then the environment map (if any) as the last entry
     float sumAll = 0.f, sumLightPowerInv = 0.f;
+    // textures + environment map (scene.cpp:136-152, 362-375)
+    std::vector<HostTexture> textures;
+    int envMapTexId = -1;
+    std::vector<AliasEntry> envAlias;      // envMapSampler over the W*H texels
+    float envSumAll = 0.f;
+    bool anyMaps = false;                  // some material references a texture / the procedural pattern
+    bool anyMRMaps = false;                // ... a metallic or roughness map (phase B then needs the per-pixel values)
+    std::vector<float> texData;            // all textures as float4 texels (rgb + pad), concatenated
+    std::vector<int> texInfo;              // per texture {w, h, first texel, 0}
+    std::vector<float> envDir;             // float4 per environment texel: Math::toSphere of its centre (scene.h:371), evaluated on the host
+    std::vector<TriUV> triUV;              // original primitive order (empty unless anyMaps)
 
     // packed device layouts
     Box rootBox;

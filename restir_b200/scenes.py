@@ -70,6 +70,10 @@ class SceneData:
     resolution: tuple = (800, 800)
     focal_dist: float = 1.0
     lens_radius: float = 0.0
+    # textures referenced by the materials' map ids ((H, W, 3) f32 linear RGB each, image.h:7-39) and the
+    # environment map (index into textures, -1 = none; scene.cpp:122-128)
+    textures: list = field(default_factory=list)
+    env_map: int = -1
 
     @property
     def num_tris(self) -> int:
@@ -168,6 +172,65 @@ def cornell_box(resolution=(800, 800), metal_tall_box: bool = False) -> SceneDat
 
 # ----------------------------------------------------------------------------- procedural many-light scene
 _GOLD = np.uint64(0x9E3779B97F4A7C15)
+
+
+def synth_textures(seed: int = 7):
+    """Five small deterministic textures: base colour 16x8, metallic 4x4, roughness 5x3, normal map 8x8 and an
+    environment map 16x8 with a bright 'sun' texel (values from the counter-based splitmix64 stream)."""
+    def u(n, stream):
+        return np.minimum(_splitmix64(seed, n, stream), 0.999999).astype(np.float32)
+
+    base = (0.1 + 0.8 * u(8 * 16 * 3, 101)).reshape(8, 16, 3)
+    yy, xx = np.mgrid[0:8, 0:16]
+    base = (base * np.where(((xx // 2 + yy // 2) & 1)[..., None] == 0, 1.0, 0.35)).astype(np.float32)
+    metallic = np.repeat(u(16, 102).reshape(4, 4, 1), 3, axis=2).astype(np.float32)
+    roughness = np.repeat((0.2 + 0.8 * u(15, 103)).reshape(3, 5, 1), 3, axis=2).astype(np.float32)
+    nm = u(8 * 8 * 3, 104).reshape(8, 8, 3)
+    normal = np.stack([0.5 + 0.3 * (nm[..., 0] - 0.5), 0.5 + 0.3 * (nm[..., 1] - 0.5), 0.8 + 0.2 * nm[..., 2]], axis=2).astype(np.float32)
+    env = (0.05 + 0.6 * u(8 * 16 * 3, 105)).reshape(8, 16, 3).astype(np.float32)
+    env[4:, :, :] *= np.float32(0.2)          # dim below the horizon
+    env[1, 5] = (40.0, 36.0, 30.0)            # sun
+    env[2, 11] = (3.0, 4.0, 6.0)
+    return [np.ascontiguousarray(t, np.float32) for t in (base, metallic, roughness, normal, env)]
+
+
+def with_textures(sd: SceneData, seed: int = 7, env: bool = True, uv_scale: float = 1.7) -> SceneData:
+    """Copy of ``sd`` exercising every branch of getTexturedMaterialAndSurface (scene.h:78-99): planar texture
+    coordinates (negative and > 1 values included), and the non-emissive materials cycled through base-colour map /
+    procedural pattern / metallic+roughness maps (MetallicWorkflow) / normal map / base-colour + normal map; with
+    ``env`` also an environment map as the last light (scene.cpp:136-152)."""
+    import copy
+
+    out = copy.copy(sd)
+    out.name = sd.name + "_textured"
+    v = np.asarray(sd.vertices, np.float32)
+    a = np.array([0.7, 0.1, 0.3], np.float32) * np.float32(uv_scale)
+    b = np.array([-0.2, 0.8, 0.45], np.float32) * np.float32(uv_scale)
+    out.texcoords = np.stack([(v * a).sum(1, dtype=np.float32) - np.float32(0.6), (v * b).sum(1, dtype=np.float32) + np.float32(0.25)], axis=1).astype(np.float32)
+    out.textures = synth_textures(seed)
+    out.env_map = 4 if env else -1
+    mats = sd.materials.copy()
+    k = 0
+    for i in range(len(mats)):
+        if mats[i]["type"] in (LIGHT, DIELECTRIC):
+            continue
+        mode = k % 5
+        k += 1
+        if mode == 0:
+            mats[i]["baseColorMapId"] = 0
+        elif mode == 1:
+            mats[i]["baseColorMapId"] = -2
+        elif mode == 2:
+            mats[i]["type"] = METALLIC_WORKFLOW
+            mats[i]["metallicMapId"] = 1
+            mats[i]["roughnessMapId"] = 2
+        elif mode == 3:
+            mats[i]["normalMapId"] = 3
+        else:
+            mats[i]["baseColorMapId"] = 0
+            mats[i]["normalMapId"] = 3
+    out.materials = mats
+    return out
 
 
 def _splitmix64(seed: int, n: int, stream: int) -> np.ndarray:

@@ -21,8 +21,39 @@ from oracle.oracle import Oracle
 from restir_b200 import scenes
 
 
+def textured(ref):
+    """6. textures, procedural pattern, normal / metallic / roughness maps, environment map"""
+    from oracle.oracle import make_camera
+    d = {}
+    for name, sd in helpers.textured_scenes().items():
+        so = ref.scene(sd)
+        d[name + "_alias"] = np.frombuffer(so.alias_table().tobytes(), np.uint8)
+        d[name + "_env_alias"] = np.frombuffer(so.env_alias()[0].tobytes(), np.uint8)
+        d[name + "_sum_power"] = so.sum_light_power()
+        W, H = sd.resolution
+        fo = so.frame(W, H)
+        cam = make_camera(sd)
+        ref.lib.orc_camera_update(C.byref(cam))
+        for it in range(2):
+            fo.pathtrace_direct(cam, 100 + it, it)
+        d[name + "_ptdirect"] = fo.buffer("radiance")
+        so.close()
+        for mode, reuse, radius in (("ris", 0, 5.0), ("st_r30", 3, 30.0)):
+            frames = helpers.run_oracle(ref, sd, 3, reuse, radius=radius)
+            for f, bufs in enumerate(frames):
+                for n, a in bufs.items():
+                    if n == "reservoir_temp" and not (reuse & 2):
+                        continue
+                    d["%s_%s_f%d_%s" % (name, mode, f, n)] = a.view(np.uint8).reshape(a.shape[0], -1) if a.dtype.fields else a
+    np.savez_compressed(os.path.join(HERE, "frames_textured.npz"), **d)
+
+
 def main():
     ref = Oracle("reference")
+    if "--only-textured" in sys.argv:
+        textured(ref)
+        return
+    textured(ref)
     # 1. RNG, alias known answers
     rng = {"l%d_i%d" % (l, i): ref.rng_draws(l, i, 8) for l, i in ((7, 12345), (0, 0), (59, 2073599), (1023, 8294399))}
     alias, total = ref.alias_build([1, 2, 3, 10])

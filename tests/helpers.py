@@ -37,6 +37,15 @@ def test_scenes():
     }
 
 
+def textured_scenes():
+    """Small cases with every texture branch of scene.h:78-99 and an environment map (scene.cpp:136-152)."""
+    return {
+        "cornell_tex": scenes.with_textures(scenes.cornell_box((48, 36)), env=True),
+        "gen2000_tex": scenes.with_textures(scenes.procedural(1, 2000, 100, (48, 36)), env=True),
+        "cornell_tex_noenv": scenes.with_textures(scenes.cornell_box((48, 36), metal_tall_box=True), env=False),
+    }
+
+
 def run_oracle(orc, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=ALL_BUFS, light_index=False, passes=1):
     """Returns a list (per frame) of {buffer name: array}."""
     W, H = sd.resolution

@@ -304,3 +304,56 @@ def test_pipelined_host_call_matches_synchronous_call(gpu):
     for o in outs + [ref]:
         gpu.pinned_free(o)
     a.close(); b.close(); sc.close()
+
+
+TEX_TOL = 1e-4      # sinf (procedural pattern, scene.h:73-74) and atan2f (environment lookup, mathUtil.h:139-144) are
+                    # libdevice on the GPU and glibc in the oracle: albedo / radiance of those pixels agree to 1e-4 relative
+
+
+@pytest.mark.parametrize("name", ["cornell_tex", "gen2000_tex", "cornell_tex_noenv"])
+def test_textured_scenes(gpu, port_oracle, name):
+    """texture maps, procedural base colour, normal maps and the environment map, in both traversal
+    modes.  Everything discrete (material id, motion, which light / environment texel every reservoir holds, M) and
+    every fp32 value that does not pass through sinf / atan2f (normal-mapped normals, depth, reservoir wi / dist /
+    weight) is bit-exact against the oracle and against the reference-generated fixture."""
+    sd = helpers.textured_scenes()[name]
+    g = np.load(os.path.join(G, "frames_textured.npz"))
+    for mode, reuse, radius in (("ris", 0, 5.0), ("st_r30", 3, 30.0)):
+        want = helpers.run_oracle(port_oracle, sd, 3, reuse, radius=radius, light_index=True)
+        for exact in (False, True):
+            got, miss = helpers.run_gpu(gpu, sd, 3, reuse, radius=radius, light_index=True, exact=exact)
+            assert miss == 0
+            for f in range(3):
+                for n in want[f]:
+                    key = "%s_%s_f%d_%s" % (name, mode, f, n)
+                    if n in ("albedo", "radiance"):
+                        a, b = got[f][n].astype(np.float64), want[f][n].astype(np.float64)
+                        assert np.all(np.abs(a - b) <= TEX_TOL * np.abs(b) + 1e-9), (name, mode, f, n)
+                        if key in g.files:
+                            assert np.all(np.abs(a - g[key]) <= TEX_TOL * np.abs(g[key]) + 1e-9), key
+                    else:
+                        assert helpers.mismatches(got[f][n], want[f][n]) == 0, (name, mode, exact, f, n)
+                        if key in g.files:
+                            assert helpers.mismatches(got[f][n], g[key]) == 0, key
+    # PTDirect
+    sc = gpu.Scene.from_arrays(sd)
+    fr = sc.frame(*sd.resolution)
+    cam = gpu.Camera.from_scene(sd)
+    for it in range(2):
+        fr.pathtrace_direct(cam, 100 + it, it)
+    a, b = fr.read("radiance").astype(np.float64), g[name + "_ptdirect"].astype(np.float64)
+    assert np.all(np.abs(a - b) <= TEX_TOL * np.abs(b) + 1e-9)
+    fr.close(); sc.close()
+
+
+def test_textured_large_scene_fast_equals_exact(gpu):
+    """Size-independent property at 1080p: with textures + environment map on the 200k-triangle scene the traced tree
+    and the reference-order walk give identical frames (same libdevice on both sides: bit-exact everywhere)."""
+    sd = scenes.with_textures(scenes.procedural(1, 200000, 10000, (1920, 1080)), env=True)
+    sc = gpu.Scene.from_arrays(sd)
+    fast, _ = helpers.run_gpu(gpu, sd, 3, 3, radius=30.0, light_index=True, scene=sc, exact=False)
+    exact, _ = helpers.run_gpu(gpu, sd, 3, 3, radius=30.0, light_index=True, scene=sc, exact=True)
+    helpers.assert_frames_equal(fast, exact, "textured fast vs exact")
+    L = sc.info.numLights
+    assert (fast[2]["light_index"] >= L - 1).sum() > 1000       # the environment map is being sampled and kept
+    sc.close()

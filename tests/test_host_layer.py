@@ -138,3 +138,29 @@ def test_cpp_host_example_links_against_the_c_abi():
     rb.lib()
     exe = _build_cpp_example(tempfile.mkdtemp())
     assert os.path.exists(exe)
+
+
+@pytest.mark.parametrize("name", ["cornell_tex", "gen2000_tex"])
+def test_textured_scene_host_tables(name):
+    """Environment map: envMapSampler over the texels and the light sampler with the map appended as its last entry
+    (scene.cpp:136-157), against the reference-generated fixture."""
+    sd = helpers.textured_scenes()[name]
+    g = np.load(os.path.join(helpers.GOLDEN, "frames_textured.npz"))
+    sc = rb.Scene.from_arrays(sd)
+    assert sc.info.numLights == sc.info.numEmissiveTris + 1 and (sc.info.envWidth, sc.info.envHeight) == (16, 8)
+    assert sc.info.numTextures == 5
+    assert np.array_equal(np.frombuffer(sc.read("alias").tobytes(), np.uint8), g[name + "_alias"])
+    assert np.array_equal(np.frombuffer(sc.read("env_alias").tobytes(), np.uint8), g[name + "_env_alias"])
+    assert sc.info.sumLightPower == float(g[name + "_sum_power"])
+    sc.close()
+
+
+def test_texture_ids_are_validated():
+    sd = helpers.textured_scenes()["cornell_tex"]
+    sd.materials = sd.materials.copy()
+    sd.materials[0]["normalMapId"] = 9
+    with pytest.raises(rb.RestirError):
+        rb.Scene.from_arrays(sd)
+    sd.materials[0]["normalMapId"] = -2           # the procedural id is only valid for the base colour (scene.h:80-97)
+    with pytest.raises(rb.RestirError):
+        rb.Scene.from_arrays(sd)

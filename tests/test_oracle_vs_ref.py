@@ -55,3 +55,14 @@ def test_probe_rays(port_oracle, ref_oracle):
             pa, oa, ma = a.intersect(o, d)
             pb, ob, mb = b.intersect(o, d)
             assert pa == pb
+
+
+@pytest.mark.parametrize("name", ["cornell_tex", "gen2000_tex"])
+def test_textured_port_equals_reference(port_oracle, ref_oracle, name):
+    """Texture / environment-map branches: restatement == the reference's own functions at a larger size than the
+    committed fixture."""
+    import dataclasses
+    sd = dataclasses.replace(helpers.textured_scenes()[name], resolution=(128, 96))
+    a = helpers.run_oracle(port_oracle, sd, 3, 3, radius=30.0)
+    b = helpers.run_oracle(ref_oracle, sd, 3, 3, radius=30.0)
+    helpers.assert_frames_equal(a, b, name)
