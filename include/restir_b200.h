@@ -124,7 +124,8 @@ enum {
     RSTR_SCENE_TEXCOORDS = 12,     /* 3T x 8 B */
     RSTR_SCENE_MATERIAL_IDS = 13,  /* T x i32 */
     RSTR_SCENE_MATERIALS = 14,     /* numMaterials x 44 B */
-    RSTR_SCENE_ENV_ALIAS = 15      /* envW*envH x {f32 prob, i32 failId}  envMapSampler, scene.cpp:147 */
+    RSTR_SCENE_ENV_ALIAS = 15,     /* envW*envH x {f32 prob, i32 failId}  envMapSampler, scene.cpp:147 */
+    RSTR_SCENE_TEXTURE0 = 32       /* +i: texture i, width x height x 12 B (size from rstr_scene_texture_info)  Scene::textures */
 };
 
 /* frame buffers readable through rstr_frame_read (reference layouts, full image rows of this frame/strip) */
@@ -162,6 +163,8 @@ int rstr_scene_set_traversal(RstrScene*, int mode);
 /* pixels recomputed with the reference-order walk since the scene was created / last reset (instrumentation);
  * count[4] = {G-buffer pixels, ReSTIR phase-A pixels, PTDirect pixels, unused} */
 int rstr_scene_fallback_rays(RstrScene*, unsigned long long* count4, int reset);
+/* size of texture i and whether it is the environment map (Scene::textures / envMapTexId, scene.h:487-491) */
+int rstr_scene_texture_info(const RstrScene*, int index, int* width, int* height, int* isEnvMap);
 int rstr_scene_read(const RstrScene*, int which, void* host, size_t bytes);
 
 /* replaces Camera::update() (sceneStructs.h:88-102) */
@@ -191,6 +194,15 @@ int rstr_pathtrace_direct(RstrFrame*, const RstrCamera*, int looper, int iter);
 /* replaces copyImageToPBO(devPBO, devImage, w, h, toneMapping, scale) (pathtrace.cu:108-113);
  * toneMapping: 0 none, 1 filmic, 2 ACES (common.h:18-22) */
 int rstr_tonemap(RstrFrame*, int toneMapping, float scale);
+/* saveImage (main.cpp:105-144): tone-map + gamma the radiance image, mirror it horizontally (main.cpp:126) and write an
+ * 8-bit RGB PNG (Image::savePNG, image.cpp:41-57).  `path` is the complete file name. */
+int rstr_frame_save_png(RstrFrame*, const char* path, int toneMapping);
+/* Image::Image(filename) (image.cpp:16-33): PNG or Radiance .hdr -> width x height x 3 f32, linear (8-bit samples / 255,
+ * stbi_ldr_to_hdr_gamma(1), scene.cpp:97); flipY = stbi_set_flip_vertically_on_load (true for material textures, false for
+ * the environment map, scene.cpp:98,124).  Call with rgbOut = NULL to get the size.  Host only, no GPU needed. */
+int rstr_image_load(const char* path, int flipY, int* width, int* height, float* rgbOut, size_t capacityBytes);
+/* Image::savePNG (image.cpp:41-57): width x height x 3 bytes, top row first.  Host only. */
+int rstr_image_write_png(const char* path, int width, int height, const unsigned char* rgb);
 
 /* One whole frame of runCuda (main.cpp:146-185) from HOST inputs to a HOST result:
  * gbuffer_render + restir_direct (or pathtrace_direct when params == NULL) + tonemap + gbuffer_update,

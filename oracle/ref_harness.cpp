@@ -29,6 +29,8 @@
 #include <omp.h>
 #endif
 
+#include <stb_image.h>
+
 #include "restir_oracle.h"
 
 using DirectReservoir = Reservoir<DirectLiSample>;
@@ -178,6 +180,22 @@ const void* orc_scene_env_alias(const OrcScene* s, int* lengthOut, float* sumAll
     return s->dev.envMapSampler.devBinomDistribs;
 }
 
+/* Image::Image(filename) (image.cpp:16-33) = stbi_loadf(..., 3) under the loader state Scene::Scene sets (scene.cpp:97-98,124) */
+int ref_image_load(const char* path, int flipY, int* w, int* h, float* out, size_t capacityBytes) {
+    stbi_ldr_to_hdr_gamma(1.f);
+    stbi_set_flip_vertically_on_load(flipY);
+    int n;
+    float* probe = stbi_loadf(path, w, h, &n, 3);      /* Image's ctor would `throw;` (terminate) on failure */
+    if (!probe) return -1;
+    stbi_image_free(probe);
+    Image img(path);
+    if (out) {
+        if (capacityBytes < img.byteSize()) return -2;
+        memcpy(out, img.data(), img.byteSize());
+    }
+    return 0;
+}
+
 /* the reference's own parser + flattening + upload (over fake cudart) */
 OrcScene* ref_scene_load_file(const char* path) {
     OrcScene* sc = new OrcScene;
@@ -189,6 +207,11 @@ OrcScene* ref_scene_load_file(const char* path) {
 }
 void ref_scene_camera(const OrcScene* sc, OrcCamera* out) { memcpy(out, &sc->fileScene->camera, sizeof(OrcCamera)); }
 int ref_scene_num_tris(const OrcScene* sc) { return sc->T; }
+int ref_scene_texture_info(const OrcScene* sc, int i, int* w, int* h, int* isEnv) {
+    if (!sc->fileScene || i < 0 || i >= (int)sc->fileScene->textures.size()) return -1;
+    *w = sc->fileScene->textures[i]->width(); *h = sc->fileScene->textures[i]->height(); *isEnv = sc->fileScene->envMapTexId == i;
+    return (int)sc->fileScene->textures.size();
+}
 int ref_scene_num_materials(const OrcScene* sc) { return sc->fileScene ? (int)sc->fileScene->materials.size() : (int)sc->materials.size(); }
 const void* ref_scene_array(const OrcScene* sc, int which) {
     switch (which) {
@@ -198,6 +221,7 @@ const void* ref_scene_array(const OrcScene* sc, int which) {
     case 3: return sc->dev.materialIds;
     case 4: return sc->dev.materials;
     }
+    if (which >= 32 && sc->fileScene && which - 32 < (int)sc->fileScene->textures.size()) return sc->fileScene->textures[which - 32]->data();
     return nullptr;
 }
 

@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
     L.rstr_scene_destroy.argtypes = [vp]
     L.rstr_scene_info.argtypes = [vp, C.POINTER(RstrSceneInfo)]
     L.rstr_scene_read.argtypes = [vp, ip, vp, C.c_size_t]
+    L.rstr_scene_texture_info.argtypes = [vp, ip, vp, vp, vp]
     L.rstr_scene_set_traversal.argtypes = [vp, ip]
     L.rstr_scene_fallback_rays.argtypes = [vp, C.POINTER(C.c_ulonglong), ip]
     L.rstr_camera_update.argtypes = [C.POINTER(RstrCamera)]
@@ -143,6 +144,9 @@ def lib() -> C.CDLL:
     L.rstr_restir_phase_b.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
     L.rstr_pathtrace_direct.argtypes = [vp, C.POINTER(RstrCamera), ip, ip]
     L.rstr_tonemap.argtypes = [vp, ip, fp]
+    L.rstr_frame_save_png.argtypes = [vp, C.c_char_p, ip]
+    L.rstr_image_load.argtypes = [C.c_char_p, ip, vp, vp, vp, C.c_size_t]
+    L.rstr_image_write_png.argtypes = [C.c_char_p, ip, ip, vp]
     L.rstr_render_frame_host.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip, vp, C.c_size_t]
     L.rstr_render_frame_host_async.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip, vp, C.c_size_t, ip]
     L.rstr_frame_wait_host.argtypes = [vp, ip]
@@ -286,6 +290,14 @@ class Scene:
         _check(lib().rstr_scene_read(self.h, which, out.ctypes.data, out.nbytes))
         return out
 
+    def texture(self, index: int):
+        """(array (H, W, 3) f32, is_env_map) of texture ``index`` (Scene::textures)."""
+        w, h, e = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(lib().rstr_scene_texture_info(self.h, index, C.byref(w), C.byref(h), C.byref(e)))
+        out = np.zeros((h.value, w.value, 3), np.float32)
+        _check(lib().rstr_scene_read(self.h, 32 + index, out.ctypes.data, out.nbytes))
+        return out, bool(e.value)
+
     def frame(self, width: int, height: int, rows=None, halo: int = 0) -> "Frame":
         return Frame(self, width, height, rows, halo)
 
@@ -334,6 +346,9 @@ class Frame:
 
     def tonemap(self, mode: int = TONEMAP_ACES, scale: float = 1.0) -> None:  # copyImageToPBO
         _check(lib().rstr_tonemap(self.f, mode, scale))
+
+    def save_png(self, path: str, tonemap: int = TONEMAP_ACES) -> None:        # saveImage (main.cpp:105-144)
+        _check(lib().rstr_frame_save_png(self.f, path.encode(), tonemap))
 
     def render_frame_host(self, cam, params, looper: int, it: int = 0, tonemap: int = TONEMAP_ACES, out=None) -> None:
         """One runCuda() frame; ``out`` is a host uint8 buffer of npix*4 bytes receiving the LDR image."""
@@ -400,6 +415,21 @@ class Frame:
             out = np.zeros((P,), RESERVOIR_DTYPE)
         _check(lib().rstr_frame_read(self.f, FRAME_BUFFERS[name], out.ctypes.data, out.nbytes))
         return out
+
+
+def load_image(path: str, flip: bool = True) -> np.ndarray:
+    """Image::Image(filename) (image.cpp:16-33): PNG / Radiance .hdr -> (H, W, 3) f32; host only."""
+    w, h = C.c_int(0), C.c_int(0)
+    _check(lib().rstr_image_load(path.encode(), 1 if flip else 0, C.addressof(w), C.addressof(h), None, 0))
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    _check(lib().rstr_image_load(path.encode(), 1 if flip else 0, C.addressof(w), C.addressof(h), out.ctypes.data, out.nbytes))
+    return out
+
+
+def write_png(path: str, rgb: np.ndarray) -> None:
+    """Image::savePNG (image.cpp:41-57): (H, W, 3) uint8."""
+    a = np.ascontiguousarray(rgb, np.uint8)
+    _check(lib().rstr_image_write_png(path.encode(), int(a.shape[1]), int(a.shape[0]), a.ctypes.data))
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:

@@ -261,6 +261,14 @@ int rstr_scene_info(const RstrScene* sc, RstrSceneInfo* info) {
     return RSTR_OK;
 }
 
+int rstr_scene_texture_info(const RstrScene* sc, int index, int* width, int* height, int* isEnvMap) {
+    if (!sc || index < 0 || index >= (int)sc->hs.textures.size()) return fail(RSTR_ERR_ARG, "rstr_scene_texture_info: bad argument");
+    if (width) *width = sc->hs.textures[index].w;
+    if (height) *height = sc->hs.textures[index].h;
+    if (isEnvMap) *isEnvMap = sc->hs.envMapTexId == index;
+    return RSTR_OK;
+}
+
 int rstr_scene_read(const RstrScene* sc, int which, void* host, size_t bytes) {
     if (!sc || !host) return fail(RSTR_ERR_ARG, "rstr_scene_read: bad argument");
     const HostScene& hs = sc->hs;
@@ -279,7 +287,9 @@ int rstr_scene_read(const RstrScene* sc, int which, void* host, size_t bytes) {
     case RSTR_SCENE_MATERIALS: src = hs.materials.data(); need = hs.materials.size() * sizeof(RstrMaterial); break;
     case RSTR_SCENE_ENV_ALIAS: src = hs.envAlias.data(); need = hs.envAlias.size() * 8; break;
     default:
-        if (which >= RSTR_SCENE_MTBVH0 && which < RSTR_SCENE_MTBVH0 + 6) {
+        if (which >= RSTR_SCENE_TEXTURE0 && which < RSTR_SCENE_TEXTURE0 + (int)hs.textures.size()) {
+            src = hs.textures[which - RSTR_SCENE_TEXTURE0].rgb.data(); need = hs.textures[which - RSTR_SCENE_TEXTURE0].rgb.size() * 12;
+        } else if (which >= RSTR_SCENE_MTBVH0 && which < RSTR_SCENE_MTBVH0 + 6) {
             exportMTBVH(hs, which - RSTR_SCENE_MTBVH0, mt);
             src = mt.data(); need = mt.size() * sizeof(MTNode);
         } else return fail(RSTR_ERR_ARG, "rstr_scene_read: unknown array");
@@ -480,6 +490,49 @@ int rstr_tonemap(RstrFrame* f, int toneMapping, float scale) {
     stageEnd(f, RSTR_T_TONEMAP);
     g_launches++;
     CU(cudaGetLastError());
+    return RSTR_OK;
+}
+
+// saveImage (main.cpp:105-144): tone-map + gamma, mirror horizontally (img.setPixel(width - 1 - x, y, ...)), 8-bit PNG
+int rstr_frame_save_png(RstrFrame* f, const char* path, int toneMapping) {
+    if (!f || !path) return fail(RSTR_ERR_ARG, "rstr_frame_save_png: bad argument");
+    int rc = rstr_tonemap(f, toneMapping, 1.f);
+    if (rc) return rc;
+    const int W = f->W, H = f->row1 - f->row0;
+    std::vector<uchar4> ldr((size_t)W * H);
+    CU(cudaMemcpyAsync(ldr.data(), f->ldr + (size_t)(f->row0 - f->bufRow0) * W, ldr.size() * sizeof(uchar4), cudaMemcpyDeviceToHost, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+    std::vector<unsigned char> rgb((size_t)W * H * 3);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const uchar4 c = ldr[(size_t)y * W + x];
+            unsigned char* o = &rgb[((size_t)y * W + (W - 1 - x)) * 3];
+            o[0] = c.x; o[1] = c.y; o[2] = c.z;
+        }
+    std::string err;
+    if (!writePNG(path, W, H, rgb.data(), err)) return fail(RSTR_ERR_IO, err);
+    return RSTR_OK;
+}
+
+// Image::Image(filename) (image.cpp:16-33).  rgbOut may be NULL to query the size only.
+int rstr_image_load(const char* path, int flipY, int* width, int* height, float* rgbOut, size_t capacityBytes) {
+    if (!path || !width || !height) return fail(RSTR_ERR_ARG, "rstr_image_load: bad argument");
+    HostTexture t;
+    std::string err;
+    if (!loadImageRGB(path, flipY != 0, t, err)) return fail(RSTR_ERR_IO, err);
+    *width = t.w; *height = t.h;
+    if (rgbOut) {
+        if (capacityBytes < t.rgb.size() * 12) return fail(RSTR_ERR_ARG, "rstr_image_load: buffer too small");
+        memcpy(rgbOut, t.rgb.data(), t.rgb.size() * 12);
+    }
+    return RSTR_OK;
+}
+
+// Image::savePNG (image.cpp:41-57)
+int rstr_image_write_png(const char* path, int width, int height, const unsigned char* rgb) {
+    if (!path || width <= 0 || height <= 0 || !rgb) return fail(RSTR_ERR_ARG, "rstr_image_write_png: bad argument");
+    std::string err;
+    if (!writePNG(path, width, height, rgb, err)) return fail(RSTR_ERR_IO, err);
     return RSTR_OK;
 }
 

@@ -1,0 +1,397 @@
+// image_io.cpp -- texture / environment-map files -> linear float RGB, and the PNG writer of the output step.
+//
+// The reference loads every texture with stbi_loadf(file, &w, &h, &n, 3) after stbi_ldr_to_hdr_gamma(1.f)
+// (image.cpp:16-33, scene.cpp:97-98): 8-bit images become v / 255.0f, Radiance .hdr files are decoded from RGBE,
+// rows are flipped vertically for material textures and kept for the environment map (scene.cpp:98, 124-126).
+// stb_image is a third-party single-header dependency of the reference (external/include/stb_image.h, v2.x); this
+// file restates the two formats the scenes use -- PNG (RFC 2083 + RFC 1950/1951 inflate) and Radiance RGBE -- and
+// is pinned against stb itself through oracle/ref_harness.cpp (ref_image_load) on the committed fixtures.
+// Writing: Image::savePNG (image.cpp:41-57) stores 8-bit RGB; here as a valid PNG with stored deflate blocks.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "scene_host.h"
+
+namespace rs {
+
+namespace {
+
+bool readFile(const std::string& path, std::vector<uint8_t>& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    size_t got = out.empty() ? 0 : fread(out.data(), 1, out.size(), f);
+    fclose(f);
+    return got == out.size();
+}
+
+// ------------------------------------------------------------------------------------------------ inflate (RFC 1951)
+struct BitReader {
+    const uint8_t* p; size_t n, pos = 0; uint32_t acc = 0; int cnt = 0; bool bad = false;
+    BitReader(const uint8_t* d, size_t len) : p(d), n(len) {}
+    uint32_t bits(int k) {
+        while (cnt < k) {
+            if (pos >= n) { bad = true; return 0; }
+            acc |= (uint32_t)p[pos++] << cnt; cnt += 8;
+        }
+        uint32_t v = acc & ((k == 32) ? 0xffffffffu : ((1u << k) - 1u));
+        acc >>= k; cnt -= k;
+        return v;
+    }
+    void alignByte() { acc = 0; cnt = 0; }
+};
+
+struct Huffman {           // canonical code, decoded bit by bit through first-code / first-symbol tables
+    uint16_t count[16] = {}, symbol[320] = {};
+    bool build(const uint8_t* lens, int n) {
+        memset(count, 0, sizeof count);
+        for (int i = 0; i < n; i++) count[lens[i]]++;
+        count[0] = 0;
+        uint16_t offs[16]; offs[1] = 0;
+        for (int l = 1; l < 15; l++) offs[l + 1] = offs[l] + count[l];
+        for (int i = 0; i < n; i++) if (lens[i]) symbol[offs[lens[i]]++] = (uint16_t)i;
+        return true;
+    }
+    int decode(BitReader& br) const {
+        int code = 0, first = 0, index = 0;
+        for (int l = 1; l <= 15; l++) {
+            code |= (int)br.bits(1);
+            if (br.bad) return -1;
+            int c = count[l];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+};
+
+bool inflateZlib(const std::vector<uint8_t>& in, std::vector<uint8_t>& out, std::string& err) {
+    if (in.size() < 6 || (in[0] & 0x0f) != 8 || ((in[0] << 8 | in[1]) % 31) != 0 || (in[1] & 0x20)) { err = "bad zlib header"; return false; }
+    BitReader br(in.data() + 2, in.size() - 2);
+    static const uint16_t lenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t lenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t distBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint8_t distExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    static const uint8_t clOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    for (;;) {
+        uint32_t final = br.bits(1), type = br.bits(2);
+        if (br.bad) { err = "truncated deflate stream"; return false; }
+        if (type == 0) {
+            br.alignByte();
+            if (br.pos + 4 > br.n) { err = "truncated stored block"; return false; }
+            uint32_t len = br.p[br.pos] | br.p[br.pos + 1] << 8, nlen = br.p[br.pos + 2] | br.p[br.pos + 3] << 8;
+            br.pos += 4;
+            if ((len ^ 0xffffu) != nlen || br.pos + len > br.n) { err = "bad stored block"; return false; }
+            out.insert(out.end(), br.p + br.pos, br.p + br.pos + len);
+            br.pos += len;
+        } else if (type == 1 || type == 2) {
+            Huffman lit, dist;
+            uint8_t lens[320];
+            if (type == 1) {
+                for (int i = 0; i < 288; i++) lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
+                lit.build(lens, 288);
+                for (int i = 0; i < 30; i++) lens[i] = 5;
+                dist.build(lens, 30);
+            } else {
+                int hlit = br.bits(5) + 257, hdist = br.bits(5) + 1, hclen = br.bits(4) + 4;
+                uint8_t cl[19] = {};
+                for (int i = 0; i < hclen; i++) cl[clOrder[i]] = (uint8_t)br.bits(3);
+                Huffman clh; clh.build(cl, 19);
+                int i = 0;
+                while (i < hlit + hdist) {
+                    int sym = clh.decode(br);
+                    if (sym < 0) { err = "bad code lengths"; return false; }
+                    if (sym < 16) lens[i++] = (uint8_t)sym;
+                    else {
+                        int rep, val = 0;
+                        if (sym == 16) { if (i == 0) { err = "bad repeat"; return false; } val = lens[i - 1]; rep = 3 + br.bits(2); }
+                        else if (sym == 17) rep = 3 + br.bits(3);
+                        else rep = 11 + br.bits(7);
+                        if (i + rep > hlit + hdist) { err = "bad repeat"; return false; }
+                        while (rep--) lens[i++] = (uint8_t)val;
+                    }
+                }
+                uint8_t dl[32];
+                memcpy(dl, lens + hlit, hdist);
+                lit.build(lens, hlit);
+                dist.build(dl, hdist);
+            }
+            for (;;) {
+                int sym = lit.decode(br);
+                if (sym < 0 || br.bad) { err = "bad literal/length code"; return false; }
+                if (sym < 256) out.push_back((uint8_t)sym);
+                else if (sym == 256) break;
+                else {
+                    sym -= 257;
+                    if (sym >= 29) { err = "bad length symbol"; return false; }
+                    int len = lenBase[sym] + (int)br.bits(lenExtra[sym]);
+                    int ds = dist.decode(br);
+                    if (ds < 0 || ds >= 30) { err = "bad distance code"; return false; }
+                    size_t d = distBase[ds] + br.bits(distExtra[ds]);
+                    if (d > out.size()) { err = "distance too far back"; return false; }
+                    size_t from = out.size() - d;
+                    for (int k = 0; k < len; k++) out.push_back(out[from + k]);
+                }
+            }
+        } else { err = "bad deflate block type"; return false; }
+        if (final) break;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ PNG -> 8-bit RGB
+uint32_t be32(const uint8_t* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+
+int paeth(int a, int b, int c) {
+    int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+bool decodePNG(const std::vector<uint8_t>& file, int& W, int& H, std::vector<uint8_t>& rgb, std::string& err) {
+    size_t pos = 8;
+    int depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, palette;
+    bool haveHdr = false;
+    while (pos + 12 <= file.size()) {
+        uint32_t len = be32(&file[pos]);
+        const uint8_t* tag = &file[pos + 4];
+        const uint8_t* data = &file[pos + 8];
+        if (pos + 12 + (size_t)len > file.size()) { err = "truncated PNG chunk"; return false; }
+        if (!memcmp(tag, "IHDR", 4)) {
+            if (len != 13) { err = "bad IHDR"; return false; }
+            W = (int)be32(data); H = (int)be32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
+            haveHdr = true;
+        } else if (!memcmp(tag, "PLTE", 4)) palette.assign(data, data + len);
+        else if (!memcmp(tag, "IDAT", 4)) idat.insert(idat.end(), data, data + len);
+        else if (!memcmp(tag, "IEND", 4)) break;
+        pos += 12 + (size_t)len;
+    }
+    if (!haveHdr || W <= 0 || H <= 0) { err = "PNG without a valid IHDR"; return false; }
+    if (interlace) { err = "interlaced PNGs are not supported"; return false; }
+    int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!channels || !(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4))) || (ctype == 3 && depth == 16)) {
+        err = "unsupported PNG colour type / bit depth"; return false;
+    }
+    std::vector<uint8_t> raw;
+    if (!inflateZlib(idat, raw, err)) { err = "PNG: " + err; return false; }
+    const size_t rowBytes = ((size_t)W * channels * depth + 7) / 8;
+    const int bpp = (channels * depth + 7) / 8;
+    if (raw.size() < (rowBytes + 1) * (size_t)H) { err = "PNG: not enough pixel data"; return false; }
+    std::vector<uint8_t> img(rowBytes * H);
+    for (int y = 0; y < H; y++) {                                   // RFC 2083 section 6: the five row filters
+        const uint8_t* src = &raw[(rowBytes + 1) * y];
+        uint8_t* cur = &img[rowBytes * y];
+        const uint8_t* up = y ? cur - rowBytes : nullptr;
+        int ft = src[0];
+        if (ft > 4) { err = "PNG: bad filter"; return false; }
+        for (size_t i = 0; i < rowBytes; i++) {
+            int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)bpp) ? up[i - bpp] : 0;
+            int pred = ft == 0 ? 0 : ft == 1 ? a : ft == 2 ? b : ft == 3 ? ((a + b) >> 1) : paeth(a, b, c);
+            cur[i] = (uint8_t)(src[1 + i] + pred);
+        }
+    }
+    rgb.resize((size_t)W * H * 3);
+    const int stride = depth == 16 ? 2 : 1;                          // 16-bit samples: the high byte (stb: >> 8)
+    for (int y = 0; y < H; y++) {
+        const uint8_t* row = &img[rowBytes * y];
+        for (int x = 0; x < W; x++) {
+            uint8_t* o = &rgb[((size_t)y * W + x) * 3];
+            if (depth < 8) {
+                int perByte = 8 / depth, shift = (perByte - 1 - x % perByte) * depth;
+                int v = (row[x / perByte] >> shift) & ((1 << depth) - 1);
+                if (ctype == 3) {
+                    if ((size_t)v * 3 + 2 >= palette.size()) { err = "PNG: palette index out of range"; return false; }
+                    o[0] = palette[v * 3]; o[1] = palette[v * 3 + 1]; o[2] = palette[v * 3 + 2];
+                } else {
+                    int g = v * (depth == 1 ? 0xff : depth == 2 ? 0x55 : 0x11);
+                    o[0] = o[1] = o[2] = (uint8_t)g;
+                }
+                continue;
+            }
+            const uint8_t* p = row + (size_t)x * channels * stride;
+            switch (ctype) {
+            case 0: case 4: o[0] = o[1] = o[2] = p[0]; break;
+            case 2: case 6: o[0] = p[0]; o[1] = p[stride]; o[2] = p[2 * stride]; break;
+            case 3:
+                if ((size_t)p[0] * 3 + 2 >= palette.size()) { err = "PNG: palette index out of range"; return false; }
+                o[0] = palette[p[0] * 3]; o[1] = palette[p[0] * 3 + 1]; o[2] = palette[p[0] * 3 + 2];
+                break;
+            }
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ Radiance RGBE
+bool hdrLine(const std::vector<uint8_t>& f, size_t& pos, std::string& line) {
+    line.clear();
+    if (pos >= f.size()) return false;
+    while (pos < f.size() && f[pos] != '\n') line.push_back((char)f[pos++]);
+    if (pos < f.size()) pos++;
+    return true;
+}
+
+void rgbeToFloat(const uint8_t* rgbe, f3& out) {
+    if (rgbe[3] != 0) {
+        float scale = (float)ldexp(1.0f, (int)rgbe[3] - (128 + 8));
+        out = mk3(rgbe[0] * scale, rgbe[1] * scale, rgbe[2] * scale);
+    } else out = mk3(0.f, 0.f, 0.f);
+}
+
+bool decodeHDR(const std::vector<uint8_t>& f, int& W, int& H, std::vector<f3>& px, std::string& err) {
+    size_t pos = 0;
+    std::string line;
+    hdrLine(f, pos, line);
+    if (line != "#?RADIANCE" && line != "#?RGBE") { err = "corrupt HDR header"; return false; }
+    bool valid = false;
+    for (;;) {
+        if (!hdrLine(f, pos, line)) { err = "truncated HDR header"; return false; }
+        if (line.empty()) break;
+        if (line == "FORMAT=32-bit_rle_rgbe") valid = true;
+    }
+    if (!valid) { err = "unsupported HDR format"; return false; }
+    hdrLine(f, pos, line);
+    char* end = nullptr;
+    if (line.compare(0, 3, "-Y ") != 0) { err = "unsupported HDR data layout"; return false; }
+    H = (int)strtol(line.c_str() + 3, &end, 10);
+    while (*end == ' ') end++;
+    if (strncmp(end, "+X ", 3) != 0) { err = "unsupported HDR data layout"; return false; }
+    W = (int)strtol(end + 3, nullptr, 10);
+    if (W <= 0 || H <= 0) { err = "bad HDR size"; return false; }
+    px.resize((size_t)W * H);
+    auto flat = [&](size_t firstPixel) {
+        for (size_t i = firstPixel; i < (size_t)W * H; i++) {
+            if (pos + 4 > f.size()) return false;
+            rgbeToFloat(&f[pos], px[i]); pos += 4;
+        }
+        return true;
+    };
+    if (W < 8 || W >= 32768) {
+        if (!flat(0)) { err = "truncated HDR data"; return false; }
+        return true;
+    }
+    std::vector<uint8_t> scan((size_t)W * 4);
+    for (int j = 0; j < H; j++) {
+        if (pos + 4 > f.size()) { err = "truncated HDR data"; return false; }
+        if (f[pos] != 2 || f[pos + 1] != 2 || (f[pos + 2] & 0x80)) {
+            // not run-length encoded: the file holds flat RGBE pixels (only meaningful on the first row)
+            if (j != 0) { err = "HDR: mixed flat / RLE scanlines"; return false; }
+            if (!flat(0)) { err = "truncated HDR data"; return false; }
+            return true;
+        }
+        int len = f[pos + 2] << 8 | f[pos + 3];
+        pos += 4;
+        if (len != W) { err = "HDR: invalid decoded scanline length"; return false; }
+        for (int k = 0; k < 4; k++) {
+            int i = 0;
+            while (i < W) {
+                if (pos >= f.size()) { err = "truncated HDR data"; return false; }
+                int count = f[pos++];
+                if (count > 128) {
+                    count -= 128;
+                    if (count > W - i || pos >= f.size()) { err = "HDR: bad RLE data"; return false; }
+                    uint8_t v = f[pos++];
+                    for (int z = 0; z < count; z++) scan[(size_t)(i++) * 4 + k] = v;
+                } else {
+                    if (count > W - i || pos + count > f.size()) { err = "HDR: bad RLE data"; return false; }
+                    for (int z = 0; z < count; z++) scan[(size_t)(i++) * 4 + k] = f[pos++];
+                }
+            }
+        }
+        for (int i = 0; i < W; i++) rgbeToFloat(&scan[(size_t)i * 4], px[(size_t)j * W + i]);
+    }
+    return true;
+}
+
+uint32_t crc32(const uint8_t* p, size_t n, uint32_t crc = 0) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+        init = true;
+    }
+    crc = ~crc;
+    for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return ~crc;
+}
+
+void putChunk(std::vector<uint8_t>& out, const char* tag, const std::vector<uint8_t>& data) {
+    uint32_t n = (uint32_t)data.size();
+    const uint8_t len[4] = {(uint8_t)(n >> 24), (uint8_t)(n >> 16), (uint8_t)(n >> 8), (uint8_t)n};
+    out.insert(out.end(), len, len + 4);
+    size_t start = out.size();
+    out.insert(out.end(), tag, tag + 4);
+    out.insert(out.end(), data.begin(), data.end());
+    uint32_t c = crc32(&out[start], out.size() - start);
+    const uint8_t cb[4] = {(uint8_t)(c >> 24), (uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c};
+    out.insert(out.end(), cb, cb + 4);
+}
+
+}  // namespace
+
+// Image::Image(filename) (image.cpp:16-33): stbi_loadf(..., 3) with ldr->hdr gamma 1; flipY = stbi_set_flip_vertically_on_load
+bool loadImageRGB(const std::string& path, bool flipY, HostTexture& out, std::string& err) {
+    std::vector<uint8_t> file;
+    if (!readFile(path, file)) { err = "cannot read image file " + path; return false; }
+    static const uint8_t pngSig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    int W = 0, H = 0;
+    std::vector<f3> px;
+    if (file.size() >= 8 && !memcmp(file.data(), pngSig, 8)) {
+        std::vector<uint8_t> rgb;
+        if (!decodePNG(file, W, H, rgb, err)) { err = path + ": " + err; return false; }
+        px.resize((size_t)W * H);
+        for (size_t i = 0; i < px.size(); i++) px[i] = mk3(rgb[3 * i] / 255.0f, rgb[3 * i + 1] / 255.0f, rgb[3 * i + 2] / 255.0f);   // stbi__ldr_to_hdr, gamma 1
+    } else if (file.size() >= 7 && (!memcmp(file.data(), "#?RADIANCE", 10) || !memcmp(file.data(), "#?RGBE", 6))) {
+        if (!decodeHDR(file, W, H, px, err)) { err = path + ": " + err; return false; }
+    } else {
+        err = path + ": unsupported image format (PNG and Radiance .hdr are supported)";
+        return false;
+    }
+    if (flipY)
+        for (int y = 0; y < H / 2; y++)
+            for (int x = 0; x < W; x++) std::swap(px[(size_t)y * W + x], px[(size_t)(H - 1 - y) * W + x]);
+    out.w = W; out.h = H; out.rgb.swap(px);
+    return true;
+}
+
+// Image::savePNG (image.cpp:41-57): 8-bit RGB rows, top row first; deflate "stored" blocks (valid, uncompressed)
+bool writePNG(const std::string& path, int W, int H, const uint8_t* rgb, std::string& err) {
+    std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<uint8_t> ihdr = {(uint8_t)(W >> 24), (uint8_t)(W >> 16), (uint8_t)(W >> 8), (uint8_t)W, (uint8_t)(H >> 24), (uint8_t)(H >> 16), (uint8_t)(H >> 8), (uint8_t)H, 8, 2, 0, 0, 0};
+    putChunk(out, "IHDR", ihdr);
+    std::vector<uint8_t> raw;
+    raw.reserve(((size_t)W * 3 + 1) * H);
+    for (int y = 0; y < H; y++) { raw.push_back(0); raw.insert(raw.end(), rgb + (size_t)y * W * 3, rgb + (size_t)(y + 1) * W * 3); }
+    std::vector<uint8_t> z = {0x78, 0x01};
+    size_t pos = 0;
+    do {
+        size_t n = raw.size() - pos < 65535 ? raw.size() - pos : 65535;
+        z.push_back(pos + n == raw.size() ? 1 : 0);
+        z.push_back((uint8_t)n); z.push_back((uint8_t)(n >> 8)); z.push_back((uint8_t)~n); z.push_back((uint8_t)(~n >> 8));
+        z.insert(z.end(), raw.begin() + pos, raw.begin() + pos + n);
+        pos += n;
+    } while (pos < raw.size());
+    uint32_t a = 1, b = 0;
+    for (uint8_t v : raw) { a = (a + v) % 65521u; b = (b + a) % 65521u; }
+    uint32_t ad = b << 16 | a;
+    z.push_back((uint8_t)(ad >> 24)); z.push_back((uint8_t)(ad >> 16)); z.push_back((uint8_t)(ad >> 8)); z.push_back((uint8_t)ad);
+    putChunk(out, "IDAT", z);
+    putChunk(out, "IEND", {});
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { err = "cannot write " + path; return false; }
+    bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    fclose(f);
+    if (!ok) err = "short write to " + path;
+    return ok;
+}
+
+}  // namespace rs

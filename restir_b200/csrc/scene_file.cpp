@@ -312,6 +312,27 @@ bool loadSceneFile(const std::string& path, HostScene& hs, RstrCamera& cam, std:
     std::vector<Instance> instances;
     const std::map<std::string, int> typeMap = {{"Lambertian", 0}, {"MetallicWorkflow", 1}, {"Dielectric", 2}, {"Light", 4}};
     auto stof3 = [](const std::vector<std::string>& t) { return mk3(std::stof(t.at(1)), std::stof(t.at(2)), std::stof(t.at(3))); };
+    // Scene::addTexture / Resource::loadTexture (scene.cpp:362-375): one Image per file NAME (the first load wins, so
+    // its vertical-flip setting too), texture ids in order of first use
+    std::map<std::string, int> textureMap;
+    hs.textures.clear(); hs.envMapTexId = -1;
+    bool flipOnLoad = true;                                                           // scene.cpp:98
+    std::string texErr;
+    auto addTexture = [&](const std::string& filename) -> int {
+        auto it = textureMap.find(filename);
+        if (it != textureMap.end()) return it->second;
+        std::string resolved = filename;
+        if (!std::ifstream(resolved.c_str()).good()) {                                // also try relative to the scene file
+            size_t slash = path.find_last_of('/');
+            if (slash != std::string::npos) resolved = path.substr(0, slash + 1) + filename;
+        }
+        HostTexture tex;
+        if (!loadImageRGB(resolved, flipOnLoad, tex, texErr)) return -3;
+        int id = (int)hs.textures.size();
+        hs.textures.push_back(std::move(tex));
+        textureMap[filename] = id;
+        return id;
+    };
     std::string line;
     try {
         while (in.good()) {
@@ -332,17 +353,18 @@ bool loadSceneFile(const std::string& path, HostScene& hs, RstrCamera& cam, std:
                         m.type = it == typeMap.end() ? 0 : it->second;                // std::map::operator[] default-inserts 0
                     } else if (t[0] == "BaseColor") {
                         if (t.size() > 2) { f3 c = stof3(t); m.baseColor[0] = c.x; m.baseColor[1] = c.y; m.baseColor[2] = c.z; }
-                        else { err = "textured / procedural BaseColor is not supported yet: " + line; return false; }
+                        else if (t.at(1) == "Procedural") m.baseColorMapId = -2;         // ProceduralTexId, material.h:13
+                        else if ((m.baseColorMapId = addTexture(t[1])) == -3) { err = texErr; return false; }
                     } else if (t[0] == "Metallic") {
                         if (isdigit((unsigned char)t.at(1).back())) m.metallic = std::stof(t[1]);
-                        else { err = "Metallic texture is not supported yet"; return false; }
+                        else if ((m.metallicMapId = addTexture(t[1])) == -3) { err = texErr; return false; }
                     } else if (t[0] == "Roughness") {
                         if (isdigit((unsigned char)t.at(1).back())) m.roughness = std::stof(t[1]);
-                        else { err = "Roughness texture is not supported yet"; return false; }
+                        else if ((m.roughnessMapId = addTexture(t[1])) == -3) { err = texErr; return false; }
                     } else if (t[0] == "Ior") {
                         m.ior = std::stof(t.at(1));
                     } else if (t[0] == "NormalMap") {
-                        if (t.at(1) != "Null") { err = "NormalMap textures are not supported yet"; return false; }
+                        if (t.at(1) != "Null" && (m.normalMapId = addTexture(t[1])) == -3) { err = texErr; return false; }
                     }
                 }
                 materialMap[tokens.at(1)] = (int)hs.materials.size();
@@ -422,7 +444,12 @@ bool loadSceneFile(const std::string& path, HostScene& hs, RstrCamera& cam, std:
                 cam.tanFovY = tanf(radians(fovy * 0.5f));
                 cameraUpdate(cam);
             } else if (tokens[0] == "EnvMap") {
-                if (tokens.size() > 1 && tokens[1] != "Null") { err = "environment maps are not supported yet (SURVEY 8f)"; return false; }
+                if (tokens.at(1) != "Null") {                                         // scene.cpp:122-128: loaded unflipped
+                    flipOnLoad = false;
+                    hs.envMapTexId = addTexture(tokens[1]);
+                    flipOnLoad = true;
+                    if (hs.envMapTexId == -3) { err = texErr; return false; }
+                }
             }
         }
     } catch (const std::exception& e) {

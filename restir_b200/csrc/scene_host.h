@@ -141,6 +141,10 @@ void buildAliasTable(const std::vector<float>& values, std::vector<AliasEntry>& 
 
 // Scene::Scene(filename): scene text + OBJ -> flattened arrays + camera (scene.cpp:96-131, 222-433, 159-190)
 bool loadSceneFile(const std::string& path, HostScene& hs, RstrCamera& cam, std::string& err);
+// Image::Image(filename) (image.cpp:16-33): PNG / Radiance .hdr -> linear float RGB; flipY = stbi_set_flip_vertically_on_load
+bool loadImageRGB(const std::string& path, bool flipY, HostTexture& out, std::string& err);
+// Image::savePNG (image.cpp:41-57): W x H x 3 bytes, top row first
+bool writePNG(const std::string& path, int W, int H, const unsigned char* rgb, std::string& err);
 // Camera::update (sceneStructs.h:88-102)
 void cameraUpdate(RstrCamera& c);
 

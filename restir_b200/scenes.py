@@ -375,7 +375,7 @@ def procedural(seed: int = 1, num_tris: int = 200_000, num_lights: int = 10_000,
 
 
 # ----------------------------------------------------------------------------- scene-file writer (reference grammar)
-def write_scene_files(scene: SceneData, out_dir: str, stem: str | None = None) -> str:
+def write_scene_files(scene: SceneData, out_dir: str, stem: str | None = None, texture_files=None) -> str:
     """Write ``<stem>.txt`` + one OBJ per material in the reference's grammar.
 
     Triangles are grouped per material (one ``Object`` per material, identity TRS with ``Scale 1 1 1``);
@@ -384,15 +384,20 @@ def write_scene_files(scene: SceneData, out_dir: str, stem: str | None = None) -
     os.makedirs(out_dir, exist_ok=True)
     stem = stem or scene.name
     lines = []
+    # ``texture_files[i]`` = image file holding scene.textures[i] (material maps / EnvMap are written as file names,
+    # scene.cpp:389-429, 122-128); the OBJs then carry ``vt`` records
+    tf = texture_files or []
+    textured = bool(tf)
     for i, m in enumerate(scene.materials):
+        bc, mm, rm, nm = (int(m[k]) for k in ("baseColorMapId", "metallicMapId", "roughnessMapId", "normalMapId"))
         lines += [
             "Material %s" % scene.material_names[i],
             "Type %s" % _TYPE_NAMES[int(m["type"])],
-            "BaseColor %r %r %r" % tuple(float(x) for x in m["baseColor"]),
-            "Metallic %r" % float(m["metallic"]),
-            "Roughness %r" % float(m["roughness"]),
+            "BaseColor Procedural" if bc == -2 else ("BaseColor %s" % tf[bc] if bc >= 0 else "BaseColor %r %r %r" % tuple(float(x) for x in m["baseColor"])),
+            "Metallic %s" % tf[mm] if mm >= 0 else "Metallic %r" % float(m["metallic"]),
+            "Roughness %s" % tf[rm] if rm >= 0 else "Roughness %r" % float(m["roughness"]),
             "Ior %r" % float(m["ior"]),
-            "NormalMap Null",
+            "NormalMap %s" % tf[nm] if nm >= 0 else "NormalMap Null",
             "",
         ]
     obj_id = 0
@@ -407,9 +412,15 @@ def write_scene_files(scene: SceneData, out_dir: str, stem: str | None = None) -
                 f.write("v %s %s %s\n" % (repr(float(p[0])), repr(float(p[1])), repr(float(p[2]))))
             for n in scene.normals[vi]:
                 f.write("vn %s %s %s\n" % (repr(float(n[0])), repr(float(n[1])), repr(float(n[2]))))
+            if textured:
+                for t in scene.texcoords[vi]:
+                    f.write("vt %s %s\n" % (repr(float(t[0])), repr(float(t[1]))))
             for k in range(sel.size):
                 a = 3 * k + 1
-                f.write("f %d//%d %d//%d %d//%d\n" % (a, a, a + 1, a + 1, a + 2, a + 2))
+                if textured:
+                    f.write("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (a, a, a, a + 1, a + 1, a + 1, a + 2, a + 2, a + 2))
+                else:
+                    f.write("f %d//%d %d//%d %d//%d\n" % (a, a, a + 1, a + 1, a + 2, a + 2))
         lines += [
             "Object %d" % obj_id,
             obj_path,
@@ -434,7 +445,7 @@ def write_scene_files(scene: SceneData, out_dir: str, stem: str | None = None) -
         "Rotation %r %r %r" % tuple(float(x) for x in scene.rotation),
         "Up 0 1 0",
         "",
-        "EnvMap Null",
+        "EnvMap %s" % tf[scene.env_map] if (textured and scene.env_map >= 0) else "EnvMap Null",
         "",
     ]
     path = os.path.join(out_dir, stem + ".txt")

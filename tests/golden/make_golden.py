@@ -48,11 +48,60 @@ def textured(ref):
     np.savez_compressed(os.path.join(HERE, "frames_textured.npz"), **d)
 
 
+TEXTURE_FILES = ["rgb8.png", "gray8.png", "gray16.png", "rgb16.png", "env_rle.hdr"]   # base colour, metallic, roughness, normal, EnvMap
+
+
+def textured_scene_file(ref):
+    """7. scene-file grammar with texture file names, `BaseColor Procedural`, NormalMap and EnvMap (scene.cpp:389-429, 122-128)"""
+    import shutil
+    from oracle.oracle import make_camera
+    tmp = tempfile.mkdtemp()
+    sd = scenes.with_textures(scenes.cornell_box((48, 36), metal_tall_box=True), env=True)
+    for f in TEXTURE_FILES:
+        shutil.copy(os.path.join(HERE, "images", f), tmp)
+    path = scenes.write_scene_files(sd, tmp, "cornell_tex_file", texture_files=TEXTURE_FILES)
+    txt = open(path).read().replace(tmp + "/", "")
+    open(path, "w").write(txt)
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    rs = ref.lib.ref_scene_load_file(os.path.basename(path).encode())
+    os.chdir(cwd)
+    T = ref.lib.ref_scene_num_tris(rs)
+    L = ref.lib.orc_scene_num_lights(rs)
+    ref.lib.ref_scene_texture_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    d = {}
+    w, h, e = C.c_int(0), C.c_int(0), C.c_int(0)
+    n = ref.lib.ref_scene_texture_info(rs, 0, C.addressof(w), C.addressof(h), C.addressof(e))
+    d["num_textures"] = n
+    for i in range(n):
+        ref.lib.ref_scene_texture_info(rs, i, C.addressof(w), C.addressof(h), C.addressof(e))
+        d["texture%d" % i] = Oracle._view(ref.lib.ref_scene_array(rs, 32 + i), np.float32, (h.value, w.value, 3))
+        if e.value:
+            d["env_map"] = i
+    nenv = C.c_int(0); tot = C.c_float(0)
+    ref.lib.orc_scene_env_alias.restype = C.c_void_p
+    pe = ref.lib.orc_scene_env_alias(C.c_void_p(rs), C.addressof(nenv), C.addressof(tot))
+    files = {f: open(os.path.join(tmp, f)).read() for f in sorted(os.listdir(tmp)) if f.endswith((".txt", ".obj"))}
+    np.savez_compressed(
+        os.path.join(HERE, "scene_file_textured.npz"),
+        vertices=Oracle._view(ref.lib.ref_scene_array(rs, 0), np.float32, (3 * T, 3)),
+        normals=Oracle._view(ref.lib.ref_scene_array(rs, 1), np.float32, (3 * T, 3)),
+        texcoords=Oracle._view(ref.lib.ref_scene_array(rs, 2), np.float32, (3 * T, 2)),
+        material_ids=Oracle._view(ref.lib.ref_scene_array(rs, 3), np.int32, (T,)),
+        materials=np.frombuffer(Oracle._view(ref.lib.ref_scene_array(rs, 4), np.dtype("V44"), (ref.lib.ref_scene_num_materials(rs),)).tobytes(), np.uint8),
+        alias=np.frombuffer(Oracle._view(ref.lib.orc_scene_alias_table(rs), np.dtype("V8"), (L,)).tobytes(), np.uint8),
+        env_alias=np.frombuffer(Oracle._view(pe, np.dtype("V8"), (nenv.value,)).tobytes(), np.uint8),
+        sum_power=ref.lib.orc_scene_sum_light_power(rs), env_sum=tot.value,
+        file_names=np.array(list(files.keys())), file_texts=np.array(list(files.values())), **d)
+
+
 def main():
     ref = Oracle("reference")
     if "--only-textured" in sys.argv:
         textured(ref)
+        textured_scene_file(ref)
         return
+    textured_scene_file(ref)
     textured(ref)
     # 1. RNG, alias known answers
     rng = {"l%d_i%d" % (l, i): ref.rng_draws(l, i, 8) for l, i in ((7, 12345), (0, 0), (59, 2073599), (1023, 8294399))}

@@ -357,3 +357,27 @@ def test_textured_large_scene_fast_equals_exact(gpu):
     L = sc.info.numLights
     assert (fast[2]["light_index"] >= L - 1).sum() > 1000       # the environment map is being sampled and kept
     sc.close()
+
+
+def test_save_png_is_the_mirrored_tone_mapped_frame(gpu, port_oracle):
+    """saveImage (main.cpp:105-144): tone-map + gamma, mirrored horizontally, 8-bit PNG.  The file must decode to the
+    mirrored LDR frame, and the LDR frame must be the oracle's radiance through ACES + gamma (1 LSB: device powf)."""
+    import tempfile
+    sd = scenes.with_textures(scenes.cornell_box((200, 150)), env=True)
+    sc = gpu.Scene.from_arrays(sd)
+    fr = sc.frame(200, 150)
+    cam = gpu.Camera.from_scene(sd)
+    prm = gpu.default_params(reuse=3, radius=30.0)
+    for k in range(3):
+        fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, k); fr.gbuffer_update(cam)
+    path = os.path.join(tempfile.mkdtemp(), "frame.png")
+    fr.save_png(path, gpu.TONEMAP_ACES)
+    ldr = fr.read("ldr").reshape(150, 200, 4)[:, :, :3]
+    img = gpu.load_image(path, flip=False)
+    assert img.shape == (150, 200, 3)
+    assert np.array_equal(img, ldr[:, ::-1, :].astype(np.float32) / np.float32(255))
+    c = fr.read("radiance").astype(np.float32)
+    aces = (c * (c * np.float32(2.51) + np.float32(0.03))) / (c * (c * np.float32(2.43) + np.float32(0.59)) + np.float32(0.14))
+    want = np.clip((np.power(aces, np.float32(1 / 2.2)) * 255).astype(np.int64), 0, 255).reshape(150, 200, 3)
+    assert np.abs(want - ldr.astype(np.int64)).max() <= 1 and ldr.max() > 100
+    fr.close(); sc.close()

@@ -164,3 +164,72 @@ def test_texture_ids_are_validated():
     sd.materials[0]["normalMapId"] = -2           # the procedural id is only valid for the base colour (scene.h:80-97)
     with pytest.raises(rb.RestirError):
         rb.Scene.from_arrays(sd)
+
+
+def test_image_loader_matches_reference_loader():
+    """PNG (every colour type / bit depth / row filter, split IDAT, stored / fixed / dynamic deflate blocks) and Radiance
+    .hdr (RLE and flat) against what the reference's loader (stb_image via Image::Image) returned, bit for bit."""
+    g = np.load(os.path.join(helpers.GOLDEN, "images.npz"))
+    assert len(g.files) == 34
+    for key in g.files:
+        name, flip = key.rsplit("_flip", 1)
+        a = rb.load_image(os.path.join(helpers.GOLDEN, "images", name), bool(int(flip)))
+        assert a.shape == g[key].shape and np.array_equal(a.view(np.uint32), g[key].view(np.uint32)), key
+    tmp = tempfile.mkdtemp()
+    bad = os.path.join(tmp, "bad.png")
+    open(bad, "wb").write(open(os.path.join(helpers.GOLDEN, "images", "rgb8.png"), "rb").read()[:200])
+    with pytest.raises(rb.RestirError):
+        rb.load_image(bad)
+    with pytest.raises(rb.RestirError):
+        rb.load_image(os.path.join(tmp, "missing.hdr"))
+
+
+def test_png_writer_round_trip():
+    """Image::savePNG replacement: the written file decodes (own loader and zlib) to the same bytes."""
+    import struct
+    import zlib
+    rs = np.random.RandomState(3)
+    img = rs.randint(0, 256, (203, 331, 3)).astype(np.uint8)          # > 64 KiB of scanlines: several stored blocks
+    path = os.path.join(tempfile.mkdtemp(), "out.png")
+    rb.write_png(path, img)
+    assert np.array_equal(rb.load_image(path, flip=False), img.astype(np.float32) / np.float32(255))
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat = 8, b""
+    while pos < len(data):
+        n, tag = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF, tag
+        if tag == b"IHDR":
+            assert struct.unpack(">IIBBBBB", body) == (331, 203, 8, 2, 0, 0, 0)
+        if tag == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(203, 1 + 331 * 3)
+    assert np.all(raw[:, 0] == 0) and np.array_equal(raw[:, 1:].reshape(203, 331, 3), img)
+
+
+def test_textured_scene_file_matches_reference_parser():
+    """Material blocks naming texture files, `BaseColor Procedural`, NormalMap and EnvMap (scene.cpp:389-429, 122-128):
+    texture ids in order of first use, material textures flipped vertically and the environment map not, OBJ `vt`
+    records, and the light sampler with the environment map as last entry -- against the reference's own parser."""
+    import shutil
+    g = np.load(os.path.join(G, "scene_file_textured.npz"))
+    tmp = tempfile.mkdtemp()
+    for n, t in zip(g["file_names"], g["file_texts"]):
+        open(os.path.join(tmp, str(n)), "w").write(str(t))
+    for f in os.listdir(os.path.join(G, "images")):
+        shutil.copy(os.path.join(G, "images", f), tmp)
+    sc = rb.Scene.from_file(os.path.join(tmp, "cornell_tex_file.txt"))
+    for n in ("vertices", "normals", "texcoords", "material_ids"):
+        assert np.array_equal(sc.read(n).view(np.uint32), g[n].view(np.uint32)), n
+    assert sc.read("materials").tobytes() == g["materials"].tobytes()
+    assert sc.info.numTextures == int(g["num_textures"])
+    for i in range(sc.info.numTextures):
+        tex, is_env = sc.texture(i)
+        assert np.array_equal(tex.view(np.uint32), g["texture%d" % i].view(np.uint32)), i
+        assert is_env == (i == int(g["env_map"]))
+    assert sc.read("alias").tobytes() == g["alias"].tobytes()
+    assert sc.read("env_alias").tobytes() == g["env_alias"].tobytes()
+    assert sc.info.sumLightPower == float(g["sum_power"])
+    sc.close()
