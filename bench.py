@@ -193,9 +193,65 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
+PROFILE_POSES = (0, 10, 20, 30, 40, 50)
+
+
 class _DevMem:
     def __init__(self, ptr: int, nbytes: int):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class StripExchange:
+    """Neighbour halo exchange of a strip frame over NCCL send/recv (NVLink): one batch_isend_irecv per call, on
+    tensors that alias the frame's device planes (no staging copies).  ``deferred=True`` issues the batch on a side
+    stream behind everything queued so far and returns; ``join()`` makes the main stream wait for it (used for the
+    history reservoirs, which are only needed by the NEXT frame's temporal step and so travel under its G-buffer)."""
+
+    def __init__(self, fr, plan, rank):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.fr, self.rank = torch, dist, fr, rank
+        self.plan = [p for p in plan if rank in (p[0], p[1])]
+        self.side = torch.cuda.Stream(priority=-1)
+        self.ev_ready, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
+        self.pending = False
+        self.keep = []
+
+    def _ops(self, planes):
+        torch, dist = self.torch, self.dist
+        ops = []
+        for plane in planes:
+            for src, dst, r0, r1 in self.plan:
+                ptr, rowbytes = self.fr.plane_row(plane, r0)
+                t = torch.as_tensor(_DevMem(ptr, rowbytes * (r1 - r0)), device="cuda")
+                self.keep.append(t)
+                ops.append(dist.P2POp(dist.isend if self.rank == src else dist.irecv, t, dst if self.rank == src else src))
+        return ops
+
+    def __call__(self, planes, deferred=False):
+        torch, dist = self.torch, self.dist
+        self.keep = self.keep[-64:]
+        ops = self._ops(planes)
+        if not ops:
+            return
+        if not deferred:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            return
+        main = torch.cuda.current_stream()
+        self.ev_ready.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_ready)
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            self.ev_done.record(self.side)
+        self.pending = True
+
+    def join(self):
+        if self.pending:
+            self.torch.cuda.current_stream().wait_event(self.ev_done)
+            self.pending = False
 
 
 def run_b200(args):
@@ -211,7 +267,9 @@ def run_b200(args):
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.is_high_priority_stream = True      # halo exchanges must get SM slots while a frame kernel fills the GPU
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     rb.init(local)
     desc, spec, res, reuse, radius = WORKLOADS[args.workload]
     W, H = res
@@ -223,59 +281,57 @@ def run_b200(args):
     prm = rb.default_params(reuse=reuse, radius=radius)
     bounds = strips.uniform_bounds(H, world)
     if world > 1 and not args.uniform_strips:
-        # measured cost profile: the image is cut into 8*N bands, every rank times its share of them (two frames of the
-        # real pipeline on a throw-away strip frame), the per-band device times are all-gathered and the cuts are placed
-        # so that every rank gets the same summed cost.  Equal-height strips balance badly: sky rows are almost free.
-        nb = 8 * world
-        bb = strips.uniform_bounds(H, nb)
-        mine = torch.zeros(nb, dtype=torch.float64, device="cuda")
-        pprm = rb.default_params(reuse=reuse & 1, radius=radius)
-        for band in range(rank, nb, world):
-            pf = sc.frame(W, H, rows=(bb[band], bb[band + 1]), halo=0)
-            tot = 0.0
-            for kk in range(3):
+        # measured cost profile: a few frames of the real pipeline on the full image with the kernels' cycle accounting
+        # on (SM cycles every 16x8-pixel block held its SM slot, per group of 8 rows), at poses spread over the orbit (the
+        # cuts are fixed for the run); the cuts then give every rank the same summed cost.  Equal-height strips balance
+        # badly: sky rows are almost free.  All ranks measure, the sum is all-reduced so that they agree on the cuts.
+        pf = sc.frame(W, H)
+        pf.row_cost(enable=True)
+        for pose in PROFILE_POSES:
+            for kk in (pose, pose + 1):
                 cam = base.orbit(orbit_index(kk))
-                pf.gbuffer_render(cam); pf.restir_direct(cam, pprm, kk, 0); pf.gbuffer_update(cam)
-                if kk:
-                    tot += sum(pf.stage_ms().values())
-            mine[band] = tot
-            pf.close()
-        dist.all_reduce(mine)
-        per_band = mine.cpu().numpy()
-        row_cost = np.concatenate([np.full(bb[i + 1] - bb[i], per_band[i] / (bb[i + 1] - bb[i])) for i in range(nb)])
+                pf.gbuffer_render(cam); pf.restir_direct(cam, prm, kk, 0); pf.gbuffer_update(cam)
+        groups = torch.from_numpy(pf.row_cost(enable=False, read=True)).cuda()
+        pf.close()
+        dist.all_reduce(groups)
+        row_cost = np.repeat(groups.cpu().numpy() / 8.0, 8)[:H]
         bounds = strips.balanced_bounds(row_cost, world, min_rows=max(8, halo))
-    rows = strips.strip_rows(H, world, rank, bounds)
-    fr = sc.frame(W, H, rows=rows, halo=halo)
+    row_cost = row_cost if (world > 1 and not args.uniform_strips) else None
+    rows = plan = fr = exchange = None
 
-    plan = strips.exchange_plan(H, world, halo, bounds) if world > 1 else []
-    if world > 1:
-        fr.set_stream(torch.cuda.current_stream().cuda_stream)
+    def make_strip():
+        nonlocal rows, plan, fr, exchange
+        if fr is not None:
+            fr.sync()
+            if world > 1:
+                torch.cuda.synchronize()
+            fr.close()
+        rows = strips.strip_rows(H, world, rank, bounds)
+        fr = sc.frame(W, H, rows=rows, halo=halo)
+        plan = strips.exchange_plan(H, world, halo, bounds) if world > 1 else []
+        if world > 1:
+            fr.set_stream(torch.cuda.current_stream().cuda_stream)
+            fr.set_halo_render(args.render_halo)
+            exchange = StripExchange(fr, plan, rank)
 
-    def exchange(plane):
-        ops, keep = [], []
-        for src, dst, r0, r1 in plan:
-            if rank not in (src, dst):
-                continue
-            ptr, rb_ = fr.plane_row(plane, r0)
-            t = torch.as_tensor(_DevMem(ptr, rb_ * (r1 - r0)), device="cuda")
-            keep.append(t)
-            ops.append(dist.P2POp(dist.isend if rank == src else dist.irecv, t, dst if rank == src else src))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+    make_strip()
 
     def frame(k):
+        # One frame of a strip: G-buffer and phase A on the strip's own rows; then ONE exchange carries the halo rows
+        # phase B reads (post-temporal reservoirs + the neighbours' G-buffer rows, unless those are rendered locally);
+        # the history reservoirs leave on a side stream and are joined just before the next frame's phase A.
         cam = base.orbit(orbit_index(k))
         fr.gbuffer_render(cam)
         if world == 1:
             fr.restir_direct(cam, prm, k, 0)
         else:
+            exchange.join()
             fr.restir_phase_a(cam, prm, k, 0)
-            if reuse & 2:
-                exchange("resv_temp")
+            planes = ([] if args.render_halo else ["geom_cur", "matid_cur"]) + (["resv_temp"] if reuse & 2 else [])
+            exchange(planes)
             fr.restir_phase_b(cam, prm, k, 0)
             if reuse & 1:
-                exchange("resv_history")
+                exchange(["resv_history"], deferred=not args.no_overlap)
         fr.gbuffer_update(cam)
 
     def barrier():
@@ -290,6 +346,31 @@ def run_b200(args):
         t = torch.tensor([x], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---- closed-loop refinement of the cuts: the cycle profile ranks rows correctly but is biased between cheap and
+    # expensive regions (block-launch overhead, tails), so a few frames are run with the current cuts, every rank
+    # reports its measured kernel time, the row costs inside each strip are rescaled by measured / predicted and the
+    # cuts are placed again.  Deterministic across ranks: everything is computed from all-gathered numbers.
+    refine_log = []
+    if row_cost is not None:
+        for it in range(args.refine):
+            tot, cnt = 0.0, 0
+            for pose in PROFILE_POSES:
+                for kk in (pose, pose + 1):
+                    frame(kk)
+                tot += sum(v for n, v in fr.stage_ms().items() if n in ("gbuffer", "ris", "spatial")); cnt += 1
+            t = torch.tensor([tot / cnt], device="cuda", dtype=torch.float64)
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            measured = np.array([float(x.item()) for x in allt])
+            refine_log.append({"bounds": list(bounds), "kernel_ms_per_rank": [round(float(x), 3) for x in measured]})
+            if measured.max() / measured.mean() < 1.02:
+                break
+            for r in range(world):
+                seg = slice(bounds[r], bounds[r + 1])
+                row_cost[seg] *= measured[r] / max(row_cost[seg].sum(), 1e-30)
+            bounds = strips.balanced_bounds(row_cost, world, min_rows=max(8, halo))
+            make_strip()
 
     k = 0
     for _ in range(args.warmup):
@@ -316,6 +397,12 @@ def run_b200(args):
             if n in stage and v > 0:
                 stage[n].append(v)
     stage_ms = {n: (sum(v) / len(v) if v else 0.0) for n, v in stage.items()}
+    stage_per_rank = None
+    if world > 1:
+        t = torch.tensor([stage_ms["gbuffer"], stage_ms["ris"], stage_ms["spatial"]], device="cuda", dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        stage_per_rank = [[round(float(x), 4) for x in a.cpu()] for a in allt]
     # ---- pass 3: end to end through the host-facing call (N = 1) / strips gathered to rank 0 (N > 1)
     npix_local = (rows[1] - rows[0]) * W
     e2e_ms = e2e_sync_ms = None
@@ -409,6 +496,7 @@ def run_b200(args):
             "config": {"workload": args.workload, "description": desc, "resolution": [W, H], "triangles": info.numTris, "emissive_triangles": info.numLights,
                        "reuse": reuse, "candidates": 32, "temporal_cap": 20, "spatial_neighbours": 5, "spatial_radius_px": radius,
                        "parallelism": "strips%d" % world, "halo_rows": halo, "strip_bounds": bounds,
+                       "gbuffer_halo": None if world == 1 else ("rendered locally" if args.render_halo else "received from the neighbours"),
                        "l2": "no explicit flush: the per-frame pixel planes (%.0f MB) exceed the 126 MB L2" % (P * 212 / 1e6)},
             "e2e": {"value": P / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms, "ms_per_step_synchronous_call": e2e_sync_ms,
                     "api": "rstr_render_frame_host_async + rstr_frame_wait_host (three pinned host frames in flight)" if world == 1 else "strips gathered to rank 0 over NCCL, one D2H",
@@ -422,6 +510,8 @@ def run_b200(args):
                          "algorithmic_bytes_per_pixel": bpp, "kernel_ms": stage_ms[dom],
                          "note": "traversal / light-gather bound kernel; HBM fraction reported as required, rays/s below is the telling figure"},
             "stage_ms": stage_ms,
+            "stage_ms_per_rank": stage_per_rank,
+            "strip_refinement": refine_log or None,
             "frame_hbm": {"algorithmic_bytes_per_frame": frame_bytes, "achieved_gbs": frame_bytes / (ms_step * 1e-3) / 1e9, "frac_of_peak": frame_bytes / (ms_step * 1e-3) / 1e9 / peak},
             "rays_per_s": 3.0 * P / (ms_step * 1e-3),
             "halo_miss": halo_miss,
@@ -451,6 +541,9 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
+    ap.add_argument("--refine", type=int, default=4, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for the history-reservoir exchange at the end of the frame instead of under the next G-buffer")
+    ap.add_argument("--render-halo", action="store_true", help="N > 1: every strip renders its G-buffer halo rows itself instead of receiving them from its neighbours")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

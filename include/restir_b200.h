@@ -251,7 +251,8 @@ enum {
     RSTR_PLANE_GEOM_CUR = 0,   /* float4 {n.xyz, depth}, current frame */
     RSTR_PLANE_MATID_CUR = 1,  /* int */
     RSTR_PLANE_RESV_HISTORY = 2, /* 32 B reservoirs written by the last restir_direct */
-    RSTR_PLANE_RESV_TEMP = 3   /* 32 B post-temporal reservoirs (input of the spatial pass) */
+    RSTR_PLANE_RESV_TEMP = 3,  /* 32 B post-temporal reservoirs (input of spatial pass 1; published by even passes) */
+    RSTR_PLANE_RESV_TEMP2 = 4  /* 32 B reservoirs published by odd spatial passes (input of pass 2; spatialPasses > 1 only) */
 };
 int rstr_frame_plane_row(RstrFrame*, int plane, int row, void** devPtr, size_t* rowBytes);
 /* copy rows [row0,row1) of `plane` from src to dst (same device or a peer device), ordered after the work queued on
@@ -261,6 +262,20 @@ int rstr_frame_copy_rows(RstrFrame* dst, RstrFrame* src, int plane, int row0, in
  * exchanges RESV_TEMP / GEOM_CUR / MATID_CUR halo rows, then phase B (spatial + shade). */
 int rstr_restir_phase_a(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter);
 int rstr_restir_phase_b(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter);
+/* One spatial pass (1-based) of phase B, for strip frames with spatialPasses > 1: pass p reads the reservoirs published
+ * by pass p-1 (RESV_TEMP for p = 1, then RESV_TEMP2, RESV_TEMP, ...) in a neighbourhood, so the caller exchanges the
+ * halo rows of that plane between two passes.  The last pass shades and closes the frame like rstr_restir_phase_b. */
+int rstr_restir_phase_b_pass(RstrFrame*, const RstrCamera*, const RstrParams*, int looper, int iter, int pass);
+/* Strip frames: by default rstr_gbuffer_render also renders the halo rows locally (no G-buffer traffic between
+ * GPUs).  With renderHalo = 0 only the strip's own rows are rendered and the caller exchanges the GEOM_CUR / MATID_CUR
+ * halo rows together with RESV_TEMP before phase B (cheaper when strips are thin: 20 B per halo pixel over NVLink
+ * instead of a primary ray each). */
+int rstr_frame_set_halo_render(RstrFrame*, int renderHalo);
+/* Cost profile for placing the strip cuts.  enable != 0 starts (or restarts from zero) the
+ * accumulation: the G-buffer and phase-A kernels add the SM cycles every block (16x8 pixels) held its SM slot to one
+ * counter per group of 8 image rows.  If cyclesPerRowGroup != NULL the counters (numGroups = ceil(height / 8)) are read
+ * first.  enable == 0 stops profiling and frees the counters. */
+int rstr_frame_row_cost(RstrFrame*, int enable, double* cyclesPerRowGroup, int numGroups);
 
 #ifdef __cplusplus
 }

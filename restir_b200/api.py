@@ -104,7 +104,7 @@ SCENE_ARRAYS = dict(boxes=0, mtbvh0=1, light_prim_ids=7, light_radiance=8, alias
 FRAME_BUFFERS = dict(albedo=0, normal=1, matid=2, depth=3, motion=4, radiance=5, reservoir=6, reservoir_temp=7,
                      light_index=8, ldr=9)
 STAGES = ("gbuffer", "ris", "spatial", "ptdirect", "tonemap")
-PLANES = dict(geom_cur=0, matid_cur=1, resv_history=2, resv_temp=3)
+PLANES = dict(geom_cur=0, matid_cur=1, resv_history=2, resv_temp=3, resv_temp2=4)
 
 _lib = None
 
@@ -143,6 +143,9 @@ def lib() -> C.CDLL:
     L.rstr_restir_phase_a.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
     L.rstr_restir_phase_b.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
     L.rstr_pathtrace_direct.argtypes = [vp, C.POINTER(RstrCamera), ip, ip]
+    L.rstr_restir_phase_b_pass.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip]
+    L.rstr_frame_set_halo_render.argtypes = [vp, ip]
+    L.rstr_frame_row_cost.argtypes = [vp, ip, vp, ip]
     L.rstr_tonemap.argtypes = [vp, ip, fp]
     L.rstr_frame_save_png.argtypes = [vp, C.c_char_p, ip]
     L.rstr_image_load.argtypes = [C.c_char_p, ip, vp, vp, vp, C.c_size_t]
@@ -337,6 +340,18 @@ class Frame:
 
     def restir_phase_b(self, cam, params, looper: int, it: int = 0) -> None:
         _check(lib().rstr_restir_phase_b(self.f, C.byref(cam), C.byref(params), looper, it))
+
+    def restir_phase_b_pass(self, cam, params, looper: int, it: int, p: int) -> None:
+        _check(lib().rstr_restir_phase_b_pass(self.f, C.byref(cam), C.byref(params), looper, it, p))
+
+    def set_halo_render(self, on: bool) -> None:
+        _check(lib().rstr_frame_set_halo_render(self.f, 1 if on else 0))
+
+    def row_cost(self, enable: bool = True, read: bool = False):
+        """Start / restart (enable) or stop the per-8-row cycle profile; with ``read`` returns the counters first."""
+        out = np.zeros((self.h + 7) // 8, np.float64) if read else None
+        _check(lib().rstr_frame_row_cost(self.f, 1 if enable else 0, out.ctypes.data if read else None, len(out) if read else 0))
+        return out
 
     def pathtrace_direct(self, cam, looper: int, it: int = 0) -> None:        # pathTraceDirect
         _check(lib().rstr_pathtrace_direct(self.f, C.byref(cam), looper, it))

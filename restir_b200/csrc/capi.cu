@@ -55,6 +55,7 @@ struct RstrFrame {
     cudaEvent_t evRendered[RSTR_LDR_SLOTS] = {}, evCopied[RSTR_LDR_SLOTS] = {};
     bool slotBusy[RSTR_LDR_SLOTS] = {};
     unsigned int* haloMiss = nullptr;
+    unsigned long long* rowCost = nullptr;    // allocated by rstr_frame_row_cost
     int* queue = nullptr;
     unsigned int* queueCount = nullptr;
     void* scratch = nullptr; size_t scratchBytes = 0;
@@ -68,6 +69,7 @@ struct RstrFrame {
     cudaEvent_t xfer = nullptr;
     cudaEvent_t marks[8] = {};
     bool ownStream = true;
+    bool renderHalo = true;        // strip frames: G-buffer halo rows rendered locally (true) or received from the neighbours
     bool ran[RSTR_T_COUNT] = {};
 };
 
@@ -91,7 +93,7 @@ static FrameDev toFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
     d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
     d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
-    d.hit = f->hit; d.hitMR = f->hitMR; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount;
+    d.hit = f->hit; d.hitMR = f->hitMR; d.rowCost = f->rowCost; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount;
     return d;
 }
 
@@ -321,7 +323,7 @@ int rstr_frame_destroy(RstrFrame* f) {
     if (!f) return RSTR_OK;
     if (f->stream) cudaStreamSynchronize(f->stream);
     for (int i = 0; i < 2; i++) { cudaFree(f->geom[i]); cudaFree(f->matId[i]); cudaFree(f->resv[i]); }
-    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->resvTemp2); cudaFree(f->hit); cudaFree(f->hitMR); cudaFree(f->ldr);
+    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->resvTemp2); cudaFree(f->hit); cudaFree(f->hitMR); cudaFree(f->rowCost); cudaFree(f->ldr);
     cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->queueCount);
     for (int i = 0; i < RSTR_LDR_SLOTS; i++) {
         cudaFree(f->ldrB[i]);
@@ -411,7 +413,8 @@ int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
     if (rc) return rc;
     // the reference reads an uninitialised lastCamera before the first GBuffer::update (gbuffer.h:56); use cam
     CamDev c = toCamDev(*cam), lc = toCamDev(f->haveLast ? f->lastCamera : *cam);
-    FrameDev d = toFrameDev(f, f->bufRow0, f->bufRow0 + f->bufRows);      // halo rows are rendered locally, not exchanged
+    FrameDev d = f->renderHalo ? toFrameDev(f, f->bufRow0, f->bufRow0 + f->bufRows)    // halo rows rendered locally ...
+                               : toFrameDev(f, f->row0, f->row1);                     // ... or exchanged by the caller
     for (bool& r : f->ran) r = false;
     stageBegin(f, RSTR_T_GBUFFER);
     g_launches += launchGBuffer(f->sc->dev, d, c, lc, f->stream);
@@ -438,30 +441,73 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     return RSTR_OK;
 }
 
-int rstr_restir_phase_b(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
+static int ensureTemp2(RstrFrame* f) {
+    if (f->resvTemp2) return RSTR_OK;
+    CU(cudaMalloc((void**)&f->resvTemp2, f->nBuf * sizeof(ResvD)));
+    CU(cudaMemcpyAsync(f->resvTemp2, f->resvTemp, f->nBuf * sizeof(ResvD), cudaMemcpyDeviceToDevice, f->stream));
+    return RSTR_OK;
+}
+
+int rstr_restir_phase_b_pass(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter, int pass) {
     int rc = checkCam(f, cam);
     if (rc) return rc;
     (void)looper;
-    if (prm->reuse & 2) {
-        const int passes = prm->spatialPasses < 1 ? 1 : prm->spatialPasses;
-        if (passes > 1 && f->bufRows != f->H)
-            return fail(RSTR_ERR_ARG, "spatialPasses > 1 needs a halo exchange per pass; not supported for strip frames yet");
-        if (passes > 1 && !f->resvTemp2) {
-            CU(cudaMalloc((void**)&f->resvTemp2, f->nBuf * sizeof(ResvD)));
-            CU(cudaMemcpyAsync(f->resvTemp2, f->resvTemp, f->nBuf * sizeof(ResvD), cudaMemcpyDeviceToDevice, f->stream));
-        }
+    const int passes = (prm->reuse & 2) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
+    if (passes && (pass < 1 || pass > passes)) return fail(RSTR_ERR_ARG, "rstr_restir_phase_b_pass: pass out of range");
+    if (passes) {
+        if (passes > 1 && (rc = ensureTemp2(f))) return rc;
         FrameDev d = toFrameDev(f, f->row0, f->row1);
         ResvD* buf[2] = {f->resvTemp, f->resvTemp2};
-        stageBegin(f, RSTR_T_SPATIAL);
-        for (int pass = 1; pass <= passes; pass++) {
-            launchRestirB(f->sc->dev, d, *prm, iter, buf[(pass - 1) & 1], buf[pass & 1], pass, pass == passes ? 1 : 0, f->stream);
-            g_launches++;
-        }
-        stageEnd(f, RSTR_T_SPATIAL);
+        if (pass == 1) stageBegin(f, RSTR_T_SPATIAL);
+        launchRestirB(f->sc->dev, d, *prm, iter, buf[(pass - 1) & 1], buf[pass & 1], pass, pass == passes ? 1 : 0, f->stream);
+        g_launches++;
+        if (pass == passes) stageEnd(f, RSTR_T_SPATIAL);
         CU(cudaGetLastError());
     }
-    f->resvOut ^= 1;                                                       // std::swap, restir.cu:434
-    f->first = false;                                                      // restir.cu:436-438
+    if (pass >= passes) {
+        f->resvOut ^= 1;                                                   // std::swap, restir.cu:434
+        f->first = false;                                                  // restir.cu:436-438
+    }
+    return RSTR_OK;
+}
+
+int rstr_restir_phase_b(RstrFrame* f, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
+    if (!f || !prm) return fail(RSTR_ERR_ARG, "null frame/params");
+    const int passes = (prm->reuse & 2) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
+    if (passes > 1 && f->bufRows != f->H)
+        return fail(RSTR_ERR_ARG, "strip frames with spatialPasses > 1: call rstr_restir_phase_b_pass per pass and exchange the published halo rows in between");
+    for (int pass = 1; pass <= (passes ? passes : 1); pass++) {
+        int rc = rstr_restir_phase_b_pass(f, cam, prm, looper, iter, pass);
+        if (rc) return rc;
+    }
+    return RSTR_OK;
+}
+
+// Cost profile for placing strip cuts: while enabled, the G-buffer and phase-A kernels add the SM cycles each block
+// (16x8 pixels) held its SM slot to one accumulator per group of 8 image rows.
+int rstr_frame_row_cost(RstrFrame* f, int enable, double* cyclesPerRowGroup, int numGroups) {
+    if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    const int G = (f->H + 7) / 8;
+    if (cyclesPerRowGroup) {
+        if (numGroups != G || !f->rowCost) return fail(RSTR_ERR_ARG, "rstr_frame_row_cost: numGroups must be ceil(H / 8) and the profile enabled");
+        std::vector<unsigned long long> h(G);
+        CU(cudaMemcpyAsync(h.data(), f->rowCost, G * sizeof(unsigned long long), cudaMemcpyDeviceToHost, f->stream));
+        CU(cudaStreamSynchronize(f->stream));
+        for (int i = 0; i < G; i++) cyclesPerRowGroup[i] = (double)h[i];
+    }
+    if (enable) {
+        if (!f->rowCost) CU(cudaMalloc((void**)&f->rowCost, G * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(f->rowCost, 0, G * sizeof(unsigned long long), f->stream));
+    } else if (f->rowCost) {
+        CU(cudaStreamSynchronize(f->stream));
+        cudaFree(f->rowCost); f->rowCost = nullptr;
+    }
+    return RSTR_OK;
+}
+
+int rstr_frame_set_halo_render(RstrFrame* f, int renderHalo) {
+    if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    f->renderHalo = renderHalo != 0;
     return RSTR_OK;
 }
 
@@ -704,6 +750,11 @@ int rstr_frame_plane_row(RstrFrame* f, int plane, int row, void** devPtr, size_t
     case RSTR_PLANE_MATID_CUR: *devPtr = f->matId[f->cur] + off; *rowBytes = (size_t)f->W * sizeof(int); break;
     case RSTR_PLANE_RESV_HISTORY: *devPtr = f->resv[f->resvOut ^ 1] + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
     case RSTR_PLANE_RESV_TEMP: *devPtr = f->resvTemp + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
+    case RSTR_PLANE_RESV_TEMP2: {
+        int rc = ensureTemp2(f);
+        if (rc) return rc;
+        *devPtr = f->resvTemp2 + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
+    }
     default: return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: unknown plane");
     }
     return RSTR_OK;

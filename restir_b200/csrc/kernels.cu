@@ -701,6 +701,14 @@ RS_D bool pixelOf(const FrameDev& f, int& x, int& y) {
 // pixels whose outcome depends on the reference's visiting order are deferred to the fix-up kernel
 RS_D void enqueuePixel(const FrameDev& f, int x, int y) { f.queue[atomicAdd(f.queueCount, 1u)] = y * f.W + x; }
 RS_D size_t planeIndex(const FrameDev& f, int x, int y) { return (size_t)(y - f.bufRow0) * f.W + x; }
+// cost profile for the strip cuts: SM cycles every block (16x8 pixels) held its SM slot, summed per group of 8 rows
+RS_D void accountBlock(const FrameDev& f, const unsigned int* t0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int y = f.rowLo + blockIdx.y * 8;
+        if (y < f.H) atomicAdd(f.rowCost + (y >> 3), (unsigned long long)((unsigned int)clock64() - *t0));
+    }
+}
 RS_D bool rowResident(const FrameDev& f, int y) { return y >= f.bufRow0 && y < f.bufRow0 + f.bufRows; }
 
 // restir.cu:216-230: final shade of a reservoir and accumulation into the radiance image
@@ -770,9 +778,11 @@ template <bool EXACT>
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GBUF) k_gbuffer(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                       const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
     RS_DECLARE_STACK(stack);
+    __shared__ unsigned int t0;
+    if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
     int x, y;
-    if (!pixelOf(f, x, y)) return;
-    if (!gbufferPixel<EXACT>(s, f, cam, lastCam, x, y, stack)) enqueuePixel(f, x, y);
+    if (pixelOf(f, x, y) && !gbufferPixel<EXACT>(s, f, cam, lastCam, x, y, stack)) enqueuePixel(f, x, y);
+    if (f.rowCost) accountBlock(f, &t0);
 }
 // recomputes the queued pixels with the reference-order walk
 __global__ void __launch_bounds__(RS_BLOCK) k_gbuffer_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
@@ -948,9 +958,11 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_RESTIR) k_restir_a(const __g
                                                        const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
                                                        int looper, int iter, int first) {
     RS_DECLARE_STACK(stack);
+    __shared__ unsigned int t0;
+    if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
     int x, y;
-    if (!pixelOf(f, x, y)) return;
-    if (!restirAPixel<EXACT, SPATIAL>(s, f, cam, prm, looper, iter, first, x, y, stack)) enqueuePixel(f, x, y);
+    if (pixelOf(f, x, y) && !restirAPixel<EXACT, SPATIAL>(s, f, cam, prm, looper, iter, first, x, y, stack)) enqueuePixel(f, x, y);
+    if (f.rowCost) accountBlock(f, &t0);
 }
 template <bool SPATIAL>
 __global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,

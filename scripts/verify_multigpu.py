@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 import restir_b200 as rb
-from bench import _DevMem
+from bench import StripExchange
 from restir_b200 import scenes, strips
 
 world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
@@ -37,28 +37,19 @@ prm = rb.default_params(reuse=3, radius=radius)
 plan = strips.exchange_plan(H, world, halo, bounds)
 
 
-def exchange(plane):
-    ops, keep = [], []
-    for src, dst, r0, r1 in plan:
-        if rank not in (src, dst):
-            continue
-        ptr, rbytes = fr.plane_row(plane, r0)
-        t = torch.as_tensor(_DevMem(ptr, rbytes * (r1 - r0)), device="cuda")
-        keep.append(t)
-        ops.append(dist.P2POp(dist.isend if rank == src else dist.irecv, t, dst if rank == src else src))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
+fr.set_halo_render(False)          # the benchmarked configuration: G-buffer halo rows travel with the reservoirs
+exchange = StripExchange(fr, plan, rank)
 
 
 bad_total = 0
 for k in range(frames):
     cam = base.orbit(k)
     fr.gbuffer_render(cam)
+    exchange.join()
     fr.restir_phase_a(cam, prm, k, 0)
-    exchange("resv_temp")
+    exchange(["geom_cur", "matid_cur", "resv_temp"])
     fr.restir_phase_b(cam, prm, k, 0)
-    exchange("resv_history")
+    exchange(["resv_history"], deferred=True)
     fr.gbuffer_update(cam)
     if full is not None:
         full.gbuffer_render(cam); full.restir_direct(cam, prm, k, 0); full.gbuffer_update(cam)

@@ -236,6 +236,42 @@ def test_strips_equal_full_frame_at_full_size(gpu):
     full.close(); sc.close()
 
 
+@pytest.mark.parametrize("passes", [1, 2, 3])
+def test_strips_with_exchanged_gbuffer_halo_and_multi_pass(gpu, passes):
+    """Strips that do NOT render their halo rows (the G-buffer halo travels with the reservoirs) and 1-3 spatial
+    passes (one more reservoir halo exchange per pass, BASELINE config 5) == the single full frame, bit for bit."""
+    sd = scenes.procedural(1, 200000, 10000, (1920, 1080))
+    sc = gpu.Scene.from_arrays(sd)
+    W, H = sd.resolution
+    base = gpu.Camera.from_scene(sd)
+    prm = gpu.default_params(reuse=3, radius=30.0, passes=passes)
+    full = sc.frame(W, H)
+    strips = [sc.frame(W, H, rows=(r0, r1), halo=40) for r0, r1 in ((0, 300), (300, 520), (520, 800), (800, 1080))]
+    for s in strips:
+        s.set_halo_render(False)
+    for k in range(3):
+        cam = base.orbit(k)
+        full.gbuffer_render(cam); full.restir_direct(cam, prm, k); full.gbuffer_update(cam)
+        for s in strips:
+            s.gbuffer_render(cam); s.restir_phase_a(cam, prm, k)
+        for plane in ("geom_cur", "matid_cur", "resv_temp"):
+            exchange_halos(gpu, strips, plane)
+        for p in range(1, passes + 1):
+            for s in strips:
+                s.restir_phase_b_pass(cam, prm, k, 0, p)
+            if p < passes:
+                exchange_halos(gpu, strips, "resv_temp2" if p & 1 else "resv_temp")
+        exchange_halos(gpu, strips, "resv_history")
+        for s in strips:
+            s.gbuffer_update(cam)
+        for n in ("matid", "motion", "depth", "radiance", "reservoir", "light_index"):
+            assert helpers.mismatches(full.read(n), np.concatenate([s.read(n) for s in strips])) == 0, "frame %d %s" % (k, n)
+    assert all(s.halo_miss() == 0 for s in strips)
+    for s in strips:
+        s.close()
+    full.close(); sc.close()
+
+
 def exchange_halos(gpu, strips, plane):
     """Single-process form of the neighbour exchange: each strip's edge rows are copied into the halo rows of the
     strips above / below (rstr_frame_copy_rows; the multi-process version sends the same rows over NCCL)."""
