@@ -107,6 +107,7 @@ typedef struct RstrSceneInfo {
     double tracedBuildSeconds;
     int numEmissiveTris;       /* numLights counts the light sampler's entries: emissive triangles + 1 for an environment map */
     int numTextures, envWidth, envHeight;
+    int tracedNodes, tracedRoot;  /* node count / root reference of the traced tree (RSTR_SCENE_TRACED_NODES) */
 } RstrSceneInfo;
 
 typedef struct RstrScene RstrScene;
@@ -125,6 +126,9 @@ enum {
     RSTR_SCENE_MATERIAL_IDS = 13,  /* T x i32 */
     RSTR_SCENE_MATERIALS = 14,     /* numMaterials x 44 B */
     RSTR_SCENE_ENV_ALIAS = 15,     /* envW*envH x {f32 prob, i32 failId}  envMapSampler, scene.cpp:147 */
+    RSTR_SCENE_TRACED_NODES = 16,  /* the binned-SAH tree the kernels walk: tracedNodes x 64 B {lmin[3],lmax[3],rmin[3],rmax[3],left,right,pad[2]};
+                                      child >= 0 node, < 0 leaf = 0x80000000 | (count-1) << 27 | first triangle of TRACED_TRIS */
+    RSTR_SCENE_TRACED_TRIS = 17,   /* T x 48 B {v0,v1,v2,matId,origPrim,pad} in leaf order */
     RSTR_SCENE_TEXTURE0 = 32       /* +i: texture i, width x height x 12 B (size from rstr_scene_texture_info)  Scene::textures */
 };
 

@@ -90,6 +90,8 @@ class RstrSceneInfo(C.Structure):
         ("numTextures", C.c_int),
         ("envWidth", C.c_int),
         ("envHeight", C.c_int),
+        ("tracedNodes", C.c_int),
+        ("tracedRoot", C.c_int),
     ]
 
 
@@ -98,9 +100,12 @@ TONEMAP_NONE, TONEMAP_FILMIC, TONEMAP_ACES = 0, 1, 2
 
 RESERVOIR_DTYPE = np.dtype([("Li", "<f4", (3,)), ("wi", "<f4", (3,)), ("dist", "<f4"), ("M", "<i4"), ("w", "<f4")])
 ALIAS_DTYPE = np.dtype([("prob", "<f4"), ("failId", "<i4")])
+TRACED_NODE_DTYPE = np.dtype([("lmin", "<f4", (3,)), ("lmax", "<f4", (3,)), ("rmin", "<f4", (3,)), ("rmax", "<f4", (3,)), ("left", "<i4"),
+                              ("right", "<i4"), ("pad", "<i4", (2,))])
+TRACED_TRI_DTYPE = np.dtype([("v", "<f4", (3, 3)), ("matId", "<i4"), ("prim", "<i4"), ("pad", "<i4")])
 
 SCENE_ARRAYS = dict(boxes=0, mtbvh0=1, light_prim_ids=7, light_radiance=8, alias=9, vertices=10, normals=11,
-                    texcoords=12, material_ids=13, materials=14, env_alias=15)
+                    texcoords=12, material_ids=13, materials=14, env_alias=15, traced_nodes=16, traced_tris=17)
 FRAME_BUFFERS = dict(albedo=0, normal=1, matid=2, depth=3, motion=4, radiance=5, reservoir=6, reservoir_temp=7,
                      light_index=8, ldr=9)
 STAGES = ("gbuffer", "ris", "spatial", "ptdirect", "tonemap")
@@ -285,6 +290,7 @@ class Scene:
             "boxes": (np.float32, (N, 6)), "mtbvh": (np.int32, (N, 3)), "light_prim_ids": (np.int32, (E,)),
             "light_radiance": (np.float32, (E, 3)), "alias": (ALIAS_DTYPE, (L,)), "vertices": (np.float32, (3 * T, 3)),
             "env_alias": (ALIAS_DTYPE, (self.info.envWidth * self.info.envHeight,)),
+            "traced_nodes": (TRACED_NODE_DTYPE, (self.info.tracedNodes,)), "traced_tris": (TRACED_TRI_DTYPE, (T,)),
             "normals": (np.float32, (3 * T, 3)), "texcoords": (np.float32, (3 * T, 2)), "material_ids": (np.int32, (T,)),
             "materials": (np.dtype("V44"), (self.info.numMaterials,)),
         }[name]

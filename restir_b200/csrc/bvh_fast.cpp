@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <limits>
 
 #include "scene_host.h"
 
@@ -135,6 +136,65 @@ struct FastBuilder {
     }
 };
 
+// BVH2 -> BVH4: every node adopts its grandchildren, largest surface area first, until it has four children (or only
+// leaves are left).  Halves the number of dependent node fetches per ray, which is what the traversal kernels wait on.
+void collapse4(HostScene& hs) {
+    hs.fastNodes4.clear();
+    hs.fastDepth4 = 0;
+    hs.fastRoot4 = hs.fastRoot;
+    if (hs.fastRoot < 0) return;                       // the whole scene is one leaf
+    struct Entry { int ref; float lo[3], hi[3]; };
+    struct Work { int node2, out, depth; };
+    std::vector<Work> stack;
+    hs.fastNodes4.reserve(hs.fastNodes.size() / 2 + 1);
+    hs.fastNodes4.push_back(FastNode4{});
+    stack.push_back(Work{hs.fastRoot, 0, 1});
+    auto children = [&](int n2, Entry& a, Entry& b) {
+        const FastNode& nd = hs.fastNodes[n2];
+        a.ref = nd.left; memcpy(a.lo, nd.lmin, 12); memcpy(a.hi, nd.lmax, 12);
+        b.ref = nd.right; memcpy(b.lo, nd.rmin, 12); memcpy(b.hi, nd.rmax, 12);
+    };
+    auto area = [](const Entry& e) {
+        float dx = e.hi[0] - e.lo[0], dy = e.hi[1] - e.lo[1], dz = e.hi[2] - e.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    };
+    while (!stack.empty()) {
+        Work w = stack.back(); stack.pop_back();
+        hs.fastDepth4 = std::max(hs.fastDepth4, w.depth);
+        Entry e[4];
+        int n = 2;
+        children(w.node2, e[0], e[1]);
+        while (n < 4) {
+            int pick = -1;
+            for (int i = 0; i < n; i++)
+                if (e[i].ref >= 0 && (pick < 0 || area(e[i]) > area(e[pick]))) pick = i;
+            if (pick < 0) break;
+            int n2 = e[pick].ref;
+            children(n2, e[pick], e[n]);
+            n++;
+        }
+        FastNode4 nd;
+        const float inf = std::numeric_limits<float>::infinity();
+        for (int i = 0; i < 4; i++) {
+            if (i < n) {
+                nd.lox[i] = e[i].lo[0]; nd.loy[i] = e[i].lo[1]; nd.loz[i] = e[i].lo[2];
+                nd.hix[i] = e[i].hi[0]; nd.hiy[i] = e[i].hi[1]; nd.hiz[i] = e[i].hi[2];
+                if (e[i].ref >= 0) {
+                    nd.child[i] = (int)hs.fastNodes4.size();
+                    hs.fastNodes4.push_back(FastNode4{});
+                    stack.push_back(Work{e[i].ref, nd.child[i], w.depth + 1});
+                } else nd.child[i] = e[i].ref;
+            } else {
+                nd.lox[i] = nd.loy[i] = nd.loz[i] = nd.hix[i] = nd.hiy[i] = nd.hiz[i] = inf;        // unused slot: child == 0x7fffffff
+                nd.child[i] = 0x7fffffff;
+            }
+            nd.pad[i] = 0;
+        }
+        hs.fastNodes4[w.out] = nd;
+    }
+    hs.fastRoot4 = 0;
+}
+
 }  // namespace
 
 void buildFastBVH(HostScene& hs) {
@@ -158,6 +218,7 @@ void buildFastBVH(HostScene& hs) {
     rootRef = b.build(0, T, 1, root);
     hs.fastRoot = rootRef;
     hs.fastDepth = b.maxDepth.load();
+    if (RS_BVH4) collapse4(hs);
     for (int a = 0; a < 3; a++) {
         float pad = 4e-6f * std::max(fabsf(root.lo[a]), fabsf(root.hi[a])) + 1e-7f;
         hs.fastRootMin[a] = root.lo[a] - pad; hs.fastRootMax[a] = root.hi[a] + pad;

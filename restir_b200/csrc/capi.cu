@@ -119,6 +119,12 @@ static int finishScene(RstrScene* sc, RstrScene** out) {
         delete sc;
         return fail(RSTR_ERR_LIMIT, b);
     }
+    if (RS_BVH4 && 3 * sc->hs.fastDepth4 + 1 > RS_STACK_DEPTH) {
+        char b[160];
+        snprintf(b, sizeof b, "traced tree depth %d exceeds the traversal stack (%d entries, 3 per level)", sc->hs.fastDepth4, RS_STACK_DEPTH);
+        delete sc;
+        return fail(RSTR_ERR_LIMIT, b);
+    }
     *out = sc;
     return RSTR_OK;
 }
@@ -129,7 +135,7 @@ static int ensureUploaded(RstrScene* sc) {
     size_t total = 0;
     cudaError_t e;
     if ((e = upload(&sc->dNodes, hs.packed, total)) != cudaSuccess || (e = upload(&sc->dTriGeom, hs.fastTris, total)) != cudaSuccess ||
-        (e = upload(&sc->dFastNodes, hs.fastNodes, total)) != cudaSuccess || (e = upload(&sc->dRank, hs.rank, total)) != cudaSuccess || (e = upload(&sc->dPrimToFast, hs.primToFast, total)) != cudaSuccess ||
+        (e = (RS_BVH4 ? upload(&sc->dFastNodes, hs.fastNodes4, total) : upload(&sc->dFastNodes, hs.fastNodes, total))) != cudaSuccess || (e = upload(&sc->dRank, hs.rank, total)) != cudaSuccess || (e = upload(&sc->dPrimToFast, hs.primToFast, total)) != cudaSuccess ||
 
         (e = upload(&sc->dTriNorm, hs.triNorm, total)) != cudaSuccess || (e = upload(&sc->dMaterials, hs.materials, total)) != cudaSuccess ||
         (e = upload(&sc->dAlias, hs.alias, total)) != cudaSuccess || (e = upload(&sc->dLights, hs.lights, total)) != cudaSuccess ||
@@ -152,7 +158,7 @@ static int ensureUploaded(RstrScene* sc) {
     d.nodes = (const float4*)sc->dNodes; d.triGeom = (const float4*)sc->dTriGeom; d.triNorm = (const float4*)sc->dTriNorm;
     d.materials = (const RstrMaterial*)sc->dMaterials; d.alias = (const float2*)sc->dAlias; d.lights = (const float4*)sc->dLights;
     d.fastNodes = (const float4*)sc->dFastNodes; d.primToFast = (const int*)sc->dPrimToFast; d.rank = (const int*)sc->dRank;
-    d.numTris = hs.T; d.fastRoot = hs.fastRoot; d.traversal = sc->traversalMode;
+    d.numTris = hs.T; d.numFastNodes = (int)(RS_BVH4 ? hs.fastNodes4.size() : hs.fastNodes.size()); d.fastRoot = RS_BVH4 ? hs.fastRoot4 : hs.fastRoot; d.traversal = sc->traversalMode;
     memcpy(d.fastRootMin, hs.fastRootMin, 12); memcpy(d.fastRootMax, hs.fastRootMax, 12);
     d.numLights = (int)hs.alias.size();           // lightSampler.length: emissive triangles (+ the environment map, last)
     d.texData = (const float4*)sc->dTexData; d.texInfo = (const int4*)sc->dTexInfo; d.triUV = (const float4*)sc->dTriUV;
@@ -257,6 +263,7 @@ int rstr_scene_info(const RstrScene* sc, RstrSceneInfo* info) {
     info->bvhDepth = sc->hs.bvhDepth; info->numMaterials = (int)sc->hs.materials.size(); info->sumLightPower = sc->hs.sumAll;
     info->buildSeconds = sc->hs.buildSeconds; info->deviceBytes = sc->deviceBytes;
     info->tracedBvhDepth = sc->hs.fastDepth; info->tracedBuildSeconds = sc->hs.fastBuildSeconds;
+    info->tracedNodes = (int)sc->hs.fastNodes.size(); info->tracedRoot = sc->hs.fastRoot;
     info->numEmissiveTris = (int)sc->hs.lightPrimIds.size(); info->numTextures = (int)sc->hs.textures.size();
     info->envWidth = info->envHeight = 0;
     if (sc->hs.envMapTexId >= 0) { info->envWidth = sc->hs.textures[sc->hs.envMapTexId].w; info->envHeight = sc->hs.textures[sc->hs.envMapTexId].h; }
@@ -288,6 +295,8 @@ int rstr_scene_read(const RstrScene* sc, int which, void* host, size_t bytes) {
     case RSTR_SCENE_MATERIAL_IDS: src = hs.materialIds.data(); need = hs.materialIds.size() * 4; break;
     case RSTR_SCENE_MATERIALS: src = hs.materials.data(); need = hs.materials.size() * sizeof(RstrMaterial); break;
     case RSTR_SCENE_ENV_ALIAS: src = hs.envAlias.data(); need = hs.envAlias.size() * 8; break;
+    case RSTR_SCENE_TRACED_NODES: src = hs.fastNodes.data(); need = hs.fastNodes.size() * sizeof(FastNode); break;
+    case RSTR_SCENE_TRACED_TRIS: src = hs.fastTris.data(); need = hs.fastTris.size() * sizeof(TriGeom); break;
     default:
         if (which >= RSTR_SCENE_TEXTURE0 && which < RSTR_SCENE_TEXTURE0 + (int)hs.textures.size()) {
             src = hs.textures[which - RSTR_SCENE_TEXTURE0].rgb.data(); need = hs.textures[which - RSTR_SCENE_TEXTURE0].rgb.size() * 12;

@@ -15,12 +15,13 @@ namespace rs {
 
 struct DevScene {
     const float4* nodes;       // PackedNode[] (reference tree), 4 x float4 each
-    const float4* fastNodes;   // FastNode[] (traced tree), 4 x float4 each
+    const float4* fastNodes;   // FastNode[] (traced tree), 4 x float4 each (FastNode4[], 8 x float4, when RS_BVH4 == 1)
     const float4* triGeom;     // TriGeom[] in the traced tree's leaf order, 3 x float4 each
     const float4* triNorm;     // TriNorm[] in original primitive order, 3 x float4 each
     const int* primToFast;     // original primitive id -> triGeom index
     const int* rank;           // [6][numTris] visiting rank in the reference's orderings (near-tie resolution)
     int numTris;
+    int numFastNodes;
     int fastRoot;
     int traversal;             // RS_TRAVERSAL_*
     unsigned int* fallbackRays;  // [3] pixels recomputed with the reference-order walk: G-buffer, ReSTIR phase A, PTDirect

@@ -163,6 +163,9 @@ struct Tri { f3 v0, v1, v2; int matId; int prim; };   // prim = original primiti
 
 // triangle record fi of the leaf-ordered array
 RS_D Tri loadTriFast(const DevScene& s, int fi) {
+#ifdef RS_DEBUG_BOUNDS
+    if (fi < 0 || fi >= s.numTris) { printf("loadTriFast: bad triangle %d (of %d)\n", fi, s.numTris); __trap(); }
+#endif
     const float4* p = s.triGeom + 3 * (size_t)fi;
     float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
     Tri t;
@@ -193,6 +196,9 @@ struct Stack {
     int lRef[RS_STACK_DEPTH - RS_SMEM_STACK];
     float lT[RS_STACK_DEPTH - RS_SMEM_STACK];
     RS_D void push(int sp, int ref, float t) {
+#ifdef RS_DEBUG_BOUNDS
+        if (sp < 0 || sp >= RS_STACK_DEPTH) { printf("stack overflow sp %d\n", sp); __trap(); }
+#endif
         if (sp < RS_SMEM_STACK) { sRef[sp * RS_BLOCK] = ref; sT[sp * RS_BLOCK] = t; }
         else { lRef[sp - RS_SMEM_STACK] = ref; lT[sp - RS_SMEM_STACK] = t; }
     }
@@ -304,6 +310,49 @@ RS_D bool slabHit(const RayF& f, float lx, float ly, float lz, float hx, float h
     return tEntry <= tExit;
 }
 
+// 4-wide node: slab tests of the four children from six LDG.128 (one plane each) + the links; the children that are
+// hit come back as sort keys (entry distance with the slot number in the two lowest mantissa bits: distances are
+// non-negative, so integer order = float order), ordered near to far by a 5-exchange network.  The two cleared bits
+// make the stored distance at most 3 ulp too small, i.e. culling at pop time stays conservative.
+#define RS_MISS 0x7fffffff
+struct Node4Hits { int k0, k1, k2, k3; int4 ch; };
+RS_D int node4Child(const Node4Hits& h, int key) {
+    int i = key & 3;
+    return i == 0 ? h.ch.x : (i == 1 ? h.ch.y : (i == 2 ? h.ch.z : h.ch.w));
+}
+RS_D float node4T(int key) { return __int_as_float(key & ~3); }
+RS_D Node4Hits node4Test(const DevScene& s, const RayF& f, int node, float tLimit) {
+#ifdef RS_DEBUG_BOUNDS
+    if (node < 0 || node >= s.numFastNodes) { printf("node4Test: bad node %d (of %d) block %d,%d thread %d\n", node, s.numFastNodes, blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
+#endif
+    const float4* np = s.fastNodes + 8 * (size_t)node;
+    float4 lo = __ldg(np), hi = __ldg(np + 1);
+    float4 t0, t1;
+#define RS_AXIS_FIRST(c, I, O)                                                                          \
+    { float a0 = __fmaf_rn(lo.c, I, O), a1 = __fmaf_rn(hi.c, I, O); t0.c = fminf(a0, a1); t1.c = fmaxf(a0, a1); }
+#define RS_AXIS_NEXT(c, I, O)                                                                           \
+    { float a0 = __fmaf_rn(lo.c, I, O), a1 = __fmaf_rn(hi.c, I, O); t0.c = fmaxf(t0.c, fminf(a0, a1)); t1.c = fminf(t1.c, fmaxf(a0, a1)); }
+    RS_AXIS_FIRST(x, f.inv.x, f.oi.x) RS_AXIS_FIRST(y, f.inv.x, f.oi.x) RS_AXIS_FIRST(z, f.inv.x, f.oi.x) RS_AXIS_FIRST(w, f.inv.x, f.oi.x)
+    lo = __ldg(np + 2); hi = __ldg(np + 3);
+    RS_AXIS_NEXT(x, f.inv.y, f.oi.y) RS_AXIS_NEXT(y, f.inv.y, f.oi.y) RS_AXIS_NEXT(z, f.inv.y, f.oi.y) RS_AXIS_NEXT(w, f.inv.y, f.oi.y)
+    lo = __ldg(np + 4); hi = __ldg(np + 5);
+    RS_AXIS_NEXT(x, f.inv.z, f.oi.z) RS_AXIS_NEXT(y, f.inv.z, f.oi.z) RS_AXIS_NEXT(z, f.inv.z, f.oi.z) RS_AXIS_NEXT(w, f.inv.z, f.oi.z)
+#undef RS_AXIS_FIRST
+#undef RS_AXIS_NEXT
+    Node4Hits h;
+    h.ch = __ldg((const int4*)(np + 6));
+    // an unused slot has child == RS_MISS (its box cannot be relied on: the slab test is symmetric in lo / hi)
+#define RS_KEY(c, i) ((fmaxf(t0.c, 0.f) <= fminf(t1.c, tLimit) && h.ch.c != RS_MISS) ? ((__float_as_int(fmaxf(t0.c, 0.f)) & ~3) | i) : RS_MISS)
+    int a = RS_KEY(x, 0), b = RS_KEY(y, 1), c = RS_KEY(z, 2), d = RS_KEY(w, 3);
+#undef RS_KEY
+    int lo01 = min(a, b), hi01 = max(a, b), lo23 = min(c, d), hi23 = max(c, d);
+    h.k0 = min(lo01, lo23);
+    int m1 = max(lo01, lo23), m2 = min(hi01, hi23);
+    h.k3 = max(hi01, hi23);
+    h.k1 = min(m1, m2); h.k2 = max(m1, m2);
+    return h;
+}
+
 // ---- what the reference's walk finds, without walking its tree ----
 // The reference reaches a triangle only through nested boxes that end in the triangle's own AABB (1 triangle per leaf,
 // bvh.cpp:25), each tested with the predicate of bvh.h:85-157 and pruned by "box distance < closest" (scene.h:260).
@@ -367,6 +416,17 @@ RS_D bool closestRun(const DevScene& s, ClosestState& st, Stack& stack, int minA
     const RayF f = st.f;
     for (;;) {
         // ---- descend through internal nodes
+#if RS_BVH4
+        while (st.cur >= 0 && st.cur != RS_DONE) {
+            Node4Hits nh = node4Test(s, f, st.cur, st.limit);
+            if (nh.k0 == RS_MISS) { st.cur = closestPop(st, stack); continue; }
+            // far children first, so that the nearest is popped first
+            if (nh.k3 != RS_MISS) { stack.push(st.sp, node4Child(nh, nh.k3), node4T(nh.k3)); st.sp++; }
+            if (nh.k2 != RS_MISS) { stack.push(st.sp, node4Child(nh, nh.k2), node4T(nh.k2)); st.sp++; }
+            if (nh.k1 != RS_MISS) { stack.push(st.sp, node4Child(nh, nh.k1), node4T(nh.k1)); st.sp++; }
+            st.cur = node4Child(nh, nh.k0);
+        }
+#else
         while (st.cur >= 0 && st.cur != RS_DONE) {
             const float4* np = s.fastNodes + 4 * (size_t)st.cur;
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
@@ -382,6 +442,7 @@ RS_D bool closestRun(const DevScene& s, ClosestState& st, Stack& stack, int minA
             else if (hR) st.cur = l.y;
             else st.cur = closestPop(st, stack);
         }
+#endif
         if (st.cur == RS_DONE) return true;
         // ---- leaf
         {
@@ -467,6 +528,20 @@ RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& 
     int sp = 0;
     int cur = s.fastRoot;
     for (;;) {
+#if RS_BVH4
+        while (cur >= 0) {
+            Node4Hits nh = node4Test(s, f, cur, dist);
+            if (nh.k0 == RS_MISS) {
+                if (sp == 0) return 0;
+                cur = stack.ref(--sp);
+                continue;
+            }
+            if (nh.k3 != RS_MISS) { stack.pushRef(sp, node4Child(nh, nh.k3)); sp++; }
+            if (nh.k2 != RS_MISS) { stack.pushRef(sp, node4Child(nh, nh.k2)); sp++; }
+            if (nh.k1 != RS_MISS) { stack.pushRef(sp, node4Child(nh, nh.k1)); sp++; }
+            cur = node4Child(nh, nh.k0);
+        }
+#else
         while (cur >= 0) {
             const float4* np = s.fastNodes + 4 * (size_t)cur;
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
@@ -485,6 +560,7 @@ RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& 
                 cur = stack.ref(--sp);
             }
         }
+#endif
         int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
         for (int i = 0; i < count; i++) {
             Tri t = loadTriFast(s, first + i);

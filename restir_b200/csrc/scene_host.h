@@ -8,6 +8,11 @@
 #include "../../include/restir_b200.h"
 #include "vecmath.h"
 
+#ifndef RS_BVH4
+#define RS_BVH4 0               /* 0: the traced tree is the binned-SAH BVH2 (FastNode); 1: its 4-wide collapse (FastNode4) -- measured
+                                   6 % SLOWER on B200 (profiles/README.md): kept as a build option for A/B runs only */
+#endif
+
 namespace rs {
 
 struct Box {            // reference AABB, 24 B (bvh.h:159-160)
@@ -33,6 +38,15 @@ struct alignas(16) FastNode {
     int pad[2];
 };
 static_assert(sizeof(FastNode) == 64, "FastNode");
+
+// One 128-byte record (= one L1 line) per internal node of the 4-wide tree the kernels walk: the four children's padded
+// boxes, structure-of-arrays so that one LDG.128 brings one plane of all four, + links.  Collapsed from the BVH2.
+struct alignas(16) FastNode4 {
+    float lox[4], hix[4], loy[4], hiy[4], loz[4], hiz[4];
+    int child[4];             // >= 0: node index; < 0: leaf (same encoding as FastNode); unused slot: 0x7fffffff
+    int pad[4];
+};
+static_assert(sizeof(FastNode4) == 128, "FastNode4");
 
 struct alignas(16) TriGeom {  // 48 B: raw vertices (Moller-Trumbore recomputes the edges exactly as intersections.h:20-21)
     float v0[3], v1[3], v2[3];
@@ -115,7 +129,9 @@ struct HostScene {
     std::vector<TriNorm> triNorm;          // original primitive order
 
     // traced tree (bvh_fast.cpp)
-    std::vector<FastNode> fastNodes;
+    std::vector<FastNode> fastNodes;       // binned-SAH BVH2 (host only: input of the 4-wide collapse)
+    std::vector<FastNode4> fastNodes4;     // the tree that is traced
+    int fastRoot4 = 0, fastDepth4 = 0;
     std::vector<int> fastOrder;            // leaf order -> original primitive id
     std::vector<int> primToFast;           // original primitive id -> position in fastTris
     std::vector<TriGeom> fastTris;         // triangles in leaf order

@@ -233,3 +233,35 @@ def test_textured_scene_file_matches_reference_parser():
     assert sc.read("env_alias").tobytes() == g["env_alias"].tobytes()
     assert sc.info.sumLightPower == float(g["sum_power"])
     sc.close()
+
+
+@pytest.mark.parametrize("name", ["cornell", "five", "gen2000"])
+def test_traced_tree_is_a_valid_bvh(name):
+    """The binned-SAH tree the kernels walk (bvh_fast.cpp): every triangle sits in exactly one leaf (<= 4 per leaf) and
+    every child box (padded) contains the triangles below it, so a conservative slab walk cannot miss a hit."""
+    sd = helpers.test_scenes()[name]
+    sc = rb.Scene.from_arrays(sd)
+    nodes, tris = sc.read("traced_nodes"), sc.read("traced_tris")
+    T = sc.info.numTris
+    assert sorted(tris["prim"].tolist()) == list(range(T))
+    assert np.array_equal(tris["v"].reshape(T, 9), np.asarray(sd.vertices, np.float32).reshape(T, 9)[tris["prim"]])
+    seen = np.zeros(T, int)
+    stack = [(sc.info.tracedRoot, None)]
+    while stack:
+        ref, box = stack.pop()
+        if ref < 0:
+            u = ref & 0xFFFFFFFF
+            first, cnt = u & 0x07FFFFFF, ((u >> 27) & 7) + 1
+            assert cnt <= 4
+            seen[first:first + cnt] += 1
+            if box is not None:
+                v = tris["v"][first:first + cnt].reshape(-1, 3)
+                assert (v >= box[0]).all() and (v <= box[1]).all()
+            continue
+        n = nodes[ref]
+        for lo, hi, child in ((n["lmin"], n["lmax"], n["left"]), (n["rmin"], n["rmax"], n["right"])):
+            if box is not None:
+                assert (lo >= box[0] - 1e-4).all() and (hi <= box[1] + 1e-4).all()
+            stack.append((int(child), (lo, hi)))
+    assert (seen == 1).all()
+    sc.close()
