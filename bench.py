@@ -315,6 +315,8 @@ def run_b200(args):
             exchange = StripExchange(fr, plan, rank)
 
     make_strip()
+    if args.no_fusion:
+        fr.set_fusion(False)
 
     def frame(k):
         # One frame of a strip: G-buffer and phase A on the strip's own rows; then ONE exchange carries the halo rows
@@ -486,6 +488,9 @@ def run_b200(args):
         dom = max(stage_ms, key=lambda n: stage_ms[n])
         bpp = KERNEL_BYTES_PER_PIXEL[dom]
         bpp = bpp[reuse] if isinstance(bpp, dict) else bpp
+        fused = stage_ms["gbuffer"] == 0.0 and stage_ms["ris"] > 0.0      # G-buffer + phase A ran as one kernel
+        if fused and dom == "ris":
+            bpp += KERNEL_BYTES_PER_PIXEL["gbuffer"]
         strip_px = npix_local
         achieved = bpp * strip_px / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
         frame_bytes = BYTES_PER_PIXEL[reuse] * P
@@ -503,7 +508,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": C.sizeof(rb.api.RstrCamera) + C.sizeof(rb.RstrParams), "d2h_bytes_per_step": P * 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": "k_restir_a", "spatial": "k_restir_b"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": "k_gbuffer_restir_a" if fused else "k_restir_a", "spatial": "k_restir_b"}[dom],
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC.get((args.workload, dom), (None, None))[0] if world == 1 else None,
                          "traffic_source": NCU_TRAFFIC.get((args.workload, dom), (None, None))[1],
@@ -542,6 +547,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
     ap.add_argument("--refine", type=int, default=4, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
+    ap.add_argument("--no-fusion", action="store_true", help="separate G-buffer and phase-A kernels instead of the fused one (A/B)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for the history-reservoir exchange at the end of the frame instead of under the next G-buffer")
     ap.add_argument("--render-halo", action="store_true", help="N > 1: every strip renders its G-buffer halo rows itself instead of receiving them from its neighbours")
     args = ap.parse_args()

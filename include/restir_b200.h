@@ -275,6 +275,12 @@ int rstr_restir_phase_b_pass(RstrFrame*, const RstrCamera*, const RstrParams*, i
  * halo rows together with RESV_TEMP before phase B (cheaper when strips are thin: 20 B per halo pixel over NVLink
  * instead of a primary ray each). */
 int rstr_frame_set_halo_render(RstrFrame*, int renderHalo);
+/* By default rstr_gbuffer_render defers its launch: when the next call on the frame is rstr_restir_direct / _phase_a
+ * with the same camera, ONE kernel renders the G-buffer and runs phase A, walking the tree once for the pixel's two
+ * primary rays (centre ray, gbuffer.cu:11-23; jittered ray, restir.cu:129).  Results are identical to the two separate
+ * kernels; any other use of the G-buffer in between (reads, plane pointers, gbuffer_update, sync, PTDirect) launches the
+ * plain G-buffer kernel first.  enable = 0 turns the fusion off (A/B measurements, tests). */
+int rstr_frame_set_fusion(RstrFrame*, int enable);
 /* Cost profile for placing the strip cuts.  enable != 0 starts (or restarts from zero) the
  * accumulation: the G-buffer and phase-A kernels add the SM cycles every block (16x8 pixels) held its SM slot to one
  * counter per group of 8 image rows.  If cyclesPerRowGroup != NULL the counters (numGroups = ceil(height / 8)) are read

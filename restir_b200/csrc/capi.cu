@@ -69,6 +69,10 @@ struct RstrFrame {
     cudaEvent_t xfer = nullptr;
     cudaEvent_t marks[8] = {};
     bool ownStream = true;
+    bool fuse = true;              // G-buffer + phase A as one kernel when both are asked for with the same camera
+    bool gbufPending = false;      // rstr_gbuffer_render was called and its launch is deferred to the next phase A (or flushed)
+    RstrCamera pendCam{};
+    CamDev pendC{}, pendLC{};
     bool renderHalo = true;        // strip frames: G-buffer halo rows rendered locally (true) or received from the neighbours
     bool ran[RSTR_T_COUNT] = {};
 };
@@ -417,23 +421,47 @@ static int checkCam(const RstrFrame* f, const RstrCamera* cam) {
 static inline void stageBegin(RstrFrame* f, int s) { cudaEventRecord(f->ev[2 * s], f->stream); f->ran[s] = true; }
 static inline void stageEnd(RstrFrame* f, int s) { cudaEventRecord(f->ev[2 * s + 1], f->stream); }
 
-int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
-    int rc = checkCam(f, cam);
-    if (rc) return rc;
-    // the reference reads an uninitialised lastCamera before the first GBuffer::update (gbuffer.h:56); use cam
-    CamDev c = toCamDev(*cam), lc = toCamDev(f->haveLast ? f->lastCamera : *cam);
+// launches a G-buffer render that rstr_gbuffer_render deferred (see there)
+static int flushGBuffer(RstrFrame* f) {
+    if (!f->gbufPending) return RSTR_OK;
+    f->gbufPending = false;
     FrameDev d = f->renderHalo ? toFrameDev(f, f->bufRow0, f->bufRow0 + f->bufRows)    // halo rows rendered locally ...
                                : toFrameDev(f, f->row0, f->row1);                     // ... or exchanged by the caller
-    for (bool& r : f->ran) r = false;
     stageBegin(f, RSTR_T_GBUFFER);
-    g_launches += launchGBuffer(f->sc->dev, d, c, lc, f->stream);
+    g_launches += launchGBuffer(f->sc->dev, d, f->pendC, f->pendLC, f->stream);
     stageEnd(f, RSTR_T_GBUFFER);
     CU(cudaGetLastError());
     return RSTR_OK;
 }
 
+int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
+    int rc = checkCam(f, cam);
+    if (rc) return rc;
+    if ((rc = flushGBuffer(f))) return rc;
+    // the reference reads an uninitialised lastCamera before the first GBuffer::update (gbuffer.h:56); use cam
+    f->pendCam = *cam;
+    f->pendC = toCamDev(*cam); f->pendLC = toCamDev(f->haveLast ? f->lastCamera : *cam);
+    for (bool& r : f->ran) r = false;
+    f->gbufPending = true;
+    // The pixel's two primary rays (centre ray here, jittered ray in rstr_restir_direct) share one tree walk when the
+    // next call on this frame is phase A with the same camera: the launch is deferred until then.  Anything else that
+    // looks at the G-buffer first (reads, halo exchange, gbuffer_update, sync, PTDirect) launches the plain kernel.
+    const bool sameRows = !f->renderHalo || f->bufRows == f->row1 - f->row0;
+    if (!f->fuse || !sameRows || f->sc->dev.traversal != RS_TRAVERSAL_FAST) return flushGBuffer(f);
+    return RSTR_OK;
+}
+
+int rstr_frame_set_fusion(RstrFrame* f, int enable) {
+    if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    int rc = flushGBuffer(f);
+    f->fuse = enable != 0;
+    return rc;
+}
+
 int rstr_gbuffer_update(RstrFrame* f, const RstrCamera* cam) {
     if (!f || !cam) return fail(RSTR_ERR_ARG, "null frame/camera");
+    int rc = flushGBuffer(f);
+    if (rc) return rc;
     f->lastCamera = *cam; f->haveLast = true; f->cur ^= 1;                // gbuffer.cu:75-78
     return RSTR_OK;
 }
@@ -443,6 +471,18 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     if (rc) return rc;
     if (!prm || prm->numCandidates < 0 || prm->numSpatial < 0 || prm->temporalCap < 1) return fail(RSTR_ERR_ARG, "bad RstrParams");
     FrameDev d = toFrameDev(f, f->row0, f->row1);
+    if (f->gbufPending && memcmp(cam, &f->pendCam, sizeof(RstrCamera)) == 0 && f->sc->dev.traversal == RS_TRAVERSAL_FAST) {
+        stageBegin(f, RSTR_T_RIS);
+        int n = launchGBufferRestirA(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, f->stream);
+        if (n > 0) {
+            f->gbufPending = false;
+            g_launches += n;
+            stageEnd(f, RSTR_T_RIS);
+            CU(cudaGetLastError());
+            return RSTR_OK;
+        }
+    }
+    if ((rc = flushGBuffer(f))) return rc;
     stageBegin(f, RSTR_T_RIS);
     g_launches += launchRestirA(f->sc->dev, d, toCamDev(*cam), *prm, looper, iter, f->first ? 1 : 0, f->stream);
     stageEnd(f, RSTR_T_RIS);
@@ -529,6 +569,7 @@ int rstr_restir_direct(RstrFrame* f, const RstrCamera* cam, const RstrParams* pr
 int rstr_pathtrace_direct(RstrFrame* f, const RstrCamera* cam, int looper, int iter) {
     int rc = checkCam(f, cam);
     if (rc) return rc;
+    if ((rc = flushGBuffer(f))) return rc;
     FrameDev d = toFrameDev(f, f->row0, f->row1);
     stageBegin(f, RSTR_T_PTDIRECT);
     g_launches += launchPTDirect(f->sc->dev, d, toCamDev(*cam), looper, iter, f->stream);
@@ -650,6 +691,8 @@ int rstr_frame_wait_host(RstrFrame* f, int slot) {
 
 int rstr_frame_sync(RstrFrame* f) {
     if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    int rc = flushGBuffer(f);
+    if (rc) return rc;
     CU(cudaStreamSynchronize(f->stream));
     return RSTR_OK;
 }
@@ -669,6 +712,10 @@ int rstr_frame_read_device(RstrFrame* f, int which, void* dev, size_t bytes) { r
 
 static int frameReadImpl(RstrFrame* f, int which, void* host, size_t bytes, bool toDevice) {
     if (!f || !host) return fail(RSTR_ERR_ARG, "rstr_frame_read: bad argument");
+    {
+        int rc = flushGBuffer(f);
+        if (rc) return rc;
+    }
     const size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
     size_t elem = 0;
     switch (which) {
@@ -753,6 +800,10 @@ int rstr_frame_halo_miss(RstrFrame* f, unsigned int* out) {
 int rstr_frame_plane_row(RstrFrame* f, int plane, int row, void** devPtr, size_t* rowBytes) {
     if (!f || !devPtr || !rowBytes) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: bad argument");
     if (row < f->bufRow0 || row > f->bufRow0 + f->bufRows) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: row not resident");
+    {
+        int rc = flushGBuffer(f);
+        if (rc) return rc;
+    }
     size_t off = (size_t)(row - f->bufRow0) * f->W;
     switch (plane) {
     case RSTR_PLANE_GEOM_CUR: *devPtr = f->geom[f->cur] + off; *rowBytes = (size_t)f->W * sizeof(float4); break;

@@ -187,6 +187,9 @@ struct Hit { float t, bx, by; int prim; };
 #ifndef RS_MINB_GBUF
 #define RS_MINB_GBUF 8      /* __launch_bounds__ minBlocks: 64 registers, 32 warps/SM (A/B on B200: -5 % vs uncapped 72) */
 #endif
+#ifndef RS_MINB_FUSED
+#define RS_MINB_FUSED 6     /* fused G-buffer + phase A kernel: 80 registers */
+#endif
 #ifndef RS_MINB_RESTIR
 #define RS_MINB_RESTIR 8    /* 64 registers instead of 94: -12 % on the 1M-triangle scene despite ~200 B of spills */
 #endif
@@ -412,6 +415,33 @@ RS_D int closestPop(ClosestState& st, const Stack& stack) {
     return RS_DONE;
 }
 
+// one triangle of a visited leaf offered to the ray's running result (best hit + its near ties)
+RS_D void closestOffer(ClosestState& st, const Tri& t) {
+    const RayT& r = st.r;
+    Cand x;
+    if (!triHit(r, t.v0, t.v1, t.v2, x.bx, x.by, x.d)) return;
+    if (!(x.d <= st.limit)) return;
+    if (!leafBox(r, t, x.tBox)) return;               // the reference never sees this triangle
+    x.prim = t.prim;
+    x.err = -1.f;
+    if (st.best.prim >= 0 && fabsf(x.d - st.best.d) <= RS_TIE_BAND * fmaxf(x.d, st.best.d)) {
+        x.err = triDistError(r, t.v0, t.v1, t.v2);
+        if (nearTie(x, st.best)) {
+            Cand keep = x;                      // the candidate that does not become `best`
+            if (x.d < st.best.d) { keep = st.best; st.best = x; st.limit = x.d * (1.f + 2.f * RS_TIE_BAND); }
+            if (st.second.prim < 0) st.second = keep;
+            else if (st.nExtra < RS_MAX_EXTRA) st.extra[st.nExtra++] = keep;
+            else st.triple = true;
+            return;
+        }
+    }
+    if (x.d < st.best.d) {
+        if (x.err < 0.f) x.err = triDistError(r, t.v0, t.v1, t.v2);
+        st.best = x; st.second.prim = -1; st.nExtra = 0; st.triple = false;     // anything near the old best is now irrelevant
+        st.limit = x.d * (1.f + 2.f * RS_TIE_BAND);
+    }
+}
+
 RS_D bool closestRun(const DevScene& s, ClosestState& st, Stack& stack, int minActive) {
     const RayF f = st.f;
     for (;;) {
@@ -446,33 +476,8 @@ RS_D bool closestRun(const DevScene& s, ClosestState& st, Stack& stack, int minA
         if (st.cur == RS_DONE) return true;
         // ---- leaf
         {
-            const RayT& r = st.r;
             int first = st.cur & 0x07ffffff, count = ((st.cur >> 27) & 7) + 1;
-            for (int i = 0; i < count; i++) {
-                Tri t = loadTriFast(s, first + i);
-                Cand x;
-                if (!triHit(r, t.v0, t.v1, t.v2, x.bx, x.by, x.d)) continue;
-                if (!(x.d <= st.limit)) continue;
-                if (!leafBox(r, t, x.tBox)) continue;               // the reference never sees this triangle
-                x.prim = t.prim;
-                x.err = -1.f;
-                if (st.best.prim >= 0 && fabsf(x.d - st.best.d) <= RS_TIE_BAND * fmaxf(x.d, st.best.d)) {
-                    x.err = triDistError(r, t.v0, t.v1, t.v2);
-                    if (nearTie(x, st.best)) {
-                        Cand keep = x;                      // the candidate that does not become `best`
-                        if (x.d < st.best.d) { keep = st.best; st.best = x; st.limit = x.d * (1.f + 2.f * RS_TIE_BAND); }
-                        if (st.second.prim < 0) st.second = keep;
-                        else if (st.nExtra < RS_MAX_EXTRA) st.extra[st.nExtra++] = keep;
-                        else st.triple = true;
-                        continue;
-                    }
-                }
-                if (x.d < st.best.d) {
-                    if (x.err < 0.f) x.err = triDistError(r, t.v0, t.v1, t.v2);
-                    st.best = x; st.second.prim = -1; st.nExtra = 0; st.triple = false;     // anything near the old best is now irrelevant
-                    st.limit = x.d * (1.f + 2.f * RS_TIE_BAND);
-                }
-            }
+            for (int i = 0; i < count; i++) closestOffer(st, loadTriFast(s, first + i));
         }
         st.cur = closestPop(st, stack);
         if (st.cur == RS_DONE) return true;
@@ -519,6 +524,57 @@ RS_D bool traceClosestFast(const DevScene& s, const RayT& r, Hit& h, Stack& stac
     closestRun(s, st, stack, 0);
     return closestResolve(s, st, h);
 }
+
+
+// Two rays of the same pixel (the G-buffer's centre ray and the ReSTIR kernel's jittered ray, gbuffer.cu:11-23 and
+// restir.cu:129) walked TOGETHER: a node is fetched once and tested against both, a child is entered when either ray
+// hits it, every triangle of a visited leaf is offered to both.  Each ray keeps its own result state, and what a ray
+// finds does not depend on which (conservative) boxes were entered on its behalf, so both results are exactly those
+// of two separate walks -- for about two thirds of the instructions and half of the dependent node fetches.
+#if !RS_BVH4
+RS_D void closestRunPair(const DevScene& s, ClosestState& a, ClosestState& b, Stack& stack) {
+    const RayF fa = a.f, fb = b.f;
+    int sp = 0;
+    int cur = (a.cur != RS_DONE || b.cur != RS_DONE) ? s.fastRoot : RS_DONE;
+    for (;;) {
+        while (cur >= 0 && cur != RS_DONE) {
+            const float4* np = s.fastNodes + 4 * (size_t)cur;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+            int2 l = __ldg((const int2*)(np + 3));
+            float tLa, tRa, tLb, tRb;
+            bool hLa = slabHit(fa, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, a.limit, tLa);
+            bool hRa = slabHit(fa, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, a.limit, tRa);
+            bool hLb = slabHit(fb, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, b.limit, tLb);
+            bool hRb = slabHit(fb, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, b.limit, tRb);
+            bool hL = hLa || hLb, hR = hRa || hRb;
+            float tL = fminf(hLa ? tLa : FLT_MAX, hLb ? tLb : FLT_MAX), tR = fminf(hRa ? tRa : FLT_MAX, hRb ? tRb : FLT_MAX);
+            if (hL && hR) {
+                bool leftNear = tL <= tR;
+                stack.push(sp, leftNear ? l.y : l.x, leftNear ? tR : tL); sp++;
+                cur = leftNear ? l.x : l.y;
+            } else if (hL) cur = l.x;
+            else if (hR) cur = l.y;
+            else {
+                cur = RS_DONE;
+                const float lim = fmaxf(a.limit, b.limit);
+                while (sp > 0) { --sp; if (stack.t(sp) <= lim) { cur = stack.ref(sp); break; } }
+            }
+        }
+        if (cur == RS_DONE) return;
+        {
+            int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            for (int i = 0; i < count; i++) {
+                Tri t = loadTriFast(s, first + i);
+                closestOffer(a, t);
+                closestOffer(b, t);
+            }
+        }
+        cur = RS_DONE;
+        const float lim = fmaxf(a.limit, b.limit);
+        while (sp > 0) { --sp; if (stack.t(sp) <= lim) { cur = stack.ref(sp); break; } }
+    }
+}
+#endif
 
 // any hit: order does not matter, the criterion above is exact per triangle
 RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& stack) {
@@ -939,9 +995,12 @@ RS_D Resv findTemporal(const FrameDev& f, size_t li, int idx) {
 
 // restir.cu:119-192 (+ :211-230 when spatial reuse is off) for one pixel; false = undecided, nothing written
 template <bool EXACT, bool SPATIAL>
+RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams& prm, int iter, int first,
+                          int x, int y, Stack& stack, Rng rng, f3 d, const Hit& h);
+
+template <bool EXACT, bool SPATIAL>
 RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& prm, int looper, int iter, int first,
                        int x, int y, Stack& stack) {
-    size_t li = planeIndex(f, x, y);
     int index = y * f.W + x;
     Rng rng;
     rng.seed(looper, index);
@@ -952,6 +1011,15 @@ RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, 
     RayT ray = makeRayT(o, d);
     Hit h;
     if (!traceClosest<EXACT>(s, ray, h, stack)) return false;
+    return restirAAfterHit<EXACT, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, d, h);
+}
+
+// restir.cu:133-192 (+ :211-230) once the jittered primary ray's hit is known
+template <bool EXACT, bool SPATIAL>
+RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams& prm, int iter, int first,
+                          int x, int y, Stack& stack, Rng rng, f3 d, const Hit& h) {
+    size_t li = planeIndex(f, x, y);
+    int index = y * f.W + x;
     int status = 0;      // 0 miss, 1 emitter, 2 shaded
     f3 pos, nrm;
     int matId = -1, type = 0;
@@ -1040,6 +1108,59 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_RESTIR) k_restir_a(const __g
     if (pixelOf(f, x, y) && !restirAPixel<EXACT, SPATIAL>(s, f, cam, prm, looper, iter, first, x, y, stack)) enqueuePixel(f, x, y);
     if (f.rowCost) accountBlock(f, &t0);
 }
+// G-buffer + phase A of one pixel in one kernel: the two primary rays of the pixel share one tree walk (closestRunPair)
+#if !RS_BVH4
+template <bool SPATIAL>
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_FUSED) k_gbuffer_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                               const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam,
+                                                               const __grid_constant__ RstrParams prm, int looper, int iter, int first) {
+    RS_DECLARE_STACK(stack);
+    __shared__ unsigned int t0;
+    if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
+    int x, y;
+    if (pixelOf(f, x, y)) {
+        Rng rng;
+        rng.seed(looper, y * f.W + x);
+        float r0 = rng.next(), r1 = rng.next();
+        rng.next(); rng.next();
+        f3 oC, dC, oJ, dJ;
+        cameraRay(cam, x, y, .5f, .5f, oC, dC);                                      // gbuffer.cu:11-23
+        cameraRay(cam, x, y, r0, r1, oJ, dJ);                                        // restir.cu:129
+        Hit hC, hJ;
+        bool ok;
+        {
+            ClosestState a, b;
+            a.r = makeRayT(oC, dC); b.r = makeRayT(oJ, dJ);
+            closestBegin(s, a); closestBegin(s, b);
+            closestRunPair(s, a, b, stack);
+            ok = closestResolve(s, a, hC);
+            ok = closestResolve(s, b, hJ) && ok;
+        }
+        if (ok) {
+            gbufferFinish(s, f, lastCam, x, y, oC, dC, hC);
+            ok = restirAAfterHit<false, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, dJ, hJ);
+        }
+        if (!ok) enqueuePixel(f, x, y);
+    }
+    if (f.rowCost) accountBlock(f, &t0);
+}
+// queued pixels: both stages again, with the reference-order walk
+template <bool SPATIAL>
+__global__ void __launch_bounds__(RS_BLOCK) k_gbuffer_restir_a_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                                   const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam,
+                                                                   const __grid_constant__ RstrParams prm, int looper, int iter, int first) {
+    RS_DECLARE_STACK(stack);
+    const unsigned n = *f.queueCount;
+    const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
+    for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
+        int idx = f.queue[i];
+        gbufferPixel<true>(s, f, cam, lastCam, idx % f.W, idx / f.W, stack);
+        restirAPixel<true, SPATIAL>(s, f, cam, prm, looper, iter, first, idx % f.W, idx / f.W, stack);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(s.fallbackRays + 0, n); atomicAdd(s.fallbackRays + 1, n); }
+}
+#endif
+
 template <bool SPATIAL>
 __global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                            const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
@@ -1291,6 +1412,23 @@ int launchRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const
         k_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
     }
     return 2;
+}
+// G-buffer + phase A in one launch (traced tree only); returns 0 when the build / traversal mode has no fused kernel
+int launchGBufferRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, const RstrParams& p, int looper, int iter, int first, cudaStream_t st) {
+#if RS_BVH4
+    return 0;
+#else
+    if (s.traversal == RS_TRAVERSAL_EXACT) return 0;
+    cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
+    if (p.reuse & 2) {
+        k_gbuffer_restir_a<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+        k_gbuffer_restir_a_fix<true><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+    } else {
+        k_gbuffer_restir_a<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+        k_gbuffer_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+    }
+    return 2;
+#endif
 }
 void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, const ResvD* src, ResvD* dst, int pass, int last, cudaStream_t st) {
     k_restir_b<<<pixelGrid(f), 128, 0, st>>>(s, f, p, iter, src, dst, pass, last);

@@ -54,6 +54,28 @@ def test_against_golden_fixtures(gpu, name):
         check(frames, want, reuse, "%s/%s vs golden" % (name, mode))
 
 
+@pytest.mark.parametrize("reuse", [0, 3])
+def test_fused_gbuffer_phase_a_equals_separate_kernels(gpu, port_oracle, reuse):
+    """One kernel walking the tree once for the pixel's two primary rays (default) == G-buffer kernel + phase-A kernel,
+    at 1080p on the 200k-triangle scene (every buffer, bit for bit), and both == the oracle on a small case."""
+    sd = scenes.procedural(1, 200000, 10000, (1920, 1080))
+    sc = gpu.Scene.from_arrays(sd)
+    fused, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=30.0, light_index=True, scene=sc, fuse=True)
+    split, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=30.0, light_index=True, scene=sc, fuse=False)
+    helpers.assert_frames_equal(fused, split, "fused vs separate kernels")
+    sc.close()
+    for sd in (scenes.cornell_box((160, 120), metal_tall_box=True), scenes.with_textures(scenes.procedural(3, 3000, 200, (160, 90)), env=False)):
+        want = helpers.run_oracle(port_oracle, sd, 3, reuse, radius=12.0, light_index=True)
+        for fuse in (True, False):
+            got, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=12.0, light_index=True, fuse=fuse)
+            for f in range(3):
+                for n in want[f]:
+                    if n in ("albedo", "radiance") and sd.textures:
+                        continue
+                    lim = int(np.ceil(MAX_TRIG_FLIP_FRACTION * want[f][n].shape[0])) if (reuse & 2) else 0
+                    assert helpers.mismatches(got[f][n], want[f][n]) <= lim, (sd.name, fuse, f, n)
+
+
 def test_reference_order_walk_mode(gpu, port_oracle):
     """RSTR traversal mode 1: every ray walks the reference tree in the reference's order (validation mode)."""
     for sd in (scenes.cornell_box((320, 240), metal_tall_box=True), scenes.procedural(1, 20000, 1000, (320, 180))):
