@@ -44,7 +44,7 @@ BYTES_PER_PIXEL = {0: 96, 1: 176, 2: 248, 3: 248}
 # ... split per kernel for the spatiotemporal frame: G-buffer write 36 | phase A: own G-buffer 24 + previous G-buffer 20 +
 # previous reservoir 36 + post-temporal reservoir 36 + history reservoir 36 = 152 | phase B: reservoir 36 + albedo 12 + radiance 12 = 60
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {("config2", "ris"): (372.6e6, "profiles/r01_prof_config2_r4.summary.txt")}
+NCU_TRAFFIC = {("config2", "ris"): (452.3e6, "profiles/r01_prof_config2_r5.summary.txt (k_gbuffer_restir_a: 66.0 MB read + 386.3 MB written)")}
 KERNEL_BYTES_PER_PIXEL = {"gbuffer": 36, "ris": {0: 60, 1: 140, 2: 116, 3: 152}, "spatial": 60}
 
 
@@ -319,9 +319,11 @@ def run_b200(args):
         fr.set_fusion(False)
 
     def frame(k):
-        # One frame of a strip: G-buffer and phase A on the strip's own rows; then ONE exchange carries the halo rows
-        # phase B reads (post-temporal reservoirs + the neighbours' G-buffer rows, unless those are rendered locally);
-        # the history reservoirs leave on a side stream and are joined just before the next frame's phase A.
+        # One frame of a strip: G-buffer and phase A on the strip's own rows (one fused kernel); then ONE exchange carries
+        # every halo row anybody needs: what phase B reads (post-temporal reservoirs + the neighbours' G-buffer rows,
+        # unless those are rendered locally) and the history reservoirs phase A just wrote, which the NEXT frame's
+        # temporal step reads (phase B does not modify them).  --split-exchange sends the history separately, after
+        # phase B, on a side stream (the first version).
         cam = base.orbit(orbit_index(k))
         fr.gbuffer_render(cam)
         if world == 1:
@@ -330,9 +332,11 @@ def run_b200(args):
             exchange.join()
             fr.restir_phase_a(cam, prm, k, 0)
             planes = ([] if args.render_halo else ["geom_cur", "matid_cur"]) + (["resv_temp"] if reuse & 2 else [])
+            if (reuse & 1) and not args.split_exchange:
+                planes.append("resv_out")
             exchange(planes)
             fr.restir_phase_b(cam, prm, k, 0)
-            if reuse & 1:
+            if (reuse & 1) and args.split_exchange:
                 exchange(["resv_history"], deferred=not args.no_overlap)
         fr.gbuffer_update(cam)
 
@@ -548,6 +552,7 @@ def main():
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
     ap.add_argument("--refine", type=int, default=4, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
     ap.add_argument("--no-fusion", action="store_true", help="separate G-buffer and phase-A kernels instead of the fused one (A/B)")
+    ap.add_argument("--split-exchange", action="store_true", help="N > 1: history reservoirs in a second exchange after phase B (A/B)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for the history-reservoir exchange at the end of the frame instead of under the next G-buffer")
     ap.add_argument("--render-halo", action="store_true", help="N > 1: every strip renders its G-buffer halo rows itself instead of receiving them from its neighbours")
     args = ap.parse_args()

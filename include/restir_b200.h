@@ -256,7 +256,10 @@ enum {
     RSTR_PLANE_MATID_CUR = 1,  /* int */
     RSTR_PLANE_RESV_HISTORY = 2, /* 32 B reservoirs written by the last restir_direct */
     RSTR_PLANE_RESV_TEMP = 3,  /* 32 B post-temporal reservoirs (input of spatial pass 1; published by even passes) */
-    RSTR_PLANE_RESV_TEMP2 = 4  /* 32 B reservoirs published by odd spatial passes (input of pass 2; spatialPasses > 1 only) */
+    RSTR_PLANE_RESV_TEMP2 = 4, /* 32 B reservoirs published by odd spatial passes (input of pass 2; spatialPasses > 1 only) */
+    RSTR_PLANE_RESV_OUT = 5    /* the history reservoirs THIS frame's phase A wrote (restir.cu:211-212; phase B does not touch them):
+                                  between phase A and phase B this is the plane RESV_HISTORY will name after phase B, so its halo
+                                  rows can travel in the same exchange as RESV_TEMP */
 };
 int rstr_frame_plane_row(RstrFrame*, int plane, int row, void** devPtr, size_t* rowBytes);
 /* copy rows [row0,row1) of `plane` from src to dst (same device or a peer device), ordered after the work queued on

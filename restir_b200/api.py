@@ -109,7 +109,7 @@ SCENE_ARRAYS = dict(boxes=0, mtbvh0=1, light_prim_ids=7, light_radiance=8, alias
 FRAME_BUFFERS = dict(albedo=0, normal=1, matid=2, depth=3, motion=4, radiance=5, reservoir=6, reservoir_temp=7,
                      light_index=8, ldr=9)
 STAGES = ("gbuffer", "ris", "spatial", "ptdirect", "tonemap")
-PLANES = dict(geom_cur=0, matid_cur=1, resv_history=2, resv_temp=3, resv_temp2=4)
+PLANES = dict(geom_cur=0, matid_cur=1, resv_history=2, resv_temp=3, resv_temp2=4, resv_out=5)
 
 _lib = None
 

@@ -810,6 +810,7 @@ int rstr_frame_plane_row(RstrFrame* f, int plane, int row, void** devPtr, size_t
     case RSTR_PLANE_MATID_CUR: *devPtr = f->matId[f->cur] + off; *rowBytes = (size_t)f->W * sizeof(int); break;
     case RSTR_PLANE_RESV_HISTORY: *devPtr = f->resv[f->resvOut ^ 1] + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
     case RSTR_PLANE_RESV_TEMP: *devPtr = f->resvTemp + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
+    case RSTR_PLANE_RESV_OUT: *devPtr = f->resv[f->resvOut] + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
     case RSTR_PLANE_RESV_TEMP2: {
         int rc = ensureTemp2(f);
         if (rc) return rc;

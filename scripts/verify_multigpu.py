@@ -47,9 +47,8 @@ for k in range(frames):
     fr.gbuffer_render(cam)
     exchange.join()
     fr.restir_phase_a(cam, prm, k, 0)
-    exchange(["geom_cur", "matid_cur", "resv_temp"])
+    exchange(["geom_cur", "matid_cur", "resv_temp", "resv_out"])      # one exchange per frame
     fr.restir_phase_b(cam, prm, k, 0)
-    exchange(["resv_history"], deferred=True)
     fr.gbuffer_update(cam)
     if full is not None:
         full.gbuffer_render(cam); full.restir_direct(cam, prm, k, 0); full.gbuffer_update(cam)
