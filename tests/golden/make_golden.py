@@ -3,7 +3,7 @@
 
     make -C oracle ref && python tests/golden/make_golden.py
 
-Outputs (small, committed): tests/golden/*.npz.  The reference ships no golden vectors of its own
+Outputs (small, committed): tests/golden/*.npz (image fixtures: tests/golden/make_images.py).  The reference ships no golden vectors of its own
 (SURVEY.md section 4); these pin the oracle restatement and, through it, the CUDA path.
 """
 import ctypes as C
@@ -95,14 +95,32 @@ def textured_scene_file(ref):
         file_names=np.array(list(files.keys())), file_texts=np.array(list(files.values())), **d)
 
 
+def multipass(ref):
+    """8. two and three spatial passes (restir.cu:201-209, the block the reference ships commented out, driven through
+    the reference's own Reservoir::preClampedMerge<4> by the harness)"""
+    d = {}
+    for name in ("cornell_metal", "gen2000"):
+        sd = helpers.test_scenes()[name]
+        for passes in (2, 3):
+            frames = helpers.run_oracle(ref, sd, 3, 3, radius=12.0, passes=passes, want=("radiance", "reservoir", "reservoir_temp"))
+            for f, bufs in enumerate(frames):
+                for n, a in bufs.items():
+                    d["%s_p%d_f%d_%s" % (name, passes, f, n)] = a.view(np.uint8).reshape(a.shape[0], -1) if a.dtype.fields else a
+    np.savez_compressed(os.path.join(HERE, "frames_multipass.npz"), **d)
+
+
 def main():
     ref = Oracle("reference")
+    if "--only-multipass" in sys.argv:
+        multipass(ref)
+        return
     if "--only-textured" in sys.argv:
         textured(ref)
         textured_scene_file(ref)
         return
     textured_scene_file(ref)
     textured(ref)
+    multipass(ref)
     # 1. RNG, alias known answers
     rng = {"l%d_i%d" % (l, i): ref.rng_draws(l, i, 8) for l, i in ((7, 12345), (0, 0), (59, 2073599), (1023, 8294399))}
     alias, total = ref.alias_build([1, 2, 3, 10])

@@ -156,3 +156,16 @@ def test_textured_frames_match_golden(port_oracle, name):
         li = helpers.run_oracle(port_oracle, sd, 1, 0, light_index=True)[0]["light_index"]
         assert (li >= L - 1).sum() > 20          # reservoirs holding an environment-map texel
         assert (frames[0]["matid"] == -1).sum() > 100 and frames[0]["radiance"][frames[0]["matid"] == -1].max() > 0
+
+
+@pytest.mark.parametrize("name", ["cornell_metal", "gen2000"])
+def test_multi_pass_frames_match_golden(port_oracle, name):
+    """Two and three spatial passes (BASELINE config 5; restir.cu:201-209 with preClampedMerge<4>): restatement against
+    the fixture the reference harness produced."""
+    sd = helpers.test_scenes()[name]
+    g = np.load(os.path.join(G, "frames_multipass.npz"))
+    for passes in (2, 3):
+        frames = helpers.run_oracle(port_oracle, sd, 3, 3, radius=12.0, passes=passes, want=("radiance", "reservoir", "reservoir_temp"))
+        for f, bufs in enumerate(frames):
+            for n, a in bufs.items():
+                assert helpers.mismatches(a, g["%s_p%d_f%d_%s" % (name, passes, f, n)]) == 0, (passes, f, n)
