@@ -136,7 +136,7 @@ def test_multi_pass_spatial(gpu, port_oracle, passes, k):
         got, _ = helpers.run_gpu(gpu, sd, 3, 3, radius=12.0, k=k, passes=passes, light_index=True)
         want = helpers.run_oracle(port_oracle, sd, 3, 3, radius=12.0, k=k, passes=passes, light_index=True)
         check(got, want, 3, "passes=%d %s" % (passes, sd.name))
-    if passes in (2, 3) and k == 5:      # the reference-generated fixture (tests/golden/frames_multipass.npz)
+    if passes in (2, 3):                 # the reference-generated fixture (tests/golden/frames_multipass.npz)
         g = np.load(os.path.join(G, "frames_multipass.npz"))
         for name in ("cornell_metal", "gen2000"):
             got, _ = helpers.run_gpu(gpu, helpers.test_scenes()[name], 3, 3, radius=12.0, passes=passes, want=("radiance", "reservoir", "reservoir_temp"))
