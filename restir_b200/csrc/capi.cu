@@ -228,7 +228,12 @@ int rstr_scene_load_file(const char* path, RstrScene** out, RstrCamera* cameraOu
     RstrCamera cam;
     memset(&cam, 0, sizeof cam);
     std::string err;
-    if (!loadSceneFile(path, sc->hs, cam, err)) { delete sc; return fail(RSTR_ERR_IO, err); }
+    try {
+        if (!loadSceneFile(path, sc->hs, cam, err)) { delete sc; return fail(RSTR_ERR_IO, err); }
+    } catch (const std::exception& e) {
+        delete sc;
+        return fail(RSTR_ERR_IO, std::string("rstr_scene_load_file: ") + e.what());
+    }
     if (cameraOut) *cameraOut = cam;
     return finishScene(sc, out);
 }
@@ -615,7 +620,11 @@ int rstr_image_load(const char* path, int flipY, int* width, int* height, float*
     if (!path || !width || !height) return fail(RSTR_ERR_ARG, "rstr_image_load: bad argument");
     HostTexture t;
     std::string err;
-    if (!loadImageRGB(path, flipY != 0, t, err)) return fail(RSTR_ERR_IO, err);
+    try {
+        if (!loadImageRGB(path, flipY != 0, t, err)) return fail(RSTR_ERR_IO, err);
+    } catch (const std::exception& e) {
+        return fail(RSTR_ERR_IO, std::string("rstr_image_load: ") + e.what());
+    }
     *width = t.w; *height = t.h;
     if (rgbOut) {
         if (capacityBytes < t.rgb.size() * 12) return fail(RSTR_ERR_ARG, "rstr_image_load: buffer too small");

@@ -176,6 +176,7 @@ bool decodePNG(const std::vector<uint8_t>& file, int& W, int& H, std::vector<uin
         pos += 12 + (size_t)len;
     }
     if (!haveHdr || W <= 0 || H <= 0) { err = "PNG without a valid IHDR"; return false; }
+    if ((size_t)W * H > idat.size() * 1100 + 1024) { err = "PNG header claims more pixels than its data can hold"; return false; }   // deflate: <= 1032x
     if (interlace) { err = "interlaced PNGs are not supported"; return false; }
     int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!channels || !(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4))) || (ctype == 3 && depth == 16)) {
@@ -267,6 +268,7 @@ bool decodeHDR(const std::vector<uint8_t>& f, int& W, int& H, std::vector<f3>& p
     if (strncmp(end, "+X ", 3) != 0) { err = "unsupported HDR data layout"; return false; }
     W = (int)strtol(end + 3, nullptr, 10);
     if (W <= 0 || H <= 0) { err = "bad HDR size"; return false; }
+    if ((size_t)W * H > f.size() * 128) { err = "HDR header claims more pixels than the file can hold"; return false; }   // RLE: <= 64 px per 2 bytes per channel
     px.resize((size_t)W * H);
     auto flat = [&](size_t firstPixel) {
         for (size_t i = firstPixel; i < (size_t)W * H; i++) {

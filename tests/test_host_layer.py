@@ -265,3 +265,32 @@ def test_traced_tree_is_a_valid_bvh(name):
             stack.append((int(child), (lo, hi)))
     assert (seen == 1).all()
     sc.close()
+
+
+def test_image_loader_rejects_damaged_files_without_crashing():
+    """Truncated / bit-flipped PNG and HDR files (texture files are external input): an error, or a decoded image, never a
+    crash or an allocation sized by a lying header (scripts/fuzz_image_loader.py runs the long version)."""
+    import random
+    rnd = random.Random(7)
+    src = os.path.join(helpers.GOLDEN, "images")
+    files = [open(os.path.join(src, f), "rb").read() for f in sorted(os.listdir(src))]
+    p = os.path.join(tempfile.mkdtemp(), "f.bin")
+    outcomes = {"ok": 0, "rejected": 0}
+    for it in range(400):
+        b = bytearray(rnd.choice(files))
+        if it % 3 == 0:
+            b = b[:rnd.randrange(0, len(b))]
+        else:
+            for _ in range(rnd.randrange(1, 6)):
+                b[rnd.randrange(len(b))] = rnd.randrange(256)
+        open(p, "wb").write(b)
+        try:
+            a = rb.load_image(p, bool(it & 1))
+            assert a.ndim == 3 and a.shape[2] == 3
+            outcomes["ok"] += 1
+        except rb.RestirError:
+            outcomes["rejected"] += 1
+    assert outcomes["ok"] > 0 and outcomes["rejected"] > 0
+    open(p, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 100000 +X 100000\n" + b"\x02\x02\x01\x86" * 10)
+    with pytest.raises(rb.RestirError):
+        rb.load_image(p)
