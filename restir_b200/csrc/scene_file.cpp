@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <fstream>
+#include <limits>
 #include <map>
 #include <sstream>
 
@@ -224,11 +225,74 @@ bool fixIndex(int idx, int n, int* out) {                       // tiny_obj_load
     return true;
 }
 
+
+struct Idx { int v, vt, vn; };     // one corner of an OBJ face: position / texcoord / normal index (0-based, -1 = absent)
+
+// Polygons with five or more corners, as tinyobj's built-in ear clipping splits them (tiny_obj_loader.h:1536-1821,
+// v2.0 without TINYOBJLOADER_USE_MAPBOX_EARCUT): project on the two axes orthogonal-ish to the first non-degenerate
+// corner's normal, then repeatedly cut the corner at `guess` when it is convex w.r.t. the (origin-based) area sign and
+// no other corner lies inside it (pnpoly, :1388-1398); give up after a full fruitless round.  The emitted corner order
+// fixes the flattened primitive order, hence everything downstream (BVH, light list): it has to be reproduced exactly.
+static bool pointInTri(const float* vx, const float* vy, float tx, float ty) {
+    bool c = false;
+    for (int i = 0, j = 2; i < 3; j = i++)
+        if (((vy[i] > ty) != (vy[j] > ty)) && (tx < (vx[j] - vx[i]) * (ty - vy[i]) / (vy[j] - vy[i]) + vx[i])) c = !c;
+    return c;
+}
+static bool earClip(const std::vector<Idx>& face, const std::vector<float>& V, std::vector<Idx>& tri) {
+    const size_t n0 = face.size();
+    for (const Idx& ix : face)
+        if (ix.v < 0 || 3 * (size_t)ix.v + 2 >= V.size()) return false;
+    size_t axes[2] = {1, 2};
+    for (size_t k = 0; k < n0; ++k) {
+        const float* p0 = &V[3 * face[k % n0].v]; const float* p1 = &V[3 * face[(k + 1) % n0].v]; const float* p2 = &V[3 * face[(k + 2) % n0].v];
+        float e0x = p1[0] - p0[0], e0y = p1[1] - p0[1], e0z = p1[2] - p0[2];
+        float e1x = p2[0] - p1[0], e1y = p2[1] - p1[1], e1z = p2[2] - p1[2];
+        float cx = fabsf(e0y * e1z - e0z * e1y), cy = fabsf(e0z * e1x - e0x * e1z), cz = fabsf(e0x * e1y - e0y * e1x);
+        const float eps = std::numeric_limits<float>::epsilon();
+        if (cx > eps || cy > eps || cz > eps) {
+            if (!(cx > cy && cx > cz)) {
+                axes[0] = 0;
+                if (cz > cx && cz > cy) axes[1] = 1;
+            }
+            break;
+        }
+    }
+    std::vector<Idx> rest = face;
+    size_t guess = 0, budget = n0, prevCount = rest.size();
+    while (rest.size() > 3 && budget > 0) {
+        const size_t n = rest.size();
+        if (guess >= n) guess -= n;
+        if (prevCount != n) { prevCount = n; budget = n; }
+        else budget--;
+        Idx ind[3];
+        float vx[3], vy[3];
+        for (int k = 0; k < 3; k++) {
+            ind[k] = rest[(guess + k) % n];
+            vx[k] = V[3 * ind[k].v + axes[0]];
+            vy[k] = V[3 * ind[k].v + axes[1]];
+        }
+        float e0x = vx[1] - vx[0], e0y = vy[1] - vy[0], e1x = vx[2] - vx[1], e1y = vy[2] - vy[1];
+        float cross = e0x * e1y - e0y * e1x;
+        float area = (vx[0] * vy[1] - vy[0] * vx[1]) * 0.5f;
+        if (cross * area < 0.0f) { guess += 1; continue; }
+        bool overlap = false;
+        for (size_t other = 3; other < n; ++other) {
+            const Idx& o = rest[(guess + other) % n];
+            if (pointInTri(vx, vy, V[3 * o.v + axes[0]], V[3 * o.v + axes[1]])) { overlap = true; break; }
+        }
+        if (overlap) { guess += 1; continue; }
+        tri.push_back(ind[0]); tri.push_back(ind[1]); tri.push_back(ind[2]);
+        rest.erase(rest.begin() + (guess + 1) % n);
+    }
+    if (rest.size() == 3) { tri.push_back(rest[0]); tri.push_back(rest[1]); tri.push_back(rest[2]); }
+    return true;
+}
+
 bool loadOBJ(const std::string& path, Mesh& mesh, std::string& err) {
     std::ifstream in(path.c_str());
     if (!in.is_open()) { err = "cannot open OBJ file " + path; return false; }
     std::vector<float> V, N, TC;
-    struct Idx { int v, vt, vn; };
     std::string line;
     while (safeGetline(in, line)) {
         const char* tok = line.c_str();
@@ -286,7 +350,7 @@ bool loadOBJ(const std::string& path, Mesh& mesh, std::string& err) {
                 if (sqr02 < sqr13) tri = {face[0], face[1], face[2], face[0], face[2], face[3]};
                 else tri = {face[0], face[1], face[3], face[1], face[2], face[3]};
             } else if (face.size() < 3) continue;
-            else { err = "OBJ polygons with more than 4 vertices are not supported: " + path; return false; }
+            else if (!earClip(face, V, tri)) { err = "OBJ polygon references a vertex that does not exist: " + path; return false; }
             for (const Idx& ix : tri) {
                 if (ix.v < 0 || 3 * ix.v + 2 >= (int)V.size()) { err = "OBJ vertex index out of range in " + path; return false; }
                 if (ix.vn < 0 || 3 * ix.vn + 2 >= (int)N.size()) { err = "OBJ faces need normals (scene.cpp:44): " + path; return false; }

@@ -109,8 +109,49 @@ def multipass(ref):
     np.savez_compressed(os.path.join(HERE, "frames_multipass.npz"), **d)
 
 
+def ngons(ref):
+    """9. OBJ polygons with 5..11 corners (tinyobj's built-in ear clipping, tiny_obj_loader.h:1536-1821): convex, star-shaped,
+    clockwise, non-planar, with a duplicated corner, in all three projection-axis classes"""
+    rs = np.random.RandomState(5)
+    tmp = tempfile.mkdtemp()
+    lines, faces, nv = [], [], 0
+    for trial in range(24):
+        n = rs.randint(5, 12)
+        ang = np.sort(rs.rand(n)) * 2 * np.pi
+        rad = 0.3 + rs.rand(n) * (1.5 if trial % 3 else 0.2)
+        u, v = np.cos(ang) * rad, np.sin(ang) * rad
+        if trial % 5 == 0:
+            u, v = u[::-1], v[::-1]
+        w = rs.randn(n) * (0.0 if trial % 2 else 0.05)
+        pts = {0: np.stack([u, v, w], 1), 1: np.stack([w, u, v], 1), 2: np.stack([u, w, v], 1), 3: np.stack([u + v * 0.3, v, u * 0.5 + w], 1)}[trial % 4].astype(np.float32)
+        if trial % 7 == 0:
+            pts[1] = pts[0]
+        pts = pts + np.float32(3.0) * np.array([trial % 6, trial // 6, 0], np.float32)
+        lines += ["v %r %r %r" % tuple(float(x) for x in p) for p in pts]
+        faces.append("f " + " ".join("%d//%d" % (nv + i + 1, 1 + (i & 1)) for i in range(n)))
+        nv += n
+    open(os.path.join(tmp, "ngons.obj"), "w").write("\n".join(lines + ["vn 0 0 1", "vn 0 1 0"] + faces) + "\n")
+    open(os.path.join(tmp, "ngons.txt"), "w").write(
+        "Material m\nType Lambertian\nBaseColor 0.5 0.5 0.5\nMetallic 0\nRoughness 1\nIor 1.5\nNormalMap Null\n\nObject 0\nngons.obj\nMaterial m\n"
+        "Translate 0 0 0\nRotate 0 0 0\nScale 1 1 1\n\nCamera\nResolution 32 32\nFovY 20\nLensRadius 0\nFocalDist 1\nApertureMask Null\nSample 1\n"
+        "Depth 1\nFile x\nEye 0 0 5\nRotation -90 0 0\nUp 0 1 0\n\nEnvMap Null\n")
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    rs_ = ref.lib.ref_scene_load_file(b"ngons.txt")
+    os.chdir(cwd)
+    T = ref.lib.ref_scene_num_tris(rs_)
+    files = {f: open(os.path.join(tmp, f)).read() for f in ("ngons.txt", "ngons.obj")}
+    np.savez_compressed(os.path.join(HERE, "scene_file_ngons.npz"),
+                        vertices=Oracle._view(ref.lib.ref_scene_array(rs_, 0), np.float32, (3 * T, 3)),
+                        normals=Oracle._view(ref.lib.ref_scene_array(rs_, 1), np.float32, (3 * T, 3)),
+                        file_names=np.array(list(files.keys())), file_texts=np.array(list(files.values())))
+
+
 def main():
     ref = Oracle("reference")
+    if "--only-ngons" in sys.argv:
+        ngons(ref)
+        return
     if "--only-multipass" in sys.argv:
         multipass(ref)
         return
@@ -121,6 +162,7 @@ def main():
     textured_scene_file(ref)
     textured(ref)
     multipass(ref)
+    ngons(ref)
     # 1. RNG, alias known answers
     rng = {"l%d_i%d" % (l, i): ref.rng_draws(l, i, 8) for l, i in ((7, 12345), (0, 0), (59, 2073599), (1023, 8294399))}
     alias, total = ref.alias_build([1, 2, 3, 10])

@@ -294,3 +294,18 @@ def test_image_loader_rejects_damaged_files_without_crashing():
     open(p, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 100000 +X 100000\n" + b"\x02\x02\x01\x86" * 10)
     with pytest.raises(rb.RestirError):
         rb.load_image(p)
+
+
+def test_obj_polygons_are_split_like_the_reference_loader():
+    """OBJ faces with 5-11 corners: the reference's tinyobj ear-clips them (tiny_obj_loader.h:1536-1821); the corner order it
+    emits fixes the flattened primitive order.  24 polygons (convex, concave, clockwise, non-planar, duplicated corner, all
+    projection-axis classes) against the reference parser's output."""
+    g = np.load(os.path.join(G, "scene_file_ngons.npz"))
+    tmp = tempfile.mkdtemp()
+    for n, t in zip(g["file_names"], g["file_texts"]):
+        open(os.path.join(tmp, str(n)), "w").write(str(t))
+    sc = rb.Scene.from_file(os.path.join(tmp, "ngons.txt"))
+    assert sc.info.numTris == g["vertices"].shape[0] // 3 > 24 * 3
+    assert np.array_equal(sc.read("vertices").view(np.uint32), g["vertices"].view(np.uint32))
+    assert np.array_equal(sc.read("normals").view(np.uint32), g["normals"].view(np.uint32))
+    sc.close()
