@@ -4,8 +4,8 @@
 // (image.cpp:16-33, scene.cpp:97-98): 8-bit images become v / 255.0f, Radiance .hdr files are decoded from RGBE,
 // rows are flipped vertically for material textures and kept for the environment map (scene.cpp:98, 124-126).
 // stb_image is a third-party single-header dependency of the reference (external/include/stb_image.h, v2.x); this
-// file restates the two formats the scenes use -- PNG (RFC 2083 + RFC 1950/1951 inflate) and Radiance RGBE -- and
-// is pinned against stb itself through oracle/ref_harness.cpp (ref_image_load) on the committed fixtures.
+// file restates the formats scenes use -- PNG (RFC 2083 + RFC 1950/1951 inflate), Radiance RGBE, and JPEG (image_jpeg.cpp) --
+// and is pinned against stb itself through oracle/ref_harness.cpp (ref_image_load) on the committed fixtures.
 // Writing: Image::savePNG (image.cpp:41-57) stores 8-bit RGB; here as a valid PNG with stored deflate blocks.
 #include <math.h>
 #include <stdint.h>
@@ -19,6 +19,8 @@
 #include "scene_host.h"
 
 namespace rs {
+
+bool decodeJPEG(const std::vector<uint8_t>& file, int& W, int& H, std::vector<uint8_t>& rgb, std::string& err);   // image_jpeg.cpp
 
 namespace {
 
@@ -352,10 +354,15 @@ bool loadImageRGB(const std::string& path, bool flipY, HostTexture& out, std::st
         if (!decodePNG(file, W, H, rgb, err)) { err = path + ": " + err; return false; }
         px.resize((size_t)W * H);
         for (size_t i = 0; i < px.size(); i++) px[i] = mk3(rgb[3 * i] / 255.0f, rgb[3 * i + 1] / 255.0f, rgb[3 * i + 2] / 255.0f);   // stbi__ldr_to_hdr, gamma 1
-    } else if (file.size() >= 7 && (!memcmp(file.data(), "#?RADIANCE", 10) || !memcmp(file.data(), "#?RGBE", 6))) {
+    } else if (file.size() >= 4 && file[0] == 0xff && file[1] == 0xd8) {
+        std::vector<uint8_t> rgb;
+        if (!decodeJPEG(file, W, H, rgb, err)) { err = path + ": " + err; return false; }
+        px.resize((size_t)W * H);
+        for (size_t i = 0; i < px.size(); i++) px[i] = mk3(rgb[3 * i] / 255.0f, rgb[3 * i + 1] / 255.0f, rgb[3 * i + 2] / 255.0f);
+    } else if (file.size() >= 11 && (!memcmp(file.data(), "#?RADIANCE", 10) || !memcmp(file.data(), "#?RGBE", 6))) {
         if (!decodeHDR(file, W, H, px, err)) { err = path + ": " + err; return false; }
     } else {
-        err = path + ": unsupported image format (PNG and Radiance .hdr are supported)";
+        err = path + ": unsupported image format (PNG, JPEG and Radiance .hdr are supported)";
         return false;
     }
     if (flipY)

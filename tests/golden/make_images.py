@@ -1,5 +1,5 @@
 """Writes the small image fixtures (PNG of every supported colour type / bit depth / row filter, Radiance .hdr flat and
-RLE) and records what THE REFERENCE'S loader (stb_image through Image::Image, oracle/_ref/libref_harness.so) returns
+RLE, JPEG baseline / progressive with the usual chroma layouts) and records what THE REFERENCE'S loader (stb_image through Image::Image, oracle/_ref/libref_harness.so) returns
 for each, flipped and unflipped -> tests/golden/images/*, tests/golden/images.npz.  Build container only."""
 import ctypes as C
 import os
@@ -110,6 +110,24 @@ def make_files():
     write_hdr(os.path.join(IMG, "env_rle.hdr"), e, True)
     write_hdr(os.path.join(IMG, "env_flat.hdr"), e, False)
     write_hdr(os.path.join(IMG, "narrow_flat.hdr"), e[:, :5].copy(), False)
+    # JPEG: baseline / progressive, 4:4:4 / 4:2:2 / 4:2:0 / 4:1:1 / 4:4:0, optimised Huffman tables, restart markers, grey,
+    # RGB-tagged components (written with Pillow and OpenCV, which are in the build image)
+    from PIL import Image
+    import cv2
+    pic = np.clip(smooth(29, 37, 3).astype(int) + (((np.mgrid[0:29, 0:37][1] // 5) % 2) * 60)[..., None], 0, 255).astype(np.uint8)
+    P = lambda name, arr, **kw: Image.fromarray(arr).save(os.path.join(IMG, name), "JPEG", **kw)
+    P("base444_q90.jpg", pic, quality=90, subsampling=0)
+    P("base422_q60_opt.jpg", pic, quality=60, subsampling=1, optimize=True)
+    P("base420_q75_rst.jpg", pic, quality=75, subsampling=2, restart_marker_blocks=2)
+    P("prog420_q80.jpg", pic, quality=80, subsampling=2, progressive=True)
+    P("prog444_q35.jpg", pic[:13, :9].copy(), quality=35, subsampling=0, progressive=True)
+    P("gray_q70.jpg", pic[..., 1].copy(), quality=70)
+    P("rgb_tagged_q85.jpg", pic, quality=85, subsampling=0, keep_rgb=True)
+    P("one_pixel.jpg", pic[:1, :1].copy(), quality=95)
+    cv2.imwrite(os.path.join(IMG, "cv411_rst.jpg"), pic, [cv2.IMWRITE_JPEG_QUALITY, 70, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                                         cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411, cv2.IMWRITE_JPEG_RST_INTERVAL, 2])
+    cv2.imwrite(os.path.join(IMG, "cv440_prog.jpg"), pic, [cv2.IMWRITE_JPEG_QUALITY, 50, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                                          cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
 
 
 def main():

@@ -167,10 +167,11 @@ def test_texture_ids_are_validated():
 
 
 def test_image_loader_matches_reference_loader():
-    """PNG (every colour type / bit depth / row filter, split IDAT, stored / fixed / dynamic deflate blocks) and Radiance
+    """PNG (every colour type / bit depth / row filter, split IDAT, stored / fixed / dynamic deflate blocks), JPEG (baseline /
+    progressive, five chroma layouts, restart markers, grey, RGB-tagged) and Radiance
     .hdr (RLE and flat) against what the reference's loader (stb_image via Image::Image) returned, bit for bit."""
     g = np.load(os.path.join(helpers.GOLDEN, "images.npz"))
-    assert len(g.files) == 34
+    assert len(g.files) == 54
     for key in g.files:
         name, flip = key.rsplit("_flip", 1)
         a = rb.load_image(os.path.join(helpers.GOLDEN, "images", name), bool(int(flip)))
