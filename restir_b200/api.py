@@ -444,7 +444,7 @@ class Frame:
 
 
 def load_image(path: str, flip: bool = True) -> np.ndarray:
-    """Image::Image(filename) (image.cpp:16-33): PNG / Radiance .hdr -> (H, W, 3) f32; host only."""
+    """Image::Image(filename) (image.cpp:16-33): PNG / JPEG / Radiance .hdr -> (H, W, 3) f32; host only."""
     w, h = C.c_int(0), C.c_int(0)
     _check(lib().rstr_image_load(path.encode(), 1 if flip else 0, C.addressof(w), C.addressof(h), None, 0))
     out = np.zeros((h.value, w.value, 3), np.float32)
