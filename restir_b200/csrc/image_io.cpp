@@ -179,55 +179,68 @@ bool decodePNG(const std::vector<uint8_t>& file, int& W, int& H, std::vector<uin
     }
     if (!haveHdr || W <= 0 || H <= 0) { err = "PNG without a valid IHDR"; return false; }
     if ((size_t)W * H > idat.size() * 1100 + 1024) { err = "PNG header claims more pixels than its data can hold"; return false; }   // deflate: <= 1032x
-    if (interlace) { err = "interlaced PNGs are not supported"; return false; }
     int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!channels || !(depth == 8 || depth == 16 || ((ctype == 0 || ctype == 3) && (depth == 1 || depth == 2 || depth == 4))) || (ctype == 3 && depth == 16)) {
         err = "unsupported PNG colour type / bit depth"; return false;
     }
+    if (interlace > 1) { err = "PNG: unknown interlace method"; return false; }
     std::vector<uint8_t> raw;
     if (!inflateZlib(idat, raw, err)) { err = "PNG: " + err; return false; }
-    const size_t rowBytes = ((size_t)W * channels * depth + 7) / 8;
+    rgb.assign((size_t)W * H * 3, 0);
     const int bpp = (channels * depth + 7) / 8;
-    if (raw.size() < (rowBytes + 1) * (size_t)H) { err = "PNG: not enough pixel data"; return false; }
-    std::vector<uint8_t> img(rowBytes * H);
-    for (int y = 0; y < H; y++) {                                   // RFC 2083 section 6: the five row filters
-        const uint8_t* src = &raw[(rowBytes + 1) * y];
-        uint8_t* cur = &img[rowBytes * y];
-        const uint8_t* up = y ? cur - rowBytes : nullptr;
-        int ft = src[0];
-        if (ft > 4) { err = "PNG: bad filter"; return false; }
-        for (size_t i = 0; i < rowBytes; i++) {
-            int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)bpp) ? up[i - bpp] : 0;
-            int pred = ft == 0 ? 0 : ft == 1 ? a : ft == 2 ? b : ft == 3 ? ((a + b) >> 1) : paeth(a, b, c);
-            cur[i] = (uint8_t)(src[1 + i] + pred);
-        }
-    }
-    rgb.resize((size_t)W * H * 3);
     const int stride = depth == 16 ? 2 : 1;                          // 16-bit samples: the high byte (stb: >> 8)
-    for (int y = 0; y < H; y++) {
-        const uint8_t* row = &img[rowBytes * y];
-        for (int x = 0; x < W; x++) {
-            uint8_t* o = &rgb[((size_t)y * W + x) * 3];
-            if (depth < 8) {
-                int perByte = 8 / depth, shift = (perByte - 1 - x % perByte) * depth;
-                int v = (row[x / perByte] >> shift) & ((1 << depth) - 1);
-                if (ctype == 3) {
-                    if ((size_t)v * 3 + 2 >= palette.size()) { err = "PNG: palette index out of range"; return false; }
-                    o[0] = palette[v * 3]; o[1] = palette[v * 3 + 1]; o[2] = palette[v * 3 + 2];
-                } else {
-                    int g = v * (depth == 1 ? 0xff : depth == 2 ? 0x55 : 0x11);
-                    o[0] = o[1] = o[2] = (uint8_t)g;
-                }
-                continue;
+    // one pass = a sub-image of its own scanlines and filter bytes (RFC 2083 section 2.6): the whole image, or the
+    // seven Adam7 passes {x0, y0, dx, dy}
+    static const int adam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    static const int whole[1][4] = {{0, 0, 1, 1}};
+    const int (*passes)[4] = interlace ? adam7 : whole;
+    size_t rawPos = 0;
+    std::vector<uint8_t> img;
+    for (int pass = 0; pass < (interlace ? 7 : 1); pass++) {
+        const int x0 = passes[pass][0], y0 = passes[pass][1], dx = passes[pass][2], dy = passes[pass][3];
+        const int pw = (W - x0 + dx - 1) / dx, ph = (H - y0 + dy - 1) / dy;
+        if (pw <= 0 || ph <= 0) continue;
+        const size_t rowBytes = ((size_t)pw * channels * depth + 7) / 8;
+        if (raw.size() < rawPos + (rowBytes + 1) * (size_t)ph) { err = "PNG: not enough pixel data"; return false; }
+        img.assign(rowBytes * ph, 0);
+        for (int y = 0; y < ph; y++) {                               // RFC 2083 section 6: the five row filters
+            const uint8_t* src = &raw[rawPos + (rowBytes + 1) * y];
+            uint8_t* cur = &img[rowBytes * y];
+            const uint8_t* up = y ? cur - rowBytes : nullptr;
+            int ft = src[0];
+            if (ft > 4) { err = "PNG: bad filter"; return false; }
+            for (size_t i = 0; i < rowBytes; i++) {
+                int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= (size_t)bpp) ? up[i - bpp] : 0;
+                int pred = ft == 0 ? 0 : ft == 1 ? a : ft == 2 ? b : ft == 3 ? ((a + b) >> 1) : paeth(a, b, c);
+                cur[i] = (uint8_t)(src[1 + i] + pred);
             }
-            const uint8_t* p = row + (size_t)x * channels * stride;
-            switch (ctype) {
-            case 0: case 4: o[0] = o[1] = o[2] = p[0]; break;
-            case 2: case 6: o[0] = p[0]; o[1] = p[stride]; o[2] = p[2 * stride]; break;
-            case 3:
-                if ((size_t)p[0] * 3 + 2 >= palette.size()) { err = "PNG: palette index out of range"; return false; }
-                o[0] = palette[p[0] * 3]; o[1] = palette[p[0] * 3 + 1]; o[2] = palette[p[0] * 3 + 2];
-                break;
+        }
+        rawPos += (rowBytes + 1) * (size_t)ph;
+        for (int y = 0; y < ph; y++) {
+            const uint8_t* row = &img[rowBytes * y];
+            for (int x = 0; x < pw; x++) {
+                uint8_t* o = &rgb[((size_t)(y0 + y * dy) * W + (x0 + x * dx)) * 3];
+                if (depth < 8) {
+                    int perByte = 8 / depth, shift = (perByte - 1 - x % perByte) * depth;
+                    int v = (row[x / perByte] >> shift) & ((1 << depth) - 1);
+                    if (ctype == 3) {
+                        if ((size_t)v * 3 + 2 >= palette.size()) { err = "PNG: palette index out of range"; return false; }
+                        o[0] = palette[v * 3]; o[1] = palette[v * 3 + 1]; o[2] = palette[v * 3 + 2];
+                    } else {
+                        int g = v * (depth == 1 ? 0xff : depth == 2 ? 0x55 : 0x11);
+                        o[0] = o[1] = o[2] = (uint8_t)g;
+                    }
+                    continue;
+                }
+                const uint8_t* p = row + (size_t)x * channels * stride;
+                switch (ctype) {
+                case 0: case 4: o[0] = o[1] = o[2] = p[0]; break;
+                case 2: case 6: o[0] = p[0]; o[1] = p[stride]; o[2] = p[2 * stride]; break;
+                case 3:
+                    if ((size_t)p[0] * 3 + 2 >= palette.size()) { err = "PNG: palette index out of range"; return false; }
+                    o[0] = palette[p[0] * 3]; o[1] = palette[p[0] * 3 + 1]; o[2] = palette[p[0] * 3 + 2];
+                    break;
+                }
             }
         }
     }

@@ -53,6 +53,41 @@ def write_png(path, w, h, ctype, depth, rows, palette=None, level=6, idat_split=
     open(path, "wb").write(data)
 
 
+def write_png_interlaced(path, w, h, ctype, depth, pixels, palette=None):
+    """Adam7: `pixels[y][x]` = tuple of samples of one pixel; every pass is filtered on its own (filter = row % 5)."""
+    nch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype]
+    bpp = max(1, nch * depth // 8)
+    raw = bytearray()
+    for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+        xs, ys = range(x0, w, dx), range(y0, h, dy)
+        if not len(xs) or not len(ys):
+            continue
+        prev = None
+        for r, y in enumerate(ys):
+            if depth >= 8:
+                row = b"".join(int(v).to_bytes(depth // 8, "big") for x in xs for v in pixels[y][x])
+            else:
+                bits = "".join(format(int(pixels[y][x][0]), "0%db" % depth) for x in xs)
+                bits += "0" * (-len(bits) % 8)
+                row = bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8))
+            if prev is None:
+                prev = bytes(len(row))
+            ft = r % 5
+            out = bytearray(len(row))
+            for i in range(len(row)):
+                a = row[i - bpp] if i >= bpp else 0
+                b = prev[i]
+                c = prev[i - bpp] if i >= bpp else 0
+                out[i] = (row[i] - (0, a, b, (a + b) >> 1, _paeth(a, b, c))[ft]) & 0xFF
+            raw += bytes([ft]) + out
+            prev = row
+    data = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 1))
+    if palette is not None:
+        data += _chunk(b"PLTE", bytes(palette))
+    data += _chunk(b"IDAT", zlib.compress(bytes(raw), 6)) + _chunk(b"IEND", b"")
+    open(path, "wb").write(data)
+
+
 def write_hdr(path, img, rle):
     """img: (h, w, 4) uint8 RGBE."""
     h, w, _ = img.shape
@@ -110,6 +145,12 @@ def make_files():
     write_hdr(os.path.join(IMG, "env_rle.hdr"), e, True)
     write_hdr(os.path.join(IMG, "env_flat.hdr"), e, False)
     write_hdr(os.path.join(IMG, "narrow_flat.hdr"), e[:, :5].copy(), False)
+    # interlaced PNG (Adam7), including sizes that leave some passes empty
+    ia = rs.randint(0, 256, (11, 13, 3))
+    write_png_interlaced(os.path.join(IMG, "adam7_rgb8.png"), 13, 11, 2, 8, ia)
+    write_png_interlaced(os.path.join(IMG, "adam7_rgba16.png"), 5, 3, 6, 16, rs.randint(0, 65536, (3, 5, 4)))
+    write_png_interlaced(os.path.join(IMG, "adam7_gray2.png"), 9, 10, 0, 2, rs.randint(0, 4, (10, 9, 1)))
+    write_png_interlaced(os.path.join(IMG, "adam7_pal4.png"), 1, 7, 3, 4, rs.randint(0, 16, (7, 1, 1)), palette=pal[:48])
     # JPEG: baseline / progressive, 4:4:4 / 4:2:2 / 4:2:0 / 4:1:1 / 4:4:0, optimised Huffman tables, restart markers, grey,
     # RGB-tagged components (written with Pillow and OpenCV, which are in the build image)
     from PIL import Image
