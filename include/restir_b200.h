@@ -201,7 +201,7 @@ int rstr_tonemap(RstrFrame*, int toneMapping, float scale);
 /* saveImage (main.cpp:105-144): tone-map + gamma the radiance image, mirror it horizontally (main.cpp:126) and write an
  * 8-bit RGB PNG (Image::savePNG, image.cpp:41-57).  `path` is the complete file name. */
 int rstr_frame_save_png(RstrFrame*, const char* path, int toneMapping);
-/* Image::Image(filename) (image.cpp:16-33): PNG, JPEG or Radiance .hdr -> width x height x 3 f32, linear (8-bit samples / 255,
+/* Image::Image(filename) (image.cpp:16-33): PNG, JPEG, BMP, TGA or Radiance .hdr -> width x height x 3 f32, linear (8-bit samples / 255,
  * stbi_ldr_to_hdr_gamma(1), scene.cpp:97); flipY = stbi_set_flip_vertically_on_load (true for material textures, false for
  * the environment map, scene.cpp:98,124).  Call with rgbOut = NULL to get the size.  Host only, no GPU needed. */
 int rstr_image_load(const char* path, int flipY, int* width, int* height, float* rgbOut, size_t capacityBytes);

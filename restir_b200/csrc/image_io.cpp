@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -329,6 +330,212 @@ bool decodeHDR(const std::vector<uint8_t>& f, int& W, int& H, std::vector<f3>& p
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------ BMP / TGA -> 8-bit RGB
+// The uncompressed Windows bitmap variants (palette 1/4/8 bit, 16/24/32 bit with the default or explicit channel
+// masks; header sizes 12/40/56/108/124) and Truevision TGA (true colour 15/16/24/32 bit, grey 8/16 bit, colour-mapped,
+// raw or run-length packets, either row order) as the reference's loader reads them (stb_image.h:5071-5460, 5469-5700):
+// channel masks are widened to 8 bits by bit replication, 5-bit TGA channels by v * 255 / 31, alpha is dropped.
+struct Bytes {
+    const std::vector<uint8_t>& f; size_t pos = 0;
+    int u8() { return pos < f.size() ? f[pos++] : 0; }
+    int u16() { int a = u8(); return a | u8() << 8; }
+    uint32_t u32() { uint32_t a = (uint32_t)u16(); return a | (uint32_t)u16() << 16; }
+    void skip(long n) { if (n > 0) pos += (size_t)n; }
+};
+int highBit(uint32_t z) { int n = -1; while (z) { n++; z >>= 1; } return n; }
+int bitCount(uint32_t a) { int n = 0; while (a) { n += a & 1; a >>= 1; } return n; }
+int widenChannel(uint32_t v, int shift, int bits) {                 // stb_image.h:5096-5114
+    static const unsigned mul[9] = {0, 0xff, 0x55, 0x49, 0x11, 0x21, 0x41, 0x81, 0x01};
+    static const unsigned sh[9] = {0, 0, 0, 1, 0, 2, 4, 6, 0};
+    if (shift < 0) v <<= -shift; else v >>= shift;
+    if (bits < 0 || bits > 8) return 0;
+    v >>= (8 - bits);
+    return (int)(v * mul[bits]) >> sh[bits];
+}
+
+bool decodeBMP(const std::vector<uint8_t>& file, int& W, int& H, std::vector<uint8_t>& rgb, std::string& err) {
+    Bytes s{file};
+    s.skip(2); s.u32(); s.u16(); s.u16();
+    const long offset = (long)s.u32();
+    const int hsz = (int)s.u32();
+    uint32_t mr = 0, mg = 0, mb = 0, ma = 0;
+    if (hsz != 12 && hsz != 40 && hsz != 56 && hsz != 108 && hsz != 124) { err = "BMP: unknown header size"; return false; }
+    long w, h;
+    if (hsz == 12) { w = s.u16(); h = s.u16(); } else { w = (int32_t)s.u32(); h = (int32_t)s.u32(); }
+    if (s.u16() != 1) { err = "BMP: bad plane count"; return false; }
+    const int bpp = s.u16();
+    if (hsz != 12) {
+        const int compress = (int)s.u32();
+        if (compress == 1 || compress == 2) { err = "BMP: run-length compressed files are not supported"; return false; }
+        for (int i = 0; i < 5; i++) s.u32();
+        if (hsz == 40 || hsz == 56) {
+            if (hsz == 56) for (int i = 0; i < 4; i++) s.u32();
+            if (bpp == 16 || bpp == 32) {
+                if (compress == 0) {
+                    if (bpp == 32) { mr = 0xffu << 16; mg = 0xffu << 8; mb = 0xffu; ma = 0xffu << 24; }
+                    else { mr = 31u << 10; mg = 31u << 5; mb = 31u; }
+                } else if (compress == 3) {
+                    mr = s.u32(); mg = s.u32(); mb = s.u32();
+                    if (mr == mg && mg == mb) { err = "BMP: bad channel masks"; return false; }
+                } else { err = "BMP: unsupported compression"; return false; }
+            }
+        } else {
+            mr = s.u32(); mg = s.u32(); mb = s.u32(); ma = s.u32();
+            s.u32();
+            for (int i = 0; i < 12; i++) s.u32();
+            if (hsz == 124) for (int i = 0; i < 4; i++) s.u32();
+        }
+    }
+    const bool bottomUp = h > 0;
+    if (h < 0) h = -h;
+    if (w <= 0 || h <= 0 || (size_t)w * (size_t)h > file.size() * 8 + 64) { err = "BMP: bad size"; return false; }
+    W = (int)w; H = (int)h;
+    rgb.assign((size_t)W * H * 3, 0);
+    size_t z = 0;
+    if (bpp < 16) {
+        int psize = hsz == 12 ? (int)((offset - 14 - 24) / 3) : (int)((offset - 14 - hsz) >> 2);
+        if (psize <= 0 || psize > 256) { err = "BMP: bad palette"; return false; }
+        uint8_t pal[256][3] = {};
+        for (int i = 0; i < psize; i++) {
+            pal[i][2] = (uint8_t)s.u8(); pal[i][1] = (uint8_t)s.u8(); pal[i][0] = (uint8_t)s.u8();
+            if (hsz != 12) s.u8();
+        }
+        s.skip(offset - 14 - hsz - (long)psize * (hsz == 12 ? 3 : 4));
+        int width;
+        if (bpp == 1) width = (W + 7) >> 3; else if (bpp == 4) width = (W + 1) >> 1; else if (bpp == 8) width = W;
+        else { err = "BMP: bad bit depth"; return false; }
+        const int pad = (-width) & 3;
+        for (int j = 0; j < H; j++) {
+            int v = 0;
+            for (int i = 0; i < W; i++) {
+                int c;
+                if (bpp == 1) { if ((i & 7) == 0) v = s.u8(); c = (v >> (7 - (i & 7))) & 1; }
+                else if (bpp == 4) { if ((i & 1) == 0) v = s.u8(); c = (i & 1) ? (v & 15) : (v >> 4); }
+                else c = s.u8();
+                rgb[z++] = pal[c][0]; rgb[z++] = pal[c][1]; rgb[z++] = pal[c][2];
+            }
+            s.skip(pad);
+        }
+    } else {
+        s.skip(offset - 14 - hsz);
+        const int width = bpp == 24 ? 3 * W : (bpp == 16 ? 2 * W : 0), pad = (-width) & 3;
+        if (bpp != 16 && bpp != 24 && bpp != 32) { err = "BMP: bad bit depth"; return false; }
+        const bool easy = bpp == 24 || (bpp == 32 && mb == 0xff && mg == 0xff00 && mr == 0x00ff0000 && ma == 0xff000000);
+        int rs = 0, gs = 0, bs = 0, rc = 0, gc = 0, bc = 0;
+        if (!easy) {
+            if (!mr || !mg || !mb) { err = "BMP: bad channel masks"; return false; }
+            rs = highBit(mr) - 7; rc = bitCount(mr); gs = highBit(mg) - 7; gc = bitCount(mg); bs = highBit(mb) - 7; bc = bitCount(mb);
+        }
+        for (int j = 0; j < H; j++) {
+            for (int i = 0; i < W; i++) {
+                if (easy) {
+                    rgb[z + 2] = (uint8_t)s.u8(); rgb[z + 1] = (uint8_t)s.u8(); rgb[z] = (uint8_t)s.u8();
+                    if (bpp == 32) s.u8();
+                } else {
+                    uint32_t v = bpp == 16 ? (uint32_t)s.u16() : s.u32();
+                    rgb[z] = (uint8_t)widenChannel(v & mr, rs, rc); rgb[z + 1] = (uint8_t)widenChannel(v & mg, gs, gc); rgb[z + 2] = (uint8_t)widenChannel(v & mb, bs, bc);
+                }
+                z += 3;
+            }
+            s.skip(pad);
+        }
+    }
+    if (bottomUp)
+        for (int j = 0; j < H / 2; j++)
+            for (int i = 0; i < W * 3; i++) std::swap(rgb[(size_t)j * W * 3 + i], rgb[(size_t)(H - 1 - j) * W * 3 + i]);
+    return true;
+}
+
+bool looksLikeTGA(const std::vector<uint8_t>& f) {                  // the format has no signature: stb_image.h:5469-5499
+    if (f.size() < 18) return false;
+    int mapType = f[1], type = f[2];
+    if (mapType > 1) return false;
+    if (mapType == 1) {
+        if (type != 1 && type != 9) return false;
+        int pb = f[7];
+        if (pb != 8 && pb != 15 && pb != 16 && pb != 24 && pb != 32) return false;
+    } else if (type != 2 && type != 3 && type != 10 && type != 11) return false;
+    if ((f[12] | f[13] << 8) < 1 || (f[14] | f[15] << 8) < 1) return false;
+    int bpp = f[16];
+    if (mapType == 1 && bpp != 8 && bpp != 16) return false;
+    return bpp == 8 || bpp == 15 || bpp == 16 || bpp == 24 || bpp == 32;
+}
+
+bool decodeTGA(const std::vector<uint8_t>& file, int& W, int& H, std::vector<uint8_t>& rgb, std::string& err) {
+    Bytes s{file};
+    const int idLen = s.u8(), indexed = s.u8();
+    int type = s.u8();
+    const int palStart = s.u16(), palLen = s.u16(), palBits = s.u8();
+    s.u16(); s.u16();
+    W = s.u16(); H = s.u16();
+    const int bpp = s.u8(), desc = s.u8();
+    const bool rle = type >= 8;
+    if (rle) type -= 8;
+    const bool bottomUp = ((desc >> 5) & 1) == 0;
+    auto compOf = [&](int bits, bool grey, bool& rgb16) {
+        rgb16 = false;
+        switch (bits) {
+        case 8: return 1;
+        case 16: if (grey) return 2;     // fall through
+        case 15: rgb16 = true; return 3;
+        case 24: return 3;
+        case 32: return 4;
+        }
+        return 0;
+    };
+    bool rgb16 = false;
+    const int comp = indexed ? compOf(palBits, false, rgb16) : compOf(bpp, type == 3, rgb16);
+    if (!comp || W < 1 || H < 1) { err = "TGA: unsupported pixel format"; return false; }
+    if ((size_t)W * H > file.size() * 128 + 64) { err = "TGA: header claims more pixels than the file can hold"; return false; }
+    std::vector<uint8_t> data((size_t)W * H * comp);
+    auto read16 = [&](uint8_t* out) {
+        int px = s.u16();
+        out[0] = (uint8_t)((((px >> 10) & 31) * 255) / 31); out[1] = (uint8_t)((((px >> 5) & 31) * 255) / 31); out[2] = (uint8_t)(((px & 31) * 255) / 31);
+    };
+    s.skip(idLen);
+    std::vector<uint8_t> palette;
+    if (indexed) {
+        s.skip(palStart);
+        palette.assign((size_t)palLen * comp, 0);
+        for (int i = 0; i < palLen; i++) {
+            if (rgb16) read16(&palette[(size_t)i * comp]);
+            else for (int j = 0; j < comp; j++) palette[(size_t)i * comp + j] = (uint8_t)s.u8();
+        }
+    }
+    uint8_t px[4] = {0, 0, 0, 0};
+    int count = 0;
+    bool repeating = false;
+    for (size_t i = 0; i < (size_t)W * H; i++) {
+        bool readNext = true;
+        if (rle) {
+            if (count == 0) { int cmd = s.u8(); count = 1 + (cmd & 127); repeating = (cmd >> 7) != 0; }
+            else if (repeating) readNext = false;
+        }
+        if (readNext) {
+            if (indexed) {
+                int idx = bpp == 8 ? s.u8() : s.u16();
+                if (idx >= palLen) idx = 0;
+                for (int j = 0; j < comp; j++) px[j] = palette.empty() ? 0 : palette[(size_t)idx * comp + j];
+            } else if (rgb16) read16(px);
+            else for (int j = 0; j < comp; j++) px[j] = (uint8_t)s.u8();
+        }
+        for (int j = 0; j < comp; j++) data[i * comp + j] = px[j];
+        --count;
+    }
+    rgb.resize((size_t)W * H * 3);
+    for (int y = 0; y < H; y++) {
+        const int sy = bottomUp ? H - 1 - y : y;
+        for (int x = 0; x < W; x++) {
+            const uint8_t* p = &data[((size_t)sy * W + x) * comp];
+            uint8_t* o = &rgb[((size_t)y * W + x) * 3];
+            if (comp <= 2) o[0] = o[1] = o[2] = p[0];
+            else if (rgb16) { o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; }
+            else { o[0] = p[2]; o[1] = p[1]; o[2] = p[0]; }       // stored BGR(A)
+        }
+    }
+    return true;
+}
+
 uint32_t crc32(const uint8_t* p, size_t n, uint32_t crc = 0) {
     static uint32_t table[256];
     static bool init = false;
@@ -374,8 +581,14 @@ bool loadImageRGB(const std::string& path, bool flipY, HostTexture& out, std::st
         for (size_t i = 0; i < px.size(); i++) px[i] = mk3(rgb[3 * i] / 255.0f, rgb[3 * i + 1] / 255.0f, rgb[3 * i + 2] / 255.0f);
     } else if (file.size() >= 11 && (!memcmp(file.data(), "#?RADIANCE", 10) || !memcmp(file.data(), "#?RGBE", 6))) {
         if (!decodeHDR(file, W, H, px, err)) { err = path + ": " + err; return false; }
+    } else if ((file.size() >= 26 && file[0] == 'B' && file[1] == 'M') || looksLikeTGA(file)) {
+        std::vector<uint8_t> rgb;
+        const bool bmp = file[0] == 'B' && file[1] == 'M';
+        if (!(bmp ? decodeBMP(file, W, H, rgb, err) : decodeTGA(file, W, H, rgb, err))) { err = path + ": " + err; return false; }
+        px.resize((size_t)W * H);
+        for (size_t i = 0; i < px.size(); i++) px[i] = mk3(rgb[3 * i] / 255.0f, rgb[3 * i + 1] / 255.0f, rgb[3 * i + 2] / 255.0f);
     } else {
-        err = path + ": unsupported image format (PNG, JPEG and Radiance .hdr are supported)";
+        err = path + ": unsupported image format (PNG, JPEG, BMP, TGA and Radiance .hdr are supported)";
         return false;
     }
     if (flipY)

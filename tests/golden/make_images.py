@@ -167,6 +167,26 @@ def make_files():
     P("one_pixel.jpg", pic[:1, :1].copy(), quality=95)
     cv2.imwrite(os.path.join(IMG, "cv411_rst.jpg"), pic, [cv2.IMWRITE_JPEG_QUALITY, 70, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
                                                          cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411, cv2.IMWRITE_JPEG_RST_INTERVAL, 2])
+    # BMP (24-bit, 32-bit with masks, 8- and 4-bit palette, 1-bit, 16-bit 565 bit fields) and TGA (true colour / grey /
+    # colour-mapped, raw and run-length, both row orders)
+    small = pic[:9, :14].copy()
+    small[:, :6] = small[:1, :1]
+    sim = Image.fromarray(small)
+    sim.save(os.path.join(IMG, "rgb24.bmp"))
+    Image.fromarray(np.dstack([small, small[..., :1]]), "RGBA").save(os.path.join(IMG, "rgba32.bmp"))
+    sim.convert("P", palette=Image.ADAPTIVE, colors=200).save(os.path.join(IMG, "pal8.bmp"))
+    sim.convert("P", palette=Image.ADAPTIVE, colors=16).save(os.path.join(IMG, "pal4.bmp"), bits=4)
+    sim.convert("1").save(os.path.join(IMG, "mono1.bmp"))
+    v565 = ((small[..., 0] >> 3).astype(np.uint16) << 11) | ((small[..., 1] >> 2).astype(np.uint16) << 5) | (small[..., 2] >> 3)
+    rows = [v565[y].astype("<u2").tobytes() for y in range(9)][::-1]
+    body = b"".join(r + b"\0" * (-len(r) % 4) for r in rows)
+    hdr = struct.pack("<IiiHHIIiiII", 40, 14, 9, 1, 16, 3, len(body), 2835, 2835, 0, 0) + struct.pack("<III", 0xF800, 0x07E0, 0x001F)
+    open(os.path.join(IMG, "rgb565.bmp"), "wb").write(b"BM" + struct.pack("<IHHI", 14 + len(hdr) + len(body), 0, 0, 14 + len(hdr)) + hdr + body)
+    sim.save(os.path.join(IMG, "rgb24.tga"))
+    sim.save(os.path.join(IMG, "rgb24_rle_topdown.tga"), compression="tga_rle", orientation=1)
+    Image.fromarray(np.dstack([small, small[..., :1]]), "RGBA").save(os.path.join(IMG, "rgba32_rle.tga"), compression="tga_rle")
+    sim.convert("L").save(os.path.join(IMG, "grey8.tga"))
+    sim.convert("P", palette=Image.ADAPTIVE, colors=64).save(os.path.join(IMG, "mapped8_rle.tga"), compression="tga_rle")
     cv2.imwrite(os.path.join(IMG, "cv440_prog.jpg"), pic, [cv2.IMWRITE_JPEG_QUALITY, 50, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
                                                           cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
 

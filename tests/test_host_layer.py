@@ -171,7 +171,7 @@ def test_image_loader_matches_reference_loader():
     progressive, five chroma layouts, restart markers, grey, RGB-tagged) and Radiance
     .hdr (RLE and flat) against what the reference's loader (stb_image via Image::Image) returned, bit for bit."""
     g = np.load(os.path.join(helpers.GOLDEN, "images.npz"))
-    assert len(g.files) == 62
+    assert len(g.files) == 84
     for key in g.files:
         name, flip = key.rsplit("_flip", 1)
         a = rb.load_image(os.path.join(helpers.GOLDEN, "images", name), bool(int(flip)))
