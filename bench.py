@@ -372,9 +372,7 @@ def run_b200(args):
             refine_log.append({"bounds": list(bounds), "kernel_ms_per_rank": [round(float(x), 3) for x in measured]})
             if measured.max() / measured.mean() < 1.02:
                 break
-            for r in range(world):
-                seg = slice(bounds[r], bounds[r + 1])
-                row_cost[seg] *= measured[r] / max(row_cost[seg].sum(), 1e-30)
+            row_cost = strips.refine_row_cost(row_cost, bounds, measured)
             bounds = strips.balanced_bounds(row_cost, world, min_rows=max(8, halo))
             make_strip()
 

@@ -46,6 +46,21 @@ def balanced_bounds(row_cost, world: int, min_rows: int = 8) -> list[int]:
     return b
 
 
+def refine_row_cost(row_cost, bounds, measured):
+    """One step of the closed loop that places the strip cuts: the row costs inside strip r are rescaled so that they sum
+    to the time rank r was MEASURED to take with the current cuts (the model keeps its shape inside a strip, its level
+    comes from the measurement).  Returns a new array; cut again with :func:`balanced_bounds`."""
+    cost = np.array(row_cost, np.float64)
+    for r in range(len(bounds) - 1):
+        seg = slice(bounds[r], bounds[r + 1])
+        total = cost[seg].sum()
+        if total > 0:
+            cost[seg] *= float(measured[r]) / total
+        else:
+            cost[seg] = float(measured[r]) / max(bounds[r + 1] - bounds[r], 1)
+    return cost
+
+
 def row_cost_from_matid(matid, width: int, shaded_weight: float = 1.0, base_weight: float = 0.03):
     """Per-row cost estimate from a G-buffer material-id plane: shaded pixels (id >= 0) run the candidate loop and two
     more rays, the others only a primary ray that leaves the scene box."""
