@@ -123,6 +123,12 @@ static int finishScene(RstrScene* sc, RstrScene** out) {
         delete sc;
         return fail(RSTR_ERR_LIMIT, b);
     }
+    if (sc->hs.fastDepth > RS_STACK_DEPTH) {
+        char b[160];
+        snprintf(b, sizeof b, "traced tree depth %d exceeds the traversal stack (%d)", sc->hs.fastDepth, RS_STACK_DEPTH);
+        delete sc;
+        return fail(RSTR_ERR_LIMIT, b);
+    }
     if (RS_BVH4 && 3 * sc->hs.fastDepth4 + 1 > RS_STACK_DEPTH) {
         char b[160];
         snprintf(b, sizeof b, "traced tree depth %d exceeds the traversal stack (%d entries, 3 per level)", sc->hs.fastDepth4, RS_STACK_DEPTH);
