@@ -308,6 +308,8 @@ def run_b200(args):
             fr.close()
         rows = strips.strip_rows(H, world, rank, bounds)
         fr = sc.frame(W, H, rows=rows, halo=halo)
+        if args.no_fusion:
+            fr.set_fusion(False)
         plan = strips.exchange_plan(H, world, halo, bounds) if world > 1 else []
         if world > 1:
             fr.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -315,8 +317,6 @@ def run_b200(args):
             exchange = StripExchange(fr, plan, rank)
 
     make_strip()
-    if args.no_fusion:
-        fr.set_fusion(False)
 
     def frame(k):
         # One frame of a strip: G-buffer and phase A on the strip's own rows (one fused kernel); then ONE exchange carries
