@@ -201,12 +201,15 @@ int rstr_tonemap(RstrFrame*, int toneMapping, float scale);
 /* saveImage (main.cpp:105-144): tone-map + gamma the radiance image, mirror it horizontally (main.cpp:126) and write an
  * 8-bit RGB PNG (Image::savePNG, image.cpp:41-57).  `path` is the complete file name. */
 int rstr_frame_save_png(RstrFrame*, const char* path, int toneMapping);
+int rstr_frame_save_jpg(RstrFrame*, const char* path, int toneMapping);   /* saveImage(jpg = true): Image::saveJPG, quality 90 (image.cpp:59-75) */
 /* Image::Image(filename) (image.cpp:16-33): PNG, JPEG, BMP, TGA or Radiance .hdr -> width x height x 3 f32, linear (8-bit samples / 255,
  * stbi_ldr_to_hdr_gamma(1), scene.cpp:97); flipY = stbi_set_flip_vertically_on_load (true for material textures, false for
  * the environment map, scene.cpp:98,124).  Call with rgbOut = NULL to get the size.  Host only, no GPU needed. */
 int rstr_image_load(const char* path, int flipY, int* width, int* height, float* rgbOut, size_t capacityBytes);
 /* Image::savePNG (image.cpp:41-57): width x height x 3 bytes, top row first.  Host only. */
 int rstr_image_write_png(const char* path, int width, int height, const unsigned char* rgb);
+/* Image::saveJPG (image.cpp:59-75): the file stbi_write_jpg writes, byte for byte; quality 1..100, 0 = 90.  Host only. */
+int rstr_image_write_jpg(const char* path, int width, int height, const unsigned char* rgb, int quality);
 
 /* One whole frame of runCuda (main.cpp:146-185) from HOST inputs to a HOST result:
  * gbuffer_render + restir_direct (or pathtrace_direct when params == NULL) + tonemap + gbuffer_update,

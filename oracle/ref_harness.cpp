@@ -196,6 +196,15 @@ int ref_image_load(const char* path, int flipY, int* w, int* h, float* out, size
     return 0;
 }
 
+/* Image::setPixel + Image::savePNG / saveJPG (image.cpp:35-75): writes <base>.png or <base>.jpg from float RGB */
+int ref_image_save(const char* base, int w, int h, const float* rgb, int jpg) {
+    Image img(w, h);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) img.setPixel(x, y, glm::vec3(rgb[3 * (y * w + x)], rgb[3 * (y * w + x) + 1], rgb[3 * (y * w + x) + 2]));
+    if (jpg) img.saveJPG(base); else img.savePNG(base);
+    return 0;
+}
+
 /* the reference's own parser + flattening + upload (over fake cudart) */
 OrcScene* ref_scene_load_file(const char* path) {
     OrcScene* sc = new OrcScene;

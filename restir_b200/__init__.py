@@ -7,5 +7,5 @@ from . import scenes  # noqa: F401
 from .api import (  # noqa: F401
     REUSE_NONE, REUSE_SPATIAL, REUSE_SPATIOTEMPORAL, REUSE_TEMPORAL, TONEMAP_ACES, TONEMAP_FILMIC, TONEMAP_NONE,
     Camera, Frame, RestirError, RstrParams, Scene, default_params, init, launch_count, lib, load_image, pinned_empty, pinned_free,
-    write_png,
+    write_jpg, write_png,
 )

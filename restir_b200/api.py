@@ -156,6 +156,8 @@ def lib() -> C.CDLL:
     L.rstr_frame_save_png.argtypes = [vp, C.c_char_p, ip]
     L.rstr_image_load.argtypes = [C.c_char_p, ip, vp, vp, vp, C.c_size_t]
     L.rstr_image_write_png.argtypes = [C.c_char_p, ip, ip, vp]
+    L.rstr_image_write_jpg.argtypes = [C.c_char_p, ip, ip, vp, ip]
+    L.rstr_frame_save_jpg.argtypes = [vp, C.c_char_p, ip]
     L.rstr_render_frame_host.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip, vp, C.c_size_t]
     L.rstr_render_frame_host_async.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip, vp, C.c_size_t, ip]
     L.rstr_frame_wait_host.argtypes = [vp, ip]
@@ -376,6 +378,9 @@ class Frame:
     def save_png(self, path: str, tonemap: int = TONEMAP_ACES) -> None:        # saveImage (main.cpp:105-144)
         _check(lib().rstr_frame_save_png(self.f, path.encode(), tonemap))
 
+    def save_jpg(self, path: str, tonemap: int = TONEMAP_ACES) -> None:        # saveImage(jpg = true)
+        _check(lib().rstr_frame_save_jpg(self.f, path.encode(), tonemap))
+
     def render_frame_host(self, cam, params, looper: int, it: int = 0, tonemap: int = TONEMAP_ACES, out=None) -> None:
         """One runCuda() frame; ``out`` is a host uint8 buffer of npix*4 bytes receiving the LDR image."""
         ptr, nbytes = (None, 0) if out is None else (out.ctypes.data, out.nbytes)
@@ -456,6 +461,12 @@ def write_png(path: str, rgb: np.ndarray) -> None:
     """Image::savePNG (image.cpp:41-57): (H, W, 3) uint8."""
     a = np.ascontiguousarray(rgb, np.uint8)
     _check(lib().rstr_image_write_png(path.encode(), int(a.shape[1]), int(a.shape[0]), a.ctypes.data))
+
+
+def write_jpg(path: str, rgb: np.ndarray, quality: int = 90) -> None:
+    """Image::saveJPG (image.cpp:59-75): (H, W, 3) uint8 -> the file stbi_write_jpg writes."""
+    a = np.ascontiguousarray(rgb, np.uint8)
+    _check(lib().rstr_image_write_jpg(path.encode(), int(a.shape[1]), int(a.shape[0]), a.ctypes.data, int(quality)))
 
 
 def pinned_empty(nbytes: int) -> np.ndarray:

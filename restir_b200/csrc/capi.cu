@@ -600,9 +600,12 @@ int rstr_tonemap(RstrFrame* f, int toneMapping, float scale) {
     return RSTR_OK;
 }
 
-// saveImage (main.cpp:105-144): tone-map + gamma, mirror horizontally (img.setPixel(width - 1 - x, y, ...)), 8-bit PNG
-int rstr_frame_save_png(RstrFrame* f, const char* path, int toneMapping) {
-    if (!f || !path) return fail(RSTR_ERR_ARG, "rstr_frame_save_png: bad argument");
+// saveImage (main.cpp:105-144): tone-map + gamma, mirror horizontally (img.setPixel(width - 1 - x, y, ...)), 8-bit PNG / JPEG
+static int frameSaveImage(RstrFrame* f, const char* path, int toneMapping, bool jpg);
+int rstr_frame_save_png(RstrFrame* f, const char* path, int toneMapping) { return frameSaveImage(f, path, toneMapping, false); }
+int rstr_frame_save_jpg(RstrFrame* f, const char* path, int toneMapping) { return frameSaveImage(f, path, toneMapping, true); }
+static int frameSaveImage(RstrFrame* f, const char* path, int toneMapping, bool jpg) {
+    if (!f || !path) return fail(RSTR_ERR_ARG, "rstr_frame_save_png/jpg: bad argument");
     int rc = rstr_tonemap(f, toneMapping, 1.f);
     if (rc) return rc;
     const int W = f->W, H = f->row1 - f->row0;
@@ -617,7 +620,15 @@ int rstr_frame_save_png(RstrFrame* f, const char* path, int toneMapping) {
             o[0] = c.x; o[1] = c.y; o[2] = c.z;
         }
     std::string err;
-    if (!writePNG(path, W, H, rgb.data(), err)) return fail(RSTR_ERR_IO, err);
+    if (!(jpg ? writeJPG(path, W, H, rgb.data(), 90, err) : writePNG(path, W, H, rgb.data(), err))) return fail(RSTR_ERR_IO, err);
+    return RSTR_OK;
+}
+
+// Image::saveJPG (image.cpp:59-75); quality 0 = the library default (90, which is also what the reference passes)
+int rstr_image_write_jpg(const char* path, int width, int height, const unsigned char* rgb, int quality) {
+    if (!path || width <= 0 || height <= 0 || !rgb) return fail(RSTR_ERR_ARG, "rstr_image_write_jpg: bad argument");
+    std::string err;
+    if (!writeJPG(path, width, height, rgb, quality, err)) return fail(RSTR_ERR_IO, err);
     return RSTR_OK;
 }
 

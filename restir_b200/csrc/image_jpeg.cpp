@@ -15,6 +15,7 @@
 // Pinned against stb itself (oracle/ref_harness.cpp:ref_image_load) on the fixtures under tests/golden/images/.
 // CMYK / YCCK (4 components), 12-bit and arithmetic-coded files are rejected.
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <string>
@@ -561,6 +562,184 @@ bool decodeJPEG(const std::vector<uint8_t>& file, int& W, int& H, std::vector<ui
     d.toRGB(rgb);
     W = d.W; H = d.H;
     return true;
+}
+
+}  // namespace rs
+
+// ------------------------------------------------------------------------------------------------ JPEG writer
+// Image::saveJPG (image.cpp:59-75) = stbi_write_jpg(..., quality 90) of stb_image_write 1.10: baseline JFIF, 4:4:4, the
+// Annex K Huffman and quantisation tables (scaled by the IJG quality rule), the Arai-Agui-Nakajima float DCT with the
+// scale factors folded into the divisors, coefficients rounded half away from zero.  Restated so that the file is the
+// one the reference writes, byte for byte (pinned through oracle/ref_harness.cpp:ref_image_save).
+namespace rs {
+
+namespace {
+
+const uint8_t kDcLumaCounts[16] = {0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0};
+const uint8_t kDcChromaCounts[16] = {0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0};
+const uint8_t kDcValues[12] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11};
+const uint8_t kAcLumaCounts[16] = {0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d};
+const uint8_t kAcChromaCounts[16] = {0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77};
+const uint8_t kAcLumaValues[162] = {
+    0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71, 0x14, 0x32, 0x81, 0x91, 0xa1, 0x08, 0x23, 0x42, 0xb1,
+    0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72, 0x82, 0x09, 0x0a, 0x16, 0x17, 0x18, 0x19, 0x1a, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37,
+    0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69, 0x6a,
+    0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3,
+    0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3,
+    0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+const uint8_t kAcChromaValues[162] = {
+    0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22, 0x32, 0x81, 0x08, 0x14, 0x42, 0x91, 0xa1, 0xb1, 0xc1,
+    0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1, 0x0a, 0x16, 0x24, 0x34, 0xe1, 0x25, 0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36,
+    0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69,
+    0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a,
+    0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca,
+    0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
+const int kLumaQ[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56, 14, 17, 22, 29, 51, 87, 80, 62,
+                        18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+const int kChromaQ[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                          99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+// position of natural-order coefficient i in the zigzag sequence
+const uint8_t kToZigzag[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30, 41, 43, 9,  11, 18, 24, 31, 40, 44, 53,
+                               10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+struct Code { uint16_t bits, len; };
+void canonicalCodes(const uint8_t counts[16], const uint8_t* values, Code table[256]) {    // T.81 Annex C
+    memset(table, 0, 256 * sizeof(Code));
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; len++) {
+        for (int i = 0; i < counts[len - 1]; i++) table[values[k++]] = Code{(uint16_t)code++, (uint16_t)len};
+        code <<= 1;
+    }
+}
+
+struct JpegOut {
+    std::vector<uint8_t> out;
+    int bitBuf = 0, bitCnt = 0;
+    void put(const void* p, size_t n) { out.insert(out.end(), (const uint8_t*)p, (const uint8_t*)p + n); }
+    void bits(Code c) {
+        bitCnt += c.len;
+        bitBuf |= c.bits << (24 - bitCnt);
+        while (bitCnt >= 8) {
+            uint8_t b = (uint8_t)((bitBuf >> 16) & 255);
+            out.push_back(b);
+            if (b == 255) out.push_back(0);
+            bitBuf <<= 8; bitCnt -= 8;
+        }
+    }
+};
+
+void fdct8(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7) {   // AAN forward DCT, one dimension
+    float t0 = d0 + d7, t7 = d0 - d7, t1 = d1 + d6, t6 = d1 - d6, t2 = d2 + d5, t5 = d2 - d5, t3 = d3 + d4, t4 = d3 - d4;
+    float t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    float e0 = t10 + t11, e4 = t10 - t11;
+    float z1 = (t12 + t13) * 0.707106781f;
+    float e2 = t13 + z1, e6 = t13 - z1;
+    t10 = t4 + t5; t11 = t5 + t6; t12 = t6 + t7;
+    float z5 = (t10 - t12) * 0.382683433f;
+    float z2 = t10 * 0.541196100f + z5, z4 = t12 * 1.306562965f + z5, z3 = t11 * 0.707106781f;
+    float z11 = t7 + z3, z13 = t7 - z3;
+    d5 = z13 + z2; d3 = z13 - z2; d1 = z11 + z4; d7 = z11 - z4;
+    d0 = e0; d2 = e2; d4 = e4; d6 = e6;
+}
+
+Code magnitude(int val) {
+    int mag = val < 0 ? -val : val;
+    val = val < 0 ? val - 1 : val;
+    uint16_t len = 1;
+    while (mag >>= 1) ++len;
+    return Code{(uint16_t)(val & ((1 << len) - 1)), len};
+}
+
+int encodeBlock(JpegOut& o, float* blk, const float* divisors, int prevDC, const Code* dcTab, const Code* acTab) {
+    for (int r = 0; r < 64; r += 8) fdct8(blk[r], blk[r + 1], blk[r + 2], blk[r + 3], blk[r + 4], blk[r + 5], blk[r + 6], blk[r + 7]);
+    for (int c = 0; c < 8; c++) fdct8(blk[c], blk[c + 8], blk[c + 16], blk[c + 24], blk[c + 32], blk[c + 40], blk[c + 48], blk[c + 56]);
+    int q[64];
+    for (int i = 0; i < 64; i++) {
+        float v = blk[i] * divisors[i];
+        q[kToZigzag[i]] = (int)(v < 0 ? v - 0.5f : v + 0.5f);
+    }
+    int diff = q[0] - prevDC;
+    if (diff == 0) o.bits(dcTab[0]);
+    else { Code m = magnitude(diff); o.bits(dcTab[m.len]); o.bits(m); }
+    int last = 63;
+    while (last > 0 && q[last] == 0) --last;
+    if (last == 0) { o.bits(acTab[0x00]); return q[0]; }
+    for (int i = 1; i <= last; ++i) {
+        int start = i;
+        while (q[i] == 0 && i <= last) ++i;
+        int zeros = i - start;
+        for (int k = 0; k < (zeros >> 4); k++) o.bits(acTab[0xf0]);
+        zeros &= 15;
+        Code m = magnitude(q[i]);
+        o.bits(acTab[(zeros << 4) + m.len]);
+        o.bits(m);
+    }
+    if (last != 63) o.bits(acTab[0x00]);
+    return q[0];
+}
+
+}  // namespace
+
+bool writeJPG(const std::string& path, int W, int H, const unsigned char* rgb, int quality, std::string& err) {
+    if (W <= 0 || H <= 0 || W > 65535 || H > 65535) { err = "JPEG: bad image size"; return false; }
+    quality = quality ? quality : 90;
+    quality = quality < 1 ? 1 : (quality > 100 ? 100 : quality);
+    quality = quality < 50 ? 5000 / quality : 200 - quality * 2;
+    uint8_t lumaT[64], chromaT[64];
+    for (int i = 0; i < 64; i++) {
+        int y = (kLumaQ[i] * quality + 50) / 100, c = (kChromaQ[i] * quality + 50) / 100;
+        lumaT[kToZigzag[i]] = (uint8_t)(y < 1 ? 1 : (y > 255 ? 255 : y));
+        chromaT[kToZigzag[i]] = (uint8_t)(c < 1 ? 1 : (c > 255 ? 255 : c));
+    }
+    static const float aan[8] = {1.0f * 2.828427125f, 1.387039845f * 2.828427125f, 1.306562965f * 2.828427125f, 1.175875602f * 2.828427125f,
+                                 1.0f * 2.828427125f, 0.785694958f * 2.828427125f, 0.541196100f * 2.828427125f, 0.275899379f * 2.828427125f};
+    float divY[64], divC[64];
+    for (int r = 0, k = 0; r < 8; r++)
+        for (int c = 0; c < 8; c++, k++) {
+            divY[k] = 1 / (lumaT[kToZigzag[k]] * aan[r] * aan[c]);
+            divC[k] = 1 / (chromaT[kToZigzag[k]] * aan[r] * aan[c]);
+        }
+    Code dcY[256], dcC[256], acY[256], acC[256];
+    canonicalCodes(kDcLumaCounts, kDcValues, dcY); canonicalCodes(kDcChromaCounts, kDcValues, dcC);
+    canonicalCodes(kAcLumaCounts, kAcLumaValues, acY); canonicalCodes(kAcChromaCounts, kAcChromaValues, acC);
+    JpegOut o;
+    static const uint8_t head0[] = {0xFF, 0xD8, 0xFF, 0xE0, 0, 0x10, 'J', 'F', 'I', 'F', 0, 1, 1, 0, 0, 1, 0, 1, 0, 0, 0xFF, 0xDB, 0, 0x84, 0};
+    o.put(head0, sizeof head0); o.put(lumaT, 64);
+    o.out.push_back(1); o.put(chromaT, 64);
+    const uint8_t sof[] = {0xFF, 0xC0, 0, 0x11, 8, (uint8_t)(H >> 8), (uint8_t)H, (uint8_t)(W >> 8), (uint8_t)W, 3, 1, 0x11, 0, 2, 0x11, 1, 3, 0x11, 1, 0xFF, 0xC4, 0x01, 0xA2, 0};
+    o.put(sof, sizeof sof);
+    o.put(kDcLumaCounts, 16); o.put(kDcValues, 12);
+    o.out.push_back(0x10); o.put(kAcLumaCounts, 16); o.put(kAcLumaValues, 162);
+    o.out.push_back(1); o.put(kDcChromaCounts, 16); o.put(kDcValues, 12);
+    o.out.push_back(0x11); o.put(kAcChromaCounts, 16); o.put(kAcChromaValues, 162);
+    static const uint8_t sos[] = {0xFF, 0xDA, 0, 0xC, 3, 1, 0, 2, 0x11, 3, 0x11, 0, 0x3F, 0};
+    o.put(sos, sizeof sos);
+    int dY = 0, dU = 0, dV = 0;
+    for (int y = 0; y < H; y += 8)
+        for (int x = 0; x < W; x += 8) {
+            float Y[64], U[64], V[64];
+            for (int row = y, pos = 0; row < y + 8; ++row) {
+                const int rr = row < H ? row : H - 1;                 // edge blocks repeat the last row / column
+                for (int col = x; col < x + 8; ++col, ++pos) {
+                    const unsigned char* p = rgb + ((size_t)rr * W + (col < W ? col : W - 1)) * 3;
+                    float r = p[0], g = p[1], b = p[2];
+                    Y[pos] = +0.29900f * r + 0.58700f * g + 0.11400f * b - 128;
+                    U[pos] = -0.16874f * r - 0.33126f * g + 0.50000f * b;
+                    V[pos] = +0.50000f * r - 0.41869f * g - 0.08131f * b;
+                }
+            }
+            dY = encodeBlock(o, Y, divY, dY, dcY, acY);
+            dU = encodeBlock(o, U, divC, dU, dcC, acC);
+            dV = encodeBlock(o, V, divC, dV, dcC, acC);
+        }
+    o.bits(Code{0x7F, 7});
+    o.out.push_back(0xFF); o.out.push_back(0xD9);
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { err = "cannot write " + path; return false; }
+    bool ok = fwrite(o.out.data(), 1, o.out.size(), f) == o.out.size();
+    fclose(f);
+    if (!ok) err = "short write to " + path;
+    return ok;
 }
 
 }  // namespace rs

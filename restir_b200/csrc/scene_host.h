@@ -161,6 +161,8 @@ bool loadSceneFile(const std::string& path, HostScene& hs, RstrCamera& cam, std:
 bool loadImageRGB(const std::string& path, bool flipY, HostTexture& out, std::string& err);
 // Image::savePNG (image.cpp:41-57): W x H x 3 bytes, top row first
 bool writePNG(const std::string& path, int W, int H, const unsigned char* rgb, std::string& err);
+// Image::saveJPG (image.cpp:59-75): stbi_write_jpg at the given quality (the reference uses 90); image_jpeg.cpp
+bool writeJPG(const std::string& path, int W, int H, const unsigned char* rgb, int quality, std::string& err);
 // Camera::update (sceneStructs.h:88-102)
 void cameraUpdate(RstrCamera& c);
 

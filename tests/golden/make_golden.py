@@ -147,8 +147,31 @@ def ngons(ref):
                         file_names=np.array(list(files.keys())), file_texts=np.array(list(files.values())))
 
 
+def image_writers(ref):
+    """10. Image::saveJPG / savePNG (image.cpp:41-75) on float images with out-of-range values: the JPEG bytes the reference
+    writes (stbi_write_jpg, quality 90) and its PNG files (decoded by the tests)"""
+    rs = np.random.RandomState(9)
+    ref.lib.ref_image_save.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    tmp = tempfile.mkdtemp()
+    d = {}
+    for i, (w, h) in enumerate(((1, 1), (9, 7), (16, 16), (37, 21))):
+        yy, xx = np.mgrid[0:h, 0:w]
+        a = np.clip(rs.randn(h, w, 3) * 0.35 + np.stack([xx / max(w - 1, 1), yy / max(h - 1, 1), 0.5 + 0 * xx], 2), -0.3, 1.4).astype(np.float32)
+        base = os.path.join(tmp, "w%d" % i)
+        a = np.ascontiguousarray(a)
+        ref.lib.ref_image_save(base.encode(), w, h, a.ctypes.data, 1)
+        ref.lib.ref_image_save(base.encode(), w, h, a.ctypes.data, 0)
+        d["img%d" % i] = a
+        d["jpg%d" % i] = np.frombuffer(open(base + ".jpg", "rb").read(), np.uint8)
+        d["png%d" % i] = np.frombuffer(open(base + ".png", "rb").read(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "image_writers.npz"), **d)
+
+
 def main():
     ref = Oracle("reference")
+    if "--only-writers" in sys.argv:
+        image_writers(ref)
+        return
     if "--only-ngons" in sys.argv:
         ngons(ref)
         return
@@ -163,6 +186,7 @@ def main():
     textured(ref)
     multipass(ref)
     ngons(ref)
+    image_writers(ref)
     # 1. RNG, alias known answers
     rng = {"l%d_i%d" % (l, i): ref.rng_draws(l, i, 8) for l, i in ((7, 12345), (0, 0), (59, 2073599), (1023, 8294399))}
     alias, total = ref.alias_build([1, 2, 3, 10])

@@ -310,3 +310,29 @@ def test_obj_polygons_are_split_like_the_reference_loader():
     assert np.array_equal(sc.read("vertices").view(np.uint32), g["vertices"].view(np.uint32))
     assert np.array_equal(sc.read("normals").view(np.uint32), g["normals"].view(np.uint32))
     sc.close()
+
+
+def test_image_writers_match_the_reference():
+    """saveImage's file formats: the JPEG writer produces the bytes Image::saveJPG (stbi_write_jpg, quality 90) wrote for
+    the same pixels, and the PNG files the reference wrote decode to the reference's 8-bit conversion
+    (clamp(pix, 0, 1) * 255, truncated: image.cpp:45-49) -- so `rstr_frame_save_jpg / _png` are drop-ins for saveImage."""
+    g = np.load(os.path.join(G, "image_writers.npz"))
+    tmp = tempfile.mkdtemp()
+    for i in range(4):
+        a = g["img%d" % i]
+        u8 = (np.clip(a, 0, 1) * np.float32(255)).astype(np.uint8)
+        p = os.path.join(tmp, "o%d.jpg" % i)
+        rb.write_jpg(p, u8, 90)
+        assert open(p, "rb").read() == g["jpg%d" % i].tobytes(), i
+        assert np.array_equal(rb.load_image(p, flip=False).shape, a.shape)           # and it is a readable JPEG
+        q = os.path.join(tmp, "r%d.png" % i)
+        open(q, "wb").write(g["png%d" % i].tobytes())
+        assert np.array_equal(rb.load_image(q, flip=False), u8.astype(np.float32) / np.float32(255)), i
+    # quality 0 = default 90; other qualities give valid files of monotone size
+    sizes = []
+    for quality in (10, 50, 90, 100):
+        p = os.path.join(tmp, "q%d.jpg" % quality)
+        rb.write_jpg(p, (np.clip(g["img3"], 0, 1) * 255).astype(np.uint8), quality)
+        assert rb.load_image(p, flip=False).shape == g["img3"].shape
+        sizes.append(os.path.getsize(p))
+    assert sizes == sorted(sizes)
