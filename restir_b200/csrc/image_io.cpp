@@ -6,7 +6,7 @@
 // stb_image is a third-party single-header dependency of the reference (external/include/stb_image.h, v2.x); this
 // file restates the formats scenes use -- PNG (RFC 2083 + RFC 1950/1951 inflate), Radiance RGBE, and JPEG (image_jpeg.cpp) --
 // and is pinned against stb itself through oracle/ref_harness.cpp (ref_image_load) on the committed fixtures.
-// Writing: Image::savePNG (image.cpp:41-57) stores 8-bit RGB; here as a valid PNG with stored deflate blocks.
+// Writing: Image::savePNG (image.cpp:41-57) stores 8-bit RGB; here with per-row filter selection and a fixed-Huffman LZ77 deflate.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -598,23 +598,92 @@ bool loadImageRGB(const std::string& path, bool flipY, HostTexture& out, std::st
     return true;
 }
 
-// Image::savePNG (image.cpp:41-57): 8-bit RGB rows, top row first; deflate "stored" blocks (valid, uncompressed)
+// ---- deflate (RFC 1951) with the fixed Huffman code: greedy LZ77 over a 32 KiB window, 3-byte hash chains
+namespace {
+struct BitWriter {
+    std::vector<uint8_t>& out; uint32_t acc = 0; int cnt = 0;
+    void put(uint32_t v, int n) { acc |= v << cnt; cnt += n; while (cnt >= 8) { out.push_back((uint8_t)acc); acc >>= 8; cnt -= 8; } }
+    void putHuff(uint32_t code, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) r |= ((code >> i) & 1u) << (n - 1 - i); put(r, n); }   // codes go MSB first
+    void flush() { if (cnt) { out.push_back((uint8_t)acc); acc = 0; cnt = 0; } }
+};
+void fixedLiteral(BitWriter& w, int sym) {            // RFC 1951 section 3.2.6
+    if (sym < 144) w.putHuff(0x30 + sym, 8);
+    else if (sym < 256) w.putHuff(0x190 + sym - 144, 9);
+    else if (sym < 280) w.putHuff(sym - 256, 7);
+    else w.putHuff(0xc0 + sym - 280, 8);
+}
+void deflateFixed(const std::vector<uint8_t>& in, std::vector<uint8_t>& out) {
+    static const uint16_t lenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint8_t lenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t distBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint8_t distExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    BitWriter w{out};
+    w.put(1, 1); w.put(1, 2);                           // one final block, fixed codes
+    const size_t n = in.size();
+    const int HASH = 1 << 15;
+    std::vector<int> head(HASH, -1), prev(n ? n : 1, -1);
+    auto hashAt = [&](size_t i) { return (int)(((in[i] << 10) ^ (in[i + 1] << 5) ^ in[i + 2]) & (HASH - 1)); };
+    size_t i = 0;
+    while (i < n) {
+        int bestLen = 0, bestDist = 0;
+        if (i + 2 < n) {
+            int h = hashAt(i), cand = head[h], chain = 0;
+            while (cand >= 0 && i - (size_t)cand <= 32768 && chain++ < 48) {
+                int l = 0;
+                const int maxLen = (int)std::min<size_t>(258, n - i);
+                while (l < maxLen && in[cand + l] == in[i + l]) l++;
+                if (l > bestLen) { bestLen = l; bestDist = (int)(i - cand); if (l == maxLen) break; }
+                cand = prev[cand];
+            }
+        }
+        auto insert = [&](size_t k) { if (k + 2 < n) { int h = hashAt(k); prev[k] = head[h]; head[h] = (int)k; } };
+        if (bestLen >= 3) {
+            int lc = 28; while (lenBase[lc] > bestLen) lc--;
+            fixedLiteral(w, 257 + lc); w.put(bestLen - lenBase[lc], lenExtra[lc]);
+            int dc = 29; while (distBase[dc] > bestDist) dc--;
+            w.putHuff(dc, 5); w.put(bestDist - distBase[dc], distExtra[dc]);
+            for (int k = 0; k < bestLen; k++) insert(i + k);
+            i += bestLen;
+        } else {
+            fixedLiteral(w, in[i]);
+            insert(i);
+            i++;
+        }
+    }
+    fixedLiteral(w, 256);
+    w.flush();
+}
+}  // namespace
+
+// Image::savePNG (image.cpp:41-57): 8-bit RGB rows, top row first.  Every row takes the PNG filter with the smallest sum of
+// absolute residuals (the heuristic stb_image_write uses too), then zlib / deflate with the fixed Huffman code.
 bool writePNG(const std::string& path, int W, int H, const uint8_t* rgb, std::string& err) {
     std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     std::vector<uint8_t> ihdr = {(uint8_t)(W >> 24), (uint8_t)(W >> 16), (uint8_t)(W >> 8), (uint8_t)W, (uint8_t)(H >> 24), (uint8_t)(H >> 16), (uint8_t)(H >> 8), (uint8_t)H, 8, 2, 0, 0, 0};
     putChunk(out, "IHDR", ihdr);
+    const size_t rowBytes = (size_t)W * 3;
     std::vector<uint8_t> raw;
-    raw.reserve(((size_t)W * 3 + 1) * H);
-    for (int y = 0; y < H; y++) { raw.push_back(0); raw.insert(raw.end(), rgb + (size_t)y * W * 3, rgb + (size_t)(y + 1) * W * 3); }
-    std::vector<uint8_t> z = {0x78, 0x01};
-    size_t pos = 0;
-    do {
-        size_t n = raw.size() - pos < 65535 ? raw.size() - pos : 65535;
-        z.push_back(pos + n == raw.size() ? 1 : 0);
-        z.push_back((uint8_t)n); z.push_back((uint8_t)(n >> 8)); z.push_back((uint8_t)~n); z.push_back((uint8_t)(~n >> 8));
-        z.insert(z.end(), raw.begin() + pos, raw.begin() + pos + n);
-        pos += n;
-    } while (pos < raw.size());
+    raw.reserve((rowBytes + 1) * H);
+    std::vector<uint8_t> cand(rowBytes), best(rowBytes);
+    for (int y = 0; y < H; y++) {
+        const uint8_t* cur = rgb + rowBytes * y;
+        const uint8_t* up = y ? cur - rowBytes : nullptr;
+        long bestSum = -1; int bestFilter = 0;
+        for (int ft = 0; ft < 5; ft++) {
+            long sum = 0;
+            for (size_t i = 0; i < rowBytes; i++) {
+                int a = i >= 3 ? cur[i - 3] : 0, b = up ? up[i] : 0, c = (up && i >= 3) ? up[i - 3] : 0;
+                int pred = ft == 0 ? 0 : ft == 1 ? a : ft == 2 ? b : ft == 3 ? ((a + b) >> 1) : paeth(a, b, c);
+                cand[i] = (uint8_t)(cur[i] - pred);
+                sum += abs((int)(int8_t)cand[i]);
+            }
+            if (bestSum < 0 || sum < bestSum) { bestSum = sum; bestFilter = ft; best.swap(cand); }
+        }
+        raw.push_back((uint8_t)bestFilter);
+        raw.insert(raw.end(), best.begin(), best.end());
+    }
+    std::vector<uint8_t> z = {0x78, 0x5e};
+    deflateFixed(raw, z);
     uint32_t a = 1, b = 0;
     for (uint8_t v : raw) { a = (a + v) % 65521u; b = (b + a) % 65521u; }
     uint32_t ad = b << 16 | a;

@@ -186,28 +186,54 @@ def test_image_loader_matches_reference_loader():
 
 
 def test_png_writer_round_trip():
-    """Image::savePNG replacement: the written file decodes (own loader and zlib) to the same bytes."""
+    """Image::savePNG replacement: a valid PNG (chunk CRCs, zlib stream with Adler-32, per-row filters, fixed-Huffman LZ77
+    deflate) that decodes to the same bytes with the library's own loader, with zlib + a textbook unfilter, and shrinks
+    smooth images."""
     import struct
     import zlib
+
+    def decode(path):
+        data = open(path, "rb").read()
+        assert data[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, idat, dims = 8, b"", None
+        while pos < len(data):
+            n, tag = struct.unpack(">I4s", data[pos:pos + 8])
+            body = data[pos + 8:pos + 8 + n]
+            assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF, tag
+            if tag == b"IHDR":
+                w, h, depth, ctype, comp, flt, lace = struct.unpack(">IIBBBBB", body)
+                assert (depth, ctype, comp, flt, lace) == (8, 2, 0, 0, 0)
+                dims = (w, h)
+            if tag == b"IDAT":
+                idat += body
+            pos += 12 + n
+        w, h = dims
+        raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w).astype(np.int64)
+        out = np.zeros((h, 3 * w), np.int64)
+        for y in range(h):
+            ft, row = raw[y, 0], raw[y, 1:]
+            for i in range(3 * w):
+                a = out[y, i - 3] if i >= 3 else 0
+                b = out[y - 1, i] if y else 0
+                c = out[y - 1, i - 3] if (y and i >= 3) else 0
+                p = a + b - c
+                pa, pb, pc = abs(p - a), abs(p - b), abs(p - c)
+                pred = (0, a, b, (a + b) >> 1, a if (pa <= pb and pa <= pc) else (b if pb <= pc else c))[ft]
+                out[y, i] = (row[i] + pred) & 255
+        return out.reshape(h, w, 3).astype(np.uint8)
+
     rs = np.random.RandomState(3)
-    img = rs.randint(0, 256, (203, 331, 3)).astype(np.uint8)          # > 64 KiB of scanlines: several stored blocks
-    path = os.path.join(tempfile.mkdtemp(), "out.png")
-    rb.write_png(path, img)
-    assert np.array_equal(rb.load_image(path, flip=False), img.astype(np.float32) / np.float32(255))
-    data = open(path, "rb").read()
-    assert data[:8] == b"\x89PNG\r\n\x1a\n"
-    pos, idat = 8, b""
-    while pos < len(data):
-        n, tag = struct.unpack(">I4s", data[pos:pos + 8])
-        body = data[pos + 8:pos + 8 + n]
-        assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF, tag
-        if tag == b"IHDR":
-            assert struct.unpack(">IIBBBBB", body) == (331, 203, 8, 2, 0, 0, 0)
-        if tag == b"IDAT":
-            idat += body
-        pos += 12 + n
-    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(203, 1 + 331 * 3)
-    assert np.all(raw[:, 0] == 0) and np.array_equal(raw[:, 1:].reshape(203, 331, 3), img)
+    tmp = tempfile.mkdtemp()
+    yy, xx = np.mgrid[0:61, 0:97]
+    smooth = np.stack([xx * 255 // 96, yy * 255 // 60, (xx + yy) * 255 // 156], 2).astype(np.uint8)
+    for name, img in (("noise", rs.randint(0, 256, (23, 31, 3)).astype(np.uint8)), ("smooth", smooth), ("one", np.full((1, 1, 3), 200, np.uint8)),
+                      ("flat", np.full((40, 300, 3), 17, np.uint8))):
+        path = os.path.join(tmp, name + ".png")
+        rb.write_png(path, img)
+        assert np.array_equal(rb.load_image(path, flip=False), img.astype(np.float32) / np.float32(255)), name
+        assert np.array_equal(decode(path), img), name
+    assert os.path.getsize(os.path.join(tmp, "smooth.png")) < smooth.nbytes // 4
+    assert os.path.getsize(os.path.join(tmp, "flat.png")) < 1000
 
 
 def test_textured_scene_file_matches_reference_parser():
