@@ -4,9 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2] [--impl b200|reference]
 
 A step is one frame of the hot path (G-buffer + ReSTIR DI, main.cpp:164-167) of the workload's camera orbit.
-Default workload = BASELINE.json configs[1]: Cornell box, 1920x1080, spatiotemporal reuse (temporal cap 20,
-5 spatial neighbours, r = 30 px), 60-frame orbiting camera.  metric = Mpixel/s (higher is better), ms_per_step =
-ms/frame.  `value` is timed on the device (CUDA events on the launching stream) with everything resident in HBM;
+Default workload = BASELINE.json configs[3] (the configuration the metric and the north-star targets are quoted on):
+procedural 1M-triangle scene with 100k emissive triangles, 3840x2160, spatiotemporal reuse (temporal cap 20, 5 spatial
+neighbours, r = 30 px), 60-frame orbiting camera.  At N = 1 the same JSON line carries a `targets` block with the
+device-timed ms/frame of config4_1080p (the <= 2 ms target), config3 and config2.  metric = Mpixel/s (higher is
+better), ms_per_step = ms/frame.  `value` is timed on the device (CUDA events on the launching stream) with everything resident in HBM;
 `e2e` goes through rstr_render_frame_host (camera in from the host, tone-mapped 8-bit frame back into pinned host
 memory every step).  N > 1: one process per GPU under torchrun, horizontal image strips, reservoir halo rows
 exchanged with NCCL send/recv; strong scaling (the image is fixed).
@@ -139,6 +141,7 @@ def _cpu_frames(kind: str, sd, reuse: float, radius: float, frames: int, warmup:
     from oracle.oracle import Oracle, default_params, make_camera, orbit_camera
 
     orc = Oracle(kind)
+    orc.lib.orc_set_threads(0)      # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers
     W, H = sd.resolution
     so = orc.scene(sd)
     fo = so.frame(W, H)
@@ -155,6 +158,13 @@ def _cpu_frames(kind: str, sd, reuse: float, radius: float, frames: int, warmup:
         fo.gbuffer_update(cam)
     dt = time.perf_counter() - t0
     return dt, orc.threads()
+
+
+def workload_config(name: str, triangles: int, emissive: int) -> dict:
+    """The workload description both arms print (identical dicts: the driver compares them)."""
+    desc, spec, res, reuse, radius = WORKLOADS[name]
+    return {"workload": name, "description": desc, "resolution": list(res), "triangles": int(triangles), "emissive_triangles": int(emissive),
+            "reuse": reuse, "candidates": 32, "temporal_cap": 20, "spatial_neighbours": 5, "spatial_radius_px": radius}
 
 
 def reference_kind() -> str:
@@ -184,7 +194,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "ReSTIR DI Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "resolution": list(res), "triangles": sd.num_tris, "emissive_triangles": sd.num_lights},
+        "config": workload_config(args.workload, sd.num_tris, sd.num_lights),
         "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": threads, "kind": kind,
                          "sample": "%d frames of the orbit at %dx%d (OpenMP over rows, %d threads)" % (steps, res[0], res[1], threads)},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -254,6 +264,56 @@ class StripExchange:
             self.pending = False
 
 
+def measure_motion_rows(sc, base, W, H, rb):
+    """Per-frame bound for the temporal halo: the largest |row(motion) - row| over every consecutive pose pair
+    of the workload's orbit, taken from G-buffer-only renders of the full image (deterministic: every rank computes the
+    same number)."""
+    fr = sc.frame(W, H)
+    for k in range(60):
+        cam = base.orbit(k)
+        fr.gbuffer_render(cam); fr.gbuffer_update(cam)
+    rows = fr.motion_rows()
+    fr.close()
+    return rows
+
+
+def time_workload(rb, name, steps, warmup):
+    """Device-timed ms/frame of another workload on this GPU (the `targets` block): same frame loop, CUDA events on the
+    launching stream around `steps` frames."""
+    desc, spec, res, reuse, radius = WORKLOADS[name]
+    sd = make_scene(spec, res)
+    sc = rb.Scene.from_arrays(sd)
+    fr = sc.frame(*res)
+    base = rb.Camera.from_scene(sd)
+    prm = rb.default_params(reuse=reuse, radius=radius)
+
+    def frame(k):
+        cam = base.orbit(orbit_index(k))
+        fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0); fr.gbuffer_update(cam)
+
+    k = 0
+    for _ in range(max(warmup, 3)):
+        frame(k); k += 1
+    fr.sync()
+    fr.mark(0)
+    for _ in range(steps):
+        frame(k); k += 1
+    fr.mark(1)
+    ms = fr.elapsed_ms(0, 1) / steps
+    stage = {"gbuffer": [], "ris": [], "spatial": []}
+    for _ in range(min(steps, 10)):
+        frame(k); k += 1
+        for n, v in fr.stage_ms().items():
+            if n in stage and v > 0:
+                stage[n].append(v)
+    out = {"ms_per_frame": ms, "mpixel_per_s": res[0] * res[1] / (ms * 1e-3) / 1e6, "resolution": list(res), "triangles": sc.info.numTris,
+           "emissive_triangles": sc.info.numLights, "steps": steps,
+           "stage_ms": {n: (sum(v) / len(v) if v else 0.0) for n, v in stage.items()}}
+    fr.close()
+    sc.close()
+    return out
+
+
 def run_b200(args):
     import restir_b200 as rb
     from restir_b200 import strips
@@ -276,9 +336,13 @@ def run_b200(args):
     P = W * H
     sd = make_scene(spec, res)
     sc = rb.Scene.from_arrays(sd)
-    halo = strips.default_halo(radius) if world > 1 else 0
     base = rb.Camera.from_scene(sd)
     prm = rb.default_params(reuse=reuse, radius=radius)
+    motion_rows = None
+    halo = 0
+    if world > 1:
+        motion_rows = measure_motion_rows(sc, base, W, H, rb) if (reuse & 1) else 0
+        halo = strips.default_halo(radius if (reuse & 2) else 0.0, motion_rows)
     bounds = strips.uniform_bounds(H, world)
     if world > 1 and not args.uniform_strips:
         # measured cost profile: a few frames of the real pipeline on the full image with the kernels' cycle accounting
@@ -357,6 +421,8 @@ def run_b200(args):
     # expensive regions (block-launch overhead, tails), so a few frames are run with the current cuts, every rank
     # reports its measured kernel time, the row costs inside each strip are rescaled by measured / predicted and the
     # cuts are placed again.  Deterministic across ranks: everything is computed from all-gathered numbers.
+    # (These frames jump between camera poses: their reprojections can leave the halo, which is why the halo-miss counter
+    # is reset after the warm-up below and checked only over consecutive frames of the orbit.)
     refine_log = []
     if row_cost is not None:
         for it in range(args.refine):
@@ -379,6 +445,8 @@ def run_b200(args):
     k = 0
     for _ in range(args.warmup):
         frame(k); k += 1
+    # from here on every frame follows its predecessor on the orbit: no read may leave the resident rows
+    fr.halo_miss_reset()
     # ---- pass 1: device-timed throughput (no per-frame synchronisation)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -401,12 +469,18 @@ def run_b200(args):
             if n in stage and v > 0:
                 stage[n].append(v)
     stage_ms = {n: (sum(v) / len(v) if v else 0.0) for n, v in stage.items()}
+    shaded_local = int((fr.read("matid") >= 0).sum())     # rays actually traced: 2 primary per pixel + 1 shadow per shaded pixel
     stage_per_rank = None
     if world > 1:
         t = torch.tensor([stage_ms["gbuffer"], stage_ms["ris"], stage_ms["spatial"]], device="cuda", dtype=torch.float64)
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         stage_per_rank = [[round(float(x), 4) for x in a.cpu()] for a in allt]
+        t = torch.tensor([shaded_local], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        shaded = int(t.item())
+    else:
+        shaded = shaded_local
     # ---- pass 3: end to end through the host-facing call (N = 1) / strips gathered to rank 0 (N > 1)
     npix_local = (rows[1] - rows[0]) * W
     e2e_ms = e2e_sync_ms = None
@@ -497,12 +571,13 @@ def run_b200(args):
         achieved = bpp * strip_px / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
         frame_bytes = BYTES_PER_PIXEL[reuse] * P
         info = sc.info
+        cfg = workload_config(args.workload, info.numTris, info.numLights)
+        traffic = NCU_TRAFFIC.get((args.workload, dom), (None, None))
         line = {
             "metric": "ReSTIR DI Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "resolution": [W, H], "triangles": info.numTris, "emissive_triangles": info.numLights,
-                       "reuse": reuse, "candidates": 32, "temporal_cap": 20, "spatial_neighbours": 5, "spatial_radius_px": radius,
-                       "parallelism": "strips%d" % world, "halo_rows": halo, "strip_bounds": bounds,
+            "config": cfg,
+            "strips": {"parallelism": "strips%d" % world, "halo_rows": halo, "motion_rows_bound": motion_rows, "strip_bounds": bounds,
                        "gbuffer_halo": None if world == 1 else ("rendered locally" if args.render_halo else "received from the neighbours"),
                        "l2": "no explicit flush: the per-frame pixel planes (%.0f MB) exceed the 126 MB L2" % (P * 212 / 1e6)},
             "e2e": {"value": P / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms, "ms_per_step_synchronous_call": e2e_sync_ms,
@@ -512,18 +587,27 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": "k_gbuffer_restir_a" if fused else "k_restir_a", "spatial": "k_restir_b"}[dom],
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC.get((args.workload, dom), (None, None))[0] if world == 1 else None,
-                         "traffic_source": NCU_TRAFFIC.get((args.workload, dom), (None, None))[1],
+                         "traffic": traffic[0] if world == 1 else None, "traffic_source": traffic[1],
                          "algorithmic_bytes_per_pixel": bpp, "kernel_ms": stage_ms[dom],
                          "note": "traversal / light-gather bound kernel; HBM fraction reported as required, rays/s below is the telling figure"},
             "stage_ms": stage_ms,
             "stage_ms_per_rank": stage_per_rank,
             "strip_refinement": refine_log or None,
             "frame_hbm": {"algorithmic_bytes_per_frame": frame_bytes, "achieved_gbs": frame_bytes / (ms_step * 1e-3) / 1e9, "frac_of_peak": frame_bytes / (ms_step * 1e-3) / 1e9 / peak},
-            "rays_per_s": 3.0 * P / (ms_step * 1e-3),
+            "rays_per_s": (2.0 * P + shaded) / (ms_step * 1e-3),
+            "rays_per_frame": {"primary": 2 * P, "shadow_upper_bound": shaded, "note": "2 primary rays per pixel (centre + jittered, one shared walk) + 1 shadow ray per shaded pixel whose reservoir weight is non-zero"},
             "halo_miss": halo_miss,
             "host_build_s": info.buildSeconds,
         }
+        if world == 1 and not args.no_targets:
+            # the north star's numeric targets, device-timed on the same box in the same run
+            line["targets"] = {}
+            for name in ("config4_1080p", "config3", "config2"):
+                if name != args.workload:
+                    line["targets"][name] = time_workload(rb, name, min(args.steps, 60), 5)
+            t4 = line["targets"].get("config4_1080p")
+            if t4:
+                line["targets"]["north_star"] = {"config4_1080p_ms_per_frame": t4["ms_per_frame"], "target_ms": 2.0, "met": t4["ms_per_frame"] <= 2.0}
         if world == 1 and not args.no_cpu_baseline:
             kind = reference_kind()
             t1, threads = cpu_frames(kind, sd, reuse, radius, 1, 0)
@@ -531,22 +615,27 @@ def run_b200(args):
             dt, threads = cpu_frames(kind, sd, reuse, radius, n, 1 if t1 < 5 else 0)
             line["cpu_baseline"] = {"value": P / (dt / n) / 1e6, "unit": "Mpixel/s", "cores": threads, "kind": kind,
                                     "sample": "%d frames of the same orbit at %dx%d, OpenMP over rows" % (n, W, H)}
+        if halo_miss != 0:
+            line["invalid"] = "halo_miss = %d: a strip read rows that were not resident, the image is NOT the single-GPU frame" % halo_miss
         print(json.dumps(line))
     fr.close()
     sc.close()
     if world > 1:
         dist.destroy_process_group()
+    if halo_miss != 0:
+        sys.exit(3)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    # 600 frames = ten laps of the 60-frame orbit clock: ~0.3 s on the device, long enough for stable clocks / nvidia-smi samples
-    ap.add_argument("--steps", type=int, default=600)
-    ap.add_argument("--warmup", type=int, default=30)
+    # 120 frames = one sweep of the 60-frame orbit there and back: ~1.7 s on the device at 4K, long enough for stable clocks / nvidia-smi samples
+    ap.add_argument("--steps", type=int, default=120)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-targets", action="store_true", help="N = 1: skip the `targets` block (device-timed config4_1080p / config3 / config2)")
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
     ap.add_argument("--refine", type=int, default=4, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
     ap.add_argument("--no-fusion", action="store_true", help="separate G-buffer and phase-A kernels instead of the fused one (A/B)")

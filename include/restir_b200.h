@@ -247,6 +247,12 @@ void* rstr_frame_stream(RstrFrame*);
 /* number of temporal / spatial neighbour reads that fell outside the rows resident in a strip frame (must stay 0
  * for results identical to the single-GPU frame; widen `halo` otherwise) */
 int rstr_frame_halo_miss(RstrFrame*, unsigned int* count);
+/* zero that counter (stream-ordered): e.g. after warm-up frames that jumped between camera poses */
+int rstr_frame_halo_miss_reset(RstrFrame*);
+/* per-frame bound for the temporal halo: the largest |row(motion) - row| over the pixels whose reprojection
+ * (gbuffer.cu:49-55) landed on screen, over every G-buffer rendered since the frame was created / the last reset.  A strip
+ * frame needs halo > this value (and > ceil(spatialRadius)) for rstr_frame_halo_miss to stay 0. */
+int rstr_frame_motion_rows(RstrFrame*, unsigned int* maxRows, int reset);
 /* page-locked host memory for rstr_render_frame_host / rstr_frame_read targets */
 void* rstr_host_alloc(size_t bytes);
 void rstr_host_free(void*);

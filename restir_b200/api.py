@@ -168,6 +168,8 @@ def lib() -> C.CDLL:
     L.rstr_frame_stream.restype = vp
     L.rstr_frame_stream.argtypes = [vp]
     L.rstr_frame_halo_miss.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.rstr_frame_halo_miss_reset.argtypes = [vp]
+    L.rstr_frame_motion_rows.argtypes = [vp, C.POINTER(C.c_uint), ip]
     L.rstr_frame_plane_row.argtypes = [vp, ip, ip, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.rstr_frame_copy_rows.argtypes = [vp, vp, ip, ip, ip]
     L.rstr_frame_read_device.argtypes = [vp, ip, vp, C.c_size_t]
@@ -405,6 +407,15 @@ class Frame:
     def halo_miss(self) -> int:
         v = C.c_uint(0)
         _check(lib().rstr_frame_halo_miss(self.f, C.byref(v)))
+        return int(v.value)
+
+    def halo_miss_reset(self) -> None:
+        _check(lib().rstr_frame_halo_miss_reset(self.f))
+
+    def motion_rows(self, reset: bool = False) -> int:
+        """Largest |row(motion) - row| seen by the G-buffer kernels so far: the temporal halo must exceed it."""
+        v = C.c_uint(0)
+        _check(lib().rstr_frame_motion_rows(self.f, C.byref(v), 1 if reset else 0))
         return int(v.value)
 
     def stream(self) -> int:

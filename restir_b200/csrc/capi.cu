@@ -33,6 +33,7 @@ struct RstrScene {
     void* dMaterials = nullptr; void* dAlias = nullptr; void* dLights = nullptr;
     void* dTexData = nullptr; void* dTexInfo = nullptr; void* dTriUV = nullptr; void* dEnvAlias = nullptr; void* dEnvDir = nullptr;
     size_t deviceBytes = 0;
+    bool uploaded = false;      // set only after every device array exists and DevScene is filled
     int traversalMode = RS_TRAVERSAL_FAST;
 };
 
@@ -97,7 +98,7 @@ static FrameDev toFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
     d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
     d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
-    d.hit = f->hit; d.hitMR = f->hitMR; d.rowCost = f->rowCost; d.haloMiss = f->haloMiss; d.queue = f->queue; d.queueCount = f->queueCount;
+    d.hit = f->hit; d.hitMR = f->hitMR; d.rowCost = f->rowCost; d.haloMiss = f->haloMiss; d.motionRows = f->haloMiss + 1; d.queue = f->queue; d.queueCount = f->queueCount;
     return d;
 }
 
@@ -139,8 +140,16 @@ static int finishScene(RstrScene* sc, RstrScene** out) {
     return RSTR_OK;
 }
 
+static void freeSceneDevice(RstrScene* sc) {
+    void** all[] = {&sc->dNodes, &sc->dTriGeom, &sc->dTriNorm, &sc->dFastNodes, &sc->dPrimToFast, &sc->dFallback, &sc->dRank, &sc->dMaterials,
+                    &sc->dAlias, &sc->dLights, &sc->dTexData, &sc->dTexInfo, &sc->dTriUV, &sc->dEnvAlias, &sc->dEnvDir};
+    for (void** p : all) { cudaFree(*p); *p = nullptr; }
+    sc->uploaded = false;
+    sc->deviceBytes = 0;
+}
+
 static int ensureUploaded(RstrScene* sc) {
-    if (sc->dNodes) return RSTR_OK;
+    if (sc->uploaded) return RSTR_OK;
     HostScene& hs = sc->hs;
     size_t total = 0;
     cudaError_t e;
@@ -153,15 +162,13 @@ static int ensureUploaded(RstrScene* sc) {
         (e = upload(&sc->dTriUV, hs.triUV, total)) != cudaSuccess || (e = upload(&sc->dEnvAlias, hs.envAlias, total)) != cudaSuccess ||
         (e = upload(&sc->dEnvDir, hs.envDir, total)) != cudaSuccess) {
         std::string m = std::string("scene upload failed: ") + cudaGetErrorString(e);
-        cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
-        cudaFree(sc->dFastNodes); cudaFree(sc->dPrimToFast);
-        cudaFree(sc->dTexData); cudaFree(sc->dTexInfo); cudaFree(sc->dTriUV); cudaFree(sc->dEnvAlias); cudaFree(sc->dEnvDir);
-        sc->dTexData = sc->dTexInfo = sc->dTriUV = sc->dEnvAlias = sc->dEnvDir = nullptr;
-        sc->dNodes = sc->dTriGeom = sc->dTriNorm = sc->dMaterials = sc->dAlias = sc->dLights = sc->dFastNodes = sc->dPrimToFast = nullptr;
+        freeSceneDevice(sc);
         return fail(RSTR_ERR_CUDA, m);
     }
-    if (cudaMalloc(&sc->dFallback, 4 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(sc->dFallback, 0, 4 * sizeof(unsigned int)) != cudaSuccess)
+    if (cudaMalloc(&sc->dFallback, 4 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(sc->dFallback, 0, 4 * sizeof(unsigned int)) != cudaSuccess) {
+        freeSceneDevice(sc);
         return fail(RSTR_ERR_CUDA, "scene upload failed: counter");
+    }
     sc->deviceBytes = total;
     DevScene& d = sc->dev;
     d.fallbackRays = (unsigned int*)sc->dFallback;
@@ -178,6 +185,7 @@ static int ensureUploaded(RstrScene* sc) {
     d.sumLightPowerInv = hs.sumLightPowerInv;
     d.rootRef = hs.rootRef;
     memcpy(d.rootMin, &hs.rootBox.pMin, 12); memcpy(d.rootMax, &hs.rootBox.pMax, 12);
+    sc->uploaded = true;
     return RSTR_OK;
 }
 
@@ -246,9 +254,7 @@ int rstr_scene_load_file(const char* path, RstrScene** out, RstrCamera* cameraOu
 
 int rstr_scene_destroy(RstrScene* sc) {
     if (!sc) return RSTR_OK;
-    cudaFree(sc->dNodes); cudaFree(sc->dTriGeom); cudaFree(sc->dTriNorm); cudaFree(sc->dMaterials); cudaFree(sc->dAlias); cudaFree(sc->dLights);
-    cudaFree(sc->dFastNodes); cudaFree(sc->dPrimToFast); cudaFree(sc->dFallback); cudaFree(sc->dRank);
-    cudaFree(sc->dTexData); cudaFree(sc->dTexInfo); cudaFree(sc->dTriUV); cudaFree(sc->dEnvAlias); cudaFree(sc->dEnvDir);
+    freeSceneDevice(sc);
     delete sc;
     return RSTR_OK;
 }
@@ -392,7 +398,7 @@ int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int
     alloc((void**)&f->hit, n * sizeof(HitRec));
     if (sc->hs.anyMRMaps) alloc((void**)&f->hitMR, n * sizeof(float2));
     alloc((void**)&f->ldr, n * sizeof(uchar4));
-    alloc((void**)&f->haloMiss, sizeof(unsigned int));
+    alloc((void**)&f->haloMiss, 4 * sizeof(unsigned int));     // [0] halo misses, [1] max |row(motion) - row|
     alloc((void**)&f->queue, n * sizeof(int));
     alloc((void**)&f->queueCount, 4 * sizeof(unsigned int));
     if (e == cudaSuccess) {
@@ -512,8 +518,9 @@ int rstr_restir_phase_b_pass(RstrFrame* f, const RstrCamera* cam, const RstrPara
     int rc = checkCam(f, cam);
     if (rc) return rc;
     (void)looper;
+    if (!prm || prm->numCandidates < 0 || prm->numSpatial < 0 || prm->temporalCap < 1) return fail(RSTR_ERR_ARG, "bad RstrParams");
     const int passes = (prm->reuse & 2) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
-    if (passes && (pass < 1 || pass > passes)) return fail(RSTR_ERR_ARG, "rstr_restir_phase_b_pass: pass out of range");
+    if ((passes && (pass < 1 || pass > passes)) || (!passes && pass != 1)) return fail(RSTR_ERR_ARG, "rstr_restir_phase_b_pass: pass out of range");
     if (passes) {
         if (passes > 1 && (rc = ensureTemp2(f))) return rc;
         FrameDev d = toFrameDev(f, f->row0, f->row1);
@@ -665,7 +672,7 @@ int rstr_render_frame_host(RstrFrame* f, const RstrCamera* cam, const RstrParams
     if (rc) return rc;
     rc = rstr_tonemap(f, toneMapping, 1.f);
     if (rc) return rc;
-    rstr_gbuffer_update(f, cam);
+    if ((rc = rstr_gbuffer_update(f, cam))) return rc;
     size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
     if (hostLdr) {
         if (bytes != n * sizeof(uchar4)) return fail(RSTR_ERR_ARG, "rstr_render_frame_host: size mismatch");
@@ -700,7 +707,7 @@ int rstr_render_frame_host_async(RstrFrame* f, const RstrCamera* cam, const Rstr
     stageEnd(f, RSTR_T_TONEMAP);
     g_launches++;
     CU(cudaGetLastError());
-    rstr_gbuffer_update(f, cam);
+    if ((rc = rstr_gbuffer_update(f, cam))) return rc;
     CU(cudaEventRecord(f->evRendered[slot], f->stream));
     CU(cudaStreamWaitEvent(f->copyStream, f->evRendered[slot], 0));
     CU(cudaMemcpyAsync(hostLdr, f->ldrB[slot], bytes, cudaMemcpyDeviceToHost, f->copyStream));
@@ -823,9 +830,25 @@ int rstr_frame_halo_miss(RstrFrame* f, unsigned int* out) {
     return RSTR_OK;
 }
 
+int rstr_frame_halo_miss_reset(RstrFrame* f) {
+    if (!f) return fail(RSTR_ERR_ARG, "rstr_frame_halo_miss_reset: null frame");
+    CU(cudaMemsetAsync(f->haloMiss, 0, sizeof(unsigned int), f->stream));
+    return RSTR_OK;
+}
+
+int rstr_frame_motion_rows(RstrFrame* f, unsigned int* out, int reset) {
+    if (!f || !out) return fail(RSTR_ERR_ARG, "rstr_frame_motion_rows: bad argument");
+    int rc = flushGBuffer(f);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, f->haloMiss + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, f->stream));
+    if (reset) CU(cudaMemsetAsync(f->haloMiss + 1, 0, sizeof(unsigned int), f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+    return RSTR_OK;
+}
+
 int rstr_frame_plane_row(RstrFrame* f, int plane, int row, void** devPtr, size_t* rowBytes) {
     if (!f || !devPtr || !rowBytes) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: bad argument");
-    if (row < f->bufRow0 || row > f->bufRow0 + f->bufRows) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: row not resident");
+    if (row < f->bufRow0 || row >= f->bufRow0 + f->bufRows) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: row not resident");
     {
         int rc = flushGBuffer(f);
         if (rc) return rc;
@@ -860,6 +883,9 @@ int rstr_frame_copy_rows(RstrFrame* dst, RstrFrame* src, int plane, int row0, in
     CU(cudaEventRecord(src->xfer, src->stream));
     CU(cudaStreamWaitEvent(dst->stream, src->xfer, 0));
     CU(cudaMemcpyAsync(pd, ps, rb * (size_t)(row1 - row0), cudaMemcpyDefault, dst->stream));
+    // ... and src must not overwrite the rows (next frame's phase A) while dst's stream is still reading them
+    CU(cudaEventRecord(dst->xfer, dst->stream));
+    CU(cudaStreamWaitEvent(src->stream, dst->xfer, 0));
     return RSTR_OK;
 }
 

@@ -92,6 +92,7 @@ struct FrameDev {
     int* queue;                // pixels deferred to the reference-order fix-up kernel
     unsigned int* queueCount;
     unsigned int* haloMiss;    // count of neighbour / reprojection reads that fell outside the resident rows
+    unsigned int* motionRows;  // running max |row(motion) - row| of the reprojected pixels (bound for the temporal halo)
     unsigned long long* rowCost;  // optional [ceil(H / 8)] cycle accumulators (rstr_frame_row_cost), else null
 };
 

@@ -895,6 +895,10 @@ RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& last
         int lx, ly;
         rasterCoord(lastCam, pos, lx, ly);                                           // gbuffer.cu:49-55
         int motion = (lx >= 0 && lx < f.W && ly >= 0 && ly < f.H) ? ly * f.W + lx : -1;
+        if (motion >= 0) {                       // per-frame bound on the temporal halo: max |row' - row|
+            unsigned int dy = (unsigned int)abs(ly - y);
+            if (dy > *f.motionRows) atomicMax(f.motionRows, dy);
+        }
         f.geom[0][li] = make_float4(nrm.x, nrm.y, nrm.z, depth);
         f.matId[0][li] = matId;
         f.albedoMotion[li] = make_float4(albedo.x, albedo.y, albedo.z, __int_as_float(motion));

@@ -1,15 +1,20 @@
 """Horizontal-strip decomposition of the image across GPUs.
 
 The path shards by image rows: scene, BVH and light tables are replicated, pixel indices and RNG streams stay
-global (restir.cu:126-127), so a strip computes exactly the pixels the full frame would.  Two neighbour
-exchanges per frame carry reservoir rows only (the G-buffer of the halo rows is re-rendered locally):
+global (restir.cu:126-127), so a strip computes exactly the pixels the full frame would.  A strip keeps ``halo``
+rows of its neighbours' planes on each side; ONE neighbour exchange per frame, between phase A and phase B, fills them:
 
-* E2, between phase A and phase B: post-temporal reservoirs (plane ``resv_temp``) for the spatial radius;
-* E1, after phase B: history reservoirs (plane ``resv_history``) for next frame's temporal reprojection.
+* current G-buffer rows (``geom_cur``, ``matid_cur``) and post-temporal reservoirs (``resv_temp``): read by THIS
+  frame's spatial pass within ceil(radius) + 1 rows (restir.cu:53-56);
+* the history reservoirs phase A just wrote (``resv_out``; phase B does not touch them, restir.cu:211-212): read by
+  the NEXT frame's temporal step at the reprojected row (restir.cu:23), together with the then-previous G-buffer rows.
+
+``halo`` must therefore exceed both ceil(radius) and the largest vertical reprojection distance of any pixel
+(``Frame.motion_rows``); a read outside the resident rows is counted (``Frame.halo_miss``) and must stay 0.
 
 Strips are described by ``bounds``: N+1 increasing row indices, rank r owns rows [bounds[r], bounds[r+1]).
 Equal-height strips balance badly (sky rows cost almost nothing, ground rows everything), so ``balanced_bounds``
-places the cuts by a per-row cost estimate taken from one G-buffer of the first frame.
+places the cuts by a measured per-row cost (``Frame.row_cost``), refined in a closed loop by ``refine_row_cost``.
 """
 from __future__ import annotations
 
@@ -95,6 +100,7 @@ def exchange_plan(height: int, world: int, halo: int, bounds=None) -> list[tuple
     return plan
 
 
-def default_halo(spatial_radius: float, temporal_margin: int = 32) -> int:
-    """Halo rows: ceil(radius)+1 for the spatial disk (restir.cu:53-55), >= temporal_margin for reprojection."""
-    return max(int(math.ceil(spatial_radius)) + 1, int(temporal_margin))
+def default_halo(spatial_radius: float, motion_rows: int = 31) -> int:
+    """Halo rows: ceil(radius)+1 for the spatial disk (restir.cu:53-55) and motion_rows+1 for the reprojection
+    (restir.cu:23; ``motion_rows`` = the measured per-frame bound ``Frame.motion_rows`` over the camera path)."""
+    return max(int(math.ceil(spatial_radius)) + 1, int(motion_rows) + 1)
