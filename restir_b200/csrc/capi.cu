@@ -124,15 +124,9 @@ static int finishScene(RstrScene* sc, RstrScene** out) {
         delete sc;
         return fail(RSTR_ERR_LIMIT, b);
     }
-    if (sc->hs.fastDepth > RS_STACK_DEPTH) {
+    if (sc->hs.fastDepth > RS_PACKET_STACK) {
         char b[160];
-        snprintf(b, sizeof b, "traced tree depth %d exceeds the traversal stack (%d)", sc->hs.fastDepth, RS_STACK_DEPTH);
-        delete sc;
-        return fail(RSTR_ERR_LIMIT, b);
-    }
-    if (RS_BVH4 && 3 * sc->hs.fastDepth4 + 1 > RS_STACK_DEPTH) {
-        char b[160];
-        snprintf(b, sizeof b, "traced tree depth %d exceeds the traversal stack (%d entries, 3 per level)", sc->hs.fastDepth4, RS_STACK_DEPTH);
+        snprintf(b, sizeof b, "traced tree depth %d exceeds the packet traversal stack (%d)", sc->hs.fastDepth, RS_PACKET_STACK);
         delete sc;
         return fail(RSTR_ERR_LIMIT, b);
     }
@@ -154,7 +148,7 @@ static int ensureUploaded(RstrScene* sc) {
     size_t total = 0;
     cudaError_t e;
     if ((e = upload(&sc->dNodes, hs.packed, total)) != cudaSuccess || (e = upload(&sc->dTriGeom, hs.fastTris, total)) != cudaSuccess ||
-        (e = (RS_BVH4 ? upload(&sc->dFastNodes, hs.fastNodes4, total) : upload(&sc->dFastNodes, hs.fastNodes, total))) != cudaSuccess || (e = upload(&sc->dRank, hs.rank, total)) != cudaSuccess || (e = upload(&sc->dPrimToFast, hs.primToFast, total)) != cudaSuccess ||
+        (e = upload(&sc->dFastNodes, hs.fastNodes, total)) != cudaSuccess || (e = upload(&sc->dRank, hs.rank, total)) != cudaSuccess || (e = upload(&sc->dPrimToFast, hs.primToFast, total)) != cudaSuccess ||
 
         (e = upload(&sc->dTriNorm, hs.triNorm, total)) != cudaSuccess || (e = upload(&sc->dMaterials, hs.materials, total)) != cudaSuccess ||
         (e = upload(&sc->dAlias, hs.alias, total)) != cudaSuccess || (e = upload(&sc->dLights, hs.lights, total)) != cudaSuccess ||
@@ -175,7 +169,7 @@ static int ensureUploaded(RstrScene* sc) {
     d.nodes = (const float4*)sc->dNodes; d.triGeom = (const float4*)sc->dTriGeom; d.triNorm = (const float4*)sc->dTriNorm;
     d.materials = (const RstrMaterial*)sc->dMaterials; d.alias = (const float2*)sc->dAlias; d.lights = (const float4*)sc->dLights;
     d.fastNodes = (const float4*)sc->dFastNodes; d.primToFast = (const int*)sc->dPrimToFast; d.rank = (const int*)sc->dRank;
-    d.numTris = hs.T; d.numFastNodes = (int)(RS_BVH4 ? hs.fastNodes4.size() : hs.fastNodes.size()); d.fastRoot = RS_BVH4 ? hs.fastRoot4 : hs.fastRoot; d.traversal = sc->traversalMode;
+    d.numTris = hs.T; d.numFastNodes = (int)hs.fastNodes.size(); d.fastRoot = hs.fastRoot; d.traversal = sc->traversalMode;
     memcpy(d.fastRootMin, hs.fastRootMin, 12); memcpy(d.fastRootMax, hs.fastRootMax, 12);
     d.numLights = (int)hs.alias.size();           // lightSampler.length: emissive triangles (+ the environment map, last)
     d.texData = (const float4*)sc->dTexData; d.texInfo = (const int4*)sc->dTexInfo; d.triUV = (const float4*)sc->dTriUV;

@@ -8,14 +8,15 @@
 
 namespace rs {
 
-#define RS_STACK_DEPTH 96      /* traversal stack entries; deeper trees are rejected at scene creation */
+#define RS_STACK_DEPTH 96      /* per-lane traversal stack entries (reference-order walk, shadow rays); deeper trees are rejected at scene creation */
+#define RS_PACKET_STACK 64     /* per-warp stack entries of the packet walk of the traced tree (one entry per level at most) */
 
 #define RS_TRAVERSAL_FAST 0     /* binned-SAH tree; reference-order walk only for near-axis and near-tie rays */
 #define RS_TRAVERSAL_EXACT 1    /* reference-order walk of the reference tree for every ray */
 
 struct DevScene {
     const float4* nodes;       // PackedNode[] (reference tree), 4 x float4 each
-    const float4* fastNodes;   // FastNode[] (traced tree), 4 x float4 each (FastNode4[], 8 x float4, when RS_BVH4 == 1)
+    const float4* fastNodes;   // FastNode[] (traced tree), 4 x float4 each
     const float4* triGeom;     // TriGeom[] in the traced tree's leaf order, 3 x float4 each
     const float4* triNorm;     // TriNorm[] in original primitive order, 3 x float4 each
     const int* primToFast;     // original primitive id -> triGeom index

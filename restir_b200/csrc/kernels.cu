@@ -212,6 +212,12 @@ struct Stack {
     RS_D int ref(int sp) const { return sp < RS_SMEM_STACK ? sRef[sp * RS_BLOCK] : lRef[sp - RS_SMEM_STACK]; }
     RS_D float t(int sp) const { return sp < RS_SMEM_STACK ? sT[sp * RS_BLOCK] : lT[sp - RS_SMEM_STACK]; }
 };
+// any-hit rays only push node references: no distance plane
+#define RS_DECLARE_REFSTACK(name)                                      \
+    __shared__ int name##_ref[RS_SMEM_STACK][RS_BLOCK];                \
+    Stack name;                                                        \
+    name.sRef = &name##_ref[0][threadIdx.x];                           \
+    name.sT = nullptr
 #define RS_DECLARE_STACK(name)                                         \
     __shared__ int name##_ref[RS_SMEM_STACK][RS_BLOCK];                \
     __shared__ float name##_t[RS_SMEM_STACK][RS_BLOCK];                \
@@ -313,268 +319,242 @@ RS_D bool slabHit(const RayF& f, float lx, float ly, float lz, float hx, float h
     return tEntry <= tExit;
 }
 
-// 4-wide node: slab tests of the four children from six LDG.128 (one plane each) + the links; the children that are
-// hit come back as sort keys (entry distance with the slot number in the two lowest mantissa bits: distances are
-// non-negative, so integer order = float order), ordered near to far by a 5-exchange network.  The two cleared bits
-// make the stored distance at most 3 ulp too small, i.e. culling at pop time stays conservative.
-#define RS_MISS 0x7fffffff
-struct Node4Hits { int k0, k1, k2, k3; int4 ch; };
-RS_D int node4Child(const Node4Hits& h, int key) {
-    int i = key & 3;
-    return i == 0 ? h.ch.x : (i == 1 ? h.ch.y : (i == 2 ? h.ch.z : h.ch.w));
-}
-RS_D float node4T(int key) { return __int_as_float(key & ~3); }
-RS_D Node4Hits node4Test(const DevScene& s, const RayF& f, int node, float tLimit) {
-#ifdef RS_DEBUG_BOUNDS
-    if (node < 0 || node >= s.numFastNodes) { printf("node4Test: bad node %d (of %d) block %d,%d thread %d\n", node, s.numFastNodes, blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
-#endif
-    const float4* np = s.fastNodes + 8 * (size_t)node;
-    float4 lo = __ldg(np), hi = __ldg(np + 1);
-    float4 t0, t1;
-#define RS_AXIS_FIRST(c, I, O)                                                                          \
-    { float a0 = __fmaf_rn(lo.c, I, O), a1 = __fmaf_rn(hi.c, I, O); t0.c = fminf(a0, a1); t1.c = fmaxf(a0, a1); }
-#define RS_AXIS_NEXT(c, I, O)                                                                           \
-    { float a0 = __fmaf_rn(lo.c, I, O), a1 = __fmaf_rn(hi.c, I, O); t0.c = fmaxf(t0.c, fminf(a0, a1)); t1.c = fminf(t1.c, fmaxf(a0, a1)); }
-    RS_AXIS_FIRST(x, f.inv.x, f.oi.x) RS_AXIS_FIRST(y, f.inv.x, f.oi.x) RS_AXIS_FIRST(z, f.inv.x, f.oi.x) RS_AXIS_FIRST(w, f.inv.x, f.oi.x)
-    lo = __ldg(np + 2); hi = __ldg(np + 3);
-    RS_AXIS_NEXT(x, f.inv.y, f.oi.y) RS_AXIS_NEXT(y, f.inv.y, f.oi.y) RS_AXIS_NEXT(z, f.inv.y, f.oi.y) RS_AXIS_NEXT(w, f.inv.y, f.oi.y)
-    lo = __ldg(np + 4); hi = __ldg(np + 5);
-    RS_AXIS_NEXT(x, f.inv.z, f.oi.z) RS_AXIS_NEXT(y, f.inv.z, f.oi.z) RS_AXIS_NEXT(z, f.inv.z, f.oi.z) RS_AXIS_NEXT(w, f.inv.z, f.oi.z)
-#undef RS_AXIS_FIRST
-#undef RS_AXIS_NEXT
-    Node4Hits h;
-    h.ch = __ldg((const int4*)(np + 6));
-    // an unused slot has child == RS_MISS (its box cannot be relied on: the slab test is symmetric in lo / hi)
-#define RS_KEY(c, i) ((fmaxf(t0.c, 0.f) <= fminf(t1.c, tLimit) && h.ch.c != RS_MISS) ? ((__float_as_int(fmaxf(t0.c, 0.f)) & ~3) | i) : RS_MISS)
-    int a = RS_KEY(x, 0), b = RS_KEY(y, 1), c = RS_KEY(z, 2), d = RS_KEY(w, 3);
-#undef RS_KEY
-    int lo01 = min(a, b), hi01 = max(a, b), lo23 = min(c, d), hi23 = max(c, d);
-    h.k0 = min(lo01, lo23);
-    int m1 = max(lo01, lo23), m2 = min(hi01, hi23);
-    h.k3 = max(hi01, hi23);
-    h.k1 = min(m1, m2); h.k2 = max(m1, m2);
-    return h;
-}
-
 // ---- what the reference's walk finds, without walking its tree ----
 // The reference reaches a triangle only through nested boxes that end in the triangle's own AABB (1 triangle per leaf,
 // bvh.cpp:25), each tested with the predicate of bvh.h:85-157 and pruned by "box distance < closest" (scene.h:260).
 // Both the predicate and the box distance are monotone along the nesting (an enclosing box passes whenever the enclosed
 // one does, and is entered no later), so the whole chain reduces to the leaf box: the reference finds triangle T iff
 //   T is hit (intersections.h:17-53),  the predicate holds for AABB(T),  boxDistance(AABB(T)) < closest  and  d < closest,
-// with candidates visited in the order of the ray's MTBVH ordering (bvh.cpp:156-193 -> DevScene::rank).  Because
-// boxDistance <= d up to rounding, the order only matters between hits whose distances differ by less than the
-// Moller-Trumbore rounding error; the traced-tree walk keeps the best hit plus one such runner-up and replays the
-// reference's two visits.  Up to four mutually near hits are replayed; more are left to the reference-order walk (fix-up kernel).
-struct Cand { float d, bx, by, tBox, err; int prim; };
+// with candidates visited in the order of the ray's MTBVH ordering (bvh.cpp:156-193 -> DevScene::rank).  The distances d
+// are computed with the reference's own arithmetic, so the order only matters between hits that can prune one another:
+// hits whose distances differ by less than the Moller-Trumbore rounding error (boxDistance <= d up to that error).  Any
+// CONSERVATIVE walk of any tree that offers every triangle near the ray to this criterion therefore finds the
+// reference's hit; the walk keeps the best hit plus the hits inside a band behind it and replays the reference's visits of
+// those in its order.  More than RS_MAX_TIES such hits leave the pixel undecided (fix-up kernel, reference-order walk).
+#define RS_TIE_BAND 1e-4f     /* relative width of the near-tie band (>= 4 x the error bound of the best hit) */
+#define RS_MAX_TIES 3
+#define RS_DONE 0x7fffffff
+#define RS_WSTACK RS_PACKET_STACK
 
 RS_D bool leafBox(const RayT& r, const Tri& t, float& tBox) {
     return boxHit(r, gmin(gmin(t.v0, t.v1), t.v2), gmax(gmax(t.v0, t.v1), t.v2), tBox);
 }
 
-#define RS_TIE_BAND 1e-4f     /* coarse relative band that triggers the error-bound computation */
-RS_D bool nearTie(const Cand& a, const Cand& b) {
-    return fabsf(a.d - b.d) <= a.err + b.err + 1e-6f * fmaxf(a.d, b.d);
-}
-
-// Closest hit over the traced tree as a resumable state machine ("while-while": lanes first descend to a leaf, then
-// test triangles together).  closestRun returns true when the ray is finished; with minActive > 0 it returns false
-// once fewer lanes than that are still traversing, so that a caller can refill idle lanes (a persistent-threads
-// G-buffer kernel built on this was 9-20 % SLOWER than the plain grid on B200 and was removed, profiles/README.md).
-#define RS_DONE 0x7fffffff
-#define RS_MAX_EXTRA 2     /* near-tie candidates beyond best + second, kept in local memory (corners where 3-4 surfaces meet) */
-struct ClosestState {
-    RayT r;
-    RayF f;
-    Cand best, second;
-    Cand extra[RS_MAX_EXTRA];
-    float limit;     // best.d widened by twice the coarse band: near-tie candidates behind the best hit are still visited
-    int sp, cur;
-    int nExtra;
-    bool triple;     // more mutually near hits than can be stored: undecided
+// near-tie candidates of one ray: RS_MAX_TIES {triangle, distance} pairs per thread in shared memory, [entry][thread]
+struct TieStore {
+    int* fi;
+    float* d;
 };
 
-RS_D void closestBegin(const DevScene& s, ClosestState& st) {
-    st.f = makeRayF(st.r);
-    st.best.d = FLT_MAX; st.best.prim = -1; st.best.bx = st.best.by = st.best.tBox = st.best.err = 0.f;
-    st.second = st.best;
-    st.nExtra = 0;
-    st.triple = false;
-    st.limit = FLT_MAX;
-    st.sp = 0;
-    float t0;
-    st.cur = slabHit(st.f, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], FLT_MAX, t0)
-                 ? s.fastRoot : RS_DONE;
+// Running result of one closest-hit ray: 16 registers.  The slab test uses cinv / oi (explicit FMAs on the padded boxes
+// of the traced tree); everything that decides which triangle is reported (triHit, leafBox) uses o / d with the
+// reference's arithmetic.
+struct PRay {
+    f3 o, d;
+    f3 cinv, oi;      // 1 / d with |d| kept >= 1e-20 (a zero component would give inf * 0 = NaN), -o / d
+    float bestD;      // distance of the best hit so far (FLT_MAX: none)
+    float band;       // absolute width of the near-tie band behind bestD: max(RS_TIE_BAND * bestD, 4 * errorBound(best))
+    float limit;      // bestD + 2 * band: nothing beyond matters.  < 0: no ray (lane outside the image)
+    int bestFi;       // leaf-order index of the best hit's triangle, -1: none
+    int nt;           // near-tie candidates in the TieStore; -1: more than RS_MAX_TIES (undecided)
+};
+
+RS_D PRay prayBegin(f3 o, f3 d, bool active) {
+    PRay p;
+    p.o = o; p.d = d;
+    float dx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
+    float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
+    float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
+    p.cinv = mk3(1.f / dx, 1.f / dy, 1.f / dz);
+    p.oi = mk3(-o.x * p.cinv.x, -o.y * p.cinv.y, -o.z * p.cinv.z);
+    p.bestD = FLT_MAX; p.band = 0.f; p.limit = active ? FLT_MAX : -1.f;
+    p.bestFi = -1; p.nt = 0;
+    return p;
 }
 
-RS_D int closestPop(ClosestState& st, const Stack& stack) {
-    while (st.sp > 0) {
-        --st.sp;
-        if (stack.t(st.sp) <= st.limit) return stack.ref(st.sp);
-    }
-    return RS_DONE;
+RS_D bool slabHitP(const PRay& p, float lx, float ly, float lz, float hx, float hy, float hz, float& tEntry) {
+    float x0 = __fmaf_rn(lx, p.cinv.x, p.oi.x), x1 = __fmaf_rn(hx, p.cinv.x, p.oi.x);
+    float y0 = __fmaf_rn(ly, p.cinv.y, p.oi.y), y1 = __fmaf_rn(hy, p.cinv.y, p.oi.y);
+    float z0 = __fmaf_rn(lz, p.cinv.z, p.oi.z), z1 = __fmaf_rn(hz, p.cinv.z, p.oi.z);
+    tEntry = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
+    float tExit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), p.limit));
+    return tEntry <= tExit;
 }
 
-// one triangle of a visited leaf offered to the ray's running result (best hit + its near ties)
-RS_D void closestOffer(ClosestState& st, const Tri& t) {
-    const RayT& r = st.r;
-    Cand x;
-    if (!triHit(r, t.v0, t.v1, t.v2, x.bx, x.by, x.d)) return;
-    if (!(x.d <= st.limit)) return;
-    if (!leafBox(r, t, x.tBox)) return;               // the reference never sees this triangle
-    x.prim = t.prim;
-    x.err = -1.f;
-    if (st.best.prim >= 0 && fabsf(x.d - st.best.d) <= RS_TIE_BAND * fmaxf(x.d, st.best.d)) {
-        x.err = triDistError(r, t.v0, t.v1, t.v2);
-        if (nearTie(x, st.best)) {
-            Cand keep = x;                      // the candidate that does not become `best`
-            if (x.d < st.best.d) { keep = st.best; st.best = x; st.limit = x.d * (1.f + 2.f * RS_TIE_BAND); }
-            if (st.second.prim < 0) st.second = keep;
-            else if (st.nExtra < RS_MAX_EXTRA) st.extra[st.nExtra++] = keep;
-            else st.triple = true;
-            return;
-        }
-    }
-    if (x.d < st.best.d) {
-        if (x.err < 0.f) x.err = triDistError(r, t.v0, t.v1, t.v2);
-        st.best = x; st.second.prim = -1; st.nExtra = 0; st.triple = false;     // anything near the old best is now irrelevant
-        st.limit = x.d * (1.f + 2.f * RS_TIE_BAND);
-    }
+// intersections.h:17-53 on (o, d)
+RS_D bool triHitOD(f3 o, f3 d, f3 v0, f3 v1, f3 v2, float& bx, float& by, float& dist) {
+    RayT r;
+    r.o = o; r.d = d;
+    return triHit(r, v0, v1, v2, bx, by, dist);
 }
 
-RS_D bool closestRun(const DevScene& s, ClosestState& st, Stack& stack, int minActive) {
-    const RayF f = st.f;
-    for (;;) {
-        // ---- descend through internal nodes
-#if RS_BVH4
-        while (st.cur >= 0 && st.cur != RS_DONE) {
-            Node4Hits nh = node4Test(s, f, st.cur, st.limit);
-            if (nh.k0 == RS_MISS) { st.cur = closestPop(st, stack); continue; }
-            // far children first, so that the nearest is popped first
-            if (nh.k3 != RS_MISS) { stack.push(st.sp, node4Child(nh, nh.k3), node4T(nh.k3)); st.sp++; }
-            if (nh.k2 != RS_MISS) { stack.push(st.sp, node4Child(nh, nh.k2), node4T(nh.k2)); st.sp++; }
-            if (nh.k1 != RS_MISS) { stack.push(st.sp, node4Child(nh, nh.k1), node4T(nh.k1)); st.sp++; }
-            st.cur = node4Child(nh, nh.k0);
-        }
-#else
-        while (st.cur >= 0 && st.cur != RS_DONE) {
-            const float4* np = s.fastNodes + 4 * (size_t)st.cur;
-            float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
-            int2 l = __ldg((const int2*)(np + 3));
-            float tL, tR;
-            bool hL = slabHit(f, a.x, a.y, a.z, a.w, b.x, b.y, st.limit, tL);
-            bool hR = slabHit(f, b.z, b.w, c.x, c.y, c.z, c.w, st.limit, tR);
-            if (hL && hR) {
-                bool leftNear = tL <= tR;
-                stack.push(st.sp, leftNear ? l.y : l.x, leftNear ? tR : tL); st.sp++;
-                st.cur = leftNear ? l.x : l.y;
-            } else if (hL) st.cur = l.x;
-            else if (hR) st.cur = l.y;
-            else st.cur = closestPop(st, stack);
-        }
-#endif
-        if (st.cur == RS_DONE) return true;
-        // ---- leaf
-        {
-            int first = st.cur & 0x07ffffff, count = ((st.cur >> 27) & 7) + 1;
-            for (int i = 0; i < count; i++) closestOffer(st, loadTriFast(s, first + i));
-        }
-        st.cur = closestPop(st, stack);
-        if (st.cur == RS_DONE) return true;
-        if (minActive && __popc(__activemask()) < minActive) return false;
+// the part of a ray's running result that a newly accepted hit changes
+struct BestState { float bestD, band, limit; int bestFi, nt; };
+
+// a triangle that is hit within the ray's limit (rare: a few times per ray): leaf-box criterion, then best / near-tie
+// update.  Everything by value: a reference to the caller's PRay would pin it in local memory for the whole walk.
+__device__ __noinline__ BestState prayAccept(f3 o, f3 dir, BestState p, const TieStore ts, f3 v0, f3 v1, f3 v2, int fi, float d) {
+    RayT rt = makeRayT(o, dir);
+    Tri t;
+    t.v0 = v0; t.v1 = v1; t.v2 = v2;
+    float tBox;
+    if (!leafBox(rt, t, tBox)) return p;                             // the reference never sees this triangle
+    if (d < p.bestD) {
+        const float band = fmaxf(RS_TIE_BAND * d, 4.f * triDistError(rt, v0, v1, v2));
+        const bool oldNear = p.bestFi >= 0 && p.bestD - d <= band;   // the old best stays a candidate
+        int n = 0;
+        bool over = false;
+        if (oldNear) {
+            // the stored candidates lie behind the old best: keep those still inside the new band, then add the old best
+            over = p.nt < 0;
+            const int m = p.nt < 0 ? RS_MAX_TIES : p.nt;
+            for (int k = 0; k < m; k++) {
+                float dk = ts.d[k * RS_BLOCK];
+                if (dk - d <= band) { ts.d[n * RS_BLOCK] = dk; ts.fi[n * RS_BLOCK] = ts.fi[k * RS_BLOCK]; n++; }
+            }
+            if (n < RS_MAX_TIES) { ts.d[n * RS_BLOCK] = p.bestD; ts.fi[n * RS_BLOCK] = p.bestFi; n++; }
+            else over = true;
+        }                                                            // else: everything recorded so far is behind the new band
+        p.nt = over ? -1 : n;
+        p.bestD = d; p.bestFi = fi; p.band = band; p.limit = d + 2.f * band;
+    } else if (d - p.bestD <= p.band) {
+        if (p.nt >= 0 && p.nt < RS_MAX_TIES) { ts.d[p.nt * RS_BLOCK] = d; ts.fi[p.nt * RS_BLOCK] = fi; p.nt++; }
+        else p.nt = -1;
     }
+    return p;
 }
 
-// false = undecided (more mutually near hits than RS_MAX_EXTRA + 2)
-RS_D bool closestResolve(const DevScene& s, const ClosestState& st, Hit& h) {
-    h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
-    const Cand& best = st.best;
-    if (best.prim < 0) return true;
-    if (st.triple) return false;
-    h.t = best.d; h.bx = best.bx; h.by = best.by; h.prim = best.prim;
-    if (st.second.prim < 0) return true;
-    // replay the reference's visits of the hits that are near the best one, in its order for this ray
-    const int* rank = s.rank + (size_t)(2 * st.r.dim + st.r.lesser) * s.numTris;
-    Cand c[RS_MAX_EXTRA + 2];
-    int rk[RS_MAX_EXTRA + 2];
-    int n = 0;
-    c[n] = best; rk[n] = __ldg(rank + best.prim); n++;
-    if (nearTie(st.second, best)) { c[n] = st.second; rk[n] = __ldg(rank + st.second.prim); n++; }
-    for (int i = 0; i < st.nExtra; i++)
-        if (nearTie(st.extra[i], best)) { c[n] = st.extra[i]; rk[n] = __ldg(rank + st.extra[i].prim); n++; }
-    if (n == 1) return true;
+// one triangle of a visited leaf offered to a ray's running result
+RS_D void prayOffer(PRay& p, const TieStore& ts, const Tri& t, int fi) {
+    float bx, by, d;
+    if (!triHitOD(p.o, p.d, t.v0, t.v1, t.v2, bx, by, d)) return;
+    if (!(d <= p.limit)) return;
+    BestState b;
+    b.bestD = p.bestD; b.band = p.band; b.limit = p.limit; b.bestFi = p.bestFi; b.nt = p.nt;
+    b = prayAccept(p.o, p.d, b, ts, t.v0, t.v1, t.v2, fi, d);
+    p.bestD = b.bestD; p.band = b.band; p.limit = b.limit; p.bestFi = b.bestFi; p.nt = b.nt;
+}
+
+// the reference's visits of the best hit and its near ties, in its order for this ray; prim == -2: undecided
+__device__ __noinline__ Hit prayReplay(const DevScene& s, f3 o, f3 dir, int bestFi, int nt, float band, const TieStore ts) {
+    const RayT rt = makeRayT(o, dir);
+    const int* rank = s.rank + (size_t)(2 * rt.dim + rt.lesser) * s.numTris;
+    float cd[RS_MAX_TIES + 1], cbx[RS_MAX_TIES + 1], cby[RS_MAX_TIES + 1], ctb[RS_MAX_TIES + 1];
+    int cprim[RS_MAX_TIES + 1], crk[RS_MAX_TIES + 1];
+    Hit h;
+    h.t = FLT_MAX; h.prim = -2; h.bx = 0.f; h.by = 0.f;
+    const int n = nt + 1;
+    for (int k = 0; k < n; k++) {
+        const int fi = k == 0 ? bestFi : ts.fi[(k - 1) * RS_BLOCK];
+        Tri t = loadTriFast(s, fi);
+        triHit(rt, t.v0, t.v1, t.v2, cbx[k], cby[k], cd[k]);
+        leafBox(rt, t, ctb[k]);
+        // a candidate whose own error bound exceeds the band could be pruned by hits that were not recorded
+        if (k > 0 && 4.f * triDistError(rt, t.v0, t.v1, t.v2) > band) return h;
+        cprim[k] = t.prim;
+        crk[k] = __ldg(rank + t.prim);
+    }
     float closest = FLT_MAX;
-    for (int k = 0; k < n; k++) {                      // n <= 4: selection by increasing rank
+    for (int k = 0; k < n; k++) {                          // n <= 4: selection by increasing rank
         int m = -1;
         for (int i = 0; i < n; i++)
-            if (rk[i] >= 0 && (m < 0 || rk[i] < rk[m])) m = i;
-        if (c[m].tBox < closest && c[m].d < closest) {  // scene.h:260,267
-            closest = c[m].d;
-            h.t = c[m].d; h.bx = c[m].bx; h.by = c[m].by; h.prim = c[m].prim;
+            if (crk[i] >= 0 && (m < 0 || crk[i] < crk[m])) m = i;
+        if (ctb[m] < closest && cd[m] < closest) {         // scene.h:260,267
+            closest = cd[m];
+            h.t = cd[m]; h.bx = cbx[m]; h.by = cby[m]; h.prim = cprim[m];
         }
-        rk[m] = -1;
+        crk[m] = -1;
     }
+    return h;
+}
+
+// false = undecided (more mutually near hits than RS_MAX_TIES + 1)
+RS_D bool prayResolve(const DevScene& s, const PRay& p, const TieStore& ts, Hit& h) {
+    h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
+    if (p.bestFi < 0) return true;
+    if (p.nt < 0) return false;
+    if (p.nt > 0) {
+        h = prayReplay(s, p.o, p.d, p.bestFi, p.nt, p.band, ts);
+        return h.prim != -2;
+    }
+    Tri t = loadTriFast(s, p.bestFi);
+    triHitOD(p.o, p.d, t.v0, t.v1, t.v2, h.bx, h.by, h.t);          // same arithmetic as during the walk: h.t == bestD
+    h.prim = t.prim;
     return true;
 }
 
-RS_D bool traceClosestFast(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
-    ClosestState st;
-    st.r = r;
-    closestBegin(s, st);
-    closestRun(s, st, stack, 0);
-    return closestResolve(s, st, h);
-}
-
-
-// Two rays of the same pixel (the G-buffer's centre ray and the ReSTIR kernel's jittered ray, gbuffer.cu:11-23 and
-// restir.cu:129) walked TOGETHER: a node is fetched once and tested against both, a child is entered when either ray
-// hits it, every triangle of a visited leaf is offered to both.  Each ray keeps its own result state, and what a ray
-// finds does not depend on which (conservative) boxes were entered on its behalf, so both results are exactly those
-// of two separate walks -- for about two thirds of the instructions and half of the dependent node fetches.
-#if !RS_BVH4
-RS_D void closestRunPair(const DevScene& s, ClosestState& a, ClosestState& b, Stack& stack) {
-    const RayF fa = a.f, fb = b.f;
+// Closest hit of a WARP's rays over the traced tree as one packet: the 32 lanes hold the rays of an 8x4-pixel tile (one
+// ray per lane, or two: the G-buffer's centre ray and the ReSTIR kernel's jittered ray of the same pixel, gbuffer.cu:11-23 /
+// restir.cu:129), and the warp walks the tree ONCE with a single stack: a node is fetched once (same address in every
+// lane), every lane slab-tests its own ray(s) against both children, a child is entered when ANY lane hits it, the
+// nearer one (smallest entry distance over the warp) first, and every triangle of a visited leaf is offered to every
+// lane's ray(s).  Each ray keeps its own result and its own limit, and what a ray finds does not depend on which
+// conservative boxes were entered (see above), so the results are exactly those of 32 / 64 separate walks.  Primary
+// rays of a tile are so coherent that the union of their walks is barely longer than the longest of them, while 32
+// independent walks in lockstep cost about twice the longest (divergence between descending and leaf-testing lanes):
+// scripts/travsim.cpp, config4 at 1080p: 106 node steps per warp against 191, with every lane busy instead of 10.6 of 32.
+template <bool TWO>
+RS_D void packetWalk(const DevScene& s, PRay& a, PRay& b, const TieStore& ta, const TieStore& tb, int2* wst) {
+    const unsigned FULL = 0xffffffffu;
     int sp = 0;
-    int cur = (a.cur != RS_DONE || b.cur != RS_DONE) ? s.fastRoot : RS_DONE;
+    float tA, tB;
+    bool hit = slabHitP(a, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], tA);
+    if (TWO) hit |= slabHitP(b, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], tB);
+    int cur = __any_sync(FULL, hit) ? s.fastRoot : RS_DONE;
+    float wlimit = FLT_MAX;                       // max of the lanes' limits (warp-uniform): culls popped entries
     for (;;) {
         while (cur >= 0 && cur != RS_DONE) {
             const float4* np = s.fastNodes + 4 * (size_t)cur;
-            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-            int2 l = __ldg((const int2*)(np + 3));
-            float tLa, tRa, tLb, tRb;
-            bool hLa = slabHit(fa, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, a.limit, tLa);
-            bool hRa = slabHit(fa, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, a.limit, tRa);
-            bool hLb = slabHit(fb, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, b.limit, tLb);
-            bool hRb = slabHit(fb, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, b.limit, tRb);
-            bool hL = hLa || hLb, hR = hRa || hRb;
-            float tL = fminf(hLa ? tLa : FLT_MAX, hLb ? tLb : FLT_MAX), tR = fminf(hRa ? tRa : FLT_MAX, hRb ? tRb : FLT_MAX);
-            if (hL && hR) {
-                bool leftNear = tL <= tR;
-                stack.push(sp, leftNear ? l.y : l.x, leftNear ? tR : tL); sp++;
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+            const int2 l = __ldg((const int2*)(np + 3));
+            float tL, tR, t2;
+            bool hL = slabHitP(a, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tL);
+            bool hR = slabHitP(a, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tR);
+            if (!hL) tL = FLT_MAX;
+            if (!hR) tR = FLT_MAX;
+            if (TWO) {
+                if (slabHitP(b, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, t2)) { hL = true; tL = fminf(tL, t2); }
+                if (slabHitP(b, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, t2)) { hR = true; tR = fminf(tR, t2); }
+            }
+            const bool anyL = __any_sync(FULL, hL), anyR = __any_sync(FULL, hR);
+            if (anyL && anyR) {
+                // entry distances are >= 0, so their bit patterns order like the floats
+                const unsigned kL = __reduce_min_sync(FULL, __float_as_uint(tL)), kR = __reduce_min_sync(FULL, __float_as_uint(tR));
+                const bool leftNear = kL <= kR;
+                wst[sp] = make_int2(leftNear ? l.y : l.x, (int)(leftNear ? kR : kL)); sp++;     // same value from every lane
                 cur = leftNear ? l.x : l.y;
-            } else if (hL) cur = l.x;
-            else if (hR) cur = l.y;
+            } else if (anyL) cur = l.x;
+            else if (anyR) cur = l.y;
             else {
                 cur = RS_DONE;
-                const float lim = fmaxf(a.limit, b.limit);
-                while (sp > 0) { --sp; if (stack.t(sp) <= lim) { cur = stack.ref(sp); break; } }
+                while (sp > 0) { --sp; const int2 e = wst[sp]; if (__int_as_float(e.y) <= wlimit) { cur = e.x; break; } }
             }
         }
         if (cur == RS_DONE) return;
         {
-            int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            const int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
             for (int i = 0; i < count; i++) {
-                Tri t = loadTriFast(s, first + i);
-                closestOffer(a, t);
-                closestOffer(b, t);
+                const Tri t = loadTriFast(s, first + i);
+                prayOffer(a, ta, t, first + i);
+                if (TWO) prayOffer(b, tb, t, first + i);
             }
         }
+        const float lim = TWO ? fmaxf(a.limit, b.limit) : a.limit;
+        wlimit = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(lim, 0.f))));
         cur = RS_DONE;
-        const float lim = fmaxf(a.limit, b.limit);
-        while (sp > 0) { --sp; if (stack.t(sp) <= lim) { cur = stack.ref(sp); break; } }
+        while (sp > 0) { --sp; const int2 e = wst[sp]; if (__int_as_float(e.y) <= wlimit) { cur = e.x; break; } }
     }
 }
-#endif
+
+// shared memory of the packet walk for a block of RS_BLOCK threads: near-tie stores of NR rays per thread + one stack per warp
+#define RS_DECLARE_PACKET(name, NR)                                                 \
+    __shared__ int name##_tfi[NR][RS_MAX_TIES][RS_BLOCK];                           \
+    __shared__ float name##_td[NR][RS_MAX_TIES][RS_BLOCK];                          \
+    __shared__ int2 name##_ws[RS_BLOCK / 32][RS_WSTACK];                            \
+    TieStore name##_ta, name##_tb;                                                  \
+    name##_ta.fi = &name##_tfi[0][0][threadIdx.x]; name##_ta.d = &name##_td[0][0][threadIdx.x];                          \
+    name##_tb.fi = &name##_tfi[NR - 1][0][threadIdx.x]; name##_tb.d = &name##_td[NR - 1][0][threadIdx.x];                \
+    int2* name##_wst = name##_ws[threadIdx.x >> 5]
 
 // any hit: order does not matter, the criterion above is exact per triangle
 RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& stack) {
@@ -584,20 +564,6 @@ RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& 
     int sp = 0;
     int cur = s.fastRoot;
     for (;;) {
-#if RS_BVH4
-        while (cur >= 0) {
-            Node4Hits nh = node4Test(s, f, cur, dist);
-            if (nh.k0 == RS_MISS) {
-                if (sp == 0) return 0;
-                cur = stack.ref(--sp);
-                continue;
-            }
-            if (nh.k3 != RS_MISS) { stack.pushRef(sp, node4Child(nh, nh.k3)); sp++; }
-            if (nh.k2 != RS_MISS) { stack.pushRef(sp, node4Child(nh, nh.k2)); sp++; }
-            if (nh.k1 != RS_MISS) { stack.pushRef(sp, node4Child(nh, nh.k1)); sp++; }
-            cur = node4Child(nh, nh.k0);
-        }
-#else
         while (cur >= 0) {
             const float4* np = s.fastNodes + 4 * (size_t)cur;
             float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
@@ -616,7 +582,6 @@ RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& 
                 cur = stack.ref(--sp);
             }
         }
-#endif
         int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
         for (int i = 0; i < count; i++) {
             Tri t = loadTriFast(s, first + i);
@@ -626,14 +591,6 @@ RS_D int traceOccludedFast(const DevScene& s, const RayT& r, float dist, Stack& 
         if (sp == 0) return 0;
         cur = stack.ref(--sp);
     }
-}
-
-// EXACT = false: walk the traced tree; a ray with three or more mutually near hits is reported undecided (its pixel is
-// queued and recomputed by the fix-up kernel).  EXACT = true: reference-order walk of the reference tree.
-template <bool EXACT>
-RS_D bool traceClosest(const DevScene& s, const RayT& r, Hit& h, Stack& stack) {
-    if (EXACT) { traceClosestExact(s, r, h, stack); return true; }
-    return traceClosestFast(s, r, h, stack);
 }
 
 // DevScene::testOcclusion (scene.h:286-316): 1 occluded, 0 free, -1 undecided (never with EXACT)
@@ -866,15 +823,14 @@ RS_D f3 shadeReservoir(const DevScene& s, const Resv& r, int type, float metalli
 // gbuffer.cu:3-73 for one pixel; false = undecided, nothing written
 RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& lastCam, int x, int y, f3 o, f3 d, const Hit& h);
 
-template <bool EXACT>
-RS_D bool gbufferPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, int x, int y, Stack& stack) {
+// with the reference-order walk of the reference tree (validation mode, fix-up kernels)
+RS_D void gbufferPixelExact(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, int x, int y, Stack& stack) {
     f3 o, d;
     cameraRay(cam, x, y, .5f, .5f, o, d);
     RayT r = makeRayT(o, d);
     Hit h;
-    if (!traceClosest<EXACT>(s, r, h, stack)) return false;
+    traceClosestExact(s, r, h, stack);
     gbufferFinish(s, f, lastCam, x, y, o, d, h);
-    return true;
 }
 
 // gbuffer.cu:28-72: what is stored for a pixel once its hit is known
@@ -910,14 +866,33 @@ RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& last
     }
 }
 
-template <bool EXACT>
+// traced tree: the warp's 32 centre rays walk as one packet
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GBUF) k_gbuffer(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                       const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
+    RS_DECLARE_PACKET(pk, 1);
+    __shared__ unsigned int t0;
+    if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
+    int x, y;
+    const bool active = pixelOf(f, x, y);
+    f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
+    if (active) cameraRay(cam, x, y, .5f, .5f, o, d);
+    PRay a = prayBegin(o, d, active);
+    packetWalk<false>(s, a, a, pk_ta, pk_ta, pk_wst);
+    if (active) {
+        Hit h;
+        if (prayResolve(s, a, pk_ta, h)) gbufferFinish(s, f, lastCam, x, y, o, d, h);
+        else enqueuePixel(f, x, y);
+    }
+    if (f.rowCost) accountBlock(f, &t0);
+}
+// reference-order walk for every pixel (RS_TRAVERSAL_EXACT)
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GBUF) k_gbuffer_exact(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                            const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam) {
     RS_DECLARE_STACK(stack);
     __shared__ unsigned int t0;
     if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
     int x, y;
-    if (pixelOf(f, x, y) && !gbufferPixel<EXACT>(s, f, cam, lastCam, x, y, stack)) enqueuePixel(f, x, y);
+    if (pixelOf(f, x, y)) gbufferPixelExact(s, f, cam, lastCam, x, y, stack);
     if (f.rowCost) accountBlock(f, &t0);
 }
 // recomputes the queued pixels with the reference-order walk
@@ -930,7 +905,7 @@ __global__ void __launch_bounds__(RS_BLOCK) k_gbuffer_fix(const __grid_constant_
     const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
     for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
         int idx = f.queue[i];
-        gbufferPixel<true>(s, f, cam, lastCam, idx % f.W, idx / f.W, stack);
+        gbufferPixelExact(s, f, cam, lastCam, idx % f.W, idx / f.W, stack);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.fallbackRays + 0, n);
 }
@@ -1002,20 +977,25 @@ template <bool EXACT, bool SPATIAL>
 RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams& prm, int iter, int first,
                           int x, int y, Stack& stack, Rng rng, f3 d, const Hit& h);
 
-template <bool EXACT, bool SPATIAL>
-RS_D bool restirAPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& prm, int looper, int iter, int first,
-                       int x, int y, Stack& stack) {
-    int index = y * f.W + x;
-    Rng rng;
-    rng.seed(looper, index);
+// the jittered primary ray of a pixel (restir.cu:126-129): seeds the pixel's RNG stream and draws sample4D
+RS_D void jitteredRay(const FrameDev& f, const CamDev& cam, int looper, int x, int y, Rng& rng, f3& o, f3& d) {
+    rng.seed(looper, y * f.W + x);
     float r0 = rng.next(), r1 = rng.next();
     rng.next(); rng.next();                                                          // r.z, r.w of sample4D are drawn and unused (restir.cu:129)
-    f3 o, d;
     cameraRay(cam, x, y, r0, r1, o, d);
+}
+
+// with the reference-order walk of the reference tree (validation mode, fix-up kernels)
+template <bool SPATIAL>
+RS_D void restirAPixelExact(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& prm, int looper, int iter, int first,
+                            int x, int y, Stack& stack) {
+    Rng rng;
+    f3 o, d;
+    jitteredRay(f, cam, looper, x, y, rng, o, d);
     RayT ray = makeRayT(o, d);
     Hit h;
-    if (!traceClosest<EXACT>(s, ray, h, stack)) return false;
-    return restirAAfterHit<EXACT, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, d, h);
+    traceClosestExact(s, ray, h, stack);
+    restirAAfterHit<true, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, d, h);
 }
 
 // restir.cu:133-192 (+ :211-230) once the jittered primary ray's hit is known
@@ -1101,45 +1081,69 @@ RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams
     return true;
 }
 
-template <bool EXACT, bool SPATIAL>
+// phase A on the traced tree: the warp's 32 jittered rays walk as one packet
+template <bool SPATIAL>
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_RESTIR) k_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                        const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
                                                        int looper, int iter, int first) {
+    RS_DECLARE_REFSTACK(stack);
+    RS_DECLARE_PACKET(pk, 1);
+    __shared__ unsigned int t0;
+    if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
+    int x, y;
+    const bool active = pixelOf(f, x, y);
+    Rng rng;
+    rng.x = 1;
+    f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
+    if (active) jitteredRay(f, cam, looper, x, y, rng, o, d);
+    PRay a = prayBegin(o, d, active);
+    packetWalk<false>(s, a, a, pk_ta, pk_ta, pk_wst);
+    if (active) {
+        Hit h;
+        if (!prayResolve(s, a, pk_ta, h) || !restirAAfterHit<false, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, d, h)) enqueuePixel(f, x, y);
+    }
+    if (f.rowCost) accountBlock(f, &t0);
+}
+// reference-order walk for every pixel (RS_TRAVERSAL_EXACT)
+template <bool SPATIAL>
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_RESTIR) k_restir_a_exact(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                             const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm,
+                                                             int looper, int iter, int first) {
     RS_DECLARE_STACK(stack);
     __shared__ unsigned int t0;
     if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
     int x, y;
-    if (pixelOf(f, x, y) && !restirAPixel<EXACT, SPATIAL>(s, f, cam, prm, looper, iter, first, x, y, stack)) enqueuePixel(f, x, y);
+    if (pixelOf(f, x, y)) restirAPixelExact<SPATIAL>(s, f, cam, prm, looper, iter, first, x, y, stack);
     if (f.rowCost) accountBlock(f, &t0);
 }
-// G-buffer + phase A of one pixel in one kernel: the two primary rays of the pixel share one tree walk (closestRunPair)
-#if !RS_BVH4
+// G-buffer + phase A of one pixel in one kernel: the two primary rays of every pixel of the warp's tile (64 rays) share
+// ONE packet walk of the tree
 template <bool SPATIAL>
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_FUSED) k_gbuffer_restir_a(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                                const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam,
                                                                const __grid_constant__ RstrParams prm, int looper, int iter, int first) {
-    RS_DECLARE_STACK(stack);
+    RS_DECLARE_REFSTACK(stack);
+    RS_DECLARE_PACKET(pk, 2);
     __shared__ unsigned int t0;
     if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
     int x, y;
-    if (pixelOf(f, x, y)) {
-        Rng rng;
-        rng.seed(looper, y * f.W + x);
-        float r0 = rng.next(), r1 = rng.next();
-        rng.next(); rng.next();
-        f3 oC, dC, oJ, dJ;
+    const bool active = pixelOf(f, x, y);
+    Rng rng;
+    rng.x = 1;
+    f3 oC = mk3(0.f), dC = mk3(0.f, 0.f, 1.f), oJ = oC, dJ = dC;
+    if (active) {
         cameraRay(cam, x, y, .5f, .5f, oC, dC);                                      // gbuffer.cu:11-23
-        cameraRay(cam, x, y, r0, r1, oJ, dJ);                                        // restir.cu:129
-        Hit hC, hJ;
-        bool ok;
-        {
-            ClosestState a, b;
-            a.r = makeRayT(oC, dC); b.r = makeRayT(oJ, dJ);
-            closestBegin(s, a); closestBegin(s, b);
-            closestRunPair(s, a, b, stack);
-            ok = closestResolve(s, a, hC);
-            ok = closestResolve(s, b, hJ) && ok;
-        }
+        jitteredRay(f, cam, looper, x, y, rng, oJ, dJ);                              // restir.cu:129
+    }
+    Hit hC, hJ;
+    bool ok;
+    {
+        PRay a = prayBegin(oC, dC, active), b = prayBegin(oJ, dJ, active);
+        packetWalk<true>(s, a, b, pk_ta, pk_tb, pk_wst);
+        ok = prayResolve(s, a, pk_ta, hC);
+        ok = prayResolve(s, b, pk_tb, hJ) && ok;
+    }
+    if (active) {
         if (ok) {
             gbufferFinish(s, f, lastCam, x, y, oC, dC, hC);
             ok = restirAAfterHit<false, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, dJ, hJ);
@@ -1155,15 +1159,16 @@ __global__ void __launch_bounds__(RS_BLOCK) k_gbuffer_restir_a_fix(const __grid_
                                                                    const __grid_constant__ RstrParams prm, int looper, int iter, int first) {
     RS_DECLARE_STACK(stack);
     const unsigned n = *f.queueCount;
+    // entry i -> lane i / numWarps of warp i % numWarps: the first numWarps entries each get a warp of their own
+    // (reference-order walks diverge completely, sharing a warp would serialise them)
     const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
     for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
         int idx = f.queue[i];
-        gbufferPixel<true>(s, f, cam, lastCam, idx % f.W, idx / f.W, stack);
-        restirAPixel<true, SPATIAL>(s, f, cam, prm, looper, iter, first, idx % f.W, idx / f.W, stack);
+        gbufferPixelExact(s, f, cam, lastCam, idx % f.W, idx / f.W, stack);
+        restirAPixelExact<SPATIAL>(s, f, cam, prm, looper, iter, first, idx % f.W, idx / f.W, stack);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { atomicAdd(s.fallbackRays + 0, n); atomicAdd(s.fallbackRays + 1, n); }
 }
-#endif
 
 template <bool SPATIAL>
 __global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
@@ -1171,12 +1176,10 @@ __global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant
                                                            int looper, int iter, int first) {
     RS_DECLARE_STACK(stack);
     const unsigned n = *f.queueCount;
-    // entry i -> lane i / numWarps of warp i % numWarps: the first numWarps entries each get a warp of their own
-    // (reference-order walks diverge completely, sharing a warp would serialise them)
     const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
     for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
         int idx = f.queue[i];
-        restirAPixel<true, SPATIAL>(s, f, cam, prm, looper, iter, first, idx % f.W, idx / f.W, stack);
+        restirAPixelExact<SPATIAL>(s, f, cam, prm, looper, iter, first, idx % f.W, idx / f.W, stack);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.fallbackRays + 1, n);
 }
@@ -1250,18 +1253,8 @@ __global__ void __launch_bounds__(128) k_restir_b(const __grid_constant__ DevSce
 
 // pathtrace.cu:279-328 with scene.h:427-459 (occlusion test BEFORE the facing test)
 template <bool EXACT>
-RS_D bool ptdirectPixel(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, int x, int y, Stack& stack) {
+RS_D bool ptdirectAfterHit(const DevScene& s, const FrameDev& f, int iter, int x, int y, Stack& stack, Rng rng, f3 d, const Hit& h) {
     size_t li = planeIndex(f, x, y);
-    int index = y * f.W + x;
-    Rng rng;
-    rng.seed(looper, index);
-    float r0 = rng.next(), r1 = rng.next();
-    rng.next(); rng.next();
-    f3 o, d;
-    cameraRay(cam, x, y, r0, r1, o, d);
-    RayT ray = makeRayT(o, d);
-    Hit h;
-    if (!traceClosest<EXACT>(s, ray, h, stack)) return false;
     f3 direct = mk3(0.f);
     if (h.prim < 0) {
         if (s.envTex >= 0) direct = envLookup(s, d);                                 // pathtrace.cu:295-300
@@ -1324,24 +1317,47 @@ RS_D bool ptdirectPixel(const DevScene& s, const FrameDev& f, const CamDev& cam,
     return true;
 }
 
-template <bool EXACT>
+RS_D void ptdirectPixelExact(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, int x, int y, Stack& stack) {
+    Rng rng;
+    f3 o, d;
+    jitteredRay(f, cam, looper, x, y, rng, o, d);
+    RayT ray = makeRayT(o, d);
+    Hit h;
+    traceClosestExact(s, ray, h, stack);
+    ptdirectAfterHit<true>(s, f, iter, x, y, stack, rng, d, h);
+}
+
 __global__ void __launch_bounds__(RS_BLOCK) k_ptdirect(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                        const __grid_constant__ CamDev cam, int looper, int iter) {
+    RS_DECLARE_REFSTACK(stack);
+    RS_DECLARE_PACKET(pk, 1);
+    int x, y;
+    const bool active = pixelOf(f, x, y);
+    Rng rng;
+    rng.x = 1;
+    f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
+    if (active) jitteredRay(f, cam, looper, x, y, rng, o, d);
+    PRay a = prayBegin(o, d, active);
+    packetWalk<false>(s, a, a, pk_ta, pk_ta, pk_wst);
+    if (active) {
+        Hit h;
+        if (!prayResolve(s, a, pk_ta, h) || !ptdirectAfterHit<false>(s, f, iter, x, y, stack, rng, d, h)) enqueuePixel(f, x, y);
+    }
+}
+__global__ void __launch_bounds__(RS_BLOCK) k_ptdirect_exact(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                             const __grid_constant__ CamDev cam, int looper, int iter) {
     RS_DECLARE_STACK(stack);
     int x, y;
-    if (!pixelOf(f, x, y)) return;
-    if (!ptdirectPixel<EXACT>(s, f, cam, looper, iter, x, y, stack)) enqueuePixel(f, x, y);
+    if (pixelOf(f, x, y)) ptdirectPixelExact(s, f, cam, looper, iter, x, y, stack);
 }
 __global__ void __launch_bounds__(RS_BLOCK) k_ptdirect_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                            const __grid_constant__ CamDev cam, int looper, int iter) {
     RS_DECLARE_STACK(stack);
     const unsigned n = *f.queueCount;
-    // entry i -> lane i / numWarps of warp i % numWarps: the first numWarps entries each get a warp of their own
-    // (reference-order walks diverge completely, sharing a warp would serialise them)
     const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
     for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
         int idx = f.queue[i];
-        ptdirectPixel<true>(s, f, cam, looper, iter, idx % f.W, idx / f.W, stack);
+        ptdirectPixelExact(s, f, cam, looper, iter, idx % f.W, idx / f.W, stack);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.fallbackRays + 2, n);
 }
@@ -1394,34 +1410,31 @@ static inline dim3 pixelGrid(const FrameDev& f) { return dim3((f.W + 15) / 16, (
 #define RS_FIX_BLOCKS 296   /* 2 per SM; the fix-up kernels stride over the queue */
 
 int launchGBuffer(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, cudaStream_t st) {
-    if (s.traversal == RS_TRAVERSAL_EXACT) { k_gbuffer<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam); return 1; }
+    if (s.traversal == RS_TRAVERSAL_EXACT) { k_gbuffer_exact<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam); return 1; }
     cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
-    k_gbuffer<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
+    k_gbuffer<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
     k_gbuffer_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam);
     return 2;
 }
 int launchRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const RstrParams& p, int looper, int iter, int first, cudaStream_t st) {
     const bool sp = (p.reuse & 2) != 0;
     if (s.traversal == RS_TRAVERSAL_EXACT) {
-        if (sp) k_restir_a<true, true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
-        else k_restir_a<true, false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+        if (sp) k_restir_a_exact<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+        else k_restir_a_exact<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
         return 1;
     }
     cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
     if (sp) {
-        k_restir_a<false, true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+        k_restir_a<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
         k_restir_a_fix<true><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
     } else {
-        k_restir_a<false, false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
+        k_restir_a<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
         k_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, p, looper, iter, first);
     }
     return 2;
 }
-// G-buffer + phase A in one launch (traced tree only); returns 0 when the build / traversal mode has no fused kernel
+// G-buffer + phase A in one launch (traced tree only); returns 0 when the traversal mode has no fused kernel
 int launchGBufferRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, const RstrParams& p, int looper, int iter, int first, cudaStream_t st) {
-#if RS_BVH4
-    return 0;
-#else
     if (s.traversal == RS_TRAVERSAL_EXACT) return 0;
     cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
     if (p.reuse & 2) {
@@ -1432,15 +1445,14 @@ int launchGBufferRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam
         k_gbuffer_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
     }
     return 2;
-#endif
 }
 void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, const ResvD* src, ResvD* dst, int pass, int last, cudaStream_t st) {
     k_restir_b<<<pixelGrid(f), 128, 0, st>>>(s, f, p, iter, src, dst, pass, last);
 }
 int launchPTDirect(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, cudaStream_t st) {
-    if (s.traversal == RS_TRAVERSAL_EXACT) { k_ptdirect<true><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, looper, iter); return 1; }
+    if (s.traversal == RS_TRAVERSAL_EXACT) { k_ptdirect_exact<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, looper, iter); return 1; }
     cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
-    k_ptdirect<false><<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, looper, iter);
+    k_ptdirect<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, looper, iter);
     k_ptdirect_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, looper, iter);
     return 2;
 }
