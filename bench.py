@@ -361,21 +361,37 @@ def run_b200(args):
         row_cost = np.repeat(groups.cpu().numpy() / 8.0, 8)[:H]
         bounds = strips.balanced_bounds(row_cost, world, min_rows=max(8, halo))
     row_cost = row_cost if (world > 1 and not args.uniform_strips) else None
-    rows = plan = fr = exchange = None
+    rows = plan = fr = exchange = grp = None
+    peer = world > 1 and args.exchange == "peer"
+
+    def all_gather_bytes(blob: bytes):
+        """The one piece of plumbing the peer data plane needs: every rank's 512-byte handle, in rank order."""
+        t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return [bytes(o.cpu().numpy().tobytes()) for o in outs]
 
     def make_strip():
-        nonlocal rows, plan, fr, exchange
+        nonlocal rows, plan, fr, exchange, grp
         if fr is not None:
             fr.sync()
             if world > 1:
                 torch.cuda.synchronize()
+                dist.barrier()               # nobody may still be storing into a slab that is about to be freed
+            if grp is not None:
+                grp.close()
+                grp = None
             fr.close()
         rows = strips.strip_rows(H, world, rank, bounds)
         fr = sc.frame(W, H, rows=rows, halo=halo)
         if args.no_fusion:
             fr.set_fusion(False)
         plan = strips.exchange_plan(H, world, halo, bounds) if world > 1 else []
-        if world > 1:
+        if peer:
+            # the library's own data plane: halo rows and the gather are peer stores over NVLink (rstr_strip_group_*)
+            grp = rb.StripGroup(fr, rank, world)
+            grp.connect(all_gather_bytes(grp.handle()))
+        elif world > 1:
             fr.set_stream(torch.cuda.current_stream().cuda_stream)
             fr.set_halo_render(args.render_halo)
             exchange = StripExchange(fr, plan, rank)
@@ -389,6 +405,9 @@ def run_b200(args):
         # temporal step reads (phase B does not modify them).  --split-exchange sends the history separately, after
         # phase B, on a side stream (the first version).
         cam = base.orbit(orbit_index(k))
+        if peer:
+            grp.render(cam, prm, k, 0)
+            return
         fr.gbuffer_render(cam)
         if world == 1:
             fr.restir_direct(cam, prm, k, 0)
@@ -512,8 +531,36 @@ def run_b200(args):
         e2e_sync_ms = (time.perf_counter() - t0) / args.steps * 1e3
         for o in outs:
             rb.pinned_free(o)
+    elif peer:
+        # every rank tone-maps its strip straight into rank 0's full-frame LDR slot (peer stores); rank 0 copies the
+        # assembled frame to one of three pinned host frames on a copy stream and consumes it two frames later
+        S = 3
+        outs = [rb.pinned_empty(P * 4) for _ in range(S)] if rank == 0 else [None] * S
+
+        def e2e_loop(n):
+            nonlocal k
+            for i in range(n):
+                frame(k); k += 1
+                grp.present(rb.TONEMAP_ACES, outs[i % S], i % S)
+                if rank == 0 and i >= S - 1:
+                    grp.wait_host((i - (S - 1)) % S)
+            if rank == 0:
+                for i in range(max(0, n - (S - 1)), n):
+                    grp.wait_host(i % S)
+            fr.sync()
+
+        e2e_loop(6)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps)
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
+        if rank == 0:
+            assert all(o.max() > 0 for o in outs)
+            for o in outs:
+                rb.pinned_free(o)
     else:
-        # strips -> GPU 0 -> pinned host frame, on a side stream so that it overlaps the next frame's rendering:
+        # (--exchange nccl) strips -> GPU 0 -> pinned host frame, on a side stream so that it overlaps the next frame's rendering:
         # ranks > 0 send their tone-mapped strip (NCCL over NVLink), rank 0 receives into place and copies D2H
         counts = [(bounds[r + 1] - bounds[r]) * W * 4 for r in range(world)]
         offs = [bounds[r] * W * 4 for r in range(world)]
@@ -554,10 +601,11 @@ def run_b200(args):
         if rank == 0:
             assert int(host.max()) > 0
     halo_miss = fr.halo_miss()
+    peer_error = bool(grp.error()) if grp is not None else False
     if world > 1:
-        t = torch.tensor([halo_miss], device="cuda", dtype=torch.int64)
+        t = torch.tensor([halo_miss, int(peer_error)], device="cuda", dtype=torch.int64)
         dist.all_reduce(t)
-        halo_miss = int(t.item())
+        halo_miss, peer_error = int(t[0].item()), bool(t[1].item())
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -577,11 +625,13 @@ def run_b200(args):
             "metric": "ReSTIR DI Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
-            "strips": {"parallelism": "strips%d" % world, "halo_rows": halo, "motion_rows_bound": motion_rows, "strip_bounds": bounds,
+            "strips": {"parallelism": "strips%d" % world, "exchange": None if world == 1 else ("peer stores over NVLink (rstr_strip_group)" if peer else "NCCL send/recv"), "halo_rows": halo, "motion_rows_bound": motion_rows, "strip_bounds": bounds,
                        "gbuffer_halo": None if world == 1 else ("rendered locally" if args.render_halo else "received from the neighbours"),
                        "l2": "no explicit flush: the per-frame pixel planes (%.0f MB) exceed the 126 MB L2" % (P * 212 / 1e6)},
             "e2e": {"value": P / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms, "ms_per_step_synchronous_call": e2e_sync_ms,
-                    "api": "rstr_render_frame_host_async + rstr_frame_wait_host (three pinned host frames in flight)" if world == 1 else "strips gathered to rank 0 over NCCL, one D2H",
+                    "api": "rstr_render_frame_host_async + rstr_frame_wait_host (three pinned host frames in flight)" if world == 1 else
+                    ("rstr_strip_group_frame + rstr_strip_group_present: strips tone-mapped into rank 0's frame by peer stores, D2H on rank 0, three host frames in flight" if peer
+                     else "strips gathered to rank 0 over NCCL, one D2H"),
                     "h2d_bytes_per_step": C.sizeof(rb.api.RstrCamera) + C.sizeof(rb.RstrParams), "d2h_bytes_per_step": P * 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -617,12 +667,18 @@ def run_b200(args):
                                     "sample": "%d frames of the same orbit at %dx%d, OpenMP over rows" % (n, W, H)}
         if halo_miss != 0:
             line["invalid"] = "halo_miss = %d: a strip read rows that were not resident, the image is NOT the single-GPU frame" % halo_miss
+        if peer_error:
+            line["invalid"] = "a wait on a peer GPU timed out"
         print(json.dumps(line))
+    if world > 1:
+        fr.sync(); torch.cuda.synchronize(); dist.barrier()
+    if grp is not None:
+        grp.close()
     fr.close()
     sc.close()
     if world > 1:
         dist.destroy_process_group()
-    if halo_miss != 0:
+    if halo_miss != 0 or peer_error:
         sys.exit(3)
 
 
@@ -636,6 +692,7 @@ def main():
     ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-targets", action="store_true", help="N = 1: skip the `targets` block (device-timed config4_1080p / config3 / config2)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: halo rows / gather as the library's peer stores over NVLink (default) or as NCCL send/recv issued from here (A/B)")
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
     ap.add_argument("--refine", type=int, default=4, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
     ap.add_argument("--no-fusion", action="store_true", help="separate G-buffer and phase-A kernels instead of the fused one (A/B)")

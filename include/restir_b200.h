@@ -299,6 +299,34 @@ int rstr_frame_set_fusion(RstrFrame*, int enable);
  * first.  enable == 0 stops profiling and frees the counters. */
 int rstr_frame_row_cost(RstrFrame*, int enable, double* cyclesPerRowGroup, int numGroups);
 
+/* ---- multi-GPU strips: one process per GPU, halo rows and the final gather as peer stores over NVLink ----
+ * Nothing in the reference to replace (it pins device 0, preview.cpp:112); this is the data plane BASELINE.json's north star
+ * asks for.  Each rank creates a strip frame (rstr_frame_create_strip, rows [bounds[r], bounds[r+1]), halo >
+ * max(ceil(spatialRadius), rstr_frame_motion_rows)), then a group on it; the ranks swap their RSTR_STRIP_HANDLE_BYTES blobs
+ * once (any transport: MPI, a pipe, torch.distributed) and connect.  From then on rstr_strip_group_frame renders this rank's
+ * strip of one frame -- identical, bit for bit, to the same rows of the single-GPU frame -- with the halo rows stored
+ * directly into the neighbours' memory by a kernel on this rank's stream and awaited by flag on the neighbours' streams
+ * (no host synchronisation, no library collective), and rstr_strip_group_present tone-maps the strip straight into rank
+ * 0's full-frame LDR slot and brings the assembled frame to the host on rank 0.  Every rank must issue the same sequence
+ * of group calls.  Ranks living in one process (tests) are connected through their device pointers instead of CUDA IPC. */
+typedef struct RstrStripGroup RstrStripGroup;
+#define RSTR_STRIP_HANDLE_BYTES 512
+int rstr_strip_group_create(RstrFrame* stripFrame, int rank, int world, RstrStripGroup**);
+int rstr_strip_group_handle(RstrStripGroup*, void* blob /* RSTR_STRIP_HANDLE_BYTES */);
+int rstr_strip_group_connect(RstrStripGroup*, const void* blobsInRankOrder /* world x RSTR_STRIP_HANDLE_BYTES */);
+/* gbuffer_render + restir_direct + gbuffer_update of runCuda (main.cpp:164-183) for this rank's strip, halo exchanges included */
+int rstr_strip_group_frame(RstrStripGroup*, const RstrCamera*, const RstrParams*, int looper, int iter);
+/* the building block of the above: push this rank's edge rows of the planes in planeMask (bit i = RSTR_PLANE_i) into the
+ * neighbours' halo rows, then make the frame's stream wait for the neighbours' rows of the same exchange */
+int rstr_strip_group_exchange(RstrStripGroup*, unsigned int planeMask);
+/* copyImageToPBO for strips: tone-map into slot (0 .. RSTR_LDR_SLOTS-1) of rank 0's full frame; on rank 0 the assembled
+ * W x H x uchar4 frame is copied to hostLdr (may be NULL) on a copy stream; rstr_strip_group_wait_host(slot) blocks until it is there */
+int rstr_strip_group_present(RstrStripGroup*, int toneMapping, void* hostLdr, size_t bytes, int slot);
+int rstr_strip_group_wait_host(RstrStripGroup*, int slot);
+/* *flag = 1 when a wait on a peer timed out (about 10 s): the peer died or the ranks issued different call sequences */
+int rstr_strip_group_error(RstrStripGroup*, int* flag);
+int rstr_strip_group_destroy(RstrStripGroup*);
+
 #ifdef __cplusplus
 }
 #endif

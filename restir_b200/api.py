@@ -176,6 +176,15 @@ def lib() -> C.CDLL:
     L.rstr_frame_mark.argtypes = [vp, ip]
     L.rstr_frame_elapsed_ms.argtypes = [vp, ip, ip, C.POINTER(fp)]
     L.rstr_frame_set_stream.argtypes = [vp, vp]
+    L.rstr_strip_group_create.argtypes = [vp, ip, ip, C.POINTER(vp)]
+    L.rstr_strip_group_handle.argtypes = [vp, vp]
+    L.rstr_strip_group_connect.argtypes = [vp, vp]
+    L.rstr_strip_group_frame.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
+    L.rstr_strip_group_exchange.argtypes = [vp, C.c_uint]
+    L.rstr_strip_group_present.argtypes = [vp, ip, vp, C.c_size_t, ip]
+    L.rstr_strip_group_wait_host.argtypes = [vp, ip]
+    L.rstr_strip_group_error.argtypes = [vp, C.POINTER(ip)]
+    L.rstr_strip_group_destroy.argtypes = [vp]
     L.rstr_host_alloc.restype = vp
     L.rstr_host_alloc.argtypes = [C.c_size_t]
     L.rstr_host_free.argtypes = [vp]
@@ -457,6 +466,57 @@ class Frame:
             out = np.zeros((P,), RESERVOIR_DTYPE)
         _check(lib().rstr_frame_read(self.f, FRAME_BUFFERS[name], out.ctypes.data, out.nbytes))
         return out
+
+
+STRIP_HANDLE_BYTES = 512
+
+
+class StripGroup:
+    """One rank of a multi-GPU strip decomposition (include/restir_b200.h, rstr_strip_group_*): halo rows and the final
+    gather travel as peer stores over NVLink between the ranks' frames; the caller only moves the 512-byte handles once."""
+
+    def __init__(self, frame: Frame, rank: int, world: int):
+        self.frame, self.rank, self.world = frame, rank, world
+        self.g = C.c_void_p()
+        _check(lib().rstr_strip_group_create(frame.f, rank, world, C.byref(self.g)))
+
+    def handle(self) -> bytes:
+        buf = (C.c_uint8 * STRIP_HANDLE_BYTES)()
+        _check(lib().rstr_strip_group_handle(self.g, buf))
+        return bytes(buf)
+
+    def connect(self, blobs) -> None:
+        """``blobs``: the handles of all ranks, in rank order."""
+        data = b"".join(blobs)
+        assert len(data) == self.world * STRIP_HANDLE_BYTES
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        _check(lib().rstr_strip_group_connect(self.g, buf))
+
+    def render(self, cam, params, looper: int, it: int = 0) -> None:
+        _check(lib().rstr_strip_group_frame(self.g, C.byref(cam), C.byref(params), looper, it))
+
+    def exchange(self, planes) -> None:
+        mask = 0
+        for p in planes:
+            mask |= 1 << PLANES[p]
+        _check(lib().rstr_strip_group_exchange(self.g, mask))
+
+    def present(self, tonemap: int, out, slot: int) -> None:
+        ptr, nbytes = (None, 0) if out is None else (out.ctypes.data, out.nbytes)
+        _check(lib().rstr_strip_group_present(self.g, tonemap, ptr, nbytes, slot))
+
+    def wait_host(self, slot: int) -> None:
+        _check(lib().rstr_strip_group_wait_host(self.g, slot))
+
+    def error(self) -> bool:
+        v = C.c_int(0)
+        _check(lib().rstr_strip_group_error(self.g, C.byref(v)))
+        return bool(v.value)
+
+    def close(self) -> None:
+        if self.g:
+            lib().rstr_strip_group_destroy(self.g)
+            self.g = None
 
 
 def load_image(path: str, flip: bool = True) -> np.ndarray:

@@ -1,82 +1,14 @@
 // capi.cu -- the C ABI (include/restir_b200.h) over the host scene builder and the sm_100a kernels.
-#include <stdio.h>
-#include <string.h>
-
-#include <atomic>
-#include <string>
-#include <vector>
-
-#include "kernels.h"
+#include "capi_internal.h"
 
 using namespace rs;
 
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-
-#define CU(expr)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (expr);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            char buf_[512];                                                                        \
-            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-            return fail(RSTR_ERR_CUDA, buf_);                                                      \
-        }                                                                                          \
-    } while (0)
-
-struct RstrScene {
-    HostScene hs;
-    DevScene dev{};
-    void* dNodes = nullptr; void* dTriGeom = nullptr; void* dTriNorm = nullptr;
-    void* dFastNodes = nullptr; void* dPrimToFast = nullptr; void* dFallback = nullptr; void* dRank = nullptr;
-    void* dMaterials = nullptr; void* dAlias = nullptr; void* dLights = nullptr;
-    void* dTexData = nullptr; void* dTexInfo = nullptr; void* dTriUV = nullptr; void* dEnvAlias = nullptr; void* dEnvDir = nullptr;
-    size_t deviceBytes = 0;
-    bool uploaded = false;      // set only after every device array exists and DevScene is filled
-    int traversalMode = RS_TRAVERSAL_FAST;
-};
-
-struct RstrFrame {
-    RstrScene* sc = nullptr;
-    int W = 0, H = 0, row0 = 0, row1 = 0, halo = 0, bufRow0 = 0, bufRows = 0;
-    size_t nBuf = 0;
-    float4* geom[2] = {nullptr, nullptr};
-    int* matId[2] = {nullptr, nullptr};
-    float4* albedoMotion = nullptr;
-    float* radiance = nullptr;
-    ResvD* resv[2] = {nullptr, nullptr};
-    ResvD* resvTemp = nullptr;
-    ResvD* resvTemp2 = nullptr;    // second publication buffer, allocated when spatialPasses > 1
-    HitRec* hit = nullptr;
-    float2* hitMR = nullptr;       // allocated when the scene has metallic / roughness maps
-    uchar4* ldr = nullptr;
-    uchar4* ldrB[RSTR_LDR_SLOTS] = {};        // LDR frames in flight of the pipelined host call
-    cudaStream_t copyStream = nullptr;
-    cudaEvent_t evRendered[RSTR_LDR_SLOTS] = {}, evCopied[RSTR_LDR_SLOTS] = {};
-    bool slotBusy[RSTR_LDR_SLOTS] = {};
-    unsigned int* haloMiss = nullptr;
-    unsigned long long* rowCost = nullptr;    // allocated by rstr_frame_row_cost
-    int* queue = nullptr;
-    unsigned int* queueCount = nullptr;
-    void* scratch = nullptr; size_t scratchBytes = 0;
-    int cur = 0;        // GBuffer::frameIdx
-    int resvOut = 0;    // which of resv[] is devDirectReservoir (written this frame)
-    RstrCamera lastCamera{};
-    bool haveLast = false;
-    bool first = true;  // ReSTIRFirstFrame
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[2 * RSTR_T_COUNT] = {};
-    cudaEvent_t xfer = nullptr;
-    cudaEvent_t marks[8] = {};
-    bool ownStream = true;
-    bool fuse = true;              // G-buffer + phase A as one kernel when both are asked for with the same camera
-    bool gbufPending = false;      // rstr_gbuffer_render was called and its launch is deferred to the next phase A (or flushed)
-    RstrCamera pendCam{};
-    CamDev pendC{}, pendLC{};
-    bool renderHalo = true;        // strip frames: G-buffer halo rows rendered locally (true) or received from the neighbours
-    bool ran[RSTR_T_COUNT] = {};
-};
+int rsFail(int code, const std::string& msg) { g_err = msg; return code; }
+void rsCountLaunches(int n) { g_launches += n; }
+static int fail(int code, const std::string& msg) { return rsFail(code, msg); }
 
 static CamDev toCamDev(const RstrCamera& c) {
     CamDev d;
@@ -91,7 +23,7 @@ static CamDev toCamDev(const RstrCamera& c) {
     return d;
 }
 
-static FrameDev toFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
+FrameDev rsToFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     FrameDev d{};
     d.W = f->W; d.H = f->H; d.rowLo = rowLo; d.rowHi = rowHi; d.bufRow0 = f->bufRow0; d.bufRows = f->bufRows;
     d.geom[0] = f->geom[f->cur]; d.geom[1] = f->geom[f->cur ^ 1];
@@ -346,8 +278,8 @@ int rstr_camera_update(RstrCamera* c) {
 int rstr_frame_destroy(RstrFrame* f) {
     if (!f) return RSTR_OK;
     if (f->stream) cudaStreamSynchronize(f->stream);
-    for (int i = 0; i < 2; i++) { cudaFree(f->geom[i]); cudaFree(f->matId[i]); cudaFree(f->resv[i]); }
-    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->resvTemp); cudaFree(f->resvTemp2); cudaFree(f->hit); cudaFree(f->hitMR); cudaFree(f->rowCost); cudaFree(f->ldr);
+    cudaFree(f->slab);             // geom[2], matId[2], resv[2], resvTemp, resvTemp2 live in the exchange slab
+    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->hit); cudaFree(f->hitMR); cudaFree(f->rowCost); cudaFree(f->ldr);
     cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->queueCount);
     for (int i = 0; i < RSTR_LDR_SLOTS; i++) {
         cudaFree(f->ldrB[i]);
@@ -381,14 +313,24 @@ int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int
         e = cudaMalloc(p, bytes);
         if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);      // restir.cu:482-489 zero-fills the reservoirs
     };
-    for (int i = 0; i < 2; i++) {
-        alloc((void**)&f->geom[i], n * sizeof(float4));
-        alloc((void**)&f->matId[i], n * sizeof(int));
-        alloc((void**)&f->resv[i], n * sizeof(ResvD));
+    {
+        // exchange slab: header of flags, then the planes a neighbouring strip reads, each 256-byte aligned
+        const size_t planeBytes[RS_XP_COUNT] = {n * sizeof(float4), n * sizeof(float4), n * sizeof(int), n * sizeof(int),
+                                                n * sizeof(ResvD), n * sizeof(ResvD), n * sizeof(ResvD), n * sizeof(ResvD)};
+        size_t off = RS_SLAB_HEADER;
+        for (int i = 0; i < RS_XP_COUNT; i++) { f->slabOff[i] = off; off += (planeBytes[i] + 255) & ~(size_t)255; }
+        f->slabBytes = off;
+        alloc(&f->slab, f->slabBytes);
+        if (e == cudaSuccess) {
+            char* b = (char*)f->slab;
+            f->geom[0] = (float4*)(b + f->slabOff[RS_XP_GEOM0]); f->geom[1] = (float4*)(b + f->slabOff[RS_XP_GEOM1]);
+            f->matId[0] = (int*)(b + f->slabOff[RS_XP_MATID0]); f->matId[1] = (int*)(b + f->slabOff[RS_XP_MATID1]);
+            f->resv[0] = (ResvD*)(b + f->slabOff[RS_XP_RESV0]); f->resv[1] = (ResvD*)(b + f->slabOff[RS_XP_RESV1]);
+            f->resvTemp = (ResvD*)(b + f->slabOff[RS_XP_TEMP]); f->resvTemp2 = (ResvD*)(b + f->slabOff[RS_XP_TEMP2]);
+        }
     }
     alloc((void**)&f->albedoMotion, n * sizeof(float4));
     alloc((void**)&f->radiance, n * 3 * sizeof(float));
-    alloc((void**)&f->resvTemp, n * sizeof(ResvD));
     alloc((void**)&f->hit, n * sizeof(HitRec));
     if (sc->hs.anyMRMaps) alloc((void**)&f->hitMR, n * sizeof(float2));
     alloc((void**)&f->ldr, n * sizeof(uchar4));
@@ -433,11 +375,11 @@ static inline void stageBegin(RstrFrame* f, int s) { cudaEventRecord(f->ev[2 * s
 static inline void stageEnd(RstrFrame* f, int s) { cudaEventRecord(f->ev[2 * s + 1], f->stream); }
 
 // launches a G-buffer render that rstr_gbuffer_render deferred (see there)
-static int flushGBuffer(RstrFrame* f) {
+int rsFlushGBuffer(RstrFrame* f) {
     if (!f->gbufPending) return RSTR_OK;
     f->gbufPending = false;
-    FrameDev d = f->renderHalo ? toFrameDev(f, f->bufRow0, f->bufRow0 + f->bufRows)    // halo rows rendered locally ...
-                               : toFrameDev(f, f->row0, f->row1);                     // ... or exchanged by the caller
+    FrameDev d = f->renderHalo ? rsToFrameDev(f, f->bufRow0, f->bufRow0 + f->bufRows)    // halo rows rendered locally ...
+                               : rsToFrameDev(f, f->row0, f->row1);                     // ... or exchanged by the caller
     stageBegin(f, RSTR_T_GBUFFER);
     g_launches += launchGBuffer(f->sc->dev, d, f->pendC, f->pendLC, f->stream);
     stageEnd(f, RSTR_T_GBUFFER);
@@ -448,7 +390,7 @@ static int flushGBuffer(RstrFrame* f) {
 int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
     int rc = checkCam(f, cam);
     if (rc) return rc;
-    if ((rc = flushGBuffer(f))) return rc;
+    if ((rc = rsFlushGBuffer(f))) return rc;
     // the reference reads an uninitialised lastCamera before the first GBuffer::update (gbuffer.h:56); use cam
     f->pendCam = *cam;
     f->pendC = toCamDev(*cam); f->pendLC = toCamDev(f->haveLast ? f->lastCamera : *cam);
@@ -458,20 +400,20 @@ int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
     // next call on this frame is phase A with the same camera: the launch is deferred until then.  Anything else that
     // looks at the G-buffer first (reads, halo exchange, gbuffer_update, sync, PTDirect) launches the plain kernel.
     const bool sameRows = !f->renderHalo || f->bufRows == f->row1 - f->row0;
-    if (!f->fuse || !sameRows || f->sc->dev.traversal != RS_TRAVERSAL_FAST) return flushGBuffer(f);
+    if (!f->fuse || !sameRows || f->sc->dev.traversal != RS_TRAVERSAL_FAST) return rsFlushGBuffer(f);
     return RSTR_OK;
 }
 
 int rstr_frame_set_fusion(RstrFrame* f, int enable) {
     if (!f) return fail(RSTR_ERR_ARG, "null frame");
-    int rc = flushGBuffer(f);
+    int rc = rsFlushGBuffer(f);
     f->fuse = enable != 0;
     return rc;
 }
 
 int rstr_gbuffer_update(RstrFrame* f, const RstrCamera* cam) {
     if (!f || !cam) return fail(RSTR_ERR_ARG, "null frame/camera");
-    int rc = flushGBuffer(f);
+    int rc = rsFlushGBuffer(f);
     if (rc) return rc;
     f->lastCamera = *cam; f->haveLast = true; f->cur ^= 1;                // gbuffer.cu:75-78
     return RSTR_OK;
@@ -481,7 +423,7 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     int rc = checkCam(f, cam);
     if (rc) return rc;
     if (!prm || prm->numCandidates < 0 || prm->numSpatial < 0 || prm->temporalCap < 1) return fail(RSTR_ERR_ARG, "bad RstrParams");
-    FrameDev d = toFrameDev(f, f->row0, f->row1);
+    FrameDev d = rsToFrameDev(f, f->row0, f->row1);
     if (f->gbufPending && memcmp(cam, &f->pendCam, sizeof(RstrCamera)) == 0 && f->sc->dev.traversal == RS_TRAVERSAL_FAST) {
         stageBegin(f, RSTR_T_RIS);
         int n = launchGBufferRestirA(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, f->stream);
@@ -493,7 +435,7 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
             return RSTR_OK;
         }
     }
-    if ((rc = flushGBuffer(f))) return rc;
+    if ((rc = rsFlushGBuffer(f))) return rc;
     stageBegin(f, RSTR_T_RIS);
     g_launches += launchRestirA(f->sc->dev, d, toCamDev(*cam), *prm, looper, iter, f->first ? 1 : 0, f->stream);
     stageEnd(f, RSTR_T_RIS);
@@ -501,10 +443,11 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     return RSTR_OK;
 }
 
-static int ensureTemp2(RstrFrame* f) {
-    if (f->resvTemp2) return RSTR_OK;
-    CU(cudaMalloc((void**)&f->resvTemp2, f->nBuf * sizeof(ResvD)));
+// first use of the second publication buffer: it starts as a copy of resvTemp (what the reference's single buffer holds)
+int rsEnsureTemp2(RstrFrame* f) {
+    if (f->temp2Ready) return RSTR_OK;
     CU(cudaMemcpyAsync(f->resvTemp2, f->resvTemp, f->nBuf * sizeof(ResvD), cudaMemcpyDeviceToDevice, f->stream));
+    f->temp2Ready = true;
     return RSTR_OK;
 }
 
@@ -516,8 +459,8 @@ int rstr_restir_phase_b_pass(RstrFrame* f, const RstrCamera* cam, const RstrPara
     const int passes = (prm->reuse & 2) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
     if ((passes && (pass < 1 || pass > passes)) || (!passes && pass != 1)) return fail(RSTR_ERR_ARG, "rstr_restir_phase_b_pass: pass out of range");
     if (passes) {
-        if (passes > 1 && (rc = ensureTemp2(f))) return rc;
-        FrameDev d = toFrameDev(f, f->row0, f->row1);
+        if (passes > 1 && (rc = rsEnsureTemp2(f))) return rc;
+        FrameDev d = rsToFrameDev(f, f->row0, f->row1);
         ResvD* buf[2] = {f->resvTemp, f->resvTemp2};
         if (pass == 1) stageBegin(f, RSTR_T_SPATIAL);
         launchRestirB(f->sc->dev, d, *prm, iter, buf[(pass - 1) & 1], buf[pass & 1], pass, pass == passes ? 1 : 0, f->stream);
@@ -581,8 +524,8 @@ int rstr_restir_direct(RstrFrame* f, const RstrCamera* cam, const RstrParams* pr
 int rstr_pathtrace_direct(RstrFrame* f, const RstrCamera* cam, int looper, int iter) {
     int rc = checkCam(f, cam);
     if (rc) return rc;
-    if ((rc = flushGBuffer(f))) return rc;
-    FrameDev d = toFrameDev(f, f->row0, f->row1);
+    if ((rc = rsFlushGBuffer(f))) return rc;
+    FrameDev d = rsToFrameDev(f, f->row0, f->row1);
     stageBegin(f, RSTR_T_PTDIRECT);
     g_launches += launchPTDirect(f->sc->dev, d, toCamDev(*cam), looper, iter, f->stream);
     stageEnd(f, RSTR_T_PTDIRECT);
@@ -718,7 +661,7 @@ int rstr_frame_wait_host(RstrFrame* f, int slot) {
 
 int rstr_frame_sync(RstrFrame* f) {
     if (!f) return fail(RSTR_ERR_ARG, "null frame");
-    int rc = flushGBuffer(f);
+    int rc = rsFlushGBuffer(f);
     if (rc) return rc;
     CU(cudaStreamSynchronize(f->stream));
     return RSTR_OK;
@@ -740,7 +683,7 @@ int rstr_frame_read_device(RstrFrame* f, int which, void* dev, size_t bytes) { r
 static int frameReadImpl(RstrFrame* f, int which, void* host, size_t bytes, bool toDevice) {
     if (!f || !host) return fail(RSTR_ERR_ARG, "rstr_frame_read: bad argument");
     {
-        int rc = flushGBuffer(f);
+        int rc = rsFlushGBuffer(f);
         if (rc) return rc;
     }
     const size_t off = (size_t)(f->row0 - f->bufRow0) * f->W, n = (size_t)(f->row1 - f->row0) * f->W;
@@ -832,7 +775,7 @@ int rstr_frame_halo_miss_reset(RstrFrame* f) {
 
 int rstr_frame_motion_rows(RstrFrame* f, unsigned int* out, int reset) {
     if (!f || !out) return fail(RSTR_ERR_ARG, "rstr_frame_motion_rows: bad argument");
-    int rc = flushGBuffer(f);
+    int rc = rsFlushGBuffer(f);
     if (rc) return rc;
     CU(cudaMemcpyAsync(out, f->haloMiss + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, f->stream));
     if (reset) CU(cudaMemsetAsync(f->haloMiss + 1, 0, sizeof(unsigned int), f->stream));
@@ -844,7 +787,7 @@ int rstr_frame_plane_row(RstrFrame* f, int plane, int row, void** devPtr, size_t
     if (!f || !devPtr || !rowBytes) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: bad argument");
     if (row < f->bufRow0 || row >= f->bufRow0 + f->bufRows) return fail(RSTR_ERR_ARG, "rstr_frame_plane_row: row not resident");
     {
-        int rc = flushGBuffer(f);
+        int rc = rsFlushGBuffer(f);
         if (rc) return rc;
     }
     size_t off = (size_t)(row - f->bufRow0) * f->W;
@@ -855,7 +798,7 @@ int rstr_frame_plane_row(RstrFrame* f, int plane, int row, void** devPtr, size_t
     case RSTR_PLANE_RESV_TEMP: *devPtr = f->resvTemp + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
     case RSTR_PLANE_RESV_OUT: *devPtr = f->resv[f->resvOut] + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
     case RSTR_PLANE_RESV_TEMP2: {
-        int rc = ensureTemp2(f);
+        int rc = rsEnsureTemp2(f);
         if (rc) return rc;
         *devPtr = f->resvTemp2 + off; *rowBytes = (size_t)f->W * sizeof(ResvD); break;
     }

@@ -317,6 +317,48 @@ def test_strips_with_exchanged_gbuffer_halo_and_multi_pass(gpu, passes):
     full.close(); sc.close()
 
 
+@pytest.mark.parametrize("passes", [1, 2])
+def test_strip_group_peer_exchange_equals_full_frame(gpu, passes):
+    """The library's multi-GPU data plane (rstr_strip_group_*: halo rows pushed into the neighbours' memory by a kernel,
+    awaited by flag, gather of the tone-mapped strips into rank 0's frame) with the ranks living in ONE process on one
+    GPU: strips == the single full frame bit for bit over 4 frames of the orbit, on uneven strips, and the gathered LDR
+    frame == the full frame's tone-mapped image.  (Across processes the same kernels run on CUDA-IPC mappings of the same
+    slabs: scripts/verify_multigpu.py under torchrun.)"""
+    sd = scenes.procedural(1, 200000, 10000, (1920, 1080))
+    sc = gpu.Scene.from_arrays(sd)
+    W, H = sd.resolution
+    base = gpu.Camera.from_scene(sd)
+    prm = gpu.default_params(reuse=3, radius=30.0, passes=passes)
+    full = sc.frame(W, H)
+    bounds = [0, 300, 520, 800, 1080]
+    frames = [sc.frame(W, H, rows=(bounds[r], bounds[r + 1]), halo=34) for r in range(4)]
+    groups = [gpu.StripGroup(f, r, 4) for r, f in enumerate(frames)]
+    blobs = [g.handle() for g in groups]
+    for g in groups:
+        g.connect(blobs)
+    out = gpu.pinned_empty(W * H * 4)
+    for k in range(4):
+        cam = base.orbit(k)
+        full.gbuffer_render(cam); full.restir_direct(cam, prm, k); full.gbuffer_update(cam)
+        for g in groups:
+            g.render(cam, prm, k, 0)
+        for g in groups:
+            g.present(gpu.TONEMAP_ACES, out if g.rank == 0 else None, k % 3)
+        groups[0].wait_host(k % 3)
+        for n in ("matid", "motion", "depth", "radiance", "reservoir", "light_index"):
+            assert helpers.mismatches(full.read(n), np.concatenate([f.read(n) for f in frames])) == 0, "frame %d %s" % (k, n)
+        full.tonemap(gpu.TONEMAP_ACES, 1.0)
+        assert helpers.mismatches(full.read("ldr"), out.reshape(-1, 4).copy()) == 0, "gathered LDR frame %d" % k
+    assert all(f.halo_miss() == 0 for f in frames)
+    assert not any(g.error() for g in groups)
+    assert max(f.motion_rows() for f in frames) < 34
+    for g in groups:
+        g.close()
+    for f in frames:
+        f.close()
+    full.close(); sc.close()
+
+
 def exchange_halos(gpu, strips, plane):
     """Single-process form of the neighbour exchange: each strip's edge rows are copied into the halo rows of the
     strips above / below (rstr_frame_copy_rows; the multi-process version sends the same rows over NCCL)."""
