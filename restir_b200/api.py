@@ -151,6 +151,7 @@ def lib() -> C.CDLL:
     L.rstr_restir_phase_b_pass.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip, ip]
     L.rstr_frame_set_halo_render.argtypes = [vp, ip]
     L.rstr_frame_set_fusion.argtypes = [vp, ip]
+    L.rstr_frame_set_pipeline.argtypes = [vp, ip]
     L.rstr_frame_row_cost.argtypes = [vp, ip, vp, ip]
     L.rstr_tonemap.argtypes = [vp, ip, fp]
     L.rstr_frame_save_png.argtypes = [vp, C.c_char_p, ip]
@@ -367,6 +368,10 @@ class Frame:
     def set_fusion(self, on: bool) -> None:
         """G-buffer + phase A as one kernel sharing the primary-ray tree walk (default on)."""
         _check(lib().rstr_frame_set_fusion(self.f, 1 if on else 0))
+
+    def set_pipeline(self, staged: bool) -> None:
+        """Phase A as the staged kernel pipeline (default) or as one fused kernel."""
+        _check(lib().rstr_frame_set_pipeline(self.f, 1 if staged else 0))
 
     def set_halo_render(self, on: bool) -> None:
         _check(lib().rstr_frame_set_halo_render(self.f, 1 if on else 0))

@@ -10,6 +10,16 @@ int rsFail(int code, const std::string& msg) { g_err = msg; return code; }
 void rsCountLaunches(int n) { g_launches += n; }
 static int fail(int code, const std::string& msg) { return rsFail(code, msg); }
 
+static int smCount() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 static CamDev toCamDev(const RstrCamera& c) {
     CamDev d;
     memcpy(d.position, c.position, 12); memcpy(d.right, c.right, 12); memcpy(d.up, c.up, 12); memcpy(d.view, c.view, 12);
@@ -30,7 +40,7 @@ FrameDev rsToFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
     d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
     d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
-    d.hit = f->hit; d.hitMR = f->hitMR; d.rowCost = f->rowCost; d.haloMiss = f->haloMiss; d.motionRows = f->haloMiss + 1; d.queue = f->queue; d.queueCount = f->queueCount;
+    d.hit = f->hit; d.hitMR = f->hitMR; d.rowCost = f->rowCost; d.haloMiss = f->haloMiss; d.motionRows = f->haloMiss + 1; d.queue = f->queue; d.queueCount = f->queueCount; d.shadeQueue = f->shadeQueue;
     return d;
 }
 
@@ -280,7 +290,7 @@ int rstr_frame_destroy(RstrFrame* f) {
     if (f->stream) cudaStreamSynchronize(f->stream);
     cudaFree(f->slab);             // geom[2], matId[2], resv[2], resvTemp, resvTemp2 live in the exchange slab
     cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->hit); cudaFree(f->hitMR); cudaFree(f->rowCost); cudaFree(f->ldr);
-    cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->queueCount);
+    cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->shadeQueue); cudaFree(f->queueCount);
     for (int i = 0; i < RSTR_LDR_SLOTS; i++) {
         cudaFree(f->ldrB[i]);
         if (f->evRendered[i]) cudaEventDestroy(f->evRendered[i]);
@@ -336,6 +346,7 @@ int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int
     alloc((void**)&f->ldr, n * sizeof(uchar4));
     alloc((void**)&f->haloMiss, 4 * sizeof(unsigned int));     // [0] halo misses, [1] max |row(motion) - row|
     alloc((void**)&f->queue, n * sizeof(int));
+    alloc((void**)&f->shadeQueue, n * sizeof(int));
     alloc((void**)&f->queueCount, 4 * sizeof(unsigned int));
     if (e == cudaSuccess) {
         // a zero-filled reference reservoir has no sample: lightId must read as "none"
@@ -404,6 +415,14 @@ int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
     return RSTR_OK;
 }
 
+// G-buffer + phase A of a frame: 1 (default) = staged pipeline (k_primary, k_candidates, k_shadow, k_temporal), 0 = one fused kernel
+int rstr_frame_set_pipeline(RstrFrame* f, int staged) {
+    if (!f) return fail(RSTR_ERR_ARG, "null frame");
+    int rc = rsFlushGBuffer(f);
+    f->staged = staged != 0;
+    return rc;
+}
+
 int rstr_frame_set_fusion(RstrFrame* f, int enable) {
     if (!f) return fail(RSTR_ERR_ARG, "null frame");
     int rc = rsFlushGBuffer(f);
@@ -426,7 +445,8 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     FrameDev d = rsToFrameDev(f, f->row0, f->row1);
     if (f->gbufPending && memcmp(cam, &f->pendCam, sizeof(RstrCamera)) == 0 && f->sc->dev.traversal == RS_TRAVERSAL_FAST) {
         stageBegin(f, RSTR_T_RIS);
-        int n = launchGBufferRestirA(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, f->stream);
+        int n = f->staged ? launchPhaseAStaged(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, smCount(), f->stream)
+                          : launchGBufferRestirA(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, f->stream);
         if (n > 0) {
             f->gbufPending = false;
             g_launches += n;

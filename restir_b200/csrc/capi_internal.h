@@ -64,6 +64,8 @@ struct RstrFrame {
     unsigned int* haloMiss = nullptr;
     unsigned long long* rowCost = nullptr;    // allocated by rstr_frame_row_cost
     int* queue = nullptr;
+    int* shadeQueue = nullptr;     // staged phase A: compact list of shaded pixels
+    bool staged = true;            // phase A as the staged pipeline (kernels.cu) instead of the single fused kernel
     unsigned int* queueCount = nullptr;
     void* scratch = nullptr; size_t scratchBytes = 0;
     int cur = 0;        // GBuffer::frameIdx

@@ -91,7 +91,8 @@ struct FrameDev {
     HitRec* hit;
     float2* hitMR;             // {metallic, roughness} of the shaded point; only allocated for scenes with such maps
     int* queue;                // pixels deferred to the reference-order fix-up kernel
-    unsigned int* queueCount;
+    unsigned int* queueCount;  // [0] fix-up queue length, [1] shaded-pixel queue length, [2] k_shadow's cursor into it
+    int* shadeQueue;           // staged phase A: pixels (global index) whose jittered ray hit a shaded surface
     unsigned int* haloMiss;    // count of neighbour / reprojection reads that fell outside the resident rows
     unsigned int* motionRows;  // running max |row(motion) - row| of the reprojected pixels (bound for the temporal halo)
     unsigned long long* rowCost;  // optional [ceil(H / 8)] cycle accumulators (rstr_frame_row_cost), else null

@@ -998,65 +998,69 @@ RS_D void restirAPixelExact(const DevScene& s, const FrameDev& f, const CamDev& 
     restirAAfterHit<true, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, d, h);
 }
 
-// restir.cu:133-192 (+ :211-230) once the jittered primary ray's hit is known
-template <bool EXACT, bool SPATIAL>
-RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams& prm, int iter, int first,
-                          int x, int y, Stack& stack, Rng rng, f3 d, const Hit& h) {
-    size_t li = planeIndex(f, x, y);
-    int index = y * f.W + x;
-    int status = 0;      // 0 miss, 1 emitter, 2 shaded
-    f3 pos, nrm;
-    int matId = -1, type = 0;
-    float metallic = 0.f, roughness = 1.f;
-    if (h.prim >= 0) {
-        Tri t = loadTri(s, h.prim);
-        const float4* np = s.triNorm + 3 * (size_t)h.prim;
-        float4 na4 = __ldg(np), nb4 = __ldg(np + 1), nc4 = __ldg(np + 2);
-        f3 na = mk3(na4.x, na4.y, na4.z), nb = mk3(na4.w, nb4.x, nb4.y), nc = mk3(nb4.z, nb4.w, nc4.x);
-        float bz = 1.f - h.bx - h.by;
-        pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;
-        nrm = normalize(nb * h.bx + nc * h.by + na * bz);
-        matId = t.matId;
-        Surf m = texturedMaterial(s, matId, h.prim, h.bx, h.by, nrm);                // restir.cu:140
-        type = m.type;
-        metallic = m.metallic;
-        roughness = m.roughness;
-        status = type == 4 ? 1 : 2;
+// ---- the stages of restir.cu:133-192 (+ :211-230) once the jittered primary ray's hit is known.  The fused kernel runs
+// them back to back in one thread (restirAAfterHit); the staged pipeline runs each in a kernel of its own over the
+// compacted list of shaded pixels.
+struct ShadePoint {
+    f3 pos, nrm, wo;
+    int matId, type;
+    float metallic, roughness;
+};
+// restir.cu:133-153: 0 miss, 1 emitter, 2 shaded (ShadePoint filled, normal flipped toward wo)
+RS_D int shadePointOf(const DevScene& s, const Hit& h, f3 d, ShadePoint& sp) {
+    if (h.prim < 0) return 0;
+    Tri t = loadTri(s, h.prim);
+    const float4* np = s.triNorm + 3 * (size_t)h.prim;
+    float4 na4 = __ldg(np), nb4 = __ldg(np + 1), nc4 = __ldg(np + 2);
+    f3 na = mk3(na4.x, na4.y, na4.z), nb = mk3(na4.w, nb4.x, nb4.y), nc = mk3(nb4.z, nb4.w, nc4.x);
+    float bz = 1.f - h.bx - h.by;
+    sp.pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;
+    sp.nrm = normalize(nb * h.bx + nc * h.by + na * bz);
+    sp.matId = t.matId;
+    Surf m = texturedMaterial(s, sp.matId, h.prim, h.bx, h.by, sp.nrm);              // restir.cu:140
+    sp.type = m.type;
+    sp.metallic = m.metallic;
+    sp.roughness = m.roughness;
+    if (sp.type == 4) return 1;
+    sp.wo = -d;
+    if (sp.type != 2 && dot(sp.nrm, sp.wo) < 0.f) sp.nrm = -sp.nrm;                  // restir.cu:150-153
+    return 2;
+}
+// restir.cu:133-146 -> WriteRadiance for a pixel whose jittered ray missed (status 0) or hit an emitter (status 1)
+template <bool SPATIAL>
+RS_D void unshadedPixel(const DevScene& s, const FrameDev& f, size_t li, int status, f3 d, int iter) {
+    f3 direct = status == 1 ? mk3(1.f) : (s.envTex >= 0 ? envLookup(s, d) : mk3(0.f));
+    writeRadiance(f, li, direct, iter);
+    if (SPATIAL) {
+        float4* q = (float4*)(f.hit + li);
+        q[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (status != 2) {                                                               // restir.cu:133-146 -> WriteRadiance
-        f3 direct = status == 1 ? mk3(1.f) : (s.envTex >= 0 ? envLookup(s, d) : mk3(0.f));
-        writeRadiance(f, li, direct, iter);
-        if (SPATIAL) {
-            float4* q = (float4*)(f.hit + li);
-            q[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        return true;
-    }
-    f3 wo = -d;
-    if (type != 2 && dot(nrm, wo) < 0.f) nrm = -nrm;                                 // restir.cu:150-153
+}
+// restir.cu:155-169: the RIS reservoir over numCandidates light samples
+RS_D Resv candidateLoop(const DevScene& s, const RstrParams& prm, const ShadePoint& sp, Rng& rng) {
     Resv R = emptyResv();
     const f3 diffuse = diffuseTerm(mk3(1.f));                                        // material.baseColor = 1 (restir.cu:141)
     const int nc = prm.numCandidates;
-    for (int i = 0; i < nc; i++) {                                                   // restir.cu:156-169
+    for (int i = 0; i < nc; i++) {
         float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
         f3 Li = mk3(0.f), wi = mk3(0.f);
         float dist = 0.f;
         int lid = -1;
-        float p = s.numLights > 0 ? sampleLight(s, pos, c0, c1, c2, c3, Li, wi, dist, lid) : -1.f;
-        f3 g = Li * materialBSDF(type, metallic, roughness, mk3(1.f), diffuse, nrm, wo, wi) * satDot(nrm, wi);
+        float p = s.numLights > 0 ? sampleLight(s, sp.pos, c0, c1, c2, c3, Li, wi, dist, lid) : -1.f;
+        f3 g = Li * materialBSDF(sp.type, sp.metallic, sp.roughness, mk3(1.f), diffuse, sp.nrm, sp.wo, wi) * satDot(sp.nrm, wi);
         float weight = luminance(g / p);
         if (isNanOrInf(weight) || p <= 0.f) weight = 0.f;
         float rnd = rng.next();
         R.w += weight; R.M++;                                                        // Reservoir::update, restir.h:38
         if (rnd * R.w < weight) { R.wi = wi; R.dist = dist; R.lightId = lid; }
     }
-    // restir.cu:172-176.  With weight == 0 the test cannot change anything, so the ray is skipped.
-    if (R.w != 0.f) {
-        int occ = traceOccluded<EXACT>(s, pos, pos + R.wi * R.dist, stack);
-        if (occ < 0) return false;
-        if (occ) R.w = 0.f;
-    }
+    return R;
+}
+// restir.cu:180-192, 211-230: temporal merge, history / publication stores, and the final shade when spatial reuse is off
+template <bool SPATIAL>
+RS_D void temporalAndStore(const DevScene& s, const FrameDev& f, const RstrParams& prm, int iter, int first, size_t li, int index,
+                           f3 nrm, f3 wo, int matId, int type, float metallic, float roughness, Resv R, Rng rng) {
     if (!first && (prm.reuse & 1)) {                                                 // restir.cu:180-185
         Resv T = findTemporal(f, li, index);
         if (!resvInvalid(T)) {
@@ -1078,6 +1082,24 @@ RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams
     } else {
         writeRadiance(f, li, shadeReservoir(s, R, type, metallic, roughness, nrm, wo), iter);
     }
+}
+
+// all stages in one thread; false = undecided, nothing written
+template <bool EXACT, bool SPATIAL>
+RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams& prm, int iter, int first,
+                          int x, int y, Stack& stack, Rng rng, f3 d, const Hit& h) {
+    size_t li = planeIndex(f, x, y);
+    ShadePoint sp;
+    const int status = shadePointOf(s, h, d, sp);
+    if (status != 2) { unshadedPixel<SPATIAL>(s, f, li, status, d, iter); return true; }
+    Resv R = candidateLoop(s, prm, sp, rng);
+    // restir.cu:172-176.  With weight == 0 the test cannot change anything, so the ray is skipped.
+    if (R.w != 0.f) {
+        int occ = traceOccluded<EXACT>(s, sp.pos, sp.pos + R.wi * R.dist, stack);
+        if (occ < 0) return false;
+        if (occ) R.w = 0.f;
+    }
+    temporalAndStore<SPATIAL>(s, f, prm, iter, first, li, y * f.W + x, sp.nrm, sp.wo, sp.matId, sp.type, sp.metallic, sp.roughness, R, rng);
     return true;
 }
 
@@ -1182,6 +1204,220 @@ __global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant
         restirAPixelExact<SPATIAL>(s, f, cam, prm, looper, iter, first, idx % f.W, idx / f.W, stack);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(s.fallbackRays + 1, n);
+}
+
+// ------------------------------------------------------------------------------------------------ staged phase A
+// The same work as k_gbuffer_restir_a, cut where the shape of the parallelism changes (default pipeline):
+//   k_primary      one packet walk per 8x4 tile for both primary rays of every pixel; G-buffer; pixels whose jittered ray
+//                  missed or hit an emitter are finished here; the others are appended to a compact queue
+//   k_candidates   one thread per QUEUED pixel: 32 light candidates (restir.cu:155-169) -- full warps, no sky lanes
+//   k_shadow       shadow rays (restir.cu:172-176) by persistent warps that refill finished lanes from the queue: shadow rays of
+//                  neighbouring pixels go to unrelated lights, so lockstep walks of a fixed set of 32 keep 6 lanes busy
+//                  (scripts/travsim.cpp); here a lane takes the next ray as soon as enough lanes are idle
+//   k_temporal     temporal merge + stores (restir.cu:180-192, 211-230) per queued pixel
+// Between the stages a pixel's state lives in planes that are free at that point: the {prim, barycentrics} of the
+// jittered hit in HitRec (rewritten by k_candidates), the reservoir before the shadow test in resvTemp, the shading
+// point in this frame's history plane resvOut (written for good by k_temporal).  Same arithmetic, same RNG stream per
+// pixel: every buffer is bit-identical to the fused kernel's (test_staged_pipeline_equals_fused_kernel).
+#ifndef RS_MINB_PRIMARY
+#define RS_MINB_PRIMARY 8
+#endif
+#ifndef RS_MINB_CAND
+#define RS_MINB_CAND 8
+#endif
+#ifndef RS_MINB_SHADOW
+#define RS_MINB_SHADOW 8
+#endif
+#ifndef RS_REFILL_MIN
+#define RS_REFILL_MIN 8       /* k_shadow refills when at least this many lanes are idle */
+#endif
+
+template <bool SPATIAL>
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_PRIMARY) k_primary(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                           const __grid_constant__ CamDev cam, const __grid_constant__ CamDev lastCam,
+                                                           int looper, int iter) {
+    RS_DECLARE_PACKET(pk, 2);
+    __shared__ unsigned int t0;
+    if (f.rowCost && threadIdx.x == 0) t0 = (unsigned int)clock64();
+    int x, y;
+    const bool active = pixelOf(f, x, y);
+    Rng rng;
+    rng.x = 1;
+    f3 oC = mk3(0.f), dC = mk3(0.f, 0.f, 1.f), oJ = oC, dJ = dC;
+    if (active) {
+        cameraRay(cam, x, y, .5f, .5f, oC, dC);                                      // gbuffer.cu:11-23
+        jitteredRay(f, cam, looper, x, y, rng, oJ, dJ);                              // restir.cu:129
+    }
+    Hit hC, hJ;
+    bool ok;
+    {
+        PRay a = prayBegin(oC, dC, active), b = prayBegin(oJ, dJ, active);
+        packetWalk<true>(s, a, b, pk_ta, pk_tb, pk_wst);
+        ok = prayResolve(s, a, pk_ta, hC);
+        ok = prayResolve(s, b, pk_tb, hJ) && ok;
+    }
+    bool shaded = false;
+    if (active) {
+        if (!ok) enqueuePixel(f, x, y);                                              // both stages again in the fix-up kernel
+        else {
+            gbufferFinish(s, f, lastCam, x, y, oC, dC, hC);
+            const size_t li = planeIndex(f, x, y);
+            int status = 0;
+            if (hJ.prim >= 0) {
+                const int matId = __float_as_int(__ldg(s.triGeom + 3 * (size_t)__ldg(s.primToFast + hJ.prim) + 2).y);
+                status = __ldg(&s.materials[matId].type) == 4 ? 1 : 2;              // restir.cu:143
+            }
+            if (status != 2) unshadedPixel<SPATIAL>(s, f, li, status, dJ, iter);
+            else {
+                shaded = true;
+                *(float4*)(f.hit + li) = make_float4(hJ.bx, hJ.by, __int_as_float(hJ.prim), 0.f);
+            }
+        }
+    }
+    // warp-aggregated append: the queue keeps the pixels of a tile together
+    const unsigned m = __ballot_sync(0xffffffffu, shaded);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(f.queueCount + 1, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (shaded) f.shadeQueue[base + __popc(m & ((1u << lane) - 1u))] = y * f.W + x;
+    }
+    if (f.rowCost) accountBlock(f, &t0);
+}
+
+// profile for the strip cuts: a thread's share of the cycles its block held its slot, booked on the pixel's row group
+RS_D void accountPixel(const FrameDev& f, int y, long long t0) {
+    atomicAdd(f.rowCost + (y >> 3), (unsigned long long)((clock64() - t0) / RS_BLOCK));
+}
+
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_CAND) k_candidates(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                           const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm, int looper) {
+    const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
+    if (i >= f.queueCount[1]) return;
+    const long long t0 = f.rowCost ? clock64() : 0;
+    const int index = f.shadeQueue[i];
+    const int x = index % f.W, y = index / f.W;
+    const size_t li = planeIndex(f, x, y);
+    Rng rng;
+    f3 o, d;
+    jitteredRay(f, cam, looper, x, y, rng, o, d);
+    const float4 q0 = *(const float4*)(f.hit + li);
+    Hit h;
+    h.bx = q0.x; h.by = q0.y; h.prim = __float_as_int(q0.z); h.t = 0.f;
+    ShadePoint sp;
+    shadePointOf(s, h, d, sp);
+    const Resv R = candidateLoop(s, prm, sp, rng);
+    storeResv(f.resvTemp + li, R);                                                   // before the shadow test
+    float4* sc = (float4*)(f.resvOut + li);                                          // free until k_temporal writes the history
+    sc[0] = make_float4(sp.pos.x, sp.pos.y, sp.pos.z, sp.metallic);
+    sc[1] = make_float4(sp.roughness, 0.f, 0.f, 0.f);
+    float4* q = (float4*)(f.hit + li);
+    q[0] = make_float4(sp.nrm.x, sp.nrm.y, sp.nrm.z, __int_as_float(sp.matId));
+    q[1] = make_float4(sp.wo.x, sp.wo.y, sp.wo.z, __uint_as_float(rng.x));
+    if (f.rowCost) accountPixel(f, y, t0);
+}
+
+// DevScene::testOcclusion (scene.h:286-316) for every queued pixel whose reservoir has weight: occluded -> weight = 0
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f) {
+    RS_DECLARE_REFSTACK(stack);
+    const unsigned FULL = 0xffffffffu;
+    const unsigned n = f.queueCount[1];
+    const int lane = threadIdx.x & 31;
+    RayT r;
+    RayF rf;
+    float dist = 0.f;
+    int cur = RS_DONE, sp = 0, rowY = 0;
+    size_t li = 0;
+    long long tRay = 0;
+    bool exhausted = false;                       // warp-uniform: the queue is empty
+    r.o = r.d = r.inv = mk3(0.f); r.flags = 0; r.dim = r.lesser = 0;
+    rf.inv = rf.oi = mk3(0.f);
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, cur == RS_DONE);
+        if (idle == FULL && exhausted) break;
+        if (!exhausted && (__popc(idle) >= RS_REFILL_MIN || idle == FULL)) {
+            unsigned base = 0;
+            const int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(f.queueCount + 2, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= n) exhausted = true;
+            const unsigned i = base + __popc(idle & ((1u << lane) - 1u));
+            if (cur == RS_DONE && i < n) {
+                const int index = f.shadeQueue[i];
+                rowY = index / f.W;
+                li = planeIndex(f, index % f.W, rowY);
+                const float4* rp = (const float4*)(f.resvTemp + li);
+                const float4 ra = rp[0];                                             // {wi, dist}
+                const float w = rp[1].x;
+                if (w != 0.f) {                                                      // restir.cu:172-176: weight 0 cannot change
+                    const float4 pp = *(const float4*)(f.resvOut + li);
+                    const f3 pos = mk3(pp.x, pp.y, pp.z);
+                    const f3 to = pos + mk3(ra.x, ra.y, ra.z) * ra.w;
+                    f3 dir = to - pos;                                               // traceOccluded (scene.h:286-295)
+                    dist = length(dir);
+                    if (dist > 0.f) {
+                        dir = dir / dist;
+                        r = makeRayT(pos + dir * 1e-5f, dir);
+                        dist -= 1e-4f * 2.f;
+                        rf = makeRayF(r);
+                        float tr;
+                        if (slabHit(rf, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], dist, tr)) {
+                            cur = s.fastRoot; sp = 0;
+                            if (f.rowCost) tRay = clock64();
+                        }
+                    }
+                }
+            }
+        }
+        if (cur != RS_DONE) {
+            if (cur >= 0) {
+                const float4* np = s.fastNodes + 4 * (size_t)cur;
+                const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+                const int2 l = __ldg((const int2*)(np + 3));
+                float tL, tR;
+                const bool hL = slabHit(rf, a.x, a.y, a.z, a.w, b.x, b.y, dist, tL);
+                const bool hR = slabHit(rf, b.z, b.w, c.x, c.y, c.z, c.w, dist, tR);
+                if (hL && hR) { stack.pushRef(sp, l.y); sp++; cur = l.x; }
+                else if (hL) cur = l.x;
+                else if (hR) cur = l.y;
+                else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
+            } else {
+                const int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+                bool occluded = false;
+                for (int i = 0; i < count && !occluded; i++) {
+                    const Tri t = loadTriFast(s, first + i);
+                    float bx, by, d, tb;
+                    occluded = triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist && leafBox(r, t, tb) && tb < dist;
+                }
+                if (occluded) { f.resvTemp[li].weight = 0.f; cur = RS_DONE; }
+                else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
+            }
+            if (f.rowCost && cur == RS_DONE) atomicAdd(f.rowCost + (rowY >> 3), (unsigned long long)((clock64() - tRay) / 24));
+        }
+    }
+}
+
+template <bool SPATIAL>
+__global__ void __launch_bounds__(RS_BLOCK) k_temporal(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                       const __grid_constant__ RstrParams prm, int iter, int first) {
+    const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
+    if (i >= f.queueCount[1]) return;
+    const long long t0 = f.rowCost ? clock64() : 0;
+    const int index = f.shadeQueue[i];
+    const int x = index % f.W, y = index / f.W;
+    const size_t li = planeIndex(f, x, y);
+    const float4* q = (const float4*)(f.hit + li);
+    const float4 h0 = q[0], h1 = q[1];
+    const float4* sc = (const float4*)(f.resvOut + li);
+    const float metallic = sc[0].w, roughness = sc[1].x;
+    const int matId = __float_as_int(h0.w);
+    Rng rng;
+    rng.x = __float_as_uint(h1.w);
+    const Resv R = loadResv(f.resvTemp + li);
+    temporalAndStore<SPATIAL>(s, f, prm, iter, first, li, index, mk3(h0.x, h0.y, h0.z), mk3(h1.x, h1.y, h1.z), matId,
+                              __ldg(&s.materials[matId].type), metallic, roughness, R, rng);
+    if (f.rowCost) accountPixel(f, y, t0);
 }
 
 // restir.cu:47-85 (+ mathUtil.h:128-132 toConcentricDisk)
@@ -1445,6 +1681,26 @@ int launchGBufferRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam
         k_gbuffer_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
     }
     return 2;
+}
+// staged form of the above (k_primary -> k_candidates -> k_shadow -> k_temporal -> fix-up)
+int launchPhaseAStaged(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, const RstrParams& p, int looper, int iter, int first, int numSMs, cudaStream_t st) {
+    if (s.traversal == RS_TRAVERSAL_EXACT) return 0;
+    cudaMemsetAsync(f.queueCount, 0, 4 * sizeof(unsigned int), st);
+    const dim3 grid = pixelGrid(f);
+    const unsigned linear = grid.x * grid.y;           // one thread per pixel of the rows: upper bound of the queue length
+    const bool sp = (p.reuse & 2) != 0;
+    if (sp) k_primary<true><<<grid, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, looper, iter);
+    else k_primary<false><<<grid, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, looper, iter);
+    k_candidates<<<linear, RS_BLOCK, 0, st>>>(s, f, cam, p, looper);
+    k_shadow<<<(unsigned)(numSMs * RS_MINB_SHADOW), RS_BLOCK, 0, st>>>(s, f);
+    if (sp) {
+        k_temporal<true><<<linear, RS_BLOCK, 0, st>>>(s, f, p, iter, first);
+        k_gbuffer_restir_a_fix<true><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+    } else {
+        k_temporal<false><<<linear, RS_BLOCK, 0, st>>>(s, f, p, iter, first);
+        k_gbuffer_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+    }
+    return 5;
 }
 void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, const ResvD* src, ResvD* dst, int pass, int last, cudaStream_t st) {
     k_restir_b<<<pixelGrid(f), 128, 0, st>>>(s, f, p, iter, src, dst, pass, last);
