@@ -277,13 +277,14 @@ def measure_motion_rows(sc, base, W, H, rb):
     return rows
 
 
-def time_workload(rb, name, steps, warmup):
+def time_workload(rb, name, steps, warmup, staged=True):
     """Device-timed ms/frame of another workload on this GPU (the `targets` block): same frame loop, CUDA events on the
     launching stream around `steps` frames."""
     desc, spec, res, reuse, radius = WORKLOADS[name]
     sd = make_scene(spec, res)
     sc = rb.Scene.from_arrays(sd)
     fr = sc.frame(*res)
+    fr.set_pipeline(staged)
     base = rb.Camera.from_scene(sd)
     prm = rb.default_params(reuse=reuse, radius=radius)
 
@@ -384,6 +385,7 @@ def run_b200(args):
             fr.close()
         rows = strips.strip_rows(H, world, rank, bounds)
         fr = sc.frame(W, H, rows=rows, halo=halo)
+        fr.set_pipeline(args.pipeline == "staged")
         if args.no_fusion:
             fr.set_fusion(False)
         plan = strips.exchange_plan(H, world, halo, bounds) if world > 1 else []
@@ -625,6 +627,7 @@ def run_b200(args):
             "metric": "ReSTIR DI Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
+            "pipeline": args.pipeline,
             "strips": {"parallelism": "strips%d" % world, "exchange": None if world == 1 else ("peer stores over NVLink (rstr_strip_group)" if peer else "NCCL send/recv"), "halo_rows": halo, "motion_rows_bound": motion_rows, "strip_bounds": bounds,
                        "gbuffer_halo": None if world == 1 else ("rendered locally" if args.render_halo else "received from the neighbours"),
                        "l2": "no explicit flush: the per-frame pixel planes (%.0f MB) exceed the 126 MB L2" % (P * 212 / 1e6)},
@@ -635,7 +638,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": C.sizeof(rb.api.RstrCamera) + C.sizeof(rb.RstrParams), "d2h_bytes_per_step": P * 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": "k_gbuffer_restir_a" if fused else "k_restir_a", "spatial": "k_restir_b"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": ("k_primary + k_candidates + k_shadow + k_temporal" if args.pipeline == "staged" else "k_gbuffer_restir_a") if fused else "k_restir_a", "spatial": "k_restir_b"}[dom],
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic[0] if world == 1 else None, "traffic_source": traffic[1],
                          "algorithmic_bytes_per_pixel": bpp, "kernel_ms": stage_ms[dom],
@@ -654,7 +657,7 @@ def run_b200(args):
             line["targets"] = {}
             for name in ("config4_1080p", "config3", "config2"):
                 if name != args.workload:
-                    line["targets"][name] = time_workload(rb, name, min(args.steps, 60), 5)
+                    line["targets"][name] = time_workload(rb, name, min(args.steps, 60), 5, args.pipeline == "staged")
             t4 = line["targets"].get("config4_1080p")
             if t4:
                 line["targets"]["north_star"] = {"config4_1080p_ms_per_frame": t4["ms_per_frame"], "target_ms": 2.0, "met": t4["ms_per_frame"] <= 2.0}
@@ -695,6 +698,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: halo rows / gather as the library's peer stores over NVLink (default) or as NCCL send/recv issued from here (A/B)")
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
     ap.add_argument("--refine", type=int, default=4, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
+    ap.add_argument("--pipeline", default="staged", choices=["staged", "fused"], help="phase A as the staged kernel pipeline (default) or as one fused kernel (A/B)")
     ap.add_argument("--no-fusion", action="store_true", help="separate G-buffer and phase-A kernels instead of the fused one (A/B)")
     ap.add_argument("--split-exchange", action="store_true", help="N > 1: history reservoirs in a second exchange after phase B (A/B)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for the history-reservoir exchange at the end of the frame instead of under the next G-buffer")

@@ -68,12 +68,13 @@ def run_oracle(orc, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, a
 
 
 def run_gpu(rb, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=ALL_BUFS, light_index=False,
-            rows=None, halo=0, scene=None, exact=False, passes=1, fuse=True):
+            rows=None, halo=0, scene=None, exact=False, passes=1, fuse=True, staged=True):
     W, H = sd.resolution
     sc = scene or rb.Scene.from_arrays(sd)
     sc.set_traversal(exact)
     fr = sc.frame(W, H, rows=rows, halo=halo)
     fr.set_fusion(fuse)
+    fr.set_pipeline(staged)
     base = rb.Camera.from_scene(sd)
     prm = rb.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates, passes=passes)
     out = []

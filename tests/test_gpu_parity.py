@@ -56,18 +56,21 @@ def test_against_golden_fixtures(gpu, name):
 
 @pytest.mark.parametrize("reuse", [0, 3])
 def test_fused_gbuffer_phase_a_equals_separate_kernels(gpu, port_oracle, reuse):
-    """One kernel walking the tree once for the pixel's two primary rays (default) == G-buffer kernel + phase-A kernel,
-    at 1080p on the 200k-triangle scene (every buffer, bit for bit), and both == the oracle on a small case."""
+    """The staged pipeline (default: k_primary / k_candidates / k_shadow / k_temporal) == one fused kernel walking the
+    tree once for the tile's primary rays == G-buffer kernel + phase-A kernel, at 1080p on the 200k-triangle scene (every
+    buffer, bit for bit), and all three == the oracle on small cases (one with metallic / roughness maps)."""
     sd = scenes.procedural(1, 200000, 10000, (1920, 1080))
     sc = gpu.Scene.from_arrays(sd)
-    fused, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=30.0, light_index=True, scene=sc, fuse=True)
+    staged, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=30.0, light_index=True, scene=sc, fuse=True, staged=True)
+    fused, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=30.0, light_index=True, scene=sc, fuse=True, staged=False)
     split, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=30.0, light_index=True, scene=sc, fuse=False)
     helpers.assert_frames_equal(fused, split, "fused vs separate kernels")
+    helpers.assert_frames_equal(staged, fused, "staged pipeline vs fused kernel")
     sc.close()
     for sd in (scenes.cornell_box((160, 120), metal_tall_box=True), scenes.with_textures(scenes.procedural(3, 3000, 200, (160, 90)), env=False)):
         want = helpers.run_oracle(port_oracle, sd, 3, reuse, radius=12.0, light_index=True)
-        for fuse in (True, False):
-            got, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=12.0, light_index=True, fuse=fuse)
+        for fuse, staged in ((True, True), (True, False), (False, False)):
+            got, _ = helpers.run_gpu(gpu, sd, 3, reuse, radius=12.0, light_index=True, fuse=fuse, staged=staged)
             for f in range(3):
                 for n in want[f]:
                     if n in ("albedo", "radiance") and sd.textures:
