@@ -204,6 +204,7 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------------- B200 arm
 PROFILE_POSES = (0, 10, 20, 30, 40, 50)
+PIPELINES = {"auto": None, "staged": True, "fused": False}
 
 
 class _DevMem:
@@ -277,7 +278,7 @@ def measure_motion_rows(sc, base, W, H, rb):
     return rows
 
 
-def time_workload(rb, name, steps, warmup, staged=True):
+def time_workload(rb, name, steps, warmup, staged=None):
     """Device-timed ms/frame of another workload on this GPU (the `targets` block): same frame loop, CUDA events on the
     launching stream around `steps` frames."""
     desc, spec, res, reuse, radius = WORKLOADS[name]
@@ -385,7 +386,7 @@ def run_b200(args):
             fr.close()
         rows = strips.strip_rows(H, world, rank, bounds)
         fr = sc.frame(W, H, rows=rows, halo=halo)
-        fr.set_pipeline(args.pipeline == "staged")
+        fr.set_pipeline(PIPELINES[args.pipeline])
         if args.no_fusion:
             fr.set_fusion(False)
         plan = strips.exchange_plan(H, world, halo, bounds) if world > 1 else []
@@ -638,7 +639,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": C.sizeof(rb.api.RstrCamera) + C.sizeof(rb.RstrParams), "d2h_bytes_per_step": P * 4},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": ("k_primary + k_candidates + k_shadow + k_temporal" if args.pipeline == "staged" else "k_gbuffer_restir_a") if fused else "k_restir_a", "spatial": "k_restir_b"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"gbuffer": "k_gbuffer", "ris": ("k_primary + k_candidates + k_shadow + k_temporal" if (args.pipeline == "staged" or (args.pipeline == "auto" and info.tracedNodes > 1024)) else "k_gbuffer_restir_a") if fused else "k_restir_a", "spatial": "k_restir_b"}[dom],
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic[0] if world == 1 else None, "traffic_source": traffic[1],
                          "algorithmic_bytes_per_pixel": bpp, "kernel_ms": stage_ms[dom],
@@ -657,7 +658,7 @@ def run_b200(args):
             line["targets"] = {}
             for name in ("config4_1080p", "config3", "config2"):
                 if name != args.workload:
-                    line["targets"][name] = time_workload(rb, name, min(args.steps, 60), 5, args.pipeline == "staged")
+                    line["targets"][name] = time_workload(rb, name, min(args.steps, 60), 5, PIPELINES[args.pipeline])
             t4 = line["targets"].get("config4_1080p")
             if t4:
                 line["targets"]["north_star"] = {"config4_1080p_ms_per_frame": t4["ms_per_frame"], "target_ms": 2.0, "met": t4["ms_per_frame"] <= 2.0}
@@ -698,7 +699,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: halo rows / gather as the library's peer stores over NVLink (default) or as NCCL send/recv issued from here (A/B)")
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
     ap.add_argument("--refine", type=int, default=4, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
-    ap.add_argument("--pipeline", default="staged", choices=["staged", "fused"], help="phase A as the staged kernel pipeline (default) or as one fused kernel (A/B)")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "staged", "fused"], help="phase A as the staged kernel pipeline, as one fused kernel, or chosen by scene size (default)")
     ap.add_argument("--no-fusion", action="store_true", help="separate G-buffer and phase-A kernels instead of the fused one (A/B)")
     ap.add_argument("--split-exchange", action="store_true", help="N > 1: history reservoirs in a second exchange after phase B (A/B)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for the history-reservoir exchange at the end of the frame instead of under the next G-buffer")

@@ -293,10 +293,12 @@ int rstr_frame_set_halo_render(RstrFrame*, int renderHalo);
  * kernels; any other use of the G-buffer in between (reads, plane pointers, gbuffer_update, sync, PTDirect) launches the
  * plain G-buffer kernel first.  enable = 0 turns the fusion off (A/B measurements, tests). */
 int rstr_frame_set_fusion(RstrFrame*, int enable);
-/* How the fused G-buffer + phase A work is launched: staged = 1 (default) runs it as a pipeline of kernels cut where the shape of
+/* How the fused G-buffer + phase A work is launched: staged = 1 runs it as a pipeline of kernels cut where the shape of
  * the parallelism changes -- one packet walk per 8x4 tile for the primary rays, then the 32 light candidates, the shadow rays
  * (persistent warps refilled from a queue) and the temporal merge over the compacted list of shaded pixels; staged = 0 runs
- * everything in one kernel, one thread per pixel.  Identical results (A/B measurements, tests). */
+ * everything in one kernel, one thread per pixel; staged = -1 (default) picks the pipeline unless the scene is tiny (a
+ * traced tree of at most 1024 nodes, e.g. a Cornell box, where no ray diverges and the extra launches cost more than
+ * they save).  Identical results in every mode (A/B measurements, tests). */
 int rstr_frame_set_pipeline(RstrFrame*, int staged);
 /* Cost profile for placing the strip cuts.  enable != 0 starts (or restarts from zero) the
  * accumulation: the G-buffer and phase-A kernels add the SM cycles every block (16x8 pixels) held its SM slot to one

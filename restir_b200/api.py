@@ -369,9 +369,9 @@ class Frame:
         """G-buffer + phase A as one kernel sharing the primary-ray tree walk (default on)."""
         _check(lib().rstr_frame_set_fusion(self.f, 1 if on else 0))
 
-    def set_pipeline(self, staged: bool) -> None:
-        """Phase A as the staged kernel pipeline (default) or as one fused kernel."""
-        _check(lib().rstr_frame_set_pipeline(self.f, 1 if staged else 0))
+    def set_pipeline(self, staged) -> None:
+        """Phase A as the staged kernel pipeline (True), as one fused kernel (False), or chosen by scene size (None, default)."""
+        _check(lib().rstr_frame_set_pipeline(self.f, -1 if staged is None else (1 if staged else 0)))
 
     def set_halo_render(self, on: bool) -> None:
         _check(lib().rstr_frame_set_halo_render(self.f, 1 if on else 0))

@@ -36,7 +36,7 @@ def nvcc_command(verbose: bool = False) -> list[str]:
         NVCC, "-std=c++17", "-O3", "-shared",
         "-ccbin", HOST_CXX,
         "-gencode", "arch=compute_100a,code=sm_100a",
-        "-lineinfo", "-fmad=false",
+        "-lineinfo", "-fmad=" + os.environ.get("RSTR_FMAD", "false"),       # RSTR_FMAD=true: the contraction experiment of scripts/ref_cuda_compare.py, never the product
         "-Xcompiler", "-fPIC,-fopenmp,-ffp-contract=off,-fno-fast-math,-O2",
         "-I", os.path.join(HERE, "..", "include"),
         "-o", LIB,

@@ -415,11 +415,12 @@ int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
     return RSTR_OK;
 }
 
-// G-buffer + phase A of a frame: 1 (default) = staged pipeline (k_primary, k_candidates, k_shadow, k_temporal), 0 = one fused kernel
+// G-buffer + phase A of a frame: 1 = staged pipeline (k_primary, k_candidates, k_shadow, k_temporal), 0 = one fused kernel,
+// -1 (default) = staged unless the scene is tiny
 int rstr_frame_set_pipeline(RstrFrame* f, int staged) {
     if (!f) return fail(RSTR_ERR_ARG, "null frame");
     int rc = rsFlushGBuffer(f);
-    f->staged = staged != 0;
+    f->staged = staged < 0 ? -1 : (staged != 0);
     return rc;
 }
 
@@ -443,10 +444,20 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     if (rc) return rc;
     if (!prm || prm->numCandidates < 0 || prm->numSpatial < 0 || prm->temporalCap < 1) return fail(RSTR_ERR_ARG, "bad RstrParams");
     FrameDev d = rsToFrameDev(f, f->row0, f->row1);
+    d.resvStage = f->resvTemp;
     if (f->gbufPending && memcmp(cam, &f->pendCam, sizeof(RstrCamera)) == 0 && f->sc->dev.traversal == RS_TRAVERSAL_FAST) {
         stageBegin(f, RSTR_T_RIS);
-        int n = f->staged ? launchPhaseAStaged(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, smCount(), f->stream)
-                          : launchGBufferRestirA(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, f->stream);
+        // auto: the staged pipeline pays for its extra launches and plane traffic once rays diverge, i.e. on real scenes; a
+        // Cornell box (a few dozen triangles, every lane in step) is 9 % faster in the single fused kernel
+        const bool staged = f->staged < 0 ? f->sc->hs.fastNodes.size() > 1024 : f->staged != 0;
+        if (staged) {
+            // the reservoir between k_candidates and k_temporal: resvTemp gets its final value from k_temporal when spatial reuse is
+            // on; with spatial reuse off the reference leaves reservoirTemp alone (restir.cu:190), so the free second buffer is used
+            d.resvStage = (prm->reuse & 2) ? f->resvTemp : f->resvTemp2;
+            if (!(prm->reuse & 2)) f->temp2Ready = false;
+        }
+        int n = staged ? launchPhaseAStaged(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, smCount(), f->stream)
+                       : launchGBufferRestirA(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, f->stream);
         if (n > 0) {
             f->gbufPending = false;
             g_launches += n;

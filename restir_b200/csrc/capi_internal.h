@@ -65,7 +65,7 @@ struct RstrFrame {
     unsigned long long* rowCost = nullptr;    // allocated by rstr_frame_row_cost
     int* queue = nullptr;
     int* shadeQueue = nullptr;     // staged phase A: compact list of shaded pixels
-    bool staged = true;            // phase A as the staged pipeline (kernels.cu) instead of the single fused kernel
+    int staged = -1;               // phase A as the staged pipeline (kernels.cu): 1, as the single fused kernel: 0, by scene size: -1
     unsigned int* queueCount = nullptr;
     void* scratch = nullptr; size_t scratchBytes = 0;
     int cur = 0;        // GBuffer::frameIdx

@@ -88,6 +88,7 @@ struct FrameDev {
     ResvD* resvOut;            // history written this frame
     const ResvD* resvIn;       // history of the previous frame
     ResvD* resvTemp;
+    ResvD* resvStage;          // staged phase A: the reservoir between k_candidates and k_temporal (resvTemp, or resvTemp2 when spatial reuse is off)
     HitRec* hit;
     float2* hitMR;             // {metallic, roughness} of the shaded point; only allocated for scenes with such maps
     int* queue;                // pixels deferred to the reference-order fix-up kernel

@@ -331,7 +331,10 @@ RS_D bool slabHit(const RayF& f, float lx, float ly, float lz, float hx, float h
 // CONSERVATIVE walk of any tree that offers every triangle near the ray to this criterion therefore finds the
 // reference's hit; the walk keeps the best hit plus the hits inside a band behind it and replays the reference's visits of
 // those in its order.  More than RS_MAX_TIES such hits leave the pixel undecided (fix-up kernel, reference-order walk).
-#define RS_TIE_BAND 1e-4f     /* relative width of the near-tie band (>= 4 x the error bound of the best hit) */
+// Two hits are "near" when their distances differ by no more than the sum of their Moller-Trumbore error bounds
+// (triDistError) plus one ulp-scale term; RS_TIE_BAND only widens the traversal limit so that such hits BEHIND the best
+// one are still visited.
+#define RS_TIE_BAND 1e-4f
 #define RS_MAX_TIES 3
 #define RS_DONE 0x7fffffff
 #define RS_WSTACK RS_PACKET_STACK
@@ -340,11 +343,14 @@ RS_D bool leafBox(const RayT& r, const Tri& t, float& tBox) {
     return boxHit(r, gmin(gmin(t.v0, t.v1), t.v2), gmax(gmax(t.v0, t.v1), t.v2), tBox);
 }
 
-// near-tie candidates of one ray: RS_MAX_TIES {triangle, distance} pairs per thread in shared memory, [entry][thread]
+// near-tie candidates of one ray: RS_MAX_TIES {triangle, distance, error bound} records per thread in shared memory, [entry][thread]
 struct TieStore {
-    int* fi;
-    float* d;
+    float* base;       // this thread's column of [field: triangle, distance, error][entry][thread]; one pointer, 2 registers
+    RS_D int& fi(int k) const { return *(int*)(base + k * RS_BLOCK); }
+    RS_D float& d(int k) const { return base[(RS_MAX_TIES + k) * RS_BLOCK]; }
+    RS_D float& e(int k) const { return base[(2 * RS_MAX_TIES + k) * RS_BLOCK]; }
 };
+RS_D bool nearTie(float da, float ea, float db, float eb) { return fabsf(da - db) <= ea + eb + 1e-6f * fmaxf(da, db); }
 
 // Running result of one closest-hit ray: 16 registers.  The slab test uses cinv / oi (explicit FMAs on the padded boxes
 // of the traced tree); everything that decides which triangle is reported (triHit, leafBox) uses o / d with the
@@ -353,8 +359,8 @@ struct PRay {
     f3 o, d;
     f3 cinv, oi;      // 1 / d with |d| kept >= 1e-20 (a zero component would give inf * 0 = NaN), -o / d
     float bestD;      // distance of the best hit so far (FLT_MAX: none)
-    float band;       // absolute width of the near-tie band behind bestD: max(RS_TIE_BAND * bestD, 4 * errorBound(best))
-    float limit;      // bestD + 2 * band: nothing beyond matters.  < 0: no ray (lane outside the image)
+    float bestErr;    // its error bound (triDistError)
+    float limit;      // bestD widened by 2 * (RS_TIE_BAND * bestD + bestErr): nothing beyond matters.  < 0: no ray (lane outside the image)
     int bestFi;       // leaf-order index of the best hit's triangle, -1: none
     int nt;           // near-tie candidates in the TieStore; -1: more than RS_MAX_TIES (undecided)
 };
@@ -367,7 +373,7 @@ RS_D PRay prayBegin(f3 o, f3 d, bool active) {
     float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
     p.cinv = mk3(1.f / dx, 1.f / dy, 1.f / dz);
     p.oi = mk3(-o.x * p.cinv.x, -o.y * p.cinv.y, -o.z * p.cinv.z);
-    p.bestD = FLT_MAX; p.band = 0.f; p.limit = active ? FLT_MAX : -1.f;
+    p.bestD = FLT_MAX; p.bestErr = 0.f; p.limit = active ? FLT_MAX : -1.f;
     p.bestFi = -1; p.nt = 0;
     return p;
 }
@@ -389,7 +395,7 @@ RS_D bool triHitOD(f3 o, f3 d, f3 v0, f3 v1, f3 v2, float& bx, float& by, float&
 }
 
 // the part of a ray's running result that a newly accepted hit changes
-struct BestState { float bestD, band, limit; int bestFi, nt; };
+struct BestState { float bestD, bestErr, limit; int bestFi, nt; };
 
 // a triangle that is hit within the ray's limit (rare: a few times per ray): leaf-box criterion, then best / near-tie
 // update.  Everything by value: a reference to the caller's PRay would pin it in local memory for the whole walk.
@@ -399,26 +405,26 @@ __device__ __noinline__ BestState prayAccept(f3 o, f3 dir, BestState p, const Ti
     t.v0 = v0; t.v1 = v1; t.v2 = v2;
     float tBox;
     if (!leafBox(rt, t, tBox)) return p;                             // the reference never sees this triangle
+    const float err = triDistError(rt, v0, v1, v2);
     if (d < p.bestD) {
-        const float band = fmaxf(RS_TIE_BAND * d, 4.f * triDistError(rt, v0, v1, v2));
-        const bool oldNear = p.bestFi >= 0 && p.bestD - d <= band;   // the old best stays a candidate
+        // the stored candidates and the old best stay candidates when they are near the NEW best
         int n = 0;
-        bool over = false;
+        const bool oldNear = p.bestFi >= 0 && nearTie(d, err, p.bestD, p.bestErr);
+        bool over = p.nt < 0 && oldNear;                             // candidates lost earlier lie behind the old best
+        const int m = p.nt < 0 ? RS_MAX_TIES : p.nt;
+        for (int k = 0; k < m; k++) {
+            const float dk = ts.d(k), ek = ts.e(k);
+            if (nearTie(d, err, dk, ek)) { ts.d(n) = dk; ts.e(n) = ek; ts.fi(n) = ts.fi(k); n++; }
+        }
         if (oldNear) {
-            // the stored candidates lie behind the old best: keep those still inside the new band, then add the old best
-            over = p.nt < 0;
-            const int m = p.nt < 0 ? RS_MAX_TIES : p.nt;
-            for (int k = 0; k < m; k++) {
-                float dk = ts.d[k * RS_BLOCK];
-                if (dk - d <= band) { ts.d[n * RS_BLOCK] = dk; ts.fi[n * RS_BLOCK] = ts.fi[k * RS_BLOCK]; n++; }
-            }
-            if (n < RS_MAX_TIES) { ts.d[n * RS_BLOCK] = p.bestD; ts.fi[n * RS_BLOCK] = p.bestFi; n++; }
+            if (n < RS_MAX_TIES) { ts.d(n) = p.bestD; ts.e(n) = p.bestErr; ts.fi(n) = p.bestFi; n++; }
             else over = true;
-        }                                                            // else: everything recorded so far is behind the new band
+        }
         p.nt = over ? -1 : n;
-        p.bestD = d; p.bestFi = fi; p.band = band; p.limit = d + 2.f * band;
-    } else if (d - p.bestD <= p.band) {
-        if (p.nt >= 0 && p.nt < RS_MAX_TIES) { ts.d[p.nt * RS_BLOCK] = d; ts.fi[p.nt * RS_BLOCK] = fi; p.nt++; }
+        p.bestD = d; p.bestErr = err; p.bestFi = fi;
+        p.limit = d + 2.f * (RS_TIE_BAND * d + err);
+    } else if (nearTie(d, err, p.bestD, p.bestErr)) {
+        if (p.nt >= 0 && p.nt < RS_MAX_TIES) { ts.d(p.nt) = d; ts.e(p.nt) = err; ts.fi(p.nt) = fi; p.nt++; }
         else p.nt = -1;
     }
     return p;
@@ -430,27 +436,25 @@ RS_D void prayOffer(PRay& p, const TieStore& ts, const Tri& t, int fi) {
     if (!triHitOD(p.o, p.d, t.v0, t.v1, t.v2, bx, by, d)) return;
     if (!(d <= p.limit)) return;
     BestState b;
-    b.bestD = p.bestD; b.band = p.band; b.limit = p.limit; b.bestFi = p.bestFi; b.nt = p.nt;
+    b.bestD = p.bestD; b.bestErr = p.bestErr; b.limit = p.limit; b.bestFi = p.bestFi; b.nt = p.nt;
     b = prayAccept(p.o, p.d, b, ts, t.v0, t.v1, t.v2, fi, d);
-    p.bestD = b.bestD; p.band = b.band; p.limit = b.limit; p.bestFi = b.bestFi; p.nt = b.nt;
+    p.bestD = b.bestD; p.bestErr = b.bestErr; p.limit = b.limit; p.bestFi = b.bestFi; p.nt = b.nt;
 }
 
-// the reference's visits of the best hit and its near ties, in its order for this ray; prim == -2: undecided
-__device__ __noinline__ Hit prayReplay(const DevScene& s, f3 o, f3 dir, int bestFi, int nt, float band, const TieStore ts) {
+// the reference's visits of the best hit and its near ties, in its order for this ray
+__device__ __noinline__ Hit prayReplay(const DevScene& s, f3 o, f3 dir, int bestFi, int nt, const TieStore ts) {
     const RayT rt = makeRayT(o, dir);
     const int* rank = s.rank + (size_t)(2 * rt.dim + rt.lesser) * s.numTris;
     float cd[RS_MAX_TIES + 1], cbx[RS_MAX_TIES + 1], cby[RS_MAX_TIES + 1], ctb[RS_MAX_TIES + 1];
     int cprim[RS_MAX_TIES + 1], crk[RS_MAX_TIES + 1];
     Hit h;
-    h.t = FLT_MAX; h.prim = -2; h.bx = 0.f; h.by = 0.f;
+    h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
     const int n = nt + 1;
     for (int k = 0; k < n; k++) {
-        const int fi = k == 0 ? bestFi : ts.fi[(k - 1) * RS_BLOCK];
+        const int fi = k == 0 ? bestFi : ts.fi(k - 1);
         Tri t = loadTriFast(s, fi);
         triHit(rt, t.v0, t.v1, t.v2, cbx[k], cby[k], cd[k]);
         leafBox(rt, t, ctb[k]);
-        // a candidate whose own error bound exceeds the band could be pruned by hits that were not recorded
-        if (k > 0 && 4.f * triDistError(rt, t.v0, t.v1, t.v2) > band) return h;
         cprim[k] = t.prim;
         crk[k] = __ldg(rank + t.prim);
     }
@@ -474,8 +478,8 @@ RS_D bool prayResolve(const DevScene& s, const PRay& p, const TieStore& ts, Hit&
     if (p.bestFi < 0) return true;
     if (p.nt < 0) return false;
     if (p.nt > 0) {
-        h = prayReplay(s, p.o, p.d, p.bestFi, p.nt, p.band, ts);
-        return h.prim != -2;
+        h = prayReplay(s, p.o, p.d, p.bestFi, p.nt, ts);
+        return true;
     }
     Tri t = loadTriFast(s, p.bestFi);
     triHitOD(p.o, p.d, t.v0, t.v1, t.v2, h.bx, h.by, h.t);          // same arithmetic as during the walk: h.t == bestD
@@ -548,12 +552,11 @@ RS_D void packetWalk(const DevScene& s, PRay& a, PRay& b, const TieStore& ta, co
 
 // shared memory of the packet walk for a block of RS_BLOCK threads: near-tie stores of NR rays per thread + one stack per warp
 #define RS_DECLARE_PACKET(name, NR)                                                 \
-    __shared__ int name##_tfi[NR][RS_MAX_TIES][RS_BLOCK];                           \
-    __shared__ float name##_td[NR][RS_MAX_TIES][RS_BLOCK];                          \
+    __shared__ float name##_ties[NR][3 * RS_MAX_TIES][RS_BLOCK];                    \
     __shared__ int2 name##_ws[RS_BLOCK / 32][RS_WSTACK];                            \
     TieStore name##_ta, name##_tb;                                                  \
-    name##_ta.fi = &name##_tfi[0][0][threadIdx.x]; name##_ta.d = &name##_td[0][0][threadIdx.x];                          \
-    name##_tb.fi = &name##_tfi[NR - 1][0][threadIdx.x]; name##_tb.d = &name##_td[NR - 1][0][threadIdx.x];                \
+    name##_ta.base = &name##_ties[0][0][threadIdx.x];                               \
+    name##_tb.base = &name##_ties[NR - 1][0][threadIdx.x];                          \
     int2* name##_wst = name##_ws[threadIdx.x >> 5]
 
 // any hit: order does not matter, the criterion above is exact per triangle
@@ -1216,7 +1219,8 @@ __global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant
 //                  (scripts/travsim.cpp); here a lane takes the next ray as soon as enough lanes are idle
 //   k_temporal     temporal merge + stores (restir.cu:180-192, 211-230) per queued pixel
 // Between the stages a pixel's state lives in planes that are free at that point: the {prim, barycentrics} of the
-// jittered hit in HitRec (rewritten by k_candidates), the reservoir before the shadow test in resvTemp, the shading
+// jittered hit in HitRec (rewritten by k_candidates), the reservoir before the shadow test in resvTemp (resvTemp2 when spatial
+// reuse is off: the reference leaves reservoirTemp alone then, restir.cu:190), the shading
 // point in this frame's history plane resvOut (written for good by k_temporal).  Same arithmetic, same RNG stream per
 // pixel: every buffer is bit-identical to the fused kernel's (test_staged_pipeline_equals_fused_kernel).
 #ifndef RS_MINB_PRIMARY
@@ -1230,6 +1234,9 @@ __global__ void __launch_bounds__(RS_BLOCK) k_restir_a_fix(const __grid_constant
 #endif
 #ifndef RS_REFILL_MIN
 #define RS_REFILL_MIN 8       /* k_shadow refills when at least this many lanes are idle */
+#endif
+#ifndef RS_LEAF_MIN
+#define RS_LEAF_MIN 8         /* k_shadow tests triangles when at least this many lanes wait at a leaf */
 #endif
 
 template <bool SPATIAL>
@@ -1308,7 +1315,7 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_CAND) k_candidates(const __g
     ShadePoint sp;
     shadePointOf(s, h, d, sp);
     const Resv R = candidateLoop(s, prm, sp, rng);
-    storeResv(f.resvTemp + li, R);                                                   // before the shadow test
+    storeResv(f.resvStage + li, R);                                                  // before the shadow test
     float4* sc = (float4*)(f.resvOut + li);                                          // free until k_temporal writes the history
     sc[0] = make_float4(sp.pos.x, sp.pos.y, sp.pos.z, sp.metallic);
     sc[1] = make_float4(sp.roughness, 0.f, 0.f, 0.f);
@@ -1347,7 +1354,7 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
                 const int index = f.shadeQueue[i];
                 rowY = index / f.W;
                 li = planeIndex(f, index % f.W, rowY);
-                const float4* rp = (const float4*)(f.resvTemp + li);
+                const float4* rp = (const float4*)(f.resvStage + li);
                 const float4 ra = rp[0];                                             // {wi, dist}
                 const float w = rp[1].x;
                 if (w != 0.f) {                                                      // restir.cu:172-176: weight 0 cannot change
@@ -1370,8 +1377,12 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
                 }
             }
         }
-        if (cur != RS_DONE) {
-            if (cur >= 0) {
+        // Lanes at an internal node step; lanes that have reached a leaf WAIT until RS_LEAF_MIN of them are there (or nobody is
+        // left to step): run lane by lane, the triangle tests -- half of this kernel's instructions -- executed with 1.5 of 32 lanes.
+        const unsigned atLeaf = __ballot_sync(FULL, cur < 0);
+        const unsigned atNode = __ballot_sync(FULL, cur >= 0 && cur != RS_DONE);
+        if (atNode && __popc(atLeaf) < RS_LEAF_MIN) {
+            if (cur >= 0 && cur != RS_DONE) {
                 const float4* np = s.fastNodes + 4 * (size_t)cur;
                 const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
                 const int2 l = __ldg((const int2*)(np + 3));
@@ -1382,17 +1393,18 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
                 else if (hL) cur = l.x;
                 else if (hR) cur = l.y;
                 else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
-            } else {
-                const int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
-                bool occluded = false;
-                for (int i = 0; i < count && !occluded; i++) {
-                    const Tri t = loadTriFast(s, first + i);
-                    float bx, by, d, tb;
-                    occluded = triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist && leafBox(r, t, tb) && tb < dist;
-                }
-                if (occluded) { f.resvTemp[li].weight = 0.f; cur = RS_DONE; }
-                else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
+                if (f.rowCost && cur == RS_DONE) atomicAdd(f.rowCost + (rowY >> 3), (unsigned long long)((clock64() - tRay) / 24));
             }
+        } else if (cur < 0) {
+            const int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            bool occluded = false;
+            for (int i = 0; i < count && !occluded; i++) {
+                const Tri t = loadTriFast(s, first + i);
+                float bx, by, d, tb;
+                occluded = triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist && leafBox(r, t, tb) && tb < dist;
+            }
+            if (occluded) { f.resvStage[li].weight = 0.f; cur = RS_DONE; }
+            else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
             if (f.rowCost && cur == RS_DONE) atomicAdd(f.rowCost + (rowY >> 3), (unsigned long long)((clock64() - tRay) / 24));
         }
     }
@@ -1414,7 +1426,7 @@ __global__ void __launch_bounds__(RS_BLOCK) k_temporal(const __grid_constant__ D
     const int matId = __float_as_int(h0.w);
     Rng rng;
     rng.x = __float_as_uint(h1.w);
-    const Resv R = loadResv(f.resvTemp + li);
+    const Resv R = loadResv(f.resvStage + li);
     temporalAndStore<SPATIAL>(s, f, prm, iter, first, li, index, mk3(h0.x, h0.y, h0.z), mk3(h1.x, h1.y, h1.z), matId,
                               __ldg(&s.materials[matId].type), metallic, roughness, R, rng);
     if (f.rowCost) accountPixel(f, y, t0);

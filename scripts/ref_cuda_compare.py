@@ -30,34 +30,50 @@ def run_ref(binary, scene_txt, frames, warmup, reuse, dump=None, dump_frame=-1):
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
-def main():
-    work = sys.argv[1] if len(sys.argv) > 1 else "config2"
-    frames = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+def have_reference_cuda() -> bool:
+    return all(os.path.exists(os.path.join(REF, b)) for b in ("ref_headless_r5", "ref_headless_r30"))
+
+
+def reference_cuda_times(txt, frames, reuse, radius, warmup=5):
+    """ms/frame of the reference's own CUDA kernels (GBuffer::render + ReSTIRDirect, CUDA events) on a scene file: as shipped
+    (device-wide sync after every launch, cudaUtil.h:13-16) and, when that build exists, with ERRORCHECK 0 (cudaUtil.h:8)."""
+    out = {}
+    binary = "ref_headless_r30" if radius == 30.0 else "ref_headless_r5"
+    out["as_shipped_ms_per_frame"] = run_ref(binary, txt, frames, warmup, reuse)["ms_per_frame"]
+    if radius == 30.0 and os.path.exists(os.path.join(REF, "ref_headless_r30_nosync")):
+        out["errorcheck0_ms_per_frame"] = run_ref("ref_headless_r30_nosync", txt, frames, warmup, reuse)["ms_per_frame"]
+    return out
+
+
+def compare(work="config2", frames=60, lib_times=True):
     desc, spec, res, reuse, radius = WORKLOADS[work]
     sd = make_scene(spec, res)
     tmp = tempfile.mkdtemp()
     txt = scenes.write_scene_files(sd, tmp, "scene")
     out = {"workload": work, "description": desc}
     # ---- timing: reference CUDA build vs this library, same scene file, same orbit
-    t = run_ref("ref_headless_r30" if radius == 30.0 else "ref_headless_r5", txt, frames, 5, reuse)
-    out["reference_cuda_ms_per_frame"] = t["ms_per_frame"]
+    out["reference_cuda"] = reference_cuda_times(txt, frames, reuse, radius)
+    out["reference_cuda_ms_per_frame"] = out["reference_cuda"]["as_shipped_ms_per_frame"]
     rb.init(0)
     sc = rb.Scene.from_file(txt)
-    fr = sc.frame(*res)
     base = sc.camera
-    prm = rb.default_params(reuse=reuse, radius=radius)
-    for k in range(5):
-        cam = base.orbit(k); fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0); fr.gbuffer_update(cam)
-    fr.sync(); fr.mark(0)
-    for k in range(5, 5 + frames):
-        cam = base.orbit(k); fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0); fr.gbuffer_update(cam)
-    fr.mark(1); fr.sync()
-    out["restir_b200_ms_per_frame"] = fr.elapsed_ms(0, 1) / frames
-    out["speedup_vs_reference_cuda"] = out["reference_cuda_ms_per_frame"] / out["restir_b200_ms_per_frame"]
-    fr.close()
-    # ---- parity: temporal mode (deterministic in the reference), literal radius, frame 3 of the orbit
     W, H = res
     P = W * H
+    if lib_times:
+        fr = sc.frame(*res)
+        prm = rb.default_params(reuse=reuse, radius=radius)
+        for k in range(5):
+            cam = base.orbit(k); fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0); fr.gbuffer_update(cam)
+        fr.sync(); fr.mark(0)
+        for k in range(5, 5 + frames):
+            cam = base.orbit(k); fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0); fr.gbuffer_update(cam)
+        fr.mark(1); fr.sync()
+        out["restir_b200_ms_per_frame"] = fr.elapsed_ms(0, 1) / frames
+        out["speedup_vs_reference_cuda"] = out["reference_cuda_ms_per_frame"] / out["restir_b200_ms_per_frame"]
+        if "errorcheck0_ms_per_frame" in out["reference_cuda"]:
+            out["speedup_vs_reference_cuda_errorcheck0"] = out["reference_cuda"]["errorcheck0_ms_per_frame"] / out["restir_b200_ms_per_frame"]
+        fr.close()
+    # ---- parity: temporal mode (deterministic in the reference), literal radius, frame 3 of the orbit
     pre = os.path.join(tmp, "ref_")
     run_ref("ref_headless_r5", txt, 4, 0, 1, pre, 3)
     fr = sc.frame(W, H)
@@ -73,15 +89,25 @@ def main():
     par["matid_mismatch_pixels"] = int((ref["matid"] != mine["matid"]).sum())
     par["motion_mismatch_pixels"] = int((ref["motion"] != mine["motion"]).sum())
     d = np.abs(ref["depth"] - mine["depth"]) / np.maximum(np.abs(ref["depth"]), 1e-20)
+    same_surface = ref["matid"] == mine["matid"]
     par["depth_max_rel"] = float(d.max()); par["depth_bitexact_fraction"] = float((ref["depth"] == mine["depth"]).mean())
+    par["depth_max_rel_where_same_material"] = float(d[same_surface].max())
     a, b = mine["radiance"].astype(np.float64), ref["radiance"].astype(np.float64)
     rel = np.abs(a - b).sum(1) / np.maximum(np.abs(b).sum(1), 1e-6)
     par["radiance_pixels_within_1e-4_rel"] = float((rel <= 1e-4).mean())
     par["radiance_pixels_bitexact"] = float((mine["radiance"] == ref["radiance"]).all(1).mean())
     par["radiance_mean_relMSE"] = float(np.mean(((a - b) ** 2).sum(1) / (b.sum(1) ** 2 + 1e-3)))
     par["mean_radiance_ref"] = float(b.mean()); par["mean_radiance_b200"] = float(a.mean())
+    par["library_fmad"] = os.environ.get("RSTR_LIBNAME", "librestir_b200.so")
     out["parity_vs_reference_cuda_temporal_frame3"] = par
-    print(json.dumps(out))
+    fr.close(); sc.close()
+    return out
+
+
+def main():
+    work = sys.argv[1] if len(sys.argv) > 1 else "config2"
+    frames = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+    print(json.dumps(compare(work, frames)))
 
 
 if __name__ == "__main__":

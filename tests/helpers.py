@@ -68,7 +68,7 @@ def run_oracle(orc, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, a
 
 
 def run_gpu(rb, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=ALL_BUFS, light_index=False,
-            rows=None, halo=0, scene=None, exact=False, passes=1, fuse=True, staged=True):
+            rows=None, halo=0, scene=None, exact=False, passes=1, fuse=True, staged=True):   # staged=None: the library's choice by scene size
     W, H = sd.resolution
     sc = scene or rb.Scene.from_arrays(sd)
     sc.set_traversal(exact)
