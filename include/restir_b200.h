@@ -326,6 +326,13 @@ int rstr_strip_group_frame(RstrStripGroup*, const RstrCamera*, const RstrParams*
 /* the building block of the above: push this rank's edge rows of the planes in planeMask (bit i = RSTR_PLANE_i) into the
  * neighbours' halo rows, then make the frame's stream wait for the neighbours' rows of the same exchange */
 int rstr_strip_group_exchange(RstrStripGroup*, unsigned int planeMask);
+/* the two halves of _exchange and of _frame.  Only needed when several ranks share ONE process (tests): all ranks' pushes must
+ * be issued before any rank's wait, because the streams of one process share hardware work queues. */
+int rstr_strip_group_push(RstrStripGroup*, unsigned int planeMask);
+int rstr_strip_group_wait(RstrStripGroup*);
+int rstr_strip_group_ack(RstrStripGroup*);     /* behind the kernels that read the halo rows: the neighbours may overwrite them */
+int rstr_strip_group_frame_begin(RstrStripGroup*, const RstrCamera*, const RstrParams*, int looper, int iter);   /* G-buffer, phase A, push */
+int rstr_strip_group_frame_end(RstrStripGroup*, const RstrCamera*, const RstrParams*, int looper, int iter);     /* wait, phase B (one pass), gbuffer_update */
 /* copyImageToPBO for strips: tone-map into slot (0 .. RSTR_LDR_SLOTS-1) of rank 0's full frame; on rank 0 the assembled
  * W x H x uchar4 frame is copied to hostLdr (may be NULL) on a copy stream; rstr_strip_group_wait_host(slot) blocks until it is there */
 int rstr_strip_group_present(RstrStripGroup*, int toneMapping, void* hostLdr, size_t bytes, int slot);

@@ -182,6 +182,11 @@ def lib() -> C.CDLL:
     L.rstr_strip_group_connect.argtypes = [vp, vp]
     L.rstr_strip_group_frame.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
     L.rstr_strip_group_exchange.argtypes = [vp, C.c_uint]
+    L.rstr_strip_group_push.argtypes = [vp, C.c_uint]
+    L.rstr_strip_group_wait.argtypes = [vp]
+    L.rstr_strip_group_ack.argtypes = [vp]
+    L.rstr_strip_group_frame_begin.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
+    L.rstr_strip_group_frame_end.argtypes = [vp, C.POINTER(RstrCamera), C.POINTER(RstrParams), ip, ip]
     L.rstr_strip_group_present.argtypes = [vp, ip, vp, C.c_size_t, ip]
     L.rstr_strip_group_wait_host.argtypes = [vp, ip]
     L.rstr_strip_group_error.argtypes = [vp, C.POINTER(ip)]
@@ -500,11 +505,30 @@ class StripGroup:
     def render(self, cam, params, looper: int, it: int = 0) -> None:
         _check(lib().rstr_strip_group_frame(self.g, C.byref(cam), C.byref(params), looper, it))
 
-    def exchange(self, planes) -> None:
+    def render_begin(self, cam, params, looper: int, it: int = 0) -> None:
+        _check(lib().rstr_strip_group_frame_begin(self.g, C.byref(cam), C.byref(params), looper, it))
+
+    def render_end(self, cam, params, looper: int, it: int = 0) -> None:
+        _check(lib().rstr_strip_group_frame_end(self.g, C.byref(cam), C.byref(params), looper, it))
+
+    @staticmethod
+    def _mask(planes) -> int:
         mask = 0
         for p in planes:
             mask |= 1 << PLANES[p]
-        _check(lib().rstr_strip_group_exchange(self.g, mask))
+        return mask
+
+    def exchange(self, planes) -> None:
+        _check(lib().rstr_strip_group_exchange(self.g, self._mask(planes)))
+
+    def push(self, planes) -> None:
+        _check(lib().rstr_strip_group_push(self.g, self._mask(planes)))
+
+    def wait(self) -> None:
+        _check(lib().rstr_strip_group_wait(self.g))
+
+    def ack(self) -> None:
+        _check(lib().rstr_strip_group_ack(self.g))
 
     def present(self, tonemap: int, out, slot: int) -> None:
         ptr, nbytes = (None, 0) if out is None else (out.ctypes.data, out.nbytes)

@@ -65,6 +65,7 @@ struct RstrStripGroup {
     uchar4* ldrFull = nullptr;       // rank 0: RSTR_LDR_SLOTS x W x H
     unsigned seq = 0;                // halo exchanges issued so far
     unsigned acked = 0;              // last exchange this rank has acknowledged to its neighbours
+    unsigned pushed = 0, waited = 0; // last exchange pushed / waited for
     unsigned ldrSeq = 0;             // frames presented so far
     cudaStream_t copyStream = nullptr;
     cudaEvent_t evTone[RSTR_LDR_SLOTS] = {}, evCopied[RSTR_LDR_SLOTS] = {};
@@ -291,10 +292,19 @@ static int ackNeighbours(RstrStripGroup* g) {
     return RSTR_OK;
 }
 
-// One halo exchange: this rank's edge rows of the selected planes (bit i = RSTR_PLANE_i) go into the neighbours' halo
-// rows, and the frame's stream then waits until the neighbours' rows of the same exchange have arrived here.
-int rstr_strip_group_exchange(RstrStripGroup* g, unsigned int planeMask) {
-    if (!g || !g->connected) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_exchange: group not connected");
+// Tell the neighbours that everything queued so far on this rank's stream has finished with the halo rows they pushed
+// (issued behind the kernels that read them; rstr_strip_group_push issues it itself if the caller did not).
+int rstr_strip_group_ack(RstrStripGroup* g) {
+    if (!g) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_ack: null group");
+    if (g->world == 1 || !g->connected) return RSTR_OK;
+    return ackNeighbours(g);
+}
+
+// First half of a halo exchange: this rank's edge rows of the selected planes (bit i = RSTR_PLANE_i) go into the
+// neighbours' halo rows and the arrival flags are released behind them.
+int rstr_strip_group_push(RstrStripGroup* g, unsigned int planeMask) {
+    if (!g || !g->connected) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_push: group not connected");
+    if (g->pushed != g->waited) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_push: the previous exchange has not been waited for");
     RstrFrame* f = g->f;
     int rc = rsFlushGBuffer(f);
     if (rc) return rc;
@@ -302,6 +312,7 @@ int rstr_strip_group_exchange(RstrStripGroup* g, unsigned int planeMask) {
     if ((planeMask & (1u << RSTR_PLANE_RESV_TEMP2)) && (rc = rsEnsureTemp2(f))) return rc;
     if ((rc = ackNeighbours(g))) return rc;          // the previous exchange's rows have been read by everything queued before this call
     const unsigned seq = ++g->seq;
+    g->pushed = seq;
     PushArgs a{};
     a.seq = seq; a.ackSeq = seq - 1; a.local = (unsigned int*)f->slab;
     a.ack[0] = a.local + RS_FL_ACK_UP; a.ack[1] = a.local + RS_FL_ACK_DOWN;
@@ -330,38 +341,85 @@ int rstr_strip_group_exchange(RstrStripGroup* g, unsigned int planeMask) {
     // enough blocks to fill the NVLink pipes, few enough to leave the SMs to the frame kernels of other streams
     const int blocks = (int)std::min<size_t>(128, std::max<size_t>(1, total / (256 * 16 * 4)));
     k_halo_push<<<blocks, 256, 0, f->stream>>>(a);
-    WaitArgs w{};
-    if (g->rank > 0) w.flag[w.n++] = a.local + RS_FL_ARRIVED_UP;
-    if (g->rank + 1 < g->world) w.flag[w.n++] = a.local + RS_FL_ARRIVED_DOWN;
-    w.value = seq; w.err = a.local + RS_FL_ERROR;
-    k_flag_wait<<<1, 32, 0, f->stream>>>(w);
-    rsCountLaunches(2);
+    rsCountLaunches(1);
     CU(cudaGetLastError());
     return RSTR_OK;
+}
+
+// Second half: the frame's stream waits until the neighbours' rows of the exchange pushed last have arrived here.
+int rstr_strip_group_wait(RstrStripGroup* g) {
+    if (!g || !g->connected) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_wait: group not connected");
+    if (g->world == 1 || g->waited == g->pushed) return RSTR_OK;
+    RstrFrame* f = g->f;
+    unsigned int* local = (unsigned int*)f->slab;
+    WaitArgs w{};
+    if (g->rank > 0) w.flag[w.n++] = local + RS_FL_ARRIVED_UP;
+    if (g->rank + 1 < g->world) w.flag[w.n++] = local + RS_FL_ARRIVED_DOWN;
+    w.value = g->pushed; w.err = local + RS_FL_ERROR;
+    k_flag_wait<<<1, 32, 0, f->stream>>>(w);
+    g->waited = g->pushed;
+    rsCountLaunches(1);
+    CU(cudaGetLastError());
+    return RSTR_OK;
+}
+
+// One halo exchange = push + wait.  (Ranks that share ONE process, as in the tests, must issue every rank's push before any
+// rank's wait -- rstr_strip_group_push / _wait -- because streams of one process share hardware work queues: a waiting
+// kernel may sit in front of the push it waits for.  One process per GPU, the deployment, has no such coupling.)
+int rstr_strip_group_exchange(RstrStripGroup* g, unsigned int planeMask) {
+    int rc = rstr_strip_group_push(g, planeMask);
+    if (rc) return rc;
+    return rstr_strip_group_wait(g);
 }
 
 // One whole frame of a strip (runCuda's sequence, main.cpp:164-183): G-buffer + phase A on the strip's own rows, ONE exchange
 // carrying every halo row anybody needs -- what this frame's spatial pass reads (current G-buffer rows, post-temporal
 // reservoirs) and the history reservoirs phase A just wrote, which the NEXT frame's temporal step reads -- then phase B;
 // with spatialPasses > 1 the plane each pass publishes is exchanged before the next pass.
-int rstr_strip_group_frame(RstrStripGroup* g, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
-    if (!g || !cam || !prm) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_frame: bad argument");
+// _frame_begin = up to and including the push; _frame_end = the wait and everything behind it.
+static unsigned frameMask(const RstrParams* prm) {
+    const bool spatial = (prm->reuse & RSTR_REUSE_SPATIAL) != 0, temporal = (prm->reuse & RSTR_REUSE_TEMPORAL) != 0;
+    unsigned mask = 0;
+    if (spatial) mask |= (1u << RSTR_PLANE_GEOM_CUR) | (1u << RSTR_PLANE_MATID_CUR) | (1u << RSTR_PLANE_RESV_TEMP);
+    if (temporal) mask |= (1u << RSTR_PLANE_GEOM_CUR) | (1u << RSTR_PLANE_MATID_CUR) | (1u << RSTR_PLANE_RESV_OUT);
+    return mask;
+}
+
+int rstr_strip_group_frame_begin(RstrStripGroup* g, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
+    if (!g || !cam || !prm) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_frame_begin: bad argument");
     RstrFrame* f = g->f;
-    if (g->world > 1 && !g->connected) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_frame: group not connected");
+    if (g->world > 1 && !g->connected) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_frame_begin: group not connected");
     if (g->world > 1) f->renderHalo = false;        // halo rows of the G-buffer come from the neighbours
     int rc = rstr_gbuffer_render(f, cam);
     if (rc) return rc;
     if ((rc = rstr_restir_phase_a(f, cam, prm, looper, iter))) return rc;
-    const bool spatial = (prm->reuse & RSTR_REUSE_SPATIAL) != 0, temporal = (prm->reuse & RSTR_REUSE_TEMPORAL) != 0;
-    const int passes = spatial ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
-    if (g->world > 1) {
-        unsigned mask = 0;
-        if (spatial) mask |= (1u << RSTR_PLANE_GEOM_CUR) | (1u << RSTR_PLANE_MATID_CUR) | (1u << RSTR_PLANE_RESV_TEMP);
-        if (temporal) mask |= (1u << RSTR_PLANE_GEOM_CUR) | (1u << RSTR_PLANE_MATID_CUR) | (1u << RSTR_PLANE_RESV_OUT);
-        if (mask && (rc = rstr_strip_group_exchange(g, mask))) return rc;
-    }
+    if (g->world > 1 && frameMask(prm) && (rc = rstr_strip_group_push(g, frameMask(prm)))) return rc;
+    return RSTR_OK;
+}
+
+int rstr_strip_group_frame_end(RstrStripGroup* g, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
+    if (!g || !cam || !prm) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_frame_end: bad argument");
+    RstrFrame* f = g->f;
+    int rc = rstr_strip_group_wait(g);
+    if (rc) return rc;
+    const int passes = (prm->reuse & RSTR_REUSE_SPATIAL) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
+    if (passes > 1 && g->world > 1)
+        return rsFail(RSTR_ERR_ARG, "rstr_strip_group_frame_end: with spatialPasses > 1 use rstr_strip_group_frame, or rstr_restir_phase_b_pass + rstr_strip_group_push / _wait per pass");
+    for (int pass = 1; pass <= (passes ? passes : 1); pass++)
+        if ((rc = rstr_restir_phase_b_pass(f, cam, prm, looper, iter, pass))) return rc;
+    if ((rc = rstr_strip_group_ack(g))) return rc;
+    return rstr_gbuffer_update(f, cam);
+}
+
+int rstr_strip_group_frame(RstrStripGroup* g, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
+    int rc = rstr_strip_group_frame_begin(g, cam, prm, looper, iter);
+    if (rc) return rc;
+    RstrFrame* f = g->f;
+    if ((rc = rstr_strip_group_wait(g))) return rc;
+    const int passes = (prm->reuse & RSTR_REUSE_SPATIAL) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
     for (int pass = 1; pass <= (passes ? passes : 1); pass++) {
         if ((rc = rstr_restir_phase_b_pass(f, cam, prm, looper, iter, pass))) return rc;
+        if ((rc = rstr_strip_group_ack(g))) return rc;
         if (g->world > 1 && pass < passes && (rc = rstr_strip_group_exchange(g, 1u << ((pass & 1) ? RSTR_PLANE_RESV_TEMP2 : RSTR_PLANE_RESV_TEMP)))) return rc;
     }
     return rstr_gbuffer_update(f, cam);

@@ -107,7 +107,7 @@ def compare(work="config2", frames=60, lib_times=True):
 def main():
     work = sys.argv[1] if len(sys.argv) > 1 else "config2"
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 60
-    print(json.dumps(compare(work, frames)))
+    print(json.dumps(compare(work, frames, lib_times="parity-only" not in sys.argv)))
 
 
 if __name__ == "__main__":

@@ -343,9 +343,30 @@ def test_strip_group_peer_exchange_equals_full_frame(gpu, passes):
     for k in range(4):
         cam = base.orbit(k)
         full.gbuffer_render(cam); full.restir_direct(cam, prm, k); full.gbuffer_update(cam)
-        for g in groups:
-            g.render(cam, prm, k, 0)
-        for g in groups:
+        # ranks sharing one process: every push is issued before any wait (streams of a process share hardware work queues;
+        # with one process per GPU a rank simply calls g.render())
+        if passes == 1:
+            for g in groups:
+                g.render_begin(cam, prm, k, 0)
+            for g in groups:
+                g.render_end(cam, prm, k, 0)
+        else:
+            for g in groups:
+                g.render_begin(cam, prm, k, 0)
+            for g in groups:
+                g.wait()
+            for p in range(1, passes + 1):
+                for g in groups:
+                    g.frame.restir_phase_b_pass(cam, prm, k, 0, p)
+                    g.ack()
+                if p < passes:
+                    for g in groups:
+                        g.push(["resv_temp2" if p & 1 else "resv_temp"])
+                    for g in groups:
+                        g.wait()
+            for g in groups:
+                g.frame.gbuffer_update(cam)
+        for g in reversed(groups):           # rank 0 last: its wait for the other strips is queued behind their stores
             g.present(gpu.TONEMAP_ACES, out if g.rank == 0 else None, k % 3)
         groups[0].wait_host(k % 3)
         for n in ("matid", "motion", "depth", "radiance", "reservoir", "light_index"):
