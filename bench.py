@@ -662,6 +662,28 @@ def run_b200(args):
             t4 = line["targets"].get("config4_1080p")
             if t4:
                 line["targets"]["north_star"] = {"config4_1080p_ms_per_frame": t4["ms_per_frame"], "target_ms": 2.0, "met": t4["ms_per_frame"] <= 2.0}
+        if world == 1 and not args.no_reference_cuda:
+            # the reference's own CUDA build on this B200 (oracle/_ref/ref_headless_*, built from /root/reference by
+            # oracle/build_ref_cuda.sh): same scene through the reference's scene-file grammar, same orbit, same settings;
+            # as shipped (device-wide sync after every launch) and with ERRORCHECK 0 (cudaUtil.h:8)
+            try:
+                from scripts import ref_cuda_compare as rcc
+
+                if rcc.have_reference_cuda():
+                    import shutil
+                    from restir_b200 import scenes as _scenes
+
+                    tmp = tempfile.mkdtemp()
+                    txt = _scenes.write_scene_files(sd, tmp, "scene")
+                    t = rcc.reference_cuda_times(txt, max(3, min(args.steps, 20)), reuse, radius, warmup=3)
+                    shutil.rmtree(tmp, ignore_errors=True)
+                    line["reference_cuda_ms"] = {"as_shipped": t.get("as_shipped_ms_per_frame"), "errorcheck0": t.get("errorcheck0_ms_per_frame"),
+                                                 "speedup_vs_as_shipped": t["as_shipped_ms_per_frame"] / ms_step,
+                                                 "note": "GBuffer::render + ReSTIRDirect of the reference's kernels compiled for sm_100a, CUDA events, same scene / orbit / settings (radius literal 30)"}
+                else:
+                    line["reference_cuda_ms"] = None
+            except Exception as e:       # a baseline, not the product: never fails the bench
+                line["reference_cuda_ms"] = {"error": str(e)[-300:]}
         if world == 1 and not args.no_cpu_baseline:
             kind = reference_kind()
             t1, threads = cpu_frames(kind, sd, reuse, radius, 1, 0)
@@ -695,6 +717,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="N = 1: skip timing the reference's own CUDA build (oracle/_ref/ref_headless_*) on the same workload")
     ap.add_argument("--no-targets", action="store_true", help="N = 1: skip the `targets` block (device-timed config4_1080p / config3 / config2)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: halo rows / gather as the library's peer stores over NVLink (default) or as NCCL send/recv issued from here (A/B)")
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
@@ -704,7 +727,10 @@ def main():
     ap.add_argument("--split-exchange", action="store_true", help="N > 1: history reservoirs in a second exchange after phase B (A/B)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for the history-reservoir exchange at the end of the frame instead of under the next G-buffer")
     ap.add_argument("--render-halo", action="store_true", help="N > 1: every strip renders its G-buffer halo rows itself instead of receiving them from its neighbours")
+    ap.add_argument("--quick", action="store_true", help="the B200 measurement only: no CPU baseline, no targets block, no reference CUDA timing (A/B runs)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_targets = args.no_reference_cuda = True
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -92,6 +92,7 @@ def compare(work="config2", frames=60, lib_times=True):
     same_surface = ref["matid"] == mine["matid"]
     par["depth_max_rel"] = float(d.max()); par["depth_bitexact_fraction"] = float((ref["depth"] == mine["depth"]).mean())
     par["depth_max_rel_where_same_material"] = float(d[same_surface].max())
+    par["depth_pixels_rel_gt_1e-5"] = int((d > 1e-5).sum())
     a, b = mine["radiance"].astype(np.float64), ref["radiance"].astype(np.float64)
     rel = np.abs(a - b).sum(1) / np.maximum(np.abs(b).sum(1), 1e-6)
     par["radiance_pixels_within_1e-4_rel"] = float((rel <= 1e-4).mean())
