@@ -75,6 +75,14 @@ typedef struct RstrParams {
     int   reuse;           /* Settings::reservoirReuse (common.h:36-43): bit0 temporal, bit1 spatial */
     int   spatialPasses;   /* 1 = as shipped (restir.cu:196-199); 2..3 add the commented-out pass restir.cu:201-209
                               (publish, barrier, new 5-neighbour aggregate, preClampedMerge<4>); values < 1 mean 1 */
+    int   unbiased;        /* 0 = the reference's reuse (a reused sample keeps the direction / distance it had at the pixel that
+                              drew it, neighbours merge with their weight sums, 1/M normalisation, visibility tested for the RIS
+                              winner only: restir.cu:172-199, restir.h:61-70 -- biased).  1 = ADDITIONAL mode the reference does not
+                              have (north star: "unbiased-MIS / visibility re-check"): reservoirs carry the light POINT and its
+                              unbiased contribution weight W; every reused sample's target function is re-evaluated at the receiving
+                              pixel; spatial merges are normalised by 1/Z, Z = sum of M over the merged pixels whose own target is
+                              non-zero for the chosen sample; visibility is tested for the final sample at the receiving pixel.
+                              The accumulated image converges to pathTraceDirect's.  Triangle lights only; single-GPU frames. */
 } RstrParams;
 
 #define RSTR_REUSE_NONE 0
@@ -300,6 +308,9 @@ int rstr_frame_set_fusion(RstrFrame*, int enable);
  * traced tree of at most 1024 nodes, e.g. a Cornell box, where no ray diverges and the extra launches cost more than
  * they save).  Identical results in every mode (A/B measurements, tests). */
 int rstr_frame_set_pipeline(RstrFrame*, int staged);
+/* The staged pipeline cuts its rows into `bands` horizontal bands (1 .. 8, default 4), each with its own queue: a band's queue kernels
+ * run on a side stream under the next band's k_primary.  1 = strictly one kernel after the other (A/B measurements). */
+int rstr_frame_set_bands(RstrFrame*, int bands);
 /* Cost profile for placing the strip cuts.  enable != 0 starts (or restarts from zero) the
  * accumulation: the G-buffer and phase-A kernels add the SM cycles every block (16x8 pixels) held its SM slot to one
  * counter per group of 8 image rows.  If cyclesPerRowGroup != NULL the counters (numGroups = ceil(height / 8)) are read

@@ -52,6 +52,7 @@ class RstrParams(C.Structure):
         ("spatialRadius", C.c_float),
         ("reuse", C.c_int),
         ("spatialPasses", C.c_int),
+        ("unbiased", C.c_int),
     ]
 
 
@@ -152,6 +153,7 @@ def lib() -> C.CDLL:
     L.rstr_frame_set_halo_render.argtypes = [vp, ip]
     L.rstr_frame_set_fusion.argtypes = [vp, ip]
     L.rstr_frame_set_pipeline.argtypes = [vp, ip]
+    L.rstr_frame_set_bands.argtypes = [vp, ip]
     L.rstr_frame_row_cost.argtypes = [vp, ip, vp, ip]
     L.rstr_tonemap.argtypes = [vp, ip, fp]
     L.rstr_frame_save_png.argtypes = [vp, C.c_char_p, ip]
@@ -208,9 +210,10 @@ def init(device: int = 0) -> None:
     _check(lib().rstr_init(device))
 
 
-def default_params(reuse: int = REUSE_TEMPORAL, radius: float = 5.0, k: int = 5, cap: int = 20, candidates: int = 32, passes: int = 1) -> RstrParams:
+def default_params(reuse: int = REUSE_TEMPORAL, radius: float = 5.0, k: int = 5, cap: int = 20, candidates: int = 32, passes: int = 1,
+                   unbiased: bool = False) -> RstrParams:
     """restir.cu literals (32 candidates, cap 20, 5 neighbours, radius 5 px, one spatial pass) unless overridden."""
-    return RstrParams(candidates, cap, k, radius, reuse, passes)
+    return RstrParams(candidates, cap, k, radius, reuse, passes, 1 if unbiased else 0)
 
 
 def launch_count() -> int:
@@ -377,6 +380,10 @@ class Frame:
     def set_pipeline(self, staged) -> None:
         """Phase A as the staged kernel pipeline (True), as one fused kernel (False), or chosen by scene size (None, default)."""
         _check(lib().rstr_frame_set_pipeline(self.f, -1 if staged is None else (1 if staged else 0)))
+
+    def set_bands(self, bands: int) -> None:
+        """Row bands of the staged pipeline (1 = no overlap between its kernels)."""
+        _check(lib().rstr_frame_set_bands(self.f, int(bands)))
 
     def set_halo_render(self, on: bool) -> None:
         _check(lib().rstr_frame_set_halo_render(self.f, 1 if on else 0))

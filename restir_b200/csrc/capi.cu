@@ -40,7 +40,7 @@ FrameDev rsToFrameDev(const RstrFrame* f, int rowLo, int rowHi) {
     d.matId[0] = f->matId[f->cur]; d.matId[1] = f->matId[f->cur ^ 1];
     d.albedoMotion = f->albedoMotion; d.radiance = f->radiance;
     d.resvOut = f->resv[f->resvOut]; d.resvIn = f->resv[f->resvOut ^ 1]; d.resvTemp = f->resvTemp;
-    d.hit = f->hit; d.hitMR = f->hitMR; d.rowCost = f->rowCost; d.haloMiss = f->haloMiss; d.motionRows = f->haloMiss + 1; d.queue = f->queue; d.queueCount = f->queueCount; d.shadeQueue = f->shadeQueue;
+    d.hit = f->hit; d.hitPos = f->hitPos; d.hitMR = f->hitMR; d.rowCost = f->rowCost; d.haloMiss = f->haloMiss; d.motionRows = f->haloMiss + 1; d.queue = f->queue; d.queueCount = f->queueCount; d.shadeQueue = f->shadeQueue;
     return d;
 }
 
@@ -141,6 +141,7 @@ int rstr_init(int device) {
 void rstr_params_default(RstrParams* p) {
     p->numCandidates = 32; p->temporalCap = 20; p->numSpatial = 5; p->spatialRadius = 5.f; p->reuse = RSTR_REUSE_TEMPORAL;   // common.cpp:14
     p->spatialPasses = 1;
+    p->unbiased = 0;
 }
 
 int rstr_scene_create(const RstrSceneDesc* desc, RstrScene** out) {
@@ -289,7 +290,7 @@ int rstr_frame_destroy(RstrFrame* f) {
     if (!f) return RSTR_OK;
     if (f->stream) cudaStreamSynchronize(f->stream);
     cudaFree(f->slab);             // geom[2], matId[2], resv[2], resvTemp, resvTemp2 live in the exchange slab
-    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->hit); cudaFree(f->hitMR); cudaFree(f->rowCost); cudaFree(f->ldr);
+    cudaFree(f->albedoMotion); cudaFree(f->radiance); cudaFree(f->hit); cudaFree(f->hitPos); cudaFree(f->hitMR); cudaFree(f->rowCost); cudaFree(f->ldr);
     cudaFree(f->haloMiss); cudaFree(f->scratch); cudaFree(f->queue); cudaFree(f->shadeQueue); cudaFree(f->queueCount);
     for (int i = 0; i < RSTR_LDR_SLOTS; i++) {
         cudaFree(f->ldrB[i]);
@@ -297,6 +298,8 @@ int rstr_frame_destroy(RstrFrame* f) {
         if (f->evCopied[i]) cudaEventDestroy(f->evCopied[i]);
     }
     if (f->copyStream) cudaStreamDestroy(f->copyStream);
+    for (int i = 0; i < 2; i++) if (f->ss.side[i]) { cudaStreamSynchronize(f->ss.side[i]); cudaStreamDestroy(f->ss.side[i]); }
+    for (int i = 0; i < RS_MAX_BANDS; i++) { if (f->ss.evPrimary[i]) cudaEventDestroy(f->ss.evPrimary[i]); if (f->ss.evDone[i]) cudaEventDestroy(f->ss.evDone[i]); }
     for (auto& e : f->ev) if (e) cudaEventDestroy(e);
     if (f->xfer) cudaEventDestroy(f->xfer);
     for (auto& e : f->marks) if (e) cudaEventDestroy(e);
@@ -347,7 +350,7 @@ int rstr_frame_create_strip(RstrScene* sc, int W, int H, int row0, int row1, int
     alloc((void**)&f->haloMiss, 4 * sizeof(unsigned int));     // [0] halo misses, [1] max |row(motion) - row|
     alloc((void**)&f->queue, n * sizeof(int));
     alloc((void**)&f->shadeQueue, n * sizeof(int));
-    alloc((void**)&f->queueCount, 4 * sizeof(unsigned int));
+    alloc((void**)&f->queueCount, (4 + 2 * RS_MAX_BANDS) * sizeof(unsigned int));
     if (e == cudaSuccess) {
         // a zero-filled reference reservoir has no sample: lightId must read as "none"
         std::vector<ResvD> init(n);
@@ -424,6 +427,13 @@ int rstr_frame_set_pipeline(RstrFrame* f, int staged) {
     return rc;
 }
 
+// number of row bands the staged pipeline overlaps (1 = no overlap; default 4)
+int rstr_frame_set_bands(RstrFrame* f, int bands) {
+    if (!f || bands < 1 || bands > RS_MAX_BANDS) return fail(RSTR_ERR_ARG, "rstr_frame_set_bands: 1 .. 8");
+    f->bands = bands;
+    return RSTR_OK;
+}
+
 int rstr_frame_set_fusion(RstrFrame* f, int enable) {
     if (!f) return fail(RSTR_ERR_ARG, "null frame");
     int rc = rsFlushGBuffer(f);
@@ -443,6 +453,14 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     int rc = checkCam(f, cam);
     if (rc) return rc;
     if (!prm || prm->numCandidates < 0 || prm->numSpatial < 0 || prm->temporalCap < 1) return fail(RSTR_ERR_ARG, "bad RstrParams");
+    if (prm->unbiased) {
+        if (f->sc->hs.envMapTexId >= 0) return fail(RSTR_ERR_ARG, "RstrParams::unbiased: environment-map lights are not supported (triangle lights only)");
+        if (f->bufRows != f->H) return fail(RSTR_ERR_ARG, "RstrParams::unbiased: strip frames are not supported (single-GPU frames only)");
+        if (!f->hitPos) {
+            CU(cudaMalloc((void**)&f->hitPos, f->nBuf * sizeof(float4)));
+            CU(cudaMemsetAsync(f->hitPos, 0, f->nBuf * sizeof(float4), f->stream));
+        }
+    }
     FrameDev d = rsToFrameDev(f, f->row0, f->row1);
     d.resvStage = f->resvTemp;
     if (f->gbufPending && memcmp(cam, &f->pendCam, sizeof(RstrCamera)) == 0 && f->sc->dev.traversal == RS_TRAVERSAL_FAST) {
@@ -456,7 +474,15 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
             d.resvStage = (prm->reuse & 2) ? f->resvTemp : f->resvTemp2;
             if (!(prm->reuse & 2)) f->temp2Ready = false;
         }
-        int n = staged ? launchPhaseAStaged(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, smCount(), f->stream)
+        if (staged && !f->ss.side[0]) {
+            for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&f->ss.side[i], cudaStreamNonBlocking));
+            for (int i = 0; i < RS_MAX_BANDS; i++) {
+                CU(cudaEventCreateWithFlags(&f->ss.evPrimary[i], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&f->ss.evDone[i], cudaEventDisableTiming));
+            }
+        }
+        f->ss.bands = f->bands;
+        int n = staged ? launchPhaseAStaged(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, smCount(), f->stream, f->ss)
                        : launchGBufferRestirA(f->sc->dev, d, f->pendC, f->pendLC, *prm, looper, iter, f->first ? 1 : 0, f->stream);
         if (n > 0) {
             f->gbufPending = false;

@@ -55,6 +55,7 @@ struct RstrFrame {
     rs::ResvD* resvTemp2 = nullptr;    // second publication buffer (spatialPasses > 1)
     bool temp2Ready = false;           // resvTemp2 holds a copy of resvTemp's initial content
     rs::HitRec* hit = nullptr;
+    float4* hitPos = nullptr;      // unbiased mode: shaded points (allocated on first use)
     float2* hitMR = nullptr;       // allocated when the scene has metallic / roughness maps
     uchar4* ldr = nullptr;
     uchar4* ldrB[RSTR_LDR_SLOTS] = {};        // LDR frames in flight of the pipelined host call
@@ -65,6 +66,8 @@ struct RstrFrame {
     unsigned long long* rowCost = nullptr;    // allocated by rstr_frame_row_cost
     int* queue = nullptr;
     int* shadeQueue = nullptr;     // staged phase A: compact list of shaded pixels
+    rs::StagedStreams ss{};        // side streams / events of the banded staged pipeline (created on first use)
+    int bands = 4;                 // row bands of the staged pipeline (their queue kernels overlap the next band's k_primary)
     int staged = -1;               // phase A as the staged pipeline (kernels.cu): 1, as the single fused kernel: 0, by scene size: -1
     unsigned int* queueCount = nullptr;
     void* scratch = nullptr; size_t scratchBytes = 0;

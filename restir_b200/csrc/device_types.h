@@ -90,10 +90,12 @@ struct FrameDev {
     ResvD* resvTemp;
     ResvD* resvStage;          // staged phase A: the reservoir between k_candidates and k_temporal (resvTemp, or resvTemp2 when spatial reuse is off)
     HitRec* hit;
+    float4* hitPos;            // unbiased mode: the shaded point {pos.xyz, -} (allocated on first use)
     float2* hitMR;             // {metallic, roughness} of the shaded point; only allocated for scenes with such maps
     int* queue;                // pixels deferred to the reference-order fix-up kernel
-    unsigned int* queueCount;  // [0] fix-up queue length, [1] shaded-pixel queue length, [2] k_shadow's cursor into it
-    int* shadeQueue;           // staged phase A: pixels (global index) whose jittered ray hit a shaded surface
+    unsigned int* queueCount;  // [0] fix-up queue length; [4 + 2b], [5 + 2b]: band b's shaded-pixel queue length and k_shadow's cursor into it
+    unsigned int* shadeCount;  // staged phase A, this launch's band: {queue length, k_shadow's cursor}
+    int* shadeQueue;           // staged phase A, this launch's band: pixels (global index) whose jittered ray hit a shaded surface
     unsigned int* haloMiss;    // count of neighbour / reprojection reads that fell outside the resident rows
     unsigned int* motionRows;  // running max |row(motion) - row| of the reprojected pixels (bound for the temporal halo)
     unsigned long long* rowCost;  // optional [ceil(H / 8)] cycle accumulators (rstr_frame_row_cost), else null

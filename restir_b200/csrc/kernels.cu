@@ -1100,6 +1100,79 @@ RS_D void temporalAndStore(const DevScene& s, const FrameDev& f, const RstrParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------ unbiased reuse
+// RstrParams::unbiased -- an ADDITIONAL mode; the reference has none (its reuse, restir.cu:172-199 / restir.h:61-70, is the biased
+// form above).  After Bitterli et al. 2020, Alg. 6, in area measure: a reservoir carries the light POINT y (in the wi slot), its
+// unbiased contribution weight W = wSum / (M * phat_owner(y)) (in the dist slot), wSum, M and the light id.  A pixel that reuses
+// a sample re-evaluates the target at ITS shading point, phat_q(y) = lum(Le f_q cos_q) * cos_l / d^2, and merges with weight
+// phat_q(y) * W * M; spatial merges are normalised by 1 / Z with Z the sum of M over the merged pixels whose own target is
+// non-zero for the chosen y; visibility is part of the integrand: ONE shadow ray per pixel, for the final sample, at the
+// receiving pixel.  Candidate generation, neighbour selection, similarity tests and the RNG draw pattern are the reference's.
+struct UnbPoint { f3 pos, nrm, wo; int type; float metallic, roughness; };
+// integrand without visibility and without albedo, (Le f cos_q) * cos_l / d^2, for light point y of triangle light `lightId`
+RS_D f3 unbIntegrand(const DevScene& s, const UnbPoint& q, f3 y, int lightId) {
+    if (lightId < 0) return mk3(0.f);
+    const float4* lp = s.lights + 4 * (size_t)lightId;
+    const F8 lB = ldg256(lp + 2);
+    const f3 nl = mk3(lB.lo.y, lB.lo.z, lB.lo.w), Le = mk3(lB.hi.x, lB.hi.y, lB.hi.z);
+    const f3 pts = y - q.pos;
+    const float cl = dot(nl, pts);
+    if (cl > -1e-6f) return mk3(0.f);                                  // single-sided emitters (scene.h:415)
+    const float d2 = dot(pts, pts);
+    const float dist = sqrtf(d2);
+    const f3 wi = pts * (1.f / dist);
+    const f3 g = Le * materialBSDF(q.type, q.metallic, q.roughness, mk3(1.f), diffuseTerm(mk3(1.f)), q.nrm, q.wo, wi) * satDot(q.nrm, wi);
+    return g * (fabsf(dot(nl, wi)) / d2);
+}
+RS_D float unbTarget(const DevScene& s, const UnbPoint& q, f3 y, int lightId) {
+    const float t = luminance(unbIntegrand(s, q, y, lightId));
+    return (isNanOrInf(t) || t < 0.f) ? 0.f : t;
+}
+// reservoir in unbiased form: wi = y, dist = W
+RS_D void unbFinalize(const DevScene& s, const UnbPoint& q, Resv& R) {
+    const float ph = R.lightId >= 0 ? unbTarget(s, q, R.wi, R.lightId) : 0.f;
+    R.dist = (ph > 0.f && R.M > 0) ? R.w / ((float)R.M * ph) : 0.f;
+    if (isNanOrInf(R.dist)) R.dist = 0.f;
+}
+RS_D void unbMerge(const DevScene& s, const UnbPoint& q, Resv& R, const Resv& N, float rnd) {
+    const float m = N.lightId >= 0 ? unbTarget(s, q, N.wi, N.lightId) * N.dist * (float)N.M : 0.f;
+    R.w += m; R.M += N.M;
+    if (rnd * R.w < m) { R.wi = N.wi; R.lightId = N.lightId; }
+}
+
+// unbiased counterpart of temporalAndStore: R arrives from candidateLoop in the reference's form {wi, dist}
+template <bool SPATIAL>
+RS_D void temporalAndStoreUnbiased(const DevScene& s, const FrameDev& f, const RstrParams& prm, int iter, int first, size_t li, int index,
+                                   const ShadePoint& sp, Resv R, Rng rng, Stack& stack) {
+    UnbPoint q;
+    q.pos = sp.pos; q.nrm = sp.nrm; q.wo = sp.wo; q.type = sp.type; q.metallic = sp.metallic; q.roughness = sp.roughness;
+    if (R.lightId >= 0) R.wi = sp.pos + R.wi * R.dist;                               // the light point
+    if (!first && (prm.reuse & 1)) {
+        Resv T = findTemporal(f, li, index);                                         // same tests as restir.cu:20-45
+        if (!resvInvalid(T)) {
+            float rnd = rng.next();
+            if (R.M > 0) resvClamp(T, (prm.temporalCap - 1) * R.M);                  // M cap as preClampedMerge (wSum is not used of T)
+            unbMerge(s, q, R, T, rnd);
+        }
+    }
+    resvCheck(R);
+    unbFinalize(s, q, R);
+    storeResv(f.resvOut + li, R);
+    if (SPATIAL) {
+        storeResv(f.resvTemp + li, R);
+        float4* h = (float4*)(f.hit + li);
+        h[0] = make_float4(sp.nrm.x, sp.nrm.y, sp.nrm.z, __int_as_float(sp.matId));
+        h[1] = make_float4(sp.wo.x, sp.wo.y, sp.wo.z, __uint_as_float(rng.x));
+        f.hitPos[li] = make_float4(sp.pos.x, sp.pos.y, sp.pos.z, 0.f);
+        if (f.hitMR) f.hitMR[li] = make_float2(sp.metallic, sp.roughness);
+    } else {
+        f3 direct = mk3(0.f);
+        if (R.lightId >= 0 && R.dist > 0.f && traceOccluded<false>(s, sp.pos, R.wi, stack) == 0) direct = unbIntegrand(s, q, R.wi, R.lightId) * R.dist;
+        if (hasNanOrInf(direct)) direct = mk3(0.f);
+        writeRadiance(f, li, direct, iter);
+    }
+}
+
 // all stages in one thread; false = undecided, nothing written
 template <bool EXACT, bool SPATIAL>
 RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams& prm, int iter, int first,
@@ -1109,6 +1182,7 @@ RS_D bool restirAAfterHit(const DevScene& s, const FrameDev& f, const RstrParams
     const int status = shadePointOf(s, h, d, sp);
     if (status != 2) { unshadedPixel<SPATIAL>(s, f, li, status, d, iter); return true; }
     Resv R = candidateLoop(s, prm, sp, rng);
+    if (prm.unbiased) { temporalAndStoreUnbiased<SPATIAL>(s, f, prm, iter, first, li, y * f.W + x, sp, R, rng, stack); return true; }
     // restir.cu:172-176.  With weight == 0 the test cannot change anything, so the ray is skipped.
     if (R.w != 0.f) {
         int occ = traceOccluded<EXACT>(s, sp.pos, sp.pos + R.wi * R.dist, stack);
@@ -1299,7 +1373,7 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_PRIMARY) k_primary(const __g
     if (m) {
         const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
         unsigned base = 0;
-        if (lane == leader) base = atomicAdd(f.queueCount + 1, (unsigned)__popc(m));
+        if (lane == leader) base = atomicAdd(f.shadeCount, (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (shaded) f.shadeQueue[base + __popc(m & ((1u << lane) - 1u))] = y * f.W + x;
     }
@@ -1314,7 +1388,7 @@ RS_D void accountPixel(const FrameDev& f, int y, long long t0) {
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_CAND) k_candidates(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                            const __grid_constant__ CamDev cam, const __grid_constant__ RstrParams prm, int looper) {
     const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
-    if (i >= f.queueCount[1]) return;
+    if (i >= f.shadeCount[0]) return;
     const long long t0 = f.rowCost ? clock64() : 0;
     const int index = f.shadeQueue[i];
     const int x = index % f.W, y = index / f.W;
@@ -1342,7 +1416,7 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_CAND) k_candidates(const __g
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f) {
     RS_DECLARE_REFSTACK(stack);
     const unsigned FULL = 0xffffffffu;
-    const unsigned n = f.queueCount[1];
+    const unsigned n = f.shadeCount[0];
     const int lane = threadIdx.x & 31;
     RayT r;
     RayF rf;
@@ -1359,7 +1433,7 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
         if (!exhausted && (__popc(idle) >= RS_REFILL_MIN || idle == FULL)) {
             unsigned base = 0;
             const int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(f.queueCount + 2, (unsigned)__popc(idle));
+            if (lane == leader) base = atomicAdd(f.shadeCount + 1, (unsigned)__popc(idle));
             base = __shfl_sync(FULL, base, leader);
             if (base >= n) exhausted = true;
             const unsigned i = base + __popc(idle & ((1u << lane) - 1u));
@@ -1428,7 +1502,7 @@ template <bool SPATIAL>
 __global__ void __launch_bounds__(RS_BLOCK) k_temporal(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                        const __grid_constant__ RstrParams prm, int iter, int first) {
     const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
-    if (i >= f.queueCount[1]) return;
+    if (i >= f.shadeCount[0]) return;
     const long long t0 = f.rowCost ? clock64() : 0;
     const int index = f.shadeQueue[i];
     const int x = index % f.W, y = index / f.W;
@@ -1444,6 +1518,31 @@ __global__ void __launch_bounds__(RS_BLOCK) k_temporal(const __grid_constant__ D
     temporalAndStore<SPATIAL>(s, f, prm, iter, first, li, index, mk3(h0.x, h0.y, h0.z), mk3(h1.x, h1.y, h1.z), matId,
                               __ldg(&s.materials[matId].type), metallic, roughness, R, rng);
     if (f.rowCost) accountPixel(f, y, t0);
+}
+
+// unbiased mode: k_temporal's counterpart (k_shadow is not launched: visibility is tested once, for the final sample)
+template <bool SPATIAL>
+__global__ void __launch_bounds__(RS_BLOCK) k_temporal_unb(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                           const __grid_constant__ RstrParams prm, int iter, int first) {
+    RS_DECLARE_REFSTACK(stack);
+    const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
+    if (i >= f.shadeCount[0]) return;
+    const int index = f.shadeQueue[i];
+    const int x = index % f.W, y = index / f.W;
+    const size_t li = planeIndex(f, x, y);
+    const float4* q = (const float4*)(f.hit + li);
+    const float4 h0 = q[0], h1 = q[1];
+    const float4* sc = (const float4*)(f.resvOut + li);
+    const float4 s0 = sc[0];
+    ShadePoint sp;
+    sp.pos = mk3(s0.x, s0.y, s0.z); sp.metallic = s0.w; sp.roughness = sc[1].x;
+    sp.nrm = mk3(h0.x, h0.y, h0.z); sp.wo = mk3(h1.x, h1.y, h1.z);
+    sp.matId = __float_as_int(h0.w);
+    sp.type = __ldg(&s.materials[sp.matId].type);
+    Rng rng;
+    rng.x = __float_as_uint(h1.w);
+    const Resv R = loadResv(f.resvStage + li);
+    temporalAndStoreUnbiased<SPATIAL>(s, f, prm, iter, first, li, index, sp, R, rng, stack);
 }
 
 // restir.cu:47-85 (+ mathUtil.h:128-132 toConcentricDisk)
@@ -1511,6 +1610,102 @@ __global__ void __launch_bounds__(128) k_restir_b(const __grid_constant__ DevSce
     if (f.hitMR) { float2 mr = f.hitMR[li]; metallic = mr.x; roughness = mr.y; }
     else { metallic = __ldg(&m->metallic); roughness = __ldg(&m->roughness); }
     writeRadiance(f, li, shadeReservoir(s, R, __ldg(&m->type), metallic, roughness, nrm, wo), iter);
+}
+
+// restir.cu:47-85 without the reservoir fetch: plane index of the neighbour drawn by (rx, ry), or -1 when it is rejected
+RS_D long long spatialNeighbour(const FrameDev& f, int x, int y, size_t li, float rx, float ry, float radius) {
+    float rr = sqrtf(rx);
+    float theta = ry * RS_PI * 2.0f;
+    float px_ = cosf(theta) * rr * radius, py_ = sinf(theta) * rr * radius;
+    int px = __float2int_rz((float)x + .5f + px_);
+    int py = __float2int_rz((float)y + .5f + py_);
+    if (px < 0 || px >= f.W || py < 0 || py >= f.H || (px == x && py == y)) return -1;
+    if (!rowResident(f, py)) { atomicAdd(f.haloMiss, 1u); return -1; }
+    size_t pli = planeIndex(f, px, py);
+    if (f.matId[0][pli] != f.matId[0][li]) return -1;
+    float4 g = f.geom[0][li], pg = f.geom[0][pli];
+    bool diff = dot(mk3(g.x, g.y, g.z), mk3(pg.x, pg.y, pg.z)) < .9f;
+    if (fabsf(g.w - pg.w) > g.w * .1f) diff = true;
+    return diff ? -1 : (long long)pli;
+}
+RS_D UnbPoint unbPointOf(const DevScene& s, const FrameDev& f, size_t li) {
+    const float4* q = (const float4*)(f.hit + li);
+    const float4 h0 = q[0], h1 = q[1], hp = f.hitPos[li];
+    UnbPoint p;
+    p.pos = mk3(hp.x, hp.y, hp.z); p.nrm = mk3(h0.x, h0.y, h0.z); p.wo = mk3(h1.x, h1.y, h1.z);
+    const int matId = __float_as_int(h0.w);
+    const RstrMaterial* m = s.materials + (matId < 0 ? 0 : matId);
+    p.type = matId < 0 ? 2 : __ldg(&m->type);                          // a pixel phase A did not shade: target 0 everywhere
+    if (f.hitMR) { float2 mr = f.hitMR[li]; p.metallic = mr.x; p.roughness = mr.y; }
+    else { p.metallic = __ldg(&m->metallic); p.roughness = __ldg(&m->roughness); }
+    return p;
+}
+
+// One spatial pass of the unbiased mode (see "unbiased reuse" above): the reference's neighbour draws and tests, every merged
+// sample re-evaluated here, 1 / Z normalisation, and on the last pass ONE shadow ray for the chosen sample.
+__global__ void __launch_bounds__(RS_BLOCK) k_restir_b_unb(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                           const __grid_constant__ RstrParams prm, int iter,
+                                                           const ResvD* __restrict__ src, ResvD* __restrict__ dst, int pass, int last) {
+    RS_DECLARE_REFSTACK(stack);
+    int x, y;
+    if (!pixelOf(f, x, y)) return;
+    size_t li = planeIndex(f, x, y);
+    float4* hq = (float4*)(f.hit + li);
+    const float4 h1 = hq[1];
+    const int matId = __float_as_int(hq[0].w);
+    if (matId < 0) {                                // phase A already wrote this pixel's radiance
+        if (!last) { const float4* a = (const float4*)(src + li); float4* b = (float4*)(dst + li); b[0] = a[0]; b[1] = a[1]; }
+        else if (src != f.resvTemp) { const float4* a = (const float4*)(src + li); float4* b = (float4*)(f.resvTemp + li); b[0] = a[0]; b[1] = a[1]; }
+        return;
+    }
+    const UnbPoint q = unbPointOf(s, f, li);
+    Rng rng; rng.x = __float_as_uint(h1.w);
+    const Rng rng0 = rng;                           // the neighbour draws are replayed for Z
+    const Resv own = loadResv(src + li);
+    const int capM = pass == 1 ? 0x7fffffff : 3 * own.M;     // later passes clamp a neighbour's M like preClampedMerge<4> (restir.cu:206)
+    Resv S = own;                                   // own sample first: weight phat_q(y_own) * W_own * M_own
+    S.w = own.lightId >= 0 ? unbTarget(s, q, own.wi, own.lightId) * own.dist * (float)own.M : 0.f;
+    for (int i = 0; i < prm.numSpatial; i++) {
+        float rx = rng.next(), ry = rng.next();
+        long long pli = spatialNeighbour(f, x, y, li, rx, ry, prm.spatialRadius);
+        float rnd = rng.next();                     // the reference draws for every try (a rejected one merges an empty reservoir)
+        if (pli < 0) continue;
+        Resv N = loadResv(src + pli);
+        if (resvInvalid(N)) continue;
+        if (N.M > capM) N.M = capM;
+        unbMerge(s, q, S, N, rnd);
+    }
+    // Z: the M of every merged pixel whose OWN target is non-zero for the chosen light point
+    float Z = 0.f;
+    const float phq = S.lightId >= 0 ? unbTarget(s, q, S.wi, S.lightId) : 0.f;
+    if (phq > 0.f) {
+        Z = (float)own.M;
+        Rng r2 = rng0;
+        for (int i = 0; i < prm.numSpatial; i++) {
+            float rx = r2.next(), ry = r2.next();
+            r2.next();
+            long long pli = spatialNeighbour(f, x, y, li, rx, ry, prm.spatialRadius);
+            if (pli < 0) continue;
+            Resv N = loadResv(src + pli);
+            if (resvInvalid(N)) continue;
+            if (N.M > capM) N.M = capM;
+            const UnbPoint pn = unbPointOf(s, f, (size_t)pli);
+            if (unbTarget(s, pn, S.wi, S.lightId) > 0.f) Z += (float)N.M;
+        }
+    }
+    const float W = (phq > 0.f && Z > 0.f) ? S.w / (Z * phq) : 0.f;
+    S.dist = isNanOrInf(W) ? 0.f : W;
+    S.w = S.dist * phq * (float)S.M;                // consistent {wSum, W, M} for a later pass
+    if (!last) {
+        storeResv(dst + li, S);
+        hq[1] = make_float4(h1.x, h1.y, h1.z, __uint_as_float(rng.x));
+        return;
+    }
+    if (src != f.resvTemp) storeResv(f.resvTemp + li, own);
+    f3 direct = mk3(0.f);
+    if (S.lightId >= 0 && S.dist > 0.f && traceOccluded<false>(s, q.pos, S.wi, stack) == 0) direct = unbIntegrand(s, q, S.wi, S.lightId) * S.dist;
+    if (hasNanOrInf(direct)) direct = mk3(0.f);
+    writeRadiance(f, li, direct, iter);
 }
 
 // pathtrace.cu:279-328 with scene.h:427-459 (occlusion test BEFORE the facing test)
@@ -1708,27 +1903,55 @@ int launchGBufferRestirA(const DevScene& s, const FrameDev& f, const CamDev& cam
     }
     return 2;
 }
-// staged form of the above (k_primary -> k_candidates -> k_shadow -> k_temporal -> fix-up)
-int launchPhaseAStaged(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, const RstrParams& p, int looper, int iter, int first, int numSMs, cudaStream_t st) {
+// staged form of the above (k_primary -> k_candidates -> k_shadow -> k_temporal -> fix-up).  The rows are cut into up to
+// RS_MAX_BANDS horizontal bands, each with its own queue: band b's k_primary runs on the frame's stream, its three queue
+// kernels on one of two side streams, so that they overlap the NEXT band's k_primary -- an issue-bound packet walk next
+// to gather-bound kernels, and every kernel's tail hidden under another kernel (measured: profiles/README.md).
+int launchPhaseAStaged(const DevScene& s, const FrameDev& f, const CamDev& cam, const CamDev& lastCam, const RstrParams& p, int looper, int iter, int first, int numSMs,
+                       cudaStream_t st, const StagedStreams& ss) {
     if (s.traversal == RS_TRAVERSAL_EXACT) return 0;
-    cudaMemsetAsync(f.queueCount, 0, 4 * sizeof(unsigned int), st);
-    const dim3 grid = pixelGrid(f);
-    const unsigned linear = grid.x * grid.y;           // one thread per pixel of the rows: upper bound of the queue length
+    const int rows = f.rowHi - f.rowLo;
+    int bands = ss.bands < 1 ? 1 : (ss.bands > RS_MAX_BANDS ? RS_MAX_BANDS : ss.bands);
+    int bandRows = ((rows + bands - 1) / bands + 7) & ~7;            // whole 8-row tiles
+    if (bandRows * (bands - 1) >= rows) bands = (rows + bandRows - 1) / bandRows;
+    cudaMemsetAsync(f.queueCount, 0, (4 + 2 * RS_MAX_BANDS) * sizeof(unsigned int), st);
     const bool sp = (p.reuse & 2) != 0;
-    if (sp) k_primary<true><<<grid, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, looper, iter);
-    else k_primary<false><<<grid, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, looper, iter);
-    k_candidates<<<linear, RS_BLOCK, 0, st>>>(s, f, cam, p, looper);
-    k_shadow<<<(unsigned)(numSMs * RS_MINB_SHADOW), RS_BLOCK, 0, st>>>(s, f);
-    if (sp) {
-        k_temporal<true><<<linear, RS_BLOCK, 0, st>>>(s, f, p, iter, first);
-        k_gbuffer_restir_a_fix<true><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
-    } else {
-        k_temporal<false><<<linear, RS_BLOCK, 0, st>>>(s, f, p, iter, first);
-        k_gbuffer_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+    int launches = 0;
+    for (int b = 0; b < bands; b++) {
+        FrameDev fb = f;
+        fb.rowLo = f.rowLo + b * bandRows;
+        fb.rowHi = fb.rowLo + bandRows < f.rowHi ? fb.rowLo + bandRows : f.rowHi;
+        fb.shadeCount = f.queueCount + 4 + 2 * b;
+        fb.shadeQueue = f.shadeQueue + (size_t)(fb.rowLo - f.rowLo) * f.W;
+        const dim3 grid = pixelGrid(fb);
+        const unsigned linear = grid.x * grid.y;           // one thread per pixel of the band: upper bound of its queue length
+        if (sp) k_primary<true><<<grid, RS_BLOCK, 0, st>>>(s, fb, cam, lastCam, looper, iter);
+        else k_primary<false><<<grid, RS_BLOCK, 0, st>>>(s, fb, cam, lastCam, looper, iter);
+        cudaStream_t q = st;
+        if (bands > 1) {
+            q = ss.side[b & 1];
+            cudaEventRecord(ss.evPrimary[b], st);
+            cudaStreamWaitEvent(q, ss.evPrimary[b], 0);
+        }
+        k_candidates<<<linear, RS_BLOCK, 0, q>>>(s, fb, cam, p, looper);
+        // the bands' shadow kernels share the machine with each other and with the next band's k_primary
+        if (!p.unbiased) k_shadow<<<(unsigned)(numSMs * (bands > 1 ? RS_MINB_SHADOW / 2 : RS_MINB_SHADOW)), RS_BLOCK, 0, q>>>(s, fb);
+        if (p.unbiased) {
+            if (sp) k_temporal_unb<true><<<linear, RS_BLOCK, 0, q>>>(s, fb, p, iter, first);
+            else k_temporal_unb<false><<<linear, RS_BLOCK, 0, q>>>(s, fb, p, iter, first);
+        } else if (sp) k_temporal<true><<<linear, RS_BLOCK, 0, q>>>(s, fb, p, iter, first);
+        else k_temporal<false><<<linear, RS_BLOCK, 0, q>>>(s, fb, p, iter, first);
+        if (bands > 1) cudaEventRecord(ss.evDone[b], q);
+        launches += 4;
     }
-    return 5;
+    if (bands > 1)
+        for (int b = 0; b < bands; b++) cudaStreamWaitEvent(st, ss.evDone[b], 0);
+    if (sp) k_gbuffer_restir_a_fix<true><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+    else k_gbuffer_restir_a_fix<false><<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, lastCam, p, looper, iter, first);
+    return launches + 1;
 }
 void launchRestirB(const DevScene& s, const FrameDev& f, const RstrParams& p, int iter, const ResvD* src, ResvD* dst, int pass, int last, cudaStream_t st) {
+    if (p.unbiased) { k_restir_b_unb<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, p, iter, src, dst, pass, last); return; }
     k_restir_b<<<pixelGrid(f), 128, 0, st>>>(s, f, p, iter, src, dst, pass, last);
 }
 int launchPTDirect(const DevScene& s, const FrameDev& f, const CamDev& cam, int looper, int iter, cudaStream_t st) {

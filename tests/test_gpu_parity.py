@@ -530,3 +530,48 @@ def test_save_png_is_the_mirrored_tone_mapped_frame(gpu, port_oracle):
     want = np.clip((np.power(aces, np.float32(1 / 2.2)) * 255).astype(np.int64), 0, 255).reshape(150, 200, 3)
     assert np.abs(want - ldr.astype(np.int64)).max() <= 1 and ldr.max() > 100
     fr.close(); sc.close()
+
+
+def _accumulate(gpu, sc, sd, frames, prm=None, checkpoints=()):
+    """Static camera, running mean over `frames` frames (Settings::accumulate, main.cpp:155-162); prm None = pathTraceDirect."""
+    W, H = sd.resolution
+    fr = sc.frame(W, H)
+    cam = gpu.Camera.from_scene(sd)
+    out = {}
+    for k in range(frames):
+        if prm is None:
+            fr.pathtrace_direct(cam, k, k)
+        else:
+            fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, k); fr.gbuffer_update(cam)
+        if k + 1 in checkpoints:
+            out[k + 1] = fr.read("radiance").astype(np.float64)
+    out[frames] = fr.read("radiance").astype(np.float64)
+    fr.close()
+    return out
+
+
+def _relmse(img, ref):
+    return float(np.mean(((img - ref) ** 2).sum(1) / (ref.sum(1) ** 2 + 1e-2)))
+
+
+@pytest.mark.parametrize("scene_name,passes", [("cornell", 1), ("cornell", 2), ("gen", 1)])
+def test_unbiased_mode_converges_to_the_path_traced_reference(gpu, scene_name, passes):
+    """RstrParams.unbiased (an additional mode: re-evaluated targets, 1/Z normalisation, visibility re-check at the receiving
+    pixel) against the accumulated one-sample NEE image of pathTraceDirect (PTDirectKernel, pathtrace.cu:279-328), the
+    reference image BASELINE config 5 names.  The reference's own reuse is biased -- its error against that image stops
+    falling -- the unbiased mode's keeps falling with the number of accumulated frames and ends far below."""
+    sd = scenes.cornell_box((160, 120)) if scene_name == "cornell" else scenes.procedural(5, 20000, 1000, (160, 90))
+    sc = gpu.Scene.from_arrays(sd)
+    ref = _accumulate(gpu, sc, sd, 6000)[6000]
+    biased = _accumulate(gpu, sc, sd, 768, gpu.default_params(reuse=3, radius=8.0, k=5, passes=passes))[768]
+    unb = _accumulate(gpu, sc, sd, 768, gpu.default_params(reuse=3, radius=8.0, k=5, passes=passes, unbiased=True), checkpoints=(96,))
+    e_b, e_u96, e_u = _relmse(biased, ref), _relmse(unb[96], ref), _relmse(unb[768], ref)
+    print("relMSE vs PTDirect: biased %.3g, unbiased %.3g (96 frames) -> %.3g (768 frames)" % (e_b, e_u96, e_u))
+    assert e_u < 0.2 * e_b, (e_u, e_b)
+    assert e_u < 0.5 * e_u96, (e_u, e_u96)
+    assert abs(unb[768].mean() - ref.mean()) <= 0.01 * ref.mean()
+    # deterministic, like every other mode
+    again = _accumulate(gpu, sc, sd, 8, gpu.default_params(reuse=3, radius=8.0, k=5, passes=passes, unbiased=True))[8]
+    first = _accumulate(gpu, sc, sd, 8, gpu.default_params(reuse=3, radius=8.0, k=5, passes=passes, unbiased=True))[8]
+    assert helpers.mismatches(again.astype(np.float32), first.astype(np.float32)) == 0
+    sc.close()
