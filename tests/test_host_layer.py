@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts():
     assert C.sizeof(rb.api.RstrCamera) == 196 and rb.api.RstrCamera.rotationMatInv.offset == 84 and rb.api.RstrCamera.lensRadius.offset == 184
     assert scenes.MATERIAL_DTYPE.itemsize == 44 and rb.api.RESERVOIR_DTYPE.itemsize == 36
-    assert C.sizeof(rb.RstrParams) == 24
+    assert C.sizeof(rb.RstrParams) == 28 and rb.RstrParams.unbiased.offset == 24
 
 
 @pytest.mark.parametrize("name", ["cornell", "cornell_metal", "gen2000", "five"])
