@@ -47,6 +47,7 @@ class OrcParams(C.Structure):
         ("spatialRadius", C.c_float),
         ("reuse", C.c_int),
         ("spatialPasses", C.c_int),
+        ("unbiased", C.c_int),
     ]
 
 
@@ -294,8 +295,8 @@ class OracleFrame:
         return Oracle._view(ptr, RESERVOIR_DTYPE, (P,))
 
 
-def default_params(reuse: int = 0, radius: float = 5.0, k: int = 5, cap: int = 20, candidates: int = 32, passes: int = 1) -> OrcParams:
-    return OrcParams(candidates, cap, k, radius, reuse, passes)
+def default_params(reuse: int = 0, radius: float = 5.0, k: int = 5, cap: int = 20, candidates: int = 32, passes: int = 1, unbiased: bool = False) -> OrcParams:
+    return OrcParams(candidates, cap, k, radius, reuse, passes, 1 if unbiased else 0)
 
 
 def orbit_camera(orc: Oracle, base: OrcCamera, k: int, speed: float = 2.7, radius: float = 1.0, fps: float = 60.0) -> OrcCamera:

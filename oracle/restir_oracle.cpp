@@ -737,13 +737,14 @@ struct OrcFrame {
     OrcCamera lastCamera;
     bool haveLast = false;
     std::vector<Resv> resv, lastResv, temp;   /* devDirectReservoir, devLastDirectReservoir, devDirectTemp (restir.cu:8-10) */
+    std::vector<Resv> unbNext;                /* unbiased mode: results of the running spatial pass */
     bool first = true;
     std::vector<ResvPacked> exportBuf;
     std::vector<int> exportIds;
     TraceStats stats;
     ShadowStats shadow;
     /* per-pixel state carried across the two phases of spatial reuse */
-    struct Carry { uint32_t rng; int status; Resv r; V3 n, wo, direct; OrcMaterial mat; };
+    struct Carry { uint32_t rng; int status; Resv r; V3 n, wo, direct, pos; OrcMaterial mat; };
     std::vector<Carry> carry;
 };
 
@@ -980,10 +981,61 @@ static Resv findSpatialNeighborDisk(const OrcFrame* f, const std::vector<Resv>& 
     }
     return diff ? Resv() : buf[pidx];
 }
+/* the same tests, returning the neighbour's pixel index (-1: rejected) -- unbiased mode */
+static int spatialNeighbourIndex(const OrcFrame* f, int x, int y, float rx, float ry, float radius) {
+    const int cur = f->frameIdx;
+    int idx = y * f->w + x;
+    float rr = sqrtf(rx);
+    float theta = ry * Pi * 2.0f;
+    V2 p = {cosf(theta) * rr * radius, sinf(theta) * rr * radius};
+    int px = f2i_cuda((float)x + .5f + p.x);
+    int py = f2i_cuda((float)y + .5f + p.y);
+    int pidx = py * f->w + px;
+    if (px < 0 || px >= f->w || py < 0 || py >= f->h || (px == x && py == y)) return -1;
+    if (f->matId[cur][pidx] != f->matId[cur][idx]) return -1;
+    V3 norm = f->normal[cur][idx], pnorm = f->normal[cur][pidx];
+    bool diff = dot(norm, pnorm) < .9f;
+    float depth = f->depth[cur][idx], pdepth = f->depth[cur][pidx];
+    if (fabsf(depth - pdepth) > depth * .1f) diff = true;
+    return diff ? -1 : pidx;
+}
 
 /* restir.cu:111-231 as two phases; frame bookkeeping restir.cu:418-446 */
+/* ---- unbiased mode (OrcParams::unbiased): restatement of the PRODUCT's additional mode, restir_b200/csrc/kernels.cu "unbiased reuse".
+ * A reservoir holds the light point y in s.wi and the contribution weight W in s.dist; the reference has no such mode. */
+struct UnbPoint { V3 pos, n, wo; OrcMaterial mat; };
+static V3 unbIntegrand(const OrcScene& sc, const UnbPoint& q, V3 y, int lightId) {
+    if (lightId < 0) return v3(0.f);
+    int prim = sc.lightPrimIds[lightId];
+    V3 v0 = sc.vertices[prim * 3], v1 = sc.vertices[prim * 3 + 1], v2 = sc.vertices[prim * 3 + 2];
+    V3 nl = triangleNormal(v0, v1, v2), Le = sc.lightUnitRadiance[lightId];
+    V3 pts = y - q.pos;
+    float cl = dot(nl, pts);
+    if (cl > -1e-6f) return v3(0.f);
+    float d2 = dot(pts, pts);
+    float dist = sqrtf(d2);
+    V3 wi = pts * (1.f / dist);
+    V3 g = Le * materialBSDF(q.mat, v3(1.f), q.n, q.wo, wi) * satDot(q.n, wi);
+    return g * (fabsf(dot(nl, wi)) / d2);
+}
+static float unbTarget(const OrcScene& sc, const UnbPoint& q, V3 y, int lightId) {
+    float t = luminance(unbIntegrand(sc, q, y, lightId));
+    return (isNanOrInf(t) || t < 0.f) ? 0.f : t;
+}
+static void unbFinalize(const OrcScene& sc, const UnbPoint& q, Resv& R) {
+    float ph = R.lightId >= 0 ? unbTarget(sc, q, R.s.wi, R.lightId) : 0.f;
+    R.s.dist = (ph > 0.f && R.M > 0) ? R.w / ((float)R.M * ph) : 0.f;
+    if (isNanOrInf(R.s.dist)) R.s.dist = 0.f;
+}
+static void unbMerge(const OrcScene& sc, const UnbPoint& q, Resv& R, const Resv& N, float rnd) {
+    float m = N.lightId >= 0 ? unbTarget(sc, q, N.s.wi, N.lightId) * N.s.dist * (float)N.M : 0.f;
+    R.w += m; R.M += N.M;
+    if (rnd * R.w < m) { R.s.wi = N.s.wi; R.s.Li = N.s.Li; R.lightId = N.lightId; }
+}
+
 void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, int looper, int iter) {
     const OrcScene& sc = *f->sc;
+    const bool unbiased = prm->unbiased != 0;
     const int W = cam->resolution[0], H = cam->resolution[1];
     const float tanFovY = tanf(radians(cam->fov[1]));
     const bool first = f->first;
@@ -1028,6 +1080,24 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
                 if (isNanOrInf(weight) || p <= 0.f) weight = 0.f;
                 reservoir.update(Sample{Li, wi, dist}, lid, weight, rng.next());
             }
+            if (unbiased) {
+                UnbPoint q{is.pos, is.norm, is.wo, material};
+                if (reservoir.lightId >= 0) reservoir.s.wi = is.pos + reservoir.s.wi * reservoir.s.dist;      /* the light point */
+                if (!first && (reuse & 1)) {
+                    Resv temporal = findTemporalNeighbor(f, in, index);
+                    if (!temporal.invalid()) {
+                        float rnd = rng.next();
+                        if (reservoir.M > 0) temporal.clamp((prm->temporalCap - 1) * reservoir.M);
+                        unbMerge(sc, q, reservoir, temporal, rnd);
+                    }
+                }
+                reservoir.checkValidity();
+                unbFinalize(sc, q, reservoir);
+                out[index] = reservoir;
+                if (reuse & 2) tmp[index] = reservoir;
+                c.status = 2; c.rng = rng.x; c.r = reservoir; c.n = is.norm; c.wo = is.wo; c.mat = material; c.pos = is.pos;
+                continue;
+            }
             Sample s = reservoir.s;
             if (sceneOccluded(sc, is.pos, is.pos + s.wi * s.dist, &sh)) reservoir.w = 0.f;   /* :172-176 */
             if (!first && (reuse & 1)) {                                       /* :180-185 */
@@ -1058,12 +1128,58 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
             for (int i = 0; i < W * H; i++)
                 if (f->carry[i].status == 2) tmp[i] = f->carry[i].r;              /* :203 */
         }
+        if (unbiased) f->unbNext.assign((size_t)W * H, Resv());
 #pragma omp parallel for schedule(dynamic, 4)
         for (int y = 0; y < H; y++) {
             for (int x = 0; x < W; x++) {
                 OrcFrame::Carry& c = f->carry[y * W + x];
                 if (c.status != 2) continue;
                 Rng rng(0, 0); rng.x = c.rng;
+                if (unbiased) {
+                    /* the product's k_restir_b_unb: neighbours read the reservoirs published in tmp; results go to a second
+                     * buffer (next) so that every pixel of a pass sees the previous stage */
+                    const UnbPoint q{c.pos, c.n, c.wo, c.mat};
+                    const Rng rng0 = rng;
+                    const Resv own = tmp[y * W + x];
+                    const int capM = pass == 1 ? 0x7fffffff : 3 * own.M;
+                    Resv S = own;
+                    S.w = own.lightId >= 0 ? unbTarget(sc, q, own.s.wi, own.lightId) * own.s.dist * (float)own.M : 0.f;
+                    for (int i = 0; i < prm->numSpatial; i++) {
+                        float rx = rng.next(), ry = rng.next();
+                        int pidx = spatialNeighbourIndex(f, x, y, rx, ry, prm->spatialRadius);
+                        float rnd = rng.next();
+                        if (pidx < 0) continue;
+                        Resv N = tmp[pidx];
+                        if (N.invalid()) continue;
+                        if (N.M > capM) N.M = capM;
+                        unbMerge(sc, q, S, N, rnd);
+                    }
+                    float Z = 0.f;
+                    const float phq = S.lightId >= 0 ? unbTarget(sc, q, S.s.wi, S.lightId) : 0.f;
+                    if (phq > 0.f) {
+                        Z = (float)own.M;
+                        Rng r2 = rng0;
+                        for (int i = 0; i < prm->numSpatial; i++) {
+                            float rx = r2.next(), ry = r2.next();
+                            r2.next();
+                            int pidx = spatialNeighbourIndex(f, x, y, rx, ry, prm->spatialRadius);
+                            if (pidx < 0) continue;
+                            Resv N = tmp[pidx];
+                            if (N.invalid()) continue;
+                            if (N.M > capM) N.M = capM;
+                            const OrcFrame::Carry& cn = f->carry[pidx];
+                            UnbPoint pn{cn.pos, cn.n, cn.wo, cn.mat};
+                            if (cn.status != 2) pn.mat.type = 2;                  /* a pixel phase A did not shade: target 0 */
+                            if (unbTarget(sc, pn, S.s.wi, S.lightId) > 0.f) Z += (float)N.M;
+                        }
+                    }
+                    const float Wn = (phq > 0.f && Z > 0.f) ? S.w / (Z * phq) : 0.f;
+                    S.s.dist = isNanOrInf(Wn) ? 0.f : Wn;
+                    S.w = S.s.dist * phq * (float)S.M;
+                    f->unbNext[y * W + x] = S;
+                    c.rng = rng.x;
+                    continue;
+                }
                 Resv agg;                                                          /* :87-100 */
                 for (int i = 0; i < prm->numSpatial; i++) {
                     float rx = rng.next(), ry = rng.next();
@@ -1078,6 +1194,11 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
                 c.rng = rng.x;
             }
         }
+        if (unbiased) {
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < W * H; i++)
+                if (f->carry[i].status == 2) f->carry[i].r = f->unbNext[i];
+        }
     }
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < H; y++) {
@@ -1087,7 +1208,12 @@ void orc_restir_direct(OrcFrame* f, const OrcCamera* cam, const OrcParams* prm, 
             V3 direct = v3(0.f);
             if (c.status == 0) direct = c.direct;
             if (c.status == 1) direct = v3(1.f);
-            if (c.status == 2) {
+            if (c.status == 2 && unbiased) {
+                const Resv& R = c.r;
+                const UnbPoint q{c.pos, c.n, c.wo, c.mat};
+                if (R.lightId >= 0 && R.s.dist > 0.f && !sceneOccluded(sc, c.pos, R.s.wi)) direct = unbIntegrand(sc, q, R.s.wi, R.lightId) * R.s.dist;
+                if (hasNanOrInf(direct)) direct = v3(0.f);
+            } else if (c.status == 2) {
                 Resv reservoir = c.r;
                 const OrcMaterial& material = c.mat;
                 Sample s = reservoir.s;                                        /* :216-222 */

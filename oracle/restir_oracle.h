@@ -54,6 +54,10 @@ typedef struct OrcParams {
     float spatialRadius;   /* restir.cu:49    5 */
     int   reuse;           /* common.h:36-43 bit0 temporal, bit1 spatial */
     int   spatialPasses;   /* restir.cu:196-209: 1 = as shipped; 2..3 = the commented-out extra pass(es), preClampedMerge<4> */
+    int   unbiased;        /* 0 = the reference's reuse.  1 = restatement of the product's ADDITIONAL unbiased mode (not in the reference):
+                              light point + contribution weight W in the reservoir, target re-evaluated at the receiver, 1/Z, one
+                              visibility test for the final sample (include/restir_b200.h, RstrParams::unbiased).  Only the port
+                              implements it; the reference harness reads the fields above only. */
 } OrcParams;
 
 /* buffer selectors for orc_frame_buffer */

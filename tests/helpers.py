@@ -46,14 +46,14 @@ def textured_scenes():
     }
 
 
-def run_oracle(orc, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=ALL_BUFS, light_index=False, passes=1):
+def run_oracle(orc, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=ALL_BUFS, light_index=False, passes=1, unbiased=False):
     """Returns a list (per frame) of {buffer name: array}."""
     W, H = sd.resolution
     so = orc.scene(sd)
     fo = so.frame(W, H)
     base = orc_mod.make_camera(sd)
     orc.lib.orc_camera_update(C.byref(base))
-    prm = orc_mod.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates, passes=passes)
+    prm = orc_mod.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates, passes=passes, unbiased=unbiased)
     out = []
     for f in range(frames):
         cam = orc_mod.orbit_camera(orc, base, f) if orbit else base
@@ -68,7 +68,7 @@ def run_oracle(orc, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, a
 
 
 def run_gpu(rb, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=ALL_BUFS, light_index=False,
-            rows=None, halo=0, scene=None, exact=False, passes=1, fuse=True, staged=True):   # staged=None: the library's choice by scene size
+            rows=None, halo=0, scene=None, exact=False, passes=1, fuse=True, staged=True, unbiased=False):   # staged=None: the library's choice by scene size
     W, H = sd.resolution
     sc = scene or rb.Scene.from_arrays(sd)
     sc.set_traversal(exact)
@@ -76,7 +76,7 @@ def run_gpu(rb, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accum
     fr.set_fusion(fuse)
     fr.set_pipeline(staged)
     base = rb.Camera.from_scene(sd)
-    prm = rb.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates, passes=passes)
+    prm = rb.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates, passes=passes, unbiased=unbiased)
     out = []
     for f in range(frames):
         cam = base.orbit(f) if orbit else base
