@@ -724,7 +724,7 @@ def main():
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
     ap.add_argument("--refine", type=int, default=4, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "staged", "fused"], help="phase A as the staged kernel pipeline, as one fused kernel, or chosen by scene size (default)")
-    ap.add_argument("--bands", type=int, default=4, help="row bands of the staged pipeline whose queue kernels overlap the next band's primary walk (1 = none)")
+    ap.add_argument("--bands", type=int, default=1, help="row bands of the staged pipeline whose queue kernels overlap the next band's primary walk (1 = none)")
     ap.add_argument("--no-fusion", action="store_true", help="separate G-buffer and phase-A kernels instead of the fused one (A/B)")
     ap.add_argument("--split-exchange", action="store_true", help="N > 1: history reservoirs in a second exchange after phase B (A/B)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for the history-reservoir exchange at the end of the frame instead of under the next G-buffer")

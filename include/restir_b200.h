@@ -308,8 +308,10 @@ int rstr_frame_set_fusion(RstrFrame*, int enable);
  * traced tree of at most 1024 nodes, e.g. a Cornell box, where no ray diverges and the extra launches cost more than
  * they save).  Identical results in every mode (A/B measurements, tests). */
 int rstr_frame_set_pipeline(RstrFrame*, int staged);
-/* The staged pipeline cuts its rows into `bands` horizontal bands (1 .. 8, default 4), each with its own queue: a band's queue kernels
- * run on a side stream under the next band's k_primary.  1 = strictly one kernel after the other (A/B measurements). */
+/* The staged pipeline can cut its rows into `bands` horizontal bands (1 .. 8), each with its own queue: a band's queue kernels run on
+ * a side stream under the next band's k_primary.  Default 1 = strictly one kernel after the other: on B200 the overlap LOSES
+ * 15 % (2.61 -> 3.00 ms on the 1M-triangle scene with 2 or 4 bands: the persistent shadow kernel and the packet walk fight for
+ * the same SMs and L1), so it stays an A/B switch. */
 int rstr_frame_set_bands(RstrFrame*, int bands);
 /* Cost profile for placing the strip cuts.  enable != 0 starts (or restarts from zero) the
  * accumulation: the G-buffer and phase-A kernels add the SM cycles every block (16x8 pixels) held its SM slot to one

@@ -427,7 +427,7 @@ int rstr_frame_set_pipeline(RstrFrame* f, int staged) {
     return rc;
 }
 
-// number of row bands the staged pipeline overlaps (1 = no overlap; default 4)
+// number of row bands the staged pipeline overlaps (1 = no overlap, the default)
 int rstr_frame_set_bands(RstrFrame* f, int bands) {
     if (!f || bands < 1 || bands > RS_MAX_BANDS) return fail(RSTR_ERR_ARG, "rstr_frame_set_bands: 1 .. 8");
     f->bands = bands;

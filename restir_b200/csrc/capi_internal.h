@@ -67,7 +67,7 @@ struct RstrFrame {
     int* queue = nullptr;
     int* shadeQueue = nullptr;     // staged phase A: compact list of shaded pixels
     rs::StagedStreams ss{};        // side streams / events of the banded staged pipeline (created on first use)
-    int bands = 4;                 // row bands of the staged pipeline (their queue kernels overlap the next band's k_primary)
+    int bands = 1;                 // row bands of the staged pipeline (bands > 1: a band's queue kernels overlap the next band's k_primary; measured slower)
     int staged = -1;               // phase A as the staged pipeline (kernels.cu): 1, as the single fused kernel: 0, by scene size: -1
     unsigned int* queueCount = nullptr;
     void* scratch = nullptr; size_t scratchBytes = 0;
