@@ -338,6 +338,11 @@ def run_b200(args):
     P = W * H
     sd = make_scene(spec, res)
     sc = rb.Scene.from_arrays(sd)
+    traced_tree = {"built": "host (binned SAH, bvh_fast.cpp)"}
+    if args.traced_tree != "host":
+        mode = 1 if args.traced_tree == "gpu-radix" else 0
+        sc.build_traced_gpu(mode)                # first call pays the allocations / cub set-up
+        traced_tree = {"built": "device (%s, bvh_gpu.cu)" % ("Morton radix tree" if mode else "PLOC"), "build_ms": sc.build_traced_gpu(mode)}
     base = rb.Camera.from_scene(sd)
     prm = rb.default_params(reuse=reuse, radius=radius)
     motion_rows = None
@@ -653,6 +658,8 @@ def run_b200(args):
             "rays_per_frame": {"primary": 2 * P, "shadow_upper_bound": shaded, "note": "2 primary rays per pixel (centre + jittered, one shared walk) + 1 shadow ray per shaded pixel whose reservoir weight is non-zero"},
             "halo_miss": halo_miss,
             "host_build_s": info.buildSeconds,
+            "traced_tree": traced_tree,
+            "build_id": rb.api.build_id(),
         }
         if world == 1 and not args.no_targets:
             # the north star's numeric targets, device-timed on the same box in the same run
@@ -729,6 +736,7 @@ def main():
     ap.add_argument("--split-exchange", action="store_true", help="N > 1: history reservoirs in a second exchange after phase B (A/B)")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: wait for the history-reservoir exchange at the end of the frame instead of under the next G-buffer")
     ap.add_argument("--render-halo", action="store_true", help="N > 1: every strip renders its G-buffer halo rows itself instead of receiving them from its neighbours")
+    ap.add_argument("--traced-tree", default="host", choices=["host", "gpu", "gpu-radix"], help="the tree the kernels trace: the host's binned-SAH build (default) or rebuilt on the device (rstr_scene_build_traced_gpu: PLOC, or the plain radix tree)")
     ap.add_argument("--quick", action="store_true", help="the B200 measurement only: no CPU baseline, no targets block, no reference CUDA timing (A/B runs)")
     args = ap.parse_args()
     if args.quick:

@@ -155,6 +155,9 @@ enum {
 };
 
 const char* rstr_last_error(void);
+/* identifies the build: first 12 hex digits of the SHA-1 over the library's sources (restir_b200/build.py), so that a
+ * measurement can be tied to the code that produced it */
+const char* rstr_build_id(void);
 /* binds the calling thread to a device (the reference pins device 0, preview.cpp:112) */
 int rstr_init(int device);
 void rstr_params_default(RstrParams*);
@@ -172,6 +175,13 @@ int rstr_scene_info(const RstrScene*, RstrSceneInfo*);
  * detected and re-traced with the reference-order walk.  1: every ray walks the reference tree in the reference's
  * order with its exact box predicate (validation mode, ~2x slower). */
 int rstr_scene_set_traversal(RstrScene*, int mode);
+/* SURVEY section 8 f3 (the role of BVHBuilder::build, bvh.cpp:10-131, for the tree that is TRACED): rebuilds the traced tree
+ * of the scene on the device and swaps it in; every frame of the scene traces it from then on.  mode 0: PLOC (Morton order,
+ * bottom-up merging of the nearest clusters by surface area, SAH leaf cut; ~ the host tree's quality); mode 1: the plain
+ * Morton radix tree (fastest build, slower to trace).  Results do not change: which hit a ray reports is decided per
+ * triangle; the reference-identical tree stays on the host for rstr_scene_read and for the
+ * visiting-rank table.  Synchronises the device.  *milliseconds (may be NULL): device time of the build. */
+int rstr_scene_build_traced_gpu(RstrScene*, int mode, float* milliseconds);
 /* pixels recomputed with the reference-order walk since the scene was created / last reset (instrumentation);
  * count[4] = {G-buffer pixels, ReSTIR phase-A pixels, PTDirect pixels, unused} */
 int rstr_scene_fallback_rays(RstrScene*, unsigned long long* count4, int reset);

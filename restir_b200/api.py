@@ -127,6 +127,7 @@ def lib() -> C.CDLL:
     L = C.CDLL(path)
     vp, ip, fp = C.c_void_p, C.c_int, C.c_float
     L.rstr_last_error.restype = C.c_char_p
+    L.rstr_build_id.restype = C.c_char_p
     L.rstr_init.argtypes = [ip]
     L.rstr_params_default.argtypes = [C.POINTER(RstrParams)]
     L.rstr_scene_create.argtypes = [C.POINTER(RstrSceneDesc), C.POINTER(vp)]
@@ -136,6 +137,7 @@ def lib() -> C.CDLL:
     L.rstr_scene_read.argtypes = [vp, ip, vp, C.c_size_t]
     L.rstr_scene_texture_info.argtypes = [vp, ip, vp, vp, vp]
     L.rstr_scene_set_traversal.argtypes = [vp, ip]
+    L.rstr_scene_build_traced_gpu.argtypes = [vp, ip, C.POINTER(C.c_float)]
     L.rstr_scene_fallback_rays.argtypes = [vp, C.POINTER(C.c_ulonglong), ip]
     L.rstr_camera_update.argtypes = [C.POINTER(RstrCamera)]
     L.rstr_camera_orbit.argtypes = [C.POINTER(RstrCamera), ip, fp, fp, fp, C.POINTER(RstrCamera)]
@@ -214,6 +216,10 @@ def default_params(reuse: int = REUSE_TEMPORAL, radius: float = 5.0, k: int = 5,
                    unbiased: bool = False) -> RstrParams:
     """restir.cu literals (32 candidates, cap 20, 5 neighbours, radius 5 px, one spatial pass) unless overridden."""
     return RstrParams(candidates, cap, k, radius, reuse, passes, 1 if unbiased else 0)
+
+
+def build_id() -> str:
+    return lib().rstr_build_id().decode()
 
 
 def launch_count() -> int:
@@ -301,6 +307,12 @@ class Scene:
     def set_traversal(self, exact: bool) -> None:
         """False (default): binned-SAH tree + rank tie-break; True: reference-order walk for every ray."""
         _check(lib().rstr_scene_set_traversal(self.h, 1 if exact else 0))
+
+    def build_traced_gpu(self, mode: int = 0) -> float:
+        """Rebuild the traced tree on the device; returns the device time of the build in ms."""
+        ms = C.c_float(0.0)
+        _check(lib().rstr_scene_build_traced_gpu(self.h, mode, C.byref(ms)))
+        return float(ms.value)
 
     def fallback_rays(self, reset: bool = True) -> dict:
         v = (C.c_ulonglong * 4)()

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 # RSTR_LIBNAME / RSTR_DEFINES: side-by-side experimental builds for A/B timing (scripts/gpu_ab.py); the default is the product
 LIB = os.path.join(HERE, os.environ.get("RSTR_LIBNAME", "librestir_b200.so"))
 EXTRA_DEFINES = [d for d in os.environ.get("RSTR_DEFINES", "").split() if d]
-SOURCES = ["capi.cu", "strip_group.cu", "kernels.cu", "scene_host.cpp", "scene_file.cpp", "bvh_fast.cpp", "image_io.cpp", "image_jpeg.cpp"]
+SOURCES = ["capi.cu", "strip_group.cu", "bvh_gpu.cu", "kernels.cu", "scene_host.cpp", "scene_file.cpp", "bvh_fast.cpp", "image_io.cpp", "image_jpeg.cpp"]
 HEADERS = ["kernels.h", "capi_internal.h", "device_types.h", "scene_host.h", "vecmath.h", os.path.join("..", "..", "include", "restir_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
@@ -31,6 +31,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+def build_id() -> str:
+    """SHA-1 over the library's sources and headers (rstr_build_id)."""
+    import hashlib
+
+    h = hashlib.sha1()
+    for s in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, s), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(EXTRA_DEFINES).encode() + os.environ.get("RSTR_FMAD", "false").encode())
+    return h.hexdigest()[:12]
+
+
 def nvcc_command(verbose: bool = False) -> list[str]:
     cmd = [
         NVCC, "-std=c++17", "-O3", "-shared",
@@ -42,6 +54,7 @@ def nvcc_command(verbose: bool = False) -> list[str]:
         "-o", LIB,
     ]
     cmd += EXTRA_DEFINES
+    cmd += ['-DRSTR_BUILD_ID="%s"' % build_id()]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -11,6 +11,7 @@
 // padded by a few ulps so that the FMA slab test stays conservative w.r.t. the exact triangle test) and fall back to
 // the reference-order walk only for the rays whose reference box test is not a conservative slab test (|d_a| > 1-1e-6,
 // bvh.h:91-123).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -39,14 +40,18 @@ struct Ref { FBox b; float c[3]; int prim; };
 
 struct FastBuilder {
     static const int NBINS = 32;
-    static const int MAX_LEAF = 4;
+    int MAX_LEAF = 4;             // RSTR_MAX_LEAF (1..8) / RSTR_LEAF_CI: development knobs for tree experiments (scripts/travsim.cpp)
+    float CI = 1.0f;
     static const int TASK_MIN = 4096;
     std::vector<Ref> refs;
     std::vector<FastNode>& nodes;
     std::vector<int>& order;
     std::atomic<int> maxDepth{0};
 
-    FastBuilder(std::vector<FastNode>& n, std::vector<int>& o) : nodes(n), order(o) {}
+    FastBuilder(std::vector<FastNode>& n, std::vector<int>& o) : nodes(n), order(o) {
+        if (const char* e = getenv("RSTR_MAX_LEAF")) MAX_LEAF = std::min(8, std::max(1, atoi(e)));
+        if (const char* e = getenv("RSTR_LEAF_CI")) CI = (float)atof(e);
+    }
 
     static int leafRef(int first, int count) { return (int)(0x80000000u | ((unsigned)(count - 1) << 27) | (unsigned)first); }
 
@@ -94,7 +99,7 @@ struct FastBuilder {
         // leaf when small and not worth splitting (traversal step ~ 1 triangle test)
         if (n <= MAX_LEAF) {
             float leafCost = (float)n * parentArea;
-            float splitCost = bestAxis < 0 ? FLT_MAX : 1.0f * parentArea + bestCost;
+            float splitCost = bestAxis < 0 ? FLT_MAX : CI * parentArea + bestCost;
             if (leafCost <= splitCost) return makeLeaf();
         }
         int mid;

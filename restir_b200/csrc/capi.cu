@@ -84,6 +84,8 @@ static void freeSceneDevice(RstrScene* sc) {
     sc->deviceBytes = 0;
 }
 
+static int ensureUploaded(RstrScene* sc);
+int rsEnsureUploaded(RstrScene* sc) { return ensureUploaded(sc); }
 static int ensureUploaded(RstrScene* sc) {
     if (sc->uploaded) return RSTR_OK;
     HostScene& hs = sc->hs;
@@ -128,6 +130,10 @@ static int ensureUploaded(RstrScene* sc) {
 extern "C" {
 
 const char* rstr_last_error(void) { return g_err.c_str(); }
+#ifndef RSTR_BUILD_ID
+#define RSTR_BUILD_ID "unknown"
+#endif
+const char* rstr_build_id(void) { return RSTR_BUILD_ID; }
 
 int rstr_init(int device) {
     int n = 0;

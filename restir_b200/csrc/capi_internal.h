@@ -33,6 +33,8 @@ struct RstrScene {
     size_t deviceBytes = 0;
     bool uploaded = false;      // set only after every device array exists and DevScene is filled
     int traversalMode = RS_TRAVERSAL_FAST;
+    int gpuTreeDepth = 0;       // > 0: the traced tree on the device was built by rstr_scene_build_traced_gpu (bvh_gpu.cu)
+    float gpuTreeMs = 0.f;
 };
 
 // Planes that a neighbouring strip reads (halo rows) live in ONE device allocation, the "exchange slab": a 256-byte header of
@@ -92,3 +94,4 @@ struct RstrFrame {
 rs::FrameDev rsToFrameDev(const RstrFrame* f, int rowLo, int rowHi);
 extern "C" int rsFlushGBuffer(RstrFrame* f);     // launches a G-buffer render that rstr_gbuffer_render deferred
 extern "C" int rsEnsureTemp2(RstrFrame* f);
+int rsEnsureUploaded(RstrScene* sc);          // uploads the host scene on first use (capi.cu)

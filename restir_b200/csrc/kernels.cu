@@ -353,20 +353,24 @@ RS_D bool leafBox(const RayT& r, const Tri& t, float& tBox) {
     return boxHit(r, gmin(gmin(t.v0, t.v1), t.v2), gmax(gmax(t.v0, t.v1), t.v2), tBox);
 }
 
-// near-tie candidates of one ray: RS_MAX_TIES {triangle, distance, error bound} records per thread in shared memory, [entry][thread]
+// near-tie candidates of one ray: RS_MAX_TIES {triangle, distance, error bound} records per thread in shared memory, [entry][thread],
+// followed by the ray's direction (three more rows): the walk needs it only at leaves, so it does not occupy registers
+#define RS_TIE_ROWS (3 * RS_MAX_TIES + 3)
 struct TieStore {
     float* base;       // this thread's column of [field: triangle, distance, error][entry][thread]; one pointer, 2 registers
     RS_D int& fi(int k) const { return *(int*)(base + k * RS_BLOCK); }
     RS_D float& d(int k) const { return base[(RS_MAX_TIES + k) * RS_BLOCK]; }
     RS_D float& e(int k) const { return base[(2 * RS_MAX_TIES + k) * RS_BLOCK]; }
+    RS_D void setDir(f3 v) const { base[3 * RS_MAX_TIES * RS_BLOCK] = v.x; base[(3 * RS_MAX_TIES + 1) * RS_BLOCK] = v.y; base[(3 * RS_MAX_TIES + 2) * RS_BLOCK] = v.z; }
+    RS_D f3 dir() const { return mk3(base[3 * RS_MAX_TIES * RS_BLOCK], base[(3 * RS_MAX_TIES + 1) * RS_BLOCK], base[(3 * RS_MAX_TIES + 2) * RS_BLOCK]); }
 };
 RS_D bool nearTie(float da, float ea, float db, float eb) { return fabsf(da - db) <= ea + eb + 1e-6f * fmaxf(da, db); }
 
-// Running result of one closest-hit ray: 16 registers.  The slab test uses cinv / oi (explicit FMAs on the padded boxes
-// of the traced tree); everything that decides which triangle is reported (triHit, leafBox) uses o / d with the
-// reference's arithmetic.
+// Running result of one closest-hit ray of a packet: 11 registers.  The slab test uses cinv / oi (explicit FMAs on the padded
+// boxes of the traced tree); everything that decides which triangle is reported (triHit, leafBox) uses the ray's (o, d) with the
+// reference's arithmetic: o is the packet's common origin (the camera position: warp-uniform, never in per-thread
+// registers), d waits in the TieStore until a leaf is reached.
 struct PRay {
-    f3 o, d;
     f3 cinv, oi;      // 1 / d with |d| kept >= 1e-20 (a zero component would give inf * 0 = NaN), -o / d
     float bestD;      // distance of the best hit so far (FLT_MAX: none)
     float bestErr;    // its error bound (triDistError)
@@ -375,9 +379,9 @@ struct PRay {
     int nt;           // near-tie candidates in the TieStore; -1: more than RS_MAX_TIES (undecided)
 };
 
-RS_D PRay prayBegin(f3 o, f3 d, bool active) {
+RS_D PRay prayBegin(f3 o, f3 d, bool active, const TieStore& ts) {
     PRay p;
-    p.o = o; p.d = d;
+    ts.setDir(d);
     float dx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
     float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
     float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
@@ -394,6 +398,16 @@ RS_D bool slabHitP(const PRay& p, float lx, float ly, float lz, float hx, float 
     float z0 = __fmaf_rn(lz, p.cinv.z, p.oi.z), z1 = __fmaf_rn(hz, p.cinv.z, p.oi.z);
     tEntry = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.f));
     float tExit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), p.limit));
+    return tEntry <= tExit;
+}
+// the same test when the caller already knows which plane of every slab the ray enters through (n*) and leaves through (f*):
+// the same products, so the same tEntry / tExit bit for bit, without the six min / max that sort them
+RS_D bool slabHitSorted(const PRay& p, float nx, float ny, float nz, float fx, float fy, float fz, float& tEntry) {
+    float x0 = __fmaf_rn(nx, p.cinv.x, p.oi.x), x1 = __fmaf_rn(fx, p.cinv.x, p.oi.x);
+    float y0 = __fmaf_rn(ny, p.cinv.y, p.oi.y), y1 = __fmaf_rn(fy, p.cinv.y, p.oi.y);
+    float z0 = __fmaf_rn(nz, p.cinv.z, p.oi.z), z1 = __fmaf_rn(fz, p.cinv.z, p.oi.z);
+    tEntry = fmaxf(fmaxf(x0, y0), fmaxf(z0, 0.f));
+    float tExit = fminf(fminf(x1, y1), fminf(z1, p.limit));
     return tEntry <= tExit;
 }
 
@@ -441,13 +455,13 @@ __device__ __noinline__ BestState prayAccept(f3 o, f3 dir, BestState p, const Ti
 }
 
 // one triangle of a visited leaf offered to a ray's running result
-RS_D void prayOffer(PRay& p, const TieStore& ts, const Tri& t, int fi) {
+RS_D void prayOffer(PRay& p, f3 o, f3 dir, const TieStore& ts, const Tri& t, int fi) {
     float bx, by, d;
-    if (!triHitOD(p.o, p.d, t.v0, t.v1, t.v2, bx, by, d)) return;
+    if (!triHitOD(o, dir, t.v0, t.v1, t.v2, bx, by, d)) return;
     if (!(d <= p.limit)) return;
     BestState b;
     b.bestD = p.bestD; b.bestErr = p.bestErr; b.limit = p.limit; b.bestFi = p.bestFi; b.nt = p.nt;
-    b = prayAccept(p.o, p.d, b, ts, t.v0, t.v1, t.v2, fi, d);
+    b = prayAccept(o, dir, b, ts, t.v0, t.v1, t.v2, fi, d);
     p.bestD = b.bestD; p.bestErr = b.bestErr; p.limit = b.limit; p.bestFi = b.bestFi; p.nt = b.nt;
 }
 
@@ -483,16 +497,16 @@ __device__ __noinline__ Hit prayReplay(const DevScene& s, f3 o, f3 dir, int best
 }
 
 // false = undecided (more mutually near hits than RS_MAX_TIES + 1)
-RS_D bool prayResolve(const DevScene& s, const PRay& p, const TieStore& ts, Hit& h) {
+RS_D bool prayResolve(const DevScene& s, f3 o, f3 dir, const PRay& p, const TieStore& ts, Hit& h) {
     h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
     if (p.bestFi < 0) return true;
     if (p.nt < 0) return false;
     if (p.nt > 0) {
-        h = prayReplay(s, p.o, p.d, p.bestFi, p.nt, ts);
+        h = prayReplay(s, o, dir, p.bestFi, p.nt, ts);
         return true;
     }
     Tri t = loadTriFast(s, p.bestFi);
-    triHitOD(p.o, p.d, t.v0, t.v1, t.v2, h.bx, h.by, h.t);          // same arithmetic as during the walk: h.t == bestD
+    triHitOD(o, dir, t.v0, t.v1, t.v2, h.bx, h.by, h.t);            // same arithmetic as during the walk: h.t == bestD
     h.prim = t.prim;
     return true;
 }
@@ -507,14 +521,42 @@ RS_D bool prayResolve(const DevScene& s, const PRay& p, const TieStore& ts, Hit&
 // rays of a tile are so coherent that the union of their walks is barely longer than the longest of them, while 32
 // independent walks in lockstep cost about twice the longest (divergence between descending and leaf-testing lanes):
 // scripts/travsim.cpp, config4 at 1080p: 106 node steps per warp against 191, with every lane busy instead of 10.6 of 32.
+// The warp's stack lives in shared memory and is addressed through ONE 32-bit shared-space cursor (8-byte entries {node, entry
+// distance bits}); every lane stores the same entry (same value, same address).
+RS_D void wsPush(unsigned& cursor, int ref, unsigned key) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(cursor), "r"(ref), "r"(key) : "memory");
+    cursor += 8;
+}
+// next stacked node that is not beyond every lane's limit, or RS_DONE
+RS_D int wsPop(unsigned& cursor, unsigned base, float wlimit) {
+    while (cursor != base) {
+        cursor -= 8;
+        int ref;
+        unsigned key;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ref), "=r"(key) : "r"(cursor) : "memory");
+        if (__uint_as_float(key) <= wlimit) return ref;
+    }
+    return RS_DONE;
+}
 template <bool TWO>
-RS_D void packetWalk(const DevScene& s, PRay& a, PRay& b, const TieStore& ta, const TieStore& tb, int2* wst) {
+RS_D void packetWalk(const DevScene& s, f3 o, PRay& a, PRay& b, const TieStore& ta, const TieStore& tb, int2* wst) {
     const unsigned FULL = 0xffffffffu;
-    int sp = 0;
+    const unsigned wbase = (unsigned)__cvta_generic_to_shared(wst);
+    unsigned wsp = wbase;
     float tA, tB;
     bool hit = slabHitP(a, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], tA);
     if (TWO) hit |= slabHitP(b, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], tB);
     int cur = __any_sync(FULL, hit) ? s.fastRoot : RS_DONE;
+    // Rays of a tile nearly always share the signs of their direction components: then the entry / exit plane of every slab
+    // is known per WARP (three uniform selects per box instead of six min / max per ray and box).  Lanes without a ray never
+    // hit whatever the planes (limit < 0), so only the lanes with rays have to agree.
+    int oct = (a.cinv.x < 0.f ? 1 : 0) | (a.cinv.y < 0.f ? 2 : 0) | (a.cinv.z < 0.f ? 4 : 0);
+    const unsigned have = __ballot_sync(FULL, a.limit >= 0.f);
+    const int oct0 = __shfl_sync(FULL, oct, have ? __ffs(have) - 1 : 0);
+    bool same = a.limit < 0.f || oct == oct0;
+    if (TWO) same = same && (b.limit < 0.f || ((b.cinv.x < 0.f ? 1 : 0) | (b.cinv.y < 0.f ? 2 : 0) | (b.cinv.z < 0.f ? 4 : 0)) == oct0);
+    const bool sorted = __all_sync(FULL, same);
+    const bool negX = (oct0 & 1) != 0, negY = (oct0 & 2) != 0, negZ = (oct0 & 4) != 0;
     float wlimit = FLT_MAX;                       // max of the lanes' limits (warp-uniform): culls popped entries
     for (;;) {
         while (cur >= 0 && cur != RS_DONE) {
@@ -523,47 +565,60 @@ RS_D void packetWalk(const DevScene& s, PRay& a, PRay& b, const TieStore& ta, co
             const float4 n0 = nA.lo, n1 = nA.hi, n2 = nB.lo;
             const int2 l = make_int2(__float_as_int(nB.hi.x), __float_as_int(nB.hi.y));
             float tL, tR, t2;
-            bool hL = slabHitP(a, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tL);
-            bool hR = slabHitP(a, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tR);
-            if (!hL) tL = FLT_MAX;
-            if (!hR) tR = FLT_MAX;
-            if (TWO) {
-                if (slabHitP(b, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, t2)) { hL = true; tL = fminf(tL, t2); }
-                if (slabHitP(b, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, t2)) { hR = true; tR = fminf(tR, t2); }
+            bool hL, hR;
+            if (sorted) {
+                const float lnx = negX ? n0.w : n0.x, lfx = negX ? n0.x : n0.w, lny = negY ? n1.x : n0.y, lfy = negY ? n0.y : n1.x;
+                const float lnz = negZ ? n1.y : n0.z, lfz = negZ ? n0.z : n1.y;
+                const float rnx = negX ? n2.y : n1.z, rfx = negX ? n1.z : n2.y, rny = negY ? n2.z : n1.w, rfy = negY ? n1.w : n2.z;
+                const float rnz = negZ ? n2.w : n2.x, rfz = negZ ? n2.x : n2.w;
+                hL = slabHitSorted(a, lnx, lny, lnz, lfx, lfy, lfz, tL);
+                hR = slabHitSorted(a, rnx, rny, rnz, rfx, rfy, rfz, tR);
+                if (!hL) tL = FLT_MAX;
+                if (!hR) tR = FLT_MAX;
+                if (TWO) {
+                    if (slabHitSorted(b, lnx, lny, lnz, lfx, lfy, lfz, t2)) { hL = true; tL = fminf(tL, t2); }
+                    if (slabHitSorted(b, rnx, rny, rnz, rfx, rfy, rfz, t2)) { hR = true; tR = fminf(tR, t2); }
+                }
+            } else {
+                hL = slabHitP(a, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tL);
+                hR = slabHitP(a, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tR);
+                if (!hL) tL = FLT_MAX;
+                if (!hR) tR = FLT_MAX;
+                if (TWO) {
+                    if (slabHitP(b, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, t2)) { hL = true; tL = fminf(tL, t2); }
+                    if (slabHitP(b, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, t2)) { hR = true; tR = fminf(tR, t2); }
+                }
             }
             const bool anyL = __any_sync(FULL, hL), anyR = __any_sync(FULL, hR);
             if (anyL && anyR) {
                 // entry distances are >= 0, so their bit patterns order like the floats
                 const unsigned kL = __reduce_min_sync(FULL, __float_as_uint(tL)), kR = __reduce_min_sync(FULL, __float_as_uint(tR));
                 const bool leftNear = kL <= kR;
-                wst[sp] = make_int2(leftNear ? l.y : l.x, (int)(leftNear ? kR : kL)); sp++;     // same value from every lane
+                wsPush(wsp, leftNear ? l.y : l.x, leftNear ? kR : kL);
                 cur = leftNear ? l.x : l.y;
             } else if (anyL) cur = l.x;
             else if (anyR) cur = l.y;
-            else {
-                cur = RS_DONE;
-                while (sp > 0) { --sp; const int2 e = wst[sp]; if (__int_as_float(e.y) <= wlimit) { cur = e.x; break; } }
-            }
+            else cur = wsPop(wsp, wbase, wlimit);
         }
         if (cur == RS_DONE) return;
         {
             const int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            const f3 da = ta.dir(), db = TWO ? tb.dir() : da;
             for (int i = 0; i < count; i++) {
                 const Tri t = loadTriFast(s, first + i);
-                prayOffer(a, ta, t, first + i);
-                if (TWO) prayOffer(b, tb, t, first + i);
+                prayOffer(a, o, da, ta, t, first + i);
+                if (TWO) prayOffer(b, o, db, tb, t, first + i);
             }
         }
         const float lim = TWO ? fmaxf(a.limit, b.limit) : a.limit;
         wlimit = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(lim, 0.f))));
-        cur = RS_DONE;
-        while (sp > 0) { --sp; const int2 e = wst[sp]; if (__int_as_float(e.y) <= wlimit) { cur = e.x; break; } }
+        cur = wsPop(wsp, wbase, wlimit);
     }
 }
 
 // shared memory of the packet walk for a block of RS_BLOCK threads: near-tie stores of NR rays per thread + one stack per warp
 #define RS_DECLARE_PACKET(name, NR)                                                 \
-    __shared__ float name##_ties[NR][3 * RS_MAX_TIES][RS_BLOCK];                    \
+    __shared__ float name##_ties[NR][RS_TIE_ROWS][RS_BLOCK];                            \
     __shared__ int2 name##_ws[RS_BLOCK / 32][RS_WSTACK];                            \
     TieStore name##_ta, name##_tb;                                                  \
     name##_ta.base = &name##_ties[0][0][threadIdx.x];                               \
@@ -636,6 +691,11 @@ RS_D void cameraRay(const CamDev& c, int x, int y, float rx, float ry, f3& o, f3
                right.z * dir.x + up.z * dir.y + view.z * dir.z);
     d = normalize(w);
     o = mk3(c.position[0], c.position[1], c.position[2]) + right * 0.f + up * 0.f;
+}
+// the origin cameraRay gives every ray (the same expression: warp-uniform, the packet walk keeps it out of per-thread registers)
+RS_D f3 cameraOrigin(const CamDev& c) {
+    f3 right = mk3(c.right[0], c.right[1], c.right[2]), up = mk3(c.up[0], c.up[1], c.up[2]);
+    return mk3(c.position[0], c.position[1], c.position[2]) + right * 0.f + up * 0.f;
 }
 
 // Camera::getRasterCoord (sceneStructs.h:23-46); float->int is cvt.rzi (saturating, NaN -> 0) as in the reference's kernel
@@ -891,11 +951,12 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GBUF) k_gbuffer(const __grid
     const bool active = pixelOf(f, x, y);
     f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
     if (active) cameraRay(cam, x, y, .5f, .5f, o, d);
-    PRay a = prayBegin(o, d, active);
-    packetWalk<false>(s, a, a, pk_ta, pk_ta, pk_wst);
+    const f3 oc = cameraOrigin(cam);
+    PRay a = prayBegin(oc, d, active, pk_ta);
+    packetWalk<false>(s, oc, a, a, pk_ta, pk_ta, pk_wst);
     if (active) {
         Hit h;
-        if (prayResolve(s, a, pk_ta, h)) gbufferFinish(s, f, lastCam, x, y, o, d, h);
+        if (prayResolve(s, oc, d, a, pk_ta, h)) gbufferFinish(s, f, lastCam, x, y, o, d, h);
         else enqueuePixel(f, x, y);
     }
     if (f.rowCost) accountBlock(f, &t0);
@@ -1208,11 +1269,12 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_RESTIR) k_restir_a(const __g
     rng.x = 1;
     f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
     if (active) jitteredRay(f, cam, looper, x, y, rng, o, d);
-    PRay a = prayBegin(o, d, active);
-    packetWalk<false>(s, a, a, pk_ta, pk_ta, pk_wst);
+    const f3 oc = cameraOrigin(cam);
+    PRay a = prayBegin(oc, d, active, pk_ta);
+    packetWalk<false>(s, oc, a, a, pk_ta, pk_ta, pk_wst);
     if (active) {
         Hit h;
-        if (!prayResolve(s, a, pk_ta, h) || !restirAAfterHit<false, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, d, h)) enqueuePixel(f, x, y);
+        if (!prayResolve(s, oc, d, a, pk_ta, h) || !restirAAfterHit<false, SPATIAL>(s, f, prm, iter, first, x, y, stack, rng, d, h)) enqueuePixel(f, x, y);
     }
     if (f.rowCost) accountBlock(f, &t0);
 }
@@ -1250,10 +1312,11 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_FUSED) k_gbuffer_restir_a(co
     Hit hC, hJ;
     bool ok;
     {
-        PRay a = prayBegin(oC, dC, active), b = prayBegin(oJ, dJ, active);
-        packetWalk<true>(s, a, b, pk_ta, pk_tb, pk_wst);
-        ok = prayResolve(s, a, pk_ta, hC);
-        ok = prayResolve(s, b, pk_tb, hJ) && ok;
+        const f3 oc = cameraOrigin(cam);
+        PRay a = prayBegin(oc, dC, active, pk_ta), b = prayBegin(oc, dJ, active, pk_tb);
+        packetWalk<true>(s, oc, a, b, pk_ta, pk_tb, pk_wst);
+        ok = prayResolve(s, oc, dC, a, pk_ta, hC);
+        ok = prayResolve(s, oc, dJ, b, pk_tb, hJ) && ok;
     }
     if (active) {
         if (ok) {
@@ -1345,10 +1408,11 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_PRIMARY) k_primary(const __g
     Hit hC, hJ;
     bool ok;
     {
-        PRay a = prayBegin(oC, dC, active), b = prayBegin(oJ, dJ, active);
-        packetWalk<true>(s, a, b, pk_ta, pk_tb, pk_wst);
-        ok = prayResolve(s, a, pk_ta, hC);
-        ok = prayResolve(s, b, pk_tb, hJ) && ok;
+        const f3 oc = cameraOrigin(cam);
+        PRay a = prayBegin(oc, dC, active, pk_ta), b = prayBegin(oc, dJ, active, pk_tb);
+        packetWalk<true>(s, oc, a, b, pk_ta, pk_tb, pk_wst);
+        ok = prayResolve(s, oc, dC, a, pk_ta, hC);
+        ok = prayResolve(s, oc, dJ, b, pk_tb, hJ) && ok;
     }
     bool shaded = false;
     if (active) {
@@ -1412,6 +1476,33 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_CAND) k_candidates(const __g
     if (f.rowCost) accountPixel(f, y, t0);
 }
 
+// any-hit test of one leaf of the traced tree with the reference's per-triangle criterion (scene.h:286-316 reduced as above)
+RS_D bool leafOccluded(const DevScene& s, const RayT& r, float dist, int ref) {
+    const int first = ref & 0x07ffffff, count = ((ref >> 27) & 7) + 1;
+    for (int i = 0; i < count; i++) {
+        const Tri t = loadTriFast(s, first + i);
+        float bx, by, d, tb;
+        if (triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist && leafBox(r, t, tb) && tb < dist) return true;
+    }
+    return false;
+}
+#ifndef RS_COOP_DRAIN
+#define RS_COOP_DRAIN 1       /* k_shadow: once the queue is empty the warp finishes its remaining rays together (below) */
+#endif
+#define RS_COOP_CAP (RS_SMEM_STACK * 32)
+
+#ifdef RS_SHADOW_STATS
+// development build only (RSTR_DEFINES=-DRS_SHADOW_STATS): steps per shadow ray as a log2 histogram [0..31], [32] rays, [33] steps,
+// [34] longest ray, [40] / [41] / [42]: globaltimer (ns) of the first warp that found the queue empty / the last warp's exit / start
+__device__ unsigned long long g_shadowStats[64];
+RS_D unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+RS_D void shadowRayDone(int steps) {
+    int b = 0;
+    while ((2 << b) <= steps && b < 31) b++;
+    atomicAdd(g_shadowStats + b, 1ull); atomicAdd(g_shadowStats + 32, 1ull); atomicAdd(g_shadowStats + 33, (unsigned long long)steps);
+    atomicMax(g_shadowStats + 34, (unsigned long long)steps);
+}
+#endif
 // DevScene::testOcclusion (scene.h:286-316) for every queued pixel whose reservoir has weight: occluded -> weight = 0
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f) {
     RS_DECLARE_REFSTACK(stack);
@@ -1427,8 +1518,15 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
     bool exhausted = false;                       // warp-uniform: the queue is empty
     r.o = r.d = r.inv = mk3(0.f); r.flags = 0; r.dim = r.lesser = 0;
     rf.inv = rf.oi = mk3(0.f);
+#ifdef RS_SHADOW_STATS
+    int steps = 0;
+    if (lane == 0) atomicMin(g_shadowStats + 42, gtimer());
+#endif
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, cur == RS_DONE);
+#ifdef RS_SHADOW_STATS
+        if (idle == FULL && exhausted && lane == 0) atomicMax(g_shadowStats + 41, gtimer());
+#endif
         if (idle == FULL && exhausted) break;
         if (!exhausted && (__popc(idle) >= RS_REFILL_MIN || idle == FULL)) {
             unsigned base = 0;
@@ -1436,6 +1534,9 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
             if (lane == leader) base = atomicAdd(f.shadeCount + 1, (unsigned)__popc(idle));
             base = __shfl_sync(FULL, base, leader);
             if (base >= n) exhausted = true;
+#ifdef RS_SHADOW_STATS
+            if (exhausted && lane == 0) atomicMin(g_shadowStats + 40, gtimer());
+#endif
             const unsigned i = base + __popc(idle & ((1u << lane) - 1u));
             if (cur == RS_DONE && i < n) {
                 const int index = f.shadeQueue[i];
@@ -1459,11 +1560,99 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
                         if (slabHit(rf, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], dist, tr)) {
                             cur = s.fastRoot; sp = 0;
                             if (f.rowCost) tRay = clock64();
+#ifdef RS_SHADOW_STATS
+                            steps = 0;
+#endif
                         }
                     }
                 }
             }
         }
+#if RS_COOP_DRAIN
+        // ---- The queue is empty: what is left in this warp is a handful of rays of very different lengths (a shadow ray takes 72
+        // node steps on average and up to ~500), and walked one ray per lane the warp would last as long as its longest ray
+        // with most lanes idle -- measured, the last 350 us of this kernel on every scene and strip.  Any-hit rays need no
+        // order, so the warp finishes them TOGETHER instead: every pending node of every remaining ray becomes an item
+        // {owner lane, node} of one warp-wide list (kept in the lanes' stack rows in shared memory), each round the lanes take
+        // 32 items, fetch the owner's ray by shuffle, test both children, append the children that are hit and test hit leaves
+        // at once.  The drain lasts as long as the deepest chain of dependent node fetches, not the longest ray.
+        if (exhausted) {
+            bool act = cur != RS_DONE;
+            const unsigned need = __reduce_add_sync(FULL, act ? (unsigned)sp + 1u : 0u);
+            if (need <= RS_COOP_CAP - 96) {
+                int* list = stack.sRef - lane;                                      // item p lives at list[(p >> 5) * RS_BLOCK + (p & 31)]
+                const unsigned lt = (1u << lane) - 1u;
+                unsigned cnt = 0, doneMask = 0;
+                const unsigned maxsp = __reduce_max_sync(FULL, act ? (unsigned)sp : 0u);
+                for (unsigned k = 0; k <= maxsp; k++) {                              // round k: every lane's k-th stacked entry; last round: its current node
+                    int ref = RS_DONE;
+                    if (act) {
+                        if (k < (unsigned)sp) ref = stack.ref((int)k);
+                        else if (k == maxsp) ref = cur;
+                    }
+                    __syncwarp();                                                    // row k has been read before items land in it
+                    bool occ = false;
+                    if (ref < 0) occ = leafOccluded(s, r, dist, ref);
+                    const bool push = ref >= 0 && ref != RS_DONE;
+                    const unsigned pm = __ballot_sync(FULL, push);
+                    if (push) { const unsigned p = cnt + __popc(pm & lt); list[(p >> 5) * RS_BLOCK + (p & 31)] = (int)(((unsigned)lane << 27) | (unsigned)ref); }
+                    cnt += __popc(pm);
+                    if (occ) { f.resvStage[li].weight = 0.f; act = false; }
+                    doneMask |= __ballot_sync(FULL, occ);
+                }
+                __syncwarp();
+                while (cnt) {
+                    const unsigned take = cnt > RS_COOP_CAP - 64 ? 1u : (cnt < 32u ? cnt : 32u);
+                    unsigned item = 0;
+                    bool valid = (unsigned)lane < take;
+                    if (valid) { const unsigned p = cnt - 1u - (unsigned)lane; item = (unsigned)list[(p >> 5) * RS_BLOCK + (p & 31)]; }
+                    cnt -= take;
+                    __syncwarp();
+                    const int owner = valid ? (int)(item >> 27) : lane;
+                    valid = valid && !((doneMask >> owner) & 1u);
+                    RayF of;
+                    of.inv.x = __shfl_sync(FULL, rf.inv.x, owner); of.inv.y = __shfl_sync(FULL, rf.inv.y, owner); of.inv.z = __shfl_sync(FULL, rf.inv.z, owner);
+                    of.oi.x = __shfl_sync(FULL, rf.oi.x, owner); of.oi.y = __shfl_sync(FULL, rf.oi.y, owner); of.oi.z = __shfl_sync(FULL, rf.oi.z, owner);
+                    const float od = __shfl_sync(FULL, dist, owner);
+                    int c0 = RS_DONE, c1 = RS_DONE;                                  // children that are hit
+                    if (valid) {
+                        const float4* np = s.fastNodes + 4 * (size_t)(item & 0x07ffffffu);
+                        const F8 nA = ldg256(np), nB = ldg256(np + 2);
+                        const float4 a = nA.lo, b = nA.hi, c = nB.lo;
+                        float tL, tR;
+                        if (slabHit(of, a.x, a.y, a.z, a.w, b.x, b.y, od, tL)) c0 = __float_as_int(nB.hi.x);
+                        if (slabHit(of, b.z, b.w, c.x, c.y, c.z, c.w, od, tR)) c1 = __float_as_int(nB.hi.y);
+                    }
+                    for (int side = 0; side < 2; side++) {
+                        const int ch = side ? c1 : c0;
+                        const bool push = ch >= 0 && ch != RS_DONE;
+                        const unsigned pm = __ballot_sync(FULL, push);
+                        if (push) { const unsigned p = cnt + __popc(pm & lt); list[(p >> 5) * RS_BLOCK + (p & 31)] = (int)(((unsigned)owner << 27) | (unsigned)ch); }
+                        cnt += __popc(pm);
+                    }
+                    bool occ = false;
+                    if (__any_sync(FULL, c0 < 0 || c1 < 0)) {
+                        f3 oo, dd;
+                        oo.x = __shfl_sync(FULL, r.o.x, owner); oo.y = __shfl_sync(FULL, r.o.y, owner); oo.z = __shfl_sync(FULL, r.o.z, owner);
+                        dd.x = __shfl_sync(FULL, r.d.x, owner); dd.y = __shfl_sync(FULL, r.d.y, owner); dd.z = __shfl_sync(FULL, r.d.z, owner);
+                        if (c0 < 0 || c1 < 0) {
+                            const RayT rr = makeRayT(oo, dd);
+                            if (c0 < 0) occ = leafOccluded(s, rr, od, c0);
+                            if (!occ && c1 < 0) occ = leafOccluded(s, rr, od, c1);
+                        }
+                    }
+                    const unsigned occBits = __reduce_or_sync(FULL, occ ? (1u << owner) : 0u);
+                    doneMask |= occBits;
+                    if ((occBits >> lane) & 1u) f.resvStage[li].weight = 0.f;         // this lane's own ray
+                    __syncwarp();
+                }
+#ifdef RS_SHADOW_STATS
+                if (lane == 0) atomicMax(g_shadowStats + 41, gtimer());
+#endif
+                break;
+            }
+        }
+#endif
         // Lanes at an internal node step; lanes that have reached a leaf WAIT until RS_LEAF_MIN of them are there (or nobody is
         // left to step): run lane by lane, the triangle tests -- half of this kernel's instructions -- executed with 1.5 of 32 lanes.
         const unsigned atLeaf = __ballot_sync(FULL, cur < 0);
@@ -1482,21 +1671,35 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
                 else if (hR) cur = l.y;
                 else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
                 if (f.rowCost && cur == RS_DONE) atomicAdd(f.rowCost + (rowY >> 3), (unsigned long long)((clock64() - tRay) / 24));
+#ifdef RS_SHADOW_STATS
+                steps++;
+                if (cur == RS_DONE) shadowRayDone(steps);
+#endif
             }
         } else if (cur < 0) {
-            const int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
-            bool occluded = false;
-            for (int i = 0; i < count && !occluded; i++) {
-                const Tri t = loadTriFast(s, first + i);
-                float bx, by, d, tb;
-                occluded = triHit(r, t.v0, t.v1, t.v2, bx, by, d) && d < dist && leafBox(r, t, tb) && tb < dist;
-            }
+            const bool occluded = leafOccluded(s, r, dist, cur);
             if (occluded) { f.resvStage[li].weight = 0.f; cur = RS_DONE; }
             else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
             if (f.rowCost && cur == RS_DONE) atomicAdd(f.rowCost + (rowY >> 3), (unsigned long long)((clock64() - tRay) / 24));
+#ifdef RS_SHADOW_STATS
+            steps++;
+            if (cur == RS_DONE) shadowRayDone(steps);
+#endif
         }
     }
 }
+#ifdef RS_SHADOW_STATS
+extern "C" int rstr_debug_shadow_stats(unsigned long long* out64, int reset) {
+    cudaDeviceSynchronize();
+    if (out64) cudaMemcpyFromSymbol(out64, g_shadowStats, sizeof g_shadowStats);
+    if (reset) {
+        unsigned long long z[64] = {};
+        z[40] = z[42] = ~0ull;
+        cudaMemcpyToSymbol(g_shadowStats, z, sizeof z);
+    }
+    return 0;
+}
+#endif
 
 template <bool SPATIAL>
 __global__ void __launch_bounds__(RS_BLOCK) k_temporal(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
@@ -1545,8 +1748,11 @@ __global__ void __launch_bounds__(RS_BLOCK) k_temporal_unb(const __grid_constant
     temporalAndStoreUnbiased<SPATIAL>(s, f, prm, iter, first, li, index, sp, R, rng, stack);
 }
 
+#ifndef RS_SPATIAL_GATHER_TOGETHER
+#define RS_SPATIAL_GATHER_TOGETHER 1
+#endif
 // restir.cu:47-85 (+ mathUtil.h:128-132 toConcentricDisk)
-RS_D Resv findSpatial(const FrameDev& f, const ResvD* src, int x, int y, size_t li, float rx, float ry, float radius) {
+RS_D Resv findSpatial(const FrameDev& f, const ResvD* src, int x, int y, int ownMat, float4 g, float rx, float ry, float radius) {
     float rr = sqrtf(rx);
     float theta = ry * RS_PI * 2.0f;
     float px_ = cosf(theta) * rr * radius, py_ = sinf(theta) * rr * radius;
@@ -1555,12 +1761,26 @@ RS_D Resv findSpatial(const FrameDev& f, const ResvD* src, int x, int y, size_t 
     if (px < 0 || px >= f.W || py < 0 || py >= f.H || (px == x && py == y)) return emptyResv();
     if (!rowResident(f, py)) { atomicAdd(f.haloMiss, 1u); return emptyResv(); }
     size_t pli = planeIndex(f, px, py);
-    if (f.matId[0][pli] != f.matId[0][li]) return emptyResv();
-    float4 g = f.geom[0][li], pg = f.geom[0][pli];
+#if RS_SPATIAL_GATHER_TOGETHER
+    // The neighbour's material id, geometry record and reservoir are requested TOGETHER (three independent loads in flight)
+    // instead of one after the other behind the two rejection tests: the next neighbour cannot be drawn before this one
+    // is decided (a rejected try draws no sample1D, restir.cu:93-99, so the RNG stream -- and the next position -- depends
+    // on it), which makes the chain of dependent L2 round trips per try what bounds this kernel, not its bytes.
+    const int pm = f.matId[0][pli];
+    const float4 pg = f.geom[0][pli];
+    const Resv N = loadResv(src + pli);
+    if (pm != ownMat) return emptyResv();
+    bool diff = dot(mk3(g.x, g.y, g.z), mk3(pg.x, pg.y, pg.z)) < .9f;
+    if (fabsf(g.w - pg.w) > g.w * .1f) diff = true;
+    return diff ? emptyResv() : N;
+#else
+    if (f.matId[0][pli] != ownMat) return emptyResv();
+    float4 pg = f.geom[0][pli];
     bool diff = dot(mk3(g.x, g.y, g.z), mk3(pg.x, pg.y, pg.z)) < .9f;
     if (fabsf(g.w - pg.w) > g.w * .1f) diff = true;
     if (diff) return emptyResv();
     return loadResv(src + pli);
+#endif
 }
 
 // One spatial pass.  pass 1 = restir.cu:196-199; passes 2.. = the commented-out block restir.cu:201-209
@@ -1586,9 +1806,11 @@ __global__ void __launch_bounds__(128) k_restir_b(const __grid_constant__ DevSce
     Resv R = loadResv(src + li);
     const Resv published = R;
     Resv S = emptyResv();                                                            // restir.cu:87-100
+    const int ownMat = f.matId[0][li];
+    const float4 ownGeom = f.geom[0][li];
     for (int i = 0; i < prm.numSpatial; i++) {
         float rx = rng.next(), ry = rng.next();
-        Resv N = findSpatial(f, src, x, y, li, rx, ry, prm.spatialRadius);
+        Resv N = findSpatial(f, src, x, y, ownMat, ownGeom, rx, ry, prm.spatialRadius);
         if (!resvInvalid(N)) resvMerge(S, N, rng.next());
     }
     if (pass == 1) {
@@ -1794,11 +2016,12 @@ __global__ void __launch_bounds__(RS_BLOCK) k_ptdirect(const __grid_constant__ D
     rng.x = 1;
     f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
     if (active) jitteredRay(f, cam, looper, x, y, rng, o, d);
-    PRay a = prayBegin(o, d, active);
-    packetWalk<false>(s, a, a, pk_ta, pk_ta, pk_wst);
+    const f3 oc = cameraOrigin(cam);
+    PRay a = prayBegin(oc, d, active, pk_ta);
+    packetWalk<false>(s, oc, a, a, pk_ta, pk_ta, pk_wst);
     if (active) {
         Hit h;
-        if (!prayResolve(s, a, pk_ta, h) || !ptdirectAfterHit<false>(s, f, iter, x, y, stack, rng, d, h)) enqueuePixel(f, x, y);
+        if (!prayResolve(s, oc, d, a, pk_ta, h) || !ptdirectAfterHit<false>(s, f, iter, x, y, stack, rng, d, h)) enqueuePixel(f, x, y);
     }
 }
 __global__ void __launch_bounds__(RS_BLOCK) k_ptdirect_exact(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,

@@ -230,6 +230,61 @@ static void simPacket(Lane2* L, int n, Stats& s) {
     s.laneNodeSteps += s.warpNodeSteps * 0; s.warps++;
 }
 
+
+// warp packet driven by the TILE FRUSTUM: a node's child is entered when its box touches the frustum of the 8x4-pixel tile
+// (4 side planes through the eye, p-vertex test) and is not beyond every lane's limit; leaf children are optionally confirmed
+// by the lanes' own slab tests before their triangles are offered.  laneNodeSteps counts the confirm tests.
+struct Frustum { float n[4][3], view[3], o[3]; };
+static inline bool frustumBox(const Frustum& F, const float* lo, const float* hi, float limit, float& nearD) {
+    for (int p = 0; p < 4; p++) {
+        float d = 0;
+        for (int a = 0; a < 3; a++) d += F.n[p][a] * ((F.n[p][a] > 0 ? hi[a] : lo[a]) - F.o[a]);
+        if (d < -1e-4f) return false;
+    }
+    float fd = 0, nd = 0;
+    for (int a = 0; a < 3; a++) { fd += F.view[a] * ((F.view[a] > 0 ? hi[a] : lo[a]) - F.o[a]); nd += F.view[a] * ((F.view[a] > 0 ? lo[a] : hi[a]) - F.o[a]); }
+    if (fd < 0) return false;
+    nearD = fmaxf(nd, 0.f);
+    return nearD <= limit;
+}
+static void simFrustum(Lane2* L, int n, const Frustum& F, bool confirm, Stats& s) {
+    for (int i = 0; i < n; i++) laneBegin(L[i]);
+    static thread_local int stack[256]; static thread_local float stackT[256];
+    int sp = 0, cur = root;
+    auto limitAll = [&]() { float m = 0; for (int i = 0; i < n; i++) m = fmaxf(m, laneLimit(L[i])); return m; };
+    auto confirmLeaf = [&](const float* lo, const float* hi) {
+        s.laneNodeSteps++;
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < L[i].nr; k++) { float t; if (slab(L[i].r[k], lo, hi, L[i].best[k], t)) return true; }
+        return false;
+    };
+    for (;;) {
+        while (cur >= 0 && cur != DONE) {
+            const Node& nd = nodes[cur];
+            s.warpNodeSteps++;
+            float lim = limitAll();
+            float tL = 0, tR = 0;
+            bool hL = frustumBox(F, nd.lmin, nd.lmax, lim, tL), hR = frustumBox(F, nd.rmin, nd.rmax, lim, tR);
+            if (confirm) {
+                if (hL && nd.left < 0) hL = confirmLeaf(nd.lmin, nd.lmax);
+                if (hR && nd.right < 0) hR = confirmLeaf(nd.rmin, nd.rmax);
+            }
+            if (hL && hR) { bool ln = tL <= tR; stack[sp] = ln ? nd.right : nd.left; stackT[sp] = ln ? tR : tL; sp++; cur = ln ? nd.left : nd.right; }
+            else if (hL) cur = nd.left;
+            else if (hR) cur = nd.right;
+            else { cur = DONE; while (sp > 0) { --sp; if (stackT[sp] <= lim) { cur = stack[sp]; break; } } }
+        }
+        if (cur == DONE) break;
+        int f = leafFirst(cur), c = leafCount(cur);
+        for (int j = 0; j < c; j++)
+            for (int i = 0; i < n; i++)
+                for (int k = 0; k < L[i].nr; k++) { float d; if (triHit(L[i].r[k], tris[f + j], d) && d < L[i].best[k]) L[i].best[k] = d; }
+        s.warpTriSteps += c;
+        cur = DONE; float lim = limitAll(); while (sp > 0) { --sp; if (stackT[sp] <= lim) { cur = stack[sp]; break; } }
+    }
+    s.warps++;
+}
+
 // per-lane wide-tree walk (sorted children), lockstep while-while
 struct LaneW { Ray r[2]; int nr; float best[2]; int stack[256]; float stackT[256]; int sp, cur; long nodeSteps, triSteps; };
 static bool laneWNode(LaneW& L) {
@@ -302,14 +357,14 @@ int main(int argc, char** argv) {
         return makeRay(cam.pos, d);
     };
     const int TW = 8, TH = 4;
-    Stats sSingle, sPair, sPacket, sPacketPair, sW4, sW8, sW4pair, sW8pair, sSingle16, sPairSub, sIfSingle, sIfPair, sShWW, sShIf, sShPacket;
+    Stats sSingle, sPair, sPacket, sPacketPair, sW4, sW8, sW4pair, sW8pair, sSingle16, sPairSub, sIfSingle, sIfPair, sShWW, sShIf, sShPacket, sFr, sFrC;
     std::vector<int> emit;
     for (int i = 0; i < (int)tris.size(); i++) if (tris[i].matId >= 6) emit.push_back(i);
     printf("emitters %zu\n", emit.size());
     int tilesX = W / TW, tilesY = H / TH;
 #pragma omp parallel
     {
-        Stats a, b, c, d, e, f, g, h, i16, ia, ib, sw, si, sp_;
+        Stats a, b, c, d, e, f, g, h, i16, ia, ib, sw, si, sp_, fr, frc, d2_;
         std::vector<Lane2> L(32); std::vector<LaneW> LW(32);
 #pragma omp for schedule(dynamic, 8)
         for (int ty = 0; ty < tilesY; ty += stride)
@@ -327,6 +382,25 @@ int main(int argc, char** argv) {
                 for (int l = 0; l < 32; l++) { L[l].nr = 2; L[l].r[0] = rc[l]; L[l].r[1] = rj[l]; }
                 simWhileWhile(L.data(), 32, b);
                 simPacket(L.data(), 32, d);
+                {
+                    Frustum F;
+                    memcpy(F.o, cam.pos, 12); memcpy(F.view, cam.view, 12);
+                    Ray c00 = makeCamRay(tx * TW, ty * TH, 0, 0), c10 = makeCamRay(tx * TW + TW, ty * TH, 0, 0), c01 = makeCamRay(tx * TW, ty * TH + TH, 0, 0), c11 = makeCamRay(tx * TW + TW, ty * TH + TH, 0, 0);
+                    const Ray* cs[5] = {&c00, &c10, &c11, &c01, &c00};
+                    Ray cc = makeCamRay(tx * TW + TW / 2, ty * TH + TH / 2, 0, 0);
+                    for (int p = 0; p < 4; p++) {
+                        const float* u = cs[p]->d; const float* v = cs[p + 1]->d;
+                        float nn[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+                        float l = 1.f / sqrtf(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+                        float sgn = (nn[0] * cc.d[0] + nn[1] * cc.d[1] + nn[2] * cc.d[2]) > 0 ? l : -l;
+                        for (int a2 = 0; a2 < 3; a2++) F.n[p][a2] = nn[a2] * sgn;
+                    }
+                    simFrustum(L.data(), 32, F, false, fr);
+                    float chk[32]; for (int l = 0; l < 32; l++) chk[l] = L[l].best[0] + L[l].best[1];
+                    simFrustum(L.data(), 32, F, true, frc);
+                    simPacket(L.data(), 32, d2_);
+                    for (int l = 0; l < 32; l++) if (chk[l] != L[l].best[0] + L[l].best[1]) { fprintf(stderr, "frustum walk result differs\n"); exit(2); }
+                }
                 simIfIf(L.data(), 32, ib);
                 for (int l = 0; l < 32; l++) { L[l].nr = 1; L[l].r[0] = rc[l]; }
                 simIfIf(L.data(), 32, ia);
@@ -383,7 +457,7 @@ int main(int argc, char** argv) {
 #pragma omp critical
         {
             auto add = [](Stats& t, const Stats& s) { t.warpNodeSteps += s.warpNodeSteps; t.warpTriSteps += s.warpTriSteps; t.laneNodeSteps += s.laneNodeSteps; t.laneTriSteps += s.laneTriSteps; t.warps += s.warps; t.maxLaneNode += s.maxLaneNode; };
-            add(sIfSingle, ia); add(sIfPair, ib); add(sShWW, sw); add(sShIf, si); add(sShPacket, sp_);
+            add(sFr, fr); add(sFrC, frc); add(sIfSingle, ia); add(sIfPair, ib); add(sShWW, sw); add(sShIf, si); add(sShPacket, sp_);
             add(sSingle, a); add(sPair, b); add(sPacket, c); add(sPacketPair, d); add(sW4, e); add(sW8, f); add(sW4pair, g); add(sW8pair, h);
         }
     }
@@ -396,6 +470,9 @@ int main(int argc, char** argv) {
     show("bvh2 while-while, pair walk", sPair);
     show("bvh2 warp packet, centre ray", sPacket);
     show("bvh2 warp packet, pair", sPacketPair);
+    show("bvh2 frustum packet, pair", sFr);
+    show("bvh2 frustum packet + leaf confirm", sFrC);
+    printf("  leaf confirm tests per warp: %.1f\n", sFrC.laneNodeSteps / sFrC.warps);
     show("bvh4 while-while, centre ray", sW4);
     show("bvh8 while-while, centre ray", sW8);
     show("bvh4 while-while, pair walk", sW4pair);
