@@ -364,6 +364,26 @@ int rstr_strip_group_wait_host(RstrStripGroup*, int slot);
 int rstr_strip_group_error(RstrStripGroup*, int* flag);
 int rstr_strip_group_destroy(RstrStripGroup*);
 
+/* ---- the reference's image-space filters (denoiser.h:14-73, denoiser.cu:25-567).  The reference creates them
+ * (main.cpp:78-80) and exposes their knobs in its GUI (preview.cpp:253-287) but never calls them from runCuda; here they are
+ * applied to a full frame's radiance plane (devDirectIllum) with the frame's current G-buffer.
+ *   RSTR_DENOISER_EAW   LeveledEAWFilter: five edge-avoiding a-trous wavelet passes (strides 1, 2, 4, 8, 16; sigmas 64 / .2 / 1)
+ *   RSTR_DENOISER_SVGF  SpatioTemporalFilter: re-projected exponential history of colour and luminance moments, variance
+ *                       estimate, five variance-guided a-trous passes (sigmas 4 / 128 / 1); the level-0 result feeds the history */
+typedef struct RstrDenoiser RstrDenoiser;
+enum { RSTR_DENOISER_EAW = 1, RSTR_DENOISER_SVGF = 2 };
+int rstr_denoiser_create(RstrFrame* fullFrame, int kind, RstrDenoiser**);          /* LeveledEAWFilter::create / SpatioTemporalFilter::create */
+int rstr_denoiser_destroy(RstrDenoiser*);                                          /* ...::destroy */
+int rstr_denoiser_set_sigmas(RstrDenoiser*, float sigLumin, float sigNormal, float sigDepth);   /* EAWaveletFilter's members (the GUI sliders) */
+/* ...::filter(devColorOut, devColorIn = the frame's radiance, gBuffer, cam): after rstr_restir_direct / rstr_pathtrace_direct and
+ * before rstr_gbuffer_update of the same frame */
+int rstr_denoiser_filter(RstrDenoiser*, const RstrCamera*);
+int rstr_denoiser_next_frame(RstrDenoiser*);                                       /* SpatioTemporalFilter::nextFrame */
+int rstr_denoiser_modulate_albedo(RstrDenoiser*);                                  /* modulateAlbedo(devColorOut, gBuffer) */
+int rstr_denoiser_add_image(RstrDenoiser* a, const RstrDenoiser* b);               /* addImage(a.devColorOut, b.devColorOut) */
+/* devColorOut as W x H x 3 floats (and, SVGF, the filtered variance as W x H floats; may be NULL) */
+int rstr_denoiser_read(RstrDenoiser*, float* rgb, float* variance);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,18 @@ class Oracle:
         L.orc_last_trace_stats.argtypes = [vp, vp, vp, vp]
         L.orc_alias_build.restype = fp
         L.orc_alias_build.argtypes = [ip, vp, vp]
+        if kind == "port":            # the image-space filters are restated in the port only (denoiser.cu's kernels cannot be built by g++)
+            L.orc_denoiser_create.restype = vp
+            L.orc_denoiser_create.argtypes = [vp, ip]
+            L.orc_denoiser_destroy.argtypes = [vp]
+            L.orc_denoiser_set_sigmas.argtypes = [vp, fp, fp, fp]
+            L.orc_denoiser_filter.argtypes = [vp, C.POINTER(OrcCamera)]
+            L.orc_denoiser_next_frame.argtypes = [vp]
+            L.orc_denoiser_modulate_albedo.argtypes = [vp]
+            L.orc_denoiser_color.restype = vp
+            L.orc_denoiser_color.argtypes = [vp]
+            L.orc_denoiser_variance.restype = vp
+            L.orc_denoiser_variance.argtypes = [vp]
         if kind == "reference":
             L.ref_scene_load_file.restype = vp
             L.ref_scene_load_file.argtypes = [C.c_char_p]
@@ -293,6 +305,36 @@ class OracleFrame:
         if name == "depth":
             return Oracle._view(ptr, np.float32, (P,))
         return Oracle._view(ptr, RESERVOIR_DTYPE, (P,))
+
+
+class OracleDenoiser:
+    """LeveledEAWFilter ("eaw") / SpatioTemporalFilter ("svgf") of denoiser.h on an oracle frame (port only)."""
+
+    def __init__(self, frame: OracleFrame, kind: str = "eaw"):
+        self.frame, self.lib = frame, frame.lib
+        self.d = self.lib.orc_denoiser_create(frame.f, {"eaw": 1, "svgf": 2}[kind])
+
+    def close(self):
+        if self.d:
+            self.lib.orc_denoiser_destroy(self.d)
+            self.d = None
+
+    def set_sigmas(self, lumin, normal, depth):
+        self.lib.orc_denoiser_set_sigmas(self.d, lumin, normal, depth)
+
+    def filter(self, cam):
+        self.lib.orc_denoiser_filter(self.d, C.byref(cam))
+
+    def next_frame(self):
+        self.lib.orc_denoiser_next_frame(self.d)
+
+    def modulate_albedo(self):
+        self.lib.orc_denoiser_modulate_albedo(self.d)
+
+    def read(self, variance: bool = False):
+        P = self.frame.w * self.frame.h
+        rgb = Oracle._view(self.lib.orc_denoiser_color(self.d), np.float32, (P, 3))
+        return (rgb, Oracle._view(self.lib.orc_denoiser_variance(self.d), np.float32, (P,))) if variance else rgb
 
 
 def default_params(reuse: int = 0, radius: float = 5.0, k: int = 5, cap: int = 20, candidates: int = 32, passes: int = 1, unbiased: bool = False) -> OrcParams:

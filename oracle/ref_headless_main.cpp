@@ -8,6 +8,9 @@
  * runCuda() (main.cpp:146-185) without GL: fixed animation clock t_k = k * animateSpeed / 60.
  *
  *   ref_headless <scene.txt> <frames> <warmup> <reuse 0..3> [dump_prefix dump_frame]
+ * With REF_DENOISE=1 in the environment the reference's own filters (denoiser.cu, linked unmodified) run on every frame's
+ * devDirectIllum as well -- SpatioTemporalFilter::filter + nextFrame each frame, LeveledEAWFilter::filter on the dump frame --
+ * outside the timed region, and their images are dumped too (eaw.bin, svgf.bin, svgf_var.bin).
  * prints one JSON line: mean ms/frame of GBuffer::render + ReSTIRDirect (CUDA events; the reference's device-wide
  * sync after every launch, cudaUtil.h:15, is left in as shipped).
  */
@@ -19,6 +22,7 @@
 #include "scene.h"
 #include "gbuffer.h"
 #include "restir.h"
+#include "denoiser.h"
 
 extern Reservoir<DirectLiSample>* devLastDirectReservoir;   /* restir.cu:9, made extern by build_ref_cuda.sh */
 
@@ -71,6 +75,18 @@ int main(int argc, char** argv) {
     GBuffer gBuffer;
     gBuffer.create(w, h);
     ReSTIRInit();
+    const bool denoise = getenv("REF_DENOISE") != nullptr;
+    LeveledEAWFilter eawFilter;                                             /* main.cpp:33-34, 78-79 */
+    SpatioTemporalFilter svgfFilter;
+    glm::vec3 *devEawOut = nullptr, *devSvgfOut = nullptr;
+    if (denoise) {
+        eawFilter.create(w, h, 5);
+        svgfFilter.create(w, h, 5);
+        devEawOut = cudaMalloc<glm::vec3>(w * h);
+        devSvgfOut = cudaMalloc<glm::vec3>(w * h);
+        /* the reference leaves its history buffers uninitialised; the first frame does not use them, but reads them */
+        for (int i = 0; i < 2; i++) { cudaMemset(svgfFilter.devAccumColor[i], 0, sizeof(glm::vec3) * w * h); cudaMemset(svgfFilter.devAccumMoment[i], 0, sizeof(glm::vec3) * w * h); }
+    }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const glm::vec3 camOrigPos = cam.position;
@@ -88,6 +104,15 @@ int main(int argc, char** argv) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         if (k >= warmup) { total += ms; timed++; }
+        if (denoise) svgfFilter.filter(devSvgfOut, devDirectIllum, gBuffer, cam);
+        if (denoise && k == dumpFrame) {
+            eawFilter.filter(devEawOut, devDirectIllum, gBuffer, cam);
+            cudaDeviceSynchronize();
+            dump(dumpPrefix + "eaw.bin", devEawOut, sizeof(glm::vec3) * w * h);
+            dump(dumpPrefix + "svgf.bin", devSvgfOut, sizeof(glm::vec3) * w * h);
+            dump(dumpPrefix + "svgf_var.bin", svgfFilter.devVariance, sizeof(float) * w * h);
+        }
+        if (denoise) svgfFilter.nextFrame();
         if (k == dumpFrame) {
             dump(dumpPrefix + "radiance.bin", devDirectIllum, sizeof(glm::vec3) * w * h);
             dump(dumpPrefix + "matid.bin", gBuffer.devPrimId[gBuffer.frameIdx], sizeof(int) * w * h);

@@ -1337,3 +1337,223 @@ int orc_occluded(const OrcScene* sc, const float* x, const float* y) {
 }
 
 } // extern "C"
+
+/* ================================================================ image-space filters (denoiser.cu:25-567)
+ * Restated only (a __global__ body cannot be compiled by g++; the harness has no counterpart): the pin for these is the
+ * reference's own CUDA build, which links denoiser.cu unmodified (oracle/ref_headless_main.cpp, tests/test_ref_cuda.py). */
+struct OrcDenoiser {
+    OrcFrame* f;
+    int kind;                       /* 1 LeveledEAWFilter, 2 SpatioTemporalFilter */
+    float sigLumin, sigNormal, sigDepth;
+    std::vector<V3> colorOut, tempColor, accumColor[2], accumMoment[2];
+    std::vector<float> variance, tempVariance, filteredVariance;
+    bool firstTime = true;
+    int frameIdx = 0;
+};
+
+static const float Gaussian3x3[3][3] = {{.075f, .124f, .075f}, {.124f, .204f, .124f}, {.075f, .124f, .075f}};          /* denoiser.cu:11-15 */
+static const float Gaussian5x5[5][5] = {{.0030f, .0133f, .0219f, .0133f, .0030f}, {.0133f, .0596f, .0983f, .0596f, .0133f},
+                                        {.0219f, .0983f, .1621f, .0983f, .0219f}, {.0133f, .0596f, .0983f, .0596f, .0133f},
+                                        {.0030f, .0133f, .0219f, .0133f, .0030f}};                                    /* :17-23 */
+
+/* Camera::getPosition, sceneStructs.h:48-64 */
+static V3 cameraPosition(const OrcCamera& c, int x, int y, float dist, float tanFovY) {
+    Ray r = cameraRay(c, x, y, .5f, .5f, tanFovY);
+    return r.origin + r.direction * dist;
+}
+
+/* waveletFilter, denoiser.cu:64-134 */
+static void eawPass(const OrcFrame* f, const OrcCamera& cam, std::vector<V3>& out, const std::vector<V3>& in, float sigDepth, float sigNormal, float sigLumin, int level) {
+    const int W = f->w, H = f->h, step = 1 << level, cur = f->frameIdx;
+    const float tanFovY = tanf(radians(cam.fov[1]));
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int p = y * W + x, idP = f->matId[cur][p];
+            if (idP <= -1) { out[p] = in[p]; continue; }
+            const V3 normP = f->normal[cur][p], colorP = in[p], posP = cameraPosition(cam, x, y, f->depth[cur][p], tanFovY);
+            V3 sum = v3(0.f);
+            float sumWeight = 0.f;
+            for (int i = -2; i <= 2; i++)
+                for (int j = -2; j <= 2; j++) {
+                    const int qx = x + j * step, qy = y + i * step;
+                    if (qx >= W || qy >= H || qx < 0 || qy < 0) continue;
+                    const int q = qy * W + qx;
+                    if (f->matId[cur][q] != idP) continue;
+                    const V3 normQ = f->normal[cur][q], colorQ = in[q], posQ = cameraPosition(cam, qx, qy, f->depth[cur][q], tanFovY);
+                    const float wColor = gmin(1.f, expf(-dot(colorP - colorQ, colorP - colorQ) / sigLumin));
+                    const float wNorm = gmin(1.f, expf(-dot(normP - normQ, normP - normQ) / sigNormal));
+                    const float wPos = gmin(1.f, expf(-dot(posP - posQ, posP - posQ) / sigDepth));
+                    const float weight = wColor * wNorm * wPos * Gaussian5x5[i + 2][j + 2];
+                    sum = sum + colorQ * weight;
+                    sumWeight += weight;
+                }
+            out[p] = sumWeight == 0.f ? in[p] : sum / sumWeight;
+        }
+}
+
+/* waveletFilter (SVGF form), denoiser.cu:139-216 */
+static void eawSvgfPass(const OrcFrame* f, const OrcCamera& cam, std::vector<V3>& out, const std::vector<V3>& in, std::vector<float>& varOut,
+                        const std::vector<float>& varIn, const std::vector<float>& varFiltered, float sigDepth, float sigNormal, float sigLumin, int level) {
+    const int W = f->w, H = f->h, step = 1 << level, cur = f->frameIdx;
+    const float tanFovY = tanf(radians(cam.fov[1]));
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int p = y * W + x, idP = f->matId[cur][p];
+            if (idP <= -1) { out[p] = in[p]; varOut[p] = varIn[p]; continue; }
+            const V3 normP = f->normal[cur][p], colorP = in[p], posP = cameraPosition(cam, x, y, f->depth[cur][p], tanFovY);
+            V3 sumColor = v3(0.f);
+            float sumVariance = 0.f, sumWeight = 0.f, sumWeight2 = 0.f;
+            for (int i = -2; i <= 2; i++)
+                for (int j = -2; j <= 2; j++) {
+                    const int qx = x + j * step, qy = y + i * step;
+                    if (qx >= W || qy >= H || qx < 0 || qy < 0) continue;
+                    const int q = qy * W + qx;
+                    if (f->matId[cur][q] != idP) continue;
+                    const V3 normQ = f->normal[cur][q], colorQ = in[q], posQ = cameraPosition(cam, qx, qy, f->depth[cur][q], tanFovY);
+                    const float varQ = varIn[q];
+                    const float wPos = expf(-dot(posP - posQ, posP - posQ) / sigDepth) + 1e-4f;
+                    const float wNorm = powf(satDot(normP, normQ), sigNormal) + 1e-4f;
+                    const float denom = sigLumin * sqrtf(gmax(varFiltered[q], 0.f)) + 1e-4f;
+                    const float wColor = expf(-fabsf(luminance(colorP) - luminance(colorQ)) / denom) + 1e-4f;
+                    const float weight = wColor * wNorm * wPos * Gaussian5x5[i + 2][j + 2];
+                    const float weight2 = weight * weight;
+                    sumColor = sumColor + colorQ * weight;
+                    sumVariance += varQ * weight2;
+                    sumWeight += weight;
+                    sumWeight2 += weight2;
+                }
+            out[p] = sumWeight < FLT_EPSILON ? in[p] : sumColor / sumWeight;
+            varOut[p] = sumWeight2 < FLT_EPSILON ? varIn[p] : sumVariance / sumWeight2;
+        }
+}
+
+/* temporalAccumulate, denoiser.cu:250-305 */
+static void temporalAccumulate(const OrcFrame* f, std::vector<V3>& colorOut, const std::vector<V3>& colorLast, std::vector<V3>& momentOut,
+                               const std::vector<V3>& momentLast, const std::vector<V3>& colorIn, bool first) {
+    const int P = f->w * f->h, cur = f->frameIdx;
+    const float Alpha = .2f;
+#pragma omp parallel for
+    for (int p = 0; p < P; p++) {
+        const int id = f->matId[cur][p], lastIdx = f->motion[p];
+        bool diff = first;
+        if (lastIdx < 0) diff = true;
+        else if (id <= -1) diff = true;
+        else if (f->matId[cur ^ 1][lastIdx] != id) diff = true;
+        else if (fabsf(dot(f->normal[cur][p], f->normal[cur ^ 1][lastIdx])) < .1f) diff = true;
+        const V3 color = colorIn[p];
+        const float lum = luminance(color);
+        if (diff) {
+            colorOut[p] = color;
+            momentOut[p] = v3(lum, lum * lum, 0.f);
+        } else {
+            const V3 lastColor = colorLast[lastIdx], lastMoment = momentLast[lastIdx];
+            colorOut[p] = mix(lastColor, color, Alpha);
+            momentOut[p] = v3(mixf(lastMoment.x, lum, Alpha), mixf(lastMoment.y, lum * lum, Alpha), lastMoment.z + 1.f);
+        }
+    }
+}
+
+/* estimateVariance, denoiser.cu:307-343 */
+static void estimateVariance(std::vector<float>& variance, const std::vector<V3>& moment, int W, int H) {
+#pragma omp parallel for
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int p = y * W + x;
+            const V3 m = moment[p];
+            if (m.z > 3.5f) { variance[p] = m.y - m.x * m.x; continue; }
+            float sx = 0.f, sy = 0.f;
+            int num = 0;
+            for (int i = -1; i <= 1; i++)
+                for (int j = -1; j <= 1; j++) {
+                    const int qx = x + j, qy = y + i;
+                    if (qx < 0 || qx >= W || qy < 0 || qy >= H) continue;
+                    sx += moment[qy * W + qx].x; sy += moment[qy * W + qx].y;
+                    num++;
+                }
+            sx /= (float)num; sy /= (float)num;
+            variance[p] = sy - sx * sx;
+        }
+}
+
+/* filterVariance, denoiser.cu:345-370 */
+static void filterVariance(std::vector<float>& out, const std::vector<float>& in, int W, int H) {
+#pragma omp parallel for
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            float sum = 0.f, sumWeight = 0.f;
+            for (int i = -1; i <= 1; i++)
+                for (int j = -1; j <= 1; j++) {
+                    const int qx = x + i, qy = y + j;
+                    if (qx < 0 || qx >= W || qy < 0 || qy >= H) continue;
+                    const float weight = Gaussian3x3[i + 1][j + 1];
+                    sum += in[qy * W + qx] * weight;
+                    sumWeight += weight;
+                }
+            out[y * W + x] = sum / sumWeight;
+        }
+}
+
+extern "C" {
+
+OrcDenoiser* orc_denoiser_create(OrcFrame* f, int kind) {
+    OrcDenoiser* d = new OrcDenoiser;
+    const size_t P = (size_t)f->w * f->h;
+    d->f = f; d->kind = kind;
+    d->colorOut.assign(P, v3(0.f)); d->tempColor.assign(P, v3(0.f));
+    if (kind == 1) { d->sigLumin = 64.f; d->sigNormal = .2f; d->sigDepth = 1.f; }             /* denoiser.cu:455 */
+    else {
+        d->sigLumin = 4.f; d->sigNormal = 128.f; d->sigDepth = 1.f;                           /* denoiser.cu:488 */
+        for (int i = 0; i < 2; i++) { d->accumColor[i].assign(P, v3(0.f)); d->accumMoment[i].assign(P, v3(0.f)); }
+        d->variance.assign(P, 0.f); d->tempVariance.assign(P, 0.f); d->filteredVariance.assign(P, 0.f);
+    }
+    return d;
+}
+void orc_denoiser_destroy(OrcDenoiser* d) { delete d; }
+void orc_denoiser_set_sigmas(OrcDenoiser* d, float sigLumin, float sigNormal, float sigDepth) { d->sigLumin = sigLumin; d->sigNormal = sigNormal; d->sigDepth = sigDepth; }
+
+/* LeveledEAWFilter::filter (denoiser.cu:463-477) / SpatioTemporalFilter::filter (:537-564) on the frame's radiance */
+void orc_denoiser_filter(OrcDenoiser* d, const OrcCamera* cam) {
+    const OrcFrame* f = d->f;
+    if (d->kind == 1) {
+        eawPass(f, *cam, d->colorOut, f->radiance, d->sigDepth, d->sigNormal, d->sigLumin, 0);
+        for (int level = 1; level <= 4; level++) {
+            eawPass(f, *cam, d->tempColor, d->colorOut, d->sigDepth, d->sigNormal, d->sigLumin, level);
+            std::swap(d->colorOut, d->tempColor);
+        }
+        return;
+    }
+    const int fi = d->frameIdx;
+    temporalAccumulate(f, d->accumColor[fi], d->accumColor[fi ^ 1], d->accumMoment[fi], d->accumMoment[fi ^ 1], f->radiance, d->firstTime);
+    d->firstTime = false;
+    estimateVariance(d->variance, d->accumMoment[fi], f->w, f->h);
+    auto wavelet = [&](std::vector<V3>& out, const std::vector<V3>& in, int level) {
+        filterVariance(d->filteredVariance, d->variance, f->w, f->h);
+        eawSvgfPass(f, *cam, out, in, d->tempVariance, d->variance, d->filteredVariance, d->sigDepth, d->sigNormal, d->sigLumin, level);
+    };
+    wavelet(d->colorOut, d->accumColor[fi], 0);
+    std::swap(d->colorOut, d->accumColor[fi]);
+    std::swap(d->tempVariance, d->variance);
+    wavelet(d->colorOut, d->accumColor[fi], 1);
+    std::swap(d->tempVariance, d->variance);
+    for (int level = 2; level <= 4; level++) {
+        wavelet(d->tempColor, d->colorOut, level);
+        std::swap(d->tempColor, d->colorOut);
+        std::swap(d->tempVariance, d->variance);
+    }
+}
+void orc_denoiser_next_frame(OrcDenoiser* d) { d->frameIdx ^= 1; }                               /* denoiser.cu:566-568 */
+/* modulateAlbedo (denoiser.cu:218-228, 405-411) on the filtered image */
+void orc_denoiser_modulate_albedo(OrcDenoiser* d) {
+    const size_t P = d->colorOut.size();
+    for (size_t p = 0; p < P; p++) {
+        V3 c = d->colorOut[p] / 1.f;
+        c = c / (v3(1.f) - c + v3(1e-4f));                                                      /* Math::LDRToHDR, mathUtil.h:40-43 */
+        d->colorOut[p] = c * gmax(d->f->albedo[p], v3(0.f));
+    }
+}
+const float* orc_denoiser_color(OrcDenoiser* d) { return &d->colorOut[0].x; }
+const float* orc_denoiser_variance(OrcDenoiser* d) { return d->variance.data(); }
+
+}  // extern "C"

@@ -122,6 +122,18 @@ float orc_alias_build(int n, const float* values, void* outTable);
 int  orc_intersect(const OrcScene*, const float* origin, const float* dir, float* outPosNormUv8, int* outMatId);
 int  orc_occluded(const OrcScene*, const float* x, const float* y);
 
+/* The reference's image-space filters (denoiser.cu:25-567): kind 1 = LeveledEAWFilter, 2 = SpatioTemporalFilter, applied to the
+ * frame's radiance with its current G-buffer.  Port only (restated): see restir_oracle.cpp. */
+typedef struct OrcDenoiser OrcDenoiser;
+OrcDenoiser* orc_denoiser_create(OrcFrame*, int kind);
+void orc_denoiser_destroy(OrcDenoiser*);
+void orc_denoiser_set_sigmas(OrcDenoiser*, float sigLumin, float sigNormal, float sigDepth);
+void orc_denoiser_filter(OrcDenoiser*, const OrcCamera*);
+void orc_denoiser_next_frame(OrcDenoiser*);
+void orc_denoiser_modulate_albedo(OrcDenoiser*);
+const float* orc_denoiser_color(OrcDenoiser*);      /* P x 3 f32 */
+const float* orc_denoiser_variance(OrcDenoiser*);   /* P f32 (kind 2) */
+
 #ifdef __cplusplus
 }
 #endif

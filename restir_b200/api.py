@@ -109,6 +109,7 @@ SCENE_ARRAYS = dict(boxes=0, mtbvh0=1, light_prim_ids=7, light_radiance=8, alias
                     texcoords=12, material_ids=13, materials=14, env_alias=15, traced_nodes=16, traced_tris=17)
 FRAME_BUFFERS = dict(albedo=0, normal=1, matid=2, depth=3, motion=4, radiance=5, reservoir=6, reservoir_temp=7,
                      light_index=8, ldr=9)
+DENOISER_EAW, DENOISER_SVGF = 1, 2
 STAGES = ("gbuffer", "ris", "spatial", "ptdirect", "tonemap")
 PLANES = dict(geom_cur=0, matid_cur=1, resv_history=2, resv_temp=3, resv_temp2=4, resv_out=5)
 
@@ -121,7 +122,7 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     try:
-        path = _build.build()
+        path = _build.build(loading=True)
     except Exception as e:  # no silent fallback
         raise RestirError("librestir_b200.so is missing and could not be built: %s" % e) from e
     L = C.CDLL(path)
@@ -138,6 +139,14 @@ def lib() -> C.CDLL:
     L.rstr_scene_texture_info.argtypes = [vp, ip, vp, vp, vp]
     L.rstr_scene_set_traversal.argtypes = [vp, ip]
     L.rstr_scene_build_traced_gpu.argtypes = [vp, ip, C.POINTER(C.c_float)]
+    L.rstr_denoiser_create.argtypes = [vp, ip, C.POINTER(vp)]
+    L.rstr_denoiser_destroy.argtypes = [vp]
+    L.rstr_denoiser_set_sigmas.argtypes = [vp, fp, fp, fp]
+    L.rstr_denoiser_filter.argtypes = [vp, C.POINTER(RstrCamera)]
+    L.rstr_denoiser_next_frame.argtypes = [vp]
+    L.rstr_denoiser_modulate_albedo.argtypes = [vp]
+    L.rstr_denoiser_add_image.argtypes = [vp, vp]
+    L.rstr_denoiser_read.argtypes = [vp, vp, vp]
     L.rstr_scene_fallback_rays.argtypes = [vp, C.POINTER(C.c_ulonglong), ip]
     L.rstr_camera_update.argtypes = [C.POINTER(RstrCamera)]
     L.rstr_camera_orbit.argtypes = [C.POINTER(RstrCamera), ip, fp, fp, fp, C.POINTER(RstrCamera)]
@@ -498,6 +507,43 @@ class Frame:
 
 
 STRIP_HANDLE_BYTES = 512
+
+
+class Denoiser:
+    """LeveledEAWFilter (kind "eaw") / SpatioTemporalFilter (kind "svgf") of denoiser.h over a full frame."""
+
+    def __init__(self, frame: "Frame", kind: str = "eaw"):
+        self.frame = frame
+        self.kind = kind
+        self.h = C.c_void_p()
+        _check(lib().rstr_denoiser_create(frame.f, {"eaw": DENOISER_EAW, "svgf": DENOISER_SVGF}[kind], C.byref(self.h)))
+
+    def close(self) -> None:
+        if self.h:
+            lib().rstr_denoiser_destroy(self.h)
+            self.h = None
+
+    def set_sigmas(self, lumin: float, normal: float, depth: float) -> None:
+        _check(lib().rstr_denoiser_set_sigmas(self.h, lumin, normal, depth))
+
+    def filter(self, cam) -> None:
+        _check(lib().rstr_denoiser_filter(self.h, C.byref(cam)))
+
+    def next_frame(self) -> None:
+        _check(lib().rstr_denoiser_next_frame(self.h))
+
+    def modulate_albedo(self) -> None:
+        _check(lib().rstr_denoiser_modulate_albedo(self.h))
+
+    def add_image(self, other: "Denoiser") -> None:
+        _check(lib().rstr_denoiser_add_image(self.h, other.h))
+
+    def read(self, variance: bool = False):
+        n = self.frame.w * self.frame.h
+        rgb = np.zeros((n, 3), np.float32)
+        var = np.zeros(n, np.float32) if variance else None
+        _check(lib().rstr_denoiser_read(self.h, rgb.ctypes.data, var.ctypes.data if variance else None))
+        return (rgb, var) if variance else rgb
 
 
 class StripGroup:

@@ -20,7 +20,7 @@ static int smCount() {
     return n;
 }
 
-static CamDev toCamDev(const RstrCamera& c) {
+CamDev rsToCamDev(const RstrCamera& c) {
     CamDev d;
     memcpy(d.position, c.position, 12); memcpy(d.right, c.right, 12); memcpy(d.up, c.up, 12); memcpy(d.view, c.view, 12);
     memcpy(d.rotInv, c.rotationMatInv, 36);
@@ -413,7 +413,7 @@ int rstr_gbuffer_render(RstrFrame* f, const RstrCamera* cam) {
     if ((rc = rsFlushGBuffer(f))) return rc;
     // the reference reads an uninitialised lastCamera before the first GBuffer::update (gbuffer.h:56); use cam
     f->pendCam = *cam;
-    f->pendC = toCamDev(*cam); f->pendLC = toCamDev(f->haveLast ? f->lastCamera : *cam);
+    f->pendC = rsToCamDev(*cam); f->pendLC = rsToCamDev(f->haveLast ? f->lastCamera : *cam);
     for (bool& r : f->ran) r = false;
     f->gbufPending = true;
     // The pixel's two primary rays (centre ray here, jittered ray in rstr_restir_direct) share one tree walk when the
@@ -500,7 +500,7 @@ int rstr_restir_phase_a(RstrFrame* f, const RstrCamera* cam, const RstrParams* p
     }
     if ((rc = rsFlushGBuffer(f))) return rc;
     stageBegin(f, RSTR_T_RIS);
-    g_launches += launchRestirA(f->sc->dev, d, toCamDev(*cam), *prm, looper, iter, f->first ? 1 : 0, f->stream);
+    g_launches += launchRestirA(f->sc->dev, d, rsToCamDev(*cam), *prm, looper, iter, f->first ? 1 : 0, f->stream);
     stageEnd(f, RSTR_T_RIS);
     CU(cudaGetLastError());
     return RSTR_OK;
@@ -590,7 +590,7 @@ int rstr_pathtrace_direct(RstrFrame* f, const RstrCamera* cam, int looper, int i
     if ((rc = rsFlushGBuffer(f))) return rc;
     FrameDev d = rsToFrameDev(f, f->row0, f->row1);
     stageBegin(f, RSTR_T_PTDIRECT);
-    g_launches += launchPTDirect(f->sc->dev, d, toCamDev(*cam), looper, iter, f->stream);
+    g_launches += launchPTDirect(f->sc->dev, d, rsToCamDev(*cam), looper, iter, f->stream);
     stageEnd(f, RSTR_T_PTDIRECT);
     CU(cudaGetLastError());
     return RSTR_OK;

@@ -92,6 +92,7 @@ struct RstrFrame {
 };
 
 rs::FrameDev rsToFrameDev(const RstrFrame* f, int rowLo, int rowHi);
+rs::CamDev rsToCamDev(const RstrCamera& c);
 extern "C" int rsFlushGBuffer(RstrFrame* f);     // launches a G-buffer render that rstr_gbuffer_render deferred
 extern "C" int rsEnsureTemp2(RstrFrame* f);
 int rsEnsureUploaded(RstrScene* sc);          // uploads the host scene on first use (capi.cu)

@@ -15,6 +15,7 @@
 // (bvh.h:85-157), which makes the visited-leaf sequence, tie-breaking and pruning identical to the
 // reference's 6-copy threaded MTBVH walk.
 #include "kernels.h"
+#include "camera_dev.h"
 
 namespace rs {
 
@@ -527,22 +528,41 @@ RS_D void wsPush(unsigned& cursor, int ref, unsigned key) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(cursor), "r"(ref), "r"(key) : "memory");
     cursor += 8;
 }
-// next stacked node that is not beyond every lane's limit, or RS_DONE
-RS_D int wsPop(unsigned& cursor, unsigned base, float wlimit) {
-    while (cursor != base) {
+// next stacked node that is not beyond every lane's limit; the bottom entry is a sentinel {RS_DONE, distance 0} that always
+// passes, so the cursor alone describes the stack (no base address to keep -- or to rebuild from %tid, S2R, in the walk)
+RS_D int wsPop(unsigned& cursor, float wlimit) {
+    for (;;) {
         cursor -= 8;
         int ref;
         unsigned key;
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ref), "=r"(key) : "r"(cursor) : "memory");
         if (__uint_as_float(key) <= wlimit) return ref;
     }
-    return RS_DONE;
+}
+// A lane's any-hit stack addressed through an OPAQUE 32-bit shared-space address: left to itself the compiler may rebuild the
+// address from %tid inside the walk (S2R, a slow instruction: measured 13 % on k_shadow's per-lane loop).
+RS_D unsigned stackAddr(const Stack& st) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(st.sRef);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+RS_D void stackPush(unsigned addr, Stack& st, int sp, int ref) {
+    if (sp < RS_SMEM_STACK) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr + (unsigned)sp * (RS_BLOCK * 4u)), "r"(ref) : "memory");
+    else st.lRef[sp - RS_SMEM_STACK] = ref;
+}
+RS_D int stackRef(unsigned addr, const Stack& st, int sp) {
+    if (sp < RS_SMEM_STACK) {
+        int ref;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ref) : "r"(addr + (unsigned)sp * (RS_BLOCK * 4u)) : "memory");
+        return ref;
+    }
+    return st.lRef[sp - RS_SMEM_STACK];
 }
 template <bool TWO>
 RS_D void packetWalk(const DevScene& s, f3 o, PRay& a, PRay& b, const TieStore& ta, const TieStore& tb, int2* wst) {
     const unsigned FULL = 0xffffffffu;
-    const unsigned wbase = (unsigned)__cvta_generic_to_shared(wst);
-    unsigned wsp = wbase;
+    unsigned wsp = (unsigned)__cvta_generic_to_shared(wst);
+    wsPush(wsp, RS_DONE, 0u);
     float tA, tB;
     bool hit = slabHitP(a, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], tA);
     if (TWO) hit |= slabHitP(b, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], tB);
@@ -598,7 +618,7 @@ RS_D void packetWalk(const DevScene& s, f3 o, PRay& a, PRay& b, const TieStore& 
                 cur = leftNear ? l.x : l.y;
             } else if (anyL) cur = l.x;
             else if (anyR) cur = l.y;
-            else cur = wsPop(wsp, wbase, wlimit);
+            else cur = wsPop(wsp, wlimit);
         }
         if (cur == RS_DONE) return;
         {
@@ -612,14 +632,14 @@ RS_D void packetWalk(const DevScene& s, f3 o, PRay& a, PRay& b, const TieStore& 
         }
         const float lim = TWO ? fmaxf(a.limit, b.limit) : a.limit;
         wlimit = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(lim, 0.f))));
-        cur = wsPop(wsp, wbase, wlimit);
+        cur = wsPop(wsp, wlimit);
     }
 }
 
 // shared memory of the packet walk for a block of RS_BLOCK threads: near-tie stores of NR rays per thread + one stack per warp
 #define RS_DECLARE_PACKET(name, NR)                                                 \
     __shared__ float name##_ties[NR][RS_TIE_ROWS][RS_BLOCK];                            \
-    __shared__ int2 name##_ws[RS_BLOCK / 32][RS_WSTACK];                            \
+    __shared__ int2 name##_ws[RS_BLOCK / 32][RS_WSTACK + 1];                            \
     TieStore name##_ta, name##_tb;                                                  \
     name##_ta.base = &name##_ties[0][0][threadIdx.x];                               \
     name##_tb.base = &name##_ties[NR - 1][0][threadIdx.x];                          \
@@ -678,25 +698,7 @@ RS_D int traceOccluded(const DevScene& s, f3 x, f3 y, Stack& stack) {
 }
 
 // ------------------------------------------------------------------------------------------------ camera
-// Camera::sample (sceneStructs.h:69-86); gbuffer.cu:11-23 is the same expression with r = (.5, .5)
-RS_D void cameraRay(const CamDev& c, int x, int y, float rx, float ry, f3& o, f3& d) {
-    float sx = (float)x * c.pixelSizeX, sy = (float)y * c.pixelSizeY;
-    float ux = sx + c.pixelSizeX * rx, uy = sy + c.pixelSizeY * ry;
-    ux = 1.f - ux * 2.f; uy = 1.f - uy * 2.f;
-    f3 pf = mk3(ux * c.aspect * c.tanFovY, uy * 1.f * c.tanFovY, 1.f) * c.focalDist;
-    f3 dir = pf - mk3(0.f);
-    f3 right = mk3(c.right[0], c.right[1], c.right[2]), up = mk3(c.up[0], c.up[1], c.up[2]), view = mk3(c.view[0], c.view[1], c.view[2]);
-    f3 w = mk3(right.x * dir.x + up.x * dir.y + view.x * dir.z,
-               right.y * dir.x + up.y * dir.y + view.y * dir.z,
-               right.z * dir.x + up.z * dir.y + view.z * dir.z);
-    d = normalize(w);
-    o = mk3(c.position[0], c.position[1], c.position[2]) + right * 0.f + up * 0.f;
-}
-// the origin cameraRay gives every ray (the same expression: warp-uniform, the packet walk keeps it out of per-thread registers)
-RS_D f3 cameraOrigin(const CamDev& c) {
-    f3 right = mk3(c.right[0], c.right[1], c.right[2]), up = mk3(c.up[0], c.up[1], c.up[2]);
-    return mk3(c.position[0], c.position[1], c.position[2]) + right * 0.f + up * 0.f;
-}
+// cameraRay / cameraOrigin: camera_dev.h
 
 // Camera::getRasterCoord (sceneStructs.h:23-46); float->int is cvt.rzi (saturating, NaN -> 0) as in the reference's kernel
 RS_D void rasterCoord(const CamDev& c, f3 pos, int& ox, int& oy) {
@@ -1486,10 +1488,125 @@ RS_D bool leafOccluded(const DevScene& s, const RayT& r, float dist, int ref) {
     }
     return false;
 }
-#ifndef RS_COOP_DRAIN
-#define RS_COOP_DRAIN 1       /* k_shadow: once the queue is empty the warp finishes its remaining rays together (below) */
+#ifndef RS_SHADOW_ORDER
+#define RS_SHADOW_ORDER 1      /* any-hit rays enter the nearer child first: -4 % of the 1080p / 4K frame on the 1M-triangle scene (profiles/r02_c15_ab.txt) */
+#endif
+#ifndef RS_DRAIN_MAX_PIXELS
+#define RS_DRAIN_MAX_PIXELS 1500000   /* k_shadow<true> (the warp finishes its last rays together) for launches over at most this many pixels */
 #endif
 #define RS_COOP_CAP (RS_SMEM_STACK * 32)
+
+// the shadow ray of queued pixel li (restir.cu:172-176 -> traceOccluded, scene.h:286-295): from the shaded point towards the
+// reservoir's sample; false when the reservoir has no weight (nothing to test) or the segment is empty
+RS_D bool shadowRayOf(const FrameDev& f, size_t li, f3& ro, f3& rd, float& dist) {
+    const float4* rp = (const float4*)(f.resvStage + li);
+    const float4 ra = rp[0];                                             // {wi, dist}
+    const float w = rp[1].x;
+    if (w == 0.f) return false;                                          // weight 0 cannot change
+    const float4 pp = *(const float4*)(f.resvOut + li);
+    const f3 pos = mk3(pp.x, pp.y, pp.z);
+    const f3 to = pos + mk3(ra.x, ra.y, ra.z) * ra.w;
+    f3 dir = to - pos;
+    dist = length(dir);
+    if (!(dist > 0.f)) return false;
+    dir = dir / dist;
+    ro = pos + dir * 1e-5f; rd = dir;
+    dist -= 1e-4f * 2.f;
+    return true;
+}
+
+// ---- k_shadow once the queue is empty.  What is left in a warp then is a handful of rays of very different lengths (a shadow ray
+// takes 72 node steps on average and up to ~500), and walked one ray per lane the warp would last as long as its longest
+// ray with most lanes idle -- measured, the last 350 us of the kernel on every scene and strip.  Any-hit rays need no order,
+// so the warp finishes them TOGETHER: every pending node of every remaining ray becomes an item {owner lane, node} of one
+// warp-wide list (kept in the lanes' stack rows in shared memory), each round the lanes take 32 items, fetch the owner's
+// ray by shuffle, test both children, append the children that are hit and test hit leaves at once.  The drain lasts as long
+// as the deepest chain of dependent node fetches, not the longest ray.  A function of its own (not inlined) so that the
+// per-lane loop keeps its registers.  Called by the whole warp; li is the lane's pixel, cur its current node (RS_DONE: no ray),
+// sRef / lRef its stack of sp entries.
+__device__ __noinline__ void shadowDrain(const DevScene& s, const FrameDev& f, int cur, int sp, size_t li, int* sRef, const int* lRef) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    bool act = cur != RS_DONE;
+    f3 ro = mk3(0.f), rd = mk3(0.f, 0.f, 1.f);                           // the lane's ray again, from its pixel (the caller keeps its registers)
+    float dist = 0.f;
+    if (act) shadowRayOf(f, li, ro, rd, dist);
+    RayF rf;
+    {
+        RayT r0;
+        r0.o = ro; r0.d = rd;
+        rf = makeRayF(r0);
+    }
+    int* list = sRef - lane;                                            // item p lives at list[(p >> 5) * RS_BLOCK + (p & 31)]
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned cnt = 0, doneMask = 0;
+    const unsigned maxsp = __reduce_max_sync(FULL, act ? (unsigned)sp : 0u);
+    {
+        const RayT r = makeRayT(ro, rd);
+        for (unsigned k = 0; k <= maxsp; k++) {                         // round k: every lane's k-th stacked entry; last round: its current node
+            int ref = RS_DONE;
+            if (act) {
+                if (k < (unsigned)sp) ref = k < RS_SMEM_STACK ? sRef[k * RS_BLOCK] : lRef[k - RS_SMEM_STACK];
+                else if (k == maxsp) ref = cur;
+            }
+            __syncwarp();                                               // row k has been read before items land in it
+            bool occ = false;
+            if (ref < 0) occ = leafOccluded(s, r, dist, ref);
+            const bool push = ref >= 0 && ref != RS_DONE;
+            const unsigned pm = __ballot_sync(FULL, push);
+            if (push) { const unsigned p = cnt + __popc(pm & lt); list[(p >> 5) * RS_BLOCK + (p & 31)] = (int)(((unsigned)lane << 27) | (unsigned)ref); }
+            cnt += __popc(pm);
+            if (occ) { f.resvStage[li].weight = 0.f; act = false; }
+            doneMask |= __ballot_sync(FULL, occ);
+        }
+    }
+    __syncwarp();
+    while (cnt) {
+        const unsigned take = cnt > RS_COOP_CAP - 64 ? 1u : (cnt < 32u ? cnt : 32u);
+        unsigned item = 0;
+        bool valid = (unsigned)lane < take;
+        if (valid) { const unsigned p = cnt - 1u - (unsigned)lane; item = (unsigned)list[(p >> 5) * RS_BLOCK + (p & 31)]; }
+        cnt -= take;
+        __syncwarp();
+        const int owner = valid ? (int)(item >> 27) : lane;
+        valid = valid && !((doneMask >> owner) & 1u);
+        RayF of;
+        of.inv.x = __shfl_sync(FULL, rf.inv.x, owner); of.inv.y = __shfl_sync(FULL, rf.inv.y, owner); of.inv.z = __shfl_sync(FULL, rf.inv.z, owner);
+        of.oi.x = __shfl_sync(FULL, rf.oi.x, owner); of.oi.y = __shfl_sync(FULL, rf.oi.y, owner); of.oi.z = __shfl_sync(FULL, rf.oi.z, owner);
+        const float od = __shfl_sync(FULL, dist, owner);
+        int c0 = RS_DONE, c1 = RS_DONE;                                 // children that are hit
+        if (valid) {
+            const float4* np = s.fastNodes + 4 * (size_t)(item & 0x07ffffffu);
+            const F8 nA = ldg256(np), nB = ldg256(np + 2);
+            const float4 a = nA.lo, b = nA.hi, c = nB.lo;
+            float tL, tR;
+            if (slabHit(of, a.x, a.y, a.z, a.w, b.x, b.y, od, tL)) c0 = __float_as_int(nB.hi.x);
+            if (slabHit(of, b.z, b.w, c.x, c.y, c.z, c.w, od, tR)) c1 = __float_as_int(nB.hi.y);
+        }
+        for (int side = 0; side < 2; side++) {
+            const int ch = side ? c1 : c0;
+            const bool push = ch >= 0 && ch != RS_DONE;
+            const unsigned pm = __ballot_sync(FULL, push);
+            if (push) { const unsigned p = cnt + __popc(pm & lt); list[(p >> 5) * RS_BLOCK + (p & 31)] = (int)(((unsigned)owner << 27) | (unsigned)ch); }
+            cnt += __popc(pm);
+        }
+        bool occ = false;
+        if (__any_sync(FULL, c0 < 0 || c1 < 0)) {
+            f3 oo, dd;
+            oo.x = __shfl_sync(FULL, ro.x, owner); oo.y = __shfl_sync(FULL, ro.y, owner); oo.z = __shfl_sync(FULL, ro.z, owner);
+            dd.x = __shfl_sync(FULL, rd.x, owner); dd.y = __shfl_sync(FULL, rd.y, owner); dd.z = __shfl_sync(FULL, rd.z, owner);
+            if (c0 < 0 || c1 < 0) {
+                const RayT rr = makeRayT(oo, dd);
+                if (c0 < 0) occ = leafOccluded(s, rr, od, c0);
+                if (!occ && c1 < 0) occ = leafOccluded(s, rr, od, c1);
+            }
+        }
+        const unsigned occBits = __reduce_or_sync(FULL, occ ? (1u << owner) : 0u);
+        doneMask |= occBits;
+        if ((occBits >> lane) & 1u) f.resvStage[li].weight = 0.f;        // this lane's own ray
+        __syncwarp();
+    }
+}
 
 #ifdef RS_SHADOW_STATS
 // development build only (RSTR_DEFINES=-DRS_SHADOW_STATS): steps per shadow ray as a log2 histogram [0..31], [32] rays, [33] steps,
@@ -1497,6 +1614,9 @@ RS_D bool leafOccluded(const DevScene& s, const RayT& r, float dist, int ref) {
 __device__ unsigned long long g_shadowStats[64];
 RS_D unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 RS_D void shadowRayDone(int steps) {
+#if RS_SHADOW_STATS >= 2      /* time stamps only: no per-ray atomics that would stretch the very tail they are meant to measure */
+    return;
+#endif
     int b = 0;
     while ((2 << b) <= steps && b < 31) b++;
     atomicAdd(g_shadowStats + b, 1ull); atomicAdd(g_shadowStats + 32, 1ull); atomicAdd(g_shadowStats + 33, (unsigned long long)steps);
@@ -1504,6 +1624,10 @@ RS_D void shadowRayDone(int steps) {
 }
 #endif
 // DevScene::testOcclusion (scene.h:286-316) for every queued pixel whose reservoir has weight: occluded -> weight = 0
+// DRAIN: the tail is finished by shadowDrain.  It shortens the kernel by ~80 us whatever the queue length, but the build that can
+// leave the loop early runs the per-lane phase ~12 % slower (measured: profiles/r02_c14_tail.txt), so it is the choice for
+// short queues only (strips, small frames): launchPhaseAStaged picks by the launch's pixel count.
+template <bool DRAIN>
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f) {
     RS_DECLARE_REFSTACK(stack);
     const unsigned FULL = 0xffffffffu;
@@ -1516,6 +1640,8 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
     size_t li = 0;
     long long tRay = 0;
     bool exhausted = false;                       // warp-uniform: the queue is empty
+    bool drain = false;                           // warp-uniform: leave the loop for shadowDrain
+    const unsigned sAddr = stackAddr(stack);
     r.o = r.d = r.inv = mk3(0.f); r.flags = 0; r.dim = r.lesser = 0;
     rf.inv = rf.oi = mk3(0.f);
 #ifdef RS_SHADOW_STATS
@@ -1542,117 +1668,26 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
                 const int index = f.shadeQueue[i];
                 rowY = index / f.W;
                 li = planeIndex(f, index % f.W, rowY);
-                const float4* rp = (const float4*)(f.resvStage + li);
-                const float4 ra = rp[0];                                             // {wi, dist}
-                const float w = rp[1].x;
-                if (w != 0.f) {                                                      // restir.cu:172-176: weight 0 cannot change
-                    const float4 pp = *(const float4*)(f.resvOut + li);
-                    const f3 pos = mk3(pp.x, pp.y, pp.z);
-                    const f3 to = pos + mk3(ra.x, ra.y, ra.z) * ra.w;
-                    f3 dir = to - pos;                                               // traceOccluded (scene.h:286-295)
-                    dist = length(dir);
-                    if (dist > 0.f) {
-                        dir = dir / dist;
-                        r = makeRayT(pos + dir * 1e-5f, dir);
-                        dist -= 1e-4f * 2.f;
-                        rf = makeRayF(r);
-                        float tr;
-                        if (slabHit(rf, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], dist, tr)) {
-                            cur = s.fastRoot; sp = 0;
-                            if (f.rowCost) tRay = clock64();
+                f3 ro, rd;
+                if (shadowRayOf(f, li, ro, rd, dist)) {
+                    r = makeRayT(ro, rd);
+                    rf = makeRayF(r);
+                    float tr;
+                    if (slabHit(rf, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], dist, tr)) {
+                        cur = s.fastRoot; sp = 0;
+                        if (f.rowCost) tRay = clock64();
 #ifdef RS_SHADOW_STATS
-                            steps = 0;
+                        steps = 0;
 #endif
-                        }
                     }
                 }
             }
         }
-#if RS_COOP_DRAIN
-        // ---- The queue is empty: what is left in this warp is a handful of rays of very different lengths (a shadow ray takes 72
-        // node steps on average and up to ~500), and walked one ray per lane the warp would last as long as its longest ray
-        // with most lanes idle -- measured, the last 350 us of this kernel on every scene and strip.  Any-hit rays need no
-        // order, so the warp finishes them TOGETHER instead: every pending node of every remaining ray becomes an item
-        // {owner lane, node} of one warp-wide list (kept in the lanes' stack rows in shared memory), each round the lanes take
-        // 32 items, fetch the owner's ray by shuffle, test both children, append the children that are hit and test hit leaves
-        // at once.  The drain lasts as long as the deepest chain of dependent node fetches, not the longest ray.
-        if (exhausted) {
-            bool act = cur != RS_DONE;
-            const unsigned need = __reduce_add_sync(FULL, act ? (unsigned)sp + 1u : 0u);
-            if (need <= RS_COOP_CAP - 96) {
-                int* list = stack.sRef - lane;                                      // item p lives at list[(p >> 5) * RS_BLOCK + (p & 31)]
-                const unsigned lt = (1u << lane) - 1u;
-                unsigned cnt = 0, doneMask = 0;
-                const unsigned maxsp = __reduce_max_sync(FULL, act ? (unsigned)sp : 0u);
-                for (unsigned k = 0; k <= maxsp; k++) {                              // round k: every lane's k-th stacked entry; last round: its current node
-                    int ref = RS_DONE;
-                    if (act) {
-                        if (k < (unsigned)sp) ref = stack.ref((int)k);
-                        else if (k == maxsp) ref = cur;
-                    }
-                    __syncwarp();                                                    // row k has been read before items land in it
-                    bool occ = false;
-                    if (ref < 0) occ = leafOccluded(s, r, dist, ref);
-                    const bool push = ref >= 0 && ref != RS_DONE;
-                    const unsigned pm = __ballot_sync(FULL, push);
-                    if (push) { const unsigned p = cnt + __popc(pm & lt); list[(p >> 5) * RS_BLOCK + (p & 31)] = (int)(((unsigned)lane << 27) | (unsigned)ref); }
-                    cnt += __popc(pm);
-                    if (occ) { f.resvStage[li].weight = 0.f; act = false; }
-                    doneMask |= __ballot_sync(FULL, occ);
-                }
-                __syncwarp();
-                while (cnt) {
-                    const unsigned take = cnt > RS_COOP_CAP - 64 ? 1u : (cnt < 32u ? cnt : 32u);
-                    unsigned item = 0;
-                    bool valid = (unsigned)lane < take;
-                    if (valid) { const unsigned p = cnt - 1u - (unsigned)lane; item = (unsigned)list[(p >> 5) * RS_BLOCK + (p & 31)]; }
-                    cnt -= take;
-                    __syncwarp();
-                    const int owner = valid ? (int)(item >> 27) : lane;
-                    valid = valid && !((doneMask >> owner) & 1u);
-                    RayF of;
-                    of.inv.x = __shfl_sync(FULL, rf.inv.x, owner); of.inv.y = __shfl_sync(FULL, rf.inv.y, owner); of.inv.z = __shfl_sync(FULL, rf.inv.z, owner);
-                    of.oi.x = __shfl_sync(FULL, rf.oi.x, owner); of.oi.y = __shfl_sync(FULL, rf.oi.y, owner); of.oi.z = __shfl_sync(FULL, rf.oi.z, owner);
-                    const float od = __shfl_sync(FULL, dist, owner);
-                    int c0 = RS_DONE, c1 = RS_DONE;                                  // children that are hit
-                    if (valid) {
-                        const float4* np = s.fastNodes + 4 * (size_t)(item & 0x07ffffffu);
-                        const F8 nA = ldg256(np), nB = ldg256(np + 2);
-                        const float4 a = nA.lo, b = nA.hi, c = nB.lo;
-                        float tL, tR;
-                        if (slabHit(of, a.x, a.y, a.z, a.w, b.x, b.y, od, tL)) c0 = __float_as_int(nB.hi.x);
-                        if (slabHit(of, b.z, b.w, c.x, c.y, c.z, c.w, od, tR)) c1 = __float_as_int(nB.hi.y);
-                    }
-                    for (int side = 0; side < 2; side++) {
-                        const int ch = side ? c1 : c0;
-                        const bool push = ch >= 0 && ch != RS_DONE;
-                        const unsigned pm = __ballot_sync(FULL, push);
-                        if (push) { const unsigned p = cnt + __popc(pm & lt); list[(p >> 5) * RS_BLOCK + (p & 31)] = (int)(((unsigned)owner << 27) | (unsigned)ch); }
-                        cnt += __popc(pm);
-                    }
-                    bool occ = false;
-                    if (__any_sync(FULL, c0 < 0 || c1 < 0)) {
-                        f3 oo, dd;
-                        oo.x = __shfl_sync(FULL, r.o.x, owner); oo.y = __shfl_sync(FULL, r.o.y, owner); oo.z = __shfl_sync(FULL, r.o.z, owner);
-                        dd.x = __shfl_sync(FULL, r.d.x, owner); dd.y = __shfl_sync(FULL, r.d.y, owner); dd.z = __shfl_sync(FULL, r.d.z, owner);
-                        if (c0 < 0 || c1 < 0) {
-                            const RayT rr = makeRayT(oo, dd);
-                            if (c0 < 0) occ = leafOccluded(s, rr, od, c0);
-                            if (!occ && c1 < 0) occ = leafOccluded(s, rr, od, c1);
-                        }
-                    }
-                    const unsigned occBits = __reduce_or_sync(FULL, occ ? (1u << owner) : 0u);
-                    doneMask |= occBits;
-                    if ((occBits >> lane) & 1u) f.resvStage[li].weight = 0.f;         // this lane's own ray
-                    __syncwarp();
-                }
-#ifdef RS_SHADOW_STATS
-                if (lane == 0) atomicMax(g_shadowStats + 41, gtimer());
-#endif
-                break;
-            }
+        // the queue is empty: the warp finishes what it still holds together (shadowDrain, after the loop), as soon as that fits the list
+        if (DRAIN && exhausted) {
+            const unsigned need = __reduce_add_sync(FULL, cur != RS_DONE ? (unsigned)sp + 1u : 0u);
+            if (need <= RS_COOP_CAP - 96) { drain = true; break; }
         }
-#endif
         // Lanes at an internal node step; lanes that have reached a leaf WAIT until RS_LEAF_MIN of them are there (or nobody is
         // left to step): run lane by lane, the triangle tests -- half of this kernel's instructions -- executed with 1.5 of 32 lanes.
         const unsigned atLeaf = __ballot_sync(FULL, cur < 0);
@@ -1666,10 +1701,14 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
                 float tL, tR;
                 const bool hL = slabHit(rf, a.x, a.y, a.z, a.w, b.x, b.y, dist, tL);
                 const bool hR = slabHit(rf, b.z, b.w, c.x, c.y, c.z, c.w, dist, tR);
-                if (hL && hR) { stack.pushRef(sp, l.y); sp++; cur = l.x; }
+#if RS_SHADOW_ORDER
+                if (hL && hR) { const bool ln = tL <= tR; stackPush(sAddr, stack, sp, ln ? l.y : l.x); sp++; cur = ln ? l.x : l.y; }     // nearer child first (A/B)
+#else
+                if (hL && hR) { stackPush(sAddr, stack, sp, l.y); sp++; cur = l.x; }
+#endif
                 else if (hL) cur = l.x;
                 else if (hR) cur = l.y;
-                else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
+                else cur = sp == 0 ? RS_DONE : stackRef(sAddr, stack, --sp);
                 if (f.rowCost && cur == RS_DONE) atomicAdd(f.rowCost + (rowY >> 3), (unsigned long long)((clock64() - tRay) / 24));
 #ifdef RS_SHADOW_STATS
                 steps++;
@@ -1679,13 +1718,19 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_shadow(const __gri
         } else if (cur < 0) {
             const bool occluded = leafOccluded(s, r, dist, cur);
             if (occluded) { f.resvStage[li].weight = 0.f; cur = RS_DONE; }
-            else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
+            else cur = sp == 0 ? RS_DONE : stackRef(sAddr, stack, --sp);
             if (f.rowCost && cur == RS_DONE) atomicAdd(f.rowCost + (rowY >> 3), (unsigned long long)((clock64() - tRay) / 24));
 #ifdef RS_SHADOW_STATS
             steps++;
             if (cur == RS_DONE) shadowRayDone(steps);
 #endif
         }
+    }
+    if (DRAIN && drain) {
+        shadowDrain(s, f, cur, sp, li, stack.sRef, stack.lRef);
+#ifdef RS_SHADOW_STATS
+        if (lane == 0) atomicMax(g_shadowStats + 41, gtimer());
+#endif
     }
 }
 #ifdef RS_SHADOW_STATS
@@ -2158,7 +2203,13 @@ int launchPhaseAStaged(const DevScene& s, const FrameDev& f, const CamDev& cam, 
         }
         k_candidates<<<linear, RS_BLOCK, 0, q>>>(s, fb, cam, p, looper);
         // the bands' shadow kernels share the machine with each other and with the next band's k_primary
-        if (!p.unbiased) k_shadow<<<(unsigned)(numSMs * (bands > 1 ? RS_MINB_SHADOW / 2 : RS_MINB_SHADOW)), RS_BLOCK, 0, q>>>(s, fb);
+        if (!p.unbiased) {
+            const unsigned sg = (unsigned)(numSMs * (bands > 1 ? RS_MINB_SHADOW / 2 : RS_MINB_SHADOW));
+            static const int forced = getenv("RSTR_SHADOW_DRAIN") ? atoi(getenv("RSTR_SHADOW_DRAIN")) : -1;      // A/B switch
+            const bool drainTail = forced >= 0 ? forced != 0 : (size_t)(fb.rowHi - fb.rowLo) * (size_t)f.W <= (size_t)RS_DRAIN_MAX_PIXELS;
+            if (drainTail) k_shadow<true><<<sg, RS_BLOCK, 0, q>>>(s, fb);
+            else k_shadow<false><<<sg, RS_BLOCK, 0, q>>>(s, fb);
+        }
         if (p.unbiased) {
             if (sp) k_temporal_unb<true><<<linear, RS_BLOCK, 0, q>>>(s, fb, p, iter, first);
             else k_temporal_unb<false><<<linear, RS_BLOCK, 0, q>>>(s, fb, p, iter, first);

@@ -18,6 +18,15 @@ base = rb.Camera.from_scene(sd)
 prm = rb.default_params(reuse=reuse, radius=radius)
 L = rb.lib()
 out = (C.c_ulonglong * 64)()
+if not hasattr(L, "rstr_debug_shadow_stats"):     # a plain build: per-stage device times only, averaged over 12 frames
+    acc = []
+    for k in range(16):
+        cam = base.orbit(orbit_index(k))
+        fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0); fr.gbuffer_update(cam)
+        if k >= 4:
+            acc.append(fr.stage_ms())
+    print(w, rows, rb.api.build_id(), "stage ms (12 frames)", {n: round(sum(a[n] for a in acc) / len(acc), 4) for n in ("ris", "spatial")})
+    sys.exit(0)
 for k in range(6):
     if k == 5:
         fr.sync(); L.rstr_debug_shadow_stats(None, 1)

@@ -20,11 +20,12 @@ from restir_b200 import scenes
 REF = os.path.join(ROOT, "oracle", "_ref")
 
 
-def run_ref(binary, scene_txt, frames, warmup, reuse, dump=None, dump_frame=-1):
+def run_ref(binary, scene_txt, frames, warmup, reuse, dump=None, dump_frame=-1, denoise=False):
     cmd = [os.path.join(REF, binary), scene_txt, str(frames), str(warmup), str(reuse)]
     if dump:
         cmd += [dump, str(dump_frame)]
-    r = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(scene_txt))
+    env = dict(os.environ, REF_DENOISE="1") if denoise else None
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(scene_txt), env=env)
     if r.returncode != 0:
         raise RuntimeError("ref_headless failed: " + r.stderr[-2000:])
     return json.loads(r.stdout.strip().splitlines()[-1])
@@ -105,7 +106,50 @@ def compare(work="config2", frames=60, lib_times=True):
     return out
 
 
+def compare_denoisers(work="config2", frames=6):
+    """The reference's own filters (denoiser.cu in its CUDA build, REF_DENOISE=1) vs rstr_denoiser_* on the same frames: temporal
+    ReSTIR of the orbit, SVGF filtering every frame (history + moments), EAW on the last one."""
+    desc, spec, res, reuse, radius = WORKLOADS[work]
+    sd = make_scene(spec, res)
+    tmp = tempfile.mkdtemp()
+    txt = scenes.write_scene_files(sd, tmp, "scene")
+    W, H = res
+    P = W * H
+    pre = os.path.join(tmp, "ref_")
+    last = frames - 1
+    run_ref("ref_headless_r5", txt, frames, 0, 1, pre, last, denoise=True)
+    rb.init(0)
+    sc = rb.Scene.from_file(txt)
+    base = sc.camera
+    fr = sc.frame(W, H)
+    eaw, svgf = rb.Denoiser(fr, "eaw"), rb.Denoiser(fr, "svgf")
+    prm = rb.default_params(reuse=1)
+    for k in range(frames):
+        cam = base.orbit(k); fr.gbuffer_render(cam); fr.restir_direct(cam, prm, k, 0)
+        svgf.filter(cam)
+        if k == last:
+            eaw.filter(cam)
+        else:
+            svgf.next_frame(); fr.gbuffer_update(cam)
+    mine = {"radiance": fr.read("radiance"), "eaw": eaw.read()}
+    mine["svgf"], mine["svgf_var"] = svgf.read(variance=True)
+    ref = {n: np.fromfile(pre + n + ".bin", np.float32).reshape(shape) for n, shape in (("radiance", (P, 3)), ("eaw", (P, 3)), ("svgf", (P, 3)), ("svgf_var", (P,)))}
+    out = {"workload": work, "frames": frames, "library": os.environ.get("RSTR_LIBNAME", "librestir_b200.so")}
+    for n in ref:
+        a, b = mine[n].astype(np.float64).reshape(P, -1), ref[n].astype(np.float64).reshape(P, -1)
+        rel = np.abs(a - b).sum(1) / np.maximum(np.abs(b).sum(1), 1e-6 * max(float(np.abs(b).max()), 1e-30))
+        out[n] = {"pixels_bitexact": float((mine[n].reshape(P, -1) == ref[n].reshape(P, -1)).all(1).mean()), "pixels_within_1e-4_rel": float((rel <= 1e-4).mean()),
+                  "max_rel": float(rel.max()), "mean_ref": float(b.mean()), "mean_b200": float(a.mean())}
+    for d in (eaw, svgf):
+        d.close()
+    fr.close(); sc.close()
+    return out
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "denoisers":
+        print(json.dumps(compare_denoisers(sys.argv[2] if len(sys.argv) > 2 else "config2", int(sys.argv[3]) if len(sys.argv) > 3 else 6)))
+        return
     work = sys.argv[1] if len(sys.argv) > 1 else "config2"
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 60
     print(json.dumps(compare(work, frames, lib_times="parity-only" not in sys.argv)))

@@ -70,3 +70,27 @@ def test_contracted_build_reproduces_the_reference_cuda_binary(rcc, work, frames
     assert p["depth_max_rel_where_same_material"] == 0.0
     assert p["radiance_pixels_within_1e-4_rel"] >= 0.9999
     assert p["radiance_mean_relMSE"] <= 1e-5
+
+
+@pytest.mark.parametrize("work", ["config2", "config3"])
+def test_denoisers_against_the_reference_cuda_build(rcc, work):
+    """rstr_denoiser_* next to the reference's own filters -- its denoiser.cu, unmodified, inside its CUDA build
+    (REF_DENOISE=1: SpatioTemporalFilter on every frame, LeveledEAWFilter on the last) -- over six frames of the orbit, with the
+    contracted twin of this library (the one that reproduces the reference's CUDA binary bit for bit on the frame itself, so that
+    the filters see the same input).  This is the pin of the filters: a g++ build of their __global__ bodies does not exist."""
+    import json
+    import subprocess
+
+    lib = os.path.join(ROOT, "restir_b200", "librestir_b200_fmad.so")
+    if not os.path.exists(lib):
+        pytest.skip("restir_b200/librestir_b200_fmad.so not built")
+    env = dict(os.environ, RSTR_LIBNAME="librestir_b200_fmad.so", RSTR_FMAD="true")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ref_cuda_compare.py"), "denoisers", work, "6"],
+                       capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["radiance"]["pixels_within_1e-4_rel"] >= 0.9999            # the filters' input is the reference's
+    for n in ("eaw", "svgf"):
+        assert out[n]["pixels_within_1e-4_rel"] >= 0.999, (n, out[n])
+        assert abs(out[n]["mean_ref"] - out[n]["mean_b200"]) <= 1e-4 * abs(out[n]["mean_ref"]), (n, out[n])
+    assert out["svgf_var"]["pixels_within_1e-4_rel"] >= 0.99, out["svgf_var"]
