@@ -469,7 +469,7 @@ def run_b200(args):
                 best = (float(measured.max()), list(bounds))
             if it == args.refine or measured.max() / measured.mean() < 1.02:
                 break
-            row_cost = strips.refine_row_cost(row_cost, bounds, measured)
+            row_cost = strips.refine_row_cost(row_cost, bounds, measured, damping=1.0 if it == 0 else 0.6)
             bounds = strips.balanced_bounds(row_cost, world, min_rows=max(8, halo))
             make_strip()
         if list(bounds) != best[1]:          # the cuts whose slowest rank was fastest, not simply the last ones tried
@@ -735,7 +735,7 @@ def main():
     ap.add_argument("--no-targets", action="store_true", help="N = 1: skip the `targets` block (device-timed config4_1080p / config3 / config2)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: halo rows / gather as the library's peer stores over NVLink (default) or as NCCL send/recv issued from here (A/B)")
     ap.add_argument("--uniform-strips", action="store_true", help="equal-height strips instead of cost-balanced cuts (N > 1)")
-    ap.add_argument("--refine", type=int, default=6, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
+    ap.add_argument("--refine", type=int, default=8, help="N > 1: closed-loop refinements of the strip cuts before the timed run")
     ap.add_argument("--pipeline", default="auto", choices=["auto", "staged", "fused"], help="phase A as the staged kernel pipeline, as one fused kernel, or chosen by scene size (default)")
     ap.add_argument("--bands", type=int, default=1, help="row bands of the staged pipeline whose queue kernels overlap the next band's primary walk (1 = none)")
     ap.add_argument("--no-fusion", action="store_true", help="separate G-buffer and phase-A kernels instead of the fused one (A/B)")

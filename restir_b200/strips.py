@@ -51,16 +51,19 @@ def balanced_bounds(row_cost, world: int, min_rows: int = 8) -> list[int]:
     return b
 
 
-def refine_row_cost(row_cost, bounds, measured):
+def refine_row_cost(row_cost, bounds, measured, damping: float = 1.0):
     """One step of the closed loop that places the strip cuts: the row costs inside strip r are rescaled so that they sum
     to the time rank r was MEASURED to take with the current cuts (the model keeps its shape inside a strip, its level
-    comes from the measurement).  Returns a new array; cut again with :func:`balanced_bounds`."""
+    comes from the measurement).  ``damping`` < 1 applies only that power of the correction: a strip whose cost sits in a
+    few of its rows (600 rows of sky above 40 rows at the horizon) otherwise overshoots from one side of the balance to
+    the other.  Returns a new array; cut again with :func:`balanced_bounds`."""
     cost = np.array(row_cost, np.float64)
+    cost *= float(np.sum(measured)) / max(float(cost.sum()), 1e-300)          # same units as the measurement
     for r in range(len(bounds) - 1):
         seg = slice(bounds[r], bounds[r + 1])
         total = cost[seg].sum()
         if total > 0:
-            cost[seg] *= float(measured[r]) / total
+            cost[seg] *= (float(measured[r]) / total) ** damping
         else:
             cost[seg] = float(measured[r]) / max(bounds[r + 1] - bounds[r], 1)
     return cost
