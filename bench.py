@@ -46,7 +46,12 @@ BYTES_PER_PIXEL = {0: 96, 1: 176, 2: 248, 3: 248}
 # ... split per kernel for the spatiotemporal frame: G-buffer write 36 | phase A: own G-buffer 24 + previous G-buffer 20 +
 # previous reservoir 36 + post-temporal reservoir 36 + history reservoir 36 = 152 | phase B: reservoir 36 + albedo 12 + radiance 12 = 60
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {("config2", "ris"): (452.3e6, "profiles/r01_prof_config2_r5.summary.txt (k_gbuffer_restir_a: 66.0 MB read + 386.3 MB written)")}
+NCU_TRAFFIC = {("config2", "ris"): (452.3e6, "profiles/r01_prof_config2_r5.summary.txt (k_gbuffer_restir_a: 66.0 MB read + 386.3 MB written; round-1 capture of the fused kernel)"),
+               # the staged phase A: four launches, DRAM bytes summed.  Above the 1559 MB of per-pixel algorithmic bytes because it also counts the
+               # scene (tree / triangles / light records streamed from HBM: 216 + 165 + 303 MB read) and the planes that carry a pixel from one
+               # stage to the next (hit records, the staged reservoir, the queue: the price of cutting the frame where the parallelism changes)
+               ("config4", "ris"): (2897.1e6, "profiles/r02_c25_prof_k_{primary,candidates,shadow,temporal}_config4.summary.txt: 914.8 + 498.5 + 351.6 + 1132.1 MB (read + written)"),
+               ("config4", "spatial"): (699.0e6, "profiles/r02_c25_prof_k_restir_b_config4.summary.txt (652.6 MB read + 46.4 MB written)")}
 KERNEL_BYTES_PER_PIXEL = {"gbuffer": 36, "ris": {0: 60, 1: 140, 2: 116, 3: 152}, "spatial": 60}
 
 

@@ -525,7 +525,7 @@ int rstr_restir_phase_b_pass(RstrFrame* f, const RstrCamera* cam, const RstrPara
         if (passes > 1 && (rc = rsEnsureTemp2(f))) return rc;
         FrameDev d = rsToFrameDev(f, f->row0, f->row1);
         ResvD* buf[2] = {f->resvTemp, f->resvTemp2};
-        if (pass == 1) { stageBegin(f, RSTR_T_SPATIAL); f->ranSplitB = false; }
+        if (pass == 1) stageBegin(f, RSTR_T_SPATIAL);
         launchRestirB(f->sc->dev, d, *prm, iter, buf[(pass - 1) & 1], buf[pass & 1], pass, pass == passes ? 1 : 0, f->stream);
         g_launches++;
         if (pass == passes) stageEnd(f, RSTR_T_SPATIAL);
@@ -535,24 +535,6 @@ int rstr_restir_phase_b_pass(RstrFrame* f, const RstrCamera* cam, const RstrPara
         f->resvOut ^= 1;                                                   // std::swap, restir.cu:434
         f->first = false;                                                  // restir.cu:436-438
     }
-    return RSTR_OK;
-}
-
-int rsRestirPhaseBRows(RstrFrame* f, const RstrParams* prm, int iter, int rowLo, int rowHi, int piece) {
-    if (rowHi <= rowLo) return RSTR_OK;
-    FrameDev d = rsToFrameDev(f, rowLo, rowHi);
-    const int e = piece == 0 ? 2 * RSTR_T_SPATIAL : 2 * RSTR_T_COUNT;
-    if (piece != 2) cudaEventRecord(f->ev[e], f->stream);                  // piece 2 extends piece 1's interval (two edge bands, back to back)
-    if (piece == 0) { f->ran[RSTR_T_SPATIAL] = true; f->ranSplitB = false; } else f->ranSplitB = true;
-    launchRestirB(f->sc->dev, d, *prm, iter, f->resvTemp, f->resvTemp2, 1, 1, f->stream);
-    cudaEventRecord(f->ev[e + 1], f->stream);
-    g_launches++;
-    CU(cudaGetLastError());
-    return RSTR_OK;
-}
-int rsRestirPhaseBDone(RstrFrame* f) {
-    f->resvOut ^= 1;                                                       // std::swap, restir.cu:434
-    f->first = false;                                                      // restir.cu:436-438
     return RSTR_OK;
 }
 
@@ -812,11 +794,6 @@ int rstr_frame_stage_ms(RstrFrame* f, float* ms, int n) {
     for (int s = 0; s < n && s < RSTR_T_COUNT; s++) {
         ms[s] = 0.f;
         if (f->ran[s]) CU(cudaEventElapsedTime(&ms[s], f->ev[2 * s], f->ev[2 * s + 1]));
-        if (s == RSTR_T_SPATIAL && f->ran[s] && f->ranSplitB) {            // the edge rows of a split pass (strip groups)
-            float extra = 0.f;
-            CU(cudaEventElapsedTime(&extra, f->ev[2 * RSTR_T_COUNT], f->ev[2 * RSTR_T_COUNT + 1]));
-            ms[s] += extra;
-        }
     }
     return RSTR_OK;
 }

@@ -79,8 +79,7 @@ struct RstrFrame {
     bool haveLast = false;
     bool first = true;  // ReSTIRFirstFrame
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[2 * RSTR_T_COUNT + 2] = {};   // begin / end per stage; the last pair: second piece of a split spatial pass
-    bool ranSplitB = false;
+    cudaEvent_t ev[2 * RSTR_T_COUNT] = {};
     cudaEvent_t xfer = nullptr;
     cudaEvent_t marks[8] = {};
     bool ownStream = true;
@@ -97,7 +96,4 @@ rs::CamDev rsToCamDev(const RstrCamera& c);
 extern "C" int rsFlushGBuffer(RstrFrame* f);     // launches a G-buffer render that rstr_gbuffer_render deferred
 extern "C" int rsEnsureTemp2(RstrFrame* f);
 int rsEnsureUploaded(RstrScene* sc);
-// single spatial pass over rows [rowLo, rowHi) only (strip groups: interior rows while the halo rows are still in flight, edge rows
-// after they arrived); piece 0 is timed as RSTR_T_SPATIAL, pieces 1 (+ 2 right behind it) are added to it.  rsRestirPhaseBDone = the end of ReSTIRDirect.
-extern "C" int rsRestirPhaseBRows(RstrFrame* f, const RstrParams* prm, int iter, int rowLo, int rowHi, int piece);
-extern "C" int rsRestirPhaseBDone(RstrFrame* f);          // uploads the host scene on first use (capi.cu)
+         // uploads the host scene on first use (capi.cu)

@@ -385,25 +385,6 @@ static unsigned frameMask(const RstrParams* prm) {
     return mask;
 }
 
-// wait + ONE spatial pass + ack + gbuffer_update.  Only the rows within `halo` of a neighbour read rows that travel: the interior
-// rows are merged and shaded while the halo rows are still in flight (and while a slower neighbour finishes its phase A); the
-// edge rows follow the wait.  Same kernel, same per-pixel work: the frame is unchanged.
-static int frameEndSinglePass(RstrStripGroup* g, const RstrCamera* cam, const RstrParams* prm, int iter) {
-    RstrFrame* f = g->f;
-    int rc;
-    const int lo = g->rank > 0 ? std::min(f->row0 + f->halo, f->row1) : f->row0;
-    const int hi = g->rank + 1 < g->world ? std::max(f->row1 - f->halo, lo) : f->row1;
-    if ((rc = rsRestirPhaseBRows(f, prm, iter, lo, hi, 0))) return rc;
-    if ((rc = rstr_strip_group_wait(g))) return rc;
-    if (hi > lo) {
-        if ((rc = rsRestirPhaseBRows(f, prm, iter, f->row0, lo, 1))) return rc;
-        if ((rc = rsRestirPhaseBRows(f, prm, iter, hi, f->row1, lo > f->row0 ? 2 : 1))) return rc;
-    } else if ((rc = rsRestirPhaseBRows(f, prm, iter, f->row0, f->row1, 0))) return rc;
-    if ((rc = rsRestirPhaseBDone(f))) return rc;
-    if ((rc = rstr_strip_group_ack(g))) return rc;
-    return rstr_gbuffer_update(f, cam);
-}
-
 int rstr_strip_group_frame_begin(RstrStripGroup* g, const RstrCamera* cam, const RstrParams* prm, int looper, int iter) {
     if (!g || !cam || !prm) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_frame_begin: bad argument");
     RstrFrame* f = g->f;
@@ -420,7 +401,6 @@ int rstr_strip_group_frame_end(RstrStripGroup* g, const RstrCamera* cam, const R
     if (!g || !cam || !prm) return rsFail(RSTR_ERR_ARG, "rstr_strip_group_frame_end: bad argument");
     RstrFrame* f = g->f;
     const int passes = (prm->reuse & RSTR_REUSE_SPATIAL) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
-    if (passes == 1 && g->world > 1 && !prm->unbiased) return frameEndSinglePass(g, cam, prm, iter);
     int rc = rstr_strip_group_wait(g);
     if (rc) return rc;
     if (passes > 1 && g->world > 1)
@@ -436,7 +416,6 @@ int rstr_strip_group_frame(RstrStripGroup* g, const RstrCamera* cam, const RstrP
     if (rc) return rc;
     RstrFrame* f = g->f;
     const int passes = (prm->reuse & RSTR_REUSE_SPATIAL) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
-    if (passes == 1 && g->world > 1 && !prm->unbiased) return frameEndSinglePass(g, cam, prm, iter);
     if ((rc = rstr_strip_group_wait(g))) return rc;
     for (int pass = 1; pass <= (passes ? passes : 1); pass++) {
         if ((rc = rstr_restir_phase_b_pass(f, cam, prm, looper, iter, pass))) return rc;

@@ -1,4 +1,5 @@
-"""BASELINE config 5 on N GPUs (torchrun -n N scripts/config5_sweep.py [workload] [frames]; N = 1 works without torchrun):
+"""BASELINE config 5 on N GPUs (torchrun -n N scripts/config5_sweep.py [workload] [frames] [b0,b1,...,bN]; N = 1 works without torchrun;
+the optional third argument gives the strip cuts, e.g. the ones bench.py's closed-loop refinement found on the same box):
 the 4K many-light scene (default workload config4) as image strips through the library's peer data plane,
 
   * spatial-reuse sweep: k = 1..8 neighbours x 1..3 spatial passes, device-timed ms/frame (max over ranks) of the orbit;
@@ -37,7 +38,10 @@ base = rb.Camera.from_scene(sd)
 motion = bench.measure_motion_rows(sc, base, W, H, rb) if world > 1 else 0
 halo = strips.default_halo(radius, motion) if world > 1 else 0
 bounds = strips.uniform_bounds(H, world)
-if world > 1:
+if world > 1 and len(sys.argv) > 3:
+    bounds = [int(v) for v in sys.argv[3].split(",")]
+    assert len(bounds) == world + 1 and bounds[0] == 0 and bounds[-1] == H
+elif world > 1:
     probe = sc.frame(W, H)
     probe.gbuffer_render(base.orbit(0))
     bounds = strips.balanced_bounds(strips.row_cost_from_matid(probe.read("matid"), W), world, min_rows=halo)
@@ -91,21 +95,25 @@ def vsum(x):
 out = {"workload": work, "resolution": [W, H], "n_gpus": world, "strip_bounds": bounds, "halo_rows": halo, "sweep_ms_per_frame": {}, "convergence": {}}
 # ---- sweep: k x passes, orbit, timed on the device
 fr, grp = make()
+f0 = 0          # the orbit runs on across the 24 settings (back and forth over its 60 poses): every frame follows its predecessor
+miss = 0
 for passes in (1, 2, 3):
     for k in range(1, 9):
         prm = rb.default_params(reuse=3, radius=radius, k=k, passes=passes)
-        f0 = 0
         for i in range(4):
             render(fr, grp, base.orbit(bench.orbit_index(f0 + i)), prm, f0 + i, 0)
         fr.sync()
         if world > 1:
             dist.barrier()
+        if f0 == 0:
+            fr.halo_miss_reset()          # frame 0 has no predecessor
         fr.mark(0)
         n = 24
         for i in range(4, 4 + n):
             render(fr, grp, base.orbit(bench.orbit_index(f0 + i)), prm, f0 + i, 0)
         fr.mark(1)
         out["sweep_ms_per_frame"]["k%d_p%d" % (k, passes)] = round(vmax(fr.elapsed_ms(0, 1)) / n, 4)
+        f0 += 4 + n
 miss = fr.halo_miss()
 close(fr, grp)
 out["halo_miss"] = int(vsum(float(miss)))

@@ -1,0 +1,10 @@
+set -x
+run() { # lib workload tag
+  RSTR_LIBNAME=$1 timeout 300 python bench.py --workload $2 --steps 40 --warmup 8 --quick > gpurun_out/r02_c22_bench_$3.json 2> gpurun_out/r02_c22_bench_$3.err
+  python -c "import sys,json; d=json.loads(open('gpurun_out/r02_c22_bench_$3.json').read().strip().splitlines()[-1]); print('$3', round(d['ms_per_step'],4), {k: round(v,4) for k,v in d['stage_ms'].items()}, round(d['e2e']['ms_per_step'],4), d.get('build_id'))" | tee -a gpurun_out/r02_c22_ab.txt
+}
+for v in "" _shad10 _shad12 _cand10 _prim10; do
+  run librestir_b200$v.so config4_1080p 1080p$v
+  run librestir_b200$v.so config4 4k$v
+done
+run librestir_b200.so config4_1080p 1080p_again
