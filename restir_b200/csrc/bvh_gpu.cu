@@ -22,7 +22,9 @@ using namespace rs;
 
 namespace {
 
-#define RS_PLOC_RADIUS 16
+#ifndef RS_PLOC_RADIUS
+#define RS_PLOC_RADIUS 16      /* search window of the clustering, in sorted positions on each side */
+#endif
 #define RS_GPU_MAX_LEAF 4
 
 struct GBox { float lo[3], hi[3]; };
