@@ -208,7 +208,13 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- B200 arm
-PROFILE_POSES = (0, 10, 20, 30, 40, 50)
+def window_frames(k0: int, n: int, count: int = 6):
+    """Up to `count` frame indices spread over [k0, k0 + n): the stretch of the orbit that is about to be rendered.  The strip
+    cuts are placed for that stretch (the balance moves with the camera: cuts that are right for the orbit's average leave the
+    slowest rank 5 % above the mean on any one stretch of it)."""
+    n = max(int(n), 1)
+    step = max(1, n // count)
+    return list(range(k0, k0 + n, step))[:count]
 PIPELINES = {"auto": None, "staged": True, "fused": False}
 
 
@@ -358,12 +364,12 @@ def run_b200(args):
     bounds = strips.uniform_bounds(H, world)
     if world > 1 and not args.uniform_strips:
         # measured cost profile: a few frames of the real pipeline on the full image with the kernels' cycle accounting
-        # on (SM cycles every 16x8-pixel block held its SM slot, per group of 8 rows), at poses spread over the orbit (the
-        # cuts are fixed for the run); the cuts then give every rank the same summed cost.  Equal-height strips balance
+        # on (SM cycles every 16x8-pixel block held its SM slot, per group of 8 rows), at poses spread over the stretch of the
+        # orbit that is timed first; the cuts then give every rank the same summed cost.  Equal-height strips balance
         # badly: sky rows are almost free.  All ranks measure, the sum is all-reduced so that they agree on the cuts.
         pf = sc.frame(W, H)
         pf.row_cost(enable=True)
-        for pose in PROFILE_POSES:
+        for pose in window_frames(args.warmup, args.steps):
             for kk in (pose, pose + 1):
                 cam = base.orbit(orbit_index(kk))
                 pf.gbuffer_render(cam); pf.restir_direct(cam, prm, kk, 0); pf.gbuffer_update(cam)
@@ -457,29 +463,35 @@ def run_b200(args):
     # (These frames jump between camera poses: their reprojections can leave the halo, which is why the halo-miss counter
     # is reset after the warm-up below and checked only over consecutive frames of the orbit.)
     refine_log = []
-    if row_cost is not None:
+
+    def refine_cuts(k0, n, tag):
+        # measured on the very frames that follow (two lead-in frames for the history, then the stretch itself, at most 120 frames)
+        nonlocal row_cost, bounds
         best = None
         for it in range(args.refine + 1):
             tot, cnt = 0.0, 0
-            for pose in PROFILE_POSES:
-                for kk in (pose, pose + 1):
-                    frame(kk)
-                tot += sum(v for n, v in fr.stage_ms().items() if n in ("gbuffer", "ris", "spatial")); cnt += 1
+            for kk in range(max(k0 - 2, 0), k0 + min(n, 120)):
+                frame(kk)
+                if kk >= k0:
+                    tot += sum(v for nm, v in fr.stage_ms().items() if nm in ("gbuffer", "ris", "spatial")); cnt += 1
             t = torch.tensor([tot / cnt], device="cuda", dtype=torch.float64)
             allt = [torch.zeros_like(t) for _ in range(world)]
             dist.all_gather(allt, t)
             measured = np.array([float(x.item()) for x in allt])
-            refine_log.append({"bounds": list(bounds), "kernel_ms_per_rank": [round(float(x), 3) for x in measured]})
+            refine_log.append({"window": tag, "bounds": list(bounds), "kernel_ms_per_rank": [round(float(x), 3) for x in measured]})
             if best is None or measured.max() < best[0]:
                 best = (float(measured.max()), list(bounds))
             if it == args.refine or measured.max() / measured.mean() < 1.02:
                 break
-            row_cost = strips.refine_row_cost(row_cost, bounds, measured, damping=1.0 if it == 0 else 0.6)
+            row_cost = strips.refine_row_cost(row_cost, bounds, measured, damping=1.0 if (it == 0 and tag == "value") else 0.6)
             bounds = strips.balanced_bounds(row_cost, world, min_rows=max(8, halo))
             make_strip()
         if list(bounds) != best[1]:          # the cuts whose slowest rank was fastest, not simply the last ones tried
             bounds = best[1]
             make_strip()
+
+    if row_cost is not None:
+        refine_cuts(args.warmup, args.steps, "value")
 
     k = 0
     for _ in range(args.warmup):
@@ -521,6 +533,11 @@ def run_b200(args):
     else:
         shaded = shaded_local
     # ---- pass 3: end to end through the host-facing call (N = 1) / strips gathered to rank 0 (N > 1)
+    miss_before_e2e = fr.halo_miss()
+    bounds_value = list(bounds)
+    npix_value = (rows[1] - rows[0]) * W     # rank 0's strip while `value` and the stage times were measured
+    if row_cost is not None:                 # the end-to-end frames lie further along the orbit: cuts for that stretch
+        refine_cuts(k, 6 + args.steps, "e2e")
     npix_local = (rows[1] - rows[0]) * W
     e2e_ms = e2e_sync_ms = None
     if world == 1:
@@ -571,6 +588,8 @@ def run_b200(args):
 
         e2e_loop(6)
         barrier()
+        if row_cost is not None:
+            fr.halo_miss_reset()             # the refinement frames above jumped between poses
         t0 = time.perf_counter()
         e2e_loop(args.steps)
         barrier()
@@ -612,6 +631,8 @@ def run_b200(args):
         for _ in range(3):
             e2e_frame(k); k += 1
         barrier(); side.synchronize()
+        if row_cost is not None:
+            fr.halo_miss_reset()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_frame(k); k += 1
@@ -620,7 +641,7 @@ def run_b200(args):
         e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
         if rank == 0:
             assert int(host.max()) > 0
-    halo_miss = fr.halo_miss()
+    halo_miss = fr.halo_miss() + (miss_before_e2e if row_cost is not None else 0)     # (re-cut strips are new frames: their counter starts at 0)
     peer_error = bool(grp.error()) if grp is not None else False
     if world > 1:
         t = torch.tensor([halo_miss, int(peer_error)], device="cuda", dtype=torch.int64)
@@ -635,7 +656,7 @@ def run_b200(args):
         fused = stage_ms["gbuffer"] == 0.0 and stage_ms["ris"] > 0.0      # G-buffer + phase A ran as one kernel
         if fused and dom == "ris":
             bpp += KERNEL_BYTES_PER_PIXEL["gbuffer"]
-        strip_px = npix_local
+        strip_px = npix_value
         achieved = bpp * strip_px / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
         frame_bytes = BYTES_PER_PIXEL[reuse] * P
         info = sc.info
@@ -646,7 +667,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
             "pipeline": args.pipeline,
-            "strips": {"parallelism": "strips%d" % world, "exchange": None if world == 1 else ("peer stores over NVLink (rstr_strip_group)" if peer else "NCCL send/recv"), "halo_rows": halo, "motion_rows_bound": motion_rows, "strip_bounds": bounds,
+            "strips": {"parallelism": "strips%d" % world, "exchange": None if world == 1 else ("peer stores over NVLink (rstr_strip_group)" if peer else "NCCL send/recv"), "halo_rows": halo, "motion_rows_bound": motion_rows, "strip_bounds": bounds_value, "strip_bounds_e2e": bounds,
                        "gbuffer_halo": None if world == 1 else ("rendered locally" if args.render_halo else "received from the neighbours"),
                        "l2": "no explicit flush: the per-frame pixel planes (%.0f MB) exceed the 126 MB L2" % (P * 212 / 1e6)},
             "e2e": {"value": P / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms, "ms_per_step_synchronous_call": e2e_sync_ms,

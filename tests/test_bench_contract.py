@@ -39,4 +39,6 @@ def test_orbit_clock_sweeps_the_60_frame_arc_back_and_forth():
     idx = [bench.orbit_index(k) for k in range(240)]
     assert idx[:60] == list(range(60)) and idx[60:120] == list(range(59, -1, -1)) and idx[120:] == idx[:120]
     assert max(abs(a - b) for a, b in zip(idx, idx[1:])) <= 1          # consecutive frames stay temporally coherent
-    assert set(bench.PROFILE_POSES) <= set(range(60))
+    w = bench.window_frames(5, 20)                                       # the driver's --warmup 5 --steps 20: cuts for the timed stretch
+    assert 1 <= len(w) <= 6 and w[0] == 5 and all(5 <= k < 25 for k in w) and w == sorted(w)
+    assert bench.window_frames(0, 1) == [0] and len(bench.window_frames(51, 26)) <= 6
