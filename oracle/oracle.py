@@ -117,6 +117,14 @@ class Oracle:
         L.orc_last_trace_stats.argtypes = [vp, vp, vp, vp]
         L.orc_alias_build.restype = fp
         L.orc_alias_build.argtypes = [ip, vp, vp]
+        L.orc_gi_create.restype = vp
+        L.orc_gi_create.argtypes = [vp]
+        L.orc_gi_destroy.argtypes = [vp]
+        L.orc_restir_indirect.argtypes = [vp, C.POINTER(OrcCamera), ip, ip, ip, ip]
+        L.orc_gi_indirect.restype = vp
+        L.orc_gi_indirect.argtypes = [vp]
+        L.orc_gi_reservoirs.restype = vp
+        L.orc_gi_reservoirs.argtypes = [vp]
         if kind == "port":            # the image-space filters are restated in the port only (denoiser.cu's kernels cannot be built by g++)
             L.orc_denoiser_create.restype = vp
             L.orc_denoiser_create.argtypes = [vp, ip]
@@ -305,6 +313,28 @@ class OracleFrame:
         if name == "depth":
             return Oracle._view(ptr, np.float32, (P,))
         return Oracle._view(ptr, RESERVOIR_DTYPE, (P,))
+
+
+class OracleGI:
+    """ReSTIRIndirect (restir.cu:448-476) on an oracle frame: indirect illumination + the indirect reservoirs."""
+
+    def __init__(self, frame: OracleFrame):
+        self.frame, self.lib = frame, frame.lib
+        self.g = self.lib.orc_gi_create(frame.f)
+
+    def close(self):
+        if self.g:
+            self.lib.orc_gi_destroy(self.g)
+            self.g = None
+
+    def restir_indirect(self, cam, looper: int, it: int = 0, max_depth: int = 3, reuse: int = 1):
+        self.lib.orc_restir_indirect(self.g, C.byref(cam), looper, it, max_depth, reuse)
+
+    def indirect(self) -> np.ndarray:
+        return Oracle._view(self.lib.orc_gi_indirect(self.g), np.float32, (self.frame.w * self.frame.h, 3))
+
+    def reservoirs(self) -> np.ndarray:
+        return Oracle._view(self.lib.orc_gi_reservoirs(self.g), np.float32, (self.frame.w * self.frame.h, 17))
 
 
 class OracleDenoiser:

@@ -522,6 +522,160 @@ void orc_pathtrace_direct(OrcFrame* f, const OrcCamera* ocam, int looper, int it
     }
 }
 
+/* ================================================================ ReSTIR GI: ReSTIRIndirectKernel (restir.cu:242-416) restated over the
+ * reference's OWN Material::{sample, pdf, BSDF}, DevScene::{intersect, sampleDirectLight, environmentMapPdf, getPrimitiveArea,
+ * getTexturedMaterialAndSurface}, Math::{powerHeuristic, pdfAreaToSolidAngle}, Reservoir<IndirectLiSample> and IndirectLiSample.
+ * Same documented deviation as the port: a pixel whose jittered ray leaves the scene or hits an emitter writes indirect = 0
+ * (the kernel would shade a history sample with uninitialised primMaterial / primWo there). */
+using IndirectReservoir = Reservoir<IndirectLiSample>;
+struct OrcGI {
+    OrcFrame* f;
+    std::vector<IndirectReservoir> resv, lastResv;
+    std::vector<glm::vec3> indirect;
+    std::vector<float> exportBuf;
+    bool first = true;
+};
+static glm::vec3 draw3(Sampler& rng) { float a = sample1D(rng), b = sample1D(rng), c = sample1D(rng); return glm::vec3(a, b, c); }   /* nvcc order */
+
+OrcGI* orc_gi_create(OrcFrame* f) {
+    OrcGI* g = new OrcGI;
+    size_t P = f->albedo.size();
+    g->f = f; g->resv.assign(P, IndirectReservoir()); g->lastResv.assign(P, IndirectReservoir()); g->indirect.assign(P, glm::vec3(0.f));
+    return g;
+}
+void orc_gi_destroy(OrcGI* g) { delete g; }
+
+void orc_restir_indirect(OrcGI* g, const OrcCamera* ocam, int looper, int iter, int maxDepth, int reuseState) {
+    OrcFrame* f = g->f;
+    Camera cam = *(const Camera*)ocam;
+    DevScene* scene = &f->sc->dev;
+    GBuffer gBuffer = f->g;
+    const bool first = g->first;
+    IndirectReservoir* temporalReservoir = g->resv.data();
+    IndirectReservoir* lastTemporalReservoir = g->lastResv.data();
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < cam.resolution.y; y++)
+        for (int x = 0; x < cam.resolution.x; x++) {
+            IndirectLiSample indirectSample;
+            int index = y * cam.resolution.x + x;
+            Sampler rng = makeSeededRandomEngine(looper, index, 0, scene->sampleSequence);
+            Ray ray = cam.sample(x, y, draw4(rng));
+            Intersection intersec;
+            scene->intersect(ray, intersec);
+            bool shaded = false, primSampleDelta = false;
+            float primSamplePdf = 1.f;
+            glm::vec3 primWo(0.f);
+            Material primMaterial;
+            if (intersec.primId != NullPrimitive) {
+                Material material = scene->getTexturedMaterialAndSurface(intersec);
+                if (material.type != Material::Type::Light) {
+                    shaded = true;
+                    glm::vec3 throughput(1.f);
+                    intersec.wo = -ray.direction;
+                    primWo = -ray.direction;
+                    primMaterial = material;
+                    for (int depth = 1; depth <= maxDepth; depth++) {
+                        bool deltaBSDF = (material.type == Material::Type::Dielectric);
+                        if (material.type != Material::Type::Dielectric && glm::dot(intersec.norm, intersec.wo) < 0.f) intersec.norm = -intersec.norm;
+                        if (!deltaBSDF && depth > 1) {
+                            glm::vec3 radiance;
+                            glm::vec3 wi;
+                            glm::vec4 r4 = draw4(rng);
+                            float lightPdf = scene->sampleDirectLight(intersec.pos, r4, radiance, wi);
+                            if (lightPdf > 0.f) {
+                                float BSDFPdf = material.pdf(intersec.norm, intersec.wo, wi);
+                                indirectSample.Lo += throughput * material.BSDF(intersec.norm, intersec.wo, wi) *
+                                    radiance * Math::satDot(intersec.norm, wi) / lightPdf * Math::powerHeuristic(lightPdf, BSDFPdf);
+                            }
+                        }
+                        BSDFSample sample;
+                        sample.dir = glm::vec3(0.f); sample.bsdf = glm::vec3(0.f); sample.pdf = 0.f; sample.type = 0;
+                        glm::vec3 r3 = draw3(rng);
+                        material.sample(intersec.norm, intersec.wo, r3, sample);
+                        if (sample.type == BSDFSampleType::Invalid) break;
+                        else if (sample.pdf < 1e-8f) break;
+                        bool deltaSample = (sample.type & BSDFSampleType::Specular);
+                        if (depth > 1) throughput *= sample.bsdf / sample.pdf * (deltaSample ? 1.f : Math::absDot(intersec.norm, sample.dir));
+                        else { primSamplePdf = sample.pdf; primSampleDelta = deltaSample; indirectSample.xv = intersec.pos; indirectSample.nv = intersec.norm; }
+                        ray = makeOffsetedRay(intersec.pos, sample.dir);
+                        glm::vec3 curPos = intersec.pos;
+                        scene->intersect(ray, intersec);
+                        intersec.wo = -ray.direction;
+                        if (intersec.primId == NullPrimitive) {
+                            if (scene->envMap != nullptr) {
+                                glm::vec3 radiance = scene->envMap->linearSample(Math::toPlane(ray.direction)) * throughput;
+                                float weight = deltaSample ? 1.f : Math::powerHeuristic(sample.pdf, scene->environmentMapPdf(ray.direction));
+                                indirectSample.Lo += radiance * weight;
+                            }
+                            break;
+                        }
+                        material = scene->getTexturedMaterialAndSurface(intersec);
+                        if (material.type == Material::Type::Light) {
+                            if (glm::dot(intersec.norm, ray.direction) < 0.f) break;      /* SCENE_LIGHT_SINGLE_SIDED */
+                            glm::vec3 radiance = material.baseColor;
+                            float weight = (deltaSample || depth == 1) ? 1.f : Math::powerHeuristic(
+                                sample.pdf,
+                                Math::pdfAreaToSolidAngle(Math::luminance(radiance) * scene->sumLightPowerInv * scene->getPrimitiveArea(intersec.primId), curPos, intersec.pos, intersec.norm));
+                            indirectSample.Lo += radiance * throughput * weight;
+                            if (depth == 1) { indirectSample.xs = intersec.pos; indirectSample.ns = intersec.norm; }
+                            break;
+                        }
+                        if (depth == 1) { indirectSample.xs = intersec.pos; indirectSample.ns = intersec.norm; }
+                    }
+                }
+            }
+            IndirectReservoir reservoir;
+            float sampleWeight = 0.f;
+            if (!indirectSample.invalid()) {
+                sampleWeight = IndirectReservoir::toScalar(indirectSample.Lo / primSamplePdf);
+                if (isnan(sampleWeight) || sampleWeight < 0.f) sampleWeight = 0.f;
+            }
+            reservoir.update(indirectSample, sampleWeight, sample1D(rng));
+            if (!first && (reuseState & ReservoirReuse::Temporal)) {
+                int primId = gBuffer.primId()[index];
+                int lastIdx = gBuffer.devMotion[index];
+                bool diff = false;
+                if (lastIdx < 0) diff = true;
+                else if (primId <= NullPrimitive) diff = true;
+                else if (gBuffer.lastPrimId()[lastIdx] != primId) diff = true;
+                else {
+                    glm::vec3 norm = DECODE_NORM(gBuffer.normal()[index]);
+                    glm::vec3 lastNorm = DECODE_NORM(gBuffer.lastNormal()[lastIdx]);
+                    float depth = gBuffer.depth()[index];
+                    float pdepth = gBuffer.lastDepth()[lastIdx];
+                    if (Math::absDot(norm, lastNorm) < .9f || glm::abs(pdepth - depth) > depth * .1f) diff = true;
+                }
+                IndirectReservoir tempReservoir = diff ? IndirectReservoir() : lastTemporalReservoir[lastIdx];
+                if (!tempReservoir.invalid()) reservoir.merge(tempReservoir, sample1D(rng));
+            }
+            glm::vec3 indirect(0.f);
+            IndirectLiSample sample = reservoir.sample;
+            reservoir.clamp<20>();
+            if (shaded && !reservoir.invalid()) {
+                glm::vec3 primWi = glm::normalize(sample.xs - sample.xv);
+                indirect = reservoir.sample.Lo / IndirectReservoir::toScalar(reservoir.sample.Lo) * reservoir.weight / static_cast<float>(reservoir.numSamples);
+                indirect *= primMaterial.BSDF(sample.nv, primWo, primWi) * (primSampleDelta ? 1.f : Math::satDot(sample.nv, primWi));
+            }
+            if (Math::hasNanOrInf(indirect)) indirect = glm::vec3(0.f);
+            temporalReservoir[index] = reservoir;
+            g->indirect[index] = (g->indirect[index] * float(iter) + indirect) / float(iter + 1);
+        }
+    std::swap(g->resv, g->lastResv);
+    g->first = false;
+}
+const float* orc_gi_indirect(OrcGI* g) { return &g->indirect[0].x; }
+const float* orc_gi_reservoirs(OrcGI* g) {
+    const size_t P = g->lastResv.size();
+    g->exportBuf.resize(P * 17);
+    for (size_t i = 0; i < P; i++) {
+        const IndirectReservoir& r = g->lastResv[i];
+        const glm::vec3 v[5] = {r.sample.Lo, r.sample.xv, r.sample.nv, r.sample.xs, r.sample.ns};
+        for (int k = 0; k < 5; k++) { g->exportBuf[i * 17 + 3 * k] = v[k].x; g->exportBuf[i * 17 + 3 * k + 1] = v[k].y; g->exportBuf[i * 17 + 3 * k + 2] = v[k].z; }
+        g->exportBuf[i * 17 + 15] = (float)r.numSamples; g->exportBuf[i * 17 + 16] = r.weight;
+    }
+    return g->exportBuf.data();
+}
+
 const void* orc_frame_buffer(OrcFrame* f, int which) {
     const int cur = f->g.frameIdx;
     switch (which) {

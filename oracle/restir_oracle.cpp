@@ -1338,6 +1338,294 @@ int orc_occluded(const OrcScene* sc, const float* x, const float* y) {
 
 } // extern "C"
 
+/* ================================================================ ReSTIR GI (restir.cu:232-416, 448-476; material.h:122-256)
+ * ReSTIRIndirectKernel as the reference ships it: commented out at its call site (main.cpp:168) and with Settings::traceDepth = 0
+ * (common.cpp:3) a no-op until the GUI raises the depth.  Restated with the depth as an argument.  One deviation: the kernel jumps
+ * to WriteSample past the initialisation of primMaterial / primWo / primSampleDelta when the jittered ray leaves the scene or
+ * hits an emitter (undefined behaviour if a history sample is then shaded with them); such a pixel writes indirect = 0 here. */
+struct BsdfSample { V3 dir, bsdf; float pdf; unsigned type; };
+enum { BS_Diffuse = 1, BS_Glossy = 2, BS_Specular = 4, BS_Reflection = 16, BS_Transmission = 32, BS_Invalid = 1 << 15 };   /* material.h:15-24 */
+
+static inline V3 matVec(V3 c0, V3 c1, V3 c2, V3 v) {                 /* type_mat3x3.inl operator*(mat3, vec3) */
+    return {c0.x * v.x + c1.x * v.y + c2.x * v.z, c0.y * v.x + c1.y * v.y + c2.y * v.z, c0.z * v.x + c1.z * v.y + c2.z * v.z};
+}
+static inline V3 reflectG(V3 I, V3 N) { return I - N * dot(N, I) * 2.f; }                     /* func_geometric.inl:176 */
+static inline V3 sampleHemisphereCosine(V3 n, float rx, float ry) {                          /* mathUtil.h:128-132, 157-161 */
+    float r = sqrtf(rx), theta = ry * Pi * 2.0f;
+    V2 d = {cosf(theta) * r, sinf(theta) * r};
+    float z = sqrtf(1.f - (d.x * d.x + d.y * d.y));
+    return localToWorld(n, v3(d.x, d.y, z));
+}
+static inline float fresnelExact(float cosIn, float ior) {                                    /* material.h:43-60 (the #if tests a misspelt macro: this branch) */
+    if (cosIn < 0) { ior = 1.f / ior; cosIn = -cosIn; }
+    float sinIn = sqrtf(1.f - cosIn * cosIn);
+    float sinTr = sinIn / ior;
+    if (sinTr >= 1.f) return 1.f;
+    float cosTr = sqrtf(1.f - sinTr * sinTr);
+    float a = (cosIn - ior * cosTr) / (cosIn + ior * cosTr), b = (ior * cosIn - cosTr) / (ior * cosIn + cosTr);
+    return (a * a + b * b) * .5f;
+}
+static inline bool refractM(V3 n, V3 wi, float ior, V3& wt) {                                 /* mathUtil.h:163-180 */
+    float cosIn = dot(n, wi);
+    if (cosIn < 0) ior = 1.f / ior;
+    float sin2In = gmax(0.f, 1.f - cosIn * cosIn);
+    float sin2Tr = sin2In / (ior * ior);
+    if (sin2Tr >= 1.f) return false;
+    float cosTr = sqrtf(1.f - sin2Tr);
+    if (cosIn < 0) cosTr = -cosTr;
+    wt = normalize(-wi / ior + n * (cosIn / ior - cosTr));
+    return true;
+}
+static inline float GTR2Pdf(V3 n, V3 m, V3 wo, float alpha) {                                 /* material.h:82-85 */
+    return GTR2Distrib(dot(n, m), alpha) * schlickG(dot(n, wo), alpha) * absDot(m, wo) / absDot(n, wo);
+}
+static V3 GTR2Sample(V3 n, V3 wo, float alpha, float rx, float ry) {                          /* material.h:93-112 */
+    V3 t0 = (fabsf(n.y) > 0.9999f) ? v3(0.f, 0.f, 1.f) : v3(0.f, 1.f, 0.f);                   /* localRefMatrix, mathUtil.h:146-151 */
+    V3 b0 = normalize(cross(n, t0));
+    t0 = cross(b0, n);
+    const V3 m0 = t0, m1 = b0, m2 = n;                                                        /* columns */
+    /* glm::inverse(mat3), type_mat3x3.inl:37-57 (m[c][r]) */
+    const float m00 = m0.x, m01 = m0.y, m02 = m0.z, m10 = m1.x, m11 = m1.y, m12 = m1.z, m20 = m2.x, m21 = m2.y, m22 = m2.z;
+    float ood = 1.f / (+m00 * (m11 * m22 - m21 * m12) - m10 * (m01 * m22 - m21 * m02) + m20 * (m01 * m12 - m11 * m02));
+    V3 i0, i1, i2;                                                                            /* columns of the inverse */
+    i0.x = +(m11 * m22 - m21 * m12) * ood; i1.x = -(m10 * m22 - m20 * m12) * ood; i2.x = +(m10 * m21 - m20 * m11) * ood;
+    i0.y = -(m01 * m22 - m21 * m02) * ood; i1.y = +(m00 * m22 - m20 * m02) * ood; i2.y = -(m00 * m21 - m20 * m01) * ood;
+    i0.z = +(m01 * m12 - m11 * m02) * ood; i1.z = -(m00 * m12 - m10 * m02) * ood; i2.z = +(m00 * m11 - m10 * m01) * ood;
+    V3 vh = normalize(matVec(i0, i1, i2, wo) * v3(alpha, alpha, 1.f));
+    float lenSq = vh.x * vh.x + vh.y * vh.y;
+    V3 t = lenSq > 0.f ? v3(-vh.y, vh.x, 0.f) / sqrtf(lenSq) : v3(1.f, 0.f, 0.f);
+    V3 b = cross(vh, t);
+    float r = sqrtf(rx), theta = ry * Pi * 2.0f;                                              /* toConcentricDisk */
+    V2 p = {cosf(theta) * r, sinf(theta) * r};
+    float s = 0.5f * (vh.z + 1.f);
+    p.y = (1.f - s) * sqrtf(1.f - p.x * p.x) + s * p.y;
+    V3 h = t * p.x + b * p.y + vh * sqrtf(gmax(0.f, 1.f - (p.x * p.x + p.y * p.y)));
+    h = v3(h.x * alpha, h.y * alpha, gmax(0.f, h.z));
+    return normalize(matVec(m0, m1, m2, h));
+}
+static float materialPdf(const OrcMaterial& m, V3 n, V3 wo, V3 wi) {                          /* material.h:230-240 */
+    switch (m.type) {
+    case 0: return satDot(n, wi) * 1.f / Pi;
+    case 1: {
+        V3 h = normalize(wo + wi);
+        return mixf(satDot(n, wi) * 1.f / Pi, GTR2Pdf(n, h, wo, m.roughness * m.roughness) / (4.f * absDot(h, wo)), 1.f / (2.f - m.metallic));
+    }
+    default: return 0.f;
+    }
+}
+static void materialSample(const OrcMaterial& m, V3 baseColor, V3 n, V3 wo, float rx, float ry, float rz, BsdfSample& s) {   /* material.h:242-256 */
+    switch (m.type) {
+    case 0:                                                                                   /* :130-135 */
+        s.dir = sampleHemisphereCosine(n, rx, ry);
+        s.bsdf = baseColor * 1.f / Pi;
+        s.pdf = satDot(n, s.dir) * 1.f / Pi;
+        s.type = BS_Diffuse | BS_Reflection;
+        return;
+    case 1: {                                                                                 /* :197-216 */
+        float alpha = m.roughness * m.roughness;
+        if (rz > (1.f / (2.f - m.metallic))) s.dir = sampleHemisphereCosine(n, rx, ry);
+        else {
+            V3 h = GTR2Sample(n, wo, alpha, rx, ry);
+            s.dir = -reflectG(wo, h);
+        }
+        if (dot(n, s.dir) < 0.f) s.type = BS_Invalid;
+        else {
+            s.bsdf = materialBSDF(m, baseColor, n, wo, s.dir);
+            s.pdf = materialPdf(m, n, wo, s.dir);
+            s.type = BS_Glossy | BS_Reflection;
+        }
+        return;
+    }
+    case 2: {                                                                                 /* :145-169 */
+        float pdfRefl = fresnelExact(dot(n, wo), m.ior);
+        s.bsdf = baseColor;
+        if (rz < pdfRefl) {
+            s.dir = reflectG(-wo, n);
+            s.type = BS_Specular | BS_Reflection;
+            s.pdf = 1.f;
+        } else {
+            if (!refractM(n, wo, m.ior, s.dir)) { s.type = BS_Invalid; return; }
+            float eta = m.ior;
+            if (dot(n, wo) < 0) eta = 1.f / eta;
+            s.bsdf = s.bsdf / (eta * eta);
+            s.type = BS_Specular | BS_Transmission;
+            s.pdf = 1.f;
+        }
+        return;
+    }
+    default: s.type = BS_Invalid;
+    }
+}
+static inline float powerHeuristic(float f, float g) { float f2 = f * f; return f2 / (f2 + g * g); }   /* mathUtil.h:81-84 */
+
+struct IndSample { V3 Lo, xv, nv, xs, ns; IndSample() { Lo = xv = nv = xs = ns = v3(0.f); } bool invalid() const { return luminance(Lo) < 1e-8f; } };   /* restir.h:13-27 */
+struct IndResv {                                                                              /* Reservoir<IndirectLiSample>, restir.h:29-117 */
+    IndSample s; int M = 0; float w = 0.f;
+    void update(const IndSample& ns, float nw, float r) { w += nw; M++; if (r * w < nw) s = ns; }
+    bool invalid() const { return isNanOrInf(w) || w < 0.f; }
+    void merge(const IndResv& rhs, float r) { w += rhs.w; M += rhs.M; if (r * w < rhs.w) s = rhs.s; }
+    void clamp(int val) { if (M > val) { w *= (float)val / M; M = val; } }
+};
+struct OrcGI {
+    OrcFrame* f;
+    std::vector<IndResv> resv, lastResv;      /* devIndTemporalReservoir, devIndLastTemporalReservoir (restir.cu:12-13) */
+    std::vector<V3> indirect;
+    std::vector<float> exportBuf;
+    bool first = true;
+};
+
+extern "C" {
+
+OrcGI* orc_gi_create(OrcFrame* f) {
+    OrcGI* g = new OrcGI;
+    const size_t P = (size_t)f->w * f->h;
+    g->f = f; g->resv.assign(P, IndResv()); g->lastResv.assign(P, IndResv()); g->indirect.assign(P, v3(0.f));
+    return g;
+}
+void orc_gi_destroy(OrcGI* g) { delete g; }
+
+/* ReSTIRIndirect (restir.cu:448-476) around ReSTIRIndirectKernel (:242-416); reuse bit 0 = temporal (common.h:36-43) */
+void orc_restir_indirect(OrcGI* g, const OrcCamera* cam, int looper, int iter, int maxDepth, int reuse) {
+    OrcFrame* f = g->f;
+    const OrcScene& sc = *f->sc;
+    const int W = cam->resolution[0], H = cam->resolution[1];
+    const float tanFovY = tanf(radians(cam->fov[1]));
+    const int cur = f->frameIdx, last = cur ^ 1;
+    const bool first = g->first;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int index = y * W + x;
+            IndSample smp;
+            Rng rng(looper, index);
+            float r4[4];
+            for (int k = 0; k < 4; k++) r4[k] = rng.next();
+            Ray ray = cameraRay(*cam, x, y, r4[0], r4[1], tanFovY);
+            Isect is;
+            sceneIntersect(sc, ray, is);
+            bool shaded = false, primDelta = false;
+            float primPdf = 1.f;
+            V3 primWo = v3(0.f), primBase = v3(0.f);
+            OrcMaterial primMat{};
+            if (is.primId != -1) {
+                OrcMaterial material = texturedMaterial(sc, is);
+                if (material.type != 4) {
+                    shaded = true;
+                    V3 throughput = v3(1.f);
+                    is.wo = -ray.direction;
+                    primWo = -ray.direction;
+                    primMat = material;
+                    primBase = {material.baseColor[0], material.baseColor[1], material.baseColor[2]};
+                    for (int depth = 1; depth <= maxDepth; depth++) {
+                        const V3 baseColor = {material.baseColor[0], material.baseColor[1], material.baseColor[2]};
+                        bool deltaBSDF = material.type == 2;
+                        if (material.type != 2 && dot(is.norm, is.wo) < 0.f) is.norm = -is.norm;
+                        if (!deltaBSDF && depth > 1) {                                        /* :290-301 */
+                            for (int k = 0; k < 4; k++) r4[k] = rng.next();
+                            V3 radiance = v3(0.f), wi = v3(0.f);
+                            float lightPdf = sampleDirectLight(sc, is.pos, r4, radiance, wi);
+                            if (lightPdf > 0.f) {
+                                float bsdfPdf = materialPdf(material, is.norm, is.wo, wi);
+                                smp.Lo = smp.Lo + throughput * materialBSDF(material, baseColor, is.norm, is.wo, wi) * radiance * satDot(is.norm, wi) / lightPdf *
+                                                      powerHeuristic(lightPdf, bsdfPdf);
+                            }
+                        }
+                        float r3[3];
+                        for (int k = 0; k < 3; k++) r3[k] = rng.next();
+                        BsdfSample bs;
+                        bs.dir = bs.bsdf = v3(0.f); bs.pdf = 0.f; bs.type = 0;
+                        materialSample(material, baseColor, is.norm, is.wo, r3[0], r3[1], r3[2], bs);
+                        if (bs.type == BS_Invalid) break;
+                        else if (bs.pdf < 1e-8f) break;
+                        const bool deltaSample = (bs.type & BS_Specular) != 0;
+                        if (depth > 1) throughput = throughput * (bs.bsdf / bs.pdf * (deltaSample ? 1.f : absDot(is.norm, bs.dir)));
+                        else { primPdf = bs.pdf; primDelta = deltaSample; smp.xv = is.pos; smp.nv = is.norm; }
+                        ray.origin = is.pos + bs.dir * 1e-5f; ray.direction = bs.dir;         /* makeOffsetedRay, intersections.h:13 */
+                        const V3 curPos = is.pos;
+                        sceneIntersect(sc, ray, is);
+                        is.wo = -ray.direction;
+                        if (is.primId == -1) {                                                /* :334-345 */
+                            if (sc.envMapTexId >= 0) {
+                                V3 radiance = envMapLookup(sc, ray.direction) * throughput;
+                                float envPdf = luminance(envMapLookup(sc, ray.direction)) * sc.sumLightPowerInv * sc.textures[sc.envMapTexId].w * sc.textures[sc.envMapTexId].h * .5f;   /* scene.h:358-362 */
+                                float weight = deltaSample ? 1.f : powerHeuristic(bs.pdf, envPdf);
+                                smp.Lo = smp.Lo + radiance * weight;
+                            }
+                            break;
+                        }
+                        material = texturedMaterial(sc, is);
+                        if (material.type == 4) {                                             /* :348-373 */
+                            if (dot(is.norm, ray.direction) < 0.f) break;                     /* SCENE_LIGHT_SINGLE_SIDED, common.h:6 */
+                            V3 radiance = {material.baseColor[0], material.baseColor[1], material.baseColor[2]};
+                            const V3 v0 = sc.vertices[is.primId * 3], v1 = sc.vertices[is.primId * 3 + 1], v2 = sc.vertices[is.primId * 3 + 2];
+                            float weight = 1.f;
+                            if (!(deltaSample || depth == 1)) {
+                                float area = length(cross(v1 - v0, v2 - v0)) * .5f;           /* getPrimitiveArea, scene.h:121-126 */
+                                V3 yx = curPos - is.pos;                                      /* pdfAreaToSolidAngle, mathUtil.h:182-185 */
+                                float lp = luminance(radiance) * sc.sumLightPowerInv * area * dot(yx, yx) / absDot(is.norm, normalize(yx));
+                                weight = powerHeuristic(bs.pdf, lp);
+                            }
+                            smp.Lo = smp.Lo + radiance * throughput * weight;
+                            if (depth == 1) { smp.xs = is.pos; smp.ns = is.norm; }
+                            break;
+                        }
+                        if (depth == 1) { smp.xs = is.pos; smp.ns = is.norm; }
+                    }
+                }
+            }
+            /* WriteSample (:382-415) */
+            IndResv reservoir;
+            float sampleWeight = 0.f;
+            if (!smp.invalid()) {
+                sampleWeight = luminance(smp.Lo / primPdf);
+                if (std::isnan(sampleWeight) || sampleWeight < 0.f) sampleWeight = 0.f;
+            }
+            reservoir.update(smp, sampleWeight, rng.next());
+            if (!first && (reuse & 1)) {
+                /* findTemporalNeighbor<IndirectReservoir>, restir.cu:20-45 */
+                const int primId = f->matId[cur][index], lastIdx = f->motion[index];
+                bool diff = false;
+                if (lastIdx < 0) diff = true;
+                else if (primId <= -1) diff = true;
+                else if (f->matId[last][lastIdx] != primId) diff = true;
+                else {
+                    float depth = f->depth[cur][index], pdepth = f->depth[last][lastIdx];
+                    if (absDot(f->normal[cur][index], f->normal[last][lastIdx]) < .9f || fabsf(pdepth - depth) > depth * .1f) diff = true;
+                }
+                IndResv temp = diff ? IndResv() : g->lastResv[lastIdx];
+                if (!temp.invalid()) reservoir.merge(temp, rng.next());
+            }
+            V3 indirect = v3(0.f);
+            const IndSample sample = reservoir.s;
+            reservoir.clamp(20);
+            if (shaded && !reservoir.invalid()) {
+                V3 primWi = normalize(sample.xs - sample.xv);
+                indirect = reservoir.s.Lo / luminance(reservoir.s.Lo) * reservoir.w / (float)reservoir.M;
+                indirect = indirect * (materialBSDF(primMat, primBase, sample.nv, primWo, primWi) * (primDelta ? 1.f : satDot(sample.nv, primWi)));
+            }
+            if (hasNanOrInf(indirect)) indirect = v3(0.f);
+            g->resv[index] = reservoir;
+            g->indirect[index] = (g->indirect[index] * (float)iter + indirect) / (float)(iter + 1);
+        }
+    std::swap(g->resv, g->lastResv);                                                          /* restir.cu:463 */
+    g->first = false;
+}
+const float* orc_gi_indirect(OrcGI* g) { return &g->indirect[0].x; }
+/* the reservoirs written by the last call as P x 17 f32: Lo xv nv xs ns (15), M, weight */
+const float* orc_gi_reservoirs(OrcGI* g) {
+    const size_t P = g->lastResv.size();
+    g->exportBuf.resize(P * 17);
+    for (size_t i = 0; i < P; i++) {
+        const IndResv& r = g->lastResv[i];
+        const V3 v[5] = {r.s.Lo, r.s.xv, r.s.nv, r.s.xs, r.s.ns};
+        for (int k = 0; k < 5; k++) { g->exportBuf[i * 17 + 3 * k] = v[k].x; g->exportBuf[i * 17 + 3 * k + 1] = v[k].y; g->exportBuf[i * 17 + 3 * k + 2] = v[k].z; }
+        g->exportBuf[i * 17 + 15] = (float)r.M; g->exportBuf[i * 17 + 16] = r.w;
+    }
+    return g->exportBuf.data();
+}
+
+}  // extern "C"
+
 /* ================================================================ image-space filters (denoiser.cu:25-567)
  * Restated only (a __global__ body cannot be compiled by g++; the harness has no counterpart): the pin for these is the
  * reference's own CUDA build, which links denoiser.cu unmodified (oracle/ref_headless_main.cpp, tests/test_ref_cuda.py). */

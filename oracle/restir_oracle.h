@@ -122,6 +122,15 @@ float orc_alias_build(int n, const float* values, void* outTable);
 int  orc_intersect(const OrcScene*, const float* origin, const float* dir, float* outPosNormUv8, int* outMatId);
 int  orc_occluded(const OrcScene*, const float* x, const float* y);
 
+/* ReSTIR GI (ReSTIRIndirect / ReSTIRIndirectKernel, restir.cu:232-476): one call = one frame of indirect illumination for the frame's
+ * current G-buffer (call between orc_gbuffer_render and orc_gbuffer_update).  maxDepth = Settings::traceDepth, reuse bit 0 = temporal. */
+typedef struct OrcGI OrcGI;
+OrcGI* orc_gi_create(OrcFrame*);
+void orc_gi_destroy(OrcGI*);
+void orc_restir_indirect(OrcGI*, const OrcCamera*, int looper, int iter, int maxDepth, int reuse);
+const float* orc_gi_indirect(OrcGI*);     /* P x 3 f32 (devIndirectIllum) */
+const float* orc_gi_reservoirs(OrcGI*);   /* P x 17 f32: Lo xv nv xs ns, M, weight of the reservoirs the last call wrote */
+
 /* The reference's image-space filters (denoiser.cu:25-567): kind 1 = LeveledEAWFilter, 2 = SpatioTemporalFilter, applied to the
  * frame's radiance with its current G-buffer.  Port only (restated): see restir_oracle.cpp. */
 typedef struct OrcDenoiser OrcDenoiser;

@@ -167,8 +167,25 @@ def image_writers(ref):
     np.savez_compressed(os.path.join(HERE, "image_writers.npz"), **d)
 
 
+def gi(ref):
+    """8. ReSTIRIndirect (restir.cu:242-416, 448-476): 3 orbit frames, traceDepth 3, temporal reuse on; every frame's
+    devIndirectIllum and the last frame's reservoirs (17 floats each: Lo xv nv xs ns, numSamples, weight)"""
+    d = {}
+    for name, sd in helpers.gi_scenes().items():
+        frames = helpers.run_oracle_gi(ref, sd, 3, max_depth=3, reuse=1)
+        for f, bufs in enumerate(frames):
+            d["%s_f%d_indirect" % (name, f)] = bufs["indirect"]
+        d["%s_f2_reservoir" % name] = frames[-1]["reservoir"]
+        acc = helpers.run_oracle_gi(ref, sd, 2, max_depth=2, reuse=0, accumulate=True, orbit=False)
+        d["%s_acc_indirect" % name] = acc[-1]["indirect"]
+    np.savez_compressed(os.path.join(HERE, "gi.npz"), **d)
+
+
 def main():
     ref = Oracle("reference")
+    if "--only-gi" in sys.argv:
+        gi(ref)
+        return
     if "--only-writers" in sys.argv:
         image_writers(ref)
         return
@@ -184,6 +201,7 @@ def main():
         return
     textured_scene_file(ref)
     textured(ref)
+    gi(ref)
     multipass(ref)
     ngons(ref)
     image_writers(ref)

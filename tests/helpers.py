@@ -108,3 +108,45 @@ def assert_frames_equal(got, want, what=""):
                 continue
             bad = mismatches(g[n], w[n])
             assert bad == 0, "%s frame %d buffer %s: %d pixels differ" % (what, f, n, bad)
+
+
+# ---------------------------------------------------------------------------------------------- ReSTIR GI
+def gi_scenes():
+    """Small cases for ReSTIRIndirect: every Material::sample branch (material.h:242-256) and the environment-map miss."""
+    import dataclasses
+    glass = scenes.cornell_box((48, 36), metal_tall_box=True)
+    mats = glass.materials.copy()
+    mats[0]["type"] = scenes.LAMBERTIAN
+    glass = dataclasses.replace(glass, name="cornell_glass", materials=np.concatenate([mats, scenes.make_materials([(scenes.DIELECTRIC, (0.95, 0.97, 1.0), 0.0, 0.0)])]),
+                                material_names=list(glass.material_names) + ["glass"])
+    ids = glass.material_ids.copy()
+    ids[12:24] = 5                      # the short box (12 triangles after the 6 quads) becomes glass, ior 1.5
+    glass = dataclasses.replace(glass, material_ids=ids)
+    return {
+        "cornell": scenes.cornell_box((48, 36)),
+        "cornell_metal": scenes.cornell_box((48, 36), metal_tall_box=True),
+        "cornell_glass": glass,
+        "gen2000": scenes.procedural(1, 2000, 100, (48, 36)),
+        "cornell_tex": scenes.with_textures(scenes.cornell_box((48, 36)), env=True),
+    }
+
+
+def run_oracle_gi(orc, sd, frames, max_depth=3, reuse=1, accumulate=False, orbit=True):
+    """Per frame {indirect (P,3), reservoir (P,17)} of ReSTIRIndirect (restir.cu:448-476) in the frame loop of main.cpp:146-185."""
+    W, H = sd.resolution
+    so = orc.scene(sd)
+    fo = so.frame(W, H)
+    gi = orc_mod.OracleGI(fo)
+    base = orc_mod.make_camera(sd)
+    orc.lib.orc_camera_update(C.byref(base))
+    out = []
+    for f in range(frames):
+        cam = orc_mod.orbit_camera(orc, base, f) if orbit else base
+        fo.gbuffer_render(cam)
+        gi.restir_indirect(cam, f, f if accumulate else 0, max_depth, reuse)
+        out.append({"indirect": gi.indirect().copy(), "reservoir": gi.reservoirs().copy()})
+        fo.gbuffer_update(cam)
+    gi.close()
+    fo.close()
+    so.close()
+    return out

@@ -66,3 +66,14 @@ def test_textured_port_equals_reference(port_oracle, ref_oracle, name):
     a = helpers.run_oracle(port_oracle, sd, 3, 3, radius=30.0)
     b = helpers.run_oracle(ref_oracle, sd, 3, 3, radius=30.0)
     helpers.assert_frames_equal(a, b, name)
+
+
+@pytest.mark.parametrize("depth,reuse", [(1, 1), (4, 1), (6, 0)])
+def test_restir_indirect_port_equals_reference(port_oracle, ref_oracle, depth, reuse):
+    """ReSTIRIndirect at other trace depths and a larger image than the committed fixture."""
+    import dataclasses
+    for name in ("cornell_glass", "cornell_tex"):
+        sd = dataclasses.replace(helpers.gi_scenes()[name], resolution=(96, 72))
+        a = helpers.run_oracle_gi(port_oracle, sd, 3, depth, reuse, accumulate=True)
+        b = helpers.run_oracle_gi(ref_oracle, sd, 3, depth, reuse, accumulate=True)
+        helpers.assert_frames_equal(a, b, "GI %s depth %d" % (name, depth))
