@@ -384,6 +384,34 @@ int rstr_denoiser_add_image(RstrDenoiser* a, const RstrDenoiser* b);            
 /* devColorOut as W x H x 3 floats (and, SVGF, the filtered variance as W x H floats; may be NULL) */
 int rstr_denoiser_read(RstrDenoiser*, float* rgb, float* variance);
 
+/* ---- ReSTIR GI (restir.h:13-27, 133; restir.cu:242-416, 448-476).  The reference ships ReSTIRIndirect commented out
+ * at its call site (main.cpp:168) and with Settings::traceDepth = 0 (common.cpp:3); here it is a handle on a full frame:
+ *   rstr_gi_create    the indirect share of ReSTIRInit (restir.cu:491-496: devIndTemporalReservoir, devIndLastTemporalReservoir, zeroed)
+ *                     plus a devIndirectIllum plane of its own
+ *   rstr_gi_destroy   ... of ReSTIRFree (restir.cu:511-512)
+ *   rstr_gi_reset     ReSTIRReset (restir.cu:516): the next call does not read the history
+ *   rstr_restir_indirect   ReSTIRIndirect(devIndirectIllum, iter, gBuffer) with State::looper, Settings::traceDepth and
+ *                     Settings::reservoirReuse (bit 0 = temporal) as arguments: between rstr_gbuffer_render and rstr_gbuffer_update of
+ *                     the frame.  target RSTR_GI_TARGET_OWN accumulates into the handle's own plane, RSTR_GI_TARGET_RADIANCE into the
+ *                     frame's radiance plane (the reference's commented call passes devDirectIllum), where rstr_tonemap, the filters
+ *                     and rstr_frame_save_* find it.
+ * A pixel whose jittered ray leaves the scene or hits an emitter writes 0 (the reference shades a history sample with uninitialised
+ * locals there).  */
+typedef struct RstrGI RstrGI;
+enum { RSTR_GI_TARGET_OWN = 0, RSTR_GI_TARGET_RADIANCE = 1 };
+int rstr_gi_create(RstrFrame* fullFrame, RstrGI**);
+int rstr_gi_destroy(RstrGI*);
+int rstr_gi_reset(RstrGI*);
+int rstr_restir_indirect(RstrGI*, const RstrCamera*, int looper, int iter, int traceDepth, int reuse, int target);
+/* the own plane as W x H x 3 floats (may be NULL) and the reservoirs the last call wrote in the reference's layout,
+ * Reservoir<IndirectLiSample> = 68 bytes: Lo xv nv xs ns (5 x vec3), numSamples (int), weight (may be NULL) */
+int rstr_gi_read(RstrGI*, float* indirectRgb, void* reservoirs);
+int rstr_gi_indirect_device(RstrGI*, float** devIndirectIllum);                    /* device pointer of the own plane */
+/* which tree the bounce rays walk when the scene's traversal mode is the traced one: 0 the traced tree (default), 1 the reference tree in
+ * the reference's order; the hits are the same either way (validation switch) */
+int rstr_gi_set_bounce_walk(RstrGI*, int traversal);
+int rstr_gi_fallback_pixels(RstrGI*, unsigned int* count, int reset);              /* pixels recomputed with the reference-order walk */
+
 #ifdef __cplusplus
 }
 #endif

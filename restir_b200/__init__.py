@@ -6,6 +6,6 @@ host scene layer in restir_b200/csrc, this package is the thin ctypes mirror use
 from . import scenes  # noqa: F401
 from .api import (  # noqa: F401
     REUSE_NONE, REUSE_SPATIAL, REUSE_SPATIOTEMPORAL, REUSE_TEMPORAL, TONEMAP_ACES, TONEMAP_FILMIC, TONEMAP_NONE,
-    Camera, Denoiser, Frame, RestirError, RstrParams, Scene, StripGroup, default_params, init, launch_count, lib, load_image, pinned_empty, pinned_free,
+    Camera, Denoiser, Frame, ReSTIRIndirect, RestirError, RstrParams, Scene, StripGroup, default_params, init, launch_count, lib, load_image, pinned_empty, pinned_free,
     write_jpg, write_png,
 )

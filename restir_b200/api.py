@@ -147,6 +147,14 @@ def lib() -> C.CDLL:
     L.rstr_denoiser_modulate_albedo.argtypes = [vp]
     L.rstr_denoiser_add_image.argtypes = [vp, vp]
     L.rstr_denoiser_read.argtypes = [vp, vp, vp]
+    L.rstr_gi_create.argtypes = [vp, C.POINTER(vp)]
+    L.rstr_gi_destroy.argtypes = [vp]
+    L.rstr_gi_reset.argtypes = [vp]
+    L.rstr_restir_indirect.argtypes = [vp, C.POINTER(RstrCamera), ip, ip, ip, ip, ip]
+    L.rstr_gi_read.argtypes = [vp, vp, vp]
+    L.rstr_gi_indirect_device.argtypes = [vp, C.POINTER(vp)]
+    L.rstr_gi_set_bounce_walk.argtypes = [vp, ip]
+    L.rstr_gi_fallback_pixels.argtypes = [vp, C.POINTER(C.c_uint), ip]
     L.rstr_scene_fallback_rays.argtypes = [vp, C.POINTER(C.c_ulonglong), ip]
     L.rstr_camera_update.argtypes = [C.POINTER(RstrCamera)]
     L.rstr_camera_orbit.argtypes = [C.POINTER(RstrCamera), ip, fp, fp, fp, C.POINTER(RstrCamera)]
@@ -544,6 +552,54 @@ class Denoiser:
         var = np.zeros(n, np.float32) if variance else None
         _check(lib().rstr_denoiser_read(self.h, rgb.ctypes.data, var.ctypes.data if variance else None))
         return (rgb, var) if variance else rgb
+
+
+# Reservoir<IndirectLiSample> (restir.h:13-27, 29-117): 68 bytes
+GI_RESERVOIR_DTYPE = np.dtype([("Lo", "<f4", (3,)), ("xv", "<f4", (3,)), ("nv", "<f4", (3,)), ("xs", "<f4", (3,)), ("ns", "<f4", (3,)),
+                               ("numSamples", "<i4"), ("weight", "<f4")])
+assert GI_RESERVOIR_DTYPE.itemsize == 68
+GI_TARGET_OWN, GI_TARGET_RADIANCE = 0, 1
+
+
+class ReSTIRIndirect:
+    """ReSTIR GI on a full frame: ReSTIRIndirect (restir.h:133, restir.cu:448-476) with its reservoirs (the indirect share of
+    ReSTIRInit / ReSTIRFree / ReSTIRReset).  Call between ``Frame.gbuffer_render`` and ``Frame.gbuffer_update``."""
+
+    def __init__(self, frame: "Frame"):
+        self.frame = frame
+        self.h = C.c_void_p()
+        _check(lib().rstr_gi_create(frame.f, C.byref(self.h)))
+
+    def close(self) -> None:
+        if self.h:
+            lib().rstr_gi_destroy(self.h)
+            self.h = None
+
+    def reset(self) -> None:                     # ReSTIRReset
+        _check(lib().rstr_gi_reset(self.h))
+
+    def restir_indirect(self, cam, looper: int, it: int = 0, trace_depth: int = 3, reuse: int = REUSE_TEMPORAL, into_radiance: bool = False) -> None:
+        _check(lib().rstr_restir_indirect(self.h, C.byref(cam), looper, it, trace_depth, reuse, GI_TARGET_RADIANCE if into_radiance else GI_TARGET_OWN))
+
+    def read(self) -> np.ndarray:
+        """devIndirectIllum (the handle's own plane) as (W*H, 3) float32."""
+        out = np.zeros((self.frame.w * self.frame.h, 3), np.float32)
+        _check(lib().rstr_gi_read(self.h, out.ctypes.data, None))
+        return out
+
+    def read_reservoirs(self) -> np.ndarray:
+        """The reservoirs the last call wrote, in the reference's 68-byte layout."""
+        out = np.zeros(self.frame.w * self.frame.h, GI_RESERVOIR_DTYPE)
+        _check(lib().rstr_gi_read(self.h, None, out.ctypes.data))
+        return out
+
+    def set_bounce_walk(self, exact: bool) -> None:
+        _check(lib().rstr_gi_set_bounce_walk(self.h, 1 if exact else 0))
+
+    def fallback_pixels(self, reset: bool = True) -> int:
+        n = C.c_uint(0)
+        _check(lib().rstr_gi_fallback_pixels(self.h, C.byref(n), 1 if reset else 0))
+        return n.value
 
 
 class StripGroup:

@@ -17,8 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 # RSTR_LIBNAME / RSTR_DEFINES: side-by-side experimental builds for A/B timing (scripts/gpu_ab.py); the default is the product
 LIB = os.path.join(HERE, os.environ.get("RSTR_LIBNAME", "librestir_b200.so"))
 EXTRA_DEFINES = [d for d in os.environ.get("RSTR_DEFINES", "").split() if d]
-SOURCES = ["capi.cu", "strip_group.cu", "bvh_gpu.cu", "denoise.cu", "kernels.cu", "scene_host.cpp", "scene_file.cpp", "bvh_fast.cpp", "image_io.cpp", "image_jpeg.cpp"]
-HEADERS = ["kernels.h", "camera_dev.h", "capi_internal.h", "device_types.h", "scene_host.h", "vecmath.h", os.path.join("..", "..", "include", "restir_b200.h")]
+SOURCES = ["capi.cu", "strip_group.cu", "bvh_gpu.cu", "denoise.cu", "gi.cu", "kernels.cu", "scene_host.cpp", "scene_file.cpp", "bvh_fast.cpp", "image_io.cpp", "image_jpeg.cpp"]
+HEADERS = ["kernels.h", "gi_kernels.inl", "camera_dev.h", "capi_internal.h", "device_types.h", "scene_host.h", "vecmath.h", os.path.join("..", "..", "include", "restir_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 

@@ -101,4 +101,20 @@ struct FrameDev {
     unsigned long long* rowCost;  // optional [ceil(H / 8)] cycle accumulators (rstr_frame_row_cost), else null
 };
 
+// ReSTIR GI (gi_kernels.inl): the indirect reservoirs and devIndirectIllum of a full frame.  A reservoir is one 64-byte record
+// {Lo, weight} {xv, numSamples} {nv, ns.x} {xs, ns.y} plus ns.z in a 4-byte plane (68 B per pixel, as Reservoir<IndirectLiSample>).
+struct GIDev {
+    float4* resvOut;           // devIndTemporalReservoir: written this frame
+    const float4* resvIn;      // devIndLastTemporalReservoir: the previous frame's
+    float* nszOut;
+    const float* nszIn;
+    float* indirect;           // 3 floats per pixel (devIndirectIllum layout)
+    unsigned int* fallback;    // pixels recomputed with the reference-order walk
+    int maxDepth;              // Settings::traceDepth
+    int reuse;                 // bit 0: temporal (ReservoirReuse::Temporal)
+    int first;                 // ReSTIRFirstFrame
+    int iter;
+    int bounceWalk;            // RS_TRAVERSAL_*: which tree the bounce rays walk in the traced mode (same hits either way)
+};
+
 }  // namespace rs

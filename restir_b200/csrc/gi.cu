@@ -1,0 +1,125 @@
+// gi.cu -- C ABI of ReSTIR GI: ReSTIRIndirect (restir.cu:448-476) and the indirect-reservoir share of
+// ReSTIRInit / ReSTIRFree / ReSTIRReset (restir.cu:491-496, 511-512, 516).  The kernels are in gi_kernels.inl (kernels.cu).
+// The reference ships the call commented out (main.cpp:168) with Settings::traceDepth = 0; here it is reachable through rstr_gi_*.
+#include <utility>
+
+#include "capi_internal.h"
+
+using namespace rs;
+
+struct RstrGI {
+    RstrFrame* f = nullptr;
+    int W = 0, H = 0;
+    float4* resv[2] = {nullptr, nullptr};      // 64-byte records
+    float* nsz[2] = {nullptr, nullptr};        // ns.z plane
+    float* indirect = nullptr;                 // devIndirectIllum (own plane)
+    float* scratch = nullptr;                  // export buffer (17 floats per pixel), allocated on first read
+    unsigned int* fallback = nullptr;
+    int out = 0;                               // which of resv[] is devIndTemporalReservoir (written by the next call)
+    bool first = true;                         // ReSTIRFirstFrame
+    int bounceWalk = RS_TRAVERSAL_FAST;
+};
+
+static void giFree(RstrGI* g) {
+    void* all[] = {g->resv[0], g->resv[1], g->nsz[0], g->nsz[1], g->indirect, g->scratch, g->fallback};
+    for (void* p : all) cudaFree(p);
+    delete g;
+}
+
+extern "C" {
+
+int rstr_gi_create(RstrFrame* f, RstrGI** out) {
+    if (!f || !out) return rsFail(RSTR_ERR_ARG, "rstr_gi_create: bad argument");
+    if (f->row0 != 0 || f->row1 != f->H || f->bufRow0 != 0) return rsFail(RSTR_ERR_ARG, "rstr_gi_create: ReSTIR GI works on full frames, not on strips");
+    RstrGI* g = new RstrGI;
+    g->f = f; g->W = f->W; g->H = f->H;
+    const size_t n = (size_t)f->W * f->H;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaMalloc(&g->resv[i], n * 64);
+        if (e == cudaSuccess) e = cudaMemset(g->resv[i], 0, n * 64);                 // restir.cu:493-496
+        if (e == cudaSuccess) e = cudaMalloc(&g->nsz[i], n * 4);
+        if (e == cudaSuccess) e = cudaMemset(g->nsz[i], 0, n * 4);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&g->indirect, n * 12);
+    if (e == cudaSuccess) e = cudaMemset(g->indirect, 0, n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&g->fallback, 4);
+    if (e == cudaSuccess) e = cudaMemset(g->fallback, 0, 4);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();       // the fills above are not ordered with the frame's (non-blocking) stream
+    if (e != cudaSuccess) { giFree(g); return rsFail(RSTR_ERR_CUDA, std::string("rstr_gi_create: ") + cudaGetErrorString(e)); }
+    *out = g;
+    return RSTR_OK;
+}
+
+int rstr_gi_destroy(RstrGI* g) {
+    if (!g) return RSTR_OK;
+    cudaStreamSynchronize(g->f->stream);
+    giFree(g);
+    return RSTR_OK;
+}
+
+int rstr_gi_reset(RstrGI* g) {
+    if (!g) return rsFail(RSTR_ERR_ARG, "rstr_gi_reset: null handle");
+    g->first = true;
+    return RSTR_OK;
+}
+
+int rstr_gi_set_bounce_walk(RstrGI* g, int traversal) {
+    if (!g || (traversal != RS_TRAVERSAL_FAST && traversal != RS_TRAVERSAL_EXACT)) return rsFail(RSTR_ERR_ARG, "rstr_gi_set_bounce_walk: bad argument");
+    g->bounceWalk = traversal;
+    return RSTR_OK;
+}
+
+int rstr_restir_indirect(RstrGI* g, const RstrCamera* cam, int looper, int iter, int traceDepth, int reuse, int target) {
+    if (!g || !cam) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: bad argument");
+    RstrFrame* f = g->f;
+    if (cam->resolution[0] != f->W || cam->resolution[1] != f->H) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: camera resolution differs from the frame");
+    if (traceDepth < 0 || traceDepth > 64 || iter < 0) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: traceDepth must be 0..64 and iter >= 0");
+    if (target != RSTR_GI_TARGET_OWN && target != RSTR_GI_TARGET_RADIANCE) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: unknown target");
+    { int rc = rsFlushGBuffer(f); if (rc) return rc; }
+    const FrameDev d = rsToFrameDev(f, 0, f->H);
+    GIDev gd{};
+    gd.resvOut = g->resv[g->out]; gd.resvIn = g->resv[g->out ^ 1];
+    gd.nszOut = g->nsz[g->out]; gd.nszIn = g->nsz[g->out ^ 1];
+    gd.indirect = target == RSTR_GI_TARGET_RADIANCE ? f->radiance : g->indirect;
+    gd.fallback = g->fallback;
+    gd.maxDepth = traceDepth; gd.reuse = reuse; gd.first = g->first ? 1 : 0; gd.iter = iter;
+    gd.bounceWalk = g->bounceWalk;
+    rsCountLaunches(launchRestirIndirect(f->sc->dev, d, rsToCamDev(*cam), gd, looper, f->stream));
+    g->out ^= 1;                                                                     // std::swap(devIndTemporalReservoir, devIndLastTemporalReservoir), restir.cu:463
+    g->first = false;
+    CU(cudaGetLastError());
+    return RSTR_OK;
+}
+
+int rstr_gi_read(RstrGI* g, float* indirectRgb, void* reservoirs) {
+    if (!g) return rsFail(RSTR_ERR_ARG, "rstr_gi_read: null handle");
+    const size_t n = (size_t)g->W * g->H;
+    cudaStream_t st = g->f->stream;
+    if (reservoirs) {
+        if (!g->scratch) CU(cudaMalloc(&g->scratch, n * 68));
+        launchExportGI(g->resv[g->out ^ 1], g->nsz[g->out ^ 1], g->scratch, n, st);   // the reservoirs the last call wrote
+        rsCountLaunches(1);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(st));
+    if (indirectRgb) CU(cudaMemcpy(indirectRgb, g->indirect, n * 12, cudaMemcpyDeviceToHost));
+    if (reservoirs) CU(cudaMemcpy(reservoirs, g->scratch, n * 68, cudaMemcpyDeviceToHost));
+    return RSTR_OK;
+}
+
+int rstr_gi_indirect_device(RstrGI* g, float** dev) {
+    if (!g || !dev) return rsFail(RSTR_ERR_ARG, "rstr_gi_indirect_device: bad argument");
+    *dev = g->indirect;
+    return RSTR_OK;
+}
+
+int rstr_gi_fallback_pixels(RstrGI* g, unsigned int* count, int reset) {
+    if (!g || !count) return rsFail(RSTR_ERR_ARG, "rstr_gi_fallback_pixels: bad argument");
+    CU(cudaStreamSynchronize(g->f->stream));
+    CU(cudaMemcpy(count, g->fallback, 4, cudaMemcpyDeviceToHost));
+    if (reset) CU(cudaMemset(g->fallback, 0, 4));
+    return RSTR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,485 @@
+// gi_kernels.inl -- ReSTIR GI: ReSTIRIndirectKernel (restir.cu:242-416) for sm_100a.  Included by kernels.cu (namespace rs), after the
+// ray / material / light helpers it shares with the direct-illumination kernels.
+//
+//   k_restir_indirect        one thread per pixel.  The jittered primary rays of an 8x4 tile walk the traced tree as one packet
+//                            (packetWalk, as in k_ptdirect); every bounce ray then walks it per lane (traceClosestFast: the same
+//                            leaf-box / near-tie criterion, so the reported hit is the reference's), next-event shadow rays use the
+//                            any-hit walk.  A pixel with an undecided ray (more mutually near hits than the tie store holds) writes
+//                            nothing and is queued.
+//   k_restir_indirect_fix    the queued pixels again with the reference-order walk of the reference tree
+//   k_restir_indirect_exact  every ray with the reference-order walk (RS_TRAVERSAL_EXACT: validation mode)
+//   k_export_gi              device reservoirs -> Reservoir<IndirectLiSample> (68 B: Lo xv nv xs ns, numSamples, weight; restir.h:13-27)
+//
+// The reference ships this kernel disabled (commented out at main.cpp:168, Settings::traceDepth = 0 in common.cpp:3); the trace depth
+// and the temporal switch are arguments here.  One deviation, shared with the oracle: the reference jumps to WriteSample past the
+// initialisation of primMaterial / primWo / primSampleDelta when the jittered ray leaves the scene or hits an emitter and then shades a
+// history sample with them (undefined behaviour); such a pixel writes indirect = 0.
+//
+// Arithmetic: every expression below keeps the operation order of the reference's (cited per function); the BSDF sampling goes through
+// sinf / cosf, so against a CPU build of the same expressions (glibc) the sampled directions agree to an ulp, not to the bit.
+//
+// Per pixel and frame: 4 + (depth - 1) * 4 + depth * 3 + 2 LCG draws at most, depth closest-hit rays + (depth - 1) shadow rays,
+// 68 B of reservoir written (64-B record + 4-B plane), 68 B of history gathered at the reprojected pixel, 24 B radiance read-modify-write.
+
+struct GISample { f3 Lo, xv, nv, xs, ns; };                                          // IndirectLiSample, restir.h:13-27
+struct GIResv { GISample s; int M; float w; };                                       // Reservoir<IndirectLiSample>, restir.h:29-117
+RS_D GISample giEmptySample() { GISample s; s.Lo = s.xv = s.nv = s.xs = s.ns = mk3(0.f); return s; }
+RS_D bool giResvInvalid(const GIResv& r) { return isNanOrInf(r.w) || r.w < 0.f; }    // restir.h:51
+
+// HBM form: one 64-byte record {Lo, weight} {xv, numSamples} {nv, ns.x} {xs, ns.y} (4 x LDG / STG.128 on one 64-B aligned line)
+// plus ns.z in a separate 4-byte plane: 68 B per pixel, the reference's size, without a record straddling sectors
+RS_D GIResv giLoad(const float4* rec, const float* nsz, size_t i) {
+    const float4 a = __ldg(rec + 4 * i), b = __ldg(rec + 4 * i + 1), c = __ldg(rec + 4 * i + 2), d = __ldg(rec + 4 * i + 3);
+    GIResv r;
+    r.s.Lo = mk3(a.x, a.y, a.z); r.w = a.w;
+    r.s.xv = mk3(b.x, b.y, b.z); r.M = __float_as_int(b.w);
+    r.s.nv = mk3(c.x, c.y, c.z);
+    r.s.xs = mk3(d.x, d.y, d.z);
+    r.s.ns = mk3(c.w, d.w, __ldg(nsz + i));
+    return r;
+}
+RS_D void giStore(float4* rec, float* nsz, size_t i, const GIResv& r) {
+    rec[4 * i] = make_float4(r.s.Lo.x, r.s.Lo.y, r.s.Lo.z, r.w);
+    rec[4 * i + 1] = make_float4(r.s.xv.x, r.s.xv.y, r.s.xv.z, __int_as_float(r.M));
+    rec[4 * i + 2] = make_float4(r.s.nv.x, r.s.nv.y, r.s.nv.z, r.s.ns.x);
+    rec[4 * i + 3] = make_float4(r.s.xs.x, r.s.xs.y, r.s.xs.z, r.s.ns.y);
+    nsz[i] = r.s.ns.z;
+}
+
+// ------------------------------------------------------------------------------------------------ closest hit of one ray, traced tree
+// The walk of traceOccludedFast with the running result of the packet walk (PRay: best hit, near ties, limit) kept per lane.
+// false = undecided.
+RS_D bool traceClosestFast(const DevScene& s, f3 o, f3 d, Stack& stack, const TieStore& ts, Hit& h) {
+    // a NaN direction (sampleHemisphereCosine with r.x == 1: sqrt of a negative rounding residue) fails every box test of the reference
+    // (bvh.h:85-157: all comparisons false) -> miss; the slab test's fminf / fmaxf would drop the NaNs and walk the whole tree instead
+    if (isnan(d.x) || isnan(d.y) || isnan(d.z) || isnan(o.x) || isnan(o.y) || isnan(o.z)) {
+        h.t = FLT_MAX; h.prim = -1; h.bx = 0.f; h.by = 0.f;
+        return true;
+    }
+    PRay p = prayBegin(o, d, true, ts);
+    float t0;
+    if (slabHitP(p, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], t0)) {
+        int sp = 0;
+        int cur = s.fastRoot;
+        for (;;) {
+            bool popped = true;
+            while (cur >= 0) {
+                const float4* np = s.fastNodes + 4 * (size_t)cur;
+                const F8 nA = ldg256(np), nB = ldg256(np + 2);
+                const float4 a = nA.lo, b = nA.hi, c = nB.lo;
+                const int2 l = make_int2(__float_as_int(nB.hi.x), __float_as_int(nB.hi.y));
+                float tL, tR;
+                const bool hL = slabHitP(p, a.x, a.y, a.z, a.w, b.x, b.y, tL);
+                const bool hR = slabHitP(p, b.z, b.w, c.x, c.y, c.z, c.w, tR);
+                if (hL && hR) {
+                    const bool leftNear = tL <= tR;
+                    stack.push(sp, leftNear ? l.y : l.x, leftNear ? tR : tL); sp++;
+                    cur = leftNear ? l.x : l.y;
+                } else if (hL) cur = l.x;
+                else if (hR) cur = l.y;
+                else {
+                    popped = false;
+                    while (sp > 0) {
+                        --sp;
+                        if (stack.t(sp) <= p.limit) { cur = stack.ref(sp); popped = true; break; }
+                    }
+                    if (!popped) break;
+                }
+            }
+            if (!popped) break;
+            const int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            for (int i = 0; i < count; i++) {
+                const Tri t = loadTriFast(s, first + i);
+                prayOffer(p, o, d, ts, t, first + i);
+            }
+            popped = false;
+            while (sp > 0) {
+                --sp;
+                if (stack.t(sp) <= p.limit) { cur = stack.ref(sp); popped = true; break; }
+            }
+            if (!popped) break;
+        }
+    }
+    return prayResolve(s, o, d, p, ts, h);
+}
+
+template <bool EXACT>
+RS_D bool giClosest(const DevScene& s, const GIDev& g, f3 o, f3 d, Stack& stack, const TieStore& ts, Hit& h) {
+    if (EXACT || g.bounceWalk == RS_TRAVERSAL_EXACT) {
+        const RayT r = makeRayT(o, d);
+        traceClosestExact(s, r, h, stack);
+        return true;
+    }
+    return traceClosestFast(s, o, d, stack, ts, h);
+}
+
+// ------------------------------------------------------------------------------------------------ surface at a hit
+// DevScene::getIntersecGeomInfo + getTexturedMaterialAndSurface (scene.h:135-151, 78-99), as in ptdirectAfterHit
+struct GISurf { f3 pos, nrm, v0, v1, v2; Surf m; float ior; };
+RS_D void giSurface(const DevScene& s, const Hit& h, GISurf& g) {
+    const Tri t = loadTri(s, h.prim);
+    const float4* np = s.triNorm + 3 * (size_t)h.prim;
+    const float4 na4 = __ldg(np), nb4 = __ldg(np + 1), nc4 = __ldg(np + 2);
+    const f3 na = mk3(na4.x, na4.y, na4.z), nb = mk3(na4.w, nb4.x, nb4.y), nc = mk3(nb4.z, nb4.w, nc4.x);
+    const float bz = 1.f - h.bx - h.by;
+    g.pos = t.v1 * h.bx + t.v2 * h.by + t.v0 * bz;
+    g.nrm = normalize(nb * h.bx + nc * h.by + na * bz);
+    g.v0 = t.v0; g.v1 = t.v1; g.v2 = t.v2;
+    g.m = texturedMaterial(s, t.matId, h.prim, h.bx, h.by, g.nrm);
+    g.ior = __ldg(&s.materials[t.matId].ior);
+}
+
+// ------------------------------------------------------------------------------------------------ Material::sample / pdf (material.h)
+RS_D f3 giMatVec(f3 c0, f3 c1, f3 c2, f3 v) {                                        // type_mat3x3.inl operator*(mat3, vec3)
+    return mk3(c0.x * v.x + c1.x * v.y + c2.x * v.z, c0.y * v.x + c1.y * v.y + c2.y * v.z, c0.z * v.x + c1.z * v.y + c2.z * v.z);
+}
+RS_D f3 giReflect(f3 I, f3 N) { return I - N * dot(N, I) * 2.f; }                    // func_geometric.inl:176
+RS_D void giConcentricDisk(float rx, float ry, float& px, float& py) {               // mathUtil.h:128-132
+    const float r = sqrtf(rx), theta = ry * RS_PI * 2.0f;
+    px = cosf(theta) * r; py = sinf(theta) * r;
+}
+RS_D f3 giSampleHemisphereCosine(f3 n, float rx, float ry) {                         // mathUtil.h:157-161
+    float dx, dy;
+    giConcentricDisk(rx, ry, dx, dy);
+    const float z = sqrtf(1.f - (dx * dx + dy * dy));
+    return localToWorld(n, mk3(dx, dy, z));
+}
+RS_D float giFresnel(float cosIn, float ior) {                                       // material.h:43-60 (the #if tests a misspelt macro: the exact branch)
+    if (cosIn < 0) { ior = 1.f / ior; cosIn = -cosIn; }
+    const float sinIn = sqrtf(1.f - cosIn * cosIn);
+    const float sinTr = sinIn / ior;
+    if (sinTr >= 1.f) return 1.f;
+    const float cosTr = sqrtf(1.f - sinTr * sinTr);
+    const float a = (cosIn - ior * cosTr) / (cosIn + ior * cosTr), b = (ior * cosIn - cosTr) / (ior * cosIn + cosTr);
+    return (a * a + b * b) * .5f;
+}
+RS_D bool giRefract(f3 n, f3 wi, float ior, f3& wt) {                                // mathUtil.h:163-180
+    const float cosIn = dot(n, wi);
+    if (cosIn < 0) ior = 1.f / ior;
+    const float sin2In = gmax(0.f, 1.f - cosIn * cosIn);
+    const float sin2Tr = sin2In / (ior * ior);
+    if (sin2Tr >= 1.f) return false;
+    float cosTr = sqrtf(1.f - sin2Tr);
+    if (cosIn < 0) cosTr = -cosTr;
+    wt = normalize(-wi / ior + n * (cosIn / ior - cosTr));
+    return true;
+}
+RS_D float giGTR2Pdf(f3 n, f3 m, f3 wo, float alpha) {                               // material.h:82-85
+    return GTR2Distrib(dot(n, m), alpha) * schlickG(dot(n, wo), alpha) * absDot(m, wo) / absDot(n, wo);
+}
+// GGX visible-normal sampling, material.h:93-112 (localRefMatrix mathUtil.h:146-151, glm::inverse(mat3) type_mat3x3.inl:37-57)
+__device__ __noinline__ f3 giGTR2Sample(f3 n, f3 wo, float alpha, float rx, float ry) {
+    f3 t0 = (fabsf(n.y) > 0.9999f) ? mk3(0.f, 0.f, 1.f) : mk3(0.f, 1.f, 0.f);
+    const f3 b0 = normalize(cross(n, t0));
+    t0 = cross(b0, n);
+    const f3 m0 = t0, m1 = b0, m2 = n;                                                // columns
+    const float m00 = m0.x, m01 = m0.y, m02 = m0.z, m10 = m1.x, m11 = m1.y, m12 = m1.z, m20 = m2.x, m21 = m2.y, m22 = m2.z;
+    const float ood = 1.f / (+m00 * (m11 * m22 - m21 * m12) - m10 * (m01 * m22 - m21 * m02) + m20 * (m01 * m12 - m11 * m02));
+    f3 i0, i1, i2;                                                                    // columns of the inverse
+    i0.x = +(m11 * m22 - m21 * m12) * ood; i1.x = -(m10 * m22 - m20 * m12) * ood; i2.x = +(m10 * m21 - m20 * m11) * ood;
+    i0.y = -(m01 * m22 - m21 * m02) * ood; i1.y = +(m00 * m22 - m20 * m02) * ood; i2.y = -(m00 * m21 - m20 * m01) * ood;
+    i0.z = +(m01 * m12 - m11 * m02) * ood; i1.z = -(m00 * m12 - m10 * m02) * ood; i2.z = +(m00 * m11 - m10 * m01) * ood;
+    const f3 vh = normalize(giMatVec(i0, i1, i2, wo) * mk3(alpha, alpha, 1.f));
+    const float lenSq = vh.x * vh.x + vh.y * vh.y;
+    const f3 t = lenSq > 0.f ? mk3(-vh.y, vh.x, 0.f) / sqrtf(lenSq) : mk3(1.f, 0.f, 0.f);
+    const f3 b = cross(vh, t);
+    float px, py;
+    giConcentricDisk(rx, ry, px, py);
+    const float sgn = 0.5f * (vh.z + 1.f);
+    py = (1.f - sgn) * sqrtf(1.f - px * px) + sgn * py;
+    f3 h = t * px + b * py + vh * sqrtf(gmax(0.f, 1.f - (px * px + py * py)));
+    h = mk3(h.x * alpha, h.y * alpha, gmax(0.f, h.z));
+    return normalize(giMatVec(m0, m1, m2, h));
+}
+RS_D float giMaterialPdf(const Surf& m, f3 n, f3 wo, f3 wi) {                        // material.h:230-240
+    if (m.type == 0) return satDot(n, wi) * 1.f / RS_PI;
+    if (m.type == 1) {
+        const f3 h = normalize(wo + wi);
+        return mixf(satDot(n, wi) * 1.f / RS_PI, giGTR2Pdf(n, h, wo, m.roughness * m.roughness) / (4.f * absDot(h, wo)), 1.f / (2.f - m.metallic));
+    }
+    return 0.f;
+}
+RS_D f3 giBSDF(const Surf& m, f3 n, f3 wo, f3 wi) { return materialBSDF(m.type, m.metallic, m.roughness, m.baseColor, diffuseTerm(m.baseColor), n, wo, wi); }
+
+enum { GI_BS_INVALID = 0, GI_BS_SMOOTH = 1, GI_BS_SPECULAR = 2 };                    // what the kernel reads of BSDFSampleType (material.h:15-24)
+struct GIBSample { f3 dir, bsdf; float pdf; int kind; };
+RS_D void giMaterialSample(const Surf& m, float ior, f3 n, f3 wo, float rx, float ry, float rz, GIBSample& s) {   // material.h:242-256
+    s.dir = mk3(0.f); s.bsdf = mk3(0.f); s.pdf = 0.f; s.kind = GI_BS_INVALID;
+    if (m.type == 0) {                                                                // lambertianSample :130-135
+        s.dir = giSampleHemisphereCosine(n, rx, ry);
+        s.bsdf = m.baseColor * 1.f / RS_PI;
+        s.pdf = satDot(n, s.dir) * 1.f / RS_PI;
+        s.kind = GI_BS_SMOOTH;
+    } else if (m.type == 1) {                                                         // metallicWorkflowSample :197-216
+        const float alpha = m.roughness * m.roughness;
+        if (rz > (1.f / (2.f - m.metallic))) s.dir = giSampleHemisphereCosine(n, rx, ry);
+        else {
+            const f3 h = giGTR2Sample(n, wo, alpha, rx, ry);
+            s.dir = -giReflect(wo, h);
+        }
+        if (!(dot(n, s.dir) < 0.f)) {
+            s.bsdf = giBSDF(m, n, wo, s.dir);
+            s.pdf = giMaterialPdf(m, n, wo, s.dir);
+            s.kind = GI_BS_SMOOTH;
+        }
+    } else if (m.type == 2) {                                                         // dielectricSample :145-169
+        const float pdfRefl = giFresnel(dot(n, wo), ior);
+        s.bsdf = m.baseColor;
+        if (rz < pdfRefl) {
+            s.dir = giReflect(-wo, n);
+            s.kind = GI_BS_SPECULAR;
+            s.pdf = 1.f;
+        } else {
+            if (!giRefract(n, wo, ior, s.dir)) return;
+            float eta = ior;
+            if (dot(n, wo) < 0) eta = 1.f / eta;
+            s.bsdf = s.bsdf / (eta * eta);
+            s.kind = GI_BS_SPECULAR;
+            s.pdf = 1.f;
+        }
+    }
+}
+RS_D float giPowerHeuristic(float f, float g) { const float f2 = f * f; return f2 / (f2 + g * g); }   // mathUtil.h:81-84
+
+// ------------------------------------------------------------------------------------------------ DevScene::sampleDirectLight
+// scene.h:427-459 (occlusion test BEFORE the facing test), :377-392 for the environment map.  Returns the pdf (<= 0: no contribution);
+// undecided = the any-hit walk could not answer (never with EXACT).
+template <bool EXACT>
+RS_D float giSampleDirectLight(const DevScene& s, f3 pos, float c0, float c1, float c2, float c3, Stack& stack, f3& Li, f3& wi, bool& undecided) {
+    const int len = s.numLights;
+    if (len <= 0) return -1.f;
+    const int pass = min(__float2int_rz((float)len * c0), len - 1);                   // sampler.h:203-207
+    const float2 e = __ldg(s.alias + pass);
+    const int lightId = (c1 < e.x) ? pass : __float_as_int(e.y);
+    if (s.envTex >= 0 && lightId == len - 1) {
+        envSample(s, c2, c3, Li, wi);
+        const int occ = traceOccluded<EXACT>(s, pos, pos + wi * 1e6f, stack);
+        if (occ < 0) { undecided = true; return -1.f; }
+        if (occ) return -1.f;
+        return envPdf(s, Li);
+    }
+    const float4* lp = s.lights + 4 * (size_t)lightId;
+    const float4 a = __ldg(lp), b = __ldg(lp + 1), c = __ldg(lp + 2), d4 = __ldg(lp + 3);
+    const f3 v0 = mk3(a.x, a.y, a.z), v1 = mk3(a.w, b.x, b.y), v2 = mk3(b.z, b.w, c.x);
+    const f3 n = mk3(c.y, c.z, c.w);
+    const float sr = sqrtf(c3);                                                       // mathUtil.h:94-100 (ru = r.z, rv = r.w)
+    const float u = 1.f - sr, v = c2 * sr;
+    const f3 sampled = v1 * u + v2 * v + v0 * (1.f - u - v);
+    const int occ = traceOccluded<EXACT>(s, pos, sampled, stack);
+    if (occ < 0) { undecided = true; return -1.f; }
+    if (occ) return -1.f;
+    const f3 pts = sampled - pos;
+    if (dot(n, pts) > -1e-6f) return -1.f;                                            // SCENE_LIGHT_SINGLE_SIDED
+    Li = mk3(d4.x, d4.y, d4.z);
+    const float len2 = dot(pts, pts);
+    wi = pts * (1.f / sqrtf(len2));
+    return d4.w * len2 / fabsf(dot(n, wi));                                           // pdfAreaToSolidAngle (see sampleLight)
+}
+
+// findTemporalNeighbor<IndirectReservoir> (restir.cu:20-45): index of the history pixel in the planes, or -1
+RS_D long long giFindTemporal(const FrameDev& f, size_t li) {
+    const int primId = f.matId[0][li];
+    const int lastIdx = __float_as_int(f.albedoMotion[li].w);
+    if (lastIdx < 0 || primId <= -1) return -1;
+    if (!rowResident(f, lastIdx / f.W)) return -1;                                    // GI runs on full frames: never taken
+    const size_t lli = (size_t)lastIdx - (size_t)f.bufRow0 * f.W;
+    if (f.matId[1][lli] != primId) return -1;
+    const float4 g = f.geom[0][li], lg = f.geom[1][lli];
+    if (absDot(mk3(g.x, g.y, g.z), mk3(lg.x, lg.y, lg.z)) < .9f || fabsf(lg.w - g.w) > g.w * .1f) return -1;
+    return (long long)lli;
+}
+
+// ------------------------------------------------------------------------------------------------ the pixel
+// restir.cu:263-415 after the jittered primary ray's hit is known.  false = undecided, nothing written.
+template <bool EXACT>
+RS_D bool giAfterHit(const DevScene& s, const FrameDev& f, const GIDev& g, int x, int y, Stack& stack, const TieStore& ts, Rng rng, f3 d, Hit h) {
+    const size_t li = planeIndex(f, x, y);
+    GISample smp = giEmptySample();
+    bool shaded = false, primDelta = false;
+    float primPdf = 1.f;
+    f3 primWo = mk3(0.f);
+    Surf primMat;
+    primMat.type = 0; primMat.baseColor = mk3(0.f); primMat.metallic = 0.f; primMat.roughness = 0.f;
+    if (h.prim >= 0) {
+        GISurf sf;
+        giSurface(s, h, sf);
+        if (sf.m.type != 4) {                                                         // :272
+            shaded = true;
+            f3 throughput = mk3(1.f);
+            f3 wo = -d;
+            f3 pos = sf.pos, nrm = sf.nrm;
+            Surf mat = sf.m;
+            float ior = sf.ior;
+            primWo = wo;
+            primMat = mat;
+            for (int depth = 1; depth <= g.maxDepth; depth++) {
+                const bool deltaBSDF = mat.type == 2;
+                if (mat.type != 2 && dot(nrm, wo) < 0.f) nrm = -nrm;                  // :284-286
+                if (!deltaBSDF && depth > 1) {                                        // :288-299: next-event estimation with MIS
+                    const float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
+                    f3 radiance = mk3(0.f), wi = mk3(0.f);
+                    bool undecided = false;
+                    const float lightPdf = giSampleDirectLight<EXACT>(s, pos, c0, c1, c2, c3, stack, radiance, wi, undecided);
+                    if (undecided) return false;
+                    if (lightPdf > 0.f) {
+                        const float bsdfPdf = giMaterialPdf(mat, nrm, wo, wi);
+                        smp.Lo = smp.Lo + throughput * giBSDF(mat, nrm, wo, wi) * radiance * satDot(nrm, wi) / lightPdf * giPowerHeuristic(lightPdf, bsdfPdf);
+                    }
+                }
+                const float r0 = rng.next(), r1 = rng.next(), r2 = rng.next();
+                GIBSample bs;
+                giMaterialSample(mat, ior, nrm, wo, r0, r1, r2, bs);
+                if (bs.kind == GI_BS_INVALID) break;                                  // :304-309
+                else if (bs.pdf < 1e-8f) break;
+                const bool deltaSample = bs.kind == GI_BS_SPECULAR;
+                if (depth > 1) throughput = throughput * (bs.bsdf / bs.pdf * (deltaSample ? 1.f : absDot(nrm, bs.dir)));
+                else { primPdf = bs.pdf; primDelta = deltaSample; smp.xv = pos; smp.nv = nrm; }
+                const f3 ro = pos + bs.dir * 1e-5f, rd = bs.dir;                      // makeOffsetedRay, intersections.h:12
+                const f3 curPos = pos;
+                Hit hh;
+                if (!giClosest<EXACT>(s, g, ro, rd, stack, ts, hh)) return false;
+                wo = -rd;
+                if (hh.prim < 0) {                                                    // :332-343
+                    if (s.envTex >= 0) {
+                        const f3 env = envLookup(s, rd);
+                        const f3 radiance = env * throughput;
+                        const int4 info = __ldg(s.texInfo + s.envTex);
+                        const float envP = luminance(env) * s.sumLightPowerInv * (float)info.x * (float)info.y * .5f;   // environmentMapPdf, scene.h:358-362
+                        const float weight = deltaSample ? 1.f : giPowerHeuristic(bs.pdf, envP);
+                        smp.Lo = smp.Lo + radiance * weight;
+                    }
+                    break;
+                }
+                giSurface(s, hh, sf);
+                pos = sf.pos; nrm = sf.nrm; mat = sf.m; ior = sf.ior;
+                if (mat.type == 4) {                                                  // :346-371
+                    if (dot(nrm, rd) < 0.f) break;                                    // SCENE_LIGHT_SINGLE_SIDED
+                    const f3 radiance = mat.baseColor;
+                    float weight = 1.f;
+                    if (!(deltaSample || depth == 1)) {
+                        const float area = triangleArea(sf.v0, sf.v1, sf.v2);         // getPrimitiveArea, scene.h:121-126
+                        const f3 yx = curPos - pos;                                   // pdfAreaToSolidAngle, mathUtil.h:182-185
+                        const float lp = luminance(radiance) * s.sumLightPowerInv * area * dot(yx, yx) / absDot(nrm, normalize(yx));
+                        weight = giPowerHeuristic(bs.pdf, lp);
+                    }
+                    smp.Lo = smp.Lo + radiance * throughput * weight;
+                    if (depth == 1) { smp.xs = pos; smp.ns = nrm; }
+                    break;
+                }
+                if (depth == 1) { smp.xs = pos; smp.ns = nrm; }
+            }
+        }
+    }
+    // WriteSample (:380-415)
+    GIResv R;
+    R.s = giEmptySample(); R.M = 0; R.w = 0.f;
+    float sampleWeight = 0.f;
+    if (!(luminance(smp.Lo) < 1e-8f)) {                                               // !IndirectLiSample::invalid()
+        sampleWeight = luminance(smp.Lo / primPdf);
+        if (isnan(sampleWeight) || sampleWeight < 0.f) sampleWeight = 0.f;
+    }
+    {
+        const float r = rng.next();                                                   // Reservoir::update, restir.h:38-45
+        R.w += sampleWeight; R.M++;
+        if (r * R.w < sampleWeight) R.s = smp;
+    }
+    if (!g.first && (g.reuse & 1)) {
+        const long long lli = giFindTemporal(f, li);
+        GIResv T;
+        T.s = giEmptySample(); T.M = 0; T.w = 0.f;
+        if (lli >= 0) T = giLoad(g.resvIn, g.nszIn, (size_t)lli);
+        if (!giResvInvalid(T)) {                                                      // Reservoir::merge, restir.h:61-70
+            const float r = rng.next();
+            R.w += T.w; R.M += T.M;
+            if (r * R.w < T.w) R.s = T.s;
+        }
+    }
+    f3 indirect = mk3(0.f);
+    const GISample sample = R.s;
+    if (R.M > 20) { R.w *= 20.f / R.M; R.M = 20; }                                    // clamp<20>, restir.h:88-93
+    if (shaded && !giResvInvalid(R)) {
+        const f3 primWi = normalize(sample.xs - sample.xv);
+        indirect = R.s.Lo / luminance(R.s.Lo) * R.w / (float)R.M;
+        indirect = indirect * (giBSDF(primMat, sample.nv, primWo, primWi) * (primDelta ? 1.f : satDot(sample.nv, primWi)));
+    }
+    if (hasNanOrInf(indirect)) indirect = mk3(0.f);
+    giStore(g.resvOut, g.nszOut, li, R);
+    float* out = g.indirect + 3 * li;
+    const f3 prev = mk3(out[0], out[1], out[2]);
+    const f3 v = (prev * (float)g.iter + indirect) / (float)(g.iter + 1);             // :415
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+    return true;
+}
+
+RS_D void giPixelExact(const DevScene& s, const FrameDev& f, const CamDev& cam, const GIDev& g, int looper, int x, int y, Stack& stack) {
+    Rng rng;
+    f3 o, d;
+    jitteredRay(f, cam, looper, x, y, rng, o, d);
+    const RayT ray = makeRayT(o, d);
+    Hit h;
+    traceClosestExact(s, ray, h, stack);
+    TieStore none;
+    none.base = nullptr;
+    giAfterHit<true>(s, f, g, x, y, stack, none, rng, d, h);
+}
+
+__global__ void __launch_bounds__(RS_BLOCK) k_restir_indirect(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                              const __grid_constant__ CamDev cam, const __grid_constant__ GIDev g, int looper) {
+    RS_DECLARE_STACK(stack);
+    RS_DECLARE_PACKET(pk, 1);
+    int x, y;
+    const bool active = pixelOf(f, x, y);
+    Rng rng;
+    rng.x = 1;
+    f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
+    if (active) jitteredRay(f, cam, looper, x, y, rng, o, d);
+    const f3 oc = cameraOrigin(cam);
+    PRay a = prayBegin(oc, d, active, pk_ta);
+    packetWalk<false>(s, oc, a, a, pk_ta, pk_ta, pk_wst);
+    if (active) {
+        Hit h;
+        if (!prayResolve(s, oc, d, a, pk_ta, h) || !giAfterHit<false>(s, f, g, x, y, stack, pk_ta, rng, d, h)) enqueuePixel(f, x, y);
+    }
+}
+__global__ void __launch_bounds__(RS_BLOCK) k_restir_indirect_exact(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                                    const __grid_constant__ CamDev cam, const __grid_constant__ GIDev g, int looper) {
+    RS_DECLARE_STACK(stack);
+    int x, y;
+    if (pixelOf(f, x, y)) giPixelExact(s, f, cam, g, looper, x, y, stack);
+}
+__global__ void __launch_bounds__(RS_BLOCK) k_restir_indirect_fix(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                                  const __grid_constant__ CamDev cam, const __grid_constant__ GIDev g, int looper) {
+    RS_DECLARE_STACK(stack);
+    const unsigned n = *f.queueCount;
+    const unsigned numWarps = gridDim.x * (RS_BLOCK / 32), gw = blockIdx.x * (RS_BLOCK / 32) + (threadIdx.x >> 5);
+    for (unsigned i = (threadIdx.x & 31) * numWarps + gw; i < n; i += 32 * numWarps) {
+        const int idx = f.queue[i];
+        giPixelExact(s, f, cam, g, looper, idx % f.W, idx / f.W, stack);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g.fallback) atomicAdd(g.fallback, n);
+}
+
+// device reservoirs -> the reference's Reservoir<IndirectLiSample> (17 x 4 bytes: Lo xv nv xs ns, numSamples (int), weight)
+__global__ void k_export_gi(const float4* __restrict__ rec, const float* __restrict__ nsz, float* out17, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GIResv r = giLoad(rec, nsz, i);
+    float* o = out17 + 17 * i;
+    o[0] = r.s.Lo.x; o[1] = r.s.Lo.y; o[2] = r.s.Lo.z; o[3] = r.s.xv.x; o[4] = r.s.xv.y; o[5] = r.s.xv.z;
+    o[6] = r.s.nv.x; o[7] = r.s.nv.y; o[8] = r.s.nv.z; o[9] = r.s.xs.x; o[10] = r.s.xs.y; o[11] = r.s.xs.z;
+    o[12] = r.s.ns.x; o[13] = r.s.ns.y; o[14] = r.s.ns.z;
+    o[15] = __int_as_float(r.M); o[16] = r.w;
+}
+
+#ifndef RS_HOST_EMU
+int launchRestirIndirect(const DevScene& s, const FrameDev& f, const CamDev& cam, const GIDev& g, int looper, cudaStream_t st) {
+    if (s.traversal == RS_TRAVERSAL_EXACT) { k_restir_indirect_exact<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, g, looper); return 1; }
+    cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
+    k_restir_indirect<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
+    k_restir_indirect_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
+    return 2;
+}
+void launchExportGI(const float4* rec, const float* nsz, float* out17, size_t n, cudaStream_t st) {
+    k_export_gi<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rec, nsz, out17, n);
+}
+#endif  // RS_HOST_EMU

@@ -7,6 +7,7 @@
 //   k_ptdirect    one-sample NEE reference image                            (pathtrace.cu:279-328)
 //   k_tonemap     tone-map + gamma + 8-bit pack                             (pathtrace.cu:30-56)
 //   k_export_*    device-internal planes -> reference host layouts
+//   k_restir_indirect*  ReSTIR GI                                            (restir.cu:242-416; gi_kernels.inl)
 //
 // Compiled with -fmad=false: every fp32 operation that feeds a discrete decision (hit selection, reservoir
 // selection, similarity tests, pixel truncation) is a plain IEEE mul/add/div/sqrt in the reference's order,
@@ -165,8 +166,12 @@ RS_D bool triHit(const RayT& r, f3 v0, f3 v1, f3 v2, float& bx, float& by, float
 struct F8 { float4 lo, hi; };
 RS_D F8 ldg256(const float4* p) {
     F8 r;
+#ifdef RS_HOST_EMU      /* tests/emu: this translation unit compiled by g++ to check the kernels' arithmetic on the CPU; never in the product */
+    r.lo = p[0]; r.hi = p[1];
+#else
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w) : "l"(p));
+#endif
     return r;
 }
 
@@ -2130,6 +2135,7 @@ __global__ void k_export_resv(const DevScene s, const ResvD* __restrict__ src, f
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+#ifndef RS_HOST_EMU
 static inline dim3 pixelGrid(const FrameDev& f) { return dim3((f.W + 15) / 16, (f.rowHi - f.rowLo + 7) / 8); }
 
 #define RS_FIX_BLOCKS 296   /* 2 per SM; the fix-up kernels stride over the queue */
@@ -2244,5 +2250,10 @@ void launchExportGeom(const float4* geom, const float4* am, float* albedo, float
 void launchExportResv(const DevScene& s, const ResvD* src, float* out36, int* lightIdx, size_t n, cudaStream_t st) {
     k_export_resv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, src, out36, lightIdx, n);
 }
+
+#endif  // RS_HOST_EMU
+
+// ------------------------------------------------------------------------------------------------ ReSTIR GI
+#include "gi_kernels.inl"
 
 }  // namespace rs

@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes driver of tests/emu/_build/libgi_emu.so (the kernels' device code compiled for the host)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import build as _emu_build  # noqa: E402
+
+from restir_b200 import api  # noqa: E402   (RstrSceneDesc / RstrCamera structures and the host-side camera functions only)
+
+
+class Emu:
+    def __init__(self):
+        L = self.lib = C.CDLL(_emu_build.build())
+        vp, ip = C.c_void_p, C.c_int
+        L.emu_scene_create.restype = vp
+        L.emu_scene_create.argtypes = [C.POINTER(api.RstrSceneDesc)]
+        L.emu_scene_destroy.argtypes = [vp]
+        L.emu_frame_create.restype = vp
+        L.emu_frame_create.argtypes = [vp, ip, ip]
+        L.emu_frame_destroy.argtypes = [vp]
+        L.emu_gbuffer_render.argtypes = [vp, C.POINTER(api.RstrCamera)]
+        L.emu_gbuffer_update.argtypes = [vp, C.POINTER(api.RstrCamera)]
+        L.emu_gi_reset.argtypes = [vp]
+        L.emu_restir_indirect.argtypes = [vp, C.POINTER(api.RstrCamera), ip, ip, ip, ip, ip]
+        L.emu_gi_undecided.restype = C.c_ulonglong
+        L.emu_gi_undecided.argtypes = [vp]
+        L.emu_gi_indirect.restype = vp
+        L.emu_gi_indirect.argtypes = [vp]
+        L.emu_gi_reservoirs.restype = vp
+        L.emu_gi_reservoirs.argtypes = [vp]
+        L.emu_frame_plane.restype = vp
+        L.emu_frame_plane.argtypes = [vp, ip]
+
+    def scene(self, sd):
+        v = np.ascontiguousarray(sd.vertices, np.float32)
+        n = np.ascontiguousarray(sd.normals, np.float32)
+        t = np.ascontiguousarray(sd.texcoords, np.float32)
+        m = np.ascontiguousarray(sd.material_ids, np.int32)
+        mats = np.ascontiguousarray(sd.materials)
+        texs = [np.ascontiguousarray(x, np.float32) for x in getattr(sd, "textures", [])]
+        tarr = (api.RstrTexture * max(len(texs), 1))()
+        for i, x in enumerate(texs):
+            tarr[i] = api.RstrTexture(int(x.shape[1]), int(x.shape[0]), x.ctypes.data)
+        desc = api.RstrSceneDesc(int(m.shape[0]), v.ctypes.data, n.ctypes.data, t.ctypes.data, m.ctypes.data, len(mats), mats.ctypes.data,
+                                 len(texs), C.cast(tarr, C.c_void_p) if texs else None, int(getattr(sd, "env_map", -1)) + 1)
+        h = self.lib.emu_scene_create(C.byref(desc))
+        assert h, "emu_scene_create failed"
+        return h
+
+    @staticmethod
+    def _view(ptr, dtype, shape):
+        n = int(np.prod(shape))
+        buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape).copy()
+
+    def run_gi(self, sd, frames, max_depth=3, reuse=1, accumulate=False, orbit=True, traced_tree=False, gbuffer=False):
+        """The frame loop of helpers.run_oracle_gi through the emulated device code.  Returns (frames, undecided pixel count)."""
+        W, H = sd.resolution
+        L = self.lib
+        sc = self.scene(sd)
+        fr = L.emu_frame_create(sc, W, H)
+        base = api.Camera.from_scene(sd)
+        out = []
+        for f in range(frames):
+            cam = base.orbit(f) if orbit else base
+            L.emu_gbuffer_render(fr, C.byref(cam))
+            L.emu_restir_indirect(fr, C.byref(cam), f, f if accumulate else 0, max_depth, reuse, 1 if traced_tree else 0)
+            r = self._view(L.emu_gi_reservoirs(fr), np.float32, (W * H, 17))
+            r[:, 15] = r[:, 15].view(np.int32).astype(np.float32)          # numSamples: int bits in the reference layout
+            d = {"indirect": self._view(L.emu_gi_indirect(fr), np.float32, (W * H, 3)), "reservoir": r}
+            if gbuffer:
+                g = self._view(L.emu_frame_plane(fr, 0), np.float32, (W * H, 4))
+                am = self._view(L.emu_frame_plane(fr, 2), np.float32, (W * H, 4))
+                d.update(normal=np.ascontiguousarray(g[:, :3]), depth=np.ascontiguousarray(g[:, 3]), matid=self._view(L.emu_frame_plane(fr, 1), np.int32, (W * H,)),
+                         albedo=np.ascontiguousarray(am[:, :3]), motion=np.ascontiguousarray(am[:, 3]).view(np.int32))
+            out.append(d)
+            L.emu_gbuffer_update(fr, C.byref(cam))
+        und = int(L.emu_gi_undecided(fr))
+        L.emu_frame_destroy(fr)
+        L.emu_scene_destroy(sc)
+        return out, und

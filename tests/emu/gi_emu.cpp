@@ -1,0 +1,194 @@
+// gi_emu.cpp -- TEST INFRASTRUCTURE ONLY (see cuda_host_shim.h).  The device code of restir_b200/csrc/kernels.cu + gi_kernels.inl compiled by
+// g++ and driven one pixel per call: G-buffer (gbufferPixelExact) and ReSTIR GI (giAfterHit), with the same libm as the oracle, so the two
+// must agree bit for bit.  Two modes: every ray with the reference-order walk, or the bounce / shadow rays with the per-lane walks of the
+// traced tree (traceClosestFast / traceOccludedFast; the warp-level packet walk cannot be emulated and its primary hit is taken from the
+// reference-order walk).  Built by tests/emu/build.py into tests/emu/_build (git-ignored); never part of librestir_b200.so.
+#include "cuda_host_shim.h"
+
+#include "../../restir_b200/csrc/kernels.cu"
+
+#include <string>
+#include <vector>
+
+using namespace rs;
+
+namespace {
+
+struct EmuScene {
+    HostScene hs;
+    DevScene dev{};
+    unsigned int fallback[4] = {0, 0, 0, 0};
+};
+
+struct EmuFrame {
+    EmuScene* sc;
+    int W, H;
+    std::vector<float4> geom[2], albedoMotion;
+    std::vector<int> matId[2];
+    std::vector<float4> resv[2];
+    std::vector<float> nsz[2], indirect, export17;
+    unsigned int counters[4] = {0, 0, 0, 0};
+    int cur = 0, out = 0;
+    bool first = true, haveLast = false;
+    RstrCamera lastCamera{};
+    unsigned long long undecided = 0;
+};
+
+CamDev toCamDev(const RstrCamera& c) {          // rsToCamDev (capi.cu)
+    CamDev d;
+    memcpy(d.position, c.position, 12); memcpy(d.right, c.right, 12); memcpy(d.up, c.up, 12); memcpy(d.view, c.view, 12);
+    memcpy(d.rotInv, c.rotationMatInv, 36);
+    d.aspect = (float)c.resolution[0] / c.resolution[1];
+    d.tanFovY = tanf(radians(c.fov[1]));
+    d.focalDist = c.focalDist;
+    d.pixelSizeX = 1.f / (float)c.resolution[0];
+    d.pixelSizeY = 1.f / (float)c.resolution[1];
+    d.resX = (float)c.resolution[0]; d.resY = (float)c.resolution[1];
+    return d;
+}
+
+FrameDev toFrameDev(EmuFrame* f) {
+    FrameDev d{};
+    d.W = f->W; d.H = f->H; d.rowLo = 0; d.rowHi = f->H; d.bufRow0 = 0; d.bufRows = f->H;
+    d.geom[0] = f->geom[f->cur].data(); d.geom[1] = f->geom[f->cur ^ 1].data();
+    d.matId[0] = f->matId[f->cur].data(); d.matId[1] = f->matId[f->cur ^ 1].data();
+    d.albedoMotion = f->albedoMotion.data();
+    d.haloMiss = f->counters; d.motionRows = f->counters + 1;
+    return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* emu_scene_create(const RstrSceneDesc* desc) {                 // the HostScene fill of rstr_scene_create (capi.cu) + buildHostScene
+    EmuScene* sc = new EmuScene;
+    HostScene& hs = sc->hs;
+    const int T = desc->numTris;
+    hs.T = T;
+    hs.vertices.resize(3 * (size_t)T); hs.normals.resize(3 * (size_t)T); hs.texcoords.assign(6 * (size_t)T, 0.f);
+    memcpy(hs.vertices.data(), desc->vertices, 36 * (size_t)T);
+    memcpy(hs.normals.data(), desc->normals, 36 * (size_t)T);
+    if (desc->texcoords) memcpy(hs.texcoords.data(), desc->texcoords, 24 * (size_t)T);
+    hs.materialIds.assign(desc->materialIds, desc->materialIds + T);
+    hs.materials.assign(desc->materials, desc->materials + desc->numMaterials);
+    hs.textures.resize(desc->numTextures);
+    for (int t = 0; t < desc->numTextures; t++) {
+        const RstrTexture& src = desc->textures[t];
+        hs.textures[t].w = src.width; hs.textures[t].h = src.height;
+        hs.textures[t].rgb.resize((size_t)src.width * src.height);
+        memcpy(hs.textures[t].rgb.data(), src.rgb, 12 * hs.textures[t].rgb.size());
+    }
+    hs.envMapTexId = desc->envMap - 1;
+    std::string err;
+    if (!buildHostScene(hs, err)) { fprintf(stderr, "emu_scene_create: %s\n", err.c_str()); delete sc; return nullptr; }
+    DevScene& d = sc->dev;                                          // ensureUploaded (capi.cu) with the host arrays themselves
+    d.fallbackRays = sc->fallback;
+    d.nodes = (const float4*)hs.packed.data(); d.triGeom = (const float4*)hs.fastTris.data(); d.triNorm = (const float4*)hs.triNorm.data();
+    d.materials = hs.materials.data(); d.alias = (const float2*)hs.alias.data(); d.lights = (const float4*)hs.lights.data();
+    d.fastNodes = (const float4*)hs.fastNodes.data(); d.primToFast = hs.primToFast.data(); d.rank = hs.rank.data();
+    d.numTris = hs.T; d.numFastNodes = (int)hs.fastNodes.size(); d.fastRoot = hs.fastRoot; d.traversal = RS_TRAVERSAL_EXACT;
+    memcpy(d.fastRootMin, hs.fastRootMin, 12); memcpy(d.fastRootMax, hs.fastRootMax, 12);
+    d.numLights = (int)hs.alias.size();
+    d.texData = (const float4*)hs.texData.data(); d.texInfo = (const int4*)hs.texInfo.data(); d.triUV = (const float4*)hs.triUV.data();
+    d.anyMaps = hs.anyMaps ? 1 : 0;
+    d.envTex = hs.envMapTexId; d.envLen = (int)hs.envAlias.size();
+    d.envAlias = (const float2*)hs.envAlias.data(); d.envDir = (const float4*)hs.envDir.data();
+    d.sumLightPowerInv = hs.sumLightPowerInv;
+    d.rootRef = hs.rootRef;
+    memcpy(d.rootMin, &hs.rootBox.pMin, 12); memcpy(d.rootMax, &hs.rootBox.pMax, 12);
+    return sc;
+}
+void emu_scene_destroy(void* sc) { delete (EmuScene*)sc; }
+
+void* emu_frame_create(void* sc, int W, int H) {
+    EmuFrame* f = new EmuFrame;
+    f->sc = (EmuScene*)sc; f->W = W; f->H = H;
+    const size_t n = (size_t)W * H;
+    for (int i = 0; i < 2; i++) {
+        f->geom[i].assign(n, make_float4(0, 0, 0, 0)); f->matId[i].assign(n, 0);
+        f->resv[i].assign(4 * n, make_float4(0, 0, 0, 0)); f->nsz[i].assign(n, 0.f);
+    }
+    f->albedoMotion.assign(n, make_float4(0, 0, 0, 0));
+    f->indirect.assign(3 * n, 0.f);
+    return f;
+}
+void emu_frame_destroy(void* f) { delete (EmuFrame*)f; }
+
+// rstr_gbuffer_render in RS_TRAVERSAL_EXACT: k_gbuffer_exact's body per pixel
+void emu_gbuffer_render(void* fv, const RstrCamera* cam) {
+    EmuFrame* f = (EmuFrame*)fv;
+    const FrameDev d = toFrameDev(f);
+    const CamDev c = toCamDev(*cam), lc = toCamDev(f->haveLast ? f->lastCamera : *cam);
+    const DevScene& s = f->sc->dev;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < f->H; y++)
+        for (int x = 0; x < f->W; x++) {
+            threadIdx.x = 0;
+            RS_DECLARE_STACK(stack);
+            gbufferPixelExact(s, d, c, lc, x, y, stack);
+        }
+}
+void emu_gbuffer_update(void* fv, const RstrCamera* cam) {
+    EmuFrame* f = (EmuFrame*)fv;
+    f->lastCamera = *cam; f->haveLast = true; f->cur ^= 1;
+}
+void emu_gi_reset(void* fv) { ((EmuFrame*)fv)->first = true; }
+
+// rstr_restir_indirect.  tracedTree = 0: k_restir_indirect_exact's body per pixel.  tracedTree = 1: the primary hit from the reference-order
+// walk (standing in for the packet walk), then giAfterHit<false>: bounce rays through traceClosestFast, shadow rays through
+// traceOccludedFast; an undecided pixel is recomputed like k_restir_indirect_fix does.
+void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, int traceDepth, int reuse, int tracedTree) {
+    EmuFrame* f = (EmuFrame*)fv;
+    const FrameDev d = toFrameDev(f);
+    const CamDev c = toCamDev(*cam);
+    const DevScene& s = f->sc->dev;
+    GIDev g{};
+    g.resvOut = f->resv[f->out].data(); g.resvIn = f->resv[f->out ^ 1].data();
+    g.nszOut = f->nsz[f->out].data(); g.nszIn = f->nsz[f->out ^ 1].data();
+    g.indirect = f->indirect.data(); g.fallback = nullptr;
+    g.maxDepth = traceDepth; g.reuse = reuse; g.first = f->first ? 1 : 0; g.iter = iter; g.bounceWalk = RS_TRAVERSAL_FAST;
+    unsigned long long undecided = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : undecided)
+    for (int y = 0; y < f->H; y++)
+        for (int x = 0; x < f->W; x++) {
+            threadIdx.x = 0;
+            RS_DECLARE_STACK(stack);
+            if (!tracedTree) { giPixelExact(s, d, c, g, looper, x, y, stack); continue; }
+            RS_DECLARE_PACKET(pk, 1);
+            (void)pk_tb; (void)pk_wst;
+            Rng rng;
+            f3 o, dir;
+            jitteredRay(d, c, looper, x, y, rng, o, dir);
+            const RayT ray = makeRayT(o, dir);
+            Hit h;
+            traceClosestExact(s, ray, h, stack);
+            if (!giAfterHit<false>(s, d, g, x, y, stack, pk_ta, rng, dir, h)) {
+                undecided++;
+                giPixelExact(s, d, c, g, looper, x, y, stack);
+            }
+        }
+    f->undecided += undecided;
+    f->out ^= 1;
+    f->first = false;
+}
+unsigned long long emu_gi_undecided(void* fv) { return ((EmuFrame*)fv)->undecided; }
+const float* emu_gi_indirect(void* fv) { return ((EmuFrame*)fv)->indirect.data(); }
+// k_export_gi's body: the reservoirs the last call wrote, 17 x 4 bytes each (numSamples as int bits)
+const float* emu_gi_reservoirs(void* fv) {
+    EmuFrame* f = (EmuFrame*)fv;
+    const size_t n = (size_t)f->W * f->H;
+    f->export17.resize(17 * n);
+    blockDim.x = 1; threadIdx.x = 0;
+    for (size_t i = 0; i < n; i++) {
+        blockIdx.x = (unsigned)i;
+        k_export_gi(f->resv[f->out ^ 1].data(), f->nsz[f->out ^ 1].data(), f->export17.data(), n);
+    }
+    return f->export17.data();
+}
+const void* emu_frame_plane(void* fv, int which) {                   // 0 geom {n, depth}, 1 matId, 2 {albedo, motion} of the current frame
+    EmuFrame* f = (EmuFrame*)fv;
+    return which == 0 ? (const void*)f->geom[f->cur].data() : which == 1 ? (const void*)f->matId[f->cur].data() : (const void*)f->albedoMotion.data();
+}
+
+}  // extern "C"

@@ -150,3 +150,51 @@ def run_oracle_gi(orc, sd, frames, max_depth=3, reuse=1, accumulate=False, orbit
     fo.close()
     so.close()
     return out
+
+
+def run_gpu_gi(rb, sd, frames, max_depth=3, reuse=1, accumulate=False, orbit=True, exact=False, bounce_exact=False, scene=None):
+    """The same loop through the C ABI (rstr_gi_*); reservoirs come back in the reference's 68-byte layout and are returned as
+    (P, 17) float32 with numSamples converted to float, like the oracle's export.  Also returns the number of fix-up pixels."""
+    W, H = sd.resolution
+    sc = scene or rb.Scene.from_arrays(sd)
+    sc.set_traversal(exact)
+    fr = sc.frame(W, H)
+    gi = rb.ReSTIRIndirect(fr)
+    gi.set_bounce_walk(bounce_exact)
+    base = rb.Camera.from_scene(sd)
+    out = []
+    for f in range(frames):
+        cam = base.orbit(f) if orbit else base
+        fr.gbuffer_render(cam)
+        gi.restir_indirect(cam, f, f if accumulate else 0, max_depth, reuse)
+        r = gi.read_reservoirs()
+        r17 = np.concatenate([r["Lo"], r["xv"], r["nv"], r["xs"], r["ns"], r["numSamples"].astype(np.float32)[:, None], r["weight"][:, None]], axis=1)
+        out.append({"indirect": gi.read(), "reservoir": np.ascontiguousarray(r17, np.float32)})
+        fr.gbuffer_update(cam)
+    fallback = gi.fallback_pixels()
+    gi.close()
+    fr.close()
+    if scene is None:
+        sc.close()
+    return out, fallback
+
+
+def gi_agreement(got, want, tol=1e-3):
+    """Per-frame agreement statistics between two GI runs whose BSDF sampling went through different libm's (sinf / cosf)."""
+    ia, ib = got["indirect"], want["indirect"]
+    scale = np.maximum(np.abs(ia), np.abs(ib)).max(1)
+    err = np.abs(ia - ib).max(1)
+    ok = err <= tol * scale + 1e-7
+    ra, rb_ = got["reservoir"], want["reservoir"]
+    lit = scale > 0
+    return {
+        "bit_identical": float((ia.view(np.uint32) == ib.view(np.uint32)).all(1).mean()),
+        "within_tol": float(ok.mean()),
+        "within_tol_lit": float(ok[lit].mean()) if lit.any() else 1.0,
+        "lit": float(lit.mean()),
+        "mean_got": float(ia.mean()), "mean_want": float(ib.mean()),
+        "M_equal": float((ra[:, 15] == rb_[:, 15]).mean()),
+        "xv_nv_bit_identical": float((ra[:, 3:9].view(np.uint32) == rb_[:, 3:9].view(np.uint32)).all(1).mean()),
+        "xs_close": float((np.abs(ra[:, 9:12] - rb_[:, 9:12]).max(1) <= 1e-4 * (1.0 + np.abs(rb_[:, 9:12]).max(1))).mean()),
+        "weight_close": float((np.abs(ra[:, 16] - rb_[:, 16]) <= tol * np.maximum(np.abs(ra[:, 16]), np.abs(rb_[:, 16])) + 1e-7).mean()),
+    }

@@ -1,0 +1,67 @@
+"""CPU: the DEVICE code of the ReSTIR GI kernels (restir_b200/csrc/kernels.cu + gi_kernels.inl), compiled by g++ through
+tests/emu/cuda_host_shim.h and run one pixel per call, against the oracle -- bit for bit, because here both sides use the same libm.
+
+This is a check of the kernels' arithmetic and control flow that needs no GPU (transcription errors, RNG ledger, reservoir logic, the
+per-lane walk of the traced tree, the fix-up path, the export layout); it is test infrastructure, not a CPU path of the product: the
+emulation library is built into tests/emu/_build and nothing under restir_b200/ can load it.  The GPU run of the same code
+(tests/test_restir_gi.py, -m gpu) differs from this one only by libdevice's sinf / cosf and by the warp-level packet walk of the
+primary rays, which cannot be emulated (its hit is taken from the reference-order walk here).
+"""
+import dataclasses
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+from restir_b200 import scenes
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from emu import Emu
+
+    return Emu()
+
+
+@pytest.mark.parametrize("name", ["cornell", "cornell_metal", "cornell_glass", "gen2000", "cornell_tex"])
+def test_gi_device_code_matches_golden(emu, name):
+    """k_gbuffer_exact + k_restir_indirect_exact per pixel against the fixture of the reference's own code (tests/golden/gi.npz)."""
+    sd = helpers.gi_scenes()[name]
+    g = np.load(os.path.join(helpers.GOLDEN, "gi.npz"))
+    got, _ = emu.run_gi(sd, 3, 3, 1)
+    for f in range(3):
+        assert helpers.mismatches(got[f]["indirect"], g["%s_f%d_indirect" % (name, f)]) == 0, f
+    assert helpers.mismatches(got[2]["reservoir"], g["%s_f2_reservoir" % name]) == 0
+    acc, _ = emu.run_gi(sd, 2, 2, 0, accumulate=True, orbit=False)
+    assert helpers.mismatches(acc[-1]["indirect"], g["%s_acc_indirect" % name]) == 0
+
+
+@pytest.mark.parametrize("name", ["gen20k", "cornell_glass", "gen2000_tex"])
+def test_gi_device_code_traced_tree_matches_oracle(emu, port_oracle, name):
+    """Bounce rays through traceClosestFast, shadow rays through traceOccludedFast, undecided pixels through the fix-up path: same
+    bits as the oracle (and therefore as the reference-order walk), depth 5, four accumulated orbit frames with temporal reuse."""
+    sd = {"gen20k": lambda: scenes.procedural(3, 20000, 1000, (320, 180)),
+          "cornell_glass": lambda: dataclasses.replace(helpers.gi_scenes()["cornell_glass"], resolution=(192, 144)),
+          "gen2000_tex": lambda: dataclasses.replace(helpers.textured_scenes()["gen2000_tex"], resolution=(192, 144))}[name]()
+    want = helpers.run_oracle_gi(port_oracle, sd, 4, 5, 1, accumulate=True)
+    exact, _ = emu.run_gi(sd, 4, 5, 1, accumulate=True)
+    traced, undecided = emu.run_gi(sd, 4, 5, 1, accumulate=True, traced_tree=True)
+    helpers.assert_frames_equal(exact, want, "device code, reference-order walk, vs oracle")
+    helpers.assert_frames_equal(traced, want, "device code, traced tree, vs oracle")
+    if name == "gen20k":
+        assert undecided > 0            # the fix-up path was exercised
+    assert (want[-1]["indirect"].sum(1) > 0).mean() > 0.2
+
+
+def test_gbuffer_device_code_matches_oracle(emu, port_oracle):
+    """The G-buffer the GI kernel reads (k_gbuffer_exact's per-pixel body) against the oracle's, over an orbit."""
+    sd = dataclasses.replace(helpers.textured_scenes()["gen2000_tex"], resolution=(96, 72))
+    got, _ = emu.run_gi(sd, 3, 1, 1, gbuffer=True)
+    want = helpers.run_oracle(port_oracle, sd, 3, 0, want=helpers.GBUF)
+    for f in range(3):
+        for n in helpers.GBUF:
+            assert helpers.mismatches(got[f][n], want[f][n]) == 0, (f, n)
