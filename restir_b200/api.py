@@ -154,6 +154,7 @@ def lib() -> C.CDLL:
     L.rstr_gi_read.argtypes = [vp, vp, vp]
     L.rstr_gi_indirect_device.argtypes = [vp, C.POINTER(vp)]
     L.rstr_gi_set_bounce_walk.argtypes = [vp, ip]
+    L.rstr_gi_set_pipeline.argtypes = [vp, ip]
     L.rstr_gi_fallback_pixels.argtypes = [vp, C.POINTER(C.c_uint), ip]
     L.rstr_scene_fallback_rays.argtypes = [vp, C.POINTER(C.c_ulonglong), ip]
     L.rstr_camera_update.argtypes = [C.POINTER(RstrCamera)]
@@ -595,6 +596,10 @@ class ReSTIRIndirect:
 
     def set_bounce_walk(self, exact: bool) -> None:
         _check(lib().rstr_gi_set_bounce_walk(self.h, 1 if exact else 0))
+
+    def set_pipeline(self, staged: bool) -> None:
+        """rstr_gi_set_pipeline: one kernel per frame, or primary rays / one launch per bounce over the live paths / resolve (same bits)."""
+        _check(lib().rstr_gi_set_pipeline(self.h, 1 if staged else 0))
 
     def fallback_pixels(self, reset: bool = True) -> int:
         n = C.c_uint(0)

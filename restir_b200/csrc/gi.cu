@@ -1,6 +1,9 @@
 // gi.cu -- C ABI of ReSTIR GI: ReSTIRIndirect (restir.cu:448-476) and the indirect-reservoir share of
 // ReSTIRInit / ReSTIRFree / ReSTIRReset (restir.cu:491-496, 511-512, 516).  The kernels are in gi_kernels.inl (kernels.cu).
 // The reference ships the call commented out (main.cpp:168) with Settings::traceDepth = 0; here it is reachable through rstr_gi_*.
+#include <stdlib.h>
+#include <string.h>
+
 #include <utility>
 
 #include "capi_internal.h"
@@ -18,10 +21,18 @@ struct RstrGI {
     int out = 0;                               // which of resv[] is devIndTemporalReservoir (written by the next call)
     bool first = true;                         // ReSTIRFirstFrame
     int bounceWalk = RS_TRAVERSAL_FAST;
+    int pipeline = RSTR_GI_PIPELINE_FUSED;
+    // staged pipeline (allocated on first use): per-pixel hand-over planes, pixel status, two path queues, per-depth path counts
+    float4* pix = nullptr;
+    int* pixStatus = nullptr;
+    float4* pathQ[2] = {nullptr, nullptr};
+    unsigned int* pathCount = nullptr;
 };
 
+#define RS_GI_MAX_DEPTH 64
+
 static void giFree(RstrGI* g) {
-    void* all[] = {g->resv[0], g->resv[1], g->nsz[0], g->nsz[1], g->indirect, g->scratch, g->fallback};
+    void* all[] = {g->resv[0], g->resv[1], g->nsz[0], g->nsz[1], g->indirect, g->scratch, g->fallback, g->pix, g->pixStatus, g->pathQ[0], g->pathQ[1], g->pathCount};
     for (void* p : all) cudaFree(p);
     delete g;
 }
@@ -47,6 +58,10 @@ int rstr_gi_create(RstrFrame* f, RstrGI** out) {
     if (e == cudaSuccess) e = cudaMemset(g->fallback, 0, 4);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();       // the fills above are not ordered with the frame's (non-blocking) stream
     if (e != cudaSuccess) { giFree(g); return rsFail(RSTR_ERR_CUDA, std::string("rstr_gi_create: ") + cudaGetErrorString(e)); }
+    if (const char* env = getenv("RSTR_GI_PIPELINE")) {                               // A/B switch for measurements; rstr_gi_set_pipeline overrides
+        if (!strcmp(env, "staged")) g->pipeline = RSTR_GI_PIPELINE_STAGED;
+        else if (!strcmp(env, "fused")) g->pipeline = RSTR_GI_PIPELINE_FUSED;
+    }
     *out = g;
     return RSTR_OK;
 }
@@ -70,11 +85,34 @@ int rstr_gi_set_bounce_walk(RstrGI* g, int traversal) {
     return RSTR_OK;
 }
 
+int rstr_gi_set_pipeline(RstrGI* g, int pipeline) {
+    if (!g || (pipeline != RSTR_GI_PIPELINE_FUSED && pipeline != RSTR_GI_PIPELINE_STAGED)) return rsFail(RSTR_ERR_ARG, "rstr_gi_set_pipeline: bad argument");
+    g->pipeline = pipeline;
+    return RSTR_OK;
+}
+
+// hand-over planes and path queues of the staged pipeline: 128 + 4 + 2 x 64 bytes per pixel
+static int giEnsureStaged(RstrGI* g) {
+    if (g->pix) return RSTR_OK;
+    const size_t n = (size_t)g->W * g->H;
+    cudaError_t e = cudaMalloc(&g->pix, n * 8 * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&g->pixStatus, n * sizeof(int));
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaMalloc(&g->pathQ[i], n * 4 * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&g->pathCount, (RS_GI_MAX_DEPTH + 2) * sizeof(unsigned int));
+    if (e != cudaSuccess) {
+        void* all[] = {g->pix, g->pixStatus, g->pathQ[0], g->pathQ[1], g->pathCount};
+        for (void* p : all) cudaFree(p);
+        g->pix = nullptr; g->pixStatus = nullptr; g->pathQ[0] = g->pathQ[1] = nullptr; g->pathCount = nullptr;
+        return rsFail(RSTR_ERR_CUDA, std::string("rstr_restir_indirect: staged buffers: ") + cudaGetErrorString(e));
+    }
+    return RSTR_OK;
+}
+
 int rstr_restir_indirect(RstrGI* g, const RstrCamera* cam, int looper, int iter, int traceDepth, int reuse, int target) {
     if (!g || !cam) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: bad argument");
     RstrFrame* f = g->f;
     if (cam->resolution[0] != f->W || cam->resolution[1] != f->H) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: camera resolution differs from the frame");
-    if (traceDepth < 0 || traceDepth > 64 || iter < 0) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: traceDepth must be 0..64 and iter >= 0");
+    if (traceDepth < 0 || traceDepth > RS_GI_MAX_DEPTH || iter < 0) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: traceDepth must be 0..64 and iter >= 0");
     if (target != RSTR_GI_TARGET_OWN && target != RSTR_GI_TARGET_RADIANCE) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: unknown target");
     { int rc = rsFlushGBuffer(f); if (rc) return rc; }
     const FrameDev d = rsToFrameDev(f, 0, f->H);
@@ -85,6 +123,12 @@ int rstr_restir_indirect(RstrGI* g, const RstrCamera* cam, int looper, int iter,
     gd.fallback = g->fallback;
     gd.maxDepth = traceDepth; gd.reuse = reuse; gd.first = g->first ? 1 : 0; gd.iter = iter;
     gd.bounceWalk = g->bounceWalk;
+    if (g->pipeline == RSTR_GI_PIPELINE_STAGED && f->sc->dev.traversal != RS_TRAVERSAL_EXACT) {   // the validation mode has one form
+        int rc = giEnsureStaged(g);
+        if (rc) return rc;
+        gd.pix = g->pix; gd.pixStatus = g->pixStatus; gd.pathQ[0] = g->pathQ[0]; gd.pathQ[1] = g->pathQ[1]; gd.pathCount = g->pathCount;
+        gd.pixStride = (size_t)g->W * g->H;
+    }
     rsCountLaunches(launchRestirIndirect(f->sc->dev, d, rsToCamDev(*cam), gd, looper, f->stream));
     g->out ^= 1;                                                                     // std::swap(devIndTemporalReservoir, devIndLastTemporalReservoir), restir.cu:463
     g->first = false;

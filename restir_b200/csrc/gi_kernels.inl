@@ -290,92 +290,106 @@ RS_D long long giFindTemporal(const FrameDev& f, size_t li) {
 }
 
 // ------------------------------------------------------------------------------------------------ the pixel
-// restir.cu:263-415 after the jittered primary ray's hit is known.  false = undecided, nothing written.
+// restir.cu:263-415 in three pieces, so that the one-kernel form (giAfterHit) and the staged form (k_gi_primary / k_gi_bounce /
+// k_gi_resolve) run the very same expressions: giHead = one iteration of the path loop up to its bounce ray (:283-318),
+// giTail = the ray and what it hits (:320-375), giWriteSample = WriteSample (:380-415).
+struct GIVertex { f3 pos, nrm, wo; Surf mat; float ior; };                           // a path vertex whose BSDF is sampled next
+struct GIRay { f3 dir; float pdf; bool delta; };                                     // the sampled bounce: makeOffsetedRay(pos, dir)
+
+// :284-286
+RS_D void giFaceForward(GIVertex& v) { if (v.mat.type != 2 && dot(v.nrm, v.wo) < 0.f) v.nrm = -v.nrm; }
+// :288-299: next-event estimation with MIS at a vertex after the first.  false: undecided shadow ray (never with EXACT)
 template <bool EXACT>
-RS_D bool giAfterHit(const DevScene& s, const FrameDev& f, const GIDev& g, int x, int y, Stack& stack, const TieStore& ts, Rng rng, f3 d, Hit h) {
-    const size_t li = planeIndex(f, x, y);
-    GISample smp = giEmptySample();
-    bool shaded = false, primDelta = false;
-    float primPdf = 1.f;
-    f3 primWo = mk3(0.f);
-    Surf primMat;
-    primMat.type = 0; primMat.baseColor = mk3(0.f); primMat.metallic = 0.f; primMat.roughness = 0.f;
-    if (h.prim >= 0) {
-        GISurf sf;
-        giSurface(s, h, sf);
-        if (sf.m.type != 4) {                                                         // :272
-            shaded = true;
-            f3 throughput = mk3(1.f);
-            f3 wo = -d;
-            f3 pos = sf.pos, nrm = sf.nrm;
-            Surf mat = sf.m;
-            float ior = sf.ior;
-            primWo = wo;
-            primMat = mat;
-            for (int depth = 1; depth <= g.maxDepth; depth++) {
-                const bool deltaBSDF = mat.type == 2;
-                if (mat.type != 2 && dot(nrm, wo) < 0.f) nrm = -nrm;                  // :284-286
-                if (!deltaBSDF && depth > 1) {                                        // :288-299: next-event estimation with MIS
-                    const float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
-                    f3 radiance = mk3(0.f), wi = mk3(0.f);
-                    bool undecided = false;
-                    const float lightPdf = giSampleDirectLight<EXACT>(s, pos, c0, c1, c2, c3, stack, radiance, wi, undecided);
-                    if (undecided) return false;
-                    if (lightPdf > 0.f) {
-                        const float bsdfPdf = giMaterialPdf(mat, nrm, wo, wi);
-                        smp.Lo = smp.Lo + throughput * giBSDF(mat, nrm, wo, wi) * radiance * satDot(nrm, wi) / lightPdf * giPowerHeuristic(lightPdf, bsdfPdf);
-                    }
-                }
-                const float r0 = rng.next(), r1 = rng.next(), r2 = rng.next();
-                GIBSample bs;
-                giMaterialSample(mat, ior, nrm, wo, r0, r1, r2, bs);
-                if (bs.kind == GI_BS_INVALID) break;                                  // :304-309
-                else if (bs.pdf < 1e-8f) break;
-                const bool deltaSample = bs.kind == GI_BS_SPECULAR;
-                if (depth > 1) throughput = throughput * (bs.bsdf / bs.pdf * (deltaSample ? 1.f : absDot(nrm, bs.dir)));
-                else { primPdf = bs.pdf; primDelta = deltaSample; smp.xv = pos; smp.nv = nrm; }
-                const f3 ro = pos + bs.dir * 1e-5f, rd = bs.dir;                      // makeOffsetedRay, intersections.h:12
-                const f3 curPos = pos;
-                Hit hh;
-                if (!giClosest<EXACT>(s, g, ro, rd, stack, ts, hh)) return false;
-                wo = -rd;
-                if (hh.prim < 0) {                                                    // :332-343
-                    if (s.envTex >= 0) {
-                        const f3 env = envLookup(s, rd);
-                        const f3 radiance = env * throughput;
-                        const int4 info = __ldg(s.texInfo + s.envTex);
-                        const float envP = luminance(env) * s.sumLightPowerInv * (float)info.x * (float)info.y * .5f;   // environmentMapPdf, scene.h:358-362
-                        const float weight = deltaSample ? 1.f : giPowerHeuristic(bs.pdf, envP);
-                        smp.Lo = smp.Lo + radiance * weight;
-                    }
-                    break;
-                }
-                giSurface(s, hh, sf);
-                pos = sf.pos; nrm = sf.nrm; mat = sf.m; ior = sf.ior;
-                if (mat.type == 4) {                                                  // :346-371
-                    if (dot(nrm, rd) < 0.f) break;                                    // SCENE_LIGHT_SINGLE_SIDED
-                    const f3 radiance = mat.baseColor;
-                    float weight = 1.f;
-                    if (!(deltaSample || depth == 1)) {
-                        const float area = triangleArea(sf.v0, sf.v1, sf.v2);         // getPrimitiveArea, scene.h:121-126
-                        const f3 yx = curPos - pos;                                   // pdfAreaToSolidAngle, mathUtil.h:182-185
-                        const float lp = luminance(radiance) * s.sumLightPowerInv * area * dot(yx, yx) / absDot(nrm, normalize(yx));
-                        weight = giPowerHeuristic(bs.pdf, lp);
-                    }
-                    smp.Lo = smp.Lo + radiance * throughput * weight;
-                    if (depth == 1) { smp.xs = pos; smp.ns = nrm; }
-                    break;
-                }
-                if (depth == 1) { smp.xs = pos; smp.ns = nrm; }
-            }
-        }
+RS_D bool giNextEvent(const DevScene& s, const GIVertex& v, f3 throughput, f3& Lo, Rng& rng, Stack& stack) {
+    const float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
+    f3 radiance = mk3(0.f), wi = mk3(0.f);
+    bool undecided = false;
+    const float lightPdf = giSampleDirectLight<EXACT>(s, v.pos, c0, c1, c2, c3, stack, radiance, wi, undecided);
+    if (undecided) return false;
+    if (lightPdf > 0.f) {
+        const float bsdfPdf = giMaterialPdf(v.mat, v.nrm, v.wo, wi);
+        Lo = Lo + throughput * giBSDF(v.mat, v.nrm, v.wo, wi) * radiance * satDot(v.nrm, wi) / lightPdf * giPowerHeuristic(lightPdf, bsdfPdf);
     }
-    // WriteSample (:380-415)
+    return true;
+}
+// :301-318: the bounce direction.  true: ray sampled, false: the path ends here (the loop's break)
+RS_D bool giSampleBounce(int depth, const GIVertex& v, f3& throughput, Rng& rng, GIRay& ray) {
+    const float r0 = rng.next(), r1 = rng.next(), r2 = rng.next();
+    GIBSample bs;
+    giMaterialSample(v.mat, v.ior, v.nrm, v.wo, r0, r1, r2, bs);
+    if (bs.kind == GI_BS_INVALID) return false;                                       // :304-309
+    else if (bs.pdf < 1e-8f) return false;
+    ray.delta = bs.kind == GI_BS_SPECULAR;
+    if (depth > 1) throughput = throughput * (bs.bsdf / bs.pdf * (ray.delta ? 1.f : absDot(v.nrm, bs.dir)));
+    ray.dir = bs.dir; ray.pdf = bs.pdf;                                               // depth 1: primSamplePdf / primSampleDelta / xv / nv, by the caller
+    return true;
+}
+// 1: ray sampled, 0: the path ends here, -1: undecided
+template <bool EXACT>
+RS_D int giHead(const DevScene& s, int depth, GIVertex& v, f3& throughput, f3& Lo, Rng& rng, Stack& stack, GIRay& ray) {
+    giFaceForward(v);
+    if (v.mat.type != 2 && depth > 1 && !giNextEvent<EXACT>(s, v, throughput, Lo, rng, stack)) return -1;
+    return giSampleBounce(depth, v, throughput, rng, ray) ? 1 : 0;
+}
+
+// 1: the path goes on from v, 0: it ends here, -1: undecided closest hit (never with EXACT).  surface: v.pos / v.nrm are a hit the
+// sample records as xs / ns when depth == 1 (:366, :374)
+template <bool EXACT>
+RS_D int giTail(const DevScene& s, const GIDev& g, int depth, f3 curPos, const GIRay& ray, f3 throughput, f3& Lo, Stack& stack, const TieStore& ts,
+                GIVertex& v, bool& surface) {
+    surface = false;
+    const f3 ro = curPos + ray.dir * 1e-5f, rd = ray.dir;                             // makeOffsetedRay, intersections.h:12
+    Hit hh;
+    if (!giClosest<EXACT>(s, g, ro, rd, stack, ts, hh)) return -1;
+    v.wo = -rd;
+    if (hh.prim < 0) {                                                                // :332-343
+        if (s.envTex >= 0) {
+            const f3 env = envLookup(s, rd);
+            const f3 radiance = env * throughput;
+            const int4 info = __ldg(s.texInfo + s.envTex);
+            const float envP = luminance(env) * s.sumLightPowerInv * (float)info.x * (float)info.y * .5f;   // environmentMapPdf, scene.h:358-362
+            const float weight = ray.delta ? 1.f : giPowerHeuristic(ray.pdf, envP);
+            Lo = Lo + radiance * weight;
+        }
+        return 0;
+    }
+    GISurf sf;
+    giSurface(s, hh, sf);
+    v.pos = sf.pos; v.nrm = sf.nrm; v.mat = sf.m; v.ior = sf.ior;
+    if (v.mat.type == 4) {                                                            // :346-371
+        if (dot(v.nrm, rd) < 0.f) return 0;                                           // SCENE_LIGHT_SINGLE_SIDED
+        const f3 radiance = v.mat.baseColor;
+        float weight = 1.f;
+        if (!(ray.delta || depth == 1)) {
+            const float area = triangleArea(sf.v0, sf.v1, sf.v2);                     // getPrimitiveArea, scene.h:121-126
+            const f3 yx = curPos - v.pos;                                             // pdfAreaToSolidAngle, mathUtil.h:182-185
+            const float lp = luminance(radiance) * s.sumLightPowerInv * area * dot(yx, yx) / absDot(v.nrm, normalize(yx));
+            weight = giPowerHeuristic(ray.pdf, lp);
+        }
+        Lo = Lo + radiance * throughput * weight;
+        surface = true;
+        return 0;
+    }
+    surface = true;
+    return 1;
+}
+
+// what WriteSample needs of the jittered primary hit (the reference's primMaterial / primWo / primSamplePdf / primSampleDelta)
+struct GIPrim { Surf mat; f3 wo; float pdf; bool delta, shaded; };
+RS_D GIPrim giEmptyPrim() {
+    GIPrim p;
+    p.mat.type = 0; p.mat.baseColor = mk3(0.f); p.mat.metallic = 0.f; p.mat.roughness = 0.f;
+    p.wo = mk3(0.f); p.pdf = 1.f; p.delta = false; p.shaded = false;
+    return p;
+}
+
+// WriteSample (:380-415)
+RS_D void giWriteSample(const FrameDev& f, const GIDev& g, size_t li, const GISample& smp, const GIPrim& prim, Rng rng) {
     GIResv R;
     R.s = giEmptySample(); R.M = 0; R.w = 0.f;
     float sampleWeight = 0.f;
     if (!(luminance(smp.Lo) < 1e-8f)) {                                               // !IndirectLiSample::invalid()
-        sampleWeight = luminance(smp.Lo / primPdf);
+        sampleWeight = luminance(smp.Lo / prim.pdf);
         if (isnan(sampleWeight) || sampleWeight < 0.f) sampleWeight = 0.f;
     }
     {
@@ -397,10 +411,10 @@ RS_D bool giAfterHit(const DevScene& s, const FrameDev& f, const GIDev& g, int x
     f3 indirect = mk3(0.f);
     const GISample sample = R.s;
     if (R.M > 20) { R.w *= 20.f / R.M; R.M = 20; }                                    // clamp<20>, restir.h:88-93
-    if (shaded && !giResvInvalid(R)) {
+    if (prim.shaded && !giResvInvalid(R)) {
         const f3 primWi = normalize(sample.xs - sample.xv);
         indirect = R.s.Lo / luminance(R.s.Lo) * R.w / (float)R.M;
-        indirect = indirect * (giBSDF(primMat, sample.nv, primWo, primWi) * (primDelta ? 1.f : satDot(sample.nv, primWi)));
+        indirect = indirect * (giBSDF(prim.mat, sample.nv, prim.wo, primWi) * (prim.delta ? 1.f : satDot(sample.nv, primWi)));
     }
     if (hasNanOrInf(indirect)) indirect = mk3(0.f);
     giStore(g.resvOut, g.nszOut, li, R);
@@ -408,7 +422,172 @@ RS_D bool giAfterHit(const DevScene& s, const FrameDev& f, const GIDev& g, int x
     const f3 prev = mk3(out[0], out[1], out[2]);
     const f3 v = (prev * (float)g.iter + indirect) / (float)(g.iter + 1);             // :415
     out[0] = v.x; out[1] = v.y; out[2] = v.z;
+}
+
+// the whole pixel after the jittered primary ray's hit is known.  false = undecided, nothing written.
+template <bool EXACT>
+RS_D bool giAfterHit(const DevScene& s, const FrameDev& f, const GIDev& g, int x, int y, Stack& stack, const TieStore& ts, Rng rng, f3 d, Hit h) {
+    const size_t li = planeIndex(f, x, y);
+    GISample smp = giEmptySample();
+    GIPrim prim = giEmptyPrim();
+    if (h.prim >= 0) {
+        GISurf sf;
+        giSurface(s, h, sf);
+        if (sf.m.type != 4) {                                                         // :272
+            prim.shaded = true;
+            f3 throughput = mk3(1.f);
+            GIVertex v;
+            v.pos = sf.pos; v.nrm = sf.nrm; v.wo = -d; v.mat = sf.m; v.ior = sf.ior;
+            prim.wo = v.wo;
+            prim.mat = v.mat;
+            for (int depth = 1; depth <= g.maxDepth; depth++) {
+                GIRay ray;
+                int r = giHead<EXACT>(s, depth, v, throughput, smp.Lo, rng, stack, ray);
+                if (r < 0) return false;
+                if (r == 0) break;
+                if (depth == 1) { prim.pdf = ray.pdf; prim.delta = ray.delta; smp.xv = v.pos; smp.nv = v.nrm; }
+                bool surface;
+                r = giTail<EXACT>(s, g, depth, v.pos, ray, throughput, smp.Lo, stack, ts, v, surface);
+                if (r < 0) return false;
+                if (depth == 1 && surface) { smp.xs = v.pos; smp.ns = v.nrm; }
+                if (r == 0) break;
+            }
+        }
+    }
+    giWriteSample(f, g, li, smp, prim, rng);
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------ the staged form
+// The same pixel as a wavefront: paths that are still alive after a bounce are appended to a queue and the next launch runs one thread
+// per live path, so the lanes of finished paths (most bounces off the ground leave the scene) do not idle through the walks of the
+// others.  Every pixel draws its random numbers in the order of the one-kernel form, so the two forms are bit-identical.
+//   k_gi_primary   packet walk of the jittered primary rays, the surface, the first bounce direction (no ray traced per lane)
+//   k_gi_bounce    once per depth: the bounce ray (per-lane walk), what it hits, next-event estimation and the next direction there
+//   k_gi_resolve   WriteSample for every pixel, coherent: reservoir update, temporal merge, shading, running mean
+// Between the stages, per pixel (g.pix, 8 planes of float4): 0 {primWo, primSamplePdf} 1 {baseColor, metallic} 2 {roughness, type |
+// delta << 8} 3 {xv, nv.x} 4 {nv.y, nv.z} 5 {Lo, RNG state} of the finished path 6 {xs, ns.x} 7 {ns.y, ns.z}; per live path 64 B:
+// {pos, pixel} {dir, RNG state} {throughput, pdf} {Lo, delta}.
+struct GIPathRec { float4 a, b, c, d; };
+RS_D GIPathRec giPackPath(int pixel, f3 pos, const GIRay& ray, f3 throughput, f3 Lo, Rng rng) {
+    GIPathRec r;
+    r.a = make_float4(pos.x, pos.y, pos.z, __int_as_float(pixel));
+    r.b = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, __uint_as_float(rng.x));
+    r.c = make_float4(throughput.x, throughput.y, throughput.z, ray.pdf);
+    r.d = make_float4(Lo.x, Lo.y, Lo.z, __int_as_float(ray.delta ? 1 : 0));
+    return r;
+}
+RS_D void giPathFinished(const GIDev& g, size_t li, f3 Lo, Rng rng) { g.pix[5 * g.pixStride + li] = make_float4(Lo.x, Lo.y, Lo.z, __uint_as_float(rng.x)); }
+
+// after the jittered primary ray's hit is known.  true: a path leaves for bounce 1 (out)
+RS_D bool giStagePrimary(const DevScene& s, const FrameDev& f, const GIDev& g, int x, int y, Rng rng, f3 d, const Hit& h, GIPathRec& out) {
+    const size_t li = planeIndex(f, x, y), n = g.pixStride;
+    bool shaded = false, live = false;
+    if (h.prim >= 0) {
+        GISurf sf;
+        giSurface(s, h, sf);
+        if (sf.m.type != 4) {                                                         // :272
+            shaded = true;
+            GIVertex v;
+            v.pos = sf.pos; v.nrm = sf.nrm; v.wo = -d; v.mat = sf.m; v.ior = sf.ior;
+            const f3 primWo = v.wo;
+            const Surf primMat = v.mat;
+            float primPdf = 1.f;
+            bool primDelta = false;
+            f3 xv = mk3(0.f), nv = mk3(0.f);
+            if (g.maxDepth >= 1) {
+                f3 throughput = mk3(1.f);
+                GIRay ray;
+                giFaceForward(v);
+                if (giSampleBounce(1, v, throughput, rng, ray)) {
+                    live = true;
+                    primPdf = ray.pdf; primDelta = ray.delta; xv = v.pos; nv = v.nrm;
+                    out = giPackPath(y * f.W + x, v.pos, ray, throughput, mk3(0.f), rng);
+                }
+            }
+            float4* px = g.pix + li;
+            px[0] = make_float4(primWo.x, primWo.y, primWo.z, primPdf);
+            px[n] = make_float4(primMat.baseColor.x, primMat.baseColor.y, primMat.baseColor.z, primMat.metallic);
+            px[2 * n] = make_float4(primMat.roughness, __int_as_float(primMat.type | (primDelta ? 256 : 0)), 0.f, 0.f);
+            px[3 * n] = make_float4(xv.x, xv.y, xv.z, nv.x);
+            px[4 * n] = make_float4(nv.y, nv.z, 0.f, 0.f);
+            px[6 * n] = make_float4(0.f, 0.f, 0.f, 0.f);                                // xs / ns unless bounce 1 finds a surface
+            px[7 * n] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    g.pixStatus[li] = shaded ? 1 : 0;
+    if (!live) giPathFinished(g, li, mk3(0.f), rng);
+    return live;
+}
+
+// bounce `depth` of one live path.  1: the path goes on (out), 0: it ended, -1: undecided ray (pixel marked; the caller queues it)
+RS_D int giStageBounce(const DevScene& s, const FrameDev& f, const GIDev& g, int depth, const GIPathRec& in, Stack& stack, const TieStore& ts, GIPathRec& out,
+                       int& x, int& y) {
+    const int pixel = __float_as_int(in.a.w);
+    x = pixel % f.W; y = pixel / f.W;
+    const size_t li = planeIndex(f, x, y), n = g.pixStride;
+    const f3 curPos = mk3(in.a.x, in.a.y, in.a.z);
+    GIRay ray;
+    ray.dir = mk3(in.b.x, in.b.y, in.b.z); ray.pdf = in.c.w; ray.delta = __float_as_int(in.d.w) != 0;
+    Rng rng;
+    rng.x = __float_as_uint(in.b.w);
+    f3 throughput = mk3(in.c.x, in.c.y, in.c.z), Lo = mk3(in.d.x, in.d.y, in.d.z);
+    GIVertex v;
+    bool surface;
+    int r = giTail<false>(s, g, depth, curPos, ray, throughput, Lo, stack, ts, v, surface);
+    if (r < 0) { g.pixStatus[li] = 2; return -1; }
+    if (depth == 1 && surface) {                                                      // :366, :374
+        g.pix[6 * n + li] = make_float4(v.pos.x, v.pos.y, v.pos.z, v.nrm.x);
+        g.pix[7 * n + li] = make_float4(v.nrm.y, v.nrm.z, 0.f, 0.f);
+    }
+    if (r == 1 && depth < g.maxDepth) {
+        r = giHead<false>(s, depth + 1, v, throughput, Lo, rng, stack, ray);
+        if (r < 0) { g.pixStatus[li] = 2; return -1; }
+        if (r == 1) {
+            out = giPackPath(pixel, v.pos, ray, throughput, Lo, rng);
+            return 1;
+        }
+    }
+    giPathFinished(g, li, Lo, rng);
+    return 0;
+}
+
+RS_D void giStageResolve(const FrameDev& f, const GIDev& g, int x, int y) {
+    const size_t li = planeIndex(f, x, y), n = g.pixStride;
+    const int status = g.pixStatus[li];
+    if (status == 2) return;                                                          // k_restir_indirect_fix writes this pixel
+    const float4* px = g.pix + li;
+    GISample smp = giEmptySample();
+    GIPrim prim = giEmptyPrim();
+    const float4 t = px[5 * n];
+    smp.Lo = mk3(t.x, t.y, t.z);
+    Rng rng;
+    rng.x = __float_as_uint(t.w);
+    if (status == 1) {
+        const float4 p0 = px[0], p1 = px[n], p2 = px[2 * n], p3 = px[3 * n], p4 = px[4 * n], p6 = px[6 * n], p7 = px[7 * n];
+        const int td = __float_as_int(p2.y);
+        prim.shaded = true;
+        prim.wo = mk3(p0.x, p0.y, p0.z); prim.pdf = p0.w;
+        prim.mat.baseColor = mk3(p1.x, p1.y, p1.z); prim.mat.metallic = p1.w; prim.mat.roughness = p2.x;
+        prim.mat.type = td & 255; prim.delta = (td & 256) != 0;
+        smp.xv = mk3(p3.x, p3.y, p3.z); smp.nv = mk3(p3.w, p4.x, p4.y);
+        smp.xs = mk3(p6.x, p6.y, p6.z); smp.ns = mk3(p6.w, p7.x, p7.y);
+    }
+    giWriteSample(f, g, li, smp, prim, rng);
+}
+
+// warp-aggregated append of one 64-byte path record per wanting lane (all 32 lanes call)
+RS_D void giAppendPath(float4* q, unsigned int* count, bool want, const GIPathRec& r) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) {
+        float4* o = q + 4 * (size_t)(base + __popc(m & ((1u << lane) - 1u)));
+        o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
+    }
 }
 
 RS_D void giPixelExact(const DevScene& s, const FrameDev& f, const CamDev& cam, const GIDev& g, int looper, int x, int y, Stack& stack) {
@@ -440,6 +619,54 @@ __global__ void __launch_bounds__(RS_BLOCK) k_restir_indirect(const __grid_const
         Hit h;
         if (!prayResolve(s, oc, d, a, pk_ta, h) || !giAfterHit<false>(s, f, g, x, y, stack, pk_ta, rng, d, h)) enqueuePixel(f, x, y);
     }
+}
+__global__ void __launch_bounds__(RS_BLOCK) k_gi_primary(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                         const __grid_constant__ CamDev cam, const __grid_constant__ GIDev g, int looper) {
+    RS_DECLARE_PACKET(pk, 1);
+    int x, y;
+    const bool active = pixelOf(f, x, y);
+    Rng rng;
+    rng.x = 1;
+    f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
+    if (active) jitteredRay(f, cam, looper, x, y, rng, o, d);
+    const f3 oc = cameraOrigin(cam);
+    PRay a = prayBegin(oc, d, active, pk_ta);
+    packetWalk<false>(s, oc, a, a, pk_ta, pk_ta, pk_wst);
+    bool live = false;
+    GIPathRec rec;
+    rec.a = rec.b = rec.c = rec.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        Hit h;
+        if (prayResolve(s, oc, d, a, pk_ta, h)) live = giStagePrimary(s, f, g, x, y, rng, d, h, rec);
+        else { g.pixStatus[planeIndex(f, x, y)] = 2; enqueuePixel(f, x, y); }
+    }
+    giAppendPath(g.pathQ[0], g.pathCount + 1, live, rec);
+}
+__global__ void __launch_bounds__(RS_BLOCK) k_gi_bounce(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                        const __grid_constant__ GIDev g, int depth) {
+    RS_DECLARE_STACK(stack);
+    RS_DECLARE_PACKET(pk, 1);
+    (void)pk_tb; (void)pk_wst;
+    const unsigned n = g.pathCount[depth];
+    if (blockIdx.x * RS_BLOCK >= n) return;                                           // whole block out of work (uniform)
+    const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
+    bool live = false;
+    GIPathRec rec;
+    rec.a = rec.b = rec.c = rec.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+        const float4* q = g.pathQ[(depth - 1) & 1] + 4 * (size_t)i;
+        GIPathRec in;
+        in.a = q[0]; in.b = q[1]; in.c = q[2]; in.d = q[3];
+        int x, y;
+        const int r = giStageBounce(s, f, g, depth, in, stack, pk_ta, rec, x, y);
+        if (r < 0) enqueuePixel(f, x, y);
+        live = r == 1;
+    }
+    giAppendPath(g.pathQ[depth & 1], g.pathCount + depth + 1, live, rec);
+}
+__global__ void __launch_bounds__(RS_BLOCK) k_gi_resolve(const __grid_constant__ FrameDev f, const __grid_constant__ GIDev g) {
+    int x, y;
+    if (pixelOf(f, x, y)) giStageResolve(f, g, x, y);
 }
 __global__ void __launch_bounds__(RS_BLOCK) k_restir_indirect_exact(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                                     const __grid_constant__ CamDev cam, const __grid_constant__ GIDev g, int looper) {
@@ -475,6 +702,15 @@ __global__ void k_export_gi(const float4* __restrict__ rec, const float* __restr
 int launchRestirIndirect(const DevScene& s, const FrameDev& f, const CamDev& cam, const GIDev& g, int looper, cudaStream_t st) {
     if (s.traversal == RS_TRAVERSAL_EXACT) { k_restir_indirect_exact<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, g, looper); return 1; }
     cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
+    if (g.pix) {                                                                      // staged: one launch per bounce over the live paths
+        cudaMemsetAsync(g.pathCount, 0, (size_t)(g.maxDepth + 2) * sizeof(unsigned int), st);
+        k_gi_primary<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
+        const unsigned blocks = (unsigned)((g.pixStride + RS_BLOCK - 1) / RS_BLOCK);   // the path count lives on the device: blocks past it return at once
+        for (int depth = 1; depth <= g.maxDepth; depth++) k_gi_bounce<<<blocks, RS_BLOCK, 0, st>>>(s, f, g, depth);
+        k_gi_resolve<<<pixelGrid(f), RS_BLOCK, 0, st>>>(f, g);
+        k_restir_indirect_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
+        return 3 + g.maxDepth;
+    }
     k_restir_indirect<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
     k_restir_indirect_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
     return 2;

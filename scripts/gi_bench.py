@@ -16,15 +16,22 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def run(rb, name, steps, warmup, depth, exact, bounce_exact):
+_SCENES = {}
+
+
+def run(rb, name, steps, warmup, depth, exact, bounce_exact, staged=False):
     desc, spec, res, _, _ = bench.WORKLOADS[name]
     t0 = time.time()
-    sd = bench.make_scene(spec, res)
-    sc = rb.Scene.from_arrays(sd)
+    if name not in _SCENES:                      # one scene per workload for all modes (GPU seconds are scarce)
+        sd = bench.make_scene(spec, res)
+        _SCENES.clear()
+        _SCENES[name] = (sd, rb.Scene.from_arrays(sd))
+    sd, sc = _SCENES[name]
     sc.set_traversal(exact)
     fr = sc.frame(*res)
     gi = rb.ReSTIRIndirect(fr)
     gi.set_bounce_walk(bounce_exact)
+    gi.set_pipeline(staged)
     base = rb.Camera.from_scene(sd)
     setup_s = time.time() - t0
     k = 0
@@ -44,12 +51,12 @@ def run(rb, name, steps, warmup, depth, exact, bounce_exact):
     img = gi.read()
     out = {"workload": name, "resolution": list(res), "triangles": sc.info.numTris, "emissive_triangles": sc.info.numLights, "trace_depth": depth,
            "traversal": "reference-order walk" if exact else ("packet primary + reference-order bounces" if bounce_exact else "traced tree"),
+           "pipeline": "one kernel" if exact or not staged else "staged (primary / bounce per depth / resolve)",
            "steps": steps, "warmup": warmup, "gi_ms_per_frame": total / steps, "mpixel_per_s": res[0] * res[1] / (total / steps * 1e-3) / 1e6,
            "fixup_pixels_per_frame": gi.fallback_pixels() / (warmup + steps), "mean_indirect": float(img.mean()), "lit_fraction": float((img.sum(1) > 0).mean()),
            "setup_s": setup_s, "build_id": rb.api.build_id()}
     gi.close()
     fr.close()
-    sc.close()
     return out
 
 
@@ -59,7 +66,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--depth", type=int, default=3)
-    ap.add_argument("--modes", nargs="+", default=["traced", "exact"], choices=["traced", "mixed", "exact"])
+    ap.add_argument("--modes", nargs="+", default=["traced", "exact"], choices=["traced", "staged", "mixed", "exact"])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "gi_bench.jsonl"))
     args = ap.parse_args()
     import restir_b200 as rb
@@ -69,7 +76,7 @@ def main():
     with open(args.out, "a") as f:
         for name in args.workloads:
             for mode in args.modes:
-                r = run(rb, name, args.steps if mode != "exact" else max(3, args.steps // 4), args.warmup, args.depth, mode == "exact", mode == "mixed")
+                r = run(rb, name, args.steps if mode != "exact" else max(3, args.steps // 4), args.warmup, args.depth, mode == "exact", mode == "mixed", mode == "staged")
                 line = json.dumps(r)
                 print(line, flush=True)
                 f.write(line + "\n")

@@ -135,7 +135,7 @@ void emu_gbuffer_update(void* fv, const RstrCamera* cam) {
 }
 void emu_gi_reset(void* fv) { ((EmuFrame*)fv)->first = true; }
 
-// rstr_restir_indirect.  tracedTree = 0: k_restir_indirect_exact's body per pixel.  tracedTree = 1: the primary hit from the reference-order
+// rstr_restir_indirect.  tracedTree = 2: the staged pipeline (below).  tracedTree = 0: k_restir_indirect_exact's body per pixel.  tracedTree = 1: the primary hit from the reference-order
 // walk (standing in for the packet walk), then giAfterHit<false>: bounce rays through traceClosestFast, shadow rays through
 // traceOccludedFast; an undecided pixel is recomputed like k_restir_indirect_fix does.
 void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, int traceDepth, int reuse, int tracedTree) {
@@ -149,6 +149,61 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
     g.indirect = f->indirect.data(); g.fallback = nullptr;
     g.maxDepth = traceDepth; g.reuse = reuse; g.first = f->first ? 1 : 0; g.iter = iter; g.bounceWalk = RS_TRAVERSAL_FAST;
     unsigned long long undecided = 0;
+    if (tracedTree == 2) {
+        // the staged form: giStagePrimary per pixel (primary hit from the reference-order walk, as above), giStageBounce per live path and depth
+        // through the queues, giStageResolve per pixel, marked pixels like k_restir_indirect_fix.  One-lane "warps": giAppendPath appends one record.
+        const size_t n = (size_t)f->W * f->H;
+        std::vector<float4> pix(8 * n), q0(4 * n), q1(4 * n);
+        std::vector<int> status(n, 0);
+        std::vector<unsigned int> counts(traceDepth + 2, 0u);
+        g.pix = pix.data(); g.pixStatus = status.data(); g.pathQ[0] = q0.data(); g.pathQ[1] = q1.data(); g.pathCount = counts.data(); g.pixStride = n;
+#pragma omp parallel for schedule(dynamic, 4)
+        for (int y = 0; y < f->H; y++)
+            for (int x = 0; x < f->W; x++) {
+                threadIdx.x = 0;
+                RS_DECLARE_STACK(stack);
+                Rng rng;
+                f3 o, dir;
+                jitteredRay(d, c, looper, x, y, rng, o, dir);
+                const RayT ray = makeRayT(o, dir);
+                Hit h;
+                traceClosestExact(s, ray, h, stack);
+                GIPathRec rec;
+                const bool live = giStagePrimary(s, d, g, x, y, rng, dir, h, rec);
+                giAppendPath(g.pathQ[0], g.pathCount + 1, live, rec);
+            }
+        for (int depth = 1; depth <= traceDepth; depth++) {
+            const long long np = counts[depth];
+#pragma omp parallel for schedule(dynamic, 16)
+            for (long long i = 0; i < np; i++) {
+                threadIdx.x = 0;
+                RS_DECLARE_STACK(stack);
+                RS_DECLARE_PACKET(pk, 1);
+                (void)pk_tb; (void)pk_wst;
+                const float4* q = g.pathQ[(depth - 1) & 1] + 4 * (size_t)i;
+                GIPathRec in, rec;
+                in.a = q[0]; in.b = q[1]; in.c = q[2]; in.d = q[3];
+                int x, y;
+                const int r = giStageBounce(s, d, g, depth, in, stack, pk_ta, rec, x, y);
+                giAppendPath(g.pathQ[depth & 1], g.pathCount + depth + 1, r == 1, rec);
+            }
+        }
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : undecided)
+        for (int y = 0; y < f->H; y++)
+            for (int x = 0; x < f->W; x++) {
+                threadIdx.x = 0;
+                giStageResolve(d, g, x, y);
+                if (status[(size_t)y * f->W + x] == 2) {
+                    RS_DECLARE_STACK(stack);
+                    undecided++;
+                    giPixelExact(s, d, c, g, looper, x, y, stack);
+                }
+            }
+        f->undecided += undecided;
+        f->out ^= 1;
+        f->first = false;
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : undecided)
     for (int y = 0; y < f->H; y++)
         for (int x = 0; x < f->W; x++) {

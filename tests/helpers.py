@@ -152,7 +152,7 @@ def run_oracle_gi(orc, sd, frames, max_depth=3, reuse=1, accumulate=False, orbit
     return out
 
 
-def run_gpu_gi(rb, sd, frames, max_depth=3, reuse=1, accumulate=False, orbit=True, exact=False, bounce_exact=False, scene=None):
+def run_gpu_gi(rb, sd, frames, max_depth=3, reuse=1, accumulate=False, orbit=True, exact=False, bounce_exact=False, scene=None, staged=None):
     """The same loop through the C ABI (rstr_gi_*); reservoirs come back in the reference's 68-byte layout and are returned as
     (P, 17) float32 with numSamples converted to float, like the oracle's export.  Also returns the number of fix-up pixels."""
     W, H = sd.resolution
@@ -161,6 +161,8 @@ def run_gpu_gi(rb, sd, frames, max_depth=3, reuse=1, accumulate=False, orbit=Tru
     fr = sc.frame(W, H)
     gi = rb.ReSTIRIndirect(fr)
     gi.set_bounce_walk(bounce_exact)
+    if staged is not None:
+        gi.set_pipeline(staged)
     base = rb.Camera.from_scene(sd)
     out = []
     for f in range(frames):

@@ -50,11 +50,23 @@ def test_gi_device_code_traced_tree_matches_oracle(emu, port_oracle, name):
     want = helpers.run_oracle_gi(port_oracle, sd, 4, 5, 1, accumulate=True)
     exact, _ = emu.run_gi(sd, 4, 5, 1, accumulate=True)
     traced, undecided = emu.run_gi(sd, 4, 5, 1, accumulate=True, traced_tree=True)
+    staged, undecided_staged = emu.run_gi(sd, 4, 5, 1, accumulate=True, staged=True)
     helpers.assert_frames_equal(exact, want, "device code, reference-order walk, vs oracle")
     helpers.assert_frames_equal(traced, want, "device code, traced tree, vs oracle")
+    helpers.assert_frames_equal(staged, want, "device code, staged pipeline (k_gi_primary / k_gi_bounce / k_gi_resolve bodies), vs oracle")
     if name == "gen20k":
         assert undecided > 0            # the fix-up path was exercised
+        assert undecided_staged == undecided
     assert (want[-1]["indirect"].sum(1) > 0).mean() > 0.2
+
+
+@pytest.mark.parametrize("depth,reuse", [(0, 1), (1, 0), (2, 1)])
+def test_gi_staged_device_code_shallow_depths(emu, port_oracle, depth, reuse):
+    """The staged bodies at depth 0 (no path leaves k_gi_primary), 1 (paths end in their first bounce) and 2, with and without history."""
+    sd = dataclasses.replace(helpers.gi_scenes()["cornell_metal"], resolution=(96, 72))
+    want = helpers.run_oracle_gi(port_oracle, sd, 3, depth, reuse, accumulate=True)
+    got, _ = emu.run_gi(sd, 3, depth, reuse, accumulate=True, staged=True)
+    helpers.assert_frames_equal(got, want, "staged device code, depth %d" % depth)
 
 
 def test_gbuffer_device_code_matches_oracle(emu, port_oracle):
