@@ -116,9 +116,9 @@ struct GIDev {
     int iter;
     int bounceWalk;            // RS_TRAVERSAL_*: which tree the bounce rays walk in the traced mode (same hits either way)
     // staged form (k_gi_primary / k_gi_bounce / k_gi_resolve); null in the one-kernel form
-    float4* pix;               // [8][pixStride] what the stages hand on per pixel: primary surface, xv / nv, xs / ns, final Lo + RNG state
+    float4* pix;               // [7][pixStride] what the stages hand on per pixel: primary surface, xv / nv, xs / ns, final Lo + RNG state
     int* pixStatus;            // 0: the jittered ray left the scene or hit an emitter, 1: shaded, 2: undecided ray (fix-up queue)
-    float4* pathQ[2];          // live paths between two bounces, 64 B each, ping-pong
+    float4* pathQ[2];          // live paths between two bounces, 96 B each, ping-pong
     unsigned int* pathCount;   // [d]: paths entering bounce d (1-based); zeroed per frame
     size_t pixStride;          // pixels of the frame
 };

@@ -91,13 +91,13 @@ int rstr_gi_set_pipeline(RstrGI* g, int pipeline) {
     return RSTR_OK;
 }
 
-// hand-over planes and path queues of the staged pipeline: 128 + 4 + 2 x 64 bytes per pixel
+// hand-over planes and path queues of the staged pipeline: 112 + 4 + 2 x 96 bytes per pixel
 static int giEnsureStaged(RstrGI* g) {
     if (g->pix) return RSTR_OK;
     const size_t n = (size_t)g->W * g->H;
-    cudaError_t e = cudaMalloc(&g->pix, n * 8 * sizeof(float4));
+    cudaError_t e = cudaMalloc(&g->pix, n * 7 * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&g->pixStatus, n * sizeof(int));
-    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaMalloc(&g->pathQ[i], n * 4 * sizeof(float4));
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaMalloc(&g->pathQ[i], n * 6 * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&g->pathCount, (RS_GI_MAX_DEPTH + 2) * sizeof(unsigned int));
     if (e != cudaSuccess) {
         void* all[] = {g->pix, g->pixStatus, g->pathQ[0], g->pathQ[1], g->pathCount};

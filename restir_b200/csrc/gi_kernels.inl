@@ -6,6 +6,8 @@
 //                            leaf-box / near-tie criterion, so the reported hit is the reference's), next-event shadow rays use the
 //                            any-hit walk.  A pixel with an undecided ray (more mutually near hits than the tie store holds) writes
 //                            nothing and is queued.
+//   k_gi_primary / k_gi_bounce / k_gi_resolve   the same frame as a wavefront (rstr_gi_set_pipeline): one launch per iteration of the path
+//                            loop over the compacted live paths; bit-identical to k_restir_indirect (see "the staged form" below)
 //   k_restir_indirect_fix    the queued pixels again with the reference-order walk of the reference tree
 //   k_restir_indirect_exact  every ray with the reference-order walk (RS_TRAVERSAL_EXACT: validation mode)
 //   k_export_gi              device reservoirs -> Reservoir<IndirectLiSample> (68 B: Lo xv nv xs ns, numSamples, weight; restir.h:13-27)
@@ -459,27 +461,43 @@ RS_D bool giAfterHit(const DevScene& s, const FrameDev& f, const GIDev& g, int x
 }
 
 // ------------------------------------------------------------------------------------------------ the staged form
-// The same pixel as a wavefront: paths that are still alive after a bounce are appended to a queue and the next launch runs one thread
-// per live path, so the lanes of finished paths (most bounces off the ground leave the scene) do not idle through the walks of the
-// others.  Every pixel draws its random numbers in the order of the one-kernel form, so the two forms are bit-identical.
-//   k_gi_primary   packet walk of the jittered primary rays, the surface, the first bounce direction (no ray traced per lane)
-//   k_gi_bounce    once per depth: the bounce ray (per-lane walk), what it hits, next-event estimation and the next direction there
+// The same pixel as a wavefront: the vertices of the paths that are still alive are appended to a queue and the next launch runs one
+// thread per live path, so the lanes of finished paths (most bounces off the ground leave the scene) do not idle through the walks of
+// the others.  A launch is one iteration of the path loop -- next-event estimation at the vertex, the bounce direction, the bounce ray,
+// the surface it hits -- so both walks of an iteration run with every lane of the warp alive.  Every pixel draws its random numbers in
+// the order of the one-kernel form, so the two forms are bit-identical.
+//   k_gi_primary   packet walk of the jittered primary rays, the surface at the hit (no per-lane walk)
+//   k_gi_bounce    once per depth over the live paths: giHead + giTail
 //   k_gi_resolve   WriteSample for every pixel, coherent: reservoir update, temporal merge, shading, running mean
-// Between the stages, per pixel (g.pix, 8 planes of float4): 0 {primWo, primSamplePdf} 1 {baseColor, metallic} 2 {roughness, type |
-// delta << 8} 3 {xv, nv.x} 4 {nv.y, nv.z} 5 {Lo, RNG state} of the finished path 6 {xs, ns.x} 7 {ns.y, ns.z}; per live path 64 B:
-// {pos, pixel} {dir, RNG state} {throughput, pdf} {Lo, delta}.
-struct GIPathRec { float4 a, b, c, d; };
-RS_D GIPathRec giPackPath(int pixel, f3 pos, const GIRay& ray, f3 throughput, f3 Lo, Rng rng) {
+// Between the stages, per pixel (g.pix, planes of float4): 0 {primWo, roughness} 1 {baseColor, metallic} 2 {xv, primSamplePdf}
+// 3 {nv, type | delta << 8} 4 {Lo, RNG state} of the finished path 5 {xs, ns.x} 6 {ns.y, ns.z}; per live path 96 B:
+// {pos, pixel} {nrm, RNG state} {wo, ior} {baseColor, metallic} {throughput, roughness} {Lo, type}.
+#define RS_GI_PATH_F4 6
+struct GIPathRec { float4 a, b, c, d, e, f; };
+RS_D GIPathRec giPackPath(int pixel, const GIVertex& v, f3 throughput, f3 Lo, Rng rng) {
     GIPathRec r;
-    r.a = make_float4(pos.x, pos.y, pos.z, __int_as_float(pixel));
-    r.b = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, __uint_as_float(rng.x));
-    r.c = make_float4(throughput.x, throughput.y, throughput.z, ray.pdf);
-    r.d = make_float4(Lo.x, Lo.y, Lo.z, __int_as_float(ray.delta ? 1 : 0));
+    r.a = make_float4(v.pos.x, v.pos.y, v.pos.z, __int_as_float(pixel));
+    r.b = make_float4(v.nrm.x, v.nrm.y, v.nrm.z, __uint_as_float(rng.x));
+    r.c = make_float4(v.wo.x, v.wo.y, v.wo.z, v.ior);
+    r.d = make_float4(v.mat.baseColor.x, v.mat.baseColor.y, v.mat.baseColor.z, v.mat.metallic);
+    r.e = make_float4(throughput.x, throughput.y, throughput.z, v.mat.roughness);
+    r.f = make_float4(Lo.x, Lo.y, Lo.z, __int_as_float(v.mat.type));
     return r;
 }
-RS_D void giPathFinished(const GIDev& g, size_t li, f3 Lo, Rng rng) { g.pix[5 * g.pixStride + li] = make_float4(Lo.x, Lo.y, Lo.z, __uint_as_float(rng.x)); }
+RS_D GIPathRec giEmptyPath() {
+    GIPathRec r;
+    r.a = r.b = r.c = r.d = r.e = r.f = make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+}
+RS_D GIPathRec giLoadPath(const float4* q, size_t i) {
+    const float4* p = q + RS_GI_PATH_F4 * i;
+    GIPathRec r;
+    r.a = p[0]; r.b = p[1]; r.c = p[2]; r.d = p[3]; r.e = p[4]; r.f = p[5];
+    return r;
+}
+RS_D void giPathFinished(const GIDev& g, size_t li, f3 Lo, Rng rng) { g.pix[4 * g.pixStride + li] = make_float4(Lo.x, Lo.y, Lo.z, __uint_as_float(rng.x)); }
 
-// after the jittered primary ray's hit is known.  true: a path leaves for bounce 1 (out)
+// after the jittered primary ray's hit is known.  true: the path's first vertex leaves for bounce 1 (out)
 RS_D bool giStagePrimary(const DevScene& s, const FrameDev& f, const GIDev& g, int x, int y, Rng rng, f3 d, const Hit& h, GIPathRec& out) {
     const size_t li = planeIndex(f, x, y), n = g.pixStride;
     bool shaded = false, live = false;
@@ -490,29 +508,17 @@ RS_D bool giStagePrimary(const DevScene& s, const FrameDev& f, const GIDev& g, i
             shaded = true;
             GIVertex v;
             v.pos = sf.pos; v.nrm = sf.nrm; v.wo = -d; v.mat = sf.m; v.ior = sf.ior;
-            const f3 primWo = v.wo;
-            const Surf primMat = v.mat;
-            float primPdf = 1.f;
-            bool primDelta = false;
-            f3 xv = mk3(0.f), nv = mk3(0.f);
-            if (g.maxDepth >= 1) {
-                f3 throughput = mk3(1.f);
-                GIRay ray;
-                giFaceForward(v);
-                if (giSampleBounce(1, v, throughput, rng, ray)) {
-                    live = true;
-                    primPdf = ray.pdf; primDelta = ray.delta; xv = v.pos; nv = v.nrm;
-                    out = giPackPath(y * f.W + x, v.pos, ray, throughput, mk3(0.f), rng);
-                }
-            }
             float4* px = g.pix + li;
-            px[0] = make_float4(primWo.x, primWo.y, primWo.z, primPdf);
-            px[n] = make_float4(primMat.baseColor.x, primMat.baseColor.y, primMat.baseColor.z, primMat.metallic);
-            px[2 * n] = make_float4(primMat.roughness, __int_as_float(primMat.type | (primDelta ? 256 : 0)), 0.f, 0.f);
-            px[3 * n] = make_float4(xv.x, xv.y, xv.z, nv.x);
-            px[4 * n] = make_float4(nv.y, nv.z, 0.f, 0.f);
-            px[6 * n] = make_float4(0.f, 0.f, 0.f, 0.f);                                // xs / ns unless bounce 1 finds a surface
-            px[7 * n] = make_float4(0.f, 0.f, 0.f, 0.f);
+            px[0] = make_float4(v.wo.x, v.wo.y, v.wo.z, v.mat.roughness);              // primWo, primMaterial
+            px[n] = make_float4(v.mat.baseColor.x, v.mat.baseColor.y, v.mat.baseColor.z, v.mat.metallic);
+            px[2 * n] = make_float4(0.f, 0.f, 0.f, 1.f);                                // xv, primSamplePdf: until bounce 1 samples a direction
+            px[3 * n] = make_float4(0.f, 0.f, 0.f, __int_as_float(v.mat.type));        // nv, primSampleDelta
+            px[5 * n] = make_float4(0.f, 0.f, 0.f, 0.f);                                // xs / ns: until bounce 1 finds a surface
+            px[6 * n] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g.maxDepth >= 1) {
+                live = true;
+                out = giPackPath(y * f.W + x, v, mk3(1.f), mk3(0.f), rng);
+            }
         }
     }
     g.pixStatus[li] = shaded ? 1 : 0;
@@ -520,31 +526,36 @@ RS_D bool giStagePrimary(const DevScene& s, const FrameDev& f, const GIDev& g, i
     return live;
 }
 
-// bounce `depth` of one live path.  1: the path goes on (out), 0: it ended, -1: undecided ray (pixel marked; the caller queues it)
+// iteration `depth` of the path loop for one live path.  1: the path goes on (out), 0: it ended, -1: undecided ray (pixel marked;
+// the caller queues it)
 RS_D int giStageBounce(const DevScene& s, const FrameDev& f, const GIDev& g, int depth, const GIPathRec& in, Stack& stack, const TieStore& ts, GIPathRec& out,
                        int& x, int& y) {
     const int pixel = __float_as_int(in.a.w);
     x = pixel % f.W; y = pixel / f.W;
     const size_t li = planeIndex(f, x, y), n = g.pixStride;
-    const f3 curPos = mk3(in.a.x, in.a.y, in.a.z);
-    GIRay ray;
-    ray.dir = mk3(in.b.x, in.b.y, in.b.z); ray.pdf = in.c.w; ray.delta = __float_as_int(in.d.w) != 0;
+    GIVertex v;
+    v.pos = mk3(in.a.x, in.a.y, in.a.z); v.nrm = mk3(in.b.x, in.b.y, in.b.z); v.wo = mk3(in.c.x, in.c.y, in.c.z); v.ior = in.c.w;
+    v.mat.baseColor = mk3(in.d.x, in.d.y, in.d.z); v.mat.metallic = in.d.w; v.mat.roughness = in.e.w; v.mat.type = __float_as_int(in.f.w);
     Rng rng;
     rng.x = __float_as_uint(in.b.w);
-    f3 throughput = mk3(in.c.x, in.c.y, in.c.z), Lo = mk3(in.d.x, in.d.y, in.d.z);
-    GIVertex v;
-    bool surface;
-    int r = giTail<false>(s, g, depth, curPos, ray, throughput, Lo, stack, ts, v, surface);
+    f3 throughput = mk3(in.e.x, in.e.y, in.e.z), Lo = mk3(in.f.x, in.f.y, in.f.z);
+    GIRay ray;
+    int r = giHead<false>(s, depth, v, throughput, Lo, rng, stack, ray);
     if (r < 0) { g.pixStatus[li] = 2; return -1; }
-    if (depth == 1 && surface) {                                                      // :366, :374
-        g.pix[6 * n + li] = make_float4(v.pos.x, v.pos.y, v.pos.z, v.nrm.x);
-        g.pix[7 * n + li] = make_float4(v.nrm.y, v.nrm.z, 0.f, 0.f);
-    }
-    if (r == 1 && depth < g.maxDepth) {
-        r = giHead<false>(s, depth + 1, v, throughput, Lo, rng, stack, ray);
+    if (r == 1) {
+        if (depth == 1) {                                                             // :311-316
+            g.pix[2 * n + li] = make_float4(v.pos.x, v.pos.y, v.pos.z, ray.pdf);
+            g.pix[3 * n + li] = make_float4(v.nrm.x, v.nrm.y, v.nrm.z, __int_as_float(v.mat.type | (ray.delta ? 256 : 0)));
+        }
+        bool surface;
+        r = giTail<false>(s, g, depth, v.pos, ray, throughput, Lo, stack, ts, v, surface);
         if (r < 0) { g.pixStatus[li] = 2; return -1; }
-        if (r == 1) {
-            out = giPackPath(pixel, v.pos, ray, throughput, Lo, rng);
+        if (depth == 1 && surface) {                                                  // :366, :374
+            g.pix[5 * n + li] = make_float4(v.pos.x, v.pos.y, v.pos.z, v.nrm.x);
+            g.pix[6 * n + li] = make_float4(v.nrm.y, v.nrm.z, 0.f, 0.f);
+        }
+        if (r == 1 && depth < g.maxDepth) {
+            out = giPackPath(pixel, v, throughput, Lo, rng);
             return 1;
         }
     }
@@ -559,24 +570,24 @@ RS_D void giStageResolve(const FrameDev& f, const GIDev& g, int x, int y) {
     const float4* px = g.pix + li;
     GISample smp = giEmptySample();
     GIPrim prim = giEmptyPrim();
-    const float4 t = px[5 * n];
+    const float4 t = px[4 * n];
     smp.Lo = mk3(t.x, t.y, t.z);
     Rng rng;
     rng.x = __float_as_uint(t.w);
     if (status == 1) {
-        const float4 p0 = px[0], p1 = px[n], p2 = px[2 * n], p3 = px[3 * n], p4 = px[4 * n], p6 = px[6 * n], p7 = px[7 * n];
-        const int td = __float_as_int(p2.y);
+        const float4 p0 = px[0], p1 = px[n], p2 = px[2 * n], p3 = px[3 * n], p5 = px[5 * n], p6 = px[6 * n];
+        const int td = __float_as_int(p3.w);
         prim.shaded = true;
-        prim.wo = mk3(p0.x, p0.y, p0.z); prim.pdf = p0.w;
-        prim.mat.baseColor = mk3(p1.x, p1.y, p1.z); prim.mat.metallic = p1.w; prim.mat.roughness = p2.x;
+        prim.wo = mk3(p0.x, p0.y, p0.z); prim.pdf = p2.w;
+        prim.mat.baseColor = mk3(p1.x, p1.y, p1.z); prim.mat.metallic = p1.w; prim.mat.roughness = p0.w;
         prim.mat.type = td & 255; prim.delta = (td & 256) != 0;
-        smp.xv = mk3(p3.x, p3.y, p3.z); smp.nv = mk3(p3.w, p4.x, p4.y);
-        smp.xs = mk3(p6.x, p6.y, p6.z); smp.ns = mk3(p6.w, p7.x, p7.y);
+        smp.xv = mk3(p2.x, p2.y, p2.z); smp.nv = mk3(p3.x, p3.y, p3.z);
+        smp.xs = mk3(p5.x, p5.y, p5.z); smp.ns = mk3(p5.w, p6.x, p6.y);
     }
     giWriteSample(f, g, li, smp, prim, rng);
 }
 
-// warp-aggregated append of one 64-byte path record per wanting lane (all 32 lanes call)
+// warp-aggregated append of one path record per wanting lane (all 32 lanes call)
 RS_D void giAppendPath(float4* q, unsigned int* count, bool want, const GIPathRec& r) {
     const unsigned m = __ballot_sync(0xffffffffu, want);
     if (!m) return;
@@ -585,8 +596,8 @@ RS_D void giAppendPath(float4* q, unsigned int* count, bool want, const GIPathRe
     if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (want) {
-        float4* o = q + 4 * (size_t)(base + __popc(m & ((1u << lane) - 1u)));
-        o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d;
+        float4* o = q + RS_GI_PATH_F4 * (size_t)(base + __popc(m & ((1u << lane) - 1u)));
+        o[0] = r.a; o[1] = r.b; o[2] = r.c; o[3] = r.d; o[4] = r.e; o[5] = r.f;
     }
 }
 
@@ -633,8 +644,7 @@ __global__ void __launch_bounds__(RS_BLOCK) k_gi_primary(const __grid_constant__
     PRay a = prayBegin(oc, d, active, pk_ta);
     packetWalk<false>(s, oc, a, a, pk_ta, pk_ta, pk_wst);
     bool live = false;
-    GIPathRec rec;
-    rec.a = rec.b = rec.c = rec.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    GIPathRec rec = giEmptyPath();
     if (active) {
         Hit h;
         if (prayResolve(s, oc, d, a, pk_ta, h)) live = giStagePrimary(s, f, g, x, y, rng, d, h, rec);
@@ -642,7 +652,10 @@ __global__ void __launch_bounds__(RS_BLOCK) k_gi_primary(const __grid_constant__
     }
     giAppendPath(g.pathQ[0], g.pathCount + 1, live, rec);
 }
-__global__ void __launch_bounds__(RS_BLOCK) k_gi_bounce(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+#ifndef RS_MINB_GI_BOUNCE
+#define RS_MINB_GI_BOUNCE 1     /* uncapped: 96 registers, 5 blocks / SM */
+#endif
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GI_BOUNCE) k_gi_bounce(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                         const __grid_constant__ GIDev g, int depth) {
     RS_DECLARE_STACK(stack);
     RS_DECLARE_PACKET(pk, 1);
@@ -651,12 +664,9 @@ __global__ void __launch_bounds__(RS_BLOCK) k_gi_bounce(const __grid_constant__ 
     if (blockIdx.x * RS_BLOCK >= n) return;                                           // whole block out of work (uniform)
     const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
     bool live = false;
-    GIPathRec rec;
-    rec.a = rec.b = rec.c = rec.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    GIPathRec rec = giEmptyPath();
     if (i < n) {
-        const float4* q = g.pathQ[(depth - 1) & 1] + 4 * (size_t)i;
-        GIPathRec in;
-        in.a = q[0]; in.b = q[1]; in.c = q[2]; in.d = q[3];
+        const GIPathRec in = giLoadPath(g.pathQ[(depth - 1) & 1], i);
         int x, y;
         const int r = giStageBounce(s, f, g, depth, in, stack, pk_ta, rec, x, y);
         if (r < 0) enqueuePixel(f, x, y);

@@ -153,7 +153,7 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
         // the staged form: giStagePrimary per pixel (primary hit from the reference-order walk, as above), giStageBounce per live path and depth
         // through the queues, giStageResolve per pixel, marked pixels like k_restir_indirect_fix.  One-lane "warps": giAppendPath appends one record.
         const size_t n = (size_t)f->W * f->H;
-        std::vector<float4> pix(8 * n), q0(4 * n), q1(4 * n);
+        std::vector<float4> pix(7 * n), q0(RS_GI_PATH_F4 * n), q1(RS_GI_PATH_F4 * n);
         std::vector<int> status(n, 0);
         std::vector<unsigned int> counts(traceDepth + 2, 0u);
         g.pix = pix.data(); g.pixStatus = status.data(); g.pathQ[0] = q0.data(); g.pathQ[1] = q1.data(); g.pathCount = counts.data(); g.pixStride = n;
@@ -180,9 +180,8 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
                 RS_DECLARE_STACK(stack);
                 RS_DECLARE_PACKET(pk, 1);
                 (void)pk_tb; (void)pk_wst;
-                const float4* q = g.pathQ[(depth - 1) & 1] + 4 * (size_t)i;
-                GIPathRec in, rec;
-                in.a = q[0]; in.b = q[1]; in.c = q[2]; in.d = q[3];
+                const GIPathRec in = giLoadPath(g.pathQ[(depth - 1) & 1], (size_t)i);
+                GIPathRec rec;
                 int x, y;
                 const int r = giStageBounce(s, d, g, depth, in, stack, pk_ta, rec, x, y);
                 giAppendPath(g.pathQ[depth & 1], g.pathCount + depth + 1, r == 1, rec);
