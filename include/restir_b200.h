@@ -410,9 +410,9 @@ int rstr_gi_indirect_device(RstrGI*, float** devIndirectIllum);                 
 /* which tree the bounce rays walk when the scene's traversal mode is the traced one: 0 the traced tree (default), 1 the reference tree in
  * the reference's order; the hits are the same either way (validation switch) */
 int rstr_gi_set_bounce_walk(RstrGI*, int traversal);
-/* how the frame is launched in the traced mode: one kernel per frame (fused) or a wavefront -- primary rays, one launch per bounce over the
- * compacted live paths, resolve (staged).  Same result bit for bit; the environment variable RSTR_GI_PIPELINE=fused|staged sets the
- * default of new handles (A/B measurements). */
+/* how the frame is launched in the traced mode: a wavefront -- primary rays, one launch per iteration of the path loop over the compacted
+ * live paths, resolve (staged, the default) -- or one kernel per frame (fused).  Same result bit for bit; the environment variable
+ * RSTR_GI_PIPELINE=fused|staged sets the default of new handles (A/B measurements). */
 enum { RSTR_GI_PIPELINE_FUSED = 0, RSTR_GI_PIPELINE_STAGED = 1 };
 int rstr_gi_set_pipeline(RstrGI*, int pipeline);
 int rstr_gi_fallback_pixels(RstrGI*, unsigned int* count, int reset);              /* pixels recomputed with the reference-order walk */

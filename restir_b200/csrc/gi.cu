@@ -21,7 +21,7 @@ struct RstrGI {
     int out = 0;                               // which of resv[] is devIndTemporalReservoir (written by the next call)
     bool first = true;                         // ReSTIRFirstFrame
     int bounceWalk = RS_TRAVERSAL_FAST;
-    int pipeline = RSTR_GI_PIPELINE_FUSED;
+    int pipeline = RSTR_GI_PIPELINE_STAGED;       // measured faster on every bench scene (profiles/r02_c34_gi_bench.jsonl)
     // staged pipeline (allocated on first use): per-pixel hand-over planes, pixel status, two path queues, per-depth path counts
     float4* pix = nullptr;
     int* pixStatus = nullptr;

@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(RS_BLOCK) k_gi_primary(const __grid_constant__
     giAppendPath(g.pathQ[0], g.pathCount + 1, live, rec);
 }
 #ifndef RS_MINB_GI_BOUNCE
-#define RS_MINB_GI_BOUNCE 1     /* uncapped: 96 registers, 5 blocks / SM */
+#define RS_MINB_GI_BOUNCE 6     /* 80 registers; A/B on B200 (profiles/r02_c34_gi_bench*.jsonl): 5.01 / 3.91 ms vs 5.45 / 4.34 ms uncapped (96), 5.05 / 3.84 at 8 (64) */
 #endif
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GI_BOUNCE) k_gi_bounce(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
                                                         const __grid_constant__ GIDev g, int depth) {
