@@ -244,20 +244,19 @@ RS_D void giMaterialSample(const Surf& m, float ior, f3 n, f3 wo, float rx, floa
 RS_D float giPowerHeuristic(float f, float g) { const float f2 = f * f; return f2 / (f2 + g * g); }   // mathUtil.h:81-84
 
 // ------------------------------------------------------------------------------------------------ DevScene::sampleDirectLight
-// scene.h:427-459 (occlusion test BEFORE the facing test), :377-392 for the environment map.  Returns the pdf (<= 0: no contribution);
-// undecided = the any-hit walk could not answer (never with EXACT).
-template <bool EXACT>
-RS_D float giSampleDirectLight(const DevScene& s, f3 pos, float c0, float c1, float c2, float c3, Stack& stack, f3& Li, f3& wi, bool& undecided) {
+// scene.h:427-459, :377-392 for the environment map, without the occlusion test: the pdf (<= 0 or NaN: no contribution whatever the test
+// would say) and the point `target` the segment from pos has to reach.  The reference tests occlusion first and the facing of the light
+// second; both only ever turn a contribution into none, so testing the facing first saves the ray without changing a bit.
+RS_D float giLightSample(const DevScene& s, f3 pos, float c0, float c1, float c2, float c3, f3& Li, f3& wi, f3& target) {
     const int len = s.numLights;
+    target = pos;
     if (len <= 0) return -1.f;
     const int pass = min(__float2int_rz((float)len * c0), len - 1);                   // sampler.h:203-207
     const float2 e = __ldg(s.alias + pass);
     const int lightId = (c1 < e.x) ? pass : __float_as_int(e.y);
     if (s.envTex >= 0 && lightId == len - 1) {
         envSample(s, c2, c3, Li, wi);
-        const int occ = traceOccluded<EXACT>(s, pos, pos + wi * 1e6f, stack);
-        if (occ < 0) { undecided = true; return -1.f; }
-        if (occ) return -1.f;
+        target = pos + wi * 1e6f;
         return envPdf(s, Li);
     }
     const float4* lp = s.lights + 4 * (size_t)lightId;
@@ -267,9 +266,7 @@ RS_D float giSampleDirectLight(const DevScene& s, f3 pos, float c0, float c1, fl
     const float sr = sqrtf(c3);                                                       // mathUtil.h:94-100 (ru = r.z, rv = r.w)
     const float u = 1.f - sr, v = c2 * sr;
     const f3 sampled = v1 * u + v2 * v + v0 * (1.f - u - v);
-    const int occ = traceOccluded<EXACT>(s, pos, sampled, stack);
-    if (occ < 0) { undecided = true; return -1.f; }
-    if (occ) return -1.f;
+    target = sampled;
     const f3 pts = sampled - pos;
     if (dot(n, pts) > -1e-6f) return -1.f;                                            // SCENE_LIGHT_SINGLE_SIDED
     Li = mk3(d4.x, d4.y, d4.z);
@@ -300,17 +297,30 @@ struct GIRay { f3 dir; float pdf; bool delta; };                                
 
 // :284-286
 RS_D void giFaceForward(GIVertex& v) { if (v.mat.type != 2 && dot(v.nrm, v.wo) < 0.f) v.nrm = -v.nrm; }
-// :288-299: next-event estimation with MIS at a vertex after the first.  false: undecided shadow ray (never with EXACT)
-template <bool EXACT>
-RS_D bool giNextEvent(const DevScene& s, const GIVertex& v, f3 throughput, f3& Lo, Rng& rng, Stack& stack) {
+// :288-299: next-event estimation with MIS at a vertex after the first, in two steps: the light sample and what it would contribute
+// (c) if the segment to `target` is free, then the occlusion test
+struct GINee { f3 c, target; bool want; };
+RS_D GINee giNextEventSample(const DevScene& s, const GIVertex& v, f3 throughput, Rng& rng) {
     const float c0 = rng.next(), c1 = rng.next(), c2 = rng.next(), c3 = rng.next();
     f3 radiance = mk3(0.f), wi = mk3(0.f);
-    bool undecided = false;
-    const float lightPdf = giSampleDirectLight<EXACT>(s, v.pos, c0, c1, c2, c3, stack, radiance, wi, undecided);
-    if (undecided) return false;
-    if (lightPdf > 0.f) {
+    GINee n;
+    n.c = mk3(0.f);
+    const float lightPdf = giLightSample(s, v.pos, c0, c1, c2, c3, radiance, wi, n.target);
+    n.want = lightPdf > 0.f;
+    if (n.want) {
         const float bsdfPdf = giMaterialPdf(v.mat, v.nrm, v.wo, wi);
-        Lo = Lo + throughput * giBSDF(v.mat, v.nrm, v.wo, wi) * radiance * satDot(v.nrm, wi) / lightPdf * giPowerHeuristic(lightPdf, bsdfPdf);
+        n.c = throughput * giBSDF(v.mat, v.nrm, v.wo, wi) * radiance * satDot(v.nrm, wi) / lightPdf * giPowerHeuristic(lightPdf, bsdfPdf);
+    }
+    return n;
+}
+// false: undecided shadow ray (never with EXACT)
+template <bool EXACT>
+RS_D bool giNextEvent(const DevScene& s, const GIVertex& v, f3 throughput, f3& Lo, Rng& rng, Stack& stack) {
+    const GINee n = giNextEventSample(s, v, throughput, rng);
+    if (n.want) {
+        const int occ = traceOccluded<EXACT>(s, v.pos, n.target, stack);
+        if (occ < 0) return false;
+        if (!occ) Lo = Lo + n.c;
     }
     return true;
 }
@@ -334,15 +344,10 @@ RS_D int giHead(const DevScene& s, int depth, GIVertex& v, f3& throughput, f3& L
     return giSampleBounce(depth, v, throughput, rng, ray) ? 1 : 0;
 }
 
-// 1: the path goes on from v, 0: it ends here, -1: undecided closest hit (never with EXACT).  surface: v.pos / v.nrm are a hit the
-// sample records as xs / ns when depth == 1 (:366, :374)
-template <bool EXACT>
-RS_D int giTail(const DevScene& s, const GIDev& g, int depth, f3 curPos, const GIRay& ray, f3 throughput, f3& Lo, Stack& stack, const TieStore& ts,
-                GIVertex& v, bool& surface) {
+// the part of giTail after the bounce ray's closest hit hh is known
+RS_D int giTailAfterHit(const DevScene& s, int depth, f3 curPos, const GIRay& ray, f3 throughput, f3& Lo, const Hit& hh, GIVertex& v, bool& surface) {
     surface = false;
-    const f3 ro = curPos + ray.dir * 1e-5f, rd = ray.dir;                             // makeOffsetedRay, intersections.h:12
-    Hit hh;
-    if (!giClosest<EXACT>(s, g, ro, rd, stack, ts, hh)) return -1;
+    const f3 rd = ray.dir;
     v.wo = -rd;
     if (hh.prim < 0) {                                                                // :332-343
         if (s.envTex >= 0) {
@@ -374,6 +379,17 @@ RS_D int giTail(const DevScene& s, const GIDev& g, int depth, f3 curPos, const G
     }
     surface = true;
     return 1;
+}
+
+// 1: the path goes on from v, 0: it ends here, -1: undecided closest hit (never with EXACT).  surface: v.pos / v.nrm are a hit the
+// sample records as xs / ns when depth == 1 (:366, :374)
+template <bool EXACT>
+RS_D int giTail(const DevScene& s, const GIDev& g, int depth, f3 curPos, const GIRay& ray, f3 throughput, f3& Lo, Stack& stack, const TieStore& ts,
+                GIVertex& v, bool& surface) {
+    const f3 ro = curPos + ray.dir * 1e-5f, rd = ray.dir;                             // makeOffsetedRay, intersections.h:12
+    Hit hh;
+    if (!giClosest<EXACT>(s, g, ro, rd, stack, ts, hh)) return -1;
+    return giTailAfterHit(s, depth, curPos, ray, throughput, Lo, hh, v, surface);
 }
 
 // what WriteSample needs of the jittered primary hit (the reference's primMaterial / primWo / primSamplePdf / primSampleDelta)
