@@ -597,9 +597,10 @@ class ReSTIRIndirect:
     def set_bounce_walk(self, exact: bool) -> None:
         _check(lib().rstr_gi_set_bounce_walk(self.h, 1 if exact else 0))
 
-    def set_pipeline(self, staged: bool) -> None:
-        """rstr_gi_set_pipeline: one kernel per frame, or primary rays / one launch per bounce over the live paths / resolve (same bits)."""
-        _check(lib().rstr_gi_set_pipeline(self.h, 1 if staged else 0))
+    def set_pipeline(self, staged) -> None:
+        """rstr_gi_set_pipeline: 0 / False one kernel per frame, 1 / True primary rays / one launch per bounce over the live paths / resolve,
+        2 the same with the walks as persistent kernels over ray lists (same bits)."""
+        _check(lib().rstr_gi_set_pipeline(self.h, int(staged)))
 
     def fallback_pixels(self, reset: bool = True) -> int:
         n = C.c_uint(0)

@@ -10,7 +10,9 @@ int rsFail(int code, const std::string& msg) { g_err = msg; return code; }
 void rsCountLaunches(int n) { g_launches += n; }
 static int fail(int code, const std::string& msg) { return rsFail(code, msg); }
 
-static int smCount() {
+int rsSmCount();
+static int smCount() { return rsSmCount(); }
+int rsSmCount() {
     static int n = 0;
     if (!n) {
         int dev = 0;

@@ -12,6 +12,7 @@
 
 int rsFail(int code, const std::string& msg);     // records the message for rstr_last_error() and returns code
 void rsCountLaunches(int n);                       // rstr_launch_count bookkeeping
+int rsSmCount();                                   // SMs of the current device (persistent kernels' grid)
 
 #define CU(expr)                                                                                   \
     do {                                                                                           \

@@ -121,6 +121,12 @@ struct GIDev {
     float4* pathQ[2];          // live paths between two bounces, 96 B each, ping-pong
     unsigned int* pathCount;   // [d]: paths entering bounce d (1-based); zeroed per frame
     size_t pixStride;          // pixels of the frame
+    // ray-queue form (k_gi_head / k_gi_walk_shadow / k_gi_walk_closest / k_gi_tail per depth); null otherwise
+    unsigned int* closestList; // slots of the live-path queue whose bounce ray is to be walked
+    unsigned int* shadowList;  // ... whose next-event segment is to be tested
+    unsigned int* walkCount;   // [4 * depth + k]: closest rays, the closest walker's cursor, shadow rays, the shadow walker's cursor
+    float4* hit;               // per slot: {bx, by, prim, undecided} of the bounce ray
+    int* occ;                  // per slot: 1 occluded, 0 free, -1 undecided
 };
 
 }  // namespace rs

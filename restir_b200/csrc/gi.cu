@@ -27,12 +27,19 @@ struct RstrGI {
     int* pixStatus = nullptr;
     float4* pathQ[2] = {nullptr, nullptr};
     unsigned int* pathCount = nullptr;
+    // ray-queue pipeline (on top of the staged buffers): slot lists of the two walkers + their counters, hits, occlusion flags
+    unsigned int* closestList = nullptr;
+    unsigned int* shadowList = nullptr;
+    unsigned int* walkCount = nullptr;
+    float4* hit = nullptr;
+    int* occ = nullptr;
 };
 
 #define RS_GI_MAX_DEPTH 64
 
 static void giFree(RstrGI* g) {
-    void* all[] = {g->resv[0], g->resv[1], g->nsz[0], g->nsz[1], g->indirect, g->scratch, g->fallback, g->pix, g->pixStatus, g->pathQ[0], g->pathQ[1], g->pathCount};
+    void* all[] = {g->resv[0], g->resv[1], g->nsz[0], g->nsz[1], g->indirect, g->scratch, g->fallback, g->pix, g->pixStatus, g->pathQ[0], g->pathQ[1], g->pathCount,
+                   g->closestList, g->shadowList, g->walkCount, g->hit, g->occ};
     for (void* p : all) cudaFree(p);
     delete g;
 }
@@ -61,6 +68,7 @@ int rstr_gi_create(RstrFrame* f, RstrGI** out) {
     if (const char* env = getenv("RSTR_GI_PIPELINE")) {                               // A/B switch for measurements; rstr_gi_set_pipeline overrides
         if (!strcmp(env, "staged")) g->pipeline = RSTR_GI_PIPELINE_STAGED;
         else if (!strcmp(env, "fused")) g->pipeline = RSTR_GI_PIPELINE_FUSED;
+        else if (!strcmp(env, "queued")) g->pipeline = RSTR_GI_PIPELINE_QUEUED;
     }
     *out = g;
     return RSTR_OK;
@@ -86,7 +94,7 @@ int rstr_gi_set_bounce_walk(RstrGI* g, int traversal) {
 }
 
 int rstr_gi_set_pipeline(RstrGI* g, int pipeline) {
-    if (!g || (pipeline != RSTR_GI_PIPELINE_FUSED && pipeline != RSTR_GI_PIPELINE_STAGED)) return rsFail(RSTR_ERR_ARG, "rstr_gi_set_pipeline: bad argument");
+    if (!g || (pipeline != RSTR_GI_PIPELINE_FUSED && pipeline != RSTR_GI_PIPELINE_STAGED && pipeline != RSTR_GI_PIPELINE_QUEUED)) return rsFail(RSTR_ERR_ARG, "rstr_gi_set_pipeline: bad argument");
     g->pipeline = pipeline;
     return RSTR_OK;
 }
@@ -108,6 +116,24 @@ static int giEnsureStaged(RstrGI* g) {
     return RSTR_OK;
 }
 
+// slot lists, hits and occlusion flags of the ray-queue pipeline: 4 + 4 + 16 + 4 bytes per pixel
+static int giEnsureQueued(RstrGI* g) {
+    if (g->hit) return RSTR_OK;
+    const size_t n = (size_t)g->W * g->H;
+    cudaError_t e = cudaMalloc(&g->closestList, n * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&g->shadowList, n * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&g->walkCount, 4 * (RS_GI_MAX_DEPTH + 2) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&g->occ, n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&g->hit, n * sizeof(float4));
+    if (e != cudaSuccess) {
+        void* all[] = {g->closestList, g->shadowList, g->walkCount, g->occ, g->hit};
+        for (void* p : all) cudaFree(p);
+        g->closestList = g->shadowList = g->walkCount = nullptr; g->occ = nullptr; g->hit = nullptr;
+        return rsFail(RSTR_ERR_CUDA, std::string("rstr_restir_indirect: ray-queue buffers: ") + cudaGetErrorString(e));
+    }
+    return RSTR_OK;
+}
+
 int rstr_restir_indirect(RstrGI* g, const RstrCamera* cam, int looper, int iter, int traceDepth, int reuse, int target) {
     if (!g || !cam) return rsFail(RSTR_ERR_ARG, "rstr_restir_indirect: bad argument");
     RstrFrame* f = g->f;
@@ -123,13 +149,18 @@ int rstr_restir_indirect(RstrGI* g, const RstrCamera* cam, int looper, int iter,
     gd.fallback = g->fallback;
     gd.maxDepth = traceDepth; gd.reuse = reuse; gd.first = g->first ? 1 : 0; gd.iter = iter;
     gd.bounceWalk = g->bounceWalk;
-    if (g->pipeline == RSTR_GI_PIPELINE_STAGED && f->sc->dev.traversal != RS_TRAVERSAL_EXACT) {   // the validation mode has one form
+    if (g->pipeline != RSTR_GI_PIPELINE_FUSED && f->sc->dev.traversal != RS_TRAVERSAL_EXACT) {    // the validation mode has one form
         int rc = giEnsureStaged(g);
         if (rc) return rc;
         gd.pix = g->pix; gd.pixStatus = g->pixStatus; gd.pathQ[0] = g->pathQ[0]; gd.pathQ[1] = g->pathQ[1]; gd.pathCount = g->pathCount;
         gd.pixStride = (size_t)g->W * g->H;
+        if (g->pipeline == RSTR_GI_PIPELINE_QUEUED && g->bounceWalk == RS_TRAVERSAL_FAST) {      // the walkers walk the traced tree
+            rc = giEnsureQueued(g);
+            if (rc) return rc;
+            gd.closestList = g->closestList; gd.shadowList = g->shadowList; gd.walkCount = g->walkCount; gd.hit = g->hit; gd.occ = g->occ;
+        }
     }
-    rsCountLaunches(launchRestirIndirect(f->sc->dev, d, rsToCamDev(*cam), gd, looper, f->stream));
+    rsCountLaunches(launchRestirIndirect(f->sc->dev, d, rsToCamDev(*cam), gd, looper, rsSmCount(), f->stream));
     g->out ^= 1;                                                                     // std::swap(devIndTemporalReservoir, devIndLastTemporalReservoir), restir.cu:463
     g->first = false;
     CU(cudaGetLastError());

@@ -603,6 +603,99 @@ RS_D void giStageResolve(const FrameDev& f, const GIDev& g, int x, int y) {
     giWriteSample(f, g, li, smp, prim, rng);
 }
 
+// ------------------------------------------------------------------------------------------------ the ray-queue form
+// k_gi_bounce's warps start full but run with 5-7 of 32 lanes: a warp lasts as long as its longest walk.  Here an iteration of the path
+// loop is four launches and the walks are kernels of their own over ray lists, persistent warps whose lanes fetch the next ray when
+// they finish one (and wait for each other at leaves), as k_shadow does for the direct path:
+//   k_gi_head          giFaceForward, the light sample and what it would contribute, the bounce direction; the record is rewritten in
+//                      place: {pos, pixel} {target, RNG} {dir, pdf} {c, flags} {throughput, -} {Lo, -}; slot numbers appended to the lists
+//   k_gi_walk_shadow   any-hit walks of the next-event segments (depth > 1)            -> occ[slot]
+//   k_gi_walk_closest  closest-hit walks of the bounce rays (leaf-box / near-tie rule)   -> hit[slot]
+//   k_gi_tail          adds c if the segment was free, giTailAfterHit, survivors to the other queue
+enum { GI_Q_ALIVE = 1, GI_Q_DELTA = 2, GI_Q_SHADOW = 4 };
+RS_D int giQHead(const DevScene& s, const FrameDev& f, const GIDev& g, int depth, GIPathRec& rec) {
+    const int pixel = __float_as_int(rec.a.w);
+    GIVertex v;
+    v.pos = mk3(rec.a.x, rec.a.y, rec.a.z); v.nrm = mk3(rec.b.x, rec.b.y, rec.b.z); v.wo = mk3(rec.c.x, rec.c.y, rec.c.z); v.ior = rec.c.w;
+    v.mat.baseColor = mk3(rec.d.x, rec.d.y, rec.d.z); v.mat.metallic = rec.d.w; v.mat.roughness = rec.e.w; v.mat.type = __float_as_int(rec.f.w);
+    Rng rng;
+    rng.x = __float_as_uint(rec.b.w);
+    f3 throughput = mk3(rec.e.x, rec.e.y, rec.e.z);
+    giFaceForward(v);
+    GINee nee;
+    nee.c = mk3(0.f); nee.target = v.pos; nee.want = false;
+    if (v.mat.type != 2 && depth > 1) nee = giNextEventSample(s, v, throughput, rng);
+    GIRay ray;
+    ray.dir = mk3(0.f); ray.pdf = 0.f; ray.delta = false;
+    const bool alive = giSampleBounce(depth, v, throughput, rng, ray);
+    if (alive && depth == 1) {                                                        // :311-316
+        const size_t li = planeIndex(f, pixel % f.W, pixel / f.W), n = g.pixStride;
+        g.pix[2 * n + li] = make_float4(v.pos.x, v.pos.y, v.pos.z, ray.pdf);
+        g.pix[3 * n + li] = make_float4(v.nrm.x, v.nrm.y, v.nrm.z, __int_as_float(v.mat.type | (ray.delta ? 256 : 0)));
+    }
+    const int flags = (alive ? GI_Q_ALIVE : 0) | (ray.delta ? GI_Q_DELTA : 0) | (nee.want ? GI_Q_SHADOW : 0);
+    rec.b = make_float4(nee.target.x, nee.target.y, nee.target.z, __uint_as_float(rng.x));
+    rec.c = make_float4(ray.dir.x, ray.dir.y, ray.dir.z, ray.pdf);
+    rec.d = make_float4(nee.c.x, nee.c.y, nee.c.z, __int_as_float(flags));
+    rec.e = make_float4(throughput.x, throughput.y, throughput.z, 0.f);
+    return flags;
+}
+// 1: the path goes on (out), 0: it ended, -1: undecided ray (pixel marked; the caller queues it)
+RS_D int giQTail(const DevScene& s, const FrameDev& f, const GIDev& g, int depth, const GIPathRec& rec, int occ, float4 hit, GIPathRec& out, int& x, int& y) {
+    const int pixel = __float_as_int(rec.a.w), flags = __float_as_int(rec.d.w);
+    x = pixel % f.W; y = pixel / f.W;
+    const size_t li = planeIndex(f, x, y), n = g.pixStride;
+    Rng rng;
+    rng.x = __float_as_uint(rec.b.w);
+    const f3 throughput = mk3(rec.e.x, rec.e.y, rec.e.z);
+    f3 Lo = mk3(rec.f.x, rec.f.y, rec.f.z);
+    if (flags & GI_Q_SHADOW) {
+        if (occ < 0) { g.pixStatus[li] = 2; return -1; }
+        if (!occ) Lo = Lo + mk3(rec.d.x, rec.d.y, rec.d.z);
+    }
+    if (flags & GI_Q_ALIVE) {
+        if (hit.w != 0.f) { g.pixStatus[li] = 2; return -1; }
+        Hit hh;
+        hh.bx = hit.x; hh.by = hit.y; hh.prim = __float_as_int(hit.z); hh.t = 0.f;
+        GIRay ray;
+        ray.dir = mk3(rec.c.x, rec.c.y, rec.c.z); ray.pdf = rec.c.w; ray.delta = (flags & GI_Q_DELTA) != 0;
+        GIVertex v;
+        bool surface;
+        const int r = giTailAfterHit(s, depth, mk3(rec.a.x, rec.a.y, rec.a.z), ray, throughput, Lo, hh, v, surface);
+        if (depth == 1 && surface) {                                                  // :366, :374
+            g.pix[5 * n + li] = make_float4(v.pos.x, v.pos.y, v.pos.z, v.nrm.x);
+            g.pix[6 * n + li] = make_float4(v.nrm.y, v.nrm.z, 0.f, 0.f);
+        }
+        if (r == 1 && depth < g.maxDepth) {
+            out = giPackPath(pixel, v, throughput, Lo, rng);
+            return 1;
+        }
+    }
+    giPathFinished(g, li, Lo, rng);
+    return 0;
+}
+// what the walkers do for one ray, in the per-lane form (tests/emu; the kernels below walk the same rays with lane refill)
+RS_D float4 giQClosestOf(const DevScene& s, const GIDev& g, const GIPathRec& rec, Stack& stack, const TieStore& ts) {
+    const f3 pos = mk3(rec.a.x, rec.a.y, rec.a.z), dir = mk3(rec.c.x, rec.c.y, rec.c.z);
+    Hit h;
+    const bool ok = giClosest<false>(s, g, pos + dir * 1e-5f, dir, stack, ts, h);
+    return make_float4(h.bx, h.by, __int_as_float(h.prim), ok ? 0.f : 1.f);
+}
+RS_D int giQShadowOf(const DevScene& s, const GIPathRec& rec, Stack& stack) {
+    return traceOccluded<false>(s, mk3(rec.a.x, rec.a.y, rec.a.z), mk3(rec.b.x, rec.b.y, rec.b.z), stack);
+}
+
+// warp-aggregated append of a slot number per wanting lane (all 32 lanes call)
+RS_D void giAppendSlot(unsigned int* list, unsigned int* count, bool want, unsigned slot) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) list[base + __popc(m & ((1u << lane) - 1u))] = slot;
+}
+
 // warp-aggregated append of one path record per wanting lane (all 32 lanes call)
 RS_D void giAppendPath(float4* q, unsigned int* count, bool want, const GIPathRec& r) {
     const unsigned m = __ballot_sync(0xffffffffu, want);
@@ -690,6 +783,207 @@ __global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GI_BOUNCE) k_gi_bounce(const
     }
     giAppendPath(g.pathQ[depth & 1], g.pathCount + depth + 1, live, rec);
 }
+// ---- the ray-queue form's kernels
+__global__ void __launch_bounds__(RS_BLOCK) k_gi_head(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                      const __grid_constant__ GIDev g, int depth) {
+    const unsigned n = g.pathCount[depth];
+    if (blockIdx.x * RS_BLOCK >= n) return;                                           // whole block out of work (uniform)
+    const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
+    int flags = 0;
+    if (i < n) {
+        float4* q = g.pathQ[(depth - 1) & 1];
+        GIPathRec rec = giLoadPath(q, i);
+        flags = giQHead(s, f, g, depth, rec);
+        float4* o = q + RS_GI_PATH_F4 * (size_t)i;                                    // {pos, pixel} and {Lo, -} stay
+        o[1] = rec.b; o[2] = rec.c; o[3] = rec.d; o[4] = rec.e;
+    }
+    giAppendSlot(g.closestList, g.walkCount + 4 * depth, (flags & GI_Q_ALIVE) != 0, i);
+    giAppendSlot(g.shadowList, g.walkCount + 4 * depth + 2, (flags & GI_Q_SHADOW) != 0, i);
+}
+
+#ifndef RS_MINB_GI_WALK
+#define RS_MINB_GI_WALK 6
+#endif
+// Closest hits of the listed bounce rays: traceClosestFast's walk as a state machine, one step per round.  A lane that has finished its
+// ray fetches the next one from the list as soon as RS_REFILL_MIN lanes are idle; lanes that have reached a leaf wait until RS_LEAF_MIN
+// of them are there (or nobody is left to step), so the triangle tests run with several lanes.  What a ray reports does not depend on
+// the order of its steps (leaf-box / near-tie rule), so the hits are traceClosestFast's.
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_GI_WALK) k_gi_walk_closest(const __grid_constant__ DevScene s, const __grid_constant__ GIDev g, int depth) {
+    RS_DECLARE_STACK(stack);
+    RS_DECLARE_PACKET(pk, 1);
+    (void)pk_tb; (void)pk_wst;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned n = g.walkCount[4 * depth];
+    unsigned int* cursor = g.walkCount + 4 * depth + 1;
+    const float4* q = g.pathQ[(depth - 1) & 1];
+    const int lane = threadIdx.x & 31;
+    PRay p = prayBegin(mk3(0.f), mk3(0.f, 0.f, 1.f), false, pk_ta);
+    f3 o = mk3(0.f);
+    int cur = RS_DONE, sp = 0;
+    unsigned slot = 0;
+    bool exhausted = false;                       // warp-uniform: the list is empty
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, cur == RS_DONE);
+        if (idle == FULL && exhausted) break;
+        if (!exhausted && (__popc(idle) >= RS_REFILL_MIN || idle == FULL)) {
+            unsigned base = 0;
+            const int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(cursor, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= n) exhausted = true;
+            const unsigned i = base + __popc(idle & ((1u << lane) - 1u));
+            if (cur == RS_DONE && i < n) {
+                slot = g.closestList[i];
+                const float4 a = q[RS_GI_PATH_F4 * (size_t)slot], c = q[RS_GI_PATH_F4 * (size_t)slot + 2];
+                const f3 dir = mk3(c.x, c.y, c.z);
+                o = mk3(a.x, a.y, a.z) + dir * 1e-5f;                                 // makeOffsetedRay, intersections.h:12
+                bool miss = isnan(dir.x) || isnan(dir.y) || isnan(dir.z) || isnan(o.x) || isnan(o.y) || isnan(o.z);   // see traceClosestFast
+                if (!miss) {
+                    p = prayBegin(o, dir, true, pk_ta);
+                    float t0;
+                    if (slabHitP(p, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], t0)) {
+                        cur = s.fastRoot; sp = 0;
+                    } else miss = true;
+                }
+                if (miss) g.hit[slot] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+            }
+        }
+        const unsigned atLeaf = __ballot_sync(FULL, cur < 0);
+        const unsigned atNode = __ballot_sync(FULL, cur >= 0 && cur != RS_DONE);
+        bool pop = false;
+        if (atNode && __popc(atLeaf) < RS_LEAF_MIN) {
+            if (cur >= 0 && cur != RS_DONE) {
+                const float4* np = s.fastNodes + 4 * (size_t)cur;
+                const F8 nA = ldg256(np), nB = ldg256(np + 2);
+                const float4 a = nA.lo, b = nA.hi, c = nB.lo;
+                const int2 l = make_int2(__float_as_int(nB.hi.x), __float_as_int(nB.hi.y));
+                float tL, tR;
+                const bool hL = slabHitP(p, a.x, a.y, a.z, a.w, b.x, b.y, tL);
+                const bool hR = slabHitP(p, b.z, b.w, c.x, c.y, c.z, c.w, tR);
+                if (hL && hR) {
+                    const bool leftNear = tL <= tR;
+                    stack.push(sp, leftNear ? l.y : l.x, leftNear ? tR : tL); sp++;
+                    cur = leftNear ? l.x : l.y;
+                } else if (hL) cur = l.x;
+                else if (hR) cur = l.y;
+                else pop = true;
+            }
+        } else if (cur < 0) {
+            const int first = cur & 0x07ffffff, count = ((cur >> 27) & 7) + 1;
+            const f3 d = pk_ta.dir();
+            for (int k = 0; k < count; k++) {
+                const Tri t = loadTriFast(s, first + k);
+                prayOffer(p, o, d, pk_ta, t, first + k);
+            }
+            pop = true;
+        }
+        if (pop) {
+            cur = RS_DONE;
+            while (sp > 0) {
+                --sp;
+                if (stack.t(sp) <= p.limit) { cur = stack.ref(sp); break; }
+            }
+            if (cur == RS_DONE) {                                                     // the ray is finished
+                Hit h;
+                const bool ok = prayResolve(s, o, pk_ta.dir(), p, pk_ta, h);
+                g.hit[slot] = make_float4(h.bx, h.by, __int_as_float(h.prim), ok ? 0.f : 1.f);
+            }
+        }
+    }
+}
+
+// The listed next-event segments, any hit: k_shadow's loop (refill, leaf wait, nearer child first) on traceOccluded's ray
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINB_SHADOW) k_gi_walk_shadow(const __grid_constant__ DevScene s, const __grid_constant__ GIDev g, int depth) {
+    RS_DECLARE_REFSTACK(stack);
+    const unsigned FULL = 0xffffffffu;
+    const unsigned n = g.walkCount[4 * depth + 2];
+    unsigned int* cursor = g.walkCount + 4 * depth + 3;
+    const float4* q = g.pathQ[(depth - 1) & 1];
+    const int lane = threadIdx.x & 31;
+    RayT r;
+    RayF rf;
+    float dist = 0.f;
+    int cur = RS_DONE, sp = 0;
+    unsigned slot = 0;
+    bool exhausted = false;
+    r.o = r.d = r.inv = mk3(0.f); r.flags = 0; r.dim = r.lesser = 0;
+    rf.inv = rf.oi = mk3(0.f);
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, cur == RS_DONE);
+        if (idle == FULL && exhausted) break;
+        if (!exhausted && (__popc(idle) >= RS_REFILL_MIN || idle == FULL)) {
+            unsigned base = 0;
+            const int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(cursor, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base >= n) exhausted = true;
+            const unsigned i = base + __popc(idle & ((1u << lane) - 1u));
+            if (cur == RS_DONE && i < n) {
+                slot = g.shadowList[i];
+                const float4 a = q[RS_GI_PATH_F4 * (size_t)slot], b = q[RS_GI_PATH_F4 * (size_t)slot + 1];
+                const f3 x = mk3(a.x, a.y, a.z);
+                f3 dir = mk3(b.x, b.y, b.z) - x;                                      // traceOccluded (scene.h:286-295)
+                float dd = length(dir);
+                if (dd > 0.f) {
+                    dir = dir / dd;
+                    r = makeRayT(x + dir * 1e-5f, dir);
+                    dist = dd - 1e-4f * 2.f;
+                    rf = makeRayF(r);
+                    float tr;
+                    if (slabHit(rf, s.fastRootMin[0], s.fastRootMin[1], s.fastRootMin[2], s.fastRootMax[0], s.fastRootMax[1], s.fastRootMax[2], dist, tr)) {
+                        cur = s.fastRoot; sp = 0;
+                    }
+                }
+                if (cur == RS_DONE) g.occ[slot] = 0;
+            }
+        }
+        const unsigned atLeaf = __ballot_sync(FULL, cur < 0);
+        const unsigned atNode = __ballot_sync(FULL, cur >= 0 && cur != RS_DONE);
+        if (atNode && __popc(atLeaf) < RS_LEAF_MIN) {
+            if (cur >= 0 && cur != RS_DONE) {
+                const float4* np = s.fastNodes + 4 * (size_t)cur;
+                const F8 nA = ldg256(np), nB = ldg256(np + 2);
+                const float4 a = nA.lo, b = nA.hi, c = nB.lo;
+                const int2 l = make_int2(__float_as_int(nB.hi.x), __float_as_int(nB.hi.y));
+                float tL, tR;
+                const bool hL = slabHit(rf, a.x, a.y, a.z, a.w, b.x, b.y, dist, tL);
+                const bool hR = slabHit(rf, b.z, b.w, c.x, c.y, c.z, c.w, dist, tR);
+                if (hL && hR) { const bool ln = tL <= tR; stack.pushRef(sp, ln ? l.y : l.x); sp++; cur = ln ? l.x : l.y; }
+                else if (hL) cur = l.x;
+                else if (hR) cur = l.y;
+                else cur = sp == 0 ? RS_DONE : stack.ref(--sp);
+                if (cur == RS_DONE) g.occ[slot] = 0;
+            }
+        } else if (cur < 0) {
+            if (leafOccluded(s, r, dist, cur)) { g.occ[slot] = 1; cur = RS_DONE; }
+            else {
+                cur = sp == 0 ? RS_DONE : stack.ref(--sp);
+                if (cur == RS_DONE) g.occ[slot] = 0;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RS_BLOCK) k_gi_tail(const __grid_constant__ DevScene s, const __grid_constant__ FrameDev f,
+                                                      const __grid_constant__ GIDev g, int depth) {
+    const unsigned n = g.pathCount[depth];
+    if (blockIdx.x * RS_BLOCK >= n) return;
+    const unsigned i = blockIdx.x * RS_BLOCK + threadIdx.x;
+    bool live = false;
+    GIPathRec rec = giEmptyPath();
+    if (i < n) {
+        const GIPathRec in = giLoadPath(g.pathQ[(depth - 1) & 1], i);
+        const int flags = __float_as_int(in.d.w);
+        const int occ = (flags & GI_Q_SHADOW) ? g.occ[i] : 0;
+        const float4 hit = (flags & GI_Q_ALIVE) ? g.hit[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        int x, y;
+        const int r = giQTail(s, f, g, depth, in, occ, hit, rec, x, y);
+        if (r < 0) enqueuePixel(f, x, y);
+        live = r == 1;
+    }
+    giAppendPath(g.pathQ[depth & 1], g.pathCount + depth + 1, live, rec);
+}
+
 __global__ void __launch_bounds__(RS_BLOCK) k_gi_resolve(const __grid_constant__ FrameDev f, const __grid_constant__ GIDev g) {
     int x, y;
     if (pixelOf(f, x, y)) giStageResolve(f, g, x, y);
@@ -725,17 +1019,30 @@ __global__ void k_export_gi(const float4* __restrict__ rec, const float* __restr
 }
 
 #ifndef RS_HOST_EMU
-int launchRestirIndirect(const DevScene& s, const FrameDev& f, const CamDev& cam, const GIDev& g, int looper, cudaStream_t st) {
+int launchRestirIndirect(const DevScene& s, const FrameDev& f, const CamDev& cam, const GIDev& g, int looper, int numSMs, cudaStream_t st) {
     if (s.traversal == RS_TRAVERSAL_EXACT) { k_restir_indirect_exact<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, g, looper); return 1; }
     cudaMemsetAsync(f.queueCount, 0, sizeof(unsigned int), st);
     if (g.pix) {                                                                      // staged: one launch per bounce over the live paths
         cudaMemsetAsync(g.pathCount, 0, (size_t)(g.maxDepth + 2) * sizeof(unsigned int), st);
         k_gi_primary<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
         const unsigned blocks = (unsigned)((g.pixStride + RS_BLOCK - 1) / RS_BLOCK);   // the path count lives on the device: blocks past it return at once
-        for (int depth = 1; depth <= g.maxDepth; depth++) k_gi_bounce<<<blocks, RS_BLOCK, 0, st>>>(s, f, g, depth);
+        int launches = 3;
+        if (g.hit) {                                                                  // ray queues: the walks as persistent kernels with lane refill
+            cudaMemsetAsync(g.walkCount, 0, (size_t)(4 * (g.maxDepth + 1)) * sizeof(unsigned int), st);
+            for (int depth = 1; depth <= g.maxDepth; depth++) {
+                k_gi_head<<<blocks, RS_BLOCK, 0, st>>>(s, f, g, depth);
+                if (depth > 1) k_gi_walk_shadow<<<(unsigned)(numSMs * RS_MINB_SHADOW), RS_BLOCK, 0, st>>>(s, g, depth);
+                k_gi_walk_closest<<<(unsigned)(numSMs * RS_MINB_GI_WALK), RS_BLOCK, 0, st>>>(s, g, depth);
+                k_gi_tail<<<blocks, RS_BLOCK, 0, st>>>(s, f, g, depth);
+                launches += depth > 1 ? 4 : 3;
+            }
+        } else {
+            for (int depth = 1; depth <= g.maxDepth; depth++) k_gi_bounce<<<blocks, RS_BLOCK, 0, st>>>(s, f, g, depth);
+            launches += g.maxDepth;
+        }
         k_gi_resolve<<<pixelGrid(f), RS_BLOCK, 0, st>>>(f, g);
         k_restir_indirect_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
-        return 3 + g.maxDepth;
+        return launches;
     }
     k_restir_indirect<<<pixelGrid(f), RS_BLOCK, 0, st>>>(s, f, cam, g, looper);
     k_restir_indirect_fix<<<RS_FIX_BLOCKS, RS_BLOCK, 0, st>>>(s, f, cam, g, looper);

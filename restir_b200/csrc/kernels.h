@@ -23,7 +23,7 @@ void launchTonemap(const float* radiance, uchar4* ldr, size_t n, int toneMapping
 void launchExportGeom(const float4* geom, const float4* am, float* albedo, float* normal, float* depth, int* motion, size_t n, cudaStream_t st);
 void launchExportResv(const DevScene& s, const ResvD* src, float* out36, int* lightIdx, size_t n, cudaStream_t st);
 // ReSTIR GI (gi_kernels.inl)
-int launchRestirIndirect(const DevScene& s, const FrameDev& f, const CamDev& cam, const GIDev& g, int looper, cudaStream_t st);
+int launchRestirIndirect(const DevScene& s, const FrameDev& f, const CamDev& cam, const GIDev& g, int looper, int numSMs, cudaStream_t st);
 void launchExportGI(const float4* rec, const float* nsz, float* out17, size_t n, cudaStream_t st);
 
 }  // namespace rs

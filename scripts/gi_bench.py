@@ -31,7 +31,7 @@ def run(rb, name, steps, warmup, depth, exact, bounce_exact, staged=False):
     fr = sc.frame(*res)
     gi = rb.ReSTIRIndirect(fr)
     gi.set_bounce_walk(bounce_exact)
-    gi.set_pipeline(staged)
+    gi.set_pipeline(int(staged))
     base = rb.Camera.from_scene(sd)
     setup_s = time.time() - t0
     k = 0
@@ -51,7 +51,7 @@ def run(rb, name, steps, warmup, depth, exact, bounce_exact, staged=False):
     img = gi.read()
     out = {"workload": name, "resolution": list(res), "triangles": sc.info.numTris, "emissive_triangles": sc.info.numLights, "trace_depth": depth,
            "traversal": "reference-order walk" if exact else ("packet primary + reference-order bounces" if bounce_exact else "traced tree"),
-           "pipeline": "one kernel" if exact or not staged else "staged (primary / bounce per depth / resolve)",
+           "pipeline": "one kernel" if exact or not staged else ("staged (primary / bounce per depth / resolve)" if staged == 1 else "ray queues (primary / head, shadow walker, closest walker, tail per depth / resolve)"),
            "steps": steps, "warmup": warmup, "gi_ms_per_frame": total / steps, "mpixel_per_s": res[0] * res[1] / (total / steps * 1e-3) / 1e6,
            "fixup_pixels_per_frame": gi.fallback_pixels() / (warmup + steps), "mean_indirect": float(img.mean()), "lit_fraction": float((img.sum(1) > 0).mean()),
            "setup_s": setup_s, "build_id": rb.api.build_id()}
@@ -66,7 +66,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--depth", type=int, default=3)
-    ap.add_argument("--modes", nargs="+", default=["traced", "exact"], choices=["traced", "staged", "mixed", "exact"])
+    ap.add_argument("--modes", nargs="+", default=["traced", "exact"], choices=["traced", "staged", "queued", "mixed", "exact"])
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "gi_bench.jsonl"))
     args = ap.parse_args()
     import restir_b200 as rb
@@ -76,7 +76,7 @@ def main():
     with open(args.out, "a") as f:
         for name in args.workloads:
             for mode in args.modes:
-                r = run(rb, name, args.steps if mode != "exact" else max(3, args.steps // 4), args.warmup, args.depth, mode == "exact", mode == "mixed", mode == "staged")
+                r = run(rb, name, args.steps if mode != "exact" else max(3, args.steps // 4), args.warmup, args.depth, mode == "exact", mode == "mixed", {"staged": 1, "queued": 2}.get(mode, 0))
                 line = json.dumps(r)
                 print(line, flush=True)
                 f.write(line + "\n")

@@ -19,6 +19,10 @@
 #define __launch_bounds__(...)
 #undef __grid_constant__
 #define __grid_constant__
+// __shared__ arrays: one copy per OS thread -- what the 32 fibers of a warp share under emuRunWarp (the kernels emulated that way keep
+// per-lane columns [..][threadIdx.x] in them); a plain per-call array in the one-thread-per-call emulation
+#undef __shared__
+#define __shared__ static thread_local
 
 struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
 static thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
@@ -47,18 +51,156 @@ static inline unsigned atomicMax(unsigned* p, unsigned v) {
 static inline long long clock64() { return 0; }
 static inline void __syncthreads() {}
 static inline void __trap() { abort(); }
-// a "warp" of one lane: enough for the warp-level code to compile; the emulation never calls the packet walk
-static inline int __any_sync(unsigned, int p) { return p; }
-static inline int __all_sync(unsigned, int p) { return p; }
-static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
-template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
-static inline unsigned __reduce_min_sync(unsigned, unsigned v) { return v; }
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return v; }
-static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return v; }
-static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
-static inline unsigned __match_any_sync(unsigned, unsigned) { return 1u; }
+// ---- warps.  Outside emuRunWarp a "warp" has one lane (the per-pixel emulation: one call = one thread).  Inside emuRunWarp the 32 lanes of
+// a warp are 32 fibers (ucontext) on one OS thread: a lane runs until its next warp-level intrinsic, deposits its value and yields; when
+// every live lane has deposited, the lanes are resumed in turn and combine the values.  All lanes of convergent code reach the same
+// sequence of intrinsics, so pass k of the scheduler is synchronisation point k of every lane; the deposits are double-buffered by the
+// parity of k (a resumed lane may reach point k + 1 and deposit again before its neighbours have read point k).  Lanes that have
+// returned from the kernel contribute 0 / are skipped, as exited threads do on the GPU.
+#include <ucontext.h>
+#define EMU_FIBER_STACK (512 * 1024)
+struct EmuWarp {
+    ucontext_t sched, ctx[32];
+    bool done[32];
+    int lane;                                    // the lane that is running
+    unsigned sync[32];                           // synchronisation points passed, per lane
+    unsigned long long val[2][32];
+    bool has[2][32];                             // the lane has deposited at this point (false: it had exited before)
+    void (*body)(void*);
+    void* arg;
+};
+static thread_local EmuWarp* emuWarp = nullptr;
+static thread_local char* emuStacks = nullptr;
+// deposit `mine`, wait for the warp, return the buffer of this synchronisation point (entries of exited lanes are 0)
+static inline const unsigned long long* emuExchange(unsigned long long mine) {
+    EmuWarp* w = emuWarp;
+    const int l = w->lane;
+    const unsigned k = w->sync[l]++ & 1u;
+    w->val[k][l] = mine;
+    w->has[k][l] = true;
+    swapcontext(&w->ctx[l], &w->sched);
+    return emuWarp->val[k];
+}
+static void emuTrampoline() {
+    EmuWarp* w = emuWarp;
+    w->body(w->arg);
+    w = emuWarp;
+    // what the lane deposited at its last synchronisation point is still being read by the lanes resumed after it in this pass (the scheduler
+    // clears it after the pass); at the next point it counts as exited
+    const int l = w->lane;
+    const unsigned next = w->sync[l] & 1u;
+    w->done[l] = true;
+    w->val[next][l] = 0; w->has[next][l] = false;
+}
+// run `body(arg)` as the 32 lanes tidBase .. tidBase + 31 of one warp; blockIdx / blockDim / gridDim are the caller's
+static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg);
+
+static inline int __any_sync(unsigned, int p) {
+    if (!emuWarp) return p;
+    const unsigned long long* v = emuExchange(p ? 1 : 0);
+    int r = 0;
+    for (int i = 0; i < 32; i++) r |= (int)v[i];
+    return r;
+}
+static inline const bool* emuHas(const unsigned long long* v) { return emuWarp->has[v == emuWarp->val[0] ? 0 : 1]; }
+static inline int __all_sync(unsigned, int p) {
+    if (!emuWarp) return p;
+    const unsigned long long* v = emuExchange(p ? 1 : 0);
+    const bool* has = emuHas(v);
+    int r = 1;
+    for (int i = 0; i < 32; i++) if (has[i]) r &= (int)v[i];
+    return r;
+}
+static inline unsigned __ballot_sync(unsigned, int p) {
+    if (!emuWarp) return p ? 1u : 0u;
+    const unsigned long long* v = emuExchange(p ? 1 : 0);
+    unsigned m = 0;
+    for (int i = 0; i < 32; i++) m |= (unsigned)v[i] << i;
+    return m;
+}
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
+    if (!emuWarp) return v;
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    const unsigned long long* all = emuExchange(bits);
+    T r;
+    memcpy(&r, &all[src & 31], sizeof(T));
+    return r;
+}
+static inline unsigned __reduce_min_sync(unsigned, unsigned x) {
+    if (!emuWarp) return x;
+    const unsigned long long* v = emuExchange(x);
+    const bool* has = emuHas(v);
+    unsigned r = 0xffffffffu;
+    for (int i = 0; i < 32; i++) if (has[i] && (unsigned)v[i] < r) r = (unsigned)v[i];
+    return r;
+}
+static inline unsigned __reduce_max_sync(unsigned, unsigned x) {
+    if (!emuWarp) return x;
+    const unsigned long long* v = emuExchange(x);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) if ((unsigned)v[i] > r) r = (unsigned)v[i];
+    return r;
+}
+static inline unsigned __reduce_or_sync(unsigned, unsigned x) {
+    if (!emuWarp) return x;
+    const unsigned long long* v = emuExchange(x);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r |= (unsigned)v[i];
+    return r;
+}
+static inline unsigned __reduce_add_sync(unsigned, unsigned x) {
+    if (!emuWarp) return x;
+    const unsigned long long* v = emuExchange(x);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r += (unsigned)v[i];
+    return r;
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) { if (emuWarp) emuExchange(0); }
+static inline unsigned __match_any_sync(unsigned, unsigned) { return 1u; }          // one-lane form only (not used under emuRunWarp)
 static inline unsigned __activemask() { return 1u; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+
+
+static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) {
+    if (!emuStacks) emuStacks = (char*)malloc((size_t)32 * EMU_FIBER_STACK);
+    EmuWarp w;
+    memset(w.done, 0, sizeof w.done); memset(w.sync, 0, sizeof w.sync); memset(w.val, 0, sizeof w.val); memset(w.has, 0, sizeof w.has);
+    w.body = body; w.arg = arg; w.lane = 0;
+    for (int l = 0; l < 32; l++) {
+        getcontext(&w.ctx[l]);
+        w.ctx[l].uc_stack.ss_sp = emuStacks + (size_t)l * EMU_FIBER_STACK;
+        w.ctx[l].uc_stack.ss_size = EMU_FIBER_STACK;
+        w.ctx[l].uc_link = &w.sched;
+        makecontext(&w.ctx[l], emuTrampoline, 0);
+    }
+    emuWarp = &w;
+    for (;;) {
+        bool any = false;
+        for (int l = 0; l < 32; l++)
+            if (!w.done[l]) {
+                any = true;
+                w.lane = l;
+                threadIdx.x = tidBase + l;
+                swapcontext(&w.sched, &w.ctx[l]);
+            }
+        if (!any) break;
+        for (int l = 0; l < 32; l++)
+            if (w.done[l]) { w.val[0][l] = w.val[1][l] = 0; w.has[0][l] = w.has[1][l] = false; }
+    }
+    emuWarp = nullptr;
+}
+// a grid of blocks of 128 threads (4 warps); the warps of the grid run on the OpenMP threads, each warp on one of them
+template <typename F> static inline void emuLaunch(unsigned gridX, unsigned gridY, F kernelCall) {
+    struct Call { static void run(void* a) { (*(F*)a)(); } };
+#pragma omp parallel for collapse(3) schedule(dynamic, 1)
+    for (unsigned by = 0; by < gridY; by++)
+        for (unsigned bx = 0; bx < gridX; bx++)
+            for (unsigned wp = 0; wp < 4; wp++) {
+                blockIdx.x = bx; blockIdx.y = by; gridDim.x = gridX; gridDim.y = gridY; blockDim.x = 128;
+                emuRunWarp(wp * 32, &Call::run, &kernelCall);
+            }
+}

@@ -68,7 +68,7 @@ class Emu:
         for f in range(frames):
             cam = base.orbit(f) if orbit else base
             L.emu_gbuffer_render(fr, C.byref(cam))
-            L.emu_restir_indirect(fr, C.byref(cam), f, f if accumulate else 0, max_depth, reuse, 2 if staged else 1 if traced_tree else 0)
+            L.emu_restir_indirect(fr, C.byref(cam), f, f if accumulate else 0, max_depth, reuse, (2 if staged is True else int(staged) + 1) if staged else 1 if traced_tree else 0)
             r = self._view(L.emu_gi_reservoirs(fr), np.float32, (W * H, 17))
             r[:, 15] = r[:, 15].view(np.int32).astype(np.float32)          # numSamples: int bits in the reference layout
             d = {"indirect": self._view(L.emu_gi_indirect(fr), np.float32, (W * H, 3)), "reservoir": r}

@@ -28,6 +28,8 @@ struct EmuFrame {
     std::vector<float4> resv[2];
     std::vector<float> nsz[2], indirect, export17;
     unsigned int counters[4] = {0, 0, 0, 0};
+    std::vector<int> queue;                      // fix-up queue of the kernels run under emuLaunch
+    unsigned int queueCount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int cur = 0, out = 0;
     bool first = true, haveLast = false;
     RstrCamera lastCamera{};
@@ -54,6 +56,8 @@ FrameDev toFrameDev(EmuFrame* f) {
     d.matId[0] = f->matId[f->cur].data(); d.matId[1] = f->matId[f->cur ^ 1].data();
     d.albedoMotion = f->albedoMotion.data();
     d.haloMiss = f->counters; d.motionRows = f->counters + 1;
+    f->queue.resize((size_t)f->W * f->H);
+    d.queue = f->queue.data(); d.queueCount = f->queueCount;
     return d;
 }
 
@@ -135,7 +139,7 @@ void emu_gbuffer_update(void* fv, const RstrCamera* cam) {
 }
 void emu_gi_reset(void* fv) { ((EmuFrame*)fv)->first = true; }
 
-// rstr_restir_indirect.  tracedTree = 2: the staged pipeline (below).  tracedTree = 0: k_restir_indirect_exact's body per pixel.  tracedTree = 1: the primary hit from the reference-order
+// rstr_restir_indirect.  tracedTree = 2 / 3: the staged / ray-queue pipeline's bodies; 4 / 5: the ray-queue / staged pipeline's kernels as warps (below).  tracedTree = 0: k_restir_indirect_exact's body per pixel.  tracedTree = 1: the primary hit from the reference-order
 // walk (standing in for the packet walk), then giAfterHit<false>: bounce rays through traceClosestFast, shadow rays through
 // traceOccludedFast; an undecided pixel is recomputed like k_restir_indirect_fix does.
 void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, int traceDepth, int reuse, int tracedTree) {
@@ -149,7 +153,7 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
     g.indirect = f->indirect.data(); g.fallback = nullptr;
     g.maxDepth = traceDepth; g.reuse = reuse; g.first = f->first ? 1 : 0; g.iter = iter; g.bounceWalk = RS_TRAVERSAL_FAST;
     unsigned long long undecided = 0;
-    if (tracedTree == 2) {
+    if (tracedTree >= 2) {
         // the staged form: giStagePrimary per pixel (primary hit from the reference-order walk, as above), giStageBounce per live path and depth
         // through the queues, giStageResolve per pixel, marked pixels like k_restir_indirect_fix.  One-lane "warps": giAppendPath appends one record.
         const size_t n = (size_t)f->W * f->H;
@@ -172,7 +176,85 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
                 const bool live = giStagePrimary(s, d, g, x, y, rng, dir, h, rec);
                 giAppendPath(g.pathQ[0], g.pathCount + 1, live, rec);
             }
-        for (int depth = 1; depth <= traceDepth; depth++) {
+        // tracedTree == 4: the ray-queue form's KERNELS (k_gi_head, k_gi_walk_shadow, k_gi_walk_closest, k_gi_tail, k_gi_resolve,
+        // k_restir_indirect_fix) as grids of 32-lane warps (emuLaunch): lane refill, leaf wait, warp-aggregated appends and all
+        if (tracedTree == 5) {                                       // the staged form's kernels as warps: k_gi_bounce per depth, k_gi_resolve, fix-up
+            f->queueCount[0] = 0;
+            const unsigned blocks = (unsigned)((n + RS_BLOCK - 1) / RS_BLOCK);
+            for (int depth = 1; depth <= traceDepth; depth++) emuLaunch(blocks, 1, [&] { k_gi_bounce(s, d, g, depth); });
+            emuLaunch((unsigned)((f->W + 15) / 16), (unsigned)((f->H + 7) / 8), [&] { k_gi_resolve(d, g); });
+            undecided = f->queueCount[0];
+            emuLaunch(2, 1, [&] { k_restir_indirect_fix(s, d, c, g, looper); });
+            f->undecided += undecided;
+            f->out ^= 1;
+            f->first = false;
+            return;
+        }
+        if (tracedTree == 4) {
+            std::vector<unsigned int> cl(n), sl(n), wc(4 * (traceDepth + 2), 0u);
+            std::vector<float4> hit(n);
+            std::vector<int> occ(n);
+            g.closestList = cl.data(); g.shadowList = sl.data(); g.walkCount = wc.data(); g.hit = hit.data(); g.occ = occ.data();
+            f->queueCount[0] = 0;
+            const unsigned blocks = (unsigned)((n + RS_BLOCK - 1) / RS_BLOCK);
+            for (int depth = 1; depth <= traceDepth; depth++) {
+                emuLaunch(blocks, 1, [&] { k_gi_head(s, d, g, depth); });
+                if (depth > 1) emuLaunch(3, 1, [&] { k_gi_walk_shadow(s, g, depth); });
+                emuLaunch(3, 1, [&] { k_gi_walk_closest(s, g, depth); });
+                emuLaunch(blocks, 1, [&] { k_gi_tail(s, d, g, depth); });
+            }
+            emuLaunch((unsigned)((f->W + 15) / 16), (unsigned)((f->H + 7) / 8), [&] { k_gi_resolve(d, g); });
+            undecided = f->queueCount[0];
+            emuLaunch(2, 1, [&] { k_restir_indirect_fix(s, d, c, g, looper); });
+            f->undecided += undecided;
+            f->out ^= 1;
+            f->first = false;
+            return;
+        }
+        // tracedTree == 3: the ray-queue form -- k_gi_head / the two walkers (one ray per call here) / k_gi_tail per depth
+        std::vector<unsigned int> closestList(tracedTree == 3 ? n : 0), shadowList(tracedTree == 3 ? n : 0), walkCount(4 * (traceDepth + 2), 0u);
+        std::vector<float4> hit(tracedTree == 3 ? n : 0);
+        std::vector<int> occ(tracedTree == 3 ? n : 0);
+        for (int depth = 1; tracedTree == 3 && depth <= traceDepth; depth++) {
+            const long long np = counts[depth];
+            float4* q = g.pathQ[(depth - 1) & 1];
+#pragma omp parallel for schedule(dynamic, 16)
+            for (long long i = 0; i < np; i++) {
+                threadIdx.x = 0;
+                GIPathRec rec = giLoadPath(q, (size_t)i);
+                const int flags = giQHead(s, d, g, depth, rec);
+                float4* o = q + RS_GI_PATH_F4 * (size_t)i;
+                o[1] = rec.b; o[2] = rec.c; o[3] = rec.d; o[4] = rec.e;
+                giAppendSlot(closestList.data(), walkCount.data() + 4 * depth, (flags & GI_Q_ALIVE) != 0, (unsigned)i);
+                giAppendSlot(shadowList.data(), walkCount.data() + 4 * depth + 2, (flags & GI_Q_SHADOW) != 0, (unsigned)i);
+            }
+            const long long nc = walkCount[4 * depth], ns = walkCount[4 * depth + 2];
+#pragma omp parallel for schedule(dynamic, 16)
+            for (long long k = 0; k < ns; k++) {
+                threadIdx.x = 0;
+                RS_DECLARE_STACK(stack);
+                occ[shadowList[k]] = giQShadowOf(s, giLoadPath(q, shadowList[k]), stack);
+            }
+#pragma omp parallel for schedule(dynamic, 16)
+            for (long long k = 0; k < nc; k++) {
+                threadIdx.x = 0;
+                RS_DECLARE_STACK(stack);
+                RS_DECLARE_PACKET(pk, 1);
+                (void)pk_tb; (void)pk_wst;
+                hit[closestList[k]] = giQClosestOf(s, g, giLoadPath(q, closestList[k]), stack, pk_ta);
+            }
+#pragma omp parallel for schedule(dynamic, 16)
+            for (long long i = 0; i < np; i++) {
+                threadIdx.x = 0;
+                const GIPathRec in = giLoadPath(q, (size_t)i);
+                const int flags = __float_as_int(in.d.w);
+                GIPathRec rec;
+                int x, y;
+                const int r = giQTail(s, d, g, depth, in, (flags & GI_Q_SHADOW) ? occ[i] : 0, (flags & GI_Q_ALIVE) ? hit[i] : make_float4(0.f, 0.f, 0.f, 0.f), rec, x, y);
+                giAppendPath(g.pathQ[depth & 1], g.pathCount + depth + 1, r == 1, rec);
+            }
+        }
+        for (int depth = 1; tracedTree == 2 && depth <= traceDepth; depth++) {
             const long long np = counts[depth];
 #pragma omp parallel for schedule(dynamic, 16)
             for (long long i = 0; i < np; i++) {

@@ -54,19 +54,40 @@ def test_gi_device_code_traced_tree_matches_oracle(emu, port_oracle, name):
     helpers.assert_frames_equal(exact, want, "device code, reference-order walk, vs oracle")
     helpers.assert_frames_equal(traced, want, "device code, traced tree, vs oracle")
     helpers.assert_frames_equal(staged, want, "device code, staged pipeline (k_gi_primary / k_gi_bounce / k_gi_resolve bodies), vs oracle")
+    queued, undecided_queued = emu.run_gi(sd, 4, 5, 1, accumulate=True, staged=2)
+    helpers.assert_frames_equal(queued, want, "device code, ray-queue pipeline (k_gi_head / walks / k_gi_tail bodies), vs oracle")
+    assert undecided_queued <= undecided
     if name == "gen20k":
         assert undecided > 0            # the fix-up path was exercised
         assert undecided_staged == undecided
     assert (want[-1]["indirect"].sum(1) > 0).mean() > 0.2
 
 
+@pytest.mark.parametrize("staged", [True, 2])
 @pytest.mark.parametrize("depth,reuse", [(0, 1), (1, 0), (2, 1)])
-def test_gi_staged_device_code_shallow_depths(emu, port_oracle, depth, reuse):
+def test_gi_staged_device_code_shallow_depths(emu, port_oracle, depth, reuse, staged):
     """The staged bodies at depth 0 (no path leaves k_gi_primary), 1 (paths end in their first bounce) and 2, with and without history."""
     sd = dataclasses.replace(helpers.gi_scenes()["cornell_metal"], resolution=(96, 72))
     want = helpers.run_oracle_gi(port_oracle, sd, 3, depth, reuse, accumulate=True)
-    got, _ = emu.run_gi(sd, 3, depth, reuse, accumulate=True, staged=True)
+    got, _ = emu.run_gi(sd, 3, depth, reuse, accumulate=True, staged=staged)
     helpers.assert_frames_equal(got, want, "staged device code, depth %d" % depth)
+
+
+@pytest.mark.parametrize("name", ["gen20k", "cornell_glass"])
+def test_gi_queued_kernels_as_warps_match_oracle(emu, port_oracle, name):
+    """The ray-queue pipeline's KERNELS (k_gi_head, k_gi_walk_shadow, k_gi_walk_closest, k_gi_tail, k_gi_resolve, k_restir_indirect_fix) run as
+    grids of 32-lane warps on the CPU (tests/emu/cuda_host_shim.h: lanes are fibers, warp intrinsics exchange their values): persistent warps
+    with lane refill from the ray lists, lanes waiting for each other at leaves, warp-aggregated appends -- same bits as the oracle."""
+    sd = {"gen20k": lambda: scenes.procedural(3, 20000, 1000, (160, 90)),
+          "cornell_glass": lambda: dataclasses.replace(helpers.gi_scenes()["cornell_glass"], resolution=(96, 72))}[name]()
+    want = helpers.run_oracle_gi(port_oracle, sd, 3, 4, 1, accumulate=True)
+    got, undecided = emu.run_gi(sd, 3, 4, 1, accumulate=True, staged=3)
+    helpers.assert_frames_equal(got, want, "ray-queue kernels as warps vs oracle")
+    staged, undecided_staged = emu.run_gi(sd, 3, 4, 1, accumulate=True, staged=4)
+    helpers.assert_frames_equal(staged, want, "staged kernels (k_gi_bounce) as warps vs oracle")
+    if name == "gen20k":
+        assert 0 < undecided <= undecided_staged          # the fix-up kernel ran on the queue the kernels wrote
+    assert (want[-1]["indirect"].sum(1) > 0).mean() > 0.2
 
 
 def test_gbuffer_device_code_matches_oracle(emu, port_oracle):

@@ -85,17 +85,20 @@ def test_gi_traced_tree_equals_reference_order_walk(gpu, name):
 @pytest.mark.parametrize("name,depth", [("cornell_glass", 4), ("cornell_tex", 3), ("gen20k", 5), ("cornell_metal", 1), ("cornell_metal", 0)])
 def test_gi_staged_pipeline_equals_one_kernel(gpu, name, depth):
     """GPU against GPU: k_gi_primary / k_gi_bounce per depth / k_gi_resolve (live paths compacted into queues between the bounces) write
-    the bits of k_restir_indirect -- every pixel draws its random numbers in the same order -- and queue the same pixels for the fix-up."""
+    the bits of k_restir_indirect -- every pixel draws its random numbers in the same order -- and queue the same pixels for the fix-up;
+    so does the ray-queue form (k_gi_head / k_gi_walk_shadow / k_gi_walk_closest / k_gi_tail per depth)."""
     sd = scenes.procedural(3, 20000, 1000, (320, 180)) if name == "gen20k" else dataclasses.replace(helpers.gi_scenes()[name], resolution=(320, 180))
     sc = gpu.Scene.from_arrays(sd)
     fused, fb = helpers.run_gpu_gi(gpu, sd, 4, depth, 1, scene=sc, accumulate=True, staged=False)
     staged, fb2 = helpers.run_gpu_gi(gpu, sd, 4, depth, 1, scene=sc, accumulate=True, staged=True)
     mixed, _ = helpers.run_gpu_gi(gpu, sd, 2, depth, 1, scene=sc, accumulate=True, staged=True, bounce_exact=True)
+    queued, fb3 = helpers.run_gpu_gi(gpu, sd, 4, depth, 1, scene=sc, accumulate=True, staged=2)
     sc.close()
-    _record("staged_%s_d%d" % (name, depth), {"fixup_pixels": fb, "fixup_pixels_staged": fb2, "lit": float((fused[-1]["indirect"].sum(1) > 0).mean())})
+    _record("staged_%s_d%d" % (name, depth), {"fixup_pixels": fb, "fixup_pixels_staged": fb2, "fixup_pixels_queued": fb3, "lit": float((fused[-1]["indirect"].sum(1) > 0).mean())})
     helpers.assert_frames_equal(staged, fused, "staged pipeline vs one kernel")
     helpers.assert_frames_equal(mixed, fused[:2], "staged pipeline, bounce rays on the reference tree, vs one kernel")
-    assert fb2 == fb
+    helpers.assert_frames_equal(queued, fused, "ray-queue pipeline (persistent walkers with lane refill) vs one kernel")
+    assert fb2 == fb                 # fb3 is recorded: the walkers visit a ray's nodes in traceClosestFast's order, so it is expected to be equal too
     if depth >= 3:
         assert (fused[-1]["indirect"].sum(1) > 0).mean() > 0.2
 
