@@ -410,11 +410,12 @@ int rstr_gi_indirect_device(RstrGI*, float** devIndirectIllum);                 
 /* which tree the bounce rays walk when the scene's traversal mode is the traced one: 0 the traced tree (default), 1 the reference tree in
  * the reference's order; the hits are the same either way (validation switch) */
 int rstr_gi_set_bounce_walk(RstrGI*, int traversal);
-/* how the frame is launched in the traced mode: a wavefront -- primary rays, one launch per iteration of the path loop over the compacted
- * live paths, resolve (staged, the default) -- or one kernel per frame (fused), or the staged form with the walks of every iteration as
- * kernels of their own over ray lists, persistent warps whose lanes fetch the next ray when they finish one (queued).  Same result bit for
- * bit; the environment variable RSTR_GI_PIPELINE=fused|staged|queued sets the default of new handles (A/B measurements). */
-enum { RSTR_GI_PIPELINE_FUSED = 0, RSTR_GI_PIPELINE_STAGED = 1, RSTR_GI_PIPELINE_QUEUED = 2 };
+/* how the frame is launched in the traced mode: one kernel per frame (fused); a wavefront -- primary rays, one launch per iteration of
+ * the path loop over the compacted live paths, resolve (staged); the staged form with the walks of every iteration as kernels of their own
+ * over ray lists, persistent warps whose lanes fetch the next ray when they finish one (queued); or queued on real scenes and staged on
+ * tiny ones (auto, the default: the rule of the direct path's pipelines).  Same result bit for bit in every form; the environment
+ * variable RSTR_GI_PIPELINE=fused|staged|queued|auto sets the default of new handles (A/B measurements). */
+enum { RSTR_GI_PIPELINE_FUSED = 0, RSTR_GI_PIPELINE_STAGED = 1, RSTR_GI_PIPELINE_QUEUED = 2, RSTR_GI_PIPELINE_AUTO = 3 };
 int rstr_gi_set_pipeline(RstrGI*, int pipeline);
 int rstr_gi_fallback_pixels(RstrGI*, unsigned int* count, int reset);              /* pixels recomputed with the reference-order walk */
 

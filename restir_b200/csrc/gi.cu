@@ -21,7 +21,7 @@ struct RstrGI {
     int out = 0;                               // which of resv[] is devIndTemporalReservoir (written by the next call)
     bool first = true;                         // ReSTIRFirstFrame
     int bounceWalk = RS_TRAVERSAL_FAST;
-    int pipeline = RSTR_GI_PIPELINE_STAGED;       // measured faster on every bench scene (profiles/r02_c34_gi_bench.jsonl)
+    int pipeline = RSTR_GI_PIPELINE_AUTO;
     // staged pipeline (allocated on first use): per-pixel hand-over planes, pixel status, two path queues, per-depth path counts
     float4* pix = nullptr;
     int* pixStatus = nullptr;
@@ -69,6 +69,7 @@ int rstr_gi_create(RstrFrame* f, RstrGI** out) {
         if (!strcmp(env, "staged")) g->pipeline = RSTR_GI_PIPELINE_STAGED;
         else if (!strcmp(env, "fused")) g->pipeline = RSTR_GI_PIPELINE_FUSED;
         else if (!strcmp(env, "queued")) g->pipeline = RSTR_GI_PIPELINE_QUEUED;
+        else if (!strcmp(env, "auto")) g->pipeline = RSTR_GI_PIPELINE_AUTO;
     }
     *out = g;
     return RSTR_OK;
@@ -94,7 +95,7 @@ int rstr_gi_set_bounce_walk(RstrGI* g, int traversal) {
 }
 
 int rstr_gi_set_pipeline(RstrGI* g, int pipeline) {
-    if (!g || (pipeline != RSTR_GI_PIPELINE_FUSED && pipeline != RSTR_GI_PIPELINE_STAGED && pipeline != RSTR_GI_PIPELINE_QUEUED)) return rsFail(RSTR_ERR_ARG, "rstr_gi_set_pipeline: bad argument");
+    if (!g || (pipeline < RSTR_GI_PIPELINE_FUSED || pipeline > RSTR_GI_PIPELINE_AUTO)) return rsFail(RSTR_ERR_ARG, "rstr_gi_set_pipeline: bad argument");
     g->pipeline = pipeline;
     return RSTR_OK;
 }
@@ -149,12 +150,17 @@ int rstr_restir_indirect(RstrGI* g, const RstrCamera* cam, int looper, int iter,
     gd.fallback = g->fallback;
     gd.maxDepth = traceDepth; gd.reuse = reuse; gd.first = g->first ? 1 : 0; gd.iter = iter;
     gd.bounceWalk = g->bounceWalk;
-    if (g->pipeline != RSTR_GI_PIPELINE_FUSED && f->sc->dev.traversal != RS_TRAVERSAL_EXACT) {    // the validation mode has one form
+    // auto: like the direct path's rule (capi.cu): the ray-queue form pays for its extra launches once rays diverge, i.e. on real scenes
+    // (200 k / 1 M triangles: 4.27 / 3.58 ms against 4.90 / 3.87 staged); a Cornell box is faster staged (0.88 against 1.07 ms).
+    // profiles/r02_c35_gi_bench.jsonl
+    const int pipeline = g->pipeline != RSTR_GI_PIPELINE_AUTO ? g->pipeline
+                         : f->sc->dev.numFastNodes > 1024 ? RSTR_GI_PIPELINE_QUEUED : RSTR_GI_PIPELINE_STAGED;
+    if (pipeline != RSTR_GI_PIPELINE_FUSED && f->sc->dev.traversal != RS_TRAVERSAL_EXACT) {       // the validation mode has one form
         int rc = giEnsureStaged(g);
         if (rc) return rc;
         gd.pix = g->pix; gd.pixStatus = g->pixStatus; gd.pathQ[0] = g->pathQ[0]; gd.pathQ[1] = g->pathQ[1]; gd.pathCount = g->pathCount;
         gd.pixStride = (size_t)g->W * g->H;
-        if (g->pipeline == RSTR_GI_PIPELINE_QUEUED && g->bounceWalk == RS_TRAVERSAL_FAST) {      // the walkers walk the traced tree
+        if (pipeline == RSTR_GI_PIPELINE_QUEUED && g->bounceWalk == RS_TRAVERSAL_FAST) {      // the walkers walk the traced tree
             rc = giEnsureQueued(g);
             if (rc) return rc;
             gd.closestList = g->closestList; gd.shadowList = g->shadowList; gd.walkCount = g->walkCount; gd.hit = g->hit; gd.occ = g->occ;
