@@ -530,7 +530,12 @@ RS_D bool prayResolve(const DevScene& s, f3 o, f3 dir, const PRay& p, const TieS
 // The warp's stack lives in shared memory and is addressed through ONE 32-bit shared-space cursor (8-byte entries {node, entry
 // distance bits}); every lane stores the same entry (same value, same address).
 RS_D void wsPush(unsigned& cursor, int ref, unsigned key) {
+#ifdef RS_HOST_EMU      /* tests/emu: a "shared-space address" is an offset from the emulation's anchor */
+    int* p = (int*)emuSharedPtr(cursor);
+    p[0] = ref; p[1] = (int)key;
+#else
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(cursor), "r"(ref), "r"(key) : "memory");
+#endif
     cursor += 8;
 }
 // next stacked node that is not beyond every lane's limit; the bottom entry is a sentinel {RS_DONE, distance 0} that always
@@ -540,7 +545,12 @@ RS_D int wsPop(unsigned& cursor, float wlimit) {
         cursor -= 8;
         int ref;
         unsigned key;
+#ifdef RS_HOST_EMU
+        const int* p = (const int*)emuSharedPtr(cursor);
+        ref = p[0]; key = (unsigned)p[1];
+#else
         asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(ref), "=r"(key) : "r"(cursor) : "memory");
+#endif
         if (__uint_as_float(key) <= wlimit) return ref;
     }
 }
@@ -552,13 +562,21 @@ RS_D unsigned stackAddr(const Stack& st) {
     return a;
 }
 RS_D void stackPush(unsigned addr, Stack& st, int sp, int ref) {
+#ifdef RS_HOST_EMU
+    if (sp < RS_SMEM_STACK) *(int*)emuSharedPtr(addr + (unsigned)sp * (RS_BLOCK * 4u)) = ref;
+#else
     if (sp < RS_SMEM_STACK) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr + (unsigned)sp * (RS_BLOCK * 4u)), "r"(ref) : "memory");
+#endif
     else st.lRef[sp - RS_SMEM_STACK] = ref;
 }
 RS_D int stackRef(unsigned addr, const Stack& st, int sp) {
     if (sp < RS_SMEM_STACK) {
         int ref;
+#ifdef RS_HOST_EMU
+        ref = *(const int*)emuSharedPtr(addr + (unsigned)sp * (RS_BLOCK * 4u));
+#else
         asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ref) : "r"(addr + (unsigned)sp * (RS_BLOCK * 4u)) : "memory");
+#endif
         return ref;
     }
     return st.lRef[sp - RS_SMEM_STACK];

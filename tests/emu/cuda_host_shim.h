@@ -52,15 +52,38 @@ static inline long long clock64() { return 0; }
 static inline void __syncthreads() {}
 static inline void __trap() { abort(); }
 // ---- warps.  Outside emuRunWarp a "warp" has one lane (the per-pixel emulation: one call = one thread).  Inside emuRunWarp the 32 lanes of
-// a warp are 32 fibers (ucontext) on one OS thread: a lane runs until its next warp-level intrinsic, deposits its value and yields; when
+// a warp are 32 fibers (own stacks, switched by hand) on one OS thread: a lane runs until its next warp-level intrinsic, deposits its value and yields; when
 // every live lane has deposited, the lanes are resumed in turn and combine the values.  All lanes of convergent code reach the same
 // sequence of intrinsics, so pass k of the scheduler is synchronisation point k of every lane; the deposits are double-buffered by the
 // parity of k (a resumed lane may reach point k + 1 and deposit again before its neighbours have read point k).  Lanes that have
 // returned from the kernel contribute 0 / are skipped, as exited threads do on the GPU.
-#include <ucontext.h>
 #define EMU_FIBER_STACK (512 * 1024)
+#if defined(__x86_64__)
+// switch stacks: callee-saved registers of the System V ABI on the old stack, its pointer to *from, the same from `to` (swapcontext costs
+// a sigprocmask system call per switch, and a packet walk synchronises its lanes a dozen times per node)
+typedef void* EmuCtx;
+__attribute__((naked, noinline)) static void emuSwitch(EmuCtx* from, EmuCtx to) {
+    asm volatile(
+        "pushq %rbp\n\tpushq %rbx\n\tpushq %r12\n\tpushq %r13\n\tpushq %r14\n\tpushq %r15\n\t"
+        "movq %rsp, (%rdi)\n\t"
+        "movq %rsi, %rsp\n\t"
+        "popq %r15\n\tpopq %r14\n\tpopq %r13\n\tpopq %r12\n\tpopq %rbx\n\tpopq %rbp\n\t"
+        "ret\n\t");
+}
+static inline void emuMakeCtx(EmuCtx* ctx, char* stack, size_t size, void (*entry)()) {
+    void** sp = (void**)(((size_t)stack + size) & ~(size_t)15);
+    *--sp = nullptr;                             // the entry's "return address": it never returns
+    *--sp = (void*)entry;                        // popped by the first switch's ret: entry runs with rsp + 8 aligned to 16, as after a call
+    for (int i = 0; i < 6; i++) *--sp = nullptr; // rbp rbx r12 r13 r14 r15
+    *ctx = sp;
+}
+#else
+#include <ucontext.h>
+typedef ucontext_t EmuCtx;
+static inline void emuSwitch(EmuCtx* from, EmuCtx& to) { swapcontext(from, &to); }
+#endif
 struct EmuWarp {
-    ucontext_t sched, ctx[32];
+    EmuCtx sched, ctx[32];
     bool done[32];
     int lane;                                    // the lane that is running
     unsigned sync[32];                           // synchronisation points passed, per lane
@@ -78,7 +101,7 @@ static inline const unsigned long long* emuExchange(unsigned long long mine) {
     const unsigned k = w->sync[l]++ & 1u;
     w->val[k][l] = mine;
     w->has[k][l] = true;
-    swapcontext(&w->ctx[l], &w->sched);
+    emuSwitch(&w->ctx[l], w->sched);
     return emuWarp->val[k];
 }
 static void emuTrampoline() {
@@ -91,6 +114,9 @@ static void emuTrampoline() {
     const unsigned next = w->sync[l] & 1u;
     w->done[l] = true;
     w->val[next][l] = 0; w->has[next][l] = false;
+#if defined(__x86_64__)
+    for (;;) emuSwitch(&w->ctx[l], w->sched);    // never resumed: the scheduler skips finished lanes
+#endif
 }
 // run `body(arg)` as the 32 lanes tidBase .. tidBase + 31 of one warp; blockIdx / blockDim / gridDim are the caller's
 static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg);
@@ -162,7 +188,11 @@ static inline unsigned __match_any_sync(unsigned, unsigned) { return 1u; }      
 static inline unsigned __activemask() { return 1u; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
-static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+// "shared-space addresses" (the kernels keep some as 32-bit cursors): offsets from a per-thread anchor; __shared__ arrays are thread_local
+// statics of the same module, so the offsets fit 32 bits
+static thread_local char emuSharedAnchor;
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)(unsigned)(int)((const char*)p - &emuSharedAnchor); }
+static inline void* emuSharedPtr(unsigned off) { return &emuSharedAnchor + (long)(int)off; }
 
 
 static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) {
@@ -171,11 +201,15 @@ static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) 
     memset(w.done, 0, sizeof w.done); memset(w.sync, 0, sizeof w.sync); memset(w.val, 0, sizeof w.val); memset(w.has, 0, sizeof w.has);
     w.body = body; w.arg = arg; w.lane = 0;
     for (int l = 0; l < 32; l++) {
+#if defined(__x86_64__)
+        emuMakeCtx(&w.ctx[l], emuStacks + (size_t)l * EMU_FIBER_STACK, EMU_FIBER_STACK, emuTrampoline);
+#else
         getcontext(&w.ctx[l]);
         w.ctx[l].uc_stack.ss_sp = emuStacks + (size_t)l * EMU_FIBER_STACK;
         w.ctx[l].uc_stack.ss_size = EMU_FIBER_STACK;
         w.ctx[l].uc_link = &w.sched;
         makecontext(&w.ctx[l], emuTrampoline, 0);
+#endif
     }
     emuWarp = &w;
     for (;;) {
@@ -185,7 +219,7 @@ static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) 
                 any = true;
                 w.lane = l;
                 threadIdx.x = tidBase + l;
-                swapcontext(&w.sched, &w.ctx[l]);
+                emuSwitch(&w.sched, w.ctx[l]);
             }
         if (!any) break;
         for (int l = 0; l < 32; l++)

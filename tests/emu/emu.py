@@ -34,6 +34,16 @@ class Emu:
         L.emu_gi_reservoirs.argtypes = [vp]
         L.emu_frame_plane.restype = vp
         L.emu_frame_plane.argtypes = [vp, ip]
+        L.emu_di_create.restype = vp
+        L.emu_di_create.argtypes = [vp, ip, ip]
+        L.emu_di_destroy.argtypes = [vp]
+        L.emu_di_frame.argtypes = [vp, C.POINTER(api.RstrCamera), C.POINTER(api.RstrParams), ip, ip, ip, ip]
+        L.emu_di_ptdirect.argtypes = [vp, C.POINTER(api.RstrCamera), ip, ip]
+        L.emu_di_update.argtypes = [vp, C.POINTER(api.RstrCamera)]
+        L.emu_di_fixup_pixels.restype = C.c_uint
+        L.emu_di_fixup_pixels.argtypes = [vp]
+        L.emu_di_buffer.restype = vp
+        L.emu_di_buffer.argtypes = [vp, ip]
 
     def scene(self, sd):
         v = np.ascontiguousarray(sd.vertices, np.float32)
@@ -83,3 +93,38 @@ class Emu:
         L.emu_frame_destroy(fr)
         L.emu_scene_destroy(sc)
         return out, und
+
+    DI_BUF = {"albedo": (0, np.float32, 3), "normal": (1, np.float32, 3), "matid": (2, np.int32, 0), "depth": (3, np.float32, 0), "motion": (4, np.int32, 0),
+              "radiance": (5, np.float32, 3), "reservoir": (6, None, 0), "reservoir_temp": (7, None, 0), "light_index": (8, np.int32, 0)}
+
+    def run_di(self, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=None, passes=1, drain=True, light_index=False, pipeline=0, unbiased=False, ptdirect=False, looper0=0):
+        """The frame loop of helpers.run_gpu with the staged pipeline's KERNELS run as 32-lane warps on the CPU (emu_di_frame).  Returns
+        (frames, fix-up pixels of the last frame)."""
+        from oracle.oracle import RESERVOIR_DTYPE
+
+        W, H = sd.resolution
+        L = self.lib
+        sc = self.scene(sd)
+        fr = L.emu_di_create(sc, W, H)
+        base = api.Camera.from_scene(sd)
+        prm = api.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates, passes=passes, unbiased=unbiased)
+        names = list(want or ("albedo", "normal", "matid", "depth", "motion", "radiance", "reservoir", "reservoir_temp")) + (["light_index"] if light_index else [])
+        out = []
+        fix = 0
+        for f in range(frames):
+            cam = base.orbit(f) if orbit else base
+            if ptdirect:
+                L.emu_di_ptdirect(fr, C.byref(cam), looper0 + f, f if accumulate else 0)
+            else:
+                L.emu_di_frame(fr, C.byref(cam), C.byref(prm), looper0 + f, f if accumulate else 0, 1 if drain else 0, pipeline)
+            fix = int(L.emu_di_fixup_pixels(fr))
+            d = {}
+            for n in names:
+                which, dt, comps = self.DI_BUF[n]
+                ptr = L.emu_di_buffer(fr, which)
+                d[n] = self._view(ptr, RESERVOIR_DTYPE, (W * H,)) if dt is None else self._view(ptr, dt, (W * H, comps) if comps else (W * H,))
+            out.append(d)
+            L.emu_di_update(fr, C.byref(cam))
+        L.emu_di_destroy(fr)
+        L.emu_scene_destroy(sc)
+        return out, fix

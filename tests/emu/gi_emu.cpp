@@ -139,7 +139,7 @@ void emu_gbuffer_update(void* fv, const RstrCamera* cam) {
 }
 void emu_gi_reset(void* fv) { ((EmuFrame*)fv)->first = true; }
 
-// rstr_restir_indirect.  tracedTree = 2 / 3: the staged / ray-queue pipeline's bodies; 4 / 5: the ray-queue / staged pipeline's kernels as warps (below).  tracedTree = 0: k_restir_indirect_exact's body per pixel.  tracedTree = 1: the primary hit from the reference-order
+// rstr_restir_indirect.  tracedTree = 2 / 3: the staged / ray-queue pipeline's bodies; 4 / 5 / 6: the ray-queue / staged / one-kernel form's KERNELS as warps (below).  tracedTree = 0: k_restir_indirect_exact's body per pixel.  tracedTree = 1: the primary hit from the reference-order
 // walk (standing in for the packet walk), then giAfterHit<false>: bounce rays through traceClosestFast, shadow rays through
 // traceOccludedFast; an undecided pixel is recomputed like k_restir_indirect_fix does.
 void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, int traceDepth, int reuse, int tracedTree) {
@@ -153,6 +153,16 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
     g.indirect = f->indirect.data(); g.fallback = nullptr;
     g.maxDepth = traceDepth; g.reuse = reuse; g.first = f->first ? 1 : 0; g.iter = iter; g.bounceWalk = RS_TRAVERSAL_FAST;
     unsigned long long undecided = 0;
+    if (tracedTree == 6) {                                           // the one-kernel form as warps: k_restir_indirect (packet walk included) + fix-up
+        f->queueCount[0] = 0;
+        emuLaunch((unsigned)((f->W + 15) / 16), (unsigned)((f->H + 7) / 8), [&] { k_restir_indirect(s, d, c, g, looper); });
+        undecided = f->queueCount[0];
+        emuLaunch(2, 1, [&] { k_restir_indirect_fix(s, d, c, g, looper); });
+        f->undecided += undecided;
+        f->out ^= 1;
+        f->first = false;
+        return;
+    }
     if (tracedTree >= 2) {
         // the staged form: giStagePrimary per pixel (primary hit from the reference-order walk, as above), giStageBounce per live path and depth
         // through the queues, giStageResolve per pixel, marked pixels like k_restir_indirect_fix.  One-lane "warps": giAppendPath appends one record.
@@ -161,8 +171,11 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
         std::vector<int> status(n, 0);
         std::vector<unsigned int> counts(traceDepth + 2, 0u);
         g.pix = pix.data(); g.pixStatus = status.data(); g.pathQ[0] = q0.data(); g.pathQ[1] = q1.data(); g.pathCount = counts.data(); g.pixStride = n;
+        f->queueCount[0] = 0;
+        if (tracedTree >= 4)                                         // kernel-level modes: the real k_gi_primary (packet walk of the jittered rays)
+            emuLaunch((unsigned)((f->W + 15) / 16), (unsigned)((f->H + 7) / 8), [&] { k_gi_primary(s, d, c, g, looper); });
 #pragma omp parallel for schedule(dynamic, 4)
-        for (int y = 0; y < f->H; y++)
+        for (int y = 0; y < (tracedTree >= 4 ? 0 : f->H); y++)
             for (int x = 0; x < f->W; x++) {
                 threadIdx.x = 0;
                 RS_DECLARE_STACK(stack);
@@ -179,7 +192,6 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
         // tracedTree == 4: the ray-queue form's KERNELS (k_gi_head, k_gi_walk_shadow, k_gi_walk_closest, k_gi_tail, k_gi_resolve,
         // k_restir_indirect_fix) as grids of 32-lane warps (emuLaunch): lane refill, leaf wait, warp-aggregated appends and all
         if (tracedTree == 5) {                                       // the staged form's kernels as warps: k_gi_bounce per depth, k_gi_resolve, fix-up
-            f->queueCount[0] = 0;
             const unsigned blocks = (unsigned)((n + RS_BLOCK - 1) / RS_BLOCK);
             for (int depth = 1; depth <= traceDepth; depth++) emuLaunch(blocks, 1, [&] { k_gi_bounce(s, d, g, depth); });
             emuLaunch((unsigned)((f->W + 15) / 16), (unsigned)((f->H + 7) / 8), [&] { k_gi_resolve(d, g); });
@@ -195,7 +207,6 @@ void emu_restir_indirect(void* fv, const RstrCamera* cam, int looper, int iter, 
             std::vector<float4> hit(n);
             std::vector<int> occ(n);
             g.closestList = cl.data(); g.shadowList = sl.data(); g.walkCount = wc.data(); g.hit = hit.data(); g.occ = occ.data();
-            f->queueCount[0] = 0;
             const unsigned blocks = (unsigned)((n + RS_BLOCK - 1) / RS_BLOCK);
             for (int depth = 1; depth <= traceDepth; depth++) {
                 emuLaunch(blocks, 1, [&] { k_gi_head(s, d, g, depth); });
@@ -325,6 +336,183 @@ const float* emu_gi_reservoirs(void* fv) {
 const void* emu_frame_plane(void* fv, int which) {                   // 0 geom {n, depth}, 1 matId, 2 {albedo, motion} of the current frame
     EmuFrame* f = (EmuFrame*)fv;
     return which == 0 ? (const void*)f->geom[f->cur].data() : which == 1 ? (const void*)f->matId[f->cur].data() : (const void*)f->albedoMotion.data();
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ the direct path's kernels as warps
+// One frame of the staged pipeline the way launchPhaseAStaged / launchRestirB (kernels.cu) and rstr_restir_phase_a / _b (capi.cu) run it:
+// k_primary (packet walk of the centre + jittered rays of every 8x4 tile: G-buffer and the shaded-pixel queue), k_candidates, k_shadow
+// (persistent, lane refill, cooperative drain), k_temporal, the fix-up kernel, k_restir_b per spatial pass, and the export kernels --
+// each launched with emuLaunch as a grid of 32-lane warps.
+struct EmuDI {
+    EmuScene* sc;
+    DevScene dev;
+    int W, H;
+    std::vector<float4> geom[2], albedoMotion;
+    std::vector<int> matId[2], queue, shadeQueue;
+    std::vector<float> radiance, export36;
+    std::vector<ResvD> resv[2], resvTemp, resvTemp2;
+    std::vector<HitRec> hit;
+    std::vector<float2> hitMR;
+    std::vector<float4> hitPos;                  // unbiased mode
+    std::vector<int> exportI;
+    unsigned int queueCount[4 + 2 * RS_MAX_BANDS];
+    unsigned int counters[4] = {0, 0, 0, 0};
+    int cur = 0, resvOut = 0;
+    bool first = true, haveLast = false, temp2Ready = false;
+    RstrCamera lastCamera{};
+};
+static FrameDev diFrameDev(EmuDI* f) {                              // rsToFrameDev (capi.cu)
+    FrameDev d{};
+    d.W = f->W; d.H = f->H; d.rowLo = 0; d.rowHi = f->H; d.bufRow0 = 0; d.bufRows = f->H;
+    d.geom[0] = f->geom[f->cur].data(); d.geom[1] = f->geom[f->cur ^ 1].data();
+    d.matId[0] = f->matId[f->cur].data(); d.matId[1] = f->matId[f->cur ^ 1].data();
+    d.albedoMotion = f->albedoMotion.data(); d.radiance = f->radiance.data();
+    d.resvOut = f->resv[f->resvOut].data(); d.resvIn = f->resv[f->resvOut ^ 1].data(); d.resvTemp = f->resvTemp.data();
+    d.hit = f->hit.data(); d.hitMR = f->hitMR.empty() ? nullptr : f->hitMR.data(); d.hitPos = f->hitPos.empty() ? nullptr : f->hitPos.data();
+    d.haloMiss = f->counters; d.motionRows = f->counters + 1;
+    d.queue = f->queue.data(); d.queueCount = f->queueCount; d.shadeQueue = f->shadeQueue.data();
+    return d;
+}
+
+extern "C" {
+
+void* emu_di_create(void* scv, int W, int H) {
+    EmuDI* f = new EmuDI;
+    f->sc = (EmuScene*)scv; f->dev = f->sc->dev; f->dev.traversal = RS_TRAVERSAL_FAST;
+    f->W = W; f->H = H;
+    const size_t n = (size_t)W * H;
+    ResvD zr;
+    memset(&zr, 0, sizeof zr);
+    zr.lightId = -1;                                                 // rstr_frame_create: a zero-filled reference reservoir has no sample
+    HitRec zh;
+    memset(&zh, 0, sizeof zh);
+    for (int i = 0; i < 2; i++) { f->geom[i].assign(n, make_float4(0, 0, 0, 0)); f->matId[i].assign(n, 0); f->resv[i].assign(n, zr); }
+    f->albedoMotion.assign(n, make_float4(0, 0, 0, 0));
+    f->radiance.assign(3 * n, 0.f);
+    f->resvTemp.assign(n, zr); f->resvTemp2.assign(n, zr);
+    f->hit.assign(n, zh);
+    if (f->sc->hs.anyMRMaps) f->hitMR.assign(n, make_float2(0.f, 0.f));
+    f->queue.assign(n, 0); f->shadeQueue.assign(n, 0);
+    memset(f->queueCount, 0, sizeof f->queueCount);
+    return f;
+}
+void emu_di_destroy(void* f) { delete (EmuDI*)f; }
+
+// rstr_gbuffer_render + rstr_restir_direct.  pipeline 0: staged (launchPhaseAStaged), 1: fused (launchGBufferRestirA), 2: split (launchGBuffer,
+// launchRestirA), 3: split with every ray in the reference's order (RS_TRAVERSAL_EXACT: k_gbuffer_exact, k_restir_a_exact)
+void emu_di_frame(void* fv, const RstrCamera* cam, const RstrParams* prm, int looper, int iter, int drain, int pipeline) {
+    EmuDI* f = (EmuDI*)fv;
+    const DevScene& s = f->dev;
+    const RstrParams p = *prm;
+    const CamDev c = toCamDev(*cam), lc = toCamDev(f->haveLast ? f->lastCamera : *cam);
+    const bool sp = (p.reuse & 2) != 0;
+    const int first = f->first ? 1 : 0;
+    if (p.unbiased && f->hitPos.empty()) f->hitPos.assign((size_t)f->W * f->H, make_float4(0, 0, 0, 0));      // rstr_restir_phase_a
+    FrameDev d = diFrameDev(f);
+    d.resvStage = f->resvTemp.data();
+    memset(f->queueCount, 0, sizeof f->queueCount);
+    d.shadeCount = f->queueCount + 4;
+    const unsigned gx = (unsigned)((f->W + 15) / 16), gy = (unsigned)((f->H + 7) / 8), linear = gx * gy;
+    if (pipeline == 0) {
+        d.resvStage = sp ? f->resvTemp.data() : f->resvTemp2.data();
+        if (!sp) f->temp2Ready = false;
+        if (sp) emuLaunch(gx, gy, [&] { k_primary<true>(s, d, c, lc, looper, iter); });
+        else emuLaunch(gx, gy, [&] { k_primary<false>(s, d, c, lc, looper, iter); });
+        emuLaunch(linear, 1, [&] { k_candidates(s, d, c, p, looper); });
+        if (!p.unbiased) {
+            if (drain) emuLaunch(3, 1, [&] { k_shadow<true>(s, d); });
+            else emuLaunch(3, 1, [&] { k_shadow<false>(s, d); });
+        }
+        if (p.unbiased) {
+            if (sp) emuLaunch(linear, 1, [&] { k_temporal_unb<true>(s, d, p, iter, first); });
+            else emuLaunch(linear, 1, [&] { k_temporal_unb<false>(s, d, p, iter, first); });
+        } else if (sp) emuLaunch(linear, 1, [&] { k_temporal<true>(s, d, p, iter, first); });
+        else emuLaunch(linear, 1, [&] { k_temporal<false>(s, d, p, iter, first); });
+        if (sp) emuLaunch(2, 1, [&] { k_gbuffer_restir_a_fix<true>(s, d, c, lc, p, looper, iter, first); });
+        else emuLaunch(2, 1, [&] { k_gbuffer_restir_a_fix<false>(s, d, c, lc, p, looper, iter, first); });
+    } else if (pipeline == 1) {
+        if (sp) {
+            emuLaunch(gx, gy, [&] { k_gbuffer_restir_a<true>(s, d, c, lc, p, looper, iter, first); });
+            emuLaunch(2, 1, [&] { k_gbuffer_restir_a_fix<true>(s, d, c, lc, p, looper, iter, first); });
+        } else {
+            emuLaunch(gx, gy, [&] { k_gbuffer_restir_a<false>(s, d, c, lc, p, looper, iter, first); });
+            emuLaunch(2, 1, [&] { k_gbuffer_restir_a_fix<false>(s, d, c, lc, p, looper, iter, first); });
+        }
+    } else if (pipeline == 2) {
+        emuLaunch(gx, gy, [&] { k_gbuffer(s, d, c, lc); });
+        emuLaunch(2, 1, [&] { k_gbuffer_fix(s, d, c, lc); });
+        f->queueCount[0] = 0;
+        if (sp) {
+            emuLaunch(gx, gy, [&] { k_restir_a<true>(s, d, c, p, looper, iter, first); });
+            emuLaunch(2, 1, [&] { k_restir_a_fix<true>(s, d, c, p, looper, iter, first); });
+        } else {
+            emuLaunch(gx, gy, [&] { k_restir_a<false>(s, d, c, p, looper, iter, first); });
+            emuLaunch(2, 1, [&] { k_restir_a_fix<false>(s, d, c, p, looper, iter, first); });
+        }
+    } else {
+        emuLaunch(gx, gy, [&] { k_gbuffer_exact(s, d, c, lc); });
+        if (sp) emuLaunch(gx, gy, [&] { k_restir_a_exact<true>(s, d, c, p, looper, iter, first); });
+        else emuLaunch(gx, gy, [&] { k_restir_a_exact<false>(s, d, c, p, looper, iter, first); });
+    }
+    const int passes = sp ? (p.spatialPasses < 1 ? 1 : p.spatialPasses) : 0;
+    for (int pass = 1; pass <= passes; pass++) {                      // rstr_restir_phase_b_pass
+        if (passes > 1 && !f->temp2Ready) { f->resvTemp2 = f->resvTemp; f->temp2Ready = true; }
+        ResvD* buf[2] = {f->resvTemp.data(), f->resvTemp2.data()};
+        const ResvD* src = buf[(pass - 1) & 1];
+        ResvD* dst = buf[pass & 1];
+        const int last = pass == passes ? 1 : 0;
+        if (p.unbiased) emuLaunch(gx, gy, [&] { k_restir_b_unb(s, d, p, iter, src, dst, pass, last); });
+        else emuLaunch(gx, gy, [&] { k_restir_b(s, d, p, iter, src, dst, pass, last); });
+    }
+    f->resvOut ^= 1;
+    f->first = false;
+}
+// rstr_gbuffer_render + rstr_pathtrace_direct (launchGBuffer, launchPTDirect)
+void emu_di_ptdirect(void* fv, const RstrCamera* cam, int looper, int iter) {
+    EmuDI* f = (EmuDI*)fv;
+    const DevScene& s = f->dev;
+    const CamDev c = toCamDev(*cam), lc = toCamDev(f->haveLast ? f->lastCamera : *cam);
+    FrameDev d = diFrameDev(f);
+    const unsigned gx = (unsigned)((f->W + 15) / 16), gy = (unsigned)((f->H + 7) / 8);
+    memset(f->queueCount, 0, sizeof f->queueCount);
+    emuLaunch(gx, gy, [&] { k_gbuffer(s, d, c, lc); });
+    emuLaunch(2, 1, [&] { k_gbuffer_fix(s, d, c, lc); });
+    f->queueCount[0] = 0;
+    emuLaunch(gx, gy, [&] { k_ptdirect(s, d, c, looper, iter); });
+    emuLaunch(2, 1, [&] { k_ptdirect_fix(s, d, c, looper, iter); });
+}
+void emu_di_update(void* fv, const RstrCamera* cam) {
+    EmuDI* f = (EmuDI*)fv;
+    f->lastCamera = *cam; f->haveLast = true; f->cur ^= 1;
+}
+unsigned emu_di_fixup_pixels(void* fv) { return ((EmuDI*)fv)->queueCount[0]; }
+// rstr_frame_read: 0 albedo 1 normal 2 matid 3 depth 4 motion 5 radiance 6 reservoir 7 reservoir_temp 8 light_index
+const void* emu_di_buffer(void* fv, int which) {
+    EmuDI* f = (EmuDI*)fv;
+    const size_t n = (size_t)f->W * f->H;
+    const unsigned blocks = (unsigned)((n + RS_BLOCK - 1) / RS_BLOCK);
+    const float4* g = f->geom[f->cur].data();
+    const float4* am = f->albedoMotion.data();
+    if (which == 5) return f->radiance.data();
+    if (which == 2) return f->matId[f->cur].data();
+    f->export36.resize(9 * n); f->exportI.resize(n);
+    float* of = f->export36.data();
+    int* oi = f->exportI.data();
+    const DevScene& s = f->dev;
+    const ResvD* hist = f->resv[f->resvOut ^ 1].data();
+    const ResvD* temp = f->resvTemp.data();
+    switch (which) {
+    case 0: emuLaunch(blocks, 1, [&] { k_export_geom(g, am, of, nullptr, nullptr, nullptr, n); }); return of;
+    case 1: emuLaunch(blocks, 1, [&] { k_export_geom(g, am, nullptr, of, nullptr, nullptr, n); }); return of;
+    case 3: emuLaunch(blocks, 1, [&] { k_export_geom(g, am, nullptr, nullptr, of, nullptr, n); }); return of;
+    case 4: emuLaunch(blocks, 1, [&] { k_export_geom(g, am, nullptr, nullptr, nullptr, oi, n); }); return oi;
+    case 6: emuLaunch(blocks, 1, [&] { k_export_resv(s, hist, of, nullptr, n); }); return of;
+    case 7: emuLaunch(blocks, 1, [&] { k_export_resv(s, temp, of, nullptr, n); }); return of;
+    case 8: emuLaunch(blocks, 1, [&] { k_export_resv(s, hist, nullptr, oi, n); }); return oi;
+    }
+    return nullptr;
 }
 
 }  // extern "C"

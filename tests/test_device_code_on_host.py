@@ -75,8 +75,8 @@ def test_gi_staged_device_code_shallow_depths(emu, port_oracle, depth, reuse, st
 
 @pytest.mark.parametrize("name", ["gen20k", "cornell_glass"])
 def test_gi_queued_kernels_as_warps_match_oracle(emu, port_oracle, name):
-    """The ray-queue pipeline's KERNELS (k_gi_head, k_gi_walk_shadow, k_gi_walk_closest, k_gi_tail, k_gi_resolve, k_restir_indirect_fix) run as
-    grids of 32-lane warps on the CPU (tests/emu/cuda_host_shim.h: lanes are fibers, warp intrinsics exchange their values): persistent warps
+    """The GI KERNELS of all three launch forms (k_gi_primary with its packet walk, k_gi_head, k_gi_walk_shadow, k_gi_walk_closest, k_gi_tail,
+    k_gi_bounce, k_gi_resolve, k_restir_indirect, k_restir_indirect_fix) run as grids of 32-lane warps on the CPU (tests/emu/cuda_host_shim.h: lanes are fibers, warp intrinsics exchange their values): persistent warps
     with lane refill from the ray lists, lanes waiting for each other at leaves, warp-aggregated appends -- same bits as the oracle."""
     sd = {"gen20k": lambda: scenes.procedural(3, 20000, 1000, (160, 90)),
           "cornell_glass": lambda: dataclasses.replace(helpers.gi_scenes()["cornell_glass"], resolution=(96, 72))}[name]()
@@ -85,9 +85,58 @@ def test_gi_queued_kernels_as_warps_match_oracle(emu, port_oracle, name):
     helpers.assert_frames_equal(got, want, "ray-queue kernels as warps vs oracle")
     staged, undecided_staged = emu.run_gi(sd, 3, 4, 1, accumulate=True, staged=4)
     helpers.assert_frames_equal(staged, want, "staged kernels (k_gi_bounce) as warps vs oracle")
+    fused, undecided_fused = emu.run_gi(sd, 3, 4, 1, accumulate=True, staged=5)
+    helpers.assert_frames_equal(fused, want, "k_restir_indirect as warps vs oracle")
+    assert undecided_fused == undecided_staged
     if name == "gen20k":
         assert 0 < undecided <= undecided_staged          # the fix-up kernel ran on the queue the kernels wrote
     assert (want[-1]["indirect"].sum(1) > 0).mean() > 0.2
+
+
+@pytest.mark.parametrize("name,res,reuse,passes,drain", [("cornell", (64, 48), 3, 1, True), ("gen2000", (160, 90), 3, 2, False), ("gen20k", (160, 90), 1, 1, True),
+                                                         ("gen2000_tex", (96, 72), 3, 1, True), ("cornell_metal", (64, 48), 0, 1, False), ("gen2000", (96, 72), 2, 3, True)])
+def test_di_kernels_as_warps_match_oracle(emu, port_oracle, name, res, reuse, passes, drain):
+    """The direct path's KERNELS -- k_primary (packet walk of the centre + jittered rays of every 8x4 tile: G-buffer and the shaded-pixel
+    queue), k_candidates, k_shadow (persistent warps, lane refill, leaf wait, cooperative drain), k_temporal, the fix-up kernel, k_restir_b per
+    spatial pass and the export kernels -- launched as grids of 32-lane warps on the CPU in the order launchPhaseAStaged / launchRestirB use:
+    every buffer of every frame bit-identical to the oracle (RIS only, temporal, spatial, spatiotemporal; 1-3 passes)."""
+    sd = {"gen2000": lambda: scenes.procedural(3, 2000, 100, res), "gen20k": lambda: scenes.procedural(3, 20000, 1000, res),
+          "gen2000_tex": lambda: dataclasses.replace(helpers.textured_scenes()["gen2000_tex"], resolution=res)}.get(
+              name, lambda: dataclasses.replace(helpers.gi_scenes()[name], resolution=res))()
+    want = helpers.run_oracle(port_oracle, sd, 3, reuse, passes=passes, light_index=True)
+    got, _ = emu.run_di(sd, 3, reuse, passes=passes, drain=drain, light_index=True)
+    helpers.assert_frames_equal(got, want, "direct-path kernels as warps vs oracle")
+    assert (want[-1]["radiance"].sum(1) > 0).mean() > 0.2
+
+
+@pytest.mark.parametrize("pipeline", [1, 2, 3])
+@pytest.mark.parametrize("name,reuse", [("gen2000", 3), ("cornell_glass", 1)])
+def test_di_other_pipelines_as_warps_match_oracle(emu, port_oracle, name, reuse, pipeline):
+    """The other launch forms of the direct path as warps: 1 the fused kernel (k_gbuffer_restir_a, what tiny scenes use), 2 G-buffer and phase A
+    as separate launches (k_gbuffer, k_restir_a: strips), 3 the validation mode (k_gbuffer_exact, k_restir_a_exact), each with its fix-up
+    kernel and k_restir_b."""
+    sd = scenes.procedural(3, 2000, 100, (96, 72)) if name == "gen2000" else dataclasses.replace(helpers.gi_scenes()[name], resolution=(64, 48))
+    want = helpers.run_oracle(port_oracle, sd, 3, reuse, light_index=True)
+    got, _ = emu.run_di(sd, 3, reuse, pipeline=pipeline, light_index=True)
+    helpers.assert_frames_equal(got, want, "direct-path kernels as warps, pipeline %d, vs oracle" % pipeline)
+
+
+@pytest.mark.parametrize("reuse,passes", [(3, 1), (2, 2), (1, 1)])
+def test_di_unbiased_kernels_as_warps_match_oracle(emu, port_oracle, reuse, passes):
+    """RstrParams::unbiased through the staged pipeline's kernels (k_temporal_unb, k_restir_b_unb; no k_shadow) as warps."""
+    sd = scenes.procedural(3, 2000, 100, (96, 72))
+    want = helpers.run_oracle(port_oracle, sd, 3, reuse, passes=passes, unbiased=True, light_index=True)
+    got, _ = emu.run_di(sd, 3, reuse, passes=passes, unbiased=True, light_index=True)
+    helpers.assert_frames_equal(got, want, "unbiased kernels as warps vs oracle")
+    assert (want[-1]["radiance"].sum(1) > 0).mean() > 0.2
+
+
+def test_ptdirect_kernels_as_warps_match_golden(emu):
+    """k_ptdirect + k_ptdirect_fix as warps against the fixture of the reference's own pathTraceDirect (tests/golden/ptdirect.npz)."""
+    g = np.load(os.path.join(helpers.GOLDEN, "ptdirect.npz"))
+    for name, sd in helpers.test_scenes().items():
+        got, _ = emu.run_di(sd, 2, 0, accumulate=True, orbit=False, ptdirect=True, looper0=100, want=("radiance",))
+        assert helpers.mismatches(got[-1]["radiance"], g[name]) == 0, name
 
 
 def test_gbuffer_device_code_matches_oracle(emu, port_oracle):
