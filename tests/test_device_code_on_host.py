@@ -1,11 +1,16 @@
-"""CPU: the DEVICE code of the ReSTIR GI kernels (restir_b200/csrc/kernels.cu + gi_kernels.inl), compiled by g++ through
-tests/emu/cuda_host_shim.h and run one pixel per call, against the oracle -- bit for bit, because here both sides use the same libm.
+"""CPU: the DEVICE code of the library's kernels (restir_b200/csrc/kernels.cu + gi_kernels.inl), compiled by g++ through
+tests/emu/cuda_host_shim.h, against the oracle -- bit for bit, because here both sides use the same libm.
 
-This is a check of the kernels' arithmetic and control flow that needs no GPU (transcription errors, RNG ledger, reservoir logic, the
-per-lane walk of the traced tree, the fix-up path, the export layout); it is test infrastructure, not a CPU path of the product: the
-emulation library is built into tests/emu/_build and nothing under restir_b200/ can load it.  The GPU run of the same code
-(tests/test_restir_gi.py, -m gpu) differs from this one only by libdevice's sinf / cosf and by the warp-level packet walk of the
-primary rays, which cannot be emulated (its hit is taken from the reference-order walk here).
+Two levels.  (1) Per pixel: the bodies of the GI kernels run one "thread" per call (transcription errors, RNG ledger, reservoir logic, the
+per-lane walk of the traced tree, the fix-up path, the export layout).  (2) Per kernel ("as warps"): the __global__ functions themselves
+launched as grids of 32-lane warps -- the lanes of a warp are fibers on one OS thread, warp intrinsics exchange the lanes' values at each
+synchronisation point, __shared__ is one copy per warp, atomics are real across the OpenMP threads running the warps -- so the packet
+walk, k_shadow's lane refill / leaf wait / cooperative drain, warp-aggregated queue appends and the persistent GI walkers run as
+written: every launch form of the direct path (staged, fused, split, reference-order, unbiased), PTDirect and the three GI forms.
+
+This needs no GPU; it is test infrastructure, not a CPU path of the product: the emulation library is built into tests/emu/_build and
+nothing under restir_b200/ can load it.  The GPU run of the same code (tests/test_gpu_parity.py, tests/test_restir_gi.py, -m gpu)
+differs from this one only by libdevice's sinf / cosf / expf.
 """
 import dataclasses
 import os
