@@ -227,14 +227,15 @@ static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) 
     }
     emuWarp = nullptr;
 }
-// a grid of blocks of 128 threads (4 warps); the warps of the grid run on the OpenMP threads, each warp on one of them
-template <typename F> static inline void emuLaunch(unsigned gridX, unsigned gridY, F kernelCall) {
+// a grid of blocks of 32 * warpsPerBlock threads (128 unless said otherwise); the warps of the grid run on the OpenMP threads, each warp
+// on one of them
+template <typename F> static inline void emuLaunch(unsigned gridX, unsigned gridY, F kernelCall, unsigned warpsPerBlock = 4) {
     struct Call { static void run(void* a) { (*(F*)a)(); } };
 #pragma omp parallel for collapse(3) schedule(dynamic, 1)
     for (unsigned by = 0; by < gridY; by++)
         for (unsigned bx = 0; bx < gridX; bx++)
-            for (unsigned wp = 0; wp < 4; wp++) {
-                blockIdx.x = bx; blockIdx.y = by; gridDim.x = gridX; gridDim.y = gridY; blockDim.x = 128;
+            for (unsigned wp = 0; wp < warpsPerBlock; wp++) {
+                blockIdx.x = bx; blockIdx.y = by; gridDim.x = gridX; gridDim.y = gridY; blockDim.x = 32 * warpsPerBlock;
                 emuRunWarp(wp * 32, &Call::run, &kernelCall);
             }
 }

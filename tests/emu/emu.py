@@ -44,6 +44,16 @@ class Emu:
         L.emu_di_fixup_pixels.argtypes = [vp]
         L.emu_di_buffer.restype = vp
         L.emu_di_buffer.argtypes = [vp, ip]
+        L.emu_denoiser_create.restype = vp
+        L.emu_denoiser_create.argtypes = [vp, ip, C.c_float, C.c_float, C.c_float]
+        L.emu_denoiser_destroy.argtypes = [vp]
+        L.emu_denoiser_filter.argtypes = [vp, C.POINTER(api.RstrCamera)]
+        L.emu_denoiser_next_frame.argtypes = [vp]
+        L.emu_denoiser_modulate_albedo.argtypes = [vp]
+        L.emu_denoiser_color.restype = vp
+        L.emu_denoiser_color.argtypes = [vp]
+        L.emu_denoiser_variance.restype = vp
+        L.emu_denoiser_variance.argtypes = [vp]
 
     def scene(self, sd):
         v = np.ascontiguousarray(sd.vertices, np.float32)
@@ -128,3 +138,30 @@ class Emu:
         L.emu_di_destroy(fr)
         L.emu_scene_destroy(sc)
         return out, fix
+
+    def run_denoiser(self, sd, frames, kind, reuse=1, modulate=False):
+        """The loop of tests/test_denoiser.py::gpu_frames with the frame's and the filter's kernels run as warps on the CPU."""
+        W, H = sd.resolution
+        L = self.lib
+        sc = self.scene(sd)
+        fr = L.emu_di_create(sc, W, H)
+        sig = {"eaw": (64.0, 0.2, 1.0), "svgf": (4.0, 128.0, 1.0)}[kind]          # LeveledEAWFilter::create / SpatioTemporalFilter::create
+        dn = L.emu_denoiser_create(fr, {"eaw": 1, "svgf": 2}[kind], *sig)
+        base = api.Camera.from_scene(sd)
+        prm = api.default_params(reuse=reuse)
+        out = []
+        for f in range(frames):
+            cam = base.orbit(f)
+            L.emu_di_frame(fr, C.byref(cam), C.byref(prm), f, 0, 1, 0)
+            L.emu_denoiser_filter(dn, C.byref(cam))
+            if modulate:
+                L.emu_denoiser_modulate_albedo(dn)
+            rgb = self._view(L.emu_denoiser_color(dn), np.float32, (W * H, 3))
+            var = self._view(L.emu_denoiser_variance(dn), np.float32, (W * H,)) if kind == "svgf" else None
+            out.append(dict(rgb=rgb, var=var, radiance=self._view(L.emu_di_buffer(fr, 5), np.float32, (W * H, 3))))
+            L.emu_denoiser_next_frame(dn)
+            L.emu_di_update(fr, C.byref(cam))
+        L.emu_denoiser_destroy(dn)
+        L.emu_di_destroy(fr)
+        L.emu_scene_destroy(sc)
+        return out

@@ -6,6 +6,7 @@
 #include "cuda_host_shim.h"
 
 #include "../../restir_b200/csrc/kernels.cu"
+#include "../../restir_b200/csrc/denoise.cu"
 
 #include <string>
 #include <vector>
@@ -514,5 +515,85 @@ const void* emu_di_buffer(void* fv, int which) {
     }
     return nullptr;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ the image-space filters' kernels as warps
+// rstr_denoiser_* (denoise.cu) on an EmuDI frame: the launch sequences of rstr_denoiser_filter (LeveledEAWFilter::filter, denoiser.cu:463-477;
+// SpatioTemporalFilter::filter, :537-564), rstr_denoiser_modulate_albedo and rstr_denoiser_next_frame.
+struct EmuDenoiser {
+    EmuDI* f;
+    int kind, W, H;
+    float sigLumin, sigNormal, sigDepth;
+    std::vector<float> buf[9];
+    float *colorOut, *tempColor, *accumColor[2], *accumMoment[2], *variance, *tempVariance, *filteredVariance;
+    bool firstTime = true;
+    int frameIdx = 0;
+};
+
+extern "C" {
+
+void* emu_denoiser_create(void* fv, int kind, float sigLumin, float sigNormal, float sigDepth) {
+    EmuDenoiser* d = new EmuDenoiser;
+    d->f = (EmuDI*)fv; d->kind = kind; d->W = d->f->W; d->H = d->f->H;
+    d->sigLumin = sigLumin; d->sigNormal = sigNormal; d->sigDepth = sigDepth;
+    const size_t n = (size_t)d->W * d->H;
+    const size_t sizes[9] = {3 * n, 3 * n, 3 * n, 3 * n, 3 * n, 3 * n, n, n, n};
+    for (int i = 0; i < 9; i++) d->buf[i].assign(sizes[i], 0.f);
+    d->colorOut = d->buf[0].data(); d->tempColor = d->buf[1].data(); d->accumColor[0] = d->buf[2].data(); d->accumColor[1] = d->buf[3].data();
+    d->accumMoment[0] = d->buf[4].data(); d->accumMoment[1] = d->buf[5].data();
+    d->variance = d->buf[6].data(); d->tempVariance = d->buf[7].data(); d->filteredVariance = d->buf[8].data();
+    return d;
+}
+void emu_denoiser_destroy(void* d) { delete (EmuDenoiser*)d; }
+void emu_denoiser_filter(void* dv, const RstrCamera* cam) {
+    EmuDenoiser* d = (EmuDenoiser*)dv;
+    EmuDI* f = d->f;
+    DenoiseG g;
+    g.W = f->W; g.H = f->H;
+    g.geom = f->geom[f->cur].data(); g.geomLast = f->geom[f->cur ^ 1].data();
+    g.id = f->matId[f->cur].data(); g.idLast = f->matId[f->cur ^ 1].data();
+    g.albedoMotion = f->albedoMotion.data();
+    const CamDev c = toCamDev(*cam);
+    const size_t n = (size_t)d->W * d->H;
+    const unsigned gx = (unsigned)((d->W + 15) / 16), gy = (unsigned)((d->H + 7) / 8), lin = (unsigned)((n + 255) / 256);           // 256-thread blocks, as launched
+    const float* colorIn = f->radiance.data();
+    if (d->kind == RSTR_DENOISER_EAW) {
+        emuLaunch(gx, gy, [&] { k_eaw(g, c, d->colorOut, colorIn, d->sigDepth, d->sigNormal, d->sigLumin, 0); });
+        for (int level = 1; level <= 4; level++) {
+            emuLaunch(gx, gy, [&] { k_eaw(g, c, d->tempColor, d->colorOut, d->sigDepth, d->sigNormal, d->sigLumin, level); });
+            std::swap(d->colorOut, d->tempColor);
+        }
+    } else {
+        const int fi = d->frameIdx;
+        const int firstTime = d->firstTime ? 1 : 0;
+        emuLaunch(lin, 1, [&] { k_temporal_accumulate(g, d->accumColor[fi], d->accumColor[fi ^ 1], d->accumMoment[fi], d->accumMoment[fi ^ 1], colorIn, firstTime); }, 8);
+        d->firstTime = false;
+        emuLaunch(lin, 1, [&] { k_estimate_variance(d->variance, d->accumMoment[fi], d->W, d->H); }, 8);
+        auto wavelet = [&](float* out, const float* in, int level) {
+            emuLaunch(lin, 1, [&] { k_filter_variance(d->filteredVariance, d->variance, d->W, d->H); }, 8);
+            emuLaunch(gx, gy, [&] { k_eaw_svgf(g, c, out, in, d->tempVariance, d->variance, d->filteredVariance, d->sigDepth, d->sigNormal, d->sigLumin, level); });
+        };
+        wavelet(d->colorOut, d->accumColor[fi], 0);
+        std::swap(d->colorOut, d->accumColor[fi]);
+        std::swap(d->tempVariance, d->variance);
+        wavelet(d->colorOut, d->accumColor[fi], 1);
+        std::swap(d->tempVariance, d->variance);
+        for (int level = 2; level <= 4; level++) {
+            wavelet(d->tempColor, d->colorOut, level);
+            std::swap(d->tempColor, d->colorOut);
+            std::swap(d->tempVariance, d->variance);
+        }
+    }
+}
+void emu_denoiser_next_frame(void* dv) { ((EmuDenoiser*)dv)->frameIdx ^= 1; }
+void emu_denoiser_modulate_albedo(void* dv) {
+    EmuDenoiser* d = (EmuDenoiser*)dv;
+    const size_t n = (size_t)d->W * d->H;
+    const float4* am = d->f->albedoMotion.data();
+    emuLaunch((unsigned)((n + 255) / 256), 1, [&] { k_modulate(d->colorOut, am, n); }, 8);
+}
+const float* emu_denoiser_color(void* dv) { return ((EmuDenoiser*)dv)->colorOut; }
+const float* emu_denoiser_variance(void* dv) { return ((EmuDenoiser*)dv)->variance; }
 
 }  // extern "C"

@@ -144,6 +144,24 @@ def test_ptdirect_kernels_as_warps_match_golden(emu):
         assert helpers.mismatches(got[-1]["radiance"], g[name]) == 0, name
 
 
+@pytest.mark.parametrize("kind,modulate", [("eaw", False), ("svgf", False), ("svgf", True)])
+def test_denoiser_kernels_as_warps_match_oracle(emu, port_oracle, kind, modulate):
+    """denoise.cu's kernels (k_eaw, k_temporal_accumulate, k_estimate_variance, k_filter_variance, k_eaw_svgf, k_modulate) in the launch
+    order of rstr_denoiser_filter, on frames the emulated direct-path kernels rendered: with glibc's expf / powf on both sides the filtered
+    colour and the variance are the oracle's bit for bit (on the GPU, libdevice: 2e-4 relative, tests/test_denoiser.py)."""
+    import test_denoiser
+
+    sd = scenes.procedural(3, 2000, 100, (96, 72))
+    want = test_denoiser.oracle_frames(port_oracle, sd, 4, kind, modulate=modulate)
+    got = emu.run_denoiser(sd, 4, kind, modulate=modulate)
+    for f in range(4):
+        assert helpers.mismatches(got[f]["radiance"], want[f]["radiance"]) == 0, f
+        assert helpers.mismatches(got[f]["rgb"], want[f]["rgb"]) == 0, (f, "filtered colour")
+        if kind == "svgf":
+            assert helpers.mismatches(got[f]["var"], want[f]["var"]) == 0, (f, "variance")
+    assert float(np.abs(got[-1]["rgb"] - got[-1]["radiance"]).max()) > 0      # the filter did something
+
+
 def test_gbuffer_device_code_matches_oracle(emu, port_oracle):
     """The G-buffer the GI kernel reads (k_gbuffer_exact's per-pixel body) against the oracle's, over an orbit."""
     sd = dataclasses.replace(helpers.textured_scenes()["gen2000_tex"], resolution=(96, 72))
