@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY: builds tests/emu/_build/libgi_emu.so -- the device code of restir_b200/csrc/kernels.cu compiled by g++
+"""TEST INFRASTRUCTURE ONLY: builds tests/emu/_build/libkernels_emu.so -- the device code of restir_b200/csrc/kernels.cu compiled by g++
 (see cuda_host_shim.h) -- for tests/test_device_code_on_host.py.  Same floating-point flags as the oracle (no contraction, no fast-math)."""
 import os
 import subprocess
@@ -6,10 +6,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "restir_b200", "csrc")
-OUT = os.path.join(HERE, "_build", "libgi_emu.so")
-SOURCES = [os.path.join(HERE, "gi_emu.cpp"), os.path.join(CSRC, "scene_host.cpp"), os.path.join(CSRC, "bvh_fast.cpp")]
+OUT = os.path.join(HERE, "_build", "libkernels_emu.so")
+SOURCES = [os.path.join(HERE, "kernels_emu.cpp"), os.path.join(CSRC, "scene_host.cpp"), os.path.join(CSRC, "bvh_fast.cpp")]
 DEPS = SOURCES + [os.path.join(HERE, "cuda_host_shim.h")] + [os.path.join(CSRC, f) for f in
-                                                             ("kernels.cu", "gi_kernels.inl", "kernels.h", "device_types.h", "vecmath.h", "camera_dev.h", "scene_host.h")]
+                                                             ("kernels.cu", "gi_kernels.inl", "denoise.cu", "capi_internal.h", "kernels.h", "device_types.h", "vecmath.h", "camera_dev.h", "scene_host.h")]
 
 
 def build(force: bool = False) -> str:
@@ -20,7 +20,7 @@ def build(force: bool = False) -> str:
            "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", "/usr/local/cuda/include", "-x", "c++"] + SOURCES + ["-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("g++ failed building libgi_emu.so:\n" + r.stderr[-4000:])
+        raise RuntimeError("g++ failed building libkernels_emu.so:\n" + r.stderr[-4000:])
     return OUT
 
 

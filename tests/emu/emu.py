@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY: ctypes driver of tests/emu/_build/libgi_emu.so (the kernels' device code compiled for the host)."""
+"""TEST INFRASTRUCTURE ONLY: ctypes driver of tests/emu/_build/libkernels_emu.so (the kernels' device code compiled for the host)."""
 import ctypes as C
 import os
 import sys

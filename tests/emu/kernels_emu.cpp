@@ -1,8 +1,9 @@
-// gi_emu.cpp -- TEST INFRASTRUCTURE ONLY (see cuda_host_shim.h).  The device code of restir_b200/csrc/kernels.cu + gi_kernels.inl compiled by
-// g++ and driven one pixel per call: G-buffer (gbufferPixelExact) and ReSTIR GI (giAfterHit), with the same libm as the oracle, so the two
-// must agree bit for bit.  Two modes: every ray with the reference-order walk, or the bounce / shadow rays with the per-lane walks of the
-// traced tree (traceClosestFast / traceOccludedFast; the warp-level packet walk cannot be emulated and its primary hit is taken from the
-// reference-order walk).  Built by tests/emu/build.py into tests/emu/_build (git-ignored); never part of librestir_b200.so.
+// kernels_emu.cpp -- TEST INFRASTRUCTURE ONLY (see cuda_host_shim.h).  The device code of restir_b200/csrc/kernels.cu + gi_kernels.inl +
+// denoise.cu compiled by g++, with the same libm as the oracle, so the two must agree bit for bit.  Two levels:
+//   per pixel    emu_gbuffer_render / emu_restir_indirect (modes 0-3): the bodies of the G-buffer and GI kernels, one "thread" per call
+//   per kernel   emu_restir_indirect (modes 4-6), emu_di_*, emu_denoiser_*: the __global__ functions launched with emuLaunch as grids of
+//                32-lane warps (fibers + exchanged warp intrinsics), in the order the library's launchers use
+// Built by tests/emu/build.py into tests/emu/_build (git-ignored); never part of librestir_b200.so.
 #include "cuda_host_shim.h"
 
 #include "../../restir_b200/csrc/kernels.cu"
