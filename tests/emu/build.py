@@ -12,16 +12,28 @@ DEPS = SOURCES + [os.path.join(HERE, "cuda_host_shim.h")] + [os.path.join(CSRC, 
                                                              ("kernels.cu", "gi_kernels.inl", "denoise.cu", "capi_internal.h", "kernels.h", "device_types.h", "vecmath.h", "camera_dev.h", "scene_host.h")]
 
 
-def build(force: bool = False) -> str:
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-w", "-shared",
-           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", "/usr/local/cuda/include", "-x", "c++"] + SOURCES + ["-o", OUT]
+def build(force: bool = False, sanitize: str = "") -> str:
+    """sanitize = "address" / "thread": the same library instrumented by ASan / TSan (tests/test_kernels_under_sanitizers.py runs it in a
+    child process with the sanitizer runtime preloaded): the memcheck / racecheck of the kernels' code that needs no GPU."""
+    out = OUT if not sanitize else OUT.replace(".so", "_%s.so" % sanitize)
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in DEPS):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    opt = ["-O2"] if not sanitize else ["-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=" + sanitize]
+    if sanitize == "thread":
+        opt.append("-DEMU_STD_THREADS")          # libgomp's barriers are invisible to TSan: the warps run on std::threads instead
+    cmd = ["/usr/bin/g++", "-std=c++17"] + opt + ["-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-w", "-shared",
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", "/usr/local/cuda/include", "-x", "c++"] + SOURCES + ["-o", out]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("g++ failed building libkernels_emu.so:\n" + r.stderr[-4000:])
-    return OUT
+        raise RuntimeError("g++ failed building %s:\n" % os.path.basename(out) + r.stderr[-4000:])
+    return out
+
+
+def sanitizer_runtime(sanitize: str) -> str:
+    """Path of libasan.so / libtsan.so for LD_PRELOAD (the interpreter itself is not instrumented)."""
+    name = {"address": "libasan.so", "thread": "libtsan.so"}[sanitize]
+    return subprocess.run(["/usr/bin/gcc", "-print-file-name=" + name], capture_output=True, text=True).stdout.strip()
 
 
 if __name__ == "__main__":

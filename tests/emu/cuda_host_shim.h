@@ -8,6 +8,10 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef EMU_STD_THREADS
+#include <atomic>
+#include <thread>
+#endif
 
 #define RS_HOST_EMU 1
 // kernels and __noinline__ device functions must not be emitted unless the emulation calls them: several contain PTX inline assembly
@@ -82,7 +86,22 @@ static inline void emuMakeCtx(EmuCtx* ctx, char* stack, size_t size, void (*entr
 typedef ucontext_t EmuCtx;
 static inline void emuSwitch(EmuCtx* from, EmuCtx& to) { swapcontext(from, &to); }
 #endif
+#if defined(__SANITIZE_THREAD__)
+// TSan keeps a shadow call stack per context: it has to be told about every switch (and orders the two sides of a switch, so the lanes of
+// a warp, which run strictly one after the other, are never reported against each other; warps on different OS threads are)
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+}
+#define EMU_TSAN_SWITCH(fiber) __tsan_switch_to_fiber(fiber, 0)
+#else
+#define EMU_TSAN_SWITCH(fiber) ((void)0)
+#endif
 struct EmuWarp {
+    void* tsanSched;
+    void* tsanLane[32];
     EmuCtx sched, ctx[32];
     bool done[32];
     int lane;                                    // the lane that is running
@@ -101,6 +120,7 @@ static inline const unsigned long long* emuExchange(unsigned long long mine) {
     const unsigned k = w->sync[l]++ & 1u;
     w->val[k][l] = mine;
     w->has[k][l] = true;
+    EMU_TSAN_SWITCH(w->tsanSched);
     emuSwitch(&w->ctx[l], w->sched);
     return emuWarp->val[k];
 }
@@ -115,7 +135,7 @@ static void emuTrampoline() {
     w->done[l] = true;
     w->val[next][l] = 0; w->has[next][l] = false;
 #if defined(__x86_64__)
-    for (;;) emuSwitch(&w->ctx[l], w->sched);    // never resumed: the scheduler skips finished lanes
+    for (;;) { EMU_TSAN_SWITCH(w->tsanSched); emuSwitch(&w->ctx[l], w->sched); }    // never resumed: the scheduler skips finished lanes
 #endif
 }
 // run `body(arg)` as the 32 lanes tidBase .. tidBase + 31 of one warp; blockIdx / blockDim / gridDim are the caller's
@@ -195,8 +215,15 @@ static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)(u
 static inline void* emuSharedPtr(unsigned off) { return &emuSharedAnchor + (long)(int)off; }
 
 
+#if defined(__SANITIZE_ADDRESS__)
+extern "C" void __asan_unpoison_memory_region(void const volatile* addr, size_t size);
+#endif
 static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) {
     if (!emuStacks) emuStacks = (char*)malloc((size_t)32 * EMU_FIBER_STACK);
+#if defined(__SANITIZE_ADDRESS__)
+    // the previous warp's lanes never returned from their trampolines: the redzones of their frames are still poisoned
+    __asan_unpoison_memory_region(emuStacks, (size_t)32 * EMU_FIBER_STACK);
+#endif
     EmuWarp w;
     memset(w.done, 0, sizeof w.done); memset(w.sync, 0, sizeof w.sync); memset(w.val, 0, sizeof w.val); memset(w.has, 0, sizeof w.has);
     w.body = body; w.arg = arg; w.lane = 0;
@@ -211,6 +238,10 @@ static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) 
         makecontext(&w.ctx[l], emuTrampoline, 0);
 #endif
     }
+#if defined(__SANITIZE_THREAD__)
+    w.tsanSched = __tsan_get_current_fiber();
+    for (int l = 0; l < 32; l++) w.tsanLane[l] = __tsan_create_fiber(0);
+#endif
     emuWarp = &w;
     for (;;) {
         bool any = false;
@@ -219,6 +250,7 @@ static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) 
                 any = true;
                 w.lane = l;
                 threadIdx.x = tidBase + l;
+                EMU_TSAN_SWITCH(w.tsanLane[l]);
                 emuSwitch(&w.sched, w.ctx[l]);
             }
         if (!any) break;
@@ -226,11 +258,32 @@ static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) 
             if (w.done[l]) { w.val[0][l] = w.val[1][l] = 0; w.has[0][l] = w.has[1][l] = false; }
     }
     emuWarp = nullptr;
+#if defined(__SANITIZE_THREAD__)
+    for (int l = 0; l < 32; l++) __tsan_destroy_fiber(w.tsanLane[l]);
+#endif
 }
 // a grid of blocks of 32 * warpsPerBlock threads (128 unless said otherwise); the warps of the grid run on the OpenMP threads, each warp
 // on one of them
 template <typename F> static inline void emuLaunch(unsigned gridX, unsigned gridY, F kernelCall, unsigned warpsPerBlock = 4) {
     struct Call { static void run(void* a) { (*(F*)a)(); } };
+#ifdef EMU_STD_THREADS
+    // the TSan build: thread creation / join are what TSan understands as the launch's ordering with the host code around it
+    {
+        const unsigned total = gridX * gridY * warpsPerBlock;
+        std::atomic<unsigned> next{0};
+        auto worker = [&] {
+            for (unsigned i = next.fetch_add(1, std::memory_order_relaxed); i < total; i = next.fetch_add(1, std::memory_order_relaxed)) {   // relaxed: no ordering between warps that TSan could take for synchronisation
+                const unsigned wp = i % warpsPerBlock, b = i / warpsPerBlock;
+                blockIdx.x = b % gridX; blockIdx.y = b / gridX; gridDim.x = gridX; gridDim.y = gridY; blockDim.x = 32 * warpsPerBlock;
+                emuRunWarp(wp * 32, &Call::run, &kernelCall);
+            }
+        };
+        std::thread pool[4];
+        for (auto& t : pool) t = std::thread(worker);
+        for (auto& t : pool) t.join();
+        return;
+    }
+#endif
 #pragma omp parallel for collapse(3) schedule(dynamic, 1)
     for (unsigned by = 0; by < gridY; by++)
         for (unsigned bx = 0; bx < gridX; bx++)

@@ -13,8 +13,8 @@ from restir_b200 import api  # noqa: E402   (RstrSceneDesc / RstrCamera structur
 
 
 class Emu:
-    def __init__(self):
-        L = self.lib = C.CDLL(_emu_build.build())
+    def __init__(self, sanitize: str = ""):
+        L = self.lib = C.CDLL(_emu_build.build(sanitize=sanitize))
         vp, ip = C.c_void_p, C.c_int
         L.emu_scene_create.restype = vp
         L.emu_scene_create.argtypes = [C.POINTER(api.RstrSceneDesc)]

@@ -392,7 +392,9 @@ void* emu_di_create(void* scv, int W, int H) {
     memset(&zh, 0, sizeof zh);
     for (int i = 0; i < 2; i++) { f->geom[i].assign(n, make_float4(0, 0, 0, 0)); f->matId[i].assign(n, 0); f->resv[i].assign(n, zr); }
     f->albedoMotion.assign(n, make_float4(0, 0, 0, 0));
-    f->radiance.assign(3 * n, 0.f);
+    // negative control of tests/test_kernels_under_sanitizers.py: a radiance plane one pixel short must be REPORTED by the sanitizer
+    const char* fault = getenv("EMU_INJECT_FAULT");
+    f->radiance.assign(3 * n - (fault && !strcmp(fault, "short_plane") ? 3 : 0), 0.f);
     f->resvTemp.assign(n, zr); f->resvTemp2.assign(n, zr);
     f->hit.assign(n, zh);
     if (f->sc->hs.anyMRMaps) f->hitMR.assign(n, make_float2(0.f, 0.f));
@@ -464,6 +466,10 @@ void emu_di_frame(void* fv, const RstrCamera* cam, const RstrParams* prm, int lo
         ResvD* buf[2] = {f->resvTemp.data(), f->resvTemp2.data()};
         const ResvD* src = buf[(pass - 1) & 1];
         ResvD* dst = buf[pass & 1];
+        // negative control of tests/test_kernels_under_sanitizers.py: spatial reuse IN PLACE -- the reference's own inter-block race
+        // (restir.cu:192-196: __syncthreads() is not a grid barrier) -- must be REPORTED by TSan
+        const char* fault = getenv("EMU_INJECT_FAULT");
+        if (fault && !strcmp(fault, "in_place_spatial")) dst = (ResvD*)src;
         const int last = pass == passes ? 1 : 0;
         if (p.unbiased) emuLaunch(gx, gy, [&] { k_restir_b_unb(s, d, p, iter, src, dst, pass, last); });
         else emuLaunch(gx, gy, [&] { k_restir_b(s, d, p, iter, src, dst, pass, last); });
