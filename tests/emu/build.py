@@ -32,7 +32,7 @@ def build(force: bool = False, sanitize: str = "") -> str:
 
 def sanitizer_runtime(sanitize: str) -> str:
     """Path of libasan.so / libtsan.so for LD_PRELOAD (the interpreter itself is not instrumented)."""
-    name = {"address": "libasan.so", "thread": "libtsan.so"}[sanitize]
+    name = {"address": "libasan.so", "thread": "libtsan.so", "undefined": "libubsan.so"}[sanitize]
     return subprocess.run(["/usr/bin/gcc", "-print-file-name=" + name], capture_output=True, text=True).stdout.strip()
 
 

@@ -212,7 +212,7 @@ static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 // statics of the same module, so the offsets fit 32 bits
 static thread_local char emuSharedAnchor;
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)(unsigned)(int)((const char*)p - &emuSharedAnchor); }
-static inline void* emuSharedPtr(unsigned off) { return &emuSharedAnchor + (long)(int)off; }
+static inline void* emuSharedPtr(unsigned off) { return (void*)((uintptr_t)&emuSharedAnchor + (uintptr_t)(intptr_t)(int)off); }   // integer arithmetic: not an offset INTO the anchor object
 
 
 #if defined(__SANITIZE_ADDRESS__)

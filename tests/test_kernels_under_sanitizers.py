@@ -1,11 +1,12 @@
-"""CPU: the library's kernels under AddressSanitizer and ThreadSanitizer.
+"""CPU: the library's kernels under AddressSanitizer, ThreadSanitizer and UndefinedBehaviorSanitizer.
 
 compute-sanitizer cannot attach on this GPU pool (profiles/r02_sanitizer_closed_on_pool.txt), so the memcheck / racecheck of SURVEY section 5 is
 run on the kernels' CODE instead: tests/emu compiles kernels.cu + gi_kernels.inl + denoise.cu with g++ -fsanitize=address / thread and launches
 every kernel family as grids of 32-lane warps (tests/emu/sanitizer_child.py).  Every global-memory access of a kernel is then an instrumented
 access to a heap buffer of exactly the plane's size (ASan: out-of-bounds reads / writes of any plane, queue, list or table), and warps on
 different OS threads are checked against each other (TSan: two warps touching the same word without an atomic; the lanes of one warp run one
-after the other and are ordered at every warp intrinsic).  Each tool also gets a negative control -- a plane one pixel short, and the
+after the other and are ordered at every warp intrinsic; UBSan: signed overflow, shifts, misaligned vector loads, float -> int casts out of
+range).  ASan and TSan each also get a negative control -- a plane one pixel short, and the
 reference's own in-place spatial reuse (restir.cu:192-196) -- that it must report, so a clean run means something.
 
 The sanitizer runtime has to be loaded before the interpreter starts, hence the child processes.  Test infrastructure only."""
@@ -30,6 +31,7 @@ def run_child(tool, what, fault=None):
     env["LD_PRELOAD"] = emu_build.sanitizer_runtime(tool)
     env["ASAN_OPTIONS"] = "detect_leaks=0:abort_on_error=0"        # the interpreter's own allocations are not the subject
     env["TSAN_OPTIONS"] = "report_signal_unsafe=0:exitcode=66"
+    env["UBSAN_OPTIONS"] = "print_stacktrace=1"
     env["OMP_NUM_THREADS"] = "1" if tool == "thread" else env.get("OMP_NUM_THREADS", "4")   # TSan: the warps run on std::threads, nothing else is parallel
     env.pop("EMU_INJECT_FAULT", None)
     if fault:
@@ -37,7 +39,7 @@ def run_child(tool, what, fault=None):
     return subprocess.run([sys.executable, CHILD, tool, what], capture_output=True, text=True, env=env, timeout=1500)
 
 
-@pytest.mark.parametrize("tool,marker", [("address", "ERROR: AddressSanitizer"), ("thread", "WARNING: ThreadSanitizer")])
+@pytest.mark.parametrize("tool,marker", [("address", "ERROR: AddressSanitizer"), ("thread", "WARNING: ThreadSanitizer"), ("undefined", "runtime error")])
 def test_every_kernel_family_is_clean(tool, marker):
     r = run_child(tool, "all")
     assert marker not in r.stderr, r.stderr[-3000:]
