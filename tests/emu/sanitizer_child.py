@@ -33,6 +33,13 @@ def main():
     for mode in (3, 4, 5):                                                # GI: ray queues, staged, one kernel
         e.run_gi(gen, 2, 3, 1, accumulate=True, staged=mode)
     e.run_gi(glass, 2, 4, 1, staged=3)
+    import test_device_code_on_host as t                                  # ragged resolution, single triangle, no lights, nothing in view
+    for name, (sd, orbit) in t.edge_scenes().items():
+        e.run_di(sd, 2, 3, orbit=orbit, light_index=True)
+        e.run_di(sd, 2, 3, orbit=orbit, pipeline=1)
+        e.run_gi(sd, 2, 3, 1, orbit=orbit, staged=3)
+        e.run_gi(sd, 2, 3, 1, orbit=orbit, staged=5)
+    e.run_denoiser(t.edge_scenes()["ragged"][0], 2, "svgf")
     e.run_denoiser(gen, 2, "eaw")
     e.run_denoiser(gen, 2, "svgf", modulate=True)
     print("sanitizer child: all kernel families ran")

@@ -114,6 +114,41 @@ def test_di_kernels_as_warps_match_oracle(emu, port_oracle, name, res, reuse, pa
     assert (want[-1]["radiance"].sum(1) > 0).mean() > 0.2
 
 
+def edge_scenes():
+    """tests/test_gpu_parity.py::test_edge_cases: ragged resolution, a single (emissive) triangle, no lights, a camera that sees nothing,
+    an exactly axis-aligned centre ray, a camera looking straight down."""
+    v = np.asarray([(-1, 0, -2), (1, 0, -2), (0, 1.5, -2)], np.float32)
+    one = scenes.SceneData("one", v, scenes._face_normals(v), np.zeros((3, 2), np.float32), np.zeros(1, np.int32),
+                           scenes.make_materials([(scenes.LIGHT, (5, 5, 5), 0.0, 1.0)]), ["l"], eye=(0, 0.5, 2), rotation=(-90, 0, 0), fovy=30.0, resolution=(40, 32))
+    away = scenes.cornell_box((48, 36))
+    away.rotation = (90.0, 0.0, 0.0)
+    down = scenes.cornell_box((33, 33))
+    down.eye, down.rotation = (0.05, 1.9, 0.02), (-90.0, -89.99, 0.0)
+    return {"ragged": (scenes.cornell_box((37, 23), metal_tall_box=True), True), "one_triangle": (one, True), "no_lights": (helpers.five_triangles(), True),
+            "all_miss": (away, True), "axis_aligned": (scenes.cornell_box((33, 33)), False), "looking_down": (down, False)}
+
+
+@pytest.mark.parametrize("name", ["ragged", "one_triangle", "no_lights", "all_miss", "axis_aligned", "looking_down"])
+@pytest.mark.parametrize("pipeline", [0, 1])
+def test_di_edge_cases_as_warps_match_oracle(emu, port_oracle, name, pipeline):
+    """The edge cases of the GPU suite through the staged and the fused kernels as warps (partial tiles, a leaf as the BVH root, an empty
+    light table, empty queues for the persistent kernels, the special cases of bvh.h:91-123)."""
+    sd, orbit = edge_scenes()[name]
+    want = helpers.run_oracle(port_oracle, sd, 2, 3, orbit=orbit, light_index=True)
+    got, _ = emu.run_di(sd, 2, 3, orbit=orbit, pipeline=pipeline, light_index=True)
+    helpers.assert_frames_equal(got, want, "edge case %s, pipeline %d" % (name, pipeline))
+
+
+@pytest.mark.parametrize("name", ["ragged", "one_triangle", "no_lights", "all_miss"])
+def test_gi_edge_cases_as_warps_match_oracle(emu, port_oracle, name):
+    """... and through the three GI forms' kernels."""
+    sd, orbit = edge_scenes()[name]
+    want = helpers.run_oracle_gi(port_oracle, sd, 2, 3, 1, orbit=orbit)
+    for mode, what in ((3, "ray queues"), (4, "staged"), (5, "one kernel")):
+        got, _ = emu.run_gi(sd, 2, 3, 1, orbit=orbit, staged=mode)
+        helpers.assert_frames_equal(got, want, "GI edge case %s, %s" % (name, what))
+
+
 @pytest.mark.parametrize("pipeline", [1, 2, 3])
 @pytest.mark.parametrize("name,reuse", [("gen2000", 3), ("cornell_glass", 1)])
 def test_di_other_pipelines_as_warps_match_oracle(emu, port_oracle, name, reuse, pipeline):
