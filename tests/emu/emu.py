@@ -44,6 +44,14 @@ class Emu:
         L.emu_di_fixup_pixels.argtypes = [vp]
         L.emu_di_buffer.restype = vp
         L.emu_di_buffer.argtypes = [vp, ip]
+        L.emu_di_create_strip.restype = vp
+        L.emu_di_create_strip.argtypes = [vp, ip, ip, ip, ip, ip]
+        L.emu_di_phase_a.argtypes = [vp, C.POINTER(api.RstrCamera), C.POINTER(api.RstrParams), ip, ip, ip, ip]
+        L.emu_di_phase_b_pass.argtypes = [vp, C.POINTER(api.RstrCamera), C.POINTER(api.RstrParams), ip, ip]
+        L.emu_di_copy_rows.restype = ip
+        L.emu_di_copy_rows.argtypes = [vp, vp, ip, ip, ip]
+        L.emu_di_halo_miss.restype = C.c_uint
+        L.emu_di_halo_miss.argtypes = [vp]
         L.emu_denoiser_create.restype = vp
         L.emu_denoiser_create.argtypes = [vp, ip, C.c_float, C.c_float, C.c_float]
         L.emu_denoiser_destroy.argtypes = [vp]
@@ -165,3 +173,59 @@ class Emu:
         L.emu_di_destroy(fr)
         L.emu_scene_destroy(sc)
         return out
+
+    def run_di_strips(self, sd, frames, bounds, halo, reuse=3, radius=5.0, passes=1, names=("matid", "motion", "depth", "radiance", "reservoir", "light_index")):
+        """tests/test_gpu_parity.py::test_strips_with_exchanged_gbuffer_halo_and_multi_pass with the kernels as warps: strips that render
+        only their own rows, the G-buffer / reservoir halo rows copied between them where the library pushes them over NVLink
+        (emu_di_copy_rows = rstr_frame_copy_rows).  Returns per frame {name: the strips' own rows concatenated} and the halo misses."""
+        from oracle.oracle import RESERVOIR_DTYPE
+
+        W, H = sd.resolution
+        L = self.lib
+        sc = self.scene(sd)
+        strips = [(L.emu_di_create_strip(sc, W, H, bounds[i], bounds[i + 1], halo), bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1)]
+        PL = dict(geom_cur=0, matid_cur=1, resv_history=2, resv_temp=3, resv_temp2=4, resv_out=5)
+
+        def exchange(plane):
+            for i, (s, s0, s1) in enumerate(strips):
+                for j in (i - 1, i + 1):
+                    if 0 <= j < len(strips):
+                        d, d0, d1 = strips[j]
+                        lo, hi = max(s0, max(0, d0 - halo)), min(s1, min(H, d1 + halo))
+                        if lo < hi:
+                            assert L.emu_di_copy_rows(d, s, PL[plane], lo, hi) == 0
+
+        base = api.Camera.from_scene(sd)
+        prm = api.default_params(reuse=reuse, radius=radius, passes=passes)
+        out = []
+        for f in range(frames):
+            cam = base.orbit(f)
+            for s, _, _ in strips:
+                L.emu_di_phase_a(s, C.byref(cam), C.byref(prm), f, 0, 1, 0)
+            for plane in ("geom_cur", "matid_cur", "resv_temp"):
+                exchange(plane)
+            for p in range(1, passes + 1):
+                for s, _, _ in strips:
+                    L.emu_di_phase_b_pass(s, C.byref(cam), C.byref(prm), 0, p)
+                if p < passes:
+                    exchange("resv_temp2" if p & 1 else "resv_temp")
+            exchange("resv_history")
+            d = {}
+            for n in names:
+                which, dt, comps = self.DI_BUF[n]
+                parts = []
+                for s, s0, s1 in strips:
+                    b0 = max(0, s0 - halo)
+                    rows = min(H, s1 + halo) - b0
+                    ptr = L.emu_di_buffer(s, which)
+                    a = self._view(ptr, RESERVOIR_DTYPE, (rows * W,)) if dt is None else self._view(ptr, dt, (rows * W, comps) if comps else (rows * W,))
+                    parts.append(a[(s0 - b0) * W:(s1 - b0) * W])
+                d[n] = np.concatenate(parts)
+            out.append(d)
+            for s, _, _ in strips:
+                L.emu_di_update(s, C.byref(cam))
+        miss = [int(L.emu_di_halo_miss(s)) for s, _, _ in strips]
+        for s, _, _ in strips:
+            L.emu_di_destroy(s)
+        L.emu_scene_destroy(sc)
+        return out, miss

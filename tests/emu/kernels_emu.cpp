@@ -351,6 +351,7 @@ struct EmuDI {
     EmuScene* sc;
     DevScene dev;
     int W, H;
+    int row0, row1, bufRow0, bufRows;            // a horizontal strip [row0, row1) with its resident rows (the full frame: 0, H, 0, H)
     std::vector<float4> geom[2], albedoMotion;
     std::vector<int> matId[2], queue, shadeQueue;
     std::vector<float> radiance, export36;
@@ -367,7 +368,7 @@ struct EmuDI {
 };
 static FrameDev diFrameDev(EmuDI* f) {                              // rsToFrameDev (capi.cu)
     FrameDev d{};
-    d.W = f->W; d.H = f->H; d.rowLo = 0; d.rowHi = f->H; d.bufRow0 = 0; d.bufRows = f->H;
+    d.W = f->W; d.H = f->H; d.rowLo = f->row0; d.rowHi = f->row1; d.bufRow0 = f->bufRow0; d.bufRows = f->bufRows;
     d.geom[0] = f->geom[f->cur].data(); d.geom[1] = f->geom[f->cur ^ 1].data();
     d.matId[0] = f->matId[f->cur].data(); d.matId[1] = f->matId[f->cur ^ 1].data();
     d.albedoMotion = f->albedoMotion.data(); d.radiance = f->radiance.data();
@@ -380,11 +381,16 @@ static FrameDev diFrameDev(EmuDI* f) {                              // rsToFrame
 
 extern "C" {
 
-void* emu_di_create(void* scv, int W, int H) {
+// rstr_frame_create: rows [row0, row1) of the W x H image plus `halo` resident rows on each side (row1 <= 0: the full frame)
+void* emu_di_create_strip(void* scv, int W, int H, int row0, int row1, int halo) {
     EmuDI* f = new EmuDI;
     f->sc = (EmuScene*)scv; f->dev = f->sc->dev; f->dev.traversal = RS_TRAVERSAL_FAST;
     f->W = W; f->H = H;
-    const size_t n = (size_t)W * H;
+    if (row1 <= 0) { row0 = 0; row1 = H; halo = 0; }
+    f->row0 = row0; f->row1 = row1;
+    f->bufRow0 = row0 - halo < 0 ? 0 : row0 - halo;
+    f->bufRows = (row1 + halo > H ? H : row1 + halo) - f->bufRow0;
+    const size_t n = (size_t)W * f->bufRows;
     ResvD zr;
     memset(&zr, 0, sizeof zr);
     zr.lightId = -1;                                                 // rstr_frame_create: a zero-filled reference reservoir has no sample
@@ -402,11 +408,20 @@ void* emu_di_create(void* scv, int W, int H) {
     memset(f->queueCount, 0, sizeof f->queueCount);
     return f;
 }
+void* emu_di_create(void* scv, int W, int H) { return emu_di_create_strip(scv, W, H, 0, 0, 0); }
 void emu_di_destroy(void* f) { delete (EmuDI*)f; }
 
 // rstr_gbuffer_render + rstr_restir_direct.  pipeline 0: staged (launchPhaseAStaged), 1: fused (launchGBufferRestirA), 2: split (launchGBuffer,
 // launchRestirA), 3: split with every ray in the reference's order (RS_TRAVERSAL_EXACT: k_gbuffer_exact, k_restir_a_exact)
+void emu_di_phase_b_pass(void* fv, const RstrCamera* cam, const RstrParams* prm, int iter, int pass);
+void emu_di_phase_a(void* fv, const RstrCamera* cam, const RstrParams* prm, int looper, int iter, int drain, int pipeline);
 void emu_di_frame(void* fv, const RstrCamera* cam, const RstrParams* prm, int looper, int iter, int drain, int pipeline) {
+    emu_di_phase_a(fv, cam, prm, looper, iter, drain, pipeline);
+    const int passes = (prm->reuse & 2) ? (prm->spatialPasses < 1 ? 1 : prm->spatialPasses) : 0;
+    for (int pass = 1; pass <= (passes ? passes : 1); pass++) emu_di_phase_b_pass(fv, cam, prm, iter, pass);
+}
+// rstr_gbuffer_render + rstr_restir_phase_a on the frame's own rows
+void emu_di_phase_a(void* fv, const RstrCamera* cam, const RstrParams* prm, int looper, int iter, int drain, int pipeline) {
     EmuDI* f = (EmuDI*)fv;
     const DevScene& s = f->dev;
     const RstrParams p = *prm;
@@ -418,7 +433,7 @@ void emu_di_frame(void* fv, const RstrCamera* cam, const RstrParams* prm, int lo
     d.resvStage = f->resvTemp.data();
     memset(f->queueCount, 0, sizeof f->queueCount);
     d.shadeCount = f->queueCount + 4;
-    const unsigned gx = (unsigned)((f->W + 15) / 16), gy = (unsigned)((f->H + 7) / 8), linear = gx * gy;
+    const unsigned gx = (unsigned)((f->W + 15) / 16), gy = (unsigned)((f->row1 - f->row0 + 7) / 8), linear = gx * gy;
     if (pipeline == 0) {
         d.resvStage = sp ? f->resvTemp.data() : f->resvTemp2.data();
         if (!sp) f->temp2Ready = false;
@@ -460,8 +475,18 @@ void emu_di_frame(void* fv, const RstrCamera* cam, const RstrParams* prm, int lo
         if (sp) emuLaunch(gx, gy, [&] { k_restir_a_exact<true>(s, d, c, p, looper, iter, first); });
         else emuLaunch(gx, gy, [&] { k_restir_a_exact<false>(s, d, c, p, looper, iter, first); });
     }
+}
+// rstr_restir_phase_b_pass: spatial pass `pass` of the frame's own rows (between the passes a strip's halo rows of the published plane
+// are exchanged by the caller); the last pass swaps the history
+void emu_di_phase_b_pass(void* fv, const RstrCamera* cam, const RstrParams* prm, int iter, int pass) {
+    EmuDI* f = (EmuDI*)fv;
+    const DevScene& s = f->dev;
+    const RstrParams p = *prm;
+    const bool sp = (p.reuse & 2) != 0;
+    FrameDev d = diFrameDev(f);
+    const unsigned gx = (unsigned)((f->W + 15) / 16), gy = (unsigned)((f->row1 - f->row0 + 7) / 8);
     const int passes = sp ? (p.spatialPasses < 1 ? 1 : p.spatialPasses) : 0;
-    for (int pass = 1; pass <= passes; pass++) {                      // rstr_restir_phase_b_pass
+    if (passes) {
         if (passes > 1 && !f->temp2Ready) { f->resvTemp2 = f->resvTemp; f->temp2Ready = true; }
         ResvD* buf[2] = {f->resvTemp.data(), f->resvTemp2.data()};
         const ResvD* src = buf[(pass - 1) & 1];
@@ -474,9 +499,27 @@ void emu_di_frame(void* fv, const RstrCamera* cam, const RstrParams* prm, int lo
         if (p.unbiased) emuLaunch(gx, gy, [&] { k_restir_b_unb(s, d, p, iter, src, dst, pass, last); });
         else emuLaunch(gx, gy, [&] { k_restir_b(s, d, p, iter, src, dst, pass, last); });
     }
-    f->resvOut ^= 1;
-    f->first = false;
+    if (pass >= passes) {
+        f->resvOut ^= 1;
+        f->first = false;
+    }
 }
+// rstr_frame_copy_rows: rows [r0, r1) of a plane from one strip's resident rows into another's.  0 geom_cur, 1 matid_cur, 2 resv_history,
+// 3 resv_temp, 4 resv_temp2, 5 resv_out
+int emu_di_copy_rows(void* dv, void* sv, int plane, int r0, int r1) {
+    EmuDI *dst = (EmuDI*)dv, *src = (EmuDI*)sv;
+    if (r0 < src->bufRow0 || r1 > src->bufRow0 + src->bufRows || r0 < dst->bufRow0 || r1 > dst->bufRow0 + dst->bufRows || r0 >= r1) return 1;
+    const size_t so = (size_t)(r0 - src->bufRow0) * src->W, dof = (size_t)(r0 - dst->bufRow0) * dst->W, cnt = (size_t)(r1 - r0) * src->W;
+    auto resv = [&](EmuDI* f) -> ResvD* {
+        if ((plane == 4) && !f->temp2Ready) { f->resvTemp2 = f->resvTemp; f->temp2Ready = true; }     // rsEnsureTemp2
+        return plane == 2 ? f->resv[f->resvOut ^ 1].data() : plane == 3 ? f->resvTemp.data() : plane == 4 ? f->resvTemp2.data() : f->resv[f->resvOut].data();
+    };
+    if (plane == 0) memcpy(dst->geom[dst->cur].data() + dof, src->geom[src->cur].data() + so, cnt * sizeof(float4));
+    else if (plane == 1) memcpy(dst->matId[dst->cur].data() + dof, src->matId[src->cur].data() + so, cnt * sizeof(int));
+    else memcpy(resv(dst) + dof, resv(src) + so, cnt * sizeof(ResvD));
+    return 0;
+}
+unsigned emu_di_halo_miss(void* fv) { return ((EmuDI*)fv)->counters[0]; }
 // rstr_gbuffer_render + rstr_pathtrace_direct (launchGBuffer, launchPTDirect)
 void emu_di_ptdirect(void* fv, const RstrCamera* cam, int looper, int iter) {
     EmuDI* f = (EmuDI*)fv;
@@ -499,7 +542,7 @@ unsigned emu_di_fixup_pixels(void* fv) { return ((EmuDI*)fv)->queueCount[0]; }
 // rstr_frame_read: 0 albedo 1 normal 2 matid 3 depth 4 motion 5 radiance 6 reservoir 7 reservoir_temp 8 light_index
 const void* emu_di_buffer(void* fv, int which) {
     EmuDI* f = (EmuDI*)fv;
-    const size_t n = (size_t)f->W * f->H;
+    const size_t n = (size_t)f->W * f->bufRows;                     // the resident rows (the caller cuts the strip's own rows out)
     const unsigned blocks = (unsigned)((n + RS_BLOCK - 1) / RS_BLOCK);
     const float4* g = f->geom[f->cur].data();
     const float4* am = f->albedoMotion.data();

@@ -39,6 +39,7 @@ def main():
         e.run_di(sd, 2, 3, orbit=orbit, pipeline=1)
         e.run_gi(sd, 2, 3, 1, orbit=orbit, staged=3)
         e.run_gi(sd, 2, 3, 1, orbit=orbit, staged=5)
+    e.run_di_strips(scenes.procedural(3, 2000, 100, (64, 56)), 2, (0, 13, 32, 56), halo=10, reuse=3, radius=5.0, passes=2)   # strips: plane indices relative to the resident rows
     e.run_denoiser(t.edge_scenes()["ragged"][0], 2, "svgf")
     e.run_denoiser(gen, 2, "eaw")
     e.run_denoiser(gen, 2, "svgf", modulate=True)

@@ -114,6 +114,21 @@ def test_di_kernels_as_warps_match_oracle(emu, port_oracle, name, res, reuse, pa
     assert (want[-1]["radiance"].sum(1) > 0).mean() > 0.2
 
 
+@pytest.mark.parametrize("passes", [1, 2, 3])
+def test_strips_of_kernels_as_warps_equal_the_full_frame(emu, port_oracle, passes):
+    """The multi-GPU decomposition with the kernels as warps: four uneven strips that render only their own rows, their G-buffer and
+    reservoir halo rows copied where the library pushes them to the neighbour (after phase A, between spatial passes, the history after the
+    frame) == the oracle's single full frame, bit for bit, with no read outside the resident rows -- strip-local plane indices, rowResident,
+    the global pixel / RNG indices of restir.cu:126-127."""
+    sd = scenes.procedural(3, 2000, 100, (96, 80))
+    want = helpers.run_oracle(port_oracle, sd, 3, 3, radius=6.0, passes=passes, light_index=True)
+    got, miss = emu.run_di_strips(sd, 3, (0, 21, 40, 64, 80), halo=12, reuse=3, radius=6.0, passes=passes)
+    for f in range(3):
+        for n in got[f]:
+            assert helpers.mismatches(got[f][n], want[f][n]) == 0, (f, n)
+    assert miss == [0, 0, 0, 0]
+
+
 def edge_scenes():
     """tests/test_gpu_parity.py::test_edge_cases: ragged resolution, a single (emissive) triangle, no lights, a camera that sees nothing,
     an exactly axis-aligned centre ray, a camera looking straight down."""
