@@ -724,6 +724,8 @@ def run_b200(args):
                     line["reference_cuda_ms"] = None
             except Exception as e:       # a baseline, not the product: never fails the bench
                 line["reference_cuda_ms"] = {"error": str(e)[-300:]}
+        if world == 1 and not args.no_targets:
+            line["restir_gi"] = gi_side_measurement()
         if world == 1 and not args.no_cpu_baseline:
             kind = reference_kind()
             t1, threads = cpu_frames(kind, sd, reuse, radius, 1, 0)
@@ -746,6 +748,24 @@ def run_b200(args):
         dist.destroy_process_group()
     if halo_miss != 0 or peer_error:
         sys.exit(3)
+
+
+def gi_side_measurement(timeout_s: int = 120):
+    """ReSTIR GI (rstr_restir_indirect, depth 3, temporal reuse) on the 1 M-triangle scene at 1080p, device-timed by
+    scripts/gi_bench.py in a child process after the frame measurements: ms / frame of the ray-queue and the staged launch forms.  A side
+    measurement of a "next" row: it can never fail or delay the bench line beyond its time-out."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts", "gi_bench.py"), "--workloads", "config4_1080p",
+                            "--steps", "10", "--modes", "queued", "staged", "--out", os.devnull], capture_output=True, text=True, timeout=timeout_s)
+        rows = [json.loads(x) for x in r.stdout.splitlines() if x.startswith("{")]
+        if not rows:
+            return {"error": (r.stderr or "no output")[-300:]}
+        return {"workload": "config4_1080p", "trace_depth": rows[0]["trace_depth"], "reuse": "temporal", "steps": rows[0]["steps"],
+                "ms_per_frame": {("ray_queues" if "ray queues" in x["pipeline"] else "staged"): x["gi_ms_per_frame"] for x in rows},
+                "fixup_pixels_per_frame": rows[0]["fixup_pixels_per_frame"], "lit_fraction": rows[0]["lit_fraction"],
+                "note": "rstr_restir_indirect alone (the G-buffer render of each frame is outside the CUDA events), scripts/gi_bench.py in a child process"}
+    except Exception as e:
+        return {"error": str(e)[-300:]}
 
 
 def main():

@@ -42,3 +42,28 @@ def test_orbit_clock_sweeps_the_60_frame_arc_back_and_forth():
     w = bench.window_frames(5, 20)                                       # the driver's --warmup 5 --steps 20: cuts for the timed stretch
     assert 1 <= len(w) <= 6 and w[0] == 5 and all(5 <= k < 25 for k in w) and w == sorted(w)
     assert bench.window_frames(0, 1) == [0] and len(bench.window_frames(51, 26)) <= 6
+
+
+def test_gi_side_measurement_never_fails_the_bench(monkeypatch):
+    """bench.py's `restir_gi` block comes from scripts/gi_bench.py in a child process: its lines are folded into one dict; without a GPU
+    (or with a child that dies or hangs) it degrades to {"error": ...} instead of raising."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    err = bench.gi_side_measurement(120)          # no GPU here: the child exits with a RestirError
+    assert set(err) == {"error"}
+    rows = [l for l in open(os.path.join(ROOT, "profiles", "r02_c35_gi_bench.jsonl")) if "config4_1080p" in l]
+
+    class Done:
+        stdout, stderr = "import noise\n" + "".join(rows), ""
+
+    monkeypatch.setattr(bench.subprocess, "run", lambda *a, **k: Done)
+    d = bench.gi_side_measurement()
+    assert d["workload"] == "config4_1080p" and d["trace_depth"] == 3 and set(d["ms_per_frame"]) == {"ray_queues", "staged"}
+    assert 0 < d["ms_per_frame"]["ray_queues"] < d["ms_per_frame"]["staged"]
+
+    def boom(*a, **k):
+        raise subprocess.TimeoutExpired("gi_bench", 1)
+
+    monkeypatch.setattr(bench.subprocess, "run", boom)
+    assert "error" in bench.gi_side_measurement()
