@@ -50,8 +50,8 @@ def test_gi_side_measurement_never_fails_the_bench(monkeypatch):
     sys.path.insert(0, ROOT)
     import bench
 
-    err = bench.gi_side_measurement(120)          # no GPU here: the child exits with a RestirError
-    assert set(err) == {"error"}
+    first = bench.gi_side_measurement(120)        # without a GPU the child exits with a RestirError; with one it measures
+    assert set(first) == {"error"} or first["ms_per_frame"]["ray_queues"] > 0
     rows = [l for l in open(os.path.join(ROOT, "profiles", "r02_c35_gi_bench.jsonl")) if "config4_1080p" in l]
 
     class Done:
