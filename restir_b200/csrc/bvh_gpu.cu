@@ -13,8 +13,10 @@
 //           triangles), a markedly slower tree to trace.
 // Both end in the kernels' 64-byte FastNode records (both children's padded boxes + links) and the triangle records re-ordered
 // into leaf order.  cub's radix sort / scan are library code on a non-hot path (scene (re)build).
+#ifndef RS_HOST_EMU      /* tests/emu compiles the kernels below with g++ and drives them itself (std::stable_sort / a serial scan for cub's) */
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#endif
 
 #include "capi_internal.h"
 
@@ -39,14 +41,21 @@ __device__ __forceinline__ unsigned long long expandBits(unsigned int v) {      
     return x;
 }
 
+// (the first read of the CAS loops below is a plain load racing with other blocks' CAS: a stale value only costs one more iteration.
+//  ThreadSanitizer's build of tests/emu reads it atomically so that the report list stays empty for real findings.)
+#ifdef RS_HOST_EMU
+#define RS_PEEK(p) __atomic_load_n(p, __ATOMIC_RELAXED)
+#else
+#define RS_PEEK(p) (*(p))
+#endif
 __device__ __forceinline__ void atomicMinF(float* a, float v) {
     int* ai = (int*)a;
-    int old = *ai;
+    int old = RS_PEEK(ai);
     while (v < __int_as_float(old)) { int assumed = old; old = atomicCAS(ai, assumed, __float_as_int(v)); if (old == assumed) break; }
 }
 __device__ __forceinline__ void atomicMaxF(float* a, float v) {
     int* ai = (int*)a;
-    int old = *ai;
+    int old = RS_PEEK(ai);
     while (v > __int_as_float(old)) { int assumed = old; old = atomicCAS(ai, assumed, __float_as_int(v)); if (old == assumed) break; }
 }
 
@@ -280,6 +289,7 @@ __global__ void k_bvh_reorder(const float4* tgOld, const unsigned int* slots, co
     primToFast[__float_as_int(c.z)] = dst;
 }
 
+#ifndef RS_HOST_EMU
 struct DevBuf {                       // frees what it allocated (and still owns) when it goes out of scope
     std::vector<void*> all;
     cudaError_t err = cudaSuccess;
@@ -292,9 +302,11 @@ struct DevBuf {                       // frees what it allocated (and still owns
     void release(void* p) { for (void*& q : all) if (q == p) q = nullptr; }
     ~DevBuf() { for (void* p : all) cudaFree(p); }
 };
+#endif
 
 }  // namespace
 
+#ifndef RS_HOST_EMU
 extern "C" {
 
 // Rebuild the traced tree of an uploaded scene on the device.  *milliseconds (may be NULL) receives the device time of the build.
@@ -400,3 +412,4 @@ int rstr_scene_build_traced_gpu(RstrScene* sc, int mode, float* milliseconds) {
 }
 
 }  // extern "C"
+#endif  // RS_HOST_EMU

@@ -9,7 +9,7 @@ CSRC = os.path.join(ROOT, "restir_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libkernels_emu.so")
 SOURCES = [os.path.join(HERE, "kernels_emu.cpp"), os.path.join(CSRC, "scene_host.cpp"), os.path.join(CSRC, "bvh_fast.cpp")]
 DEPS = SOURCES + [os.path.join(HERE, "cuda_host_shim.h")] + [os.path.join(CSRC, f) for f in
-                                                             ("kernels.cu", "gi_kernels.inl", "denoise.cu", "capi_internal.h", "kernels.h", "device_types.h", "vecmath.h", "camera_dev.h", "scene_host.h")]
+                                                             ("kernels.cu", "gi_kernels.inl", "denoise.cu", "bvh_gpu.cu", "capi_internal.h", "kernels.h", "device_types.h", "vecmath.h", "camera_dev.h", "scene_host.h")]
 
 
 def build(force: bool = False, sanitize: str = "") -> str:

@@ -45,15 +45,32 @@ static inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4);
 static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
-static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+// CUDA's atomics are relaxed and the kernels order them with __threadfence() where it matters (bvh_gpu.cu's bottom-up pass: "the second child
+// to arrive finishes the node").  TSan does not model fences, so in its build the read-modify-writes themselves carry acquire / release --
+// the standard reading of the fence + atomic idiom; elsewhere they stay relaxed.
+#if defined(__SANITIZE_THREAD__)
+#define EMU_RMW __ATOMIC_ACQ_REL
+#else
+#define EMU_RMW __ATOMIC_RELAXED
+#endif
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, EMU_RMW); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, EMU_RMW); }
 static inline unsigned atomicMax(unsigned* p, unsigned v) {
     unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (o < v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     return o;
 }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, EMU_RMW); }
+static inline int atomicCAS(int* p, int expected, int desired) { __atomic_compare_exchange_n(p, &expected, desired, false, EMU_RMW, __ATOMIC_RELAXED); return expected; }
+static inline int atomicMax(int* p, int v) {
+    int o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (o < v && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline long long clock64() { return 0; }
-static inline void __syncthreads() {}
 static inline void __trap() { abort(); }
 // ---- warps.  Outside emuRunWarp a "warp" has one lane (the per-pixel emulation: one call = one thread).  Inside emuRunWarp the 32 lanes of
 // a warp are 32 fibers (own stacks, switched by hand) on one OS thread: a lane runs until its next warp-level intrinsic, deposits its value and yields; when
@@ -99,15 +116,18 @@ void __tsan_switch_to_fiber(void* fiber, unsigned flags);
 #else
 #define EMU_TSAN_SWITCH(fiber) ((void)0)
 #endif
+#define EMU_MAX_LANES 256                        /* 32: a warp; up to 256: a whole block whose only synchronisation is __syncthreads (emuLaunchBlock) */
 struct EmuWarp {
     void* tsanSched;
-    void* tsanLane[32];
-    EmuCtx sched, ctx[32];
-    bool done[32];
+    void* tsanLane[EMU_MAX_LANES];
+    EmuCtx sched, ctx[EMU_MAX_LANES];
+    bool done[EMU_MAX_LANES];
     int lane;                                    // the lane that is running
-    unsigned sync[32];                           // synchronisation points passed, per lane
-    unsigned long long val[2][32];
-    bool has[2][32];                             // the lane has deposited at this point (false: it had exited before)
+    int nLanes;
+    bool block;                                  // the lanes are a thread block: __syncthreads is their synchronisation point
+    unsigned sync[EMU_MAX_LANES];                // synchronisation points passed, per lane
+    unsigned long long val[2][EMU_MAX_LANES];
+    bool has[2][EMU_MAX_LANES];                  // the lane has deposited at this point (false: it had exited before)
     void (*body)(void*);
     void* arg;
 };
@@ -139,7 +159,8 @@ static void emuTrampoline() {
 #endif
 }
 // run `body(arg)` as the 32 lanes tidBase .. tidBase + 31 of one warp; blockIdx / blockDim / gridDim are the caller's
-static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg);
+static inline void emuRunLanes(unsigned tidBase, int nLanes, bool block, void (*body)(void*), void* arg);
+static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) { emuRunLanes(tidBase, 32, false, body, arg); }
 
 static inline int __any_sync(unsigned, int p) {
     if (!emuWarp) return p;
@@ -204,6 +225,7 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned x) {
     return r;
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { if (emuWarp) emuExchange(0); }
+static inline void __syncthreads() { if (emuWarp && emuWarp->block) emuExchange(0); }   // warps of a grid launched with emuLaunch share nothing
 static inline unsigned __match_any_sync(unsigned, unsigned) { return 1u; }          // one-lane form only (not used under emuRunWarp)
 static inline unsigned __activemask() { return 1u; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
@@ -218,7 +240,8 @@ static inline void* emuSharedPtr(unsigned off) { return (void*)((uintptr_t)&emuS
 #if defined(__SANITIZE_ADDRESS__)
 extern "C" void __asan_unpoison_memory_region(void const volatile* addr, size_t size);
 #endif
-static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) {
+static inline void emuRunLanes(unsigned tidBase, int nLanes, bool block, void (*body)(void*), void* arg) {
+    const size_t stackSize = ((size_t)32 * EMU_FIBER_STACK / nLanes) & ~(size_t)4095;      // 512 KB per lane of a warp, 64 KB per lane of a 256-thread block
     if (!emuStacks) emuStacks = (char*)malloc((size_t)32 * EMU_FIBER_STACK);
 #if defined(__SANITIZE_ADDRESS__)
     // the previous warp's lanes never returned from their trampolines: the redzones of their frames are still poisoned
@@ -226,26 +249,26 @@ static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) 
 #endif
     EmuWarp w;
     memset(w.done, 0, sizeof w.done); memset(w.sync, 0, sizeof w.sync); memset(w.val, 0, sizeof w.val); memset(w.has, 0, sizeof w.has);
-    w.body = body; w.arg = arg; w.lane = 0;
-    for (int l = 0; l < 32; l++) {
+    w.body = body; w.arg = arg; w.lane = 0; w.nLanes = nLanes; w.block = block;
+    for (int l = 0; l < nLanes; l++) {
 #if defined(__x86_64__)
-        emuMakeCtx(&w.ctx[l], emuStacks + (size_t)l * EMU_FIBER_STACK, EMU_FIBER_STACK, emuTrampoline);
+        emuMakeCtx(&w.ctx[l], emuStacks + (size_t)l * stackSize, stackSize, emuTrampoline);
 #else
         getcontext(&w.ctx[l]);
-        w.ctx[l].uc_stack.ss_sp = emuStacks + (size_t)l * EMU_FIBER_STACK;
-        w.ctx[l].uc_stack.ss_size = EMU_FIBER_STACK;
+        w.ctx[l].uc_stack.ss_sp = emuStacks + (size_t)l * stackSize;
+        w.ctx[l].uc_stack.ss_size = stackSize;
         w.ctx[l].uc_link = &w.sched;
         makecontext(&w.ctx[l], emuTrampoline, 0);
 #endif
     }
 #if defined(__SANITIZE_THREAD__)
     w.tsanSched = __tsan_get_current_fiber();
-    for (int l = 0; l < 32; l++) w.tsanLane[l] = __tsan_create_fiber(0);
+    for (int l = 0; l < nLanes; l++) w.tsanLane[l] = __tsan_create_fiber(0);
 #endif
     emuWarp = &w;
     for (;;) {
         bool any = false;
-        for (int l = 0; l < 32; l++)
+        for (int l = 0; l < nLanes; l++)
             if (!w.done[l]) {
                 any = true;
                 w.lane = l;
@@ -254,12 +277,12 @@ static inline void emuRunWarp(unsigned tidBase, void (*body)(void*), void* arg) 
                 emuSwitch(&w.sched, w.ctx[l]);
             }
         if (!any) break;
-        for (int l = 0; l < 32; l++)
+        for (int l = 0; l < nLanes; l++)
             if (w.done[l]) { w.val[0][l] = w.val[1][l] = 0; w.has[0][l] = w.has[1][l] = false; }
     }
     emuWarp = nullptr;
 #if defined(__SANITIZE_THREAD__)
-    for (int l = 0; l < 32; l++) __tsan_destroy_fiber(w.tsanLane[l]);
+    for (int l = 0; l < nLanes; l++) __tsan_destroy_fiber(w.tsanLane[l]);
 #endif
 }
 // a grid of blocks of 32 * warpsPerBlock threads (128 unless said otherwise); the warps of the grid run on the OpenMP threads, each warp
@@ -291,4 +314,29 @@ template <typename F> static inline void emuLaunch(unsigned gridX, unsigned grid
                 blockIdx.x = bx; blockIdx.y = by; gridDim.x = gridX; gridDim.y = gridY; blockDim.x = 32 * warpsPerBlock;
                 emuRunWarp(wp * 32, &Call::run, &kernelCall);
             }
+}
+// a grid of blocks whose threads synchronise with __syncthreads (and use no warp intrinsic): the whole block is one set of fibers on one OS
+// thread, so its __shared__ arrays are shared by exactly its threads
+template <typename F> static inline void emuLaunchBlock(unsigned gridX, F kernelCall, unsigned threadsPerBlock = 256) {
+    struct Call { static void run(void* a) { (*(F*)a)(); } };
+#ifdef EMU_STD_THREADS
+    {
+        std::atomic<unsigned> next{0};
+        auto worker = [&] {
+            for (unsigned b = next.fetch_add(1, std::memory_order_relaxed); b < gridX; b = next.fetch_add(1, std::memory_order_relaxed)) {
+                blockIdx.x = b; blockIdx.y = 0; gridDim.x = gridX; gridDim.y = 1; blockDim.x = threadsPerBlock;
+                emuRunLanes(0, (int)threadsPerBlock, true, &Call::run, &kernelCall);
+            }
+        };
+        std::thread pool[4];
+        for (auto& t : pool) t = std::thread(worker);
+        for (auto& t : pool) t.join();
+        return;
+    }
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (unsigned b = 0; b < gridX; b++) {
+        blockIdx.x = b; blockIdx.y = 0; gridDim.x = gridX; gridDim.y = 1; blockDim.x = threadsPerBlock;
+        emuRunLanes(0, (int)threadsPerBlock, true, &Call::run, &kernelCall);
+    }
 }

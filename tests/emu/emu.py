@@ -44,6 +44,8 @@ class Emu:
         L.emu_di_fixup_pixels.argtypes = [vp]
         L.emu_di_buffer.restype = vp
         L.emu_di_buffer.argtypes = [vp, ip]
+        L.emu_scene_build_traced.restype = ip
+        L.emu_scene_build_traced.argtypes = [vp, ip]
         L.emu_di_create_strip.restype = vp
         L.emu_di_create_strip.argtypes = [vp, ip, ip, ip, ip, ip]
         L.emu_di_phase_a.argtypes = [vp, C.POINTER(api.RstrCamera), C.POINTER(api.RstrParams), ip, ip, ip, ip]
@@ -63,6 +65,8 @@ class Emu:
         L.emu_denoiser_variance.restype = vp
         L.emu_denoiser_variance.argtypes = [vp]
 
+    traced_build = None      # 0 / 1: rebuild the traced tree with the device-side builder's kernels (PLOC / radix tree) after scene creation
+
     def scene(self, sd):
         v = np.ascontiguousarray(sd.vertices, np.float32)
         n = np.ascontiguousarray(sd.normals, np.float32)
@@ -77,6 +81,9 @@ class Emu:
                                  len(texs), C.cast(tarr, C.c_void_p) if texs else None, int(getattr(sd, "env_map", -1)) + 1)
         h = self.lib.emu_scene_create(C.byref(desc))
         assert h, "emu_scene_create failed"
+        if self.traced_build is not None:
+            rc = self.lib.emu_scene_build_traced(h, self.traced_build)
+            assert rc == 0, "emu_scene_build_traced failed: %d" % rc
         return h
 
     @staticmethod

@@ -8,6 +8,10 @@
 
 #include "../../restir_b200/csrc/kernels.cu"
 #include "../../restir_b200/csrc/denoise.cu"
+#include "../../restir_b200/csrc/bvh_gpu.cu"
+
+#include <algorithm>
+#include <numeric>
 
 #include <string>
 #include <vector>
@@ -647,3 +651,72 @@ const float* emu_denoiser_color(void* dv) { return ((EmuDenoiser*)dv)->colorOut;
 const float* emu_denoiser_variance(void* dv) { return ((EmuDenoiser*)dv)->variance; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ the device-side tree build as warps / blocks
+// rstr_scene_build_traced_gpu (bvh_gpu.cu) on an emulated scene: the same kernels in the same order; cub's radix sort and exclusive scan
+// (library code) are std::stable_sort by key and a serial scan.  The new tree replaces the host-built one the scene's DevScene points at.
+extern "C" int emu_scene_build_traced(void* scv, int mode) {
+    EmuScene* sc = (EmuScene*)scv;
+    HostScene& hs = sc->hs;
+    const int T = hs.T;
+    if (T < 8 || (mode != 0 && mode != 1)) return 1;
+    const size_t N2 = 2 * (size_t)T - 1;
+    std::vector<unsigned long long> keys(T), keysSorted(T);
+    std::vector<unsigned int> slots(T), slotsSorted(T), arrived(T, 0u);
+    std::vector<int> left(N2, 0), right(N2, 0), parent(N2, 0), count(N2, 0), firstPos(N2, 0), cidA(T), cidB(T), cidTmp(T), keep(T), pos(T), nearest(T);
+    std::vector<float> cost(N2, 0.f);
+    std::vector<GBox> box(N2);
+    int scalars[4] = {0, 0, 0, 0};
+    float bounds[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+    std::vector<FastNode> nodes(T - 1);
+    std::vector<TriGeom> tgNew(T);
+    std::vector<int> primToFast(T);
+    const float4* tg = (const float4*)hs.fastTris.data();
+    const int B = 256, G = (T + B - 1) / B;
+    emuLaunchBlock((unsigned)std::min(G, 1184), [&] { k_bvh_scene_bounds(tg, T, bounds); });
+    emuLaunchBlock((unsigned)G, [&] { k_bvh_morton(tg, T, bounds, keys.data(), slots.data()); });
+    {                                                                // cub::DeviceRadixSort::SortPairs: stable, ascending keys
+        std::vector<int> order(T);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+        for (int i = 0; i < T; i++) { keysSorted[i] = keys[order[i]]; slotsSorted[i] = slots[order[i]]; }
+    }
+    int root = T;
+    if (mode == 1) {
+        emuLaunchBlock((unsigned)G, [&] { k_bvh_radix_tree(keysSorted.data(), T, left.data(), right.data(), parent.data()); });
+        emuLaunchBlock((unsigned)G, [&] { k_bvh_bottom_up(tg, slotsSorted.data(), T, left.data(), right.data(), parent.data(), box.data(), count.data(), cost.data(), arrived.data()); });
+    } else {
+        emuLaunchBlock((unsigned)G, [&] { k_ploc_init(tg, slotsSorted.data(), T, box.data(), count.data(), cost.data(), parent.data(), cidA.data()); });
+        int n = T;
+        int *cur = cidA.data(), *nxt = cidB.data();
+        while (n > 1) {
+            const int g = (n + B - 1) / B;
+            emuLaunchBlock((unsigned)g, [&] { k_ploc_nearest(cur, n, box.data(), nearest.data()); });
+            emuLaunchBlock((unsigned)g, [&] { k_ploc_merge(cur, n, nearest.data(), T, box.data(), count.data(), cost.data(), left.data(), right.data(), parent.data(), scalars, cidTmp.data(), keep.data()); });
+            int run = 0;                                             // cub::DeviceScan::ExclusiveSum
+            for (int i = 0; i < n; i++) { pos[i] = run; run += keep[i]; }
+            emuLaunchBlock((unsigned)g, [&] { k_ploc_compact(cidTmp.data(), keep.data(), pos.data(), n, nxt, scalars + 1); });
+            const int n2 = scalars[1];
+            if (n2 >= n) return 2;
+            n = n2;
+            std::swap(cur, nxt);
+        }
+        root = cur[0];
+    }
+    const int G2 = (int)((N2 + B - 1) / B);
+    emuLaunchBlock((unsigned)G2, [&] { k_bvh_first(T, (int)N2, left.data(), right.data(), parent.data(), count.data(), firstPos.data(), scalars + 2); });
+    emuLaunchBlock((unsigned)G, [&] { k_bvh_emit(T, left.data(), right.data(), box.data(), count.data(), cost.data(), firstPos.data(), nodes.data()); });
+    emuLaunchBlock((unsigned)G, [&] { k_bvh_reorder(tg, slotsSorted.data(), firstPos.data(), T, (float4*)tgNew.data(), primToFast.data()); });
+    const int depth = scalars[2];
+    if (depth + 1 > RS_PACKET_STACK) return 3;
+    const GBox rootBox = box[root];
+    hs.fastNodes.swap(nodes); hs.fastTris.swap(tgNew); hs.primToFast.swap(primToFast);      // swap the new tree in
+    DevScene& d = sc->dev;
+    d.fastNodes = (const float4*)hs.fastNodes.data(); d.triGeom = (const float4*)hs.fastTris.data(); d.primToFast = hs.primToFast.data();
+    d.numFastNodes = T - 1; d.fastRoot = root - T;
+    for (int a = 0; a < 3; a++) {
+        const float pad = 4e-6f * fmaxf(fabsf(rootBox.lo[a]), fabsf(rootBox.hi[a])) + 1e-7f;
+        d.fastRootMin[a] = rootBox.lo[a] - pad; d.fastRootMax[a] = rootBox.hi[a] + pad;
+    }
+    return 0;
+}

@@ -41,6 +41,11 @@ def main():
         e.run_gi(sd, 2, 3, 1, orbit=orbit, staged=5)
     e.run_di_strips(scenes.procedural(3, 2000, 100, (64, 56)), 2, (0, 13, 32, 56), halo=10, reuse=3, radius=5.0, passes=2)   # strips: plane indices relative to the resident rows
     e.run_denoiser(t.edge_scenes()["ragged"][0], 2, "svgf")
+    for mode in (0, 1):                                                   # bvh_gpu.cu: the device-side builders' kernels as 256-thread blocks, then frames on their trees
+        e.traced_build = mode
+        e.run_di(gen, 1, 3)
+        e.run_gi(gen, 1, 3, 1, staged=3)
+    e.traced_build = None
     e.run_denoiser(gen, 2, "eaw")
     e.run_denoiser(gen, 2, "svgf", modulate=True)
     print("sanitizer child: all kernel families ran")

@@ -129,6 +129,25 @@ def test_strips_of_kernels_as_warps_equal_the_full_frame(emu, port_oracle, passe
     assert miss == [0, 0, 0, 0]
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_device_side_tree_build_as_blocks_gives_the_same_frames(emu, port_oracle, mode):
+    """rstr_scene_build_traced_gpu's kernels (bvh_gpu.cu: Morton codes, PLOC clustering rounds or the binary radix tree with its bottom-up
+    pass, the leaf rule, node emission, triangle re-ordering) run as 256-thread blocks on the CPU (__syncthreads = the block's
+    synchronisation point, __shared__ per block, real atomics); the direct path's and the GI kernels then trace THAT tree: the frames are
+    the oracle's bit for bit, because what a ray reports does not depend on the tree it walks."""
+    sd = scenes.procedural(3, 2000, 100, (96, 72))
+    want = helpers.run_oracle(port_oracle, sd, 2, 3, light_index=True)
+    want_gi = helpers.run_oracle_gi(port_oracle, sd, 2, 3, 1)
+    emu.traced_build = mode
+    try:
+        got, _ = emu.run_di(sd, 2, 3, light_index=True)
+        got_gi, _ = emu.run_gi(sd, 2, 3, 1, staged=3)
+    finally:
+        emu.traced_build = None
+    helpers.assert_frames_equal(got, want, "direct path on the device-built tree (mode %d)" % mode)
+    helpers.assert_frames_equal(got_gi, want_gi, "GI ray queues on the device-built tree (mode %d)" % mode)
+
+
 def edge_scenes():
     """tests/test_gpu_parity.py::test_edge_cases: ragged resolution, a single (emissive) triangle, no lights, a camera that sees nothing,
     an exactly axis-aligned centre ray, a camera looking straight down."""

@@ -27,6 +27,9 @@ def run_child(tool, what, fault=None):
     if not os.path.isabs(emu_build.sanitizer_runtime(tool)):
         pytest.skip("gcc has no %s sanitizer runtime here" % tool)
     emu_build.build(sanitize=tool)
+    from restir_b200 import build as product_build
+
+    product_build.build()                     # the child uses the library's host-side camera functions: never let it run nvcc under a sanitizer preload
     env = dict(os.environ)
     env["LD_PRELOAD"] = emu_build.sanitizer_runtime(tool)
     env["ASAN_OPTIONS"] = "detect_leaks=0:abort_on_error=0"        # the interpreter's own allocations are not the subject
