@@ -52,6 +52,7 @@ class Emu:
         L.emu_di_phase_b_pass.argtypes = [vp, C.POINTER(api.RstrCamera), C.POINTER(api.RstrParams), ip, ip]
         L.emu_di_copy_rows.restype = ip
         L.emu_di_copy_rows.argtypes = [vp, vp, ip, ip, ip]
+        L.emu_di_set_bands.argtypes = [vp, ip]
         L.emu_di_halo_miss.restype = C.c_uint
         L.emu_di_halo_miss.argtypes = [vp]
         L.emu_denoiser_create.restype = vp
@@ -122,7 +123,7 @@ class Emu:
     DI_BUF = {"albedo": (0, np.float32, 3), "normal": (1, np.float32, 3), "matid": (2, np.int32, 0), "depth": (3, np.float32, 0), "motion": (4, np.int32, 0),
               "radiance": (5, np.float32, 3), "reservoir": (6, None, 0), "reservoir_temp": (7, None, 0), "light_index": (8, np.int32, 0)}
 
-    def run_di(self, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=None, passes=1, drain=True, light_index=False, pipeline=0, unbiased=False, ptdirect=False, looper0=0):
+    def run_di(self, sd, frames, reuse, radius=5.0, k=5, cap=20, candidates=32, accumulate=False, orbit=True, want=None, passes=1, drain=True, light_index=False, pipeline=0, unbiased=False, ptdirect=False, looper0=0, bands=1):
         """The frame loop of helpers.run_gpu with the staged pipeline's KERNELS run as 32-lane warps on the CPU (emu_di_frame).  Returns
         (frames, fix-up pixels of the last frame)."""
         from oracle.oracle import RESERVOIR_DTYPE
@@ -131,6 +132,7 @@ class Emu:
         L = self.lib
         sc = self.scene(sd)
         fr = L.emu_di_create(sc, W, H)
+        L.emu_di_set_bands(fr, bands)
         base = api.Camera.from_scene(sd)
         prm = api.default_params(reuse=reuse, radius=radius, k=k, cap=cap, candidates=candidates, passes=passes, unbiased=unbiased)
         names = list(want or ("albedo", "normal", "matid", "depth", "motion", "radiance", "reservoir", "reservoir_temp")) + (["light_index"] if light_index else [])

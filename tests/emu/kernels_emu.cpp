@@ -367,6 +367,7 @@ struct EmuDI {
     unsigned int queueCount[4 + 2 * RS_MAX_BANDS];
     unsigned int counters[4] = {0, 0, 0, 0};
     int cur = 0, resvOut = 0;
+    int bands = 1;                               // rstr_frame_set_bands: the staged pipeline cuts the rows into bands with a queue each
     bool first = true, haveLast = false, temp2Ready = false;
     RstrCamera lastCamera{};
 };
@@ -441,18 +442,31 @@ void emu_di_phase_a(void* fv, const RstrCamera* cam, const RstrParams* prm, int 
     if (pipeline == 0) {
         d.resvStage = sp ? f->resvTemp.data() : f->resvTemp2.data();
         if (!sp) f->temp2Ready = false;
-        if (sp) emuLaunch(gx, gy, [&] { k_primary<true>(s, d, c, lc, looper, iter); });
-        else emuLaunch(gx, gy, [&] { k_primary<false>(s, d, c, lc, looper, iter); });
-        emuLaunch(linear, 1, [&] { k_candidates(s, d, c, p, looper); });
-        if (!p.unbiased) {
-            if (drain) emuLaunch(3, 1, [&] { k_shadow<true>(s, d); });
-            else emuLaunch(3, 1, [&] { k_shadow<false>(s, d); });
+        // launchPhaseAStaged: up to RS_MAX_BANDS horizontal bands of whole 8-row tiles, each with its own shaded-pixel queue
+        const int rows = d.rowHi - d.rowLo;
+        int bands = f->bands < 1 ? 1 : (f->bands > RS_MAX_BANDS ? RS_MAX_BANDS : f->bands);
+        const int bandRows = ((rows + bands - 1) / bands + 7) & ~7;
+        if (bandRows * (bands - 1) >= rows) bands = (rows + bandRows - 1) / bandRows;
+        for (int b = 0; b < bands; b++) {
+            FrameDev fb = d;
+            fb.rowLo = d.rowLo + b * bandRows;
+            fb.rowHi = fb.rowLo + bandRows < d.rowHi ? fb.rowLo + bandRows : d.rowHi;
+            fb.shadeCount = f->queueCount + 4 + 2 * b;
+            fb.shadeQueue = d.shadeQueue + (size_t)(fb.rowLo - d.rowLo) * d.W;
+            const unsigned by = (unsigned)((fb.rowHi - fb.rowLo + 7) / 8), lin = gx * by;
+            if (sp) emuLaunch(gx, by, [&] { k_primary<true>(s, fb, c, lc, looper, iter); });
+            else emuLaunch(gx, by, [&] { k_primary<false>(s, fb, c, lc, looper, iter); });
+            emuLaunch(lin, 1, [&] { k_candidates(s, fb, c, p, looper); });
+            if (!p.unbiased) {
+                if (drain) emuLaunch(3, 1, [&] { k_shadow<true>(s, fb); });
+                else emuLaunch(3, 1, [&] { k_shadow<false>(s, fb); });
+            }
+            if (p.unbiased) {
+                if (sp) emuLaunch(lin, 1, [&] { k_temporal_unb<true>(s, fb, p, iter, first); });
+                else emuLaunch(lin, 1, [&] { k_temporal_unb<false>(s, fb, p, iter, first); });
+            } else if (sp) emuLaunch(lin, 1, [&] { k_temporal<true>(s, fb, p, iter, first); });
+            else emuLaunch(lin, 1, [&] { k_temporal<false>(s, fb, p, iter, first); });
         }
-        if (p.unbiased) {
-            if (sp) emuLaunch(linear, 1, [&] { k_temporal_unb<true>(s, d, p, iter, first); });
-            else emuLaunch(linear, 1, [&] { k_temporal_unb<false>(s, d, p, iter, first); });
-        } else if (sp) emuLaunch(linear, 1, [&] { k_temporal<true>(s, d, p, iter, first); });
-        else emuLaunch(linear, 1, [&] { k_temporal<false>(s, d, p, iter, first); });
         if (sp) emuLaunch(2, 1, [&] { k_gbuffer_restir_a_fix<true>(s, d, c, lc, p, looper, iter, first); });
         else emuLaunch(2, 1, [&] { k_gbuffer_restir_a_fix<false>(s, d, c, lc, p, looper, iter, first); });
     } else if (pipeline == 1) {
@@ -538,6 +552,7 @@ void emu_di_ptdirect(void* fv, const RstrCamera* cam, int looper, int iter) {
     emuLaunch(gx, gy, [&] { k_ptdirect(s, d, c, looper, iter); });
     emuLaunch(2, 1, [&] { k_ptdirect_fix(s, d, c, looper, iter); });
 }
+void emu_di_set_bands(void* fv, int bands) { ((EmuDI*)fv)->bands = bands; }
 void emu_di_update(void* fv, const RstrCamera* cam) {
     EmuDI* f = (EmuDI*)fv;
     f->lastCamera = *cam; f->haveLast = true; f->cur ^= 1;

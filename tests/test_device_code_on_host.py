@@ -148,6 +148,16 @@ def test_device_side_tree_build_as_blocks_gives_the_same_frames(emu, port_oracle
     helpers.assert_frames_equal(got_gi, want_gi, "GI ray queues on the device-built tree (mode %d)" % mode)
 
 
+@pytest.mark.parametrize("bands", [2, 3, 8])
+def test_di_staged_bands_as_warps_match_oracle(emu, port_oracle, bands):
+    """rstr_frame_set_bands: the staged pipeline over horizontal bands of whole 8-row tiles, each with its own shaded-pixel queue and cursor
+    (launchPhaseAStaged), incl. a last band that is shorter and a band count the image cannot fill."""
+    sd = scenes.procedural(3, 2000, 100, (96, 52))
+    want = helpers.run_oracle(port_oracle, sd, 3, 3, light_index=True)
+    got, _ = emu.run_di(sd, 3, 3, bands=bands, light_index=True)
+    helpers.assert_frames_equal(got, want, "staged pipeline in %d bands" % bands)
+
+
 def edge_scenes():
     """tests/test_gpu_parity.py::test_edge_cases: ragged resolution, a single (emissive) triangle, no lights, a camera that sees nothing,
     an exactly axis-aligned centre ray, a camera looking straight down."""
