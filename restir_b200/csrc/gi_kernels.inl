@@ -8,6 +8,8 @@
 //                            nothing and is queued.
 //   k_gi_primary / k_gi_bounce / k_gi_resolve   the same frame as a wavefront (rstr_gi_set_pipeline): one launch per iteration of the path
 //                            loop over the compacted live paths; bit-identical to k_restir_indirect (see "the staged form" below)
+//   k_gi_head / k_gi_walk_shadow / k_gi_walk_closest / k_gi_tail   the wavefront with the walks of an iteration as persistent kernels over
+//                            ray lists, lanes refilled from the list as they finish (see "the ray-queue form"); the default on real scenes
 //   k_restir_indirect_fix    the queued pixels again with the reference-order walk of the reference tree
 //   k_restir_indirect_exact  every ray with the reference-order walk (RS_TRAVERSAL_EXACT: validation mode)
 //   k_export_gi              device reservoirs -> Reservoir<IndirectLiSample> (68 B: Lo xv nv xs ns, numSamples, weight; restir.h:13-27)
