@@ -1,0 +1,90 @@
+"""Fuzz the library's kernels against the oracle without a GPU: random triangle soups (clustered, grid-snapped vertices: shared edges, coplanar
+faces, hits at equal distance = near ties; slivers; Lambertian / metal / glass / emitters; random cameras and ragged resolutions) through
+the kernels run as 32-lane warps on the CPU (tests/emu), every buffer of two frames compared bit for bit with the oracle: the direct path
+(RIS / temporal / spatial / spatiotemporal, 1-3 passes, staged and fused pipelines) and ReSTIR GI (ray queues / staged / one kernel).
+
+    python scripts/fuzz_kernels_on_cpu.py <first seed> <last seed>        # ~100 scenes per second
+
+tests/test_device_code_on_host.py::test_fuzzed_scenes_as_warps_match_oracle runs a bounded range of seeds."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emu")):
+    sys.path.insert(0, _p)
+import numpy as np
+import helpers
+from emu import Emu
+from oracle import oracle as orc_mod
+from restir_b200 import scenes
+
+def soup(seed):
+    """random triangle soup: clustered + grid-snapped vertices (shared edges, coplanar and coincident-distance hits = near ties), slivers,
+    random emitters / metals / glass, random camera"""
+    r = np.random.default_rng(seed)
+    T = int(r.integers(9, 120))
+    snap = r.choice([0.0, 0.25, 0.5])
+    c = r.uniform(-1.5, 1.5, (T, 1, 3)).astype(np.float32)
+    v = (c + r.normal(0, r.choice([0.05, 0.4, 1.0]), (T, 3, 3))).astype(np.float32)
+    if snap:
+        v = (np.round(v / snap) * snap).astype(np.float32)
+    if r.random() < 0.35:
+        # a stack of overlapping coplanar triangles (shifted in their plane): a ray through the overlap hits them all at the same distance,
+        # more near ties than a ray keeps -> undecided -> the fix-up kernels (reference-order walk)
+        k = int(r.integers(3, 9))
+        base = r.uniform(-1, 1, (3, 3)).astype(np.float32) * 1.5
+        e1, e2 = base[1] - base[0], base[2] - base[0]
+        stack = np.stack([base + (e1 * r.uniform(-0.2, 0.2) + e2 * r.uniform(-0.2, 0.2)).astype(np.float32) for _ in range(k)])
+        v = np.concatenate([v, stack.astype(np.float32)])
+        T = len(v)
+    # drop degenerate triangles (the reference's builder needs distinct centroids; zero-area triangles are culled by the determinant test anyway)
+    e1, e2 = v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]
+    area = np.linalg.norm(np.cross(e1, e2), axis=1)
+    cen = v.mean(1)
+    _, first = np.unique(np.round(cen, 5), axis=0, return_index=True)
+    keep = np.zeros(T, bool); keep[first] = True
+    keep &= area > 1e-4
+    v = v[keep]
+    T = len(v)
+    if T < 9:
+        return None
+    verts = v.reshape(-1, 3)
+    mats = scenes.make_materials([(scenes.LAMBERTIAN, (0.7, 0.6, 0.5), 0.0, 1.0), (scenes.METALLIC_WORKFLOW, (0.9, 0.8, 0.7), float(r.uniform(0, 1)), float(r.uniform(0.05, 1))),
+                                  (scenes.DIELECTRIC, (0.95, 0.95, 1.0), 0.0, 0.0), (scenes.LIGHT, (8, 7, 6), 0.0, 1.0), (scenes.LIGHT, (2, 9, 3), 0.0, 1.0)])
+    ids = r.choice(5, T, p=[0.45, 0.2, 0.1, 0.15, 0.1]).astype(np.int32)
+    eye = tuple(float(x) for x in r.uniform(-3, 3, 3))
+    rot = (float(r.uniform(-180, 180)), float(r.uniform(-60, 60)), 0.0)
+    W, H = int(r.integers(17, 49)), int(r.integers(9, 33))
+    return scenes.SceneData("soup%d" % seed, verts, scenes._face_normals(verts), np.zeros((3 * T, 2), np.float32), ids, mats, ["a", "b", "c", "d", "e"],
+                            eye=eye, rotation=rot, fovy=float(r.uniform(15, 40)), resolution=(W, H))
+
+def run(e, orc, lo, hi, verbose=True):
+    bad = 0; ran = 0; fixups = 0; lit = 0; t0 = time.time()
+    for seed in range(lo, hi):
+        sd = soup(seed)
+        if sd is None: continue
+        ran += 1
+        reuse = seed % 4; passes = 1 + seed % 3 if reuse & 2 else 1
+        try:
+            want = helpers.run_oracle(orc, sd, 2, reuse, passes=passes, light_index=True)
+        except Exception as ex:
+            print(seed, "oracle rejected:", str(ex)[:80])
+            continue
+        got, fix = e.run_di(sd, 2, reuse, passes=passes, light_index=True, pipeline=seed % 2)
+        m = {n: helpers.mismatches(got[f][n], want[f][n]) for f in range(2) for n in want[f] if helpers.mismatches(got[f][n], want[f][n])}
+        wg = helpers.run_oracle_gi(orc, sd, 2, 3, 1)
+        gg, _ = e.run_gi(sd, 2, 3, 1, staged=3 + seed % 3)
+        mg = {n: helpers.mismatches(gg[f][n], wg[f][n]) for f in range(2) for n in wg[f] if helpers.mismatches(gg[f][n], wg[f][n])}
+        fixups += fix > 0
+        lit += bool((want[-1]["radiance"].sum(1) > 0).any())
+        if m or mg:
+            bad += 1
+            print("MISMATCH seed", seed, sd.num_tris, sd.resolution, reuse, passes, m, mg, "fix", fix, flush=True)
+    if verbose:
+        print("scenes %d, mismatching %d, with fix-up pixels %d, with lit pixels %d, %.1f s" % (ran, bad, fixups, lit, time.time() - t0))
+    return ran, bad
+
+
+if __name__ == "__main__":
+    run(Emu(), orc_mod.Oracle("port"), int(sys.argv[1]), int(sys.argv[2]))

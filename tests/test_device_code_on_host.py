@@ -158,6 +158,17 @@ def test_di_staged_bands_as_warps_match_oracle(emu, port_oracle, bands):
     helpers.assert_frames_equal(got, want, "staged pipeline in %d bands" % bands)
 
 
+def test_fuzzed_scenes_as_warps_match_oracle(emu, port_oracle):
+    """scripts/fuzz_kernels_on_cpu.py over a bounded range of seeds: random triangle soups with shared edges, coplanar stacks (near ties
+    beyond what a ray keeps: the fix-up kernels), slivers, metal / glass / emitters, random cameras and ragged resolutions, through the direct
+    path (all reuse modes, 1-3 passes, staged / fused) and the three GI forms, every buffer bit for bit."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import fuzz_kernels_on_cpu as fz
+
+    ran, bad = fz.run(emu, port_oracle, 0, 400, verbose=False)
+    assert ran > 300 and bad == 0
+
+
 def edge_scenes():
     """tests/test_gpu_parity.py::test_edge_cases: ragged resolution, a single (emissive) triangle, no lights, a camera that sees nothing,
     an exactly axis-aligned centre ray, a camera looking straight down."""
