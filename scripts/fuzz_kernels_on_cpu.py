@@ -56,8 +56,11 @@ def soup(seed):
     eye = tuple(float(x) for x in r.uniform(-3, 3, 3))
     rot = (float(r.uniform(-180, 180)), float(r.uniform(-60, 60)), 0.0)
     W, H = int(r.integers(17, 49)), int(r.integers(9, 33))
-    return scenes.SceneData("soup%d" % seed, verts, scenes._face_normals(verts), np.zeros((3 * T, 2), np.float32), ids, mats, ["a", "b", "c", "d", "e"],
+    sd = scenes.SceneData("soup%d" % seed, verts, scenes._face_normals(verts), np.zeros((3 * T, 2), np.float32), ids, mats, ["a", "b", "c", "d", "e"],
                             eye=eye, rotation=rot, fovy=float(r.uniform(15, 40)), resolution=(W, H))
+    if seed % 5 == 4:
+        sd = scenes.with_textures(sd, env=bool(seed % 2))      # base-colour / metallic / roughness / normal maps, procedural pattern, environment-map light
+    return sd
 
 def run(e, orc, lo, hi, verbose=True):
     bad = 0; ran = 0; fixups = 0; lit = 0; t0 = time.time()
@@ -71,10 +74,28 @@ def run(e, orc, lo, hi, verbose=True):
         except Exception as ex:
             print(seed, "oracle rejected:", str(ex)[:80])
             continue
-        got, fix = e.run_di(sd, 2, reuse, passes=passes, light_index=True, pipeline=seed % 2)
-        m = {n: helpers.mismatches(got[f][n], want[f][n]) for f in range(2) for n in want[f] if helpers.mismatches(got[f][n], want[f][n])}
+        e.traced_build = (None, None, 0, 1)[seed % 4] if sd.num_tris >= 8 else None    # half of the scenes on a tree built by the device-side builders' kernels
+        try:
+            got, fix = e.run_di(sd, 2, reuse, passes=passes, light_index=True, pipeline=seed % 2, bands=1 + (seed // 2) % 3, drain=bool(seed % 3))
+            m = {n: helpers.mismatches(got[f][n], want[f][n]) for f in range(2) for n in want[f] if helpers.mismatches(got[f][n], want[f][n])}
+            if seed % 7 == 0 and sd.env_map < 0:                 # the unbiased mode (triangle lights only)
+                wu = helpers.run_oracle(orc, sd, 2, reuse, passes=passes, unbiased=True, light_index=True)
+                gu, _ = e.run_di(sd, 2, reuse, passes=passes, unbiased=True, light_index=True)
+                m.update({"unbiased " + n: helpers.mismatches(gu[f][n], wu[f][n]) for f in range(2) for n in wu[f] if helpers.mismatches(gu[f][n], wu[f][n])})
+            if seed % 6 == 0 and reuse == 3 and sd.resolution[1] >= 16:    # strips with random cuts (halo: radius 5 px + the motion of one orbit step)
+                H = sd.resolution[1]
+                cut = sorted(set([0, H] + [int(x) for x in np.random.default_rng(seed).integers(1, H, 2)]))
+                gs, miss = e.run_di_strips(sd, 2, tuple(cut), halo=H, reuse=3, radius=5.0, passes=passes)
+                m.update({"strips " + n: helpers.mismatches(gs[f][n], want[f][n]) for f in range(2) for n in gs[f] if helpers.mismatches(gs[f][n], want[f][n])})
+                if any(miss):
+                    m["halo_miss"] = miss
+        finally:
+            pass
         wg = helpers.run_oracle_gi(orc, sd, 2, 3, 1)
-        gg, _ = e.run_gi(sd, 2, 3, 1, staged=3 + seed % 3)
+        try:
+            gg, _ = e.run_gi(sd, 2, 3, 1, staged=3 + seed % 3)
+        finally:
+            e.traced_build = None
         mg = {n: helpers.mismatches(gg[f][n], wg[f][n]) for f in range(2) for n in wg[f] if helpers.mismatches(gg[f][n], wg[f][n])}
         fixups += fix > 0
         lit += bool((want[-1]["radiance"].sum(1) > 0).any())
