@@ -198,7 +198,9 @@ struct Hit { float t, bx, by; int prim; };
 // Traversal stack: the first RS_SMEM_STACK entries of every thread live in shared memory, laid out [entry][thread] so
 // that a lane always hits its own bank whatever its stack depth (divergent depths cost nothing); deeper entries
 // spill to a per-thread local array.
-#define RS_SMEM_STACK 24
+#ifndef RS_SMEM_STACK
+#define RS_SMEM_STACK 24       /* (tests/emu also builds with 4: every walk then spills, which exercises the local-array halves of the stacks) */
+#endif
 #define RS_BLOCK 128
 #ifndef RS_MINB_GBUF
 #define RS_MINB_GBUF 8      /* __launch_bounds__ minBlocks: 64 registers, 32 warps/SM (A/B on B200: -5 % vs uncapped 72) */

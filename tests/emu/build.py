@@ -12,14 +12,18 @@ DEPS = SOURCES + [os.path.join(HERE, "cuda_host_shim.h")] + [os.path.join(CSRC, 
                                                              ("kernels.cu", "gi_kernels.inl", "denoise.cu", "bvh_gpu.cu", "capi_internal.h", "kernels.h", "device_types.h", "vecmath.h", "camera_dev.h", "scene_host.h")]
 
 
-def build(force: bool = False, sanitize: str = "") -> str:
+def build(force: bool = False, sanitize: str = "", small_stack: bool = False) -> str:
     """sanitize = "address" / "thread": the same library instrumented by ASan / TSan (tests/test_kernels_under_sanitizers.py runs it in a
     child process with the sanitizer runtime preloaded): the memcheck / racecheck of the kernels' code that needs no GPU."""
     out = OUT if not sanitize else OUT.replace(".so", "_%s.so" % sanitize)
+    if small_stack:                              # RS_SMEM_STACK = 4: the per-lane stacks spill to their local arrays after four entries
+        out = out.replace(".so", "_stack4.so")
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in DEPS):
         return out
     os.makedirs(os.path.dirname(out), exist_ok=True)
     opt = ["-O2"] if not sanitize else ["-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=" + sanitize]
+    if small_stack:
+        opt.append("-DRS_SMEM_STACK=4")
     if sanitize == "thread":
         opt.append("-DEMU_STD_THREADS")          # libgomp's barriers are invisible to TSan: the warps run on std::threads instead
     cmd = ["/usr/bin/g++", "-std=c++17"] + opt + ["-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC", "-w", "-shared",

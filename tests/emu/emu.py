@@ -13,8 +13,8 @@ from restir_b200 import api  # noqa: E402   (RstrSceneDesc / RstrCamera structur
 
 
 class Emu:
-    def __init__(self, sanitize: str = ""):
-        L = self.lib = C.CDLL(_emu_build.build(sanitize=sanitize))
+    def __init__(self, sanitize: str = "", small_stack: bool = False):
+        L = self.lib = C.CDLL(_emu_build.build(sanitize=sanitize, small_stack=small_stack))
         vp, ip = C.c_void_p, C.c_int
         L.emu_scene_create.restype = vp
         L.emu_scene_create.argtypes = [C.POINTER(api.RstrSceneDesc)]

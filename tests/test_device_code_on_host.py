@@ -169,6 +169,29 @@ def test_fuzzed_scenes_as_warps_match_oracle(emu, port_oracle):
     assert ran > 300 and bad == 0
 
 
+def test_spilling_stacks_as_warps_match_oracle(port_oracle):
+    """The same kernels built with RS_SMEM_STACK = 4 instead of 24: every per-lane walk (reference-order walk, traceClosestFast /
+    traceOccludedFast, k_shadow and its cooperative drain, the GI walkers) runs past the shared-memory part of its stack into the
+    local-array part -- on the bench scenes only the deepest rays do -- and must report the same hits."""
+    from emu import Emu
+
+    e = Emu(small_stack=True)
+    sd = scenes.procedural(3, 20000, 1000, (96, 54))
+    want = helpers.run_oracle(port_oracle, sd, 2, 3, light_index=True)
+    for pipeline, drain in ((0, True), (0, False), (3, True)):
+        got, _ = e.run_di(sd, 2, 3, pipeline=pipeline, drain=drain, light_index=True)
+        helpers.assert_frames_equal(got, want, "RS_SMEM_STACK = 4, pipeline %d" % pipeline)
+    want_gi = helpers.run_oracle_gi(port_oracle, sd, 2, 4, 1)
+    for mode in (3, 4, 5):
+        got, _ = e.run_gi(sd, 2, 4, 1, staged=mode)
+        helpers.assert_frames_equal(got, want_gi, "RS_SMEM_STACK = 4, GI form %d" % mode)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import fuzz_kernels_on_cpu as fz
+
+    ran, bad = fz.run(e, port_oracle, 1000, 1150, verbose=False)
+    assert ran > 100 and bad == 0
+
+
 def edge_scenes():
     """tests/test_gpu_parity.py::test_edge_cases: ragged resolution, a single (emissive) triangle, no lights, a camera that sees nothing,
     an exactly axis-aligned centre ray, a camera looking straight down."""
