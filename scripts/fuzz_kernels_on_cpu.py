@@ -19,6 +19,9 @@ from emu import Emu
 from oracle import oracle as orc_mod
 from restir_b200 import scenes
 
+SCALE = 1.0
+
+
 def soup(seed):
     """random triangle soup: clustered + grid-snapped vertices (shared edges, coplanar and coincident-distance hits = near ties), slivers,
     random emitters / metals / glass, random camera"""
@@ -50,10 +53,12 @@ def soup(seed):
     if T < 9:
         return None
     verts = v.reshape(-1, 3)
+    scale = np.float32(SCALE)                    # --scale: the whole scene (and the camera) far from the unit scale the epsilons were chosen at
+    verts = (verts * scale).astype(np.float32)
     mats = scenes.make_materials([(scenes.LAMBERTIAN, (0.7, 0.6, 0.5), 0.0, 1.0), (scenes.METALLIC_WORKFLOW, (0.9, 0.8, 0.7), float(r.uniform(0, 1)), float(r.uniform(0.05, 1))),
                                   (scenes.DIELECTRIC, (0.95, 0.95, 1.0), 0.0, 0.0), (scenes.LIGHT, (8, 7, 6), 0.0, 1.0), (scenes.LIGHT, (2, 9, 3), 0.0, 1.0)])
     ids = r.choice(5, T, p=[0.45, 0.2, 0.1, 0.15, 0.1]).astype(np.int32)
-    eye = tuple(float(x) for x in r.uniform(-3, 3, 3))
+    eye = tuple(float(x) * float(scale) for x in r.uniform(-3, 3, 3))
     rot = (float(r.uniform(-180, 180)), float(r.uniform(-60, 60)), 0.0)
     W, H = int(r.integers(17, 49)), int(r.integers(9, 33))
     sd = scenes.SceneData("soup%d" % seed, verts, scenes._face_normals(verts), np.zeros((3 * T, 2), np.float32), ids, mats, ["a", "b", "c", "d", "e"],
@@ -97,6 +102,16 @@ def run(e, orc, lo, hi, verbose=True):
         finally:
             e.traced_build = None
         mg = {n: helpers.mismatches(gg[f][n], wg[f][n]) for f in range(2) for n in wg[f] if helpers.mismatches(gg[f][n], wg[f][n])}
+        if seed % 8 == 1:                                        # the image-space filters on the frames of this scene
+            import test_denoiser
+
+            kind = "svgf" if seed % 16 == 1 else "eaw"
+            wd = test_denoiser.oracle_frames(orc, sd, 3, kind, modulate=bool(seed % 3))
+            gd = e.run_denoiser(sd, 3, kind, modulate=bool(seed % 3))
+            for f in range(3):
+                for n in ("rgb", "var"):
+                    if wd[f][n] is not None and helpers.mismatches(gd[f][n], wd[f][n]):
+                        mg["denoiser %s %s f%d" % (kind, n, f)] = helpers.mismatches(gd[f][n], wd[f][n])
         fixups += fix > 0
         lit += bool((want[-1]["radiance"].sum(1) > 0).any())
         if m or mg:
@@ -108,4 +123,6 @@ def run(e, orc, lo, hi, verbose=True):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 3:
+        SCALE = float(sys.argv[3])
     run(Emu(), orc_mod.Oracle("port"), int(sys.argv[1]), int(sys.argv[2]))
