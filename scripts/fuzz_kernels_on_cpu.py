@@ -96,9 +96,10 @@ def run(e, orc, lo, hi, verbose=True):
                     m["halo_miss"] = miss
         finally:
             pass
-        wg = helpers.run_oracle_gi(orc, sd, 2, 3, 1)
+        gi_depth, gi_reuse = (3, 1) if seed % 3 else ((seed // 3) % 7, (seed // 21) % 2)     # a third of the scenes: trace depth 0..6, with / without history
+        wg = helpers.run_oracle_gi(orc, sd, 2, gi_depth, gi_reuse, accumulate=bool(seed % 2))
         try:
-            gg, _ = e.run_gi(sd, 2, 3, 1, staged=3 + seed % 3)
+            gg, _ = e.run_gi(sd, 2, gi_depth, gi_reuse, accumulate=bool(seed % 2), staged=3 + seed % 3)
         finally:
             e.traced_build = None
         mg = {n: helpers.mismatches(gg[f][n], wg[f][n]) for f in range(2) for n in wg[f] if helpers.mismatches(gg[f][n], wg[f][n])}
