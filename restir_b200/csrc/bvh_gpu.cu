@@ -41,13 +41,7 @@ __device__ __forceinline__ unsigned long long expandBits(unsigned int v) {      
     return x;
 }
 
-// (the first read of the CAS loops below is a plain load racing with other blocks' CAS: a stale value only costs one more iteration.
-//  ThreadSanitizer's build of tests/emu reads it atomically so that the report list stays empty for real findings.)
-#ifdef RS_HOST_EMU
-#define RS_PEEK(p) __atomic_load_n(p, __ATOMIC_RELAXED)
-#else
-#define RS_PEEK(p) (*(p))
-#endif
+// (RS_PEEK, device_types.h: the first read of the CAS loops below is a plain load racing with other blocks' CAS)
 __device__ __forceinline__ void atomicMinF(float* a, float v) {
     int* ai = (int*)a;
     int old = RS_PEEK(ai);

@@ -130,3 +130,12 @@ struct GIDev {
 };
 
 }  // namespace rs
+
+// A plain load that only decides whether an atomic is worth issuing (a running maximum, the first value of a CAS loop): racing with other
+// blocks' atomics is harmless -- a stale value costs one redundant atomic or one more CAS iteration.  The ThreadSanitizer build of tests/emu
+// reads it atomically so that its report list stays empty for real findings.
+#ifdef RS_HOST_EMU
+#define RS_PEEK(p) __atomic_load_n(p, __ATOMIC_RELAXED)
+#else
+#define RS_PEEK(p) (*(p))
+#endif

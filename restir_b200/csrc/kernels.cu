@@ -955,7 +955,7 @@ RS_D void gbufferFinish(const DevScene& s, const FrameDev& f, const CamDev& last
         int motion = (lx >= 0 && lx < f.W && ly >= 0 && ly < f.H) ? ly * f.W + lx : -1;
         if (motion >= 0) {                       // per-frame bound on the temporal halo: max |row' - row|
             unsigned int dy = (unsigned int)abs(ly - y);
-            if (dy > *f.motionRows) atomicMax(f.motionRows, dy);
+            if (dy > RS_PEEK(f.motionRows)) atomicMax(f.motionRows, dy);
         }
         f.geom[0][li] = make_float4(nrm.x, nrm.y, nrm.z, depth);
         f.matId[0][li] = matId;
@@ -1922,9 +1922,12 @@ RS_D long long spatialNeighbour(const FrameDev& f, int x, int y, size_t li, floa
 }
 RS_D UnbPoint unbPointOf(const DevScene& s, const FrameDev& f, size_t li) {
     const float4* q = (const float4*)(f.hit + li);
-    const float4 h0 = q[0], h1 = q[1], hp = f.hitPos[li];
+    const float4 h0 = q[0], hp = f.hitPos[li];
+    // wo as three words: the fourth word of that float4 is the pixel's RNG state, which its owner rewrites between spatial passes while
+    // neighbours read its wo (k_restir_b_unb, !last) -- a 16-byte load here would overlap that store
+    const float* w3 = (const float*)(q + 1);
     UnbPoint p;
-    p.pos = mk3(hp.x, hp.y, hp.z); p.nrm = mk3(h0.x, h0.y, h0.z); p.wo = mk3(h1.x, h1.y, h1.z);
+    p.pos = mk3(hp.x, hp.y, hp.z); p.nrm = mk3(h0.x, h0.y, h0.z); p.wo = mk3(w3[0], w3[1], w3[2]);
     const int matId = __float_as_int(h0.w);
     const RstrMaterial* m = s.materials + (matId < 0 ? 0 : matId);
     p.type = matId < 0 ? 2 : __ldg(&m->type);                          // a pixel phase A did not shade: target 0 everywhere
@@ -1990,7 +1993,7 @@ __global__ void __launch_bounds__(RS_BLOCK) k_restir_b_unb(const __grid_constant
     S.w = S.dist * phq * (float)S.M;                // consistent {wSum, W, M} for a later pass
     if (!last) {
         storeResv(dst + li, S);
-        hq[1] = make_float4(h1.x, h1.y, h1.z, __uint_as_float(rng.x));
+        ((float*)(hq + 1))[3] = __uint_as_float(rng.x);      // only the RNG word: neighbours are reading wo in the first three (unbPointOf)
         return;
     }
     if (src != f.resvTemp) storeResv(f.resvTemp + li, own);

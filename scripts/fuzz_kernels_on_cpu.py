@@ -3,7 +3,7 @@ faces, hits at equal distance = near ties; slivers; Lambertian / metal / glass /
 the kernels run as 32-lane warps on the CPU (tests/emu), every buffer of two frames compared bit for bit with the oracle: the direct path
 (RIS / temporal / spatial / spatiotemporal, 1-3 passes, staged and fused pipelines) and ReSTIR GI (ray queues / staged / one kernel).
 
-    python scripts/fuzz_kernels_on_cpu.py <first seed> <last seed>        # ~100 scenes per second
+    python scripts/fuzz_kernels_on_cpu.py <first seed> <last seed> [scale [address|thread|undefined|stack4]]       # ~100 scenes per second
 
 tests/test_device_code_on_host.py::test_fuzzed_scenes_as_warps_match_oracle runs a bounded range of seeds."""
 import os
@@ -126,4 +126,6 @@ def run(e, orc, lo, hi, verbose=True):
 if __name__ == "__main__":
     if len(sys.argv) > 3:
         SCALE = float(sys.argv[3])
-    run(Emu(), orc_mod.Oracle("port"), int(sys.argv[1]), int(sys.argv[2]))
+    variant = sys.argv[4] if len(sys.argv) > 4 else ""           # address / thread / undefined (run with the runtime in LD_PRELOAD, see
+    emu = Emu(small_stack=True) if variant == "stack4" else Emu(sanitize=variant)     # tests/test_kernels_under_sanitizers.py), or stack4
+    run(emu, orc_mod.Oracle("port"), int(sys.argv[1]), int(sys.argv[2]))

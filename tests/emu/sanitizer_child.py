@@ -28,7 +28,7 @@ def main():
     e.run_di(gen, 2, 3, pipeline=1)                                       # fused: k_gbuffer_restir_a
     e.run_di(gen, 2, 2, pipeline=2)                                       # split: k_gbuffer, k_restir_a
     e.run_di(glass, 2, 3, pipeline=3)                                     # reference-order kernels
-    e.run_di(gen, 2, 3, unbiased=True)                                    # k_temporal_unb, k_restir_b_unb
+    e.run_di(gen, 2, 3, unbiased=True, passes=2)                          # k_temporal_unb, k_restir_b_unb (two passes: a pixel's RNG word is rewritten between them while neighbours read its wo)
     e.run_di(gen, 2, 0, ptdirect=True, want=("radiance",))               # k_ptdirect
     for mode in (3, 4, 5):                                                # GI: ray queues, staged, one kernel
         e.run_gi(gen, 2, 3, 1, accumulate=True, staged=mode)
